@@ -1,0 +1,183 @@
+"""Generate the golden fixtures in this directory from the UNMODIFIED reference.
+
+Runs only in the build container (needs ``/root/reference``).  For every case:
+
+1. random-init backbones are built exactly like ``oracle.hf_oracle.build_backbones``
+   (``torch.manual_seed(seed)``, speech model first, text model second) and saved
+   as local checkpoints (there is no network / hub cache);
+2. the reference's own ``HFSpeechMixEED`` (``/root/reference/speechmix/hf_model.py``,
+   imported with an ``s3prl`` stub because that dependency is not installable
+   here) is constructed from those checkpoint directories and run on the
+   synthetic batch;
+3. the oracle restatement (``oracle/hf_oracle.py``) is run on the same weights and
+   MUST reproduce the reference bit-for-bit (asserted here);
+4. loss, argmax ids, a strided sample of the full-vocabulary logits and of the
+   encoder states, and selected gradient norms are written to ``<case>.json``.
+
+The fixtures are what pins the oracle on the GPU box, where ``/root/reference``
+does not exist:  ``tests/test_oracle_golden.py`` rebuilds the same seeded
+weights through the oracle and compares against these numbers.
+
+Usage:  python tests/golden/make_golden.py [case ...]
+"""
+import json
+import os
+import sys
+import tempfile
+import types
+
+os.environ.setdefault("TRANSFORMERS_OFFLINE", "1")
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from oracle import hf_oracle as O  # noqa: E402
+
+CASES = {
+    # name: (speech kind, speech model_type, text kind, ctor kwargs, batch, seconds, t_dec, ignore_tail, backward)
+    "mini_eed_ds2": ("mini", "wav2vec2", "bart-mini", dict(down_scale=2), 2, 1.0, 8, True, True),
+    "mini_eed_ds8_ws": ("mini", "wav2vec2", "bart-mini", dict(down_scale=8, weighted_sum=True), 2, 1.5, 8, False, True),
+    "mini_eed_share": ("mini", "wav2vec2", "bart-mini", dict(down_scale=4, share_layer_ratio=0.5), 1, 1.0, 6, False, False),
+    "mini_large_mbart": ("mini_large", "hubert", "mbart-mini", dict(down_scale=2), 2, 1.0, 8, False, True),
+    "mini_t5": ("mini", "wav2vec2", "t5-mini", dict(down_scale=2), 2, 1.0, 8, False, True),
+    "cfg1_base": ("base", "wav2vec2", "bart-base", dict(down_scale=2), 1, 5.0, 24, False, False),
+}
+
+
+def save_tokenizer(path, vocab_size):
+    from tokenizers import Tokenizer
+    from tokenizers.models import WordLevel
+    from tokenizers.pre_tokenizers import Whitespace
+    from transformers import PreTrainedTokenizerFast
+
+    vocab = {"<s>": 0, "<pad>": 1, "</s>": 2, "<unk>": 3}
+    for i in range(4, min(vocab_size, 64)):
+        vocab[f"w{i}"] = i
+    tok = Tokenizer(WordLevel(vocab, unk_token="<unk>"))
+    tok.pre_tokenizer = Whitespace()
+    PreTrainedTokenizerFast(tokenizer_object=tok, bos_token="<s>", eos_token="</s>",
+                            pad_token="<pad>", unk_token="<unk>").save_pretrained(path)
+
+
+def import_reference():
+    sys.modules.setdefault("s3prl", types.ModuleType("s3prl"))
+    sys.modules.setdefault("s3prl.hub", types.ModuleType("s3prl.hub"))
+    sys.path.insert(0, "/root/reference")
+    import speechmix  # noqa: F401
+
+    return speechmix
+
+
+def sample(t, n=64):
+    flat = t.detach().reshape(-1).double()
+    idx = torch.linspace(0, flat.numel() - 1, min(n, flat.numel())).long()
+    return {"idx": idx.tolist(), "val": flat[idx].tolist(), "sum": float(flat.sum()),
+            "abs_sum": float(flat.abs().sum()), "shape": list(t.shape)}
+
+
+def run_case(name):
+    sp_kind, sp_type, tx_kind, kw, B, secs, t_dec, ignore_tail, backward = CASES[name]
+    speechmix = import_reference()
+    sp_cfg = O.speech_config(sp_kind, model_type=sp_type)
+    tx_cfg = O.text_config(tx_kind)
+    speech, text = O.build_backbones(sp_cfg, tx_cfg, seed=0)
+    tmp = tempfile.mkdtemp(prefix="smx_golden_")
+    # the reference picks the encoder class from a substring of the path (ref :210-215)
+    sp_dir = os.path.join(tmp, "hubert" if sp_type == "hubert" else "wav2vec2")
+    tx_dir = os.path.join(tmp, "text")
+    speech.save_pretrained(sp_dir)
+    text.save_pretrained(tx_dir)
+    save_tokenizer(tx_dir, tx_cfg.vocab_size)
+
+    ref = speechmix.HFSpeechMixEED(sp_dir, tx_dir, **kw)
+    O.reinit_glue(ref, seed=1)  # glue parameters: deterministic re-draw (see oracle.reinit_glue)
+    ref.train(False) if not backward else ref.train(True)
+
+    # oracle restatement on the same weights
+    speech2, text2 = O.build_backbones(sp_cfg, tx_cfg, seed=0)
+    ora = O.OracleEED(speech2, text2, **kw)
+    O.reinit_glue(ora, seed=1)
+    for (ka, va), (kb, vb) in zip(sorted(ref.state_dict().items()), sorted(ora.state_dict().items())):
+        assert ka == kb and torch.equal(va, vb), (ka, kb)  # seeded rebuild == saved checkpoints
+    ora.train(ref.training)
+
+    x, labels = O.synthetic_batch(B, secs, t_dec, tx_cfg.vocab_size, seed=0, ignore_tail=ignore_tail)
+
+    # capture the reference's full-vocabulary logits through a hook on decoder_model
+    cap = {}
+    h = ref.decoder_model.register_forward_hook(lambda m, i, o: cap.__setitem__("logits", o.logits.detach().clone()))
+    h2 = ref.encoder_model.register_forward_hook(lambda m, i, o: cap.__setitem__("speech", o.last_hidden_state.detach().clone()))
+    out_ref = ref(x, labels=labels)
+    h.remove(); h2.remove()
+    out_ora = ora(x, labels=labels, keep_full_logits=True)
+
+    assert torch.equal(out_ref["loss"], out_ora["loss"]), (out_ref["loss"], out_ora["loss"])
+    assert torch.equal(out_ref["logits"], out_ora["logits"])
+    assert torch.equal(cap["logits"], out_ora["full_logits"])
+    assert torch.equal(cap["speech"], out_ora["speech_last_hidden_state"])
+    assert torch.equal(out_ref["encoder_last_hidden_state"], out_ora["encoder_last_hidden_state"])
+
+    fixture = {
+        "case": name, "speech": sp_kind, "speech_type": sp_type, "text": tx_kind, "kwargs": kw,
+        "batch": B, "seconds": secs, "t_dec": t_dec, "ignore_tail": ignore_tail,
+        "train_mode": bool(ref.training),
+        "transformers": __import__("transformers").__version__, "torch": torch.__version__,
+        "n_params": sum(p.numel() for p in ref.parameters()),
+        "n_state_keys": len(ref.state_dict()),
+        "list_no_grad": len(ref.list_no_grad),
+        "speech_encoder_layer": ref.speech_encoder_layer,
+        "nlp_encoder_layer": ref.nlp_encoder_layer,
+        "loss": float(out_ref["loss"]),
+        "argmax_ids": out_ref["logits"].tolist(),
+        "logits": sample(cap["logits"]),
+        "speech_last_hidden_state": sample(cap["speech"]),
+        "encoder_last_hidden_state": sample(out_ref["encoder_last_hidden_state"]),
+    }
+    if backward:
+        out_ref["loss"].backward()
+        out_ora["loss"].backward()
+        grads = {}
+        pr, po = dict(ref.named_parameters()), dict(ora.named_parameters())
+        picks = ["enc_to_dec_proj.weight", "length_adapters.0.weight",
+                 "encoder_model.feature_extractor.conv_layers.0.conv.weight",
+                 "encoder_model.feature_extractor.conv_layers.1.conv.weight",
+                 "encoder_model.encoder.layers.0.attention.q_proj.weight",
+                 "encoder_model.encoder.layers.1.feed_forward.output_dense.bias",
+                 "encoder_model.encoder.pos_conv_embed.conv.parametrizations.weight.original1",
+                 "encoder_model.feature_projection.projection.weight"]
+        for k in pr:
+            if k.startswith("decoder_model") and ("shared" in k or "layers.0.fc1.weight" in k
+                                                  or "block.0.layer.0.SelfAttention.q.weight" in k):
+                picks.append(k)
+        if "weights_sum" in pr:
+            picks.append("weights_sum")
+        for k in picks:
+            if k in pr and pr[k].grad is not None:
+                assert torch.equal(pr[k].grad, po[k].grad), k
+                grads[k] = {"norm": float(pr[k].grad.double().norm()), **sample(pr[k].grad, 16)}
+        fixture["grads"] = grads
+
+    # greedy decode the way eval.ipynb does, on the reference forward itself
+    if name.startswith("mini") and not backward:
+        ref.eval(); ora.eval()
+        start = ref.decoder_model.config.decoder_start_token_id
+        dec = torch.full((B, 1), start, dtype=torch.long)
+        with torch.no_grad():
+            for _ in range(7):
+                ids = ref(x, decoder_input_ids=dec)["logits"]
+                dec = torch.cat([dec, ids[:, -1:]], 1)
+        g2 = O.greedy_full_recompute(ora, x, max_length=8, eos_token_id=-1)
+        assert torch.equal(dec, g2), (dec, g2)
+        fixture["greedy_ids"] = dec.tolist()
+
+    path = os.path.join(HERE, name + ".json")
+    with open(path, "w") as f:
+        json.dump(fixture, f, indent=1)
+    print("wrote", path, "loss", fixture["loss"])
+
+
+if __name__ == "__main__":
+    for c in (sys.argv[1:] or list(CASES)):
+        run_case(c)

@@ -1,0 +1,75 @@
+"""The oracle (oracle/hf_oracle.py) against the golden fixtures produced by the
+unmodified reference (tests/golden/make_golden.py).  CPU only.
+
+The fixtures were generated bit-exactly; here a small tolerance absorbs
+different CPU kernels (MKL/oneDNN thread counts) on other hosts."""
+import pytest
+import torch
+
+from tests._cases import build_oracle, check_sample, load_fixture
+
+MINI = ["mini_eed_ds2", "mini_eed_ds8_ws", "mini_eed_share", "mini_large_mbart", "mini_t5"]
+
+
+@pytest.mark.parametrize("name", MINI)
+def test_oracle_matches_reference_golden(name):
+    fx = load_fixture(name)
+    model, x, labels = build_oracle(fx)
+    assert sum(p.numel() for p in model.parameters()) == fx["n_params"]
+    assert len(model.state_dict()) == fx["n_state_keys"]
+    assert len(model.list_no_grad) == fx["list_no_grad"]
+    assert model.speech_encoder_layer == fx["speech_encoder_layer"]
+    assert model.nlp_encoder_layer == fx["nlp_encoder_layer"]
+    out = model(x, labels=labels, keep_full_logits=True)
+    assert abs(float(out["loss"]) - fx["loss"]) < 2e-5
+    assert out["logits"].tolist() == fx["argmax_ids"]
+    check_sample(out["full_logits"], fx["logits"], atol=2e-4)
+    check_sample(out["speech_last_hidden_state"], fx["speech_last_hidden_state"], atol=2e-4)
+    check_sample(out["encoder_last_hidden_state"], fx["encoder_last_hidden_state"], atol=2e-4)
+    if "grads" in fx:
+        out["loss"].backward()
+        params = dict(model.named_parameters())
+        for k, rec in fx["grads"].items():
+            g = params[k].grad
+            assert abs(float(g.double().norm()) - rec["norm"]) <= 1e-3 * rec["norm"] + 1e-7, k
+            check_sample(g, rec, atol=1e-5, rtol=1e-3)
+
+
+def test_oracle_greedy_matches_reference_loop():
+    from oracle import hf_oracle as O
+
+    fx = load_fixture("mini_eed_share")
+    model, x, _ = build_oracle(fx)
+    model.eval()
+    ids = O.greedy_full_recompute(model, x, max_length=8, eos_token_id=-1)
+    assert ids.tolist() == fx["greedy_ids"]
+
+
+def test_structural_asserts_of_reference_tests():
+    """ref:test/test_hf_model.py:18-57 restated offline on mini backbones."""
+    from oracle import hf_oracle as O
+
+    for ratio, kept in [(1, 0), (0.5, 1), (0, 2)]:
+        sp, tx = O.build_backbones(O.speech_config("mini"), O.text_config("bart-mini"))
+        m = O.OracleEED(sp, tx, share_layer_ratio=ratio, down_scale=8)
+        assert m.speech_encoder_layer == kept and m.nlp_encoder_layer == 2
+        assert len(m.list_no_grad) == 0
+    x, labels = O.synthetic_batch(1, 1.0, 4, 1000)
+    for ds in (1, 2, 4, 8):
+        sp, tx = O.build_backbones(O.speech_config("mini"), O.text_config("bart-mini"))
+        m = O.OracleEED(sp, tx, share_layer_ratio=0.5, down_scale=ds, weighted_sum=True).eval()
+        d = m(x, labels=labels)["detail"]
+        assert round(d["shape_before_length_adapter"][1] / d["shape_before_enc_dec_projector"][1]) == ds
+        assert d["weighted_sum"].shape[0] == 2  # L_kept + 1
+
+
+@pytest.mark.slow
+def test_oracle_cfg1_full_size():
+    fx = load_fixture("cfg1_base")
+    model, x, labels = build_oracle(fx)
+    assert sum(p.numel() for p in model.parameters()) == fx["n_params"]
+    with torch.no_grad():
+        out = model(x, labels=labels, keep_full_logits=True)
+    assert abs(float(out["loss"]) - fx["loss"]) < 5e-5
+    assert out["logits"].tolist() == fx["argmax_ids"]
+    check_sample(out["full_logits"], fx["logits"], atol=5e-4)
