@@ -1,0 +1,235 @@
+/* libspeechmix_sm100.so -- C ABI of the B200-native SpeechMix hot path.
+ *
+ * The reference (voidful/SpeechMix) has no FFI of its own: its hot path is
+ * Python glue (ref:speechmix/hf_model.py:185-447) over `transformers` modules.
+ * The drop-in seam is therefore the Python class API (speechmix_b200.SpeechMixEED
+ * etc.); THIS header is the boundary between that Python host layer and the
+ * hand-written sm_100a kernels.  Every entry point names the reference /
+ * transformers code whose arithmetic it replaces.
+ *
+ * Conventions
+ *  - plain C: raw device pointers, sizes, a cudaStream_t passed as void*.
+ *  - pointers are BORROWED; the library never allocates or frees device memory
+ *    and keeps no global state besides lazily-set kernel attributes.
+ *  - every call only ENQUEUES work on the given stream (no host sync) and is
+ *    CUDA-graph capturable.
+ *  - return 0 on success, negative on error; smx_last_error() gives the message
+ *    (thread-local).
+ *  - activations: bf16, row-major, channels-last ([batch][time][channel]);
+ *    statistics / losses / master gradients: fp32; token ids: int64.
+ */
+#ifndef SPEECHMIX_SM100_H_
+#define SPEECHMIX_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMX_ABI_VERSION 1
+
+const char* smx_last_error(void);
+int smx_abi_version(void);
+/* 1 if the current device is sm_100 (B200), 0 otherwise, <0 on CUDA error. */
+int smx_device_ok(void);
+
+/* ------------------------------------------------------------------------
+ * Tensor-core GEMM family (tcgen05.mma + TMEM accumulators, TMA-fed).
+ *
+ * A bf16 operand is a 3-D view  [batches][rows][inner]  with `inner`
+ * contiguous; strides are in ELEMENTS and must be multiples of 8.
+ * ------------------------------------------------------------------------ */
+typedef struct SmxView3 {
+  const void* ptr;
+  int64_t inner, rows, batches;
+  int64_t row_stride, batch_stride;
+} SmxView3;
+
+#define SMX_MAX_SEG 4
+
+enum { SMX_GEMM_NT = 0, SMX_GEMM_NN = 1, SMX_GEMM_TN = 2 };
+enum { SMX_ACT_NONE = 0, SMX_ACT_GELU = 1, SMX_ACT_RELU = 2, SMX_ACT_DGELU = 3, SMX_ACT_DRELU = 4 };
+enum { SMX_OUT_BF16 = 0, SMX_OUT_F32 = 1 };
+
+/* One descriptor covers every contraction on the path:
+ *
+ *  NT  C[b,r,n] = sum_k A[b, r+a_row_off[s], a_col_off[s]+kin] * B[n, b_col_off[s]+kin]
+ *      (k = s*seg_len + kin).  Linear layers (hf:models/wav2vec2/modeling_wav2vec2.py:466-573,
+ *      hf:models/bart/modeling_bart.py:143-391) use one segment; the strided
+ *      Conv1d layers of the feature encoder (hf:...wav2vec2.py:254-323) and the
+ *      k=2,s=2 length adapters (ref:speechmix/hf_model.py:253-266) use one
+ *      segment per tap over a frame-pair view of the channels-last input, so the
+ *      convolution runs as an implicit GEMM with no im2col buffer.
+ *  NN  C[b,r,n] = sum_k A[b, r+a_row_off[s], a_col_off[s]+kin] * B[b_row_off[s]+kin, b_col_off[s]+n]
+ *      (data gradients: B is the forward weight read MN-major, no transpose copy).
+ *  TN  C[m,n]  (+)= sum_{b,r} A[b, r+a_row_off[0], a_col_off[0]+m] * B[b, r+b_row_off[s], b_col_off[s]+nin]
+ *      (n = s*seg_len + nin; weight gradients, contraction over rows, fp32 output,
+ *       optional split over the contraction with atomic accumulation).
+ *
+ * Epilogue (NT/NN):  v = alpha*acc (+bias[n]);  aux_out <- v (optional);
+ *   v = act(v) | v*gelu'(aux_in) | v*[aux_in>0];  v += residual;  C <- v.
+ */
+typedef struct SmxGemm {
+  int32_t mode;
+  int32_t out_dtype;    /* SMX_OUT_* (TN: always fp32) */
+  SmxView3 a, b;
+  int64_t m;            /* NT/NN: output rows per batch.  TN: output rows (= extent of A.inner used) */
+  int64_t n;            /* output columns */
+  int64_t k;            /* NT/NN: contraction length (= nseg*seg_len).  TN: contraction rows per batch */
+  int64_t batches;
+  int32_t nseg;
+  int32_t seg_len;
+  int32_t a_row_off[SMX_MAX_SEG], a_col_off[SMX_MAX_SEG];
+  int32_t b_row_off[SMX_MAX_SEG], b_col_off[SMX_MAX_SEG];
+  void* c;
+  int64_t c_row_stride, c_batch_stride; /* elements */
+  int32_t act;
+  int32_t split_k;      /* TN only; >1 => atomic fp32 accumulation into a zeroed or live C */
+  int32_t accumulate;   /* TN only; 1 => add into C even when split_k == 1 */
+  float alpha;
+  const float* bias;    /* [n] fp32 or NULL */
+  const void* residual; /* bf16, same shape/strides as C, or NULL */
+  int64_t res_row_stride, res_batch_stride;
+  void* aux_out;        /* bf16 pre-activation copy, C's strides, or NULL */
+  const void* aux_in;   /* bf16 pre-activation for DGELU/DRELU, C's strides */
+} SmxGemm;
+
+int smx_gemm(const SmxGemm* g, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Row-wise kernels (HBM-bound)
+ * ------------------------------------------------------------------------ */
+/* y = LayerNorm(x (+ res)) * gamma + beta over the last dim (cols), eps as
+ * given; optionally also writes sum = x + res (bf16) and per-row mean / rstd.
+ * hf:...wav2vec2.py:422-434 (feature projection), :576-655 (encoder layers),
+ * hf:...bart.py:261-391.  rms_only=1 gives T5 RMSNorm (hf:models/t5/modeling_t5.py:46-69). */
+int smx_layernorm_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* y,
+                      void* sum_out, float* mean, float* rstd, int64_t rows, int64_t cols, float eps,
+                      int rms_only, void* stream);
+/* dx (+= dres_in) for the op above; dgamma/dbeta are ACCUMULATED (fp32 atomics)
+ * into zero-initialised buffers. */
+int smx_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                      const void* dres_in, void* dx, float* dgamma, float* dbeta, int64_t rows, int64_t cols,
+                      int rms_only, void* stream);
+
+/* out[n] (+)= sum_r x[r, n]   (bias gradients). fp32 accumulate via atomics into a zeroed buffer. */
+int smx_colsum(const void* x, float* out, int64_t rows, int64_t cols, int64_t row_stride, void* stream);
+
+/* elementwise helpers */
+int smx_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+int smx_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
+int smx_act_bf16(const void* x, void* y, int64_t n, int act, void* stream);
+/* dst[o, t*cin + c] = src[o, c, t] : Conv1d weight [out][in][k] -> packed [out][k*in] bf16 */
+int smx_pack_conv_weight(const float* src, void* dst, int64_t cout, int64_t cin, int64_t k, void* stream);
+/* inverse of the above for fp32 gradients: dst[o, c, t] = src[o, t*cin + c] */
+int smx_unpack_conv_wgrad(const float* src, float* dst, int64_t cout, int64_t cin, int64_t k, void* stream);
+
+/* ------------------------------------------------------------------------
+ * conv0 of the feature encoder: Conv1d(1->C,k,s, no bias) + GroupNorm(C groups)
+ * + GELU, fused; the un-normalised conv output never exists in HBM.
+ * hf:...wav2vec2.py:302-323 (Wav2Vec2GroupNormConvLayer).
+ * ------------------------------------------------------------------------ */
+/* stats[b][c] = {mean, rstd} of the conv output over time, from the raw audio's
+ * window moments (exact algebra, one pass over the waveform). */
+int smx_conv0_stats(const float* audio, const float* w, float* moments, float* stats, int64_t batch,
+                    int64_t n_samples, int64_t t_out, int channels, int ksize, int stride, float eps,
+                    void* stream);
+int smx_conv0_gn_gelu_fwd(const float* audio, const float* w, const float* gamma, const float* beta,
+                          const float* stats, void* y, int64_t batch, int64_t n_samples, int64_t t_out,
+                          int channels, int ksize, int stride, void* stream);
+/* one pass over dy: partial[b][c][k+2] = {sum dz, sum dz*xhat, sum_t dz*x[s*t+j], j<k} */
+int smx_conv0_gn_gelu_bwd(const float* audio, const float* w, const float* gamma, const float* beta,
+                          const float* stats, const void* dy, float* partial, int64_t batch,
+                          int64_t n_samples, int64_t t_out, int channels, int ksize, int stride,
+                          void* stream);
+
+/* ------------------------------------------------------------------------
+ * Positional conv embedding: grouped Conv1d(H->H, k=128, pad=64, groups=16),
+ * drop last frame, GELU.  hf:...wav2vec2.py:326-379.  Tensor-core implicit
+ * GEMM over shifted windows of one smem-resident input slab.
+ * w_packed: [groups][k][cg_out][cg_in] bf16.  y may carry the fused residual:
+ * y = x + gelu(conv(x) + bias)   when add_input != 0.
+ * ------------------------------------------------------------------------ */
+int smx_posconv_fwd(const void* x, const void* w_packed, const float* bias, void* y, void* pre_out,
+                    int64_t batch, int64_t t, int hidden, int groups, int ksize, int add_input, void* stream);
+/* dx_conv = conv^T(dpre) with w_packed_t = taps flipped, in/out swapped */
+int smx_posconv_dgrad(const void* dpre, const void* w_packed_t, void* dx, int64_t batch, int64_t t, int hidden,
+                      int groups, int ksize, void* stream);
+/* dw[g][k][o][c] (fp32, zero-initialised) += sum_{b,t} dpre[b,t,g*cg+o] * x[b,t+k-pad,g*cg+c] */
+int smx_posconv_wgrad(const void* dpre, const void* x, float* dw, int64_t batch, int64_t t, int hidden,
+                      int groups, int ksize, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Attention (head_dim 64), flash-style: scores never reach HBM.
+ * q/k/v/o are bf16 views [batch][time][heads*64] with arbitrary row strides
+ * (so a fused QKV buffer can be addressed in place).
+ * hf:...wav2vec2.py:438-549, hf:...bart.py:143-258, hf:models/t5/modeling_t5.py:153-345.
+ * causal: 0/1.  scale: multiplies q.k (T5: 1.0).  bias: optional additive
+ * [heads][tq][tk] fp32 (T5 relative position bias) or NULL.
+ * lse: [batch][heads][tq] fp32 (natural log), written by fwd, read by bwd.
+ * ------------------------------------------------------------------------ */
+typedef struct SmxAttn {
+  const void *q, *k, *v;
+  void* o;
+  float* lse;
+  int64_t q_row_stride, k_row_stride, v_row_stride, o_row_stride;       /* elements */
+  int64_t q_batch_stride, k_batch_stride, v_batch_stride, o_batch_stride;
+  int32_t batch, heads, tq, tk, causal;
+  float scale;
+  const float* bias;
+  /* backward only */
+  const void* d_o;
+  void *dq, *dk, *dv;
+  float* delta; /* [batch][heads][tq] workspace: rowsum(dO * O) */
+  float* dbias; /* optional [heads][tq][tk] fp32, accumulated */
+  int64_t do_row_stride, do_batch_stride;
+  int64_t dq_row_stride, dk_row_stride, dv_row_stride;
+  int64_t dq_batch_stride, dk_batch_stride, dv_batch_stride;
+} SmxAttn;
+int smx_attn_fwd(const SmxAttn* a, void* stream);
+int smx_attn_bwd(const SmxAttn* a, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Decoder input embedding: tok_emb[id]*scale + pos_emb[t + offset]  (bf16 out)
+ * hf:...bart.py:74-111, :620-640.  bwd scatters fp32 into the tied table grad.
+ * ------------------------------------------------------------------------ */
+int smx_embed_fwd(const int64_t* ids, const float* tok_emb, const float* pos_emb, void* out, int64_t batch,
+                  int64_t t, int64_t dim, float scale, int64_t pos_offset, int64_t t_start, void* stream);
+int smx_embed_bwd(const int64_t* ids, const void* dout, float* d_tok_emb, float* d_pos_emb, int64_t batch,
+                  int64_t t, int64_t dim, float scale, int64_t pos_offset, void* stream);
+
+/* ------------------------------------------------------------------------
+ * LM head + cross-entropy without materialising [rows, vocab] logits.
+ * hf:...bart.py:940-947 ; ref:speechmix/hf_model.py:446 (argmax).
+ * fwd: per row online logsumexp, label logit, argmax (lowest index wins ties)
+ *      over vocab tiles of  h . E^T * logit_scale + bias.
+ * partial: workspace of smx_lmhead_ws_bytes(rows, vocab) bytes.
+ * loss_sum[0] += sum of per-row NLL over labels != ignore_index; count[0] += #rows counted.
+ * ------------------------------------------------------------------------ */
+size_t smx_lmhead_ws_bytes(int64_t rows, int64_t vocab);
+int smx_lmhead_ce_fwd(const void* h, const void* emb, const float* bias, const int64_t* labels, float* lse,
+                      int64_t* argmax, float* row_loss, float* loss_sum, float* count, void* workspace,
+                      int64_t rows, int64_t dim, int64_t vocab, float logit_scale, int64_t ignore_index,
+                      void* stream);
+/* dlogits chunk [rows][v0:v0+vn) = (softmax - onehot(label)) * coef[row]  as bf16, for the
+ * chunked backward (the chunk stays L2-resident between the two GEMMs that consume it). */
+int smx_lmhead_dlogits(const void* h, const void* emb, const float* bias, const int64_t* labels,
+                       const float* lse, const float* grad_scale, void* dlogits, int64_t rows, int64_t dim,
+                       int64_t vocab, int64_t v0, int64_t vn, float logit_scale, int64_t ignore_index,
+                       void* stream);
+
+/* ------------------------------------------------------------------------
+ * Weighted layer sum (ref:speechmix/hf_model.py:411-423): out = sum_l w[l]*x_l
+ * ------------------------------------------------------------------------ */
+int smx_weighted_sum_fwd(const void* const* xs, const float* w, void* out, int n_layers, int64_t n,
+                         void* stream);
+/* dw[l] += sum(dout * x_l) */
+int smx_weighted_sum_bwd_w(const void* const* xs, const void* dout, float* dw, int n_layers, int64_t n,
+                           void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPEECHMIX_SM100_H_ */

@@ -1,0 +1,112 @@
+"""ctypes binding of libspeechmix_sm100.so (see include/speechmix_sm100.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call
+fails, a ``RuntimeError`` is raised.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libspeechmix_sm100.so")
+SMX_MAX_SEG = 4
+
+GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_DGELU, ACT_DRELU = 0, 1, 2, 3, 4
+OUT_BF16, OUT_F32 = 0, 1
+
+
+class SmxView3(Structure):
+    _fields_ = [("ptr", c_void_p), ("inner", c_int64), ("rows", c_int64), ("batches", c_int64),
+                ("row_stride", c_int64), ("batch_stride", c_int64)]
+
+
+class SmxGemm(Structure):
+    _fields_ = [("mode", c_int32), ("out_dtype", c_int32), ("a", SmxView3), ("b", SmxView3),
+                ("m", c_int64), ("n", c_int64), ("k", c_int64), ("batches", c_int64),
+                ("nseg", c_int32), ("seg_len", c_int32),
+                ("a_row_off", c_int32 * SMX_MAX_SEG), ("a_col_off", c_int32 * SMX_MAX_SEG),
+                ("b_row_off", c_int32 * SMX_MAX_SEG), ("b_col_off", c_int32 * SMX_MAX_SEG),
+                ("c", c_void_p), ("c_row_stride", c_int64), ("c_batch_stride", c_int64),
+                ("act", c_int32), ("split_k", c_int32), ("accumulate", c_int32), ("alpha", c_float),
+                ("bias", c_void_p), ("residual", c_void_p),
+                ("res_row_stride", c_int64), ("res_batch_stride", c_int64),
+                ("aux_out", c_void_p), ("aux_in", c_void_p)]
+
+
+class SmxAttn(Structure):
+    _fields_ = [("q", c_void_p), ("k", c_void_p), ("v", c_void_p), ("o", c_void_p), ("lse", c_void_p),
+                ("q_row_stride", c_int64), ("k_row_stride", c_int64), ("v_row_stride", c_int64),
+                ("o_row_stride", c_int64),
+                ("q_batch_stride", c_int64), ("k_batch_stride", c_int64), ("v_batch_stride", c_int64),
+                ("o_batch_stride", c_int64),
+                ("batch", c_int32), ("heads", c_int32), ("tq", c_int32), ("tk", c_int32), ("causal", c_int32),
+                ("scale", c_float), ("bias", c_void_p),
+                ("d_o", c_void_p), ("dq", c_void_p), ("dk", c_void_p), ("dv", c_void_p),
+                ("delta", c_void_p), ("dbias", c_void_p),
+                ("do_row_stride", c_int64), ("do_batch_stride", c_int64),
+                ("dq_row_stride", c_int64), ("dk_row_stride", c_int64), ("dv_row_stride", c_int64),
+                ("dq_batch_stride", c_int64), ("dk_batch_stride", c_int64), ("dv_batch_stride", c_int64)]
+
+
+_P = c_void_p
+_I64 = c_int64
+
+# name -> (restype, argtypes); mirrors include/speechmix_sm100.h one to one
+SIGNATURES = {
+    "smx_last_error": (c_char_p, []),
+    "smx_abi_version": (c_int, []),
+    "smx_device_ok": (c_int, []),
+    "smx_gemm": (c_int, [POINTER(SmxGemm), _P]),
+    "smx_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, c_float, c_int, _P]),
+    "smx_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, c_int, _P]),
+    "smx_colsum": (c_int, [_P, _P, _I64, _I64, _I64, _P]),
+    "smx_cast_f32_to_bf16": (c_int, [_P, _P, _I64, _P]),
+    "smx_add_bf16": (c_int, [_P, _P, _P, _I64, _P]),
+    "smx_act_bf16": (c_int, [_P, _P, _I64, c_int, _P]),
+    "smx_pack_conv_weight": (c_int, [_P, _P, _I64, _I64, _I64, _P]),
+    "smx_unpack_conv_wgrad": (c_int, [_P, _P, _I64, _I64, _I64, _P]),
+    "smx_conv0_stats": (c_int, [_P, _P, _P, _P, _I64, _I64, _I64, c_int, c_int, c_int, c_float, _P]),
+    "smx_conv0_gn_gelu_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, c_int, c_int, c_int, _P]),
+    "smx_conv0_gn_gelu_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, c_int, c_int, c_int, _P]),
+    "smx_posconv_fwd": (c_int, [_P, _P, _P, _P, _P, _I64, _I64, c_int, c_int, c_int, c_int, _P]),
+    "smx_posconv_dgrad": (c_int, [_P, _P, _P, _I64, _I64, c_int, c_int, c_int, _P]),
+    "smx_posconv_wgrad": (c_int, [_P, _P, _P, _I64, _I64, c_int, c_int, c_int, _P]),
+    "smx_attn_fwd": (c_int, [POINTER(SmxAttn), _P]),
+    "smx_attn_bwd": (c_int, [POINTER(SmxAttn), _P]),
+    "smx_embed_fwd": (c_int, [_P, _P, _P, _P, _I64, _I64, _I64, c_float, _I64, _I64, _P]),
+    "smx_embed_bwd": (c_int, [_P, _P, _P, _P, _I64, _I64, _I64, c_float, _I64, _P]),
+    "smx_lmhead_ws_bytes": (c_size_t, [_I64, _I64]),
+    "smx_lmhead_ce_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, c_float, _I64, _P]),
+    "smx_lmhead_dlogits": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, c_float, _I64, _P]),
+    "smx_weighted_sum_fwd": (c_int, [_P, _P, _P, c_int, _I64, _P]),
+    "smx_weighted_sum_bwd_w": (c_int, [_P, _P, _P, c_int, _I64, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libspeechmix_sm100.so is missing (%s). Build it with `python -m speechmix_b200.build`; "
+            "there is no CPU or PyTorch fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.smx_abi_version() != 1:
+        raise RuntimeError("libspeechmix_sm100.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().smx_last_error()
+        raise RuntimeError("libspeechmix_sm100 %s failed: %s" % (what, msg.decode() if msg else "?"))

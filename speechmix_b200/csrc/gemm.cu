@@ -1,0 +1,488 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:
+//   warp 0     : TMA producer (one thread) -> 4-stage smem ring
+//   warp 1     : tcgen05.mma issuer (one thread), accumulators in TMEM (2 x 256 columns,
+//                so the epilogue of tile i overlaps the MMAs of tile i+1)
+//   warps 2..5 : epilogue, TMEM -> registers -> fused bias/activation/residual -> HBM
+// Tile 128 x 256 x 64, 128-byte swizzled operands, K-major or MN-major via the
+// shared-memory descriptors (no transpose copies for dgrad / wgrad).
+//
+// Modes (see include/speechmix_sm100.h): NT forward (+ implicit-GEMM conv taps),
+// NN data gradient, TN weight gradient (fp32 out, split-K with atomics).
+#include "../../include/speechmix_sm100.h"
+#include "host_common.h"
+#include "sm100_prims.cuh"
+
+#include <string.h>
+
+namespace smx {
+
+namespace gemm {
+
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;  // 16 KiB
+constexpr int B_BYTES = BN * BK * 2;  // 32 KiB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int PANEL_BYTES = 64 * BK * 2;  // one 64(MN) x 64(K) MN-major panel, 8 KiB
+constexpr int BAR_BYTES = 256;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+
+struct Params {
+  int mode, out_f32;
+  long long m, n;
+  int batches;
+  int kblocks, kb_per_batch;
+  int m_tiles_per_batch, m_tiles, n_tiles, split_k;
+  int nseg, seg_len;
+  int a_row_off[SMX_MAX_SEG], a_col_off[SMX_MAX_SEG];
+  int b_row_off[SMX_MAX_SEG], b_col_off[SMX_MAX_SEG];
+  int b_inner_oob;
+  void* c;
+  long long c_row_stride, c_batch_stride;
+  int act, atomic;
+  float alpha;
+  const float* bias;
+  const bf16* residual;
+  long long res_row_stride, res_batch_stride;
+  bf16* aux_out;
+  const bf16* aux_in;
+};
+
+struct TileCoord {
+  int m_blk, n_blk, split, kb_begin, kb_end;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const Params& p, int tile) {
+  TileCoord t;
+  t.m_blk = tile % p.m_tiles;
+  const int rest = tile / p.m_tiles;
+  t.n_blk = rest % p.n_tiles;
+  t.split = rest / p.n_tiles;
+  t.kb_begin = (int)(((long long)p.kblocks * t.split) / p.split_k);
+  t.kb_end = (int)(((long long)p.kblocks * (t.split + 1)) / p.split_k);
+  return t;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles * p.split_k;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        const int n0 = t.n_blk * BN;
+        int bidx = 0, r0 = 0, m0 = 0;
+        if (MODE == SMX_GEMM_TN) {
+          m0 = t.m_blk * BM;
+        } else {
+          bidx = t.m_blk / p.m_tiles_per_batch;
+          r0 = (t.m_blk % p.m_tiles_per_batch) * BM;
+        }
+        for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], STAGE_BYTES);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          if (MODE == SMX_GEMM_TN) {
+            const int cb = kb / p.kb_per_batch;
+            const int cr0 = (kb % p.kb_per_batch) * BK;
+#pragma unroll
+            for (int pn = 0; pn < BM / 64; ++pn)
+              tma_load_3d(sa + pn * PANEL_BYTES, &tma_a, &full[stage], p.a_col_off[0] + m0 + 64 * pn,
+                          cr0 + p.a_row_off[0], cb);
+#pragma unroll
+            for (int pn = 0; pn < BN / 64; ++pn) {
+              const int nn = n0 + 64 * pn;
+              int c0 = p.b_inner_oob, roff = 0;
+              if (nn < p.n) {
+                const int s = nn / p.seg_len;
+                c0 = p.b_col_off[s] + (nn - s * p.seg_len);
+                roff = p.b_row_off[s];
+              }
+              tma_load_3d(sb + pn * PANEL_BYTES, &tma_b, &full[stage], c0, cr0 + roff, cb);
+            }
+          } else {
+            const int k0 = kb * BK;
+            const int s = k0 / p.seg_len;
+            const int kin = k0 - s * p.seg_len;
+            tma_load_3d(sa, &tma_a, &full[stage], p.a_col_off[s] + kin, r0 + p.a_row_off[s], bidx);
+            if (MODE == SMX_GEMM_NT) {
+              tma_load_2d(sb, &tma_b, &full[stage], p.b_col_off[s] + kin, n0);
+            } else {
+#pragma unroll
+              for (int pn = 0; pn < BN / 64; ++pn)
+                tma_load_2d(sb + pn * PANEL_BYTES, &tma_b, &full[stage], p.b_col_off[s] + n0 + 64 * pn,
+                            p.b_row_off[s] + kin);
+            }
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr bool A_MN = (MODE == SMX_GEMM_TN);
+      constexpr bool B_MN = (MODE != SMX_GEMM_NT);
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      // K-major SW128: 8-row groups 1024 B apart, 16 K-elements = +32 B inside the swizzle atom.
+      // MN-major SW128: 64-wide panels LBO = 8 KiB apart, 8-row K groups 1024 B apart, 16 K = +2 KiB.
+      constexpr uint32_t a_lbo = A_MN ? PANEL_BYTES : 16, a_kstep = A_MN ? 2048 : 32;
+      constexpr uint32_t b_lbo = B_MN ? PANEL_BYTES : 16, b_kstep = B_MN ? 2048 : 32;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const uint32_t smem_base = smem_u32(smem);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t adesc = umma_smem_desc(sa + kk * a_kstep, a_lbo, 1024, kLayoutSW128);
+            const uint64_t bdesc = umma_smem_desc(sb + kk * b_kstep, b_lbo, 1024, kLayoutSW128);
+            umma_ss(d_tmem, adesc, bdesc, idesc, (kb > t.kb_begin || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row_in_tile = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool c_vec_ok = (p.c_row_stride % 8 == 0) && (p.c_batch_stride % 8 == 0) &&
+                          ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
+    const bool res_vec_ok = p.residual == nullptr ||
+                            ((p.res_row_stride % 8 == 0) && (p.res_batch_stride % 8 == 0) &&
+                             ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0));
+    const bool aux_vec_ok = ((p.aux_out == nullptr) || ((reinterpret_cast<uintptr_t>(p.aux_out) & 15) == 0)) &&
+                            ((p.aux_in == nullptr) || ((reinterpret_cast<uintptr_t>(p.aux_in) & 15) == 0));
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int n0 = t.n_blk * BN;
+      long long row, row_limit;
+      long long c_off, res_off = 0;
+      if (MODE == SMX_GEMM_TN) {
+        row = (long long)t.m_blk * BM + row_in_tile;
+        row_limit = p.m;
+        c_off = row * p.c_row_stride;
+      } else {
+        const int bidx = t.m_blk / p.m_tiles_per_batch;
+        row = (long long)(t.m_blk % p.m_tiles_per_batch) * BM + row_in_tile;
+        row_limit = p.m;
+        c_off = (long long)bidx * p.c_batch_stride + row * p.c_row_stride;
+        res_off = (long long)bidx * p.res_batch_stride + row * p.res_row_stride;
+      }
+      const bool row_ok = row < row_limit;
+
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after_sync();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.n) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld_x32(t_row + c * 32, v);
+        tmem_ld_wait();
+        if (row_ok) {
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = p.alpha * __uint_as_float(v[j]);
+        const bool full_chunk = (col0 + 32 <= p.n);
+
+        if (MODE == SMX_GEMM_TN) {
+          float* cp = reinterpret_cast<float*>(p.c) + c_off + col0;
+          if (p.atomic) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.n) atomicAdd(cp + j, f[j]);
+          } else if (full_chunk && (p.c_row_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(cp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.n) cp[j] = f[j];
+          }
+        } else {
+
+        if (p.bias) {
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+              f[j] += b4.x;
+              f[j + 1] += b4.y;
+              f[j + 2] += b4.z;
+              f[j + 3] += b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.n) f[j] += __ldg(p.bias + col0 + j);
+          }
+        }
+        const bool vec = full_chunk && c_vec_ok && res_vec_ok && aux_vec_ok;
+        if (p.aux_out) {
+          bf16* ap = p.aux_out + c_off + col0;
+          if (vec) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 u;
+              u.x = pack_bf16x2(f[j], f[j + 1]);
+              u.y = pack_bf16x2(f[j + 2], f[j + 3]);
+              u.z = pack_bf16x2(f[j + 4], f[j + 5]);
+              u.w = pack_bf16x2(f[j + 6], f[j + 7]);
+              *reinterpret_cast<uint4*>(ap + j) = u;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.n) ap[j] = __float2bfloat16(f[j]);
+          }
+        }
+        if (p.act == SMX_ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+        } else if (p.act == SMX_ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+        } else if (p.act == SMX_ACT_DGELU || p.act == SMX_ACT_DRELU) {
+          const bf16* xp = p.aux_in + c_off + col0;
+          float x[32];
+          if (vec) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 u = __ldg(reinterpret_cast<const uint4*>(xp + j));
+              x[j] = bf16_lo(u.x), x[j + 1] = bf16_hi(u.x);
+              x[j + 2] = bf16_lo(u.y), x[j + 3] = bf16_hi(u.y);
+              x[j + 4] = bf16_lo(u.z), x[j + 5] = bf16_hi(u.z);
+              x[j + 6] = bf16_lo(u.w), x[j + 7] = bf16_hi(u.w);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = (col0 + j < p.n) ? __bfloat162float(xp[j]) : 0.0f;
+          }
+          if (p.act == SMX_ACT_DGELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] *= gelu_erf_grad(x[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = x[j] > 0.0f ? f[j] : 0.0f;
+          }
+        }
+        if (p.residual) {
+          const bf16* rp = p.residual + res_off + col0;
+          if (vec) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp + j));
+              f[j] += bf16_lo(u.x), f[j + 1] += bf16_hi(u.x);
+              f[j + 2] += bf16_lo(u.y), f[j + 3] += bf16_hi(u.y);
+              f[j + 4] += bf16_lo(u.z), f[j + 5] += bf16_hi(u.z);
+              f[j + 6] += bf16_lo(u.w), f[j + 7] += bf16_hi(u.w);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.n) f[j] += __bfloat162float(rp[j]);
+          }
+        }
+        if (p.out_f32) {
+          float* cp = reinterpret_cast<float*>(p.c) + c_off + col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.n) cp[j] = f[j];
+        } else {
+          bf16* cp = reinterpret_cast<bf16*>(p.c) + c_off + col0;
+          if (vec) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 u;
+              u.x = pack_bf16x2(f[j], f[j + 1]);
+              u.y = pack_bf16x2(f[j + 2], f[j + 3]);
+              u.z = pack_bf16x2(f[j + 4], f[j + 5]);
+              u.w = pack_bf16x2(f[j + 6], f[j + 7]);
+              *reinterpret_cast<uint4*>(cp + j) = u;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.n) cp[j] = __float2bfloat16(f[j]);
+          }
+        }
+        }  // NT/NN epilogue
+        }  // row_ok
+        __syncwarp();
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int MODE>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  const int total = p.m_tiles * p.n_tiles * p.split_k;
+  const int grid = total < num_sms() ? total : num_sms();
+  gemm_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, p);
+  SMX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace gemm
+}  // namespace smx
+
+extern "C" int smx_gemm(const SmxGemm* g, void* stream) {
+  using namespace smx;
+  using namespace smx::gemm;
+  SMX_REQUIRE(g != nullptr, "smx_gemm: null descriptor");
+  SMX_REQUIRE(g->mode >= 0 && g->mode <= 2, "smx_gemm: bad mode %d", g->mode);
+  SMX_REQUIRE(g->m > 0 && g->n > 0 && g->k > 0 && g->batches > 0, "smx_gemm: empty problem m=%lld n=%lld k=%lld b=%lld",
+              (long long)g->m, (long long)g->n, (long long)g->k, (long long)g->batches);
+  SMX_REQUIRE(g->nseg >= 1 && g->nseg <= SMX_MAX_SEG, "smx_gemm: nseg %d out of range", g->nseg);
+  SMX_REQUIRE(g->nseg == 1 || g->seg_len % 64 == 0, "smx_gemm: seg_len %d must be a multiple of 64", g->seg_len);
+  SMX_REQUIRE(g->a.ptr && g->b.ptr && g->c, "smx_gemm: null operand");
+
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.mode = g->mode;
+  p.m = g->m;
+  p.n = g->n;
+  p.batches = (int)g->batches;
+  p.nseg = g->nseg;
+  p.seg_len = g->seg_len;
+  for (int i = 0; i < SMX_MAX_SEG; ++i) {
+    p.a_row_off[i] = g->a_row_off[i];
+    p.a_col_off[i] = g->a_col_off[i];
+    p.b_row_off[i] = g->b_row_off[i];
+    p.b_col_off[i] = g->b_col_off[i];
+  }
+  p.c = g->c;
+  p.c_row_stride = g->c_row_stride;
+  p.c_batch_stride = g->c_batch_stride;
+  p.act = g->act;
+  p.alpha = g->alpha;
+  p.bias = g->bias;
+  p.residual = reinterpret_cast<const bf16*>(g->residual);
+  p.res_row_stride = g->res_row_stride;
+  p.res_batch_stride = g->res_batch_stride;
+  p.aux_out = reinterpret_cast<bf16*>(g->aux_out);
+  p.aux_in = reinterpret_cast<const bf16*>(g->aux_in);
+  p.n_tiles = (int)ceil_div(g->n, BN);
+  p.split_k = 1;
+
+  CUtensorMap ta, tb;
+  const uint64_t a_dims[3] = {(uint64_t)g->a.inner, (uint64_t)g->a.rows, (uint64_t)g->a.batches};
+  const uint64_t a_str[2] = {(uint64_t)g->a.row_stride,
+                             (uint64_t)(g->a.batches > 1 ? g->a.batch_stride : g->a.row_stride * g->a.rows)};
+  const uint64_t b_dims[3] = {(uint64_t)g->b.inner, (uint64_t)g->b.rows, (uint64_t)g->b.batches};
+  const uint64_t b_str[2] = {(uint64_t)g->b.row_stride,
+                             (uint64_t)(g->b.batches > 1 ? g->b.batch_stride : g->b.row_stride * g->b.rows)};
+
+  if (g->mode == SMX_GEMM_TN) {
+    SMX_REQUIRE(g->n == (int64_t)g->nseg * g->seg_len, "smx_gemm TN: n %lld != nseg*seg_len", (long long)g->n);
+    p.out_f32 = 1;
+    p.m_tiles_per_batch = 0;
+    p.m_tiles = (int)ceil_div(g->m, BM);
+    p.kb_per_batch = (int)ceil_div(g->k, BK);
+    p.kblocks = p.kb_per_batch * (int)g->batches;
+    p.split_k = g->split_k > 1 ? g->split_k : 1;
+    if (p.split_k > p.kblocks) p.split_k = p.kblocks;
+    p.atomic = (p.split_k > 1 || g->accumulate) ? 1 : 0;
+    p.b_inner_oob = (int)g->b.inner + 64;
+    const uint32_t box[3] = {64, 64, 1};
+    if (encode_tmap_bf16(&ta, g->a.ptr, 3, a_dims, a_str, box, true)) return -1;
+    if (encode_tmap_bf16(&tb, g->b.ptr, 3, b_dims, b_str, box, true)) return -1;
+    return launch<SMX_GEMM_TN>(ta, tb, p, (cudaStream_t)stream);
+  }
+
+  SMX_REQUIRE(g->k == (int64_t)g->nseg * g->seg_len, "smx_gemm: k %lld != nseg*seg_len", (long long)g->k);
+  SMX_REQUIRE(g->act != SMX_ACT_DGELU && g->act != SMX_ACT_DRELU || g->aux_in, "smx_gemm: DGELU/DRELU need aux_in");
+  p.out_f32 = g->out_dtype == SMX_OUT_F32;
+  p.m_tiles_per_batch = (int)ceil_div(g->m, BM);
+  p.m_tiles = p.m_tiles_per_batch * (int)g->batches;
+  p.kblocks = (int)ceil_div(g->k, BK);
+  p.kb_per_batch = p.kblocks;
+  const uint32_t a_box[3] = {64, 128, 1};
+  if (encode_tmap_bf16(&ta, g->a.ptr, 3, a_dims, a_str, a_box, true)) return -1;
+  if (g->mode == SMX_GEMM_NT) {
+    const uint32_t b_box[2] = {64, 256};
+    if (encode_tmap_bf16(&tb, g->b.ptr, 2, b_dims, b_str, b_box, true)) return -1;
+    return launch<SMX_GEMM_NT>(ta, tb, p, (cudaStream_t)stream);
+  }
+  const uint32_t b_box[2] = {64, 64};
+  if (encode_tmap_bf16(&tb, g->b.ptr, 2, b_dims, b_str, b_box, true)) return -1;
+  return launch<SMX_GEMM_NN>(ta, tb, p, (cudaStream_t)stream);
+}
