@@ -192,11 +192,14 @@ int smx_attn_fwd(const SmxAttn* a, void* stream);
 int smx_attn_bwd(const SmxAttn* a, void* stream);
 
 /* ------------------------------------------------------------------------
- * Decoder input embedding: tok_emb[id]*scale + pos_emb[t + offset]  (bf16 out)
- * hf:...bart.py:74-111, :620-640.  bwd scatters fp32 into the tied table grad.
+ * Input embeddings:  out[b,t,:] = tok_emb[ids[b,t]]*scale (if ids) + x_in[b,t,:] (if x_in)
+ *                                 + pos_emb[t + t_start + pos_offset] (if pos_emb)      (bf16 out)
+ * hf:...bart.py:74-111 (learned positions, offset 2), :508-530 (encoder on inputs_embeds),
+ * :620-640 (decoder).  bwd scatters fp32 into the (tied) table gradients.
  * ------------------------------------------------------------------------ */
-int smx_embed_fwd(const int64_t* ids, const float* tok_emb, const float* pos_emb, void* out, int64_t batch,
-                  int64_t t, int64_t dim, float scale, int64_t pos_offset, int64_t t_start, void* stream);
+int smx_embed_fwd(const int64_t* ids, const float* tok_emb, const float* pos_emb, const void* x_in, void* out,
+                  int64_t batch, int64_t t, int64_t dim, float scale, int64_t pos_offset, int64_t t_start,
+                  void* stream);
 int smx_embed_bwd(const int64_t* ids, const void* dout, float* d_tok_emb, float* d_pos_emb, int64_t batch,
                   int64_t t, int64_t dim, float scale, int64_t pos_offset, void* stream);
 

@@ -74,7 +74,7 @@ SIGNATURES = {
     "smx_posconv_wgrad": (c_int, [_P, _P, _P, _I64, _I64, c_int, c_int, c_int, _P]),
     "smx_attn_fwd": (c_int, [POINTER(SmxAttn), _P]),
     "smx_attn_bwd": (c_int, [POINTER(SmxAttn), _P]),
-    "smx_embed_fwd": (c_int, [_P, _P, _P, _P, _I64, _I64, _I64, c_float, _I64, _I64, _P]),
+    "smx_embed_fwd": (c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I64, c_float, _I64, _I64, _P]),
     "smx_embed_bwd": (c_int, [_P, _P, _P, _P, _I64, _I64, _I64, c_float, _I64, _P]),
     "smx_lmhead_ws_bytes": (c_size_t, [_I64, _I64]),
     "smx_lmhead_ce_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, c_float, _I64, _P]),

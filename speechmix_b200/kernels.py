@@ -226,3 +226,49 @@ def pack_conv_weight(w):
 def unpack_conv_wgrad(dw_packed, in_c, k):
     out_c = dw_packed.shape[0]
     return dw_packed.view(out_c, k, in_c).permute(0, 2, 1).contiguous()
+
+
+# ---------------------------------------------------------------------------
+# attention (head_dim 64); q/k/v: [B, T, heads*64] views with unit inner stride
+# ---------------------------------------------------------------------------
+def _attn_desc(q, k, v, o, lse, heads, causal, scale, bias):
+    B, Tq, HD = q.shape
+    Tk = k.shape[1]
+    assert HD == heads * 64 and q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1
+    a = SmxAttn()
+    a.q, a.k, a.v, a.o, a.lse = _ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(lse)
+    a.q_row_stride, a.k_row_stride, a.v_row_stride, a.o_row_stride = q.stride(1), k.stride(1), v.stride(1), o.stride(1)
+    a.q_batch_stride, a.k_batch_stride, a.v_batch_stride, a.o_batch_stride = (
+        q.stride(0), k.stride(0), v.stride(0), o.stride(0))
+    a.batch, a.heads, a.tq, a.tk, a.causal = B, heads, Tq, Tk, 1 if causal else 0
+    a.scale = scale
+    a.bias = _ptr(bias)
+    return a
+
+
+def attn_fwd(q, k, v, heads, causal=False, scale=None, bias=None):
+    B, Tq, HD = q.shape
+    scale = (1.0 / math.sqrt(64)) if scale is None else scale
+    o = torch.empty(B, Tq, HD, device=q.device, dtype=BF16)
+    lse = torch.empty(B, heads, Tq, device=q.device, dtype=torch.float32)
+    a = _attn_desc(q, k, v, o, lse, heads, causal, scale, bias)
+    _lib.check(_lib.load().smx_attn_fwd(ctypes.byref(a), _stream()), "smx_attn_fwd")
+    return o, lse
+
+
+def attn_bwd(do, q, k, v, o, lse, heads, causal=False, scale=None, bias=None, dq=None, dk=None, dv=None):
+    B, Tq, HD = q.shape
+    Tk = k.shape[1]
+    scale = (1.0 / math.sqrt(64)) if scale is None else scale
+    assert do.stride(2) == 1
+    dq = torch.empty(B, Tq, HD, device=q.device, dtype=BF16) if dq is None else dq
+    dk = torch.empty(B, Tk, HD, device=q.device, dtype=BF16) if dk is None else dk
+    dv = torch.empty(B, Tk, HD, device=q.device, dtype=BF16) if dv is None else dv
+    delta = torch.empty(B, heads, Tq, device=q.device, dtype=torch.float32)
+    a = _attn_desc(q, k, v, o, lse, heads, causal, scale, bias)
+    a.d_o, a.dq, a.dk, a.dv, a.delta = _ptr(do), _ptr(dq), _ptr(dk), _ptr(dv), _ptr(delta)
+    a.do_row_stride, a.do_batch_stride = do.stride(1), do.stride(0)
+    a.dq_row_stride, a.dk_row_stride, a.dv_row_stride = dq.stride(1), dk.stride(1), dv.stride(1)
+    a.dq_batch_stride, a.dk_batch_stride, a.dv_batch_stride = dq.stride(0), dk.stride(0), dv.stride(0)
+    _lib.check(_lib.load().smx_attn_bwd(ctypes.byref(a), _stream()), "smx_attn_bwd")
+    return dq, dk, dv

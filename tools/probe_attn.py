@@ -1,0 +1,141 @@
+"""GPU probe for the attention kernels (development tool; pytest version in tests/)."""
+import json
+import math
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+CASES = {}
+
+
+def case(fn):
+    CASES[fn.__name__] = fn
+    return fn
+
+
+def _rep(name, got, ref):
+    import torch
+    got = got.float()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-9
+    rec = {"case": name, "max_err": err, "ref_max": scale, "rel": err / scale, "nan": bool(torch.isnan(got).any())}
+    print(json.dumps(rec), flush=True)
+    return rec["rel"] < 2e-2 and not rec["nan"]
+
+
+def _ref(q, k, v, heads, causal, scale):
+    import torch
+    B, Tq, _ = q.shape
+    Tk = k.shape[1]
+    qh = q.float().view(B, Tq, heads, 64).transpose(1, 2)
+    kh = k.float().view(B, Tk, heads, 64).transpose(1, 2)
+    vh = v.float().view(B, Tk, heads, 64).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2) * scale
+    if causal:
+        mask = torch.ones(Tq, Tk, device=q.device, dtype=torch.bool).tril(Tk - Tq)
+        s = s.masked_fill(~mask, float("-inf"))
+    p = torch.softmax(s, -1)
+    o = (p @ vh).transpose(1, 2).reshape(B, Tq, heads * 64)
+    return o, torch.logsumexp(s, -1)
+
+
+def _run(B, Tq, Tk, heads, causal, fused=False, bwd=True):
+    import torch
+    from speechmix_b200 import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(0)
+    scale = 1 / 8.0
+    if fused and Tq == Tk:
+        qkv = torch.randn(B, Tq, 3 * heads * 64, device="cuda", generator=g).to(torch.bfloat16)
+        q, k, v = qkv[..., :heads * 64], qkv[..., heads * 64:2 * heads * 64], qkv[..., 2 * heads * 64:]
+    else:
+        q = torch.randn(B, Tq, heads * 64, device="cuda", generator=g).to(torch.bfloat16)
+        k = torch.randn(B, Tk, heads * 64, device="cuda", generator=g).to(torch.bfloat16)
+        v = torch.randn(B, Tk, heads * 64, device="cuda", generator=g).to(torch.bfloat16)
+    name = f"B{B} Tq{Tq} Tk{Tk} H{heads} causal{int(causal)} fused{int(fused)}"
+    o, lse = K.attn_fwd(q, k, v, heads, causal=causal, scale=scale)
+    torch.cuda.synchronize()
+    qr, kr, vr = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+    o_ref, lse_ref = _ref(qr, kr, vr, heads, causal, scale)
+    ok = _rep("fwd o " + name, o, o_ref.detach())
+    ok &= _rep("fwd lse " + name, lse, lse_ref.detach())
+    if bwd:
+        do = torch.randn(B, Tq, heads * 64, device="cuda", generator=g).to(torch.bfloat16)
+        o_ref.backward(do.float())
+        dq, dk, dv = K.attn_bwd(do, q, k, v, o, lse, heads, causal=causal, scale=scale)
+        torch.cuda.synchronize()
+        ok &= _rep("bwd dq " + name, dq, qr.grad)
+        ok &= _rep("bwd dk " + name, dk, kr.grad)
+        ok &= _rep("bwd dv " + name, dv, vr.grad)
+    return ok
+
+
+@case
+def fwd_small():
+    ok = True
+    for args in [(1, 128, 128, 1, False), (2, 100, 100, 2, False), (2, 256, 256, 2, False), (1, 300, 200, 4, False),
+                 (2, 64, 64, 4, True), (2, 200, 200, 2, True), (2, 64, 374, 4, False)]:
+        ok &= _run(*args, bwd=False)
+    return ok
+
+
+@case
+def bwd_small():
+    ok = True
+    for args in [(1, 128, 128, 1, False), (2, 100, 100, 2, False), (2, 256, 256, 2, False), (1, 300, 200, 4, False),
+                 (2, 64, 64, 4, True), (2, 200, 200, 2, True), (2, 64, 374, 4, False)]:
+        ok &= _run(*args, bwd=True)
+    return ok
+
+
+@case
+def full_size():
+    ok = _run(4, 749, 749, 12, False, fused=True)
+    ok &= _run(2, 1499, 1499, 16, False, fused=True)
+    return ok
+
+
+@case
+def perf():
+    import torch
+    from speechmix_b200 import kernels as K
+    B, T, H = 32, 749, 12
+    g = torch.Generator(device="cuda").manual_seed(0)
+    qkv = torch.randn(B, T, 3 * H * 64, device="cuda", generator=g).to(torch.bfloat16)
+    q, k, v = qkv[..., :H * 64], qkv[..., H * 64:2 * H * 64], qkv[..., 2 * H * 64:]
+    do = torch.randn(B, T, H * 64, device="cuda", generator=g).to(torch.bfloat16)
+    o, lse = K.attn_fwd(q, k, v, H)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for fn, nm, mult in ((lambda: K.attn_fwd(q, k, v, H), "fwd", 4), (lambda: K.attn_bwd(do, q, k, v, o, lse, H), "bwd", 10)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(json.dumps({"perf": nm, "ms": ms, "tflops_alg": mult * B * H * T * T * 64 / ms / 1e9}), flush=True)
+    return True
+
+
+def main():
+    if len(sys.argv) > 2 and sys.argv[1] == "--case":
+        ok = CASES[sys.argv[2]]()
+        print(json.dumps({"case_done": sys.argv[2], "ok": bool(ok)}), flush=True)
+        sys.exit(0 if ok else 1)
+    for n in (sys.argv[1:] or list(CASES)):
+        t = time.time()
+        try:
+            r = subprocess.run([sys.executable, __file__, "--case", n], capture_output=True, text=True, timeout=300)
+            out, rc = r.stdout + "\n" + r.stderr[-3000:], r.returncode
+        except subprocess.TimeoutExpired as e:
+            out, rc = (e.stdout or b"").decode() + "\nTIMEOUT", -9
+        print(f"===== {n} rc={rc} ({time.time() - t:.1f}s)\n{out}", flush=True)
+
+
+if __name__ == "__main__":
+    main()
