@@ -87,7 +87,7 @@ typedef struct SmxGemm {
   int64_t c_row_stride, c_batch_stride; /* elements */
   int32_t act;
   int32_t split_k;      /* TN only; >1 => atomic fp32 accumulation into a zeroed or live C */
-  int32_t accumulate;   /* TN only; 1 => add into C even when split_k == 1 */
+  int32_t accumulate;   /* TN: add into C even when split_k == 1.  NT/NN with fp32 output: C += v */
   float alpha;
   const float* bias;    /* [n] fp32 or NULL */
   const void* residual; /* bf16, same shape/strides as C, or NULL */
@@ -121,6 +121,8 @@ int smx_colsum(const void* x, float* out, int64_t rows, int64_t cols, int64_t ro
 int smx_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 int smx_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
 int smx_act_bf16(const void* x, void* y, int64_t n, int act, void* stream);
+/* out = dy * act'(pre), act in {SMX_ACT_GELU, SMX_ACT_RELU} */
+int smx_dact_bf16(const void* dy, const void* pre, void* out, int64_t n, int act, void* stream);
 /* dst[o, t*cin + c] = src[o, c, t] : Conv1d weight [out][in][k] -> packed [out][k*in] bf16 */
 int smx_pack_conv_weight(const float* src, void* dst, int64_t cout, int64_t cin, int64_t k, void* stream);
 /* inverse of the above for fp32 gradients: dst[o, c, t] = src[o, t*cin + c] */
@@ -131,19 +133,20 @@ int smx_unpack_conv_wgrad(const float* src, float* dst, int64_t cout, int64_t ci
  * + GELU, fused; the un-normalised conv output never exists in HBM.
  * hf:...wav2vec2.py:302-323 (Wav2Vec2GroupNormConvLayer).
  * ------------------------------------------------------------------------ */
-/* stats[b][c] = {mean, rstd} of the conv output over time, from the raw audio's
- * window moments (exact algebra, one pass over the waveform). */
+/* moments: workspace [batch][110] fp32 (window sums + second-moment matrix of the raw audio);
+ * stats[b][c] = {mean, rstd} of the conv output over time, derived from the moments
+ * (exact algebra, one pass over the waveform). */
 int smx_conv0_stats(const float* audio, const float* w, float* moments, float* stats, int64_t batch,
                     int64_t n_samples, int64_t t_out, int channels, int ksize, int stride, float eps,
                     void* stream);
 int smx_conv0_gn_gelu_fwd(const float* audio, const float* w, const float* gamma, const float* beta,
                           const float* stats, void* y, int64_t batch, int64_t n_samples, int64_t t_out,
                           int channels, int ksize, int stride, void* stream);
-/* one pass over dy: partial[b][c][k+2] = {sum dz, sum dz*xhat, sum_t dz*x[s*t+j], j<k} */
+/* one pass over dy; partial: workspace [batch][channels][ksize+2] fp32; writes dw [C][k], dgamma, dbeta */
 int smx_conv0_gn_gelu_bwd(const float* audio, const float* w, const float* gamma, const float* beta,
-                          const float* stats, const void* dy, float* partial, int64_t batch,
-                          int64_t n_samples, int64_t t_out, int channels, int ksize, int stride,
-                          void* stream);
+                          const float* stats, const float* moments, const void* dy, float* partial, float* dw,
+                          float* dgamma, float* dbeta, int64_t batch, int64_t n_samples, int64_t t_out,
+                          int channels, int ksize, int stride, void* stream);
 
 /* ------------------------------------------------------------------------
  * Positional conv embedding: grouped Conv1d(H->H, k=128, pad=64, groups=16),
@@ -154,9 +157,9 @@ int smx_conv0_gn_gelu_bwd(const float* audio, const float* w, const float* gamma
  * ------------------------------------------------------------------------ */
 int smx_posconv_fwd(const void* x, const void* w_packed, const float* bias, void* y, void* pre_out,
                     int64_t batch, int64_t t, int hidden, int groups, int ksize, int add_input, void* stream);
-/* dx_conv = conv^T(dpre) with w_packed_t = taps flipped, in/out swapped */
-int smx_posconv_dgrad(const void* dpre, const void* w_packed_t, void* dx, int64_t batch, int64_t t, int hidden,
-                      int groups, int ksize, void* stream);
+/* dx = conv^T(dpre) (+ residual) with w_packed_t = taps flipped, in/out swapped */
+int smx_posconv_dgrad(const void* dpre, const void* w_packed_t, const void* residual, void* dx, int64_t batch,
+                      int64_t t, int hidden, int groups, int ksize, void* stream);
 /* dw[g][k][o][c] (fp32, zero-initialised) += sum_{b,t} dpre[b,t,g*cg+o] * x[b,t+k-pad,g*cg+c] */
 int smx_posconv_wgrad(const void* dpre, const void* x, float* dw, int64_t batch, int64_t t, int hidden,
                       int groups, int ksize, void* stream);
@@ -216,12 +219,12 @@ int smx_lmhead_ce_fwd(const void* h, const void* emb, const float* bias, const i
                       int64_t* argmax, float* row_loss, float* loss_sum, float* count, void* workspace,
                       int64_t rows, int64_t dim, int64_t vocab, float logit_scale, int64_t ignore_index,
                       void* stream);
-/* dlogits chunk [rows][v0:v0+vn) = (softmax - onehot(label)) * coef[row]  as bf16, for the
- * chunked backward (the chunk stays L2-resident between the two GEMMs that consume it). */
+/* dlogits[rows][0:vn) (row stride ld, bf16) = (softmax(logits)[v0:v0+vn) - onehot(label)) * coef[row]
+ * for the chunked backward: the chunk stays L2-resident between the two GEMMs that consume it
+ * (dh += dlogits . E[v0:v0+vn), dE[v0:v0+vn) = dlogits^T . h).  coef[row] = dloss/count or 0. */
 int smx_lmhead_dlogits(const void* h, const void* emb, const float* bias, const int64_t* labels,
-                       const float* lse, const float* grad_scale, void* dlogits, int64_t rows, int64_t dim,
-                       int64_t vocab, int64_t v0, int64_t vn, float logit_scale, int64_t ignore_index,
-                       void* stream);
+                       const float* lse, const float* coef, void* dlogits, int64_t ld, int64_t rows,
+                       int64_t dim, int64_t vocab, int64_t v0, int64_t vn, float logit_scale, void* stream);
 
 /* ------------------------------------------------------------------------
  * Weighted layer sum (ref:speechmix/hf_model.py:411-423): out = sum_l w[l]*x_l

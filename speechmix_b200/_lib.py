@@ -64,13 +64,14 @@ SIGNATURES = {
     "smx_cast_f32_to_bf16": (c_int, [_P, _P, _I64, _P]),
     "smx_add_bf16": (c_int, [_P, _P, _P, _I64, _P]),
     "smx_act_bf16": (c_int, [_P, _P, _I64, c_int, _P]),
+    "smx_dact_bf16": (c_int, [_P, _P, _P, _I64, c_int, _P]),
     "smx_pack_conv_weight": (c_int, [_P, _P, _I64, _I64, _I64, _P]),
     "smx_unpack_conv_wgrad": (c_int, [_P, _P, _I64, _I64, _I64, _P]),
     "smx_conv0_stats": (c_int, [_P, _P, _P, _P, _I64, _I64, _I64, c_int, c_int, c_int, c_float, _P]),
     "smx_conv0_gn_gelu_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, c_int, c_int, c_int, _P]),
-    "smx_conv0_gn_gelu_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, c_int, c_int, c_int, _P]),
+    "smx_conv0_gn_gelu_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, c_int, c_int, c_int, _P]),
     "smx_posconv_fwd": (c_int, [_P, _P, _P, _P, _P, _I64, _I64, c_int, c_int, c_int, c_int, _P]),
-    "smx_posconv_dgrad": (c_int, [_P, _P, _P, _I64, _I64, c_int, c_int, c_int, _P]),
+    "smx_posconv_dgrad": (c_int, [_P, _P, _P, _P, _I64, _I64, c_int, c_int, c_int, _P]),
     "smx_posconv_wgrad": (c_int, [_P, _P, _P, _I64, _I64, c_int, c_int, c_int, _P]),
     "smx_attn_fwd": (c_int, [POINTER(SmxAttn), _P]),
     "smx_attn_bwd": (c_int, [POINTER(SmxAttn), _P]),
@@ -78,7 +79,7 @@ SIGNATURES = {
     "smx_embed_bwd": (c_int, [_P, _P, _P, _P, _I64, _I64, _I64, c_float, _I64, _P]),
     "smx_lmhead_ws_bytes": (c_size_t, [_I64, _I64]),
     "smx_lmhead_ce_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, c_float, _I64, _P]),
-    "smx_lmhead_dlogits": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, c_float, _I64, _P]),
+    "smx_lmhead_dlogits": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, c_float, _P]),
     "smx_weighted_sum_fwd": (c_int, [_P, _P, _P, c_int, _I64, _P]),
     "smx_weighted_sum_bwd_w": (c_int, [_P, _P, _P, c_int, _I64, _P]),
 }

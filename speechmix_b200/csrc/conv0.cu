@@ -1,0 +1,295 @@
+// conv0 of the wav2vec2 / HuBERT feature encoder, fused:
+//   Conv1d(1 -> C, k = 10, stride 5, no bias)  ->  GroupNorm(C groups == per (batch, channel) over time)
+//   -> GELU                                     hf:models/wav2vec2/modeling_wav2vec2.py:302-323
+//
+// The convolution is linear in a 10-sample window, so the GroupNorm statistics
+// follow exactly from the window moments of the raw waveform:
+//   mean_c = w_c . E[win],   E[y_c^2] = w_c^T E[win win^T] w_c.
+// Forward therefore makes ONE pass that reads the waveform (tiny) and writes the
+// normalised, activated [B, T, C] bf16 output (the largest activation of the whole
+// model) exactly once; the un-normalised conv output never exists in HBM.
+// Backward makes one pass over dY, recomputing the pre-activation from the waveform,
+// and reduces everything the weight / affine gradients need to 12 numbers per (b, c).
+#include "../../include/speechmix_sm100.h"
+#include "host_common.h"
+#include "sm100_prims.cuh"
+
+namespace smx {
+namespace conv0 {
+
+constexpr int K = 10, S = 5;
+constexpr int NMOM = K + K * K;  // window sums + full second-moment matrix
+
+// ------------------------------------------------------------------ window moments
+__global__ void __launch_bounds__(256) moments_kernel(const float* __restrict__ audio, float* __restrict__ moments,
+                                                      long long n_samples, long long t_out) {
+  const int b = blockIdx.y;
+  const float* x = audio + (long long)b * n_samples;
+  float m[K], r[K * (K + 1) / 2];
+#pragma unroll
+  for (int i = 0; i < K; ++i) m[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < K * (K + 1) / 2; ++i) r[i] = 0.f;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < t_out; t += (long long)gridDim.x * blockDim.x) {
+    float w[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) w[i] = x[t * S + i];
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      m[i] += w[i];
+#pragma unroll
+      for (int j = i; j < K; ++j) r[idx++] += w[i] * w[j];
+    }
+  }
+  __shared__ float red[8][K + K * (K + 1) / 2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    const float v = warp_sum(m[i]);
+    if (lane == 0) red[warp][i] = v;
+  }
+#pragma unroll
+  for (int i = 0; i < K * (K + 1) / 2; ++i) {
+    const float v = warp_sum(r[i]);
+    if (lane == 0) red[warp][K + i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < K + K * (K + 1) / 2) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    float* mo = moments + (long long)b * NMOM;
+    if (threadIdx.x < K) {
+      atomicAdd(mo + threadIdx.x, v);
+    } else {
+      int rem = threadIdx.x - K, i = 0;
+      while (rem >= K - i) {
+        rem -= K - i;
+        ++i;
+      }
+      const int j = i + rem;
+      atomicAdd(mo + K + i * K + j, v);
+      if (i != j) atomicAdd(mo + K + j * K + i, v);
+    }
+  }
+}
+
+__global__ void stats_kernel(const float* __restrict__ w, const float* __restrict__ moments, float* __restrict__ stats,
+                             int batch, int channels, long long t_out, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * channels) return;
+  const int b = i / channels, c = i % channels;
+  const float* mo = moments + (long long)b * NMOM;
+  const float* wc = w + c * K;
+  const double inv_t = 1.0 / (double)t_out;
+  double mean = 0.0, ey2 = 0.0;
+  for (int j = 0; j < K; ++j) {
+    mean += (double)wc[j] * mo[j];
+    double row = 0.0;
+    for (int l = 0; l < K; ++l) row += (double)wc[l] * mo[K + j * K + l];
+    ey2 += (double)wc[j] * row;
+  }
+  mean *= inv_t;
+  ey2 *= inv_t;
+  double var = ey2 - mean * mean;
+  if (var < 0.0) var = 0.0;
+  stats[2 * i] = (float)mean;
+  stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// ------------------------------------------------------------------ forward
+// block: 64 channel-octets x 4 frame lanes; FR frames per block staged through smem
+constexpr int FWD_FR = 256;
+__global__ void __launch_bounds__(256) fwd_kernel(const float* __restrict__ audio, const float* __restrict__ w,
+                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                  const float* __restrict__ stats, bf16* __restrict__ y,
+                                                  long long n_samples, long long t_out, int channels) {
+  __shared__ float xs[FWD_FR * S + K];
+  const int b = blockIdx.y;
+  const long long t0 = (long long)blockIdx.x * FWD_FR;
+  const long long nfr = (t_out - t0) < FWD_FR ? (t_out - t0) : FWD_FR;
+  const float* x = audio + (long long)b * n_samples + t0 * S;
+  const int nload = (int)nfr * S + (K - S);
+  for (int i = threadIdx.x; i < nload; i += blockDim.x) xs[i] = x[i];
+  __syncthreads();
+  const int octs = channels / 8;
+  const int lanes = blockDim.x / 64;
+  for (int og = threadIdx.x % 64; og < octs; og += 64) {
+    const int c0 = og * 8;
+    float wf[8][K], bf[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      const float mean = stats[2 * ((long long)b * channels + c)];
+      const float rstd = stats[2 * ((long long)b * channels + c) + 1];
+      const float g = gamma[c] * rstd;
+#pragma unroll
+      for (int k = 0; k < K; ++k) wf[j][k] = w[c * K + k] * g;
+      bf[j] = beta[c] - mean * g;
+    }
+    for (int f = threadIdx.x / 64; f < nfr; f += lanes) {
+      float win[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) win[k] = xs[f * S + k];
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float z = bf[j];
+#pragma unroll
+        for (int k = 0; k < K; ++k) z = fmaf(wf[j][k], win[k], z);
+        o[j] = gelu_erf(z);
+      }
+      uint4 u;
+      u.x = pack_bf16x2(o[0], o[1]), u.y = pack_bf16x2(o[2], o[3]);
+      u.z = pack_bf16x2(o[4], o[5]), u.w = pack_bf16x2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(y + ((long long)b * t_out + t0 + f) * channels + c0) = u;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ backward (single pass over dy)
+// partial[b][c][0] = sum dz, [1] = sum dz*xhat, [2+k] = sum_t dz * x[S t + k]
+constexpr int BWD_FR = 1024;
+__global__ void __launch_bounds__(256) bwd_kernel(const float* __restrict__ audio, const float* __restrict__ w,
+                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                  const float* __restrict__ stats, const bf16* __restrict__ dy,
+                                                  float* __restrict__ partial, long long n_samples, long long t_out,
+                                                  int channels) {
+  __shared__ float xs[BWD_FR * S + K];
+  const int b = blockIdx.y;
+  const long long t0 = (long long)blockIdx.x * BWD_FR;
+  const long long nfr = (t_out - t0) < BWD_FR ? (t_out - t0) : BWD_FR;
+  const float* x = audio + (long long)b * n_samples + t0 * S;
+  const int nload = (int)nfr * S + (K - S);
+  for (int i = threadIdx.x; i < nload; i += blockDim.x) xs[i] = x[i];
+  __syncthreads();
+  const int quads = channels / 4;
+  const int lanes = blockDim.x / 128;  // 2 frame lanes
+  for (int qg = threadIdx.x % 128; qg < quads; qg += 128) {
+    const int c0 = qg * 4;
+    float wn[4][K], mn[4], gm[4], bt[4];
+    float acc[4][K + 2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + j;
+      const float mean = stats[2 * ((long long)b * channels + c)];
+      const float rstd = stats[2 * ((long long)b * channels + c) + 1];
+#pragma unroll
+      for (int k = 0; k < K; ++k) wn[j][k] = w[c * K + k] * rstd;
+      mn[j] = mean * rstd;
+      gm[j] = gamma[c];
+      bt[j] = beta[c];
+#pragma unroll
+      for (int k = 0; k < K + 2; ++k) acc[j][k] = 0.f;
+    }
+    for (int f = threadIdx.x / 128; f < nfr; f += lanes) {
+      float win[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) win[k] = xs[f * S + k];
+      const uint2 u = *reinterpret_cast<const uint2*>(dy + ((long long)b * t_out + t0 + f) * channels + c0);
+      const float d[4] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y)};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float xh = -mn[j];
+#pragma unroll
+        for (int k = 0; k < K; ++k) xh = fmaf(wn[j][k], win[k], xh);
+        const float z = fmaf(gm[j], xh, bt[j]);
+        const float dz = d[j] * gelu_erf_grad(z);
+        acc[j][0] += dz;
+        acc[j][1] = fmaf(dz, xh, acc[j][1]);
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[j][2 + k] = fmaf(dz, win[k], acc[j][2 + k]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float* pp = partial + ((long long)b * channels + c0 + j) * (K + 2);
+#pragma unroll
+      for (int k = 0; k < K + 2; ++k) atomicAdd(pp + k, acc[j][k]);
+    }
+  }
+}
+
+// dw[c][j], dgamma[c], dbeta[c] from the per-(b,c) partial sums
+__global__ void bwd_finalize_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+                                    const float* __restrict__ stats, const float* __restrict__ moments,
+                                    const float* __restrict__ partial, float* __restrict__ dw,
+                                    float* __restrict__ dgamma, float* __restrict__ dbeta, int batch, int channels,
+                                    long long t_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= channels * (K + 2)) return;
+  const int c = i / (K + 2), j = i % (K + 2);
+  const double inv_t = 1.0 / (double)t_out;
+  double out = 0.0;
+  for (int b = 0; b < batch; ++b) {
+    const float* pp = partial + ((long long)b * channels + c) * (K + 2);
+    if (j == K) {
+      out += pp[1];  // dgamma
+    } else if (j == K + 1) {
+      out += pp[0];  // dbeta
+    } else {
+      const float* mo = moments + (long long)b * NMOM;
+      const double mean = stats[2 * ((long long)b * channels + c)];
+      const double rstd = stats[2 * ((long long)b * channels + c) + 1];
+      double wr = 0.0;
+      for (int l = 0; l < K; ++l) wr += (double)w[c * K + l] * mo[K + l * K + j];
+      const double sum_xhat_x = rstd * (wr - mean * mo[j]);
+      out += (double)gamma[c] * rstd * ((double)pp[2 + j] - (double)pp[0] * inv_t * mo[j] - (double)pp[1] * inv_t * sum_xhat_x);
+    }
+  }
+  if (j == K) dgamma[c] = (float)out;
+  else if (j == K + 1) dbeta[c] = (float)out;
+  else dw[c * K + j] = (float)out;
+}
+
+}  // namespace conv0
+}  // namespace smx
+
+using namespace smx;
+using namespace smx::conv0;
+
+extern "C" {
+
+int smx_conv0_stats(const float* audio, const float* w, float* moments, float* stats, int64_t batch,
+                    int64_t n_samples, int64_t t_out, int channels, int ksize, int stride, float eps, void* stream) {
+  SMX_REQUIRE(ksize == K && stride == S, "conv0: only kernel 10 / stride 5 is supported (got %d/%d)", ksize, stride);
+  SMX_REQUIRE(t_out == (n_samples - K) / S + 1 && t_out > 0, "conv0: inconsistent t_out");
+  cudaStream_t st = (cudaStream_t)stream;
+  SMX_CHECK_CUDA(cudaMemsetAsync(moments, 0, sizeof(float) * NMOM * batch, st));
+  int gx = (int)ceil_div(t_out, 256 * 8);
+  if (gx < 1) gx = 1;
+  moments_kernel<<<dim3(gx, (unsigned)batch), 256, 0, st>>>(audio, moments, n_samples, t_out);
+  SMX_CHECK_CUDA(cudaGetLastError());
+  stats_kernel<<<(int)ceil_div(batch * channels, 256), 256, 0, st>>>(w, moments, stats, (int)batch, channels, t_out, eps);
+  SMX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int smx_conv0_gn_gelu_fwd(const float* audio, const float* w, const float* gamma, const float* beta,
+                          const float* stats, void* y, int64_t batch, int64_t n_samples, int64_t t_out, int channels,
+                          int ksize, int stride, void* stream) {
+  SMX_REQUIRE(ksize == K && stride == S, "conv0: only kernel 10 / stride 5 is supported");
+  SMX_REQUIRE(channels % 8 == 0, "conv0: channels must be a multiple of 8");
+  fwd_kernel<<<dim3((unsigned)ceil_div(t_out, FWD_FR), (unsigned)batch), 256, 0, (cudaStream_t)stream>>>(
+      audio, w, gamma, beta, stats, (bf16*)y, n_samples, t_out, channels);
+  SMX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int smx_conv0_gn_gelu_bwd(const float* audio, const float* w, const float* gamma, const float* beta,
+                          const float* stats, const float* moments, const void* dy, float* partial, float* dw,
+                          float* dgamma, float* dbeta, int64_t batch, int64_t n_samples, int64_t t_out, int channels,
+                          int ksize, int stride, void* stream) {
+  SMX_REQUIRE(ksize == K && stride == S, "conv0: only kernel 10 / stride 5 is supported");
+  SMX_REQUIRE(channels % 4 == 0, "conv0: channels must be a multiple of 4");
+  cudaStream_t st = (cudaStream_t)stream;
+  SMX_CHECK_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * (K + 2) * batch * channels, st));
+  bwd_kernel<<<dim3((unsigned)ceil_div(t_out, BWD_FR), (unsigned)batch), 256, 0, st>>>(
+      audio, w, gamma, beta, stats, (const bf16*)dy, partial, n_samples, t_out, channels);
+  SMX_CHECK_CUDA(cudaGetLastError());
+  bwd_finalize_kernel<<<(int)ceil_div(channels * (K + 2), 128), 128, 0, st>>>(w, gamma, stats, moments, partial, dw,
+                                                                             dgamma, dbeta, (int)batch, channels, t_out);
+  SMX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+}

@@ -48,6 +48,14 @@ struct Params {
   long long res_row_stride, res_batch_stride;
   bf16* aux_out;
   const bf16* aux_in;
+  // special epilogues (LM head): 0 = regular, 1 = per-tile softmax statistics, 2 = dlogits
+  int epi, accumulate_f32;
+  float4* lm_partial;        // [rows][n_tiles] {max, sumexp, best, best_idx}
+  float* lm_label_logit;     // [rows]
+  const long long* lm_labels;
+  const float* lm_lse;       // [rows]
+  const float* lm_coef;      // [rows]
+  long long lm_label_off;    // vocab index of column 0 of this launch
 };
 
 struct TileCoord {
@@ -236,6 +244,89 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 
+      if (MODE == SMX_GEMM_NT && p.epi == 1) {
+        // ---- LM head: online softmax statistics of this 256-column vocabulary tile, one row per thread
+        float mx = -INFINITY, se = 0.f, best = -INFINITY;
+        int best_idx = 0x7fffffff;
+        const long long label = row_ok ? p.lm_labels[row] : -1;
+        for (int c = 0; c < BN / 32; ++c) {
+          const int col0 = n0 + c * 32;
+          if (col0 >= p.n) break;
+          uint32_t v[32];
+          tmem_ld_x32(t_row + c * 32, v);
+          tmem_ld_wait();
+          float f[32];
+          float cmax = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;
+            float x = p.alpha * __uint_as_float(v[j]);
+            if (col < p.n) {
+              if (p.bias) x += __ldg(p.bias + col);
+            } else {
+              x = -INFINITY;
+            }
+            f[j] = x;
+            cmax = fmaxf(cmax, x);
+            if (x > best) best = x, best_idx = col;
+          }
+          const float m_new = fmaxf(mx, cmax);
+          float acc_e = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc_e += __expf(f[j] - m_new);
+          se = se * __expf(mx - m_new) + acc_e;
+          mx = m_new;
+          if (label >= col0 && label < col0 + 32) {
+            float lv = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) lv = (label - col0 == j) ? f[j] : lv;
+            if (row_ok) p.lm_label_logit[row] = lv;
+          }
+          __syncwarp();
+        }
+        if (row_ok) p.lm_partial[row * p.n_tiles + t.n_blk] = make_float4(mx, se, best, __int_as_float(best_idx));
+      } else if (MODE == SMX_GEMM_NT && p.epi == 2) {
+        // ---- LM head backward: dlogits = (softmax - onehot) * coef, bf16
+        const float lse = row_ok ? p.lm_lse[row] : 0.f;
+        const float coef = row_ok ? p.lm_coef[row] : 0.f;
+        const long long label = row_ok ? p.lm_labels[row] - p.lm_label_off : -1;
+        for (int c = 0; c < BN / 32; ++c) {
+          const int col0 = n0 + c * 32;
+          if (col0 >= p.n) break;
+          uint32_t v[32];
+          tmem_ld_x32(t_row + c * 32, v);
+          tmem_ld_wait();
+          if (row_ok) {
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = col0 + j;
+              float x = p.alpha * __uint_as_float(v[j]);
+              if (p.bias && col < p.n) x += __ldg(p.bias + col);
+              float g = __expf(x - lse) * coef;
+              if (col == label) g -= coef;
+              f[j] = g;
+            }
+            bf16* cp = reinterpret_cast<bf16*>(p.c) + c_off + col0;
+            if (col0 + 32 <= p.n && c_vec_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 u;
+                u.x = pack_bf16x2(f[j], f[j + 1]);
+                u.y = pack_bf16x2(f[j + 2], f[j + 3]);
+                u.z = pack_bf16x2(f[j + 4], f[j + 5]);
+                u.w = pack_bf16x2(f[j + 6], f[j + 7]);
+                *reinterpret_cast<uint4*>(cp + j) = u;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.n) cp[j] = __float2bfloat16(f[j]);
+            }
+          }
+          __syncwarp();
+        }
+      } else
       for (int c = 0; c < BN / 32; ++c) {
         const int col0 = n0 + c * 32;
         if (col0 >= p.n) break;  // warp-uniform
@@ -349,9 +440,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
         if (p.out_f32) {
           float* cp = reinterpret_cast<float*>(p.c) + c_off + col0;
+          if (p.accumulate_f32) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.n) cp[j] = f[j];
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.n) cp[j] += f[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.n) cp[j] = f[j];
+          }
         } else {
           bf16* cp = reinterpret_cast<bf16*>(p.c) + c_off + col0;
           if (vec) {
@@ -404,7 +501,24 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
 }  // namespace gemm
 }  // namespace smx
 
-extern "C" int smx_gemm(const SmxGemm* g, void* stream) {
+namespace smx {
+namespace gemm {
+struct LmExtra {
+  int epi;
+  float4* partial;
+  float* label_logit;
+  const long long* labels;
+  const float* lse;
+  const float* coef;
+  long long label_off;
+};
+int run(const SmxGemm* g, const LmExtra* lm, void* stream);
+}  // namespace gemm
+}  // namespace smx
+
+extern "C" int smx_gemm(const SmxGemm* g, void* stream) { return smx::gemm::run(g, nullptr, stream); }
+
+int smx::gemm::run(const SmxGemm* g, const LmExtra* lm, void* stream) {
   using namespace smx;
   using namespace smx::gemm;
   SMX_REQUIRE(g != nullptr, "smx_gemm: null descriptor");
@@ -442,6 +556,16 @@ extern "C" int smx_gemm(const SmxGemm* g, void* stream) {
   p.aux_in = reinterpret_cast<const bf16*>(g->aux_in);
   p.n_tiles = (int)ceil_div(g->n, BN);
   p.split_k = 1;
+  p.accumulate_f32 = (g->mode != SMX_GEMM_TN && g->accumulate) ? 1 : 0;
+  if (lm) {
+    p.epi = lm->epi;
+    p.lm_partial = lm->partial;
+    p.lm_label_logit = lm->label_logit;
+    p.lm_labels = lm->labels;
+    p.lm_lse = lm->lse;
+    p.lm_coef = lm->coef;
+    p.lm_label_off = lm->label_off;
+  }
 
   CUtensorMap ta, tb;
   const uint64_t a_dims[3] = {(uint64_t)g->a.inner, (uint64_t)g->a.rows, (uint64_t)g->a.batches};

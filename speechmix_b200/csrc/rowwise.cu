@@ -243,6 +243,20 @@ __global__ void act_kernel(const bf16* __restrict__ a, bf16* __restrict__ o, lon
     store8(o + i, x);
   }
 }
+// out = dy * act'(pre)
+__global__ void dact_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ pre, bf16* __restrict__ o, long long n,
+                            int act) {
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  const long long stride = (long long)gridDim.x * blockDim.x * 8;
+  for (; i + 8 <= n; i += stride) {
+    float d[8], x[8];
+    load8(dy + i, d);
+    load8(pre + i, x);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] = act == SMX_ACT_GELU ? d[j] * gelu_erf_grad(x[j]) : (x[j] > 0.f ? d[j] : 0.f);
+    store8(o + i, d);
+  }
+}
 __global__ void pack_conv_w_kernel(const float* __restrict__ s, bf16* __restrict__ d, long long cout, long long cin,
                                    long long k) {
   const long long n = cout * cin * k;
@@ -451,6 +465,14 @@ int smx_act_bf16(const void* x, void* y, int64_t n, int act, void* stream) {
   if (n == 0) return 0;
   SMX_REQUIRE(n % 8 == 0, "act: n must be a multiple of 8");
   act_kernel<<<grid_for(ceil_div(n, 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, n, act);
+  SMX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int smx_dact_bf16(const void* dy, const void* pre, void* out, int64_t n, int act, void* stream) {
+  if (n == 0) return 0;
+  SMX_REQUIRE(n % 8 == 0, "dact: n must be a multiple of 8");
+  dact_kernel<<<grid_for(ceil_div(n, 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, (const bf16*)pre,
+                                                                               (bf16*)out, n, act);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -272,3 +272,241 @@ def attn_bwd(do, q, k, v, o, lse, heads, causal=False, scale=None, bias=None, dq
     a.dq_batch_stride, a.dk_batch_stride, a.dv_batch_stride = dq.stride(0), dk.stride(0), dv.stride(0)
     _lib.check(_lib.load().smx_attn_bwd(ctypes.byref(a), _stream()), "smx_attn_bwd")
     return dq, dk, dv
+
+
+# ---------------------------------------------------------------------------
+# row-wise kernels
+# ---------------------------------------------------------------------------
+def _L():
+    return _lib.load()
+
+
+def layernorm_fwd(x, gamma, beta, eps=1e-5, res=None, want_sum=False, rms_only=False):
+    """x: [..., C] bf16 contiguous.  Returns y, (sum or x), mean, rstd."""
+    C = x.shape[-1]
+    rows = x.numel() // C
+    y = torch.empty_like(x)
+    s = torch.empty_like(x) if (want_sum and res is not None) else None
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+    _lib.check(_L().smx_layernorm_fwd(_ptr(x), _ptr(res), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(s), _ptr(mean),
+                                      _ptr(rstd), rows, C, eps, 1 if rms_only else 0, _stream()), "layernorm_fwd")
+    return y, (s if s is not None else x), mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, rms_only=False, want_dbeta=True):
+    C = x.shape[-1]
+    rows = x.numel() // C
+    dx = torch.empty_like(x)
+    dgamma = torch.zeros(C, device=x.device, dtype=torch.float32)
+    dbeta = torch.zeros(C, device=x.device, dtype=torch.float32) if want_dbeta else None
+    _lib.check(_L().smx_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dres), _ptr(dx),
+                                      _ptr(dgamma), _ptr(dbeta), rows, C, 1 if rms_only else 0, _stream()),
+               "layernorm_bwd")
+    return dx, dgamma, dbeta
+
+
+def colsum(x2d):
+    """fp32 column sums of a [rows, cols] bf16 matrix (row stride may exceed cols)."""
+    rows, cols = x2d.shape
+    out = torch.zeros(cols, device=x2d.device, dtype=torch.float32)
+    assert x2d.stride(1) == 1
+    _lib.check(_L().smx_colsum(_ptr(x2d), _ptr(out), rows, cols, x2d.stride(0), _stream()), "colsum")
+    return out
+
+
+def to_bf16(src):
+    """fp32 -> bf16 copy through the library (weights are cached as bf16 between optimizer steps)."""
+    src = src.detach().contiguous()
+    dst = torch.empty(src.shape, device=src.device, dtype=BF16)
+    if src.numel() % 8 == 0 and src.data_ptr() % 16 == 0:
+        _lib.check(_L().smx_cast_f32_to_bf16(_ptr(src), _ptr(dst), src.numel(), _stream()), "cast")
+    else:
+        dst.copy_(src)
+    return dst
+
+
+def add_bf16(a, b):
+    out = torch.empty_like(a)
+    _lib.check(_L().smx_add_bf16(_ptr(a), _ptr(b), _ptr(out), a.numel(), _stream()), "add")
+    return out
+
+
+def dact(dy, pre, act=ACT_GELU):
+    out = torch.empty_like(dy)
+    _lib.check(_L().smx_dact_bf16(_ptr(dy), _ptr(pre), _ptr(out), dy.numel(), act, _stream()), "dact")
+    return out
+
+
+# ---------------------------------------------------------------------------
+# conv0 + GroupNorm + GELU
+# ---------------------------------------------------------------------------
+def conv0_fwd(audio, w, gamma, beta, eps=1e-5):
+    """audio [B, n] fp32, w [C, 1, 10] fp32.  Returns y [B, T, C] bf16 (slack-padded), stats, moments."""
+    B, n = audio.shape
+    C, _, k = w.shape
+    s = 5
+    T = (n - k) // s + 1
+    moments = torch.empty(B, 110, device=audio.device, dtype=torch.float32)
+    stats = torch.empty(B, C, 2, device=audio.device, dtype=torch.float32)
+    L = _L()
+    _lib.check(L.smx_conv0_stats(_ptr(audio), _ptr(w), _ptr(moments), _ptr(stats), B, n, T, C, k, s, eps, _stream()),
+               "conv0_stats")
+    y = alloc_act(B, T, C, audio.device)
+    _lib.check(L.smx_conv0_gn_gelu_fwd(_ptr(audio), _ptr(w), _ptr(gamma), _ptr(beta), _ptr(stats), _ptr(y), B, n, T,
+                                       C, k, s, _stream()), "conv0_fwd")
+    return y, stats, moments
+
+
+def conv0_bwd(audio, w, gamma, beta, stats, moments, dy):
+    B, n = audio.shape
+    C, _, k = w.shape
+    T = dy.shape[1]
+    partial = torch.empty(B, C, k + 2, device=audio.device, dtype=torch.float32)
+    dw = torch.empty_like(w)
+    dgamma = torch.empty(C, device=audio.device, dtype=torch.float32)
+    dbeta = torch.empty(C, device=audio.device, dtype=torch.float32)
+    _lib.check(_L().smx_conv0_gn_gelu_bwd(_ptr(audio), _ptr(w), _ptr(gamma), _ptr(beta), _ptr(stats), _ptr(moments),
+                                          _ptr(dy), _ptr(partial), _ptr(dw), _ptr(dgamma), _ptr(dbeta), B, n, T, C,
+                                          k, 5, _stream()), "conv0_bwd")
+    return dw, dgamma, dbeta
+
+
+# ---------------------------------------------------------------------------
+# positional conv embedding
+# ---------------------------------------------------------------------------
+def posconv_pack(weight, groups):
+    """weight [H, cg, k] fp32 (Conv1d layout, out-major) ->
+    (fwd pack, dgrad pack), each bf16 [G][k][K/8][N][8] with
+      fwd:   Wp[g][tap][c][o]   = w[g*cg+o, c, tap]
+      dgrad: Wp[g][tap''][o][c] = w[g*cg+o, c, k-1-tap'']."""
+    H, cg, k = weight.shape
+    w = weight.detach().view(groups, cg, cg, k)              # [g][o][c][tap]
+    fwd = w.permute(0, 3, 2, 1)                              # [g][tap][c(K)][o(N)]
+    dgr = w.flip(3).permute(0, 3, 1, 2)                      # [g][tap''][o(K)][c(N)]
+
+    def pack(m):  # [g][tap][K][N] -> [g][tap][K/8][N][8]
+        return m.reshape(groups, k, cg // 8, 8, cg).permute(0, 1, 2, 4, 3).to(BF16).contiguous()
+
+    return pack(fwd), pack(dgr)
+
+
+def posconv_fwd(x, w_fwd, bias, groups, ksize, add_input=True):
+    B, T, H = x.shape
+    y = torch.empty_like(x)
+    pre = torch.empty_like(x)
+    _lib.check(_L().smx_posconv_fwd(_ptr(x), _ptr(w_fwd), _ptr(bias), _ptr(y), _ptr(pre), B, T, H, groups, ksize,
+                                    1 if add_input else 0, _stream()), "posconv_fwd")
+    return y, pre
+
+
+def posconv_dgrad(dpre, w_dgrad, groups, ksize, residual=None):
+    B, T, H = dpre.shape
+    dx = torch.empty_like(dpre)
+    _lib.check(_L().smx_posconv_dgrad(_ptr(dpre), _ptr(w_dgrad), _ptr(residual), _ptr(dx), B, T, H, groups, ksize,
+                                      _stream()), "posconv_dgrad")
+    return dx
+
+
+def posconv_wgrad(dpre, x, groups, ksize):
+    """Returns dweight in Conv1d layout [H, cg, k] fp32."""
+    B, T, H = x.shape
+    cg = H // groups
+    dw = torch.zeros(groups, ksize, cg, cg, device=x.device, dtype=torch.float32)  # [g][tap][o][c]
+    _lib.check(_L().smx_posconv_wgrad(_ptr(dpre), _ptr(x), _ptr(dw), B, T, H, groups, ksize, _stream()),
+               "posconv_wgrad")
+    return dw.permute(0, 2, 3, 1).reshape(H, cg, ksize).contiguous()
+
+
+# ---------------------------------------------------------------------------
+# embeddings
+# ---------------------------------------------------------------------------
+def embed_fwd(ids, tok_emb, pos_emb, x_in, batch, t, dim, scale=1.0, pos_offset=0, t_start=0, device=None):
+    out = torch.empty(batch, t, dim, device=device, dtype=BF16)
+    _lib.check(_L().smx_embed_fwd(_ptr(ids), _ptr(tok_emb), _ptr(pos_emb), _ptr(x_in), _ptr(out), batch, t, dim, scale,
+                                  pos_offset, t_start, _stream()), "embed_fwd")
+    return out
+
+
+def embed_bwd(ids, dout, d_tok, d_pos, scale=1.0, pos_offset=0):
+    B, T, D = dout.shape
+    _lib.check(_L().smx_embed_bwd(_ptr(ids), _ptr(dout), _ptr(d_tok), _ptr(d_pos), B, T, D, scale, pos_offset,
+                                  _stream()), "embed_bwd")
+
+
+# ---------------------------------------------------------------------------
+# LM head + cross entropy
+# ---------------------------------------------------------------------------
+def lmhead_ce_fwd(h, emb16, bias, labels, logit_scale=1.0, ignore_index=-100):
+    """h [M, D] bf16, emb16 [V, D] bf16, labels [M] int64 -> lse, argmax, row_loss, loss_sum, count"""
+    M, D = h.shape
+    V = emb16.shape[0]
+    L = _L()
+    ws = torch.empty(L.smx_lmhead_ws_bytes(M, V) // 4 + 4, device=h.device, dtype=torch.float32)
+    lse = torch.empty(M, device=h.device, dtype=torch.float32)
+    argmax = torch.empty(M, device=h.device, dtype=torch.int64)
+    row_loss = torch.empty(M, device=h.device, dtype=torch.float32)
+    acc = torch.zeros(2, device=h.device, dtype=torch.float32)
+    _lib.check(L.smx_lmhead_ce_fwd(_ptr(h), _ptr(emb16), _ptr(bias), _ptr(labels), _ptr(lse), _ptr(argmax),
+                                   _ptr(row_loss), _ptr(acc), _ptr(acc, 1), _ptr(ws), M, D, V, logit_scale,
+                                   ignore_index, _stream()), "lmhead_ce_fwd")
+    return lse, argmax, row_loss, acc
+
+
+def lmhead_dlogits(h, emb16, bias, labels, lse, coef, buf, v0, vn, logit_scale=1.0):
+    M, D = h.shape
+    V = emb16.shape[0]
+    _lib.check(_L().smx_lmhead_dlogits(_ptr(h), _ptr(emb16), _ptr(bias), _ptr(labels), _ptr(lse), _ptr(coef),
+                                       _ptr(buf), buf.stride(0), M, D, V, v0, vn, logit_scale, _stream()),
+               "lmhead_dlogits")
+
+
+def gemm_nn_acc_f32(a, a_cols, w_rows_view, out_f32, alpha=1.0, accumulate=True):
+    """out_f32[M, K] (+)= a[M, :a_cols] @ w_rows_view[a_cols, K]  (a may have a larger row stride)."""
+    M = a.shape[0]
+    K = w_rows_view.shape[1]
+    g = SmxGemm()
+    g.mode, g.out_dtype = GEMM_NN, OUT_F32
+    g.a = _view(a, a_cols, M, 1, a.stride(0), M * a.stride(0))
+    g.b = _view(w_rows_view, K, a_cols, 1, w_rows_view.stride(0), a_cols * w_rows_view.stride(0))
+    g.m, g.n, g.k, g.batches = M, K, a_cols, 1
+    _set_seg(g, 1, a_cols)
+    g.accumulate = 1 if accumulate else 0
+    _epilogue(g, out_f32, K, M * K, None, ACT_NONE, None, None, None, None, alpha)
+    _run_gemm(g)
+
+
+def gemm_tn_into(a, a_cols, x, out_rows_view, alpha=1.0):
+    """out_rows_view[a_cols, K] (fp32, plain store) = a[M, :a_cols]^T @ x[M, K]."""
+    M = a.shape[0]
+    K = x.shape[1]
+    g = SmxGemm()
+    g.mode, g.out_dtype = GEMM_TN, OUT_F32
+    g.a = _view(a, a_cols, M, 1, a.stride(0), M * a.stride(0))
+    g.b = _view(x, K, M, 1, x.stride(0), M * x.stride(0))
+    g.m, g.n, g.k, g.batches = a_cols, K, M, 1
+    _set_seg(g, 1, K)
+    g.split_k = 1
+    g.c = _ptr(out_rows_view)
+    g.c_row_stride, g.c_batch_stride = out_rows_view.stride(0), a_cols * out_rows_view.stride(0)
+    g.alpha = alpha
+    _run_gemm(g)
+
+
+# ---------------------------------------------------------------------------
+# weighted layer sum
+# ---------------------------------------------------------------------------
+def weighted_sum_fwd(xs, w):
+    n = xs[0].numel()
+    out = torch.empty_like(xs[0])
+    arr = (ctypes.c_void_p * len(xs))(*[x.data_ptr() for x in xs])
+    _lib.check(_L().smx_weighted_sum_fwd(arr, _ptr(w), _ptr(out), len(xs), n, _stream()), "wsum_fwd")
+    return out
+
+
+def weighted_sum_bwd_w(xs, dout):
+    n = xs[0].numel()
+    dw = torch.zeros(len(xs), device=dout.device, dtype=torch.float32)
+    arr = (ctypes.c_void_p * len(xs))(*[x.data_ptr() for x in xs])
+    _lib.check(_L().smx_weighted_sum_bwd_w(arr, _ptr(dout), _ptr(dw), len(xs), n, _stream()), "wsum_bwd")
+    return dw

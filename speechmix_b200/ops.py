@@ -1,0 +1,495 @@
+"""Autograd functions of the hot path.  Every forward AND backward here is a
+sequence of calls into libspeechmix_sm100.so (``kernels.py``); torch is used for
+tensor allocation, views and the autograd graph only.
+
+Parameters stay fp32 ``nn.Parameter``s (state_dict-compatible with the
+reference); bf16 / packed copies are cached per parameter version
+(``WeightCache``) and refreshed after an optimizer step.  Activations are bf16.
+Weight gradients come out of the TN GEMM in fp32.
+"""
+import math
+
+import torch
+
+from . import kernels as K
+from .kernels import ACT_DGELU, ACT_DRELU, ACT_GELU, ACT_NONE, ACT_RELU, BF16
+
+
+class WeightCache:
+    """bf16 / packed copies of fp32 parameters, keyed by tensor identity + version."""
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, key_tensors, kind, build):
+        if not isinstance(key_tensors, (tuple, list)):
+            key_tensors = (key_tensors,)
+        key = (kind,) + tuple(id(t) for t in key_tensors)
+        ver = tuple((t._version, t.data_ptr()) for t in key_tensors)
+        hit = self._store.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        with torch.no_grad():
+            val = build(*key_tensors)
+        self._store[key] = (ver, val)
+        return val
+
+    def clear(self):
+        self._store.clear()
+
+
+CACHE = WeightCache()
+
+
+def w16(p):
+    return CACHE.get(p, "bf16", lambda t: K.to_bf16(t))
+
+
+def cat16(ps):
+    return CACHE.get(tuple(ps), "cat16", lambda *ts: K.to_bf16(torch.cat([t.detach() for t in ts], 0)))
+
+
+def cat32(ps):
+    return CACHE.get(tuple(ps), "cat32", lambda *ts: torch.cat([t.detach().float() for t in ts], 0).contiguous())
+
+
+def conv_packed16(p):
+    return CACHE.get(p, "convpack", lambda t: K.pack_conv_weight(t))
+
+
+def _act_codes(name):
+    if name in ("gelu", "gelu_new"):
+        return ACT_GELU, ACT_DGELU
+    if name == "relu":
+        return ACT_RELU, ACT_DRELU
+    raise ValueError("unsupported activation %r" % (name,))
+
+
+def _need(ctx, i):
+    return ctx.needs_input_grad[i]
+
+
+# ---------------------------------------------------------------------------
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, rms_only):
+        x = x.contiguous()
+        y, _, mean, rstd = K.layernorm_fwd(x, gamma.detach(), None if beta is None else beta.detach(), eps,
+                                           rms_only=rms_only)
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        ctx.rms_only = rms_only
+        ctx.has_beta = beta is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        dx, dg, db = K.layernorm_bwd(dy.contiguous(), x, gamma.detach(), mean, rstd, rms_only=ctx.rms_only,
+                                     want_dbeta=ctx.has_beta)
+        return dx, dg, db, None, None
+
+
+def layer_norm(x, gamma, beta, eps=1e-5, rms_only=False):
+    return LayerNormFn.apply(x, gamma, beta, eps, rms_only)
+
+
+# ---------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b (+ residual)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual):
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1])
+        wb = w16(weight)
+        r2 = residual.reshape(-1, weight.shape[0]) if residual is not None else None
+        y = K.linear_fwd(x2, wb, None if bias is None else bias.detach(), residual=r2)
+        ctx.save_for_backward(x2, wb)
+        ctx.shp = shp
+        ctx.has_bias = bias is not None
+        ctx.has_res = residual is not None
+        return y.view(*shp[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, wb = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
+        dx = K.linear_dgrad(dy2, wb).view(ctx.shp) if _need(ctx, 0) else None
+        dw = K.linear_wgrad(dy2, x2) if _need(ctx, 1) else None
+        db = K.colsum(dy2) if (ctx.has_bias and _need(ctx, 2)) else None
+        dres = dy if ctx.has_res else None
+        return dx, dw, db, dres
+
+
+def linear(x, weight, bias=None, residual=None):
+    return LinearFn.apply(x, weight, bias, residual)
+
+
+# ---------------------------------------------------------------------------
+class AttnBlockFn(torch.autograd.Function):
+    """(self- or cross-) attention sub-block with its residual and LayerNorm.
+
+      post-LN:  y = LN(x + Wo.attn(q(x), kv(src)) + bo)          (wav2vec2-base, BART)
+      pre-LN :  y = x + Wo.attn(q(LN(x)), kv(LN(x) | src)) + bo   (stable-LN wav2vec2/HuBERT, mBART)
+
+    hf:models/wav2vec2/modeling_wav2vec2.py:466-549,576-655 ; hf:models/bart/modeling_bart.py:143-391 ;
+    hf:models/mbart/modeling_mbart.py:274-430.
+    inputs: x, src (None for self-attention), cfg, q_w,q_b,k_w,k_b,v_w,v_b,o_w,o_b, ln_w, ln_b
+    """
+
+    @staticmethod
+    def forward(ctx, x, src, cfg, q_w, q_b, k_w, k_b, v_w, v_b, o_w, o_b, ln_w, ln_b):
+        heads, causal, pre_ln, eps = cfg["heads"], cfg["causal"], cfg["pre_ln"], cfg["eps"]
+        scale = cfg.get("scale", 1.0 / math.sqrt(64))
+        B, T, H = x.shape
+        x2 = x.reshape(B * T, H)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        saved = {}
+        if pre_ln:
+            n, _, mean, rstd = K.layernorm_fwd(x2, ln_w.detach(), ln_b.detach(), eps)
+            a_in = n
+        else:
+            a_in = x2
+        if src is None:
+            wqkv = cat16((q_w, k_w, v_w))
+            bqkv = cat32((q_b, k_b, v_b)) if q_b is not None else None
+            qkv = K.linear_fwd(a_in, wqkv, bqkv).view(B, T, 3 * H)
+            q, k, v = qkv[..., :H], qkv[..., H:2 * H], qkv[..., 2 * H:]
+            kv_src2 = None
+            Ts = T
+        else:
+            Bs, Ts, Hs = src.shape
+            src2 = src.reshape(Bs * Ts, Hs)
+            if not src2.is_contiguous():
+                src2 = src2.contiguous()
+            q = K.linear_fwd(a_in, w16(q_w), None if q_b is None else q_b.detach()).view(B, T, H)
+            wkv = cat16((k_w, v_w))
+            bkv = cat32((k_b, v_b)) if k_b is not None else None
+            kv = K.linear_fwd(src2, wkv, bkv).view(Bs, Ts, 2 * H)
+            k, v = kv[..., :H], kv[..., H:]
+            qkv = (q, kv)
+            kv_src2 = src2
+        o, lse = K.attn_fwd(q, k, v, heads, causal=causal, scale=scale)
+        s = K.linear_fwd(o.view(B * T, H), w16(o_w), None if o_b is None else o_b.detach(), residual=x2)
+        if pre_ln:
+            y = s
+            ctx.save_for_backward(x2, n, mean, rstd, o, lse, kv_src2, ln_w, *(qkv if src is not None else (qkv,)))
+        else:
+            y, _, mean, rstd = K.layernorm_fwd(s, ln_w.detach(), ln_b.detach(), eps)
+            ctx.save_for_backward(x2, s, mean, rstd, o, lse, kv_src2, ln_w, *(qkv if src is not None else (qkv,)))
+        ctx.cfg = dict(cfg, scale=scale)
+        ctx.dims = (B, T, H, Ts)
+        ctx.cross = src is not None
+        ctx.wrefs = (q_w, k_w, v_w, o_w)
+        ctx.has_bias = q_b is not None
+        return y.view(B, T, H)
+
+    @staticmethod
+    def backward(ctx, dy):
+        cfg = ctx.cfg
+        heads, causal, pre_ln, scale = cfg["heads"], cfg["causal"], cfg["pre_ln"], cfg["scale"]
+        B, T, H, Ts = ctx.dims
+        q_w, k_w, v_w, o_w = ctx.wrefs
+        sv = ctx.saved_tensors
+        x2, a, mean, rstd, o, lse, kv_src2, ln_w = sv[:8]
+        dy2 = dy.reshape(B * T, H).contiguous()
+        if pre_ln:
+            ds = dy2
+            a_in = a          # normalised input
+        else:
+            ds, dlnw, dlnb = K.layernorm_bwd(dy2, a, ln_w.detach(), mean, rstd)
+            a_in = x2
+        o2 = o.view(B * T, H)
+        d_ob = K.colsum(ds) if ctx.has_bias else None
+        d_ow = K.linear_wgrad(ds, o2) if _need(ctx, 9) else None
+        do = K.linear_dgrad(ds, w16(o_w)).view(B, T, H)
+        dsrc = None
+        if not ctx.cross:
+            qkv = sv[8]
+            q, k, v = qkv[..., :H], qkv[..., H:2 * H], qkv[..., 2 * H:]
+            dqkv = torch.empty_like(qkv)
+            K.attn_bwd(do, q, k, v, o, lse, heads, causal=causal, scale=scale, dq=dqkv[..., :H],
+                       dk=dqkv[..., H:2 * H], dv=dqkv[..., 2 * H:])
+            dqkv2 = dqkv.view(B * T, 3 * H)
+            need_w = _need(ctx, 3) or _need(ctx, 5) or _need(ctx, 7)
+            dwqkv = K.linear_wgrad(dqkv2, a_in) if need_w else None
+            dbqkv = K.colsum(dqkv2) if (ctx.has_bias and need_w) else None
+            wqkv = cat16((q_w, k_w, v_w))
+            d_in = K.linear_dgrad(dqkv2, wqkv, residual=None if pre_ln else ds)
+            dq_w, dk_w, dv_w = (dwqkv[:H], dwqkv[H:2 * H], dwqkv[2 * H:]) if need_w else (None, None, None)
+            dq_b, dk_b, dv_b = (dbqkv[:H], dbqkv[H:2 * H], dbqkv[2 * H:]) if dbqkv is not None else (None, None, None)
+        else:
+            q, kv = sv[8], sv[9]
+            k, v = kv[..., :H], kv[..., H:]
+            dq = torch.empty_like(q)
+            dkv = torch.empty_like(kv)
+            K.attn_bwd(do, q, k, v, o, lse, heads, causal=causal, scale=scale, dq=dq, dk=dkv[..., :H], dv=dkv[..., H:])
+            dq2 = dq.view(B * T, H)
+            dkv2 = dkv.view(-1, 2 * H)
+            need_q = _need(ctx, 3)
+            need_kv = _need(ctx, 5) or _need(ctx, 7)
+            dq_w = K.linear_wgrad(dq2, a_in) if need_q else None
+            dq_b = K.colsum(dq2) if (ctx.has_bias and need_q) else None
+            dwkv = K.linear_wgrad(dkv2, kv_src2) if need_kv else None
+            dbkv = K.colsum(dkv2) if (ctx.has_bias and need_kv) else None
+            dk_w, dv_w = (dwkv[:H], dwkv[H:]) if need_kv else (None, None)
+            dk_b, dv_b = (dbkv[:H], dbkv[H:]) if dbkv is not None else (None, None)
+            d_in = K.linear_dgrad(dq2, w16(q_w), residual=None if pre_ln else ds)
+            if _need(ctx, 1):
+                dsrc = K.linear_dgrad(dkv2, cat16((k_w, v_w))).view(-1, Ts, kv_src2.shape[1])
+        if pre_ln:
+            dx, dlnw, dlnb = K.layernorm_bwd(d_in, x2, ln_w.detach(), mean, rstd, dres=ds)
+        else:
+            dx = d_in
+        return (dx.view(B, T, H), dsrc, None, dq_w, dq_b, dk_w, dk_b, dv_w, dv_b, d_ow, d_ob, dlnw, dlnb)
+
+
+class FFNBlockFn(torch.autograd.Function):
+    """post-LN: y = LN(x + W2.act(W1 x + b1) + b2);  pre-LN: y = x + W2.act(W1 LN(x) + b1) + b2.
+    hf:...wav2vec2.py:552-573 ; hf:...bart.py:296-309."""
+
+    @staticmethod
+    def forward(ctx, x, cfg, w1, b1, w2, b2, ln_w, ln_b):
+        pre_ln, eps = cfg["pre_ln"], cfg["eps"]
+        act, dact = _act_codes(cfg.get("act", "gelu"))
+        shp = x.shape
+        H = shp[-1]
+        x2 = x.reshape(-1, H)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        if pre_ln:
+            n, _, mean, rstd = K.layernorm_fwd(x2, ln_w.detach(), ln_b.detach(), eps)
+            a_in = n
+        else:
+            a_in = x2
+        h, pre = K.linear_fwd(a_in, w16(w1), None if b1 is None else b1.detach(), act=act, want_pre=True)
+        s = K.linear_fwd(h, w16(w2), None if b2 is None else b2.detach(), residual=x2)
+        if pre_ln:
+            y = s
+            ctx.save_for_backward(x2, n, mean, rstd, pre, h, ln_w)
+        else:
+            y, _, mean, rstd = K.layernorm_fwd(s, ln_w.detach(), ln_b.detach(), eps)
+            ctx.save_for_backward(x2, s, mean, rstd, pre, h, ln_w)
+        ctx.pre_ln, ctx.dact, ctx.shp = pre_ln, dact, shp
+        ctx.wrefs = (w1, w2)
+        ctx.has_bias = b1 is not None
+        return y.view(shp)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, a, mean, rstd, pre, h, ln_w = ctx.saved_tensors
+        w1, w2 = ctx.wrefs
+        H = ctx.shp[-1]
+        dy2 = dy.reshape(-1, H).contiguous()
+        if ctx.pre_ln:
+            ds, a_in = dy2, a
+        else:
+            ds, dlnw, dlnb = K.layernorm_bwd(dy2, a, ln_w.detach(), mean, rstd)
+            a_in = x2
+        db2 = K.colsum(ds) if ctx.has_bias else None
+        dw2 = K.linear_wgrad(ds, h) if _need(ctx, 4) else None
+        dpre = K.linear_dgrad(ds, w16(w2), act=ctx.dact, aux_in=pre)
+        db1 = K.colsum(dpre) if ctx.has_bias else None
+        dw1 = K.linear_wgrad(dpre, a_in) if _need(ctx, 2) else None
+        d_in = K.linear_dgrad(dpre, w16(w1), residual=None if ctx.pre_ln else ds)
+        if ctx.pre_ln:
+            dx, dlnw, dlnb = K.layernorm_bwd(d_in, x2, ln_w.detach(), mean, rstd, dres=ds)
+        else:
+            dx = d_in
+        return dx.view(ctx.shp), None, dw1, db1, dw2, db2, dlnw, dlnb
+
+
+# ---------------------------------------------------------------------------
+class FeatureEncoderGroupFn(torch.autograd.Function):
+    """wav2vec2 / HuBERT conv feature encoder, feat_extract_norm="group", conv_bias=False:
+    conv0 + GroupNorm + GELU (fused, CUDA cores), then k=3/2 stride-2 convs + GELU as
+    implicit tcgen05 GEMMs.  hf:...wav2vec2.py:254-323, 382-419.
+    inputs: audio, kernel sizes, w0, gn_w, gn_b, w1..w6   ->  [B, T, C] bf16 (channels-last)"""
+
+    @staticmethod
+    def forward(ctx, audio, ks, w0, gn_w, gn_b, *ws):
+        audio = audio.contiguous().float()
+        y, stats, moments = K.conv0_fwd(audio, w0.detach().contiguous(), gn_w.detach(), gn_b.detach())
+        acts, pres = [y], []
+        for w, k in zip(ws, ks):
+            y, pre = K.conv_s2_fwd(y, conv_packed16(w), k, act=ACT_GELU, want_pre=True)
+            acts.append(y)
+            pres.append(pre)
+        ctx.save_for_backward(audio, w0, gn_w, gn_b, stats, moments, *acts[:-1], *pres)
+        ctx.ks, ctx.ws, ctx.n = ks, ws, len(ws)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        sv = ctx.saved_tensors
+        audio, w0, gn_w, gn_b, stats, moments = sv[:6]
+        n = ctx.n
+        acts, pres = sv[6:6 + n], sv[6 + n:6 + 2 * n]
+        dpre = K.dact(dy.contiguous(), pres[n - 1], ACT_GELU)
+        dws = [None] * n
+        for i in range(n - 1, -1, -1):
+            w, k = ctx.ws[i], ctx.ks[i]
+            x_in = acts[i]
+            if ctx.needs_input_grad[5 + i]:
+                dws[i] = K.unpack_conv_wgrad(K.conv_s2_wgrad(dpre, x_in, k), x_in.shape[2], k)
+            if i > 0:
+                dpre = K.conv_s2_dgrad(dpre, conv_packed16(w), k, x_in.shape[1], act=ACT_DGELU, aux_in=pres[i - 1])
+            else:
+                dpre = K.conv_s2_dgrad(dpre, conv_packed16(w), k, x_in.shape[1])
+        dw0, dg, db = K.conv0_bwd(audio, w0.detach().contiguous(), gn_w.detach(), gn_b.detach(), stats, moments, dpre)
+        return (None, None, dw0, dg, db, *dws)
+
+
+class ConvS2Fn(torch.autograd.Function):
+    """Conv1d(C -> N, k, stride 2, bias) on channels-last input, no activation
+    (the down_scale length adapters, ref:speechmix/hf_model.py:253-266, 426-427)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, k):
+        B, T, C = x.shape
+        xa = K.alloc_act(B, T, C, x.device)
+        xa.copy_(x)
+        wp = conv_packed16(weight)
+        y = K.conv_s2_fwd(xa, wp, k, bias=None if bias is None else bias.detach())
+        ctx.save_for_backward(xa, wp)
+        ctx.k = k
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xa, wp = ctx.saved_tensors
+        k = ctx.k
+        B, T_out, N = dy.shape
+        dya = K.alloc_act(B, T_out, N, dy.device)
+        dya.copy_(dy)
+        dx = K.conv_s2_dgrad(dya, wp, k, xa.shape[1]) if _need(ctx, 0) else None
+        dw = K.unpack_conv_wgrad(K.conv_s2_wgrad(dya, xa, k), xa.shape[2], k) if _need(ctx, 1) else None
+        db = K.colsum(dya.view(B * T_out, N)) if _need(ctx, 2) else None
+        return dx, dw, db, None
+
+
+class PosConvFn(torch.autograd.Function):
+    """y = x + GELU(grouped_conv(x) + b)[drop last frame]   hf:...wav2vec2.py:326-379, 690-693."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, groups):
+        x = x.contiguous()
+        ksize = weight.shape[2]
+        wf, wd = CACHE.get(weight, "posconv%d" % groups, lambda t: K.posconv_pack(t, groups)) \
+            if not weight.requires_grad or weight.is_leaf else K.posconv_pack(weight, groups)
+        y, pre = K.posconv_fwd(x, wf, bias.detach(), groups, ksize, add_input=True)
+        ctx.save_for_backward(x, pre, wd)
+        ctx.groups, ctx.ksize = groups, ksize
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, pre, wd = ctx.saved_tensors
+        dy = dy.contiguous()
+        dpre = K.dact(dy, pre, ACT_GELU)
+        dx = K.posconv_dgrad(dpre, wd, ctx.groups, ctx.ksize, residual=dy)
+        dw = K.posconv_wgrad(dpre, x, ctx.groups, ctx.ksize) if _need(ctx, 1) else None
+        db = K.colsum(dpre.view(-1, dpre.shape[-1])) if _need(ctx, 2) else None
+        return dx, dw, db, None
+
+
+# ---------------------------------------------------------------------------
+class EmbedFn(torch.autograd.Function):
+    """out = tok[ids]*scale (ids given) + x_in (given) + pos[t + offset]   (bf16)
+    hf:...bart.py:74-111, 508-530, 620-640."""
+
+    @staticmethod
+    def forward(ctx, ids, x_in, tok, pos, scale, pos_offset, t_start):
+        if ids is not None:
+            B, T = ids.shape
+            dev = ids.device
+        else:
+            B, T = x_in.shape[:2]
+            dev = x_in.device
+        D = pos.shape[1] if pos is not None else tok.shape[1]
+        out = K.embed_fwd(ids, None if tok is None else tok.detach(), None if pos is None else pos.detach(),
+                          None if x_in is None else x_in.contiguous(), B, T, D, scale, pos_offset, t_start, device=dev)
+        ctx.save_for_backward(ids)
+        ctx.meta = (scale, pos_offset + t_start, None if tok is None else tok.shape, None if pos is None else pos.shape,
+                    x_in is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (ids,) = ctx.saved_tensors
+        scale, off, tok_shape, pos_shape, has_x = ctx.meta
+        dout = dout.contiguous()
+        d_tok = torch.zeros(tok_shape, device=dout.device, dtype=torch.float32) if (tok_shape and _need(ctx, 2)) else None
+        d_pos = torch.zeros(pos_shape, device=dout.device, dtype=torch.float32) if (pos_shape and _need(ctx, 3)) else None
+        if d_tok is not None or d_pos is not None:
+            K.embed_bwd(ids, dout, d_tok, d_pos, scale, off)
+        return None, (dout if has_x else None), d_tok, d_pos, None, None, None
+
+
+# ---------------------------------------------------------------------------
+LM_CHUNK = 8192
+
+
+class LMHeadCEFn(torch.autograd.Function):
+    """(loss, argmax ids) = CE(h E^T * s + b, labels) with the [rows, vocab] logits never
+    materialised.  hf:...bart.py:940-947 ; ref:speechmix/hf_model.py:446.
+    Returns loss (mean over labels != -100; 0-dim fp32) and argmax ids [rows] int64."""
+
+    @staticmethod
+    def forward(ctx, h, emb, bias, labels, logit_scale):
+        shp = h.shape
+        h2 = h.reshape(-1, shp[-1]).contiguous()
+        e16 = w16(emb)
+        lab = labels.reshape(-1).contiguous()
+        b = None if bias is None else bias.detach().reshape(-1).float().contiguous()
+        lse, argmax, row_loss, acc = K.lmhead_ce_fwd(h2, e16, b, lab, logit_scale)
+        loss = acc[0] / acc[1]
+        ctx.save_for_backward(h2, e16, lab, lse, acc)
+        ctx.bias = b
+        ctx.scale = logit_scale
+        ctx.shp = shp
+        ctx.emb_shape = emb.shape
+        ctx.mark_non_differentiable(argmax)
+        return loss, argmax.view(shp[:-1])
+
+    @staticmethod
+    def backward(ctx, dloss, _unused):
+        h2, e16, lab, lse, acc = ctx.saved_tensors
+        M, D = h2.shape
+        V = e16.shape[0]
+        coef = ((lab != -100).float() * (dloss.float() / acc[1])).contiguous()
+        need_h, need_e = _need(ctx, 0), _need(ctx, 1)
+        dh = torch.zeros(M, D, device=h2.device, dtype=torch.float32) if need_h else None
+        dE = torch.empty(V, D, device=h2.device, dtype=torch.float32) if need_e else None
+        buf = torch.empty(M, LM_CHUNK, device=h2.device, dtype=BF16)
+        for v0 in range(0, V, LM_CHUNK):
+            vn = min(LM_CHUNK, V - v0)
+            K.lmhead_dlogits(h2, e16, ctx.bias, lab, lse, coef, buf, v0, vn, ctx.scale)
+            if need_h:
+                K.gemm_nn_acc_f32(buf, vn, e16[v0:v0 + vn], dh, alpha=ctx.scale, accumulate=True)
+            if need_e:
+                K.gemm_tn_into(buf, vn, h2, dE[v0:v0 + vn], alpha=ctx.scale)
+        dh16 = K.to_bf16(dh).view(ctx.shp) if need_h else None
+        return dh16, dE, None, None, None
+
+
+# ---------------------------------------------------------------------------
+class WeightedSumFn(torch.autograd.Function):
+    """out = sum_l softmax(w)[l] * x_l   (ref:speechmix/hf_model.py:411-423); takes normalised weights."""
+
+    @staticmethod
+    def forward(ctx, norm_w, *xs):
+        xs = [x.contiguous() for x in xs]
+        out = K.weighted_sum_fwd(xs, norm_w.detach().float().contiguous())
+        ctx.save_for_backward(norm_w, *xs)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        norm_w, *xs = ctx.saved_tensors
+        dout = dout.contiguous()
+        dw = K.weighted_sum_bwd_w(xs, dout)
+        wl = norm_w.detach().float()
+        dxs = [K.weighted_sum_fwd([dout], wl[l:l + 1].contiguous()) for l in range(len(xs))]
+        return (dw, *dxs)
