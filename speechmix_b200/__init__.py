@@ -1,0 +1,13 @@
+"""speechmix_b200 -- B200-native (sm_100a) implementation of the SpeechMix speech-to-text hot path.
+
+    from speechmix_b200 import SpeechMixEED
+    model = SpeechMixEED(speech_ckpt_dir, text_ckpt_dir, down_scale=2).cuda()
+    out = model(input_values, labels=labels)      # out["loss"], out["logits"] (argmax ids)
+
+The CUDA library must be built first (``python -m speechmix_b200.build``); there is no fallback.
+"""
+from .model import (HFSpeechMixEED, HFSpeechMixFixed, SpeechMixConfig, SpeechMixEED, SpeechMixFixed,  # noqa: F401
+                    handle_decoder_input_none, shift_tokens_right)
+
+__all__ = ["SpeechMixEED", "SpeechMixFixed", "HFSpeechMixEED", "HFSpeechMixFixed", "SpeechMixConfig",
+           "shift_tokens_right", "handle_decoder_input_none"]

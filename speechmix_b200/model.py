@@ -1,0 +1,252 @@
+"""SpeechMix model classes on the B200-native kernels -- the drop-in boundary.
+
+Same constructor surface, attributes, ``forward`` contract and ``state_dict`` layout as the
+reference's ``HFSpeechMixEED`` / ``HFSpeechMixFixed`` / ``HFSpeechMixAdapter`` / ``HFSpeechMixSelf``
+(ref:speechmix/hf_model.py:185-583); every FLOP runs in libspeechmix_sm100.so.  There is no CPU
+path: constructing a model without the built library, or running it without a B200, raises.
+"""
+import math
+
+import torch
+from torch import nn
+
+from . import _lib, ops
+from .speech import SpeechOutput, speech_from_pretrained
+from .text import text_from_pretrained
+
+
+def handle_decoder_input_none(decoder_config, batch=1, device="cpu"):
+    """ref:speechmix/hf_model.py:20-22"""
+    return torch.tensor([[decoder_config.decoder_start_token_id]] * batch).to(device)
+
+
+def shift_tokens_right(input_ids, pad_token_id, decoder_start_token_id):
+    """ref:speechmix/hf_model.py:25-34"""
+    shifted = input_ids.new_zeros(input_ids.shape)
+    shifted[:, 1:] = input_ids[:, :-1].clone()
+    shifted[:, 0] = decoder_start_token_id
+    assert pad_token_id is not None, "self.model.config.pad_token_id has to be defined."
+    shifted.masked_fill_(shifted == -100, pad_token_id)
+    return shifted
+
+
+class SpeechMixConfig:
+    """Composite config (ref:speechmix/hf_model.py:37-79): ``encoder`` / ``decoder`` sub-configs."""
+
+    model_type = "speechmix"
+
+    def __init__(self, encoder, decoder):
+        self.encoder = encoder
+        self.decoder = decoder
+        self.is_encoder_decoder = True
+        self.pad_token_id = decoder.pad_token_id
+        self.decoder_start_token_id = decoder.decoder_start_token_id
+
+    def to_dict(self):
+        return {"encoder": self.encoder.to_dict(), "decoder": self.decoder.to_dict(), "model_type": self.model_type}
+
+
+DEFAULT_FIXED_EXCEPT = ["layer_norm", "encoder_attn", "enc_to_dec_proj", "length_adapter", "layernorm_embedding",
+                        "attention"]
+
+
+class SpeechMixEED(nn.Module):
+    """ref:speechmix/hf_model.py:185-447 (HFSpeechMixEED)."""
+
+    main_input_name = "input_values"
+
+    def __init__(self, speech_model_config, nlp_model_config, share_layer_ratio=0, down_scale=8, weighted_sum=False,
+                 fixed_parameters=False, fixed_except=None, tokenizer=None, **kwargs):
+        super().__init__()
+        _lib.load()  # fail loudly when the CUDA library has not been built
+        # ref :206-220 -- `speech_model_config` / `nlp_model_config` are checkpoint directories / hub
+        # names in the reference; config objects (random init) are accepted too for offline use.
+        self.encoder_model = speech_from_pretrained(speech_model_config)
+        self.decoder_model = text_from_pretrained(nlp_model_config)
+        self.config = SpeechMixConfig(self.encoder_model.config, self.decoder_model.config)
+        self.tokenizer = tokenizer
+        if tokenizer is None and isinstance(nlp_model_config, str):
+            try:
+                from transformers import AutoTokenizer
+                self.tokenizer = AutoTokenizer.from_pretrained(nlp_model_config)
+            except Exception:  # tokenizer files are optional for training on pre-tokenised labels
+                self.tokenizer = None
+        self.weighted_sum = weighted_sum
+
+        # ref :222-229
+        enc = self.decoder_model.base_model.encoder
+        num_nlp_encoder_layers = len(enc.layers) if hasattr(enc, "layers") else len(getattr(enc, "block", []))
+        # ref :231-251
+        n_layers = len(self.encoder_model.encoder.layers)
+        print("Before layer sharing num_speech_encoder_layers", n_layers)
+        remove_layers = int(n_layers * share_layer_ratio) if share_layer_ratio != 0 else 0
+        self.encoder_model.encoder.layers = self.encoder_model.encoder.layers[:n_layers - remove_layers]
+        self.num_speech_encoder_layers = len(self.encoder_model.encoder.layers)
+        print("After layer sharing ", "num_speech_encoder_layers", self.num_speech_encoder_layers,
+              "num_nlp_encoder_layers", num_nlp_encoder_layers, "share_layer_ratio", share_layer_ratio,
+              "remove_layers", remove_layers)
+        # ref :253-266
+        self.downsize = down_scale
+        self.downloop = int(math.log(self.downsize, 2))
+        hs = self.encoder_model.config.hidden_size
+        if self.downsize > 1:
+            self.length_adapters = nn.Sequential(*[nn.Conv1d(hs, hs, kernel_size=2, stride=2)
+                                                   for _ in range(self.downloop)])
+        else:
+            self.length_adapters = nn.Sequential(nn.Identity())
+        # ref :268-272
+        if self.weighted_sum:
+            self.weights_sum = nn.Parameter(torch.zeros(self.num_speech_encoder_layers + 1))
+        self.enc_to_dec_proj = nn.Linear(hs, self.decoder_model.config.hidden_size)
+        self.custom_modules(**kwargs)
+        # ref :274-286
+        if fixed_parameters:
+            fixed_except = DEFAULT_FIXED_EXCEPT if fixed_except is None else fixed_except
+            self.encoder_model.eval()
+            self.decoder_model.eval()
+            for xcoder in (self.encoder_model.named_parameters, self.decoder_model.named_parameters):
+                for name, param in xcoder():
+                    if param.requires_grad:
+                        param.requires_grad = any(k in name for k in fixed_except)
+        # ref :288-302
+        self.list_grad = [n for n, p in self.named_parameters() if p.requires_grad]
+        self.list_no_grad = [n for n, p in self.named_parameters() if not p.requires_grad]
+        self.nlp_emb = self.decoder_model.get_input_embeddings()
+        self.speech_encoder_layer = len(self.encoder_model.encoder.layers)
+        self.nlp_encoder_layer = num_nlp_encoder_layers
+        self.decoder_outputs = None
+
+    # ------------------------------------------------------------------ reference API surface
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def get_encoder(self):
+        return self.encoder_model
+
+    def get_decoder(self):
+        return self.decoder_model
+
+    def prepare_decoder_input_ids_from_labels(self, labels):
+        return shift_tokens_right(labels, self.config.pad_token_id, self.config.decoder_start_token_id)
+
+    def prepare_inputs_for_generation(self, input_ids, past=None, attention_mask=None, use_cache=None,
+                                      encoder_outputs=None, **kwargs):
+        d = {"encoder_outputs": encoder_outputs, "attention_mask": attention_mask, "use_cache": use_cache,
+             "past_key_values": past, "decoder_input_ids": input_ids}
+        d.update(kwargs)
+        return d
+
+    def custom_modules(self, **kwargs):
+        return None
+
+    # ------------------------------------------------------------------ hot path
+    def cal_loss(self, inputs_embeds=None, text_input_ids=None, attention_mask=None, decoder_outputs=None,
+                 decoder_input_ids=None, labels=None, past_key_values=None, use_cache=None):
+        """ref:speechmix/hf_model.py:343-376"""
+        if past_key_values is None:
+            self.decoder_outputs = None
+        cached = decoder_outputs if decoder_outputs else self.decoder_outputs
+        if inputs_embeds is not None:
+            output = self.decoder_model(inputs_embeds=inputs_embeds, encoder_outputs=cached,
+                                        decoder_input_ids=decoder_input_ids, labels=labels)
+        elif text_input_ids is not None:
+            output = self.decoder_model(input_ids=text_input_ids, encoder_outputs=cached,
+                                        decoder_input_ids=decoder_input_ids, labels=labels)
+        else:
+            raise ValueError("cal_loss needs inputs_embeds or text_input_ids")
+        self.decoder_outputs = [output.encoder_last_hidden_state]
+        return output
+
+    def bridge(self, encoder_outputs, detail=None):
+        """weighted layer sum -> down_scale length adapters -> projector (ref :410-430)."""
+        x = encoder_outputs.last_hidden_state
+        if self.weighted_sum:
+            norm_weights = torch.softmax(self.weights_sum, dim=-1)  # L+1 scalars: torch autograd
+            if detail is not None:
+                detail["weighted_sum"] = norm_weights
+            x = ops.WeightedSumFn.apply(norm_weights, *encoder_outputs.hidden_states)
+        if detail is not None:
+            detail["shape_before_length_adapter"] = x.shape
+        if self.downsize > 1:
+            for conv in self.length_adapters:
+                x = ops.ConvS2Fn.apply(x, conv.weight, conv.bias, 2)
+        if detail is not None:
+            detail["shape_before_enc_dec_projector"] = x.shape
+        x = ops.linear(x, self.enc_to_dec_proj.weight, self.enc_to_dec_proj.bias)
+        if detail is not None:
+            detail["shape_after_enc_dec_projector"] = x.shape
+        return x
+
+    def forward(self, input_values=None, decoder_text_prompt=None, text_input_ids=None, decoder_input_ids=None,
+                labels=None, encoder_outputs=None, decoder_outputs=None, past_key_values=None, use_cache=None,
+                return_model_detail=True, output_attentions=None, output_hidden_states=None, return_dict=None,
+                **kwargs):
+        """ref:speechmix/hf_model.py:378-447.  Returns a mapping with ``loss`` and ``logits`` (= argmax
+        token ids, as the reference returns them at :446) plus the model-detail breadcrumbs."""
+        detail = {} if return_model_detail else None
+        if encoder_outputs is None:
+            encoder_outputs = self.encoder_model(input_values, output_hidden_states=True)
+        if decoder_input_ids is None and labels is None:
+            decoder_input_ids = handle_decoder_input_none(self.decoder_model.config,
+                                                          encoder_outputs.last_hidden_state.shape[0], device=self.device)
+        elif decoder_input_ids is None and labels is not None:
+            decoder_input_ids = shift_tokens_right(labels, self.decoder_model.config.pad_token_id,
+                                                   self.decoder_model.config.decoder_start_token_id)
+        inputs_embeds = self.bridge(encoder_outputs, detail)
+        if decoder_text_prompt is not None:
+            if isinstance(decoder_text_prompt, str):
+                ids = self.tokenizer(decoder_text_prompt, return_tensors="pt")["input_ids"].to(self.device)
+            else:
+                ids = decoder_text_prompt.to(self.device)
+            prompt = ops.EmbedFn.apply(ids, None, self.nlp_emb.weight, None, self.decoder_model.model.encoder.embed_scale, 0, 0)
+            inputs_embeds = torch.cat((prompt.expand(inputs_embeds.shape[0], -1, -1), inputs_embeds), 1)
+        outputs = self.cal_loss(inputs_embeds=inputs_embeds, decoder_outputs=decoder_outputs,
+                                text_input_ids=text_input_ids, decoder_input_ids=decoder_input_ids, labels=labels,
+                                past_key_values=past_key_values, use_cache=use_cache)
+        outputs["speech_last_hidden_state"] = encoder_outputs.last_hidden_state
+        outputs["inputs_embeds"] = inputs_embeds
+        if detail:
+            outputs.update(detail)
+            outputs["detail"] = detail
+        return outputs
+
+    @torch.no_grad()
+    def generate(self, input_values, max_length=32, decoder_text_prompt=None, eos_token_id=None, **kwargs):
+        """Greedy decode (ref:eval.py:12-13; loop semantics of ref:eval.ipynb cell 6): the speech
+        encoder, bridge and text encoder run once, the decoder is re-run on the growing prefix."""
+        cfg = self.decoder_model.config
+        eos = cfg.eos_token_id if eos_token_id is None else eos_token_id
+        enc = self.encoder_model(input_values, output_hidden_states=True)
+        B = input_values.shape[0]
+        dec = torch.full((B, 1), cfg.decoder_start_token_id, dtype=torch.long, device=self.device)
+        done = torch.zeros(B, dtype=torch.bool, device=self.device)
+        text_enc = None
+        for _ in range(max_length - 1):
+            out = self.forward(encoder_outputs=enc, decoder_input_ids=dec, decoder_text_prompt=decoder_text_prompt,
+                               decoder_outputs=text_enc, return_model_detail=False)
+            text_enc = [out.encoder_last_hidden_state]
+            nxt = out["logits"][:, -1]
+            dec = torch.cat([dec, nxt[:, None]], dim=1)
+            done |= nxt == eos
+            if bool(done.all()):
+                break
+        return dec
+
+
+class SpeechMixFixed(SpeechMixEED):
+    """ref:speechmix/hf_model.py:450-462"""
+
+    def custom_modules(self, fixed_speech=False, fixed_nlp=True, **kwargs):
+        self.encoder_model.eval()
+        self.decoder_model.eval()
+        if fixed_speech:
+            for _, p in self.encoder_model.named_parameters():
+                p.requires_grad = False
+        if fixed_nlp:
+            for _, p in self.decoder_model.named_parameters():
+                p.requires_grad = False
+
+
+HFSpeechMixEED = SpeechMixEED
+HFSpeechMixFixed = SpeechMixFixed

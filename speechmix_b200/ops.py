@@ -8,6 +8,7 @@ reference); bf16 / packed copies are cached per parameter version
 Weight gradients come out of the TN GEMM in fp32.
 """
 import math
+import weakref
 
 import torch
 
@@ -16,7 +17,8 @@ from .kernels import ACT_DGELU, ACT_DRELU, ACT_GELU, ACT_NONE, ACT_RELU, BF16
 
 
 class WeightCache:
-    """bf16 / packed copies of fp32 parameters, keyed by tensor identity + version."""
+    """bf16 / packed copies of fp32 parameters, keyed by tensor identity + version.
+    Entries hold weak references, so a recycled ``id()`` can never alias a dead tensor."""
 
     def __init__(self):
         self._store = {}
@@ -27,11 +29,13 @@ class WeightCache:
         key = (kind,) + tuple(id(t) for t in key_tensors)
         ver = tuple((t._version, t.data_ptr()) for t in key_tensors)
         hit = self._store.get(key)
-        if hit is not None and hit[0] == ver:
+        if hit is not None and hit[0] == ver and all(r() is t for r, t in zip(hit[2], key_tensors)):
             return hit[1]
         with torch.no_grad():
             val = build(*key_tensors)
-        self._store[key] = (ver, val)
+        if len(self._store) > 4096:
+            self._store = {k: v for k, v in self._store.items() if all(r() is not None for r in v[2])}
+        self._store[key] = (ver, val, tuple(weakref.ref(t) for t in key_tensors))
         return val
 
     def clear(self):
@@ -373,11 +377,12 @@ class PosConvFn(torch.autograd.Function):
     """y = x + GELU(grouped_conv(x) + b)[drop last frame]   hf:...wav2vec2.py:326-379, 690-693."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, groups):
+    def forward(ctx, x, weight, bias, groups, key_params):
         x = x.contiguous()
         ksize = weight.shape[2]
-        wf, wd = CACHE.get(weight, "posconv%d" % groups, lambda t: K.posconv_pack(t, groups)) \
-            if not weight.requires_grad or weight.is_leaf else K.posconv_pack(weight, groups)
+        # `weight` is usually recomputed every step from its weight-norm factors; the packed bf16
+        # copies are cached on the leaf parameters it derives from.
+        wf, wd = CACHE.get(tuple(key_params), "posconv%d" % groups, lambda *_: K.posconv_pack(weight, groups))
         y, pre = K.posconv_fwd(x, wf, bias.detach(), groups, ksize, add_input=True)
         ctx.save_for_backward(x, pre, wd)
         ctx.groups, ctx.ksize = groups, ksize
@@ -391,7 +396,7 @@ class PosConvFn(torch.autograd.Function):
         dx = K.posconv_dgrad(dpre, wd, ctx.groups, ctx.ksize, residual=dy)
         dw = K.posconv_wgrad(dpre, x, ctx.groups, ctx.ksize) if _need(ctx, 1) else None
         db = K.colsum(dpre.view(-1, dpre.shape[-1])) if _need(ctx, 2) else None
-        return dx, dw, db, None
+        return dx, dw, db, None, None
 
 
 # ---------------------------------------------------------------------------

@@ -1,0 +1,255 @@
+"""wav2vec2 / HuBERT speech encoder on the sm_100a kernels.
+
+Module / parameter names mirror ``transformers``' ``Wav2Vec2Model`` / ``HubertModel``
+(hf:models/wav2vec2/modeling_wav2vec2.py, hf:models/hubert/modeling_hubert.py) so that a
+reference ``state_dict`` loads unchanged; the ``torch.nn`` leaf modules are used as
+parameter containers only -- all arithmetic goes through ``ops.py`` -> libspeechmix_sm100.
+"""
+import os
+import types
+
+import torch
+from torch import nn
+
+from . import ops
+
+
+class SpeechOutput(dict):
+    """Mapping with attribute access (stands in for transformers' BaseModelOutput)."""
+
+    __getattr__ = dict.get
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+class _ConvLayer(nn.Module):
+    def __init__(self, cin, cout, k, stride, bias, norm):
+        super().__init__()
+        self.conv = nn.Conv1d(cin, cout, k, stride=stride, bias=bias)
+        if norm == "group":
+            self.layer_norm = nn.GroupNorm(num_groups=cout, num_channels=cout, affine=True)
+        elif norm == "layer":
+            self.layer_norm = nn.LayerNorm(cout, elementwise_affine=True)
+
+
+class FeatureEncoder(nn.Module):
+    """hf:...wav2vec2.py:382-419"""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        n = config.num_feat_extract_layers
+        dims, ks, ss = list(config.conv_dim), list(config.conv_kernel), list(config.conv_stride)
+        layers = []
+        for i in range(n):
+            if config.feat_extract_norm == "group":
+                norm = "group" if i == 0 else None
+            elif config.feat_extract_norm == "layer":
+                norm = "layer"
+            else:
+                raise ValueError(config.feat_extract_norm)
+            layers.append(_ConvLayer(1 if i == 0 else dims[i - 1], dims[i], ks[i], ss[i], config.conv_bias, norm))
+        self.conv_layers = nn.ModuleList(layers)
+        self._ks, self._ss = ks, ss
+
+    def forward(self, input_values):
+        cfg = self.config
+        if cfg.feat_extract_norm != "group" or cfg.conv_bias:
+            raise NotImplementedError(
+                "feat_extract_norm='layer' / conv_bias=True feature encoders are not wired to the sm_100a kernels yet")
+        if cfg.feat_extract_activation != "gelu":
+            raise NotImplementedError("only GELU feature encoders are supported")
+        if self._ks[0] != 10 or self._ss[0] != 5 or any(s != 2 for s in self._ss[1:]) or \
+                any(k not in (2, 3) for k in self._ks[1:]):
+            raise NotImplementedError("unsupported conv feature-encoder geometry %r / %r" % (self._ks, self._ss))
+        l0 = self.conv_layers[0]
+        ws = [l.conv.weight for l in self.conv_layers[1:]]
+        return ops.FeatureEncoderGroupFn.apply(input_values, tuple(self._ks[1:]), l0.conv.weight, l0.layer_norm.weight,
+                                               l0.layer_norm.bias, *ws)
+
+
+class FeatureProjection(nn.Module):
+    """hf:...wav2vec2.py:422-434 / hf:...hubert.py:216-232"""
+
+    def __init__(self, config, with_layer_norm=True):
+        super().__init__()
+        self.with_layer_norm = with_layer_norm
+        if with_layer_norm:
+            self.layer_norm = nn.LayerNorm(config.conv_dim[-1], eps=config.layer_norm_eps)
+        self.projection = nn.Linear(config.conv_dim[-1], config.hidden_size)
+        self.eps = config.layer_norm_eps
+
+    def forward(self, x):
+        if self.with_layer_norm:
+            x = ops.layer_norm(x, self.layer_norm.weight, self.layer_norm.bias, self.eps)
+        return ops.linear(x, self.projection.weight, self.projection.bias)
+
+
+class PositionalConvEmbedding(nn.Module):
+    """hf:...wav2vec2.py:326-379; the weight-norm factors keep the reference's parameter names
+    (conv.parametrizations.weight.original0/1)."""
+
+    def __init__(self, config):
+        super().__init__()
+        conv = nn.Conv1d(config.hidden_size, config.hidden_size, kernel_size=config.num_conv_pos_embeddings,
+                         padding=config.num_conv_pos_embeddings // 2, groups=config.num_conv_pos_embedding_groups)
+        self.conv = nn.utils.parametrizations.weight_norm(conv, name="weight", dim=2)
+        self.groups = config.num_conv_pos_embedding_groups
+        if config.num_conv_pos_embeddings % 2 != 0:
+            raise NotImplementedError("odd positional-conv kernels are not supported")
+
+    def forward(self, x):
+        """returns x + GELU(conv(x)) (the residual add is fused into the kernel epilogue)."""
+        p = self.conv.parametrizations.weight
+        weight = self.conv.weight  # g * v / ||v||, tiny tensor algebra kept in torch autograd
+        return ops.PosConvFn.apply(x, weight, self.conv.bias, self.groups, (p.original0, p.original1))
+
+
+class _Attention(nn.Module):
+    def __init__(self, dim, bias=True):
+        super().__init__()
+        # registration order follows hf BartAttention / Wav2Vec2Attention (k, v, q, out) so that
+        # named_parameters() -- and with it list_grad / list_no_grad -- enumerate like the reference
+        self.k_proj = nn.Linear(dim, dim, bias=bias)
+        self.v_proj = nn.Linear(dim, dim, bias=bias)
+        self.q_proj = nn.Linear(dim, dim, bias=bias)
+        self.out_proj = nn.Linear(dim, dim, bias=bias)
+
+    def params(self):
+        return (self.q_proj.weight, self.q_proj.bias, self.k_proj.weight, self.k_proj.bias, self.v_proj.weight,
+                self.v_proj.bias, self.out_proj.weight, self.out_proj.bias)
+
+
+class _FeedForward(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.intermediate_dense = nn.Linear(config.hidden_size, config.intermediate_size)
+        self.output_dense = nn.Linear(config.intermediate_size, config.hidden_size)
+
+
+class EncoderLayer(nn.Module):
+    """hf:...wav2vec2.py:576-609 (post-LN) and :612-655 (stable / pre-LN)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.attention = _Attention(config.hidden_size)
+        self.layer_norm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+        self.feed_forward = _FeedForward(config)
+        self.final_layer_norm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+        self.cfg = dict(heads=config.num_attention_heads, causal=False, pre_ln=bool(config.do_stable_layer_norm),
+                        eps=config.layer_norm_eps, act=config.hidden_act)
+        if config.hidden_size // config.num_attention_heads != 64:
+            raise NotImplementedError("attention kernels are specialised for head_dim 64")
+
+    def forward(self, x):
+        x = ops.AttnBlockFn.apply(x, None, self.cfg, *self.attention.params(), self.layer_norm.weight,
+                                  self.layer_norm.bias)
+        ff = self.feed_forward
+        return ops.FFNBlockFn.apply(x, self.cfg, ff.intermediate_dense.weight, ff.intermediate_dense.bias,
+                                    ff.output_dense.weight, ff.output_dense.bias, self.final_layer_norm.weight,
+                                    self.final_layer_norm.bias)
+
+
+class Encoder(nn.Module):
+    """hf:...wav2vec2.py:658-803"""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.pos_conv_embed = PositionalConvEmbedding(config)
+        self.layer_norm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+        self.layers = nn.ModuleList([EncoderLayer(config) for _ in range(config.num_hidden_layers)])
+        self.stable = bool(config.do_stable_layer_norm)
+
+    def forward(self, x, output_hidden_states=False):
+        hs = []
+        x = self.pos_conv_embed(x)
+        if not self.stable:
+            x = ops.layer_norm(x, self.layer_norm.weight, self.layer_norm.bias, self.config.layer_norm_eps)
+        for layer in self.layers:
+            if output_hidden_states:
+                hs.append(x)
+            # LayerDrop (hf :702-704) is a training-time regulariser of the reference recipe; it is
+            # honoured on the host exactly like the reference does.
+            if self.training and self.config.layerdrop > 0 and float(torch.rand([])) < self.config.layerdrop:
+                continue
+            x = layer(x)
+        if self.stable:
+            x = ops.layer_norm(x, self.layer_norm.weight, self.layer_norm.bias, self.config.layer_norm_eps)
+        if output_hidden_states:
+            hs.append(x)
+        return x, tuple(hs)
+
+
+class SpeechEncoderModel(nn.Module):
+    """Drop-in for ``Wav2Vec2Model`` / ``HubertModel`` on the SpeechMix path
+    (``encoder_model(input_values, output_hidden_states=True)``, ref:speechmix/hf_model.py:397)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.feature_extractor = FeatureEncoder(config)
+        is_hubert = config.model_type == "hubert"
+        self.feature_projection = FeatureProjection(
+            config, with_layer_norm=(not is_hubert) or bool(getattr(config, "feat_proj_layer_norm", True)))
+        if config.mask_time_prob > 0.0 or config.mask_feature_prob > 0.0:  # hf:...wav2vec2.py:1262-1264
+            self.masked_spec_embed = nn.Parameter(torch.empty(config.hidden_size).uniform_())
+        self.encoder = Encoder(config)
+        if getattr(config, "add_adapter", False):
+            raise NotImplementedError("wav2vec2 adapter stacks are out of scope")
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def forward(self, input_values, attention_mask=None, output_hidden_states=False, **kwargs):
+        if attention_mask is not None:
+            raise NotImplementedError("the SpeechMix path never passes an attention mask (SURVEY section 8)")
+        x = self.feature_extractor(input_values)          # [B, T, C] channels-last (HF: [B, C, T] + transpose)
+        x = self.feature_projection(x)
+        # SpecAugment (hf :1280-1324) only fires in training with mask_time_prob > 0.
+        if self.training and getattr(self.config, "apply_spec_augment", False) and \
+                (self.config.mask_time_prob > 0 or self.config.mask_feature_prob > 0):
+            raise NotImplementedError("SpecAugment masking is not implemented; set apply_spec_augment=False")
+        x, hs = self.encoder(x, output_hidden_states=output_hidden_states)
+        return SpeechOutput(last_hidden_state=x, hidden_states=hs if output_hidden_states else None)
+
+
+# ---------------------------------------------------------------------------
+def load_checkpoint_state(path):
+    """state dict of a transformers checkpoint directory (safetensors or .bin)."""
+    st = os.path.join(path, "model.safetensors")
+    if os.path.exists(st):
+        from safetensors.torch import load_file
+        return load_file(st)
+    pt = os.path.join(path, "pytorch_model.bin")
+    if os.path.exists(pt):
+        return torch.load(pt, map_location="cpu")
+    raise FileNotFoundError("no model.safetensors / pytorch_model.bin under %s" % path)
+
+
+def speech_from_pretrained(path_or_config):
+    """Build from a local transformers checkpoint directory (config + weights) or a config object
+    (random init, HF initialisers are not reproduced -- load a state dict afterwards)."""
+    from transformers import AutoConfig, PretrainedConfig
+
+    if isinstance(path_or_config, PretrainedConfig):
+        return SpeechEncoderModel(path_or_config)
+    config = AutoConfig.from_pretrained(path_or_config)
+    model = SpeechEncoderModel(config)
+    sd = load_checkpoint_state(path_or_config)
+    fixed = {}
+    for k, v in sd.items():
+        for prefix in ("wav2vec2.", "hubert."):
+            if k.startswith(prefix):
+                k = k[len(prefix):]
+        k = k.replace("pos_conv_embed.conv.weight_g", "pos_conv_embed.conv.parametrizations.weight.original0")
+        k = k.replace("pos_conv_embed.conv.weight_v", "pos_conv_embed.conv.parametrizations.weight.original1")
+        fixed[k] = v
+    own = model.state_dict()
+    missing = [k for k in own if k not in fixed]
+    model.load_state_dict({k: v for k, v in fixed.items() if k in own}, strict=False)
+    if missing:
+        raise RuntimeError("checkpoint %s lacks %d tensors, e.g. %s" % (path_or_config, len(missing), missing[:3]))
+    return model

@@ -1,0 +1,204 @@
+"""BART / mBART sequence-to-sequence LM on the sm_100a kernels: text encoder fed with
+speech embeddings, decoder with causal self-attention and cross-attention, tied LM head
+with fused cross-entropy (no [rows, vocab] logits in HBM).
+
+Module / parameter names mirror ``BartForConditionalGeneration`` /
+``MBartForConditionalGeneration`` (hf:models/bart/modeling_bart.py,
+hf:models/mbart/modeling_mbart.py) so reference state dicts load unchanged.
+"""
+import math
+
+import torch
+from torch import nn
+
+from . import kernels as K
+from . import ops
+from .speech import SpeechOutput, _Attention, load_checkpoint_state
+
+
+class _EncoderLayer(nn.Module):
+    """hf:...bart.py:261-309 (post-LN) / hf:...mbart.py:274-328 (pre-LN)"""
+
+    def __init__(self, d, heads, ffn, act, pre_ln):
+        super().__init__()
+        self.self_attn = _Attention(d)
+        self.self_attn_layer_norm = nn.LayerNorm(d)
+        self.fc1 = nn.Linear(d, ffn)
+        self.fc2 = nn.Linear(ffn, d)
+        self.final_layer_norm = nn.LayerNorm(d)
+        self.cfg = dict(heads=heads, causal=False, pre_ln=pre_ln, eps=1e-5, act=act)
+
+    def forward(self, x):
+        x = ops.AttnBlockFn.apply(x, None, self.cfg, *self.self_attn.params(), self.self_attn_layer_norm.weight,
+                                  self.self_attn_layer_norm.bias)
+        return ops.FFNBlockFn.apply(x, self.cfg, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias,
+                                    self.final_layer_norm.weight, self.final_layer_norm.bias)
+
+
+class _DecoderLayer(nn.Module):
+    """hf:...bart.py:312-391 / hf:...mbart.py:331-430"""
+
+    def __init__(self, d, heads, ffn, act, pre_ln):
+        super().__init__()
+        self.self_attn = _Attention(d)
+        self.self_attn_layer_norm = nn.LayerNorm(d)
+        self.encoder_attn = _Attention(d)
+        self.encoder_attn_layer_norm = nn.LayerNorm(d)
+        self.fc1 = nn.Linear(d, ffn)
+        self.fc2 = nn.Linear(ffn, d)
+        self.final_layer_norm = nn.LayerNorm(d)
+        self.cfg_self = dict(heads=heads, causal=True, pre_ln=pre_ln, eps=1e-5, act=act)
+        self.cfg_cross = dict(heads=heads, causal=False, pre_ln=pre_ln, eps=1e-5, act=act)
+
+    def forward(self, x, enc):
+        x = ops.AttnBlockFn.apply(x, None, self.cfg_self, *self.self_attn.params(), self.self_attn_layer_norm.weight,
+                                  self.self_attn_layer_norm.bias)
+        x = ops.AttnBlockFn.apply(x, enc, self.cfg_cross, *self.encoder_attn.params(),
+                                  self.encoder_attn_layer_norm.weight, self.encoder_attn_layer_norm.bias)
+        return ops.FFNBlockFn.apply(x, self.cfg_cross, self.fc1.weight, self.fc1.bias, self.fc2.weight,
+                                    self.fc2.bias, self.final_layer_norm.weight, self.final_layer_norm.bias)
+
+
+class _Stack(nn.Module):
+    POS_OFFSET = 2  # BartLearnedPositionalEmbedding / MBartLearnedPositionalEmbedding (hf:...bart.py:74-98)
+
+    def __init__(self, config, shared, is_decoder):
+        super().__init__()
+        d = config.d_model
+        self.config = config
+        self.is_decoder = is_decoder
+        self.embed_tokens = shared
+        self.embed_scale = math.sqrt(d) if config.scale_embedding else 1.0
+        self.embed_positions = nn.Embedding(config.max_position_embeddings + self.POS_OFFSET, d)
+        pre_ln = config.model_type == "mbart"
+        n = config.decoder_layers if is_decoder else config.encoder_layers
+        heads = config.decoder_attention_heads if is_decoder else config.encoder_attention_heads
+        ffn = config.decoder_ffn_dim if is_decoder else config.encoder_ffn_dim
+        if d // heads != 64:
+            raise NotImplementedError("attention kernels are specialised for head_dim 64")
+        cls = _DecoderLayer if is_decoder else _EncoderLayer
+        self.layers = nn.ModuleList([cls(d, heads, ffn, config.activation_function, pre_ln) for _ in range(n)])
+        self.layernorm_embedding = nn.LayerNorm(d)
+        if pre_ln:
+            self.layer_norm = nn.LayerNorm(d)
+        self.pre_ln = pre_ln
+
+    def embed(self, input_ids=None, inputs_embeds=None, t_start=0):
+        """tokens*scale (or given embeddings, unscaled: hf:...bart.py:520-524) + learned positions, then LN."""
+        x = ops.EmbedFn.apply(input_ids, inputs_embeds, self.embed_tokens.weight if input_ids is not None else None,
+                              self.embed_positions.weight, self.embed_scale, self.POS_OFFSET, t_start)
+        return ops.layer_norm(x, self.layernorm_embedding.weight, self.layernorm_embedding.bias, 1e-5)
+
+    def forward(self, input_ids=None, inputs_embeds=None, encoder_hidden_states=None, output_hidden_states=False):
+        x = self.embed(input_ids, inputs_embeds)
+        hs = [x] if output_hidden_states else None
+        for layer in self.layers:
+            x = layer(x, encoder_hidden_states) if self.is_decoder else layer(x)
+            if output_hidden_states:
+                hs.append(x)
+        if self.pre_ln:
+            x = ops.layer_norm(x, self.layer_norm.weight, self.layer_norm.bias, 1e-5)
+            if output_hidden_states:
+                hs[-1] = x
+        return x, hs
+
+
+class _Body(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.shared = nn.Embedding(config.vocab_size, config.d_model, config.pad_token_id)
+        self.encoder = _Stack(config, self.shared, is_decoder=False)
+        self.decoder = _Stack(config, self.shared, is_decoder=True)
+
+
+class Seq2SeqLM(nn.Module):
+    """Drop-in for ``AutoModelForSeq2SeqLM.from_pretrained(<bart|mbart>)`` on the SpeechMix path
+    (call site ref:speechmix/hf_model.py:357-374)."""
+
+    def __init__(self, config):
+        super().__init__()
+        if config.model_type not in ("bart", "mbart"):
+            raise NotImplementedError("text backbone %r is not wired to the sm_100a kernels yet" % config.model_type)
+        self.config = config
+        self.model = _Body(config)
+        self.lm_head = nn.Linear(config.d_model, config.vocab_size, bias=False)
+        self.lm_head.weight = self.model.shared.weight  # tied (hf:...bart.py:806-812)
+        self.register_buffer("final_logits_bias", torch.zeros((1, config.vocab_size)))
+
+    @property
+    def base_model(self):
+        return self.model
+
+    @property
+    def device(self):
+        return self.model.shared.weight.device
+
+    def get_input_embeddings(self):
+        return self.model.shared
+
+    def get_encoder(self):
+        return self.model.encoder
+
+    def encode(self, input_ids=None, inputs_embeds=None, output_hidden_states=False):
+        return self.model.encoder(input_ids=input_ids, inputs_embeds=inputs_embeds,
+                                  output_hidden_states=output_hidden_states)
+
+    def decode_hidden(self, decoder_input_ids, encoder_hidden_states):
+        x, _ = self.model.decoder(input_ids=decoder_input_ids, encoder_hidden_states=encoder_hidden_states)
+        return x
+
+    def full_logits(self, hidden):
+        """fp32 [.., V] logits, materialised -- parity tests / debugging only, never on the training path."""
+        h2 = hidden.reshape(-1, hidden.shape[-1]).contiguous()
+        lg = K.linear_fwd(h2, ops.w16(self.model.shared.weight), self.final_logits_bias.reshape(-1).float().contiguous(),
+                          out_f32=True)
+        return lg.view(*hidden.shape[:-1], -1)
+
+    def forward(self, input_ids=None, inputs_embeds=None, attention_mask=None, decoder_input_ids=None, labels=None,
+                encoder_outputs=None, output_hidden_states=False, past_key_values=None, use_cache=None, **kwargs):
+        if attention_mask is not None:
+            raise NotImplementedError("the SpeechMix path never passes an attention mask (SURVEY section 8)")
+        cfg = self.config
+        if decoder_input_ids is None and labels is not None:
+            from .model import shift_tokens_right
+            decoder_input_ids = shift_tokens_right(labels, cfg.pad_token_id, cfg.decoder_start_token_id)
+        enc_hs = None
+        if encoder_outputs is None:
+            enc, enc_hs = self.encode(input_ids, inputs_embeds, output_hidden_states)
+        else:
+            enc = encoder_outputs[0] if isinstance(encoder_outputs, (list, tuple)) else encoder_outputs
+        hidden = self.decode_hidden(decoder_input_ids, enc)
+        B, T, _ = hidden.shape
+        lab = labels if labels is not None else torch.full((B, T), -100, device=hidden.device, dtype=torch.long)
+        loss, ids = ops.LMHeadCEFn.apply(hidden, self.model.shared.weight, self.final_logits_bias, lab, 1.0)
+        out = SpeechOutput(loss=loss if labels is not None else None, logits=ids, argmax_ids=ids,
+                           encoder_last_hidden_state=enc, decoder_last_hidden_state=hidden)
+        if output_hidden_states:
+            out["encoder_hidden_states"] = tuple(enc_hs) if enc_hs is not None else None
+        return out
+
+
+def text_from_pretrained(path_or_config):
+    from transformers import AutoConfig, PretrainedConfig
+
+    if isinstance(path_or_config, PretrainedConfig):
+        return Seq2SeqLM(path_or_config)
+    config = AutoConfig.from_pretrained(path_or_config)
+    model = Seq2SeqLM(config)
+    sd = dict(load_checkpoint_state(path_or_config))
+    # tied aliases may be stored once
+    base = None
+    for k in ("model.shared.weight", "model.encoder.embed_tokens.weight", "model.decoder.embed_tokens.weight",
+              "lm_head.weight"):
+        if k in sd:
+            base = sd[k]
+            break
+    own = model.state_dict()
+    for k in ("model.shared.weight", "model.encoder.embed_tokens.weight", "model.decoder.embed_tokens.weight",
+              "lm_head.weight"):
+        sd.setdefault(k, base)
+    missing = [k for k in own if k not in sd]
+    if missing:
+        raise RuntimeError("checkpoint %s lacks %d tensors, e.g. %s" % (path_or_config, len(missing), missing[:3]))
+    model.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=False)
+    return model

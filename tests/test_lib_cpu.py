@@ -1,0 +1,108 @@
+"""CPU-side checks of the C-ABI boundary: the library builds for sm_100a, loads without a
+GPU, and exports exactly the symbols include/speechmix_sm100.h declares.  No compute calls."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "speechmix_sm100.h")
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    from speechmix_b200 import build
+    return build.build()
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(smx_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_entry_points():
+    syms = declared_symbols()
+    assert "smx_gemm" in syms and "smx_attn_fwd" in syms and "smx_lmhead_ce_fwd" in syms
+    assert len(syms) >= 25
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    lib = ctypes.CDLL(lib_path)
+    for s in declared_symbols():
+        assert hasattr(lib, s), "missing export: " + s
+
+
+def test_binding_table_matches_header(lib_path):
+    from speechmix_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared_symbols()
+    lib = _lib.load()
+    assert lib.smx_abi_version() == 1
+
+
+def test_struct_layout_matches_c():
+    """sizeof(SmxGemm)/sizeof(SmxAttn) as seen by ctypes == as compiled by gcc from the header."""
+    from speechmix_b200 import _lib
+    prog = '#include <stdio.h>\n#include "speechmix_sm100.h"\nint main(){printf("%zu %zu %zu", sizeof(SmxGemm), sizeof(SmxAttn), sizeof(SmxView3));return 0;}'
+    exe = "/tmp/smx_sizeof"
+    subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=prog.encode(), check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
+    assert [int(v) for v in out] == [ctypes.sizeof(_lib.SmxGemm), ctypes.sizeof(_lib.SmxAttn), ctypes.sizeof(_lib.SmxView3)]
+
+
+def test_kernels_are_blackwell_native(lib_path):
+    """SASS evidence: tcgen05.mma -> UTC*MMA, TMA -> UTMALDG, tcgen05.ld -> LDTM."""
+    sass = subprocess.run(["cuobjdump", "-sass", lib_path], capture_output=True, text=True).stdout
+    if not sass:
+        pytest.skip("cuobjdump unavailable")
+    assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass
+    assert "HMMA." not in sass.replace("UTCHMMA", "")  # no legacy mma.sync path
+
+
+def test_no_fallback_without_gpu(lib_path):
+    import torch
+    from speechmix_b200 import _lib
+    lib = _lib.load()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert lib.smx_device_ok() != 1  # no device -> error, never a silent CPU path
+    assert lib.smx_last_error()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "speechmix_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg, f)).read()
+            assert "oracle" not in src, f
+
+
+def test_state_dict_layout_matches_reference_oracle():
+    """drop-in boundary: same parameter names / shapes / requires_grad bookkeeping as HFSpeechMixEED."""
+    from oracle import hf_oracle as O
+    from speechmix_b200 import SpeechMixEED
+    for tx in ("bart-mini", "mbart-mini"):
+        spc, txc = O.speech_config("mini"), O.text_config(tx)
+        s, t = O.build_backbones(spc, txc)
+        ora = O.OracleEED(s, t, down_scale=4, weighted_sum=True, fixed_parameters=True)
+        mine = SpeechMixEED(spc, txc, down_scale=4, weighted_sum=True, fixed_parameters=True)
+        a, b = ora.state_dict(), mine.state_dict()
+        assert list(a) == list(b) or set(a) == set(b)
+        assert all(a[k].shape == b[k].shape for k in a)
+        assert ora.list_no_grad == mine.list_no_grad and ora.list_grad == mine.list_grad
+        assert mine.speech_encoder_layer == ora.speech_encoder_layer and mine.nlp_encoder_layer == ora.nlp_encoder_layer
+        mine.load_state_dict(a)
+
+
+def test_share_layer_ratio_and_helpers():
+    """ref:test/test_hf_model.py:18-33 restated on the product classes."""
+    import torch
+    from oracle import hf_oracle as O
+    from speechmix_b200 import SpeechMixEED, shift_tokens_right
+    for ratio, kept in [(1, 0), (0.5, 1), (0, 2)]:
+        m = SpeechMixEED(O.speech_config("mini"), O.text_config("bart-mini"), share_layer_ratio=ratio, down_scale=8)
+        assert m.speech_encoder_layer == kept and m.nlp_encoder_layer == 2 and len(m.list_no_grad) == 0
+    lab = torch.tensor([[5, 6, -100, -100], [7, 8, 9, 10]])
+    assert torch.equal(shift_tokens_right(lab, 1, 2), O.shift_tokens_right(lab, 1, 2))
