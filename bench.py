@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""Headline benchmark: SpeechMixEED wav2vec2-base + bart-base, down_scale=2, batch 32 x 15 s per GPU,
+bf16 forward + loss + backward + optimizer step  ->  train audio-seconds / second (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL); data parallel, weak scaling.
+Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for what every key means.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("TRANSFORMERS_OFFLINE", "1")
+os.environ.setdefault("TOKENIZERS_PARALLELISM", "false")
+
+SECONDS, BATCH_PER_GPU, T_DEC, RATE = 15.0, 32, 64, 16000
+CPU_SAMPLE_BATCH = 2
+
+
+def fwd_flops_per_sample(secs=SECONDS, t_dec=T_DEC, H=768, FF=3072, L=12, D=768, DFF=3072, Le=6, Ld=6, V=50265, ds=2):
+    """BASELINE.md section 3 formulas (2*MAC, dense attention)."""
+    T = int(secs * RATE)
+    ks, ss = (10, 3, 3, 3, 3, 2, 2), (5, 2, 2, 2, 2, 2, 2)
+    fl, cin = 0.0, 1
+    for k, s in zip(ks, ss):
+        T = (T - k) // s + 1
+        fl += 2.0 * T * 512 * cin * k
+        cin = 512
+    fl += 2.0 * T * 512 * H
+    fl += 2.0 * T * H * (H // 16) * 128
+    fl += L * (8.0 * T * H * H + 4.0 * T * T * H + 4.0 * T * H * FF)
+    Tds = T
+    for _ in range(int(round(__import__("math").log2(ds)))):
+        Tds = (Tds - 2) // 2 + 1
+        fl += 4.0 * Tds * H * H
+    fl += 2.0 * Tds * H * D
+    fl += Le * (8.0 * Tds * D * D + 4.0 * Tds * Tds * D + 4.0 * Tds * D * DFF)
+    fl += Ld * (8.0 * t_dec * D * D + 4.0 * t_dec * t_dec * D + 4.0 * t_dec * D * D + 4.0 * Tds * D * D +
+                4.0 * t_dec * Tds * D + 4.0 * t_dec * D * DFF)
+    fl += 2.0 * t_dec * D * V
+    return fl
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def build_cpu_reference(batch):
+    """The reference's CPU path, restated (oracle/hf_oracle.py; /root/reference does not exist on the
+    GPU box): HFSpeechMixEED glue over transformers' Wav2Vec2Model + BartForConditionalGeneration, fp32."""
+    import torch
+    from oracle import hf_oracle as O
+    spc, txc = O.speech_config("base"), O.text_config("bart-base")
+    s, t = O.build_backbones(spc, txc, seed=0)
+    model = O.OracleEED(s, t, down_scale=2).train()
+    x, labels = O.synthetic_batch(batch, SECONDS, T_DEC, txc.vocab_size, seed=0)
+    return model, x, labels
+
+
+def time_cpu_reference(steps, warmup, batch=CPU_SAMPLE_BATCH):
+    import torch
+    torch.set_num_threads(os.cpu_count())
+    model, x, labels = build_cpu_reference(batch)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-5)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        out = model(x, labels=labels)
+        out["loss"].backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    return batch * SECONDS / sec, sec, torch.get_num_threads()
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    val, sec, threads = time_cpu_reference(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": "train audio-sec/s", "value": val, "unit": "audio-s/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "SpeechMixEED wav2vec2-base + bart-base down_scale=2, fwd+bwd+AdamW",
+                       "sample": "batch %d x 15 s per step on host CPU" % CPU_SAMPLE_BATCH},
+            "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": threads, "kind": "port",
+                             "sample": "oracle/hf_oracle.py OracleEED (restated reference glue over transformers), "
+                                       "batch %d x 15 s, %d timed steps" % (CPU_SAMPLE_BATCH, args.steps)},
+            "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from speechmix_b200 import SpeechMixEED, kernels, parallel
+    from oracle import hf_oracle as O  # configs only (shapes of wav2vec2-base / bart-base); no oracle compute here
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    spc, txc = O.speech_config("base"), O.text_config("bart-base")
+    torch.manual_seed(0)
+    model = SpeechMixEED(spc, txc, down_scale=2)
+    parallel.init_like_reference(model, seed=0)
+    model = model.to(dev).train()
+    B = args.batch
+    n_samples = int(SECONDS * RATE)
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_x = [torch.randn(B, n_samples, generator=g).pin_memory() for _ in range(2)]
+    host_y = [torch.randint(4, txc.vocab_size, (B, T_DEC), generator=g).pin_memory() for _ in range(2)]
+    dev_x = [t.to(dev) for t in host_x]
+    dev_y = [t.to(dev) for t in host_y]
+
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-5, fused=True)
+    dp = parallel.GradientAllReducer(model, world) if world > 1 else None
+
+    def step(x, y):
+        opt.zero_grad(set_to_none=True)
+        out = model(x, labels=y, return_model_detail=False)
+        out["loss"].backward()
+        if dp is not None:
+            dp.finish()
+        opt.step()
+        return out["loss"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, e2e):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for i in range(n):
+            if e2e:
+                x = host_x[i & 1].to(dev, non_blocking=True)
+                y = host_y[i & 1].to(dev, non_blocking=True)
+                last = step(x, y).item()
+            else:
+                last = step(dev_x[i & 1], dev_y[i & 1])
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / n
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, last
+
+    for _ in range(args.warmup):
+        step(dev_x[0], dev_y[0])
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = kernels.LAUNCHES[0]
+    kernels.TIMING = [] if rank == 0 else None
+    ms, _ = timed(args.steps, e2e=False)
+    gemm_events = kernels.TIMING
+    kernels.TIMING = None
+    launches = (kernels.LAUNCHES[0] - launches0) // args.steps
+    ms_e2e, _ = timed(args.steps, e2e=True)
+    sampler.stop_flag = True
+
+    if rank == 0:
+        audio_s = B * world * SECONDS
+        fl_step = 3.0 * fwd_flops_per_sample() * B
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+        # dominant kernel: the FFN up-projection GEMM (M = B*749, N = 3072, K = 768), timed live with CUDA events
+        dom = [(a.elapsed_time(b), fl) for (tag, fl, a, b) in (gemm_events or []) if tag == "nt_%d_3072_768" % (B * 749)]
+        roof = None
+        if dom:
+            avg_ms = sum(d for d, _ in dom) / len(dom)
+            ach = dom[0][1] / avg_ms / 1e9
+            roof = {"bound": "tensor", "kernel": "gemm_kernel<NT> M=%d N=3072 K=768 (FFN up-projection + bias + GELU)" % (B * 749),
+                    "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
+                    "launches_timed": len(dom), "traffic": None,
+                    "step_frac_of_peak": fl_step / (ms * 1e-3) / 1e12 / peak_tf}
+        line = {"metric": "train audio-sec/s", "value": audio_s / (ms * 1e-3), "unit": "audio-s/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "SpeechMixEED wav2vec2-base + bart-base down_scale=2, batch %d x 15 s per GPU, "
+                                       "T_dec=64, fwd+loss+bwd+AdamW (BASELINE.json configs[1])" % B,
+                           "global_batch": B * world, "parallelism": "dp%d" % world,
+                           "l2": "per-step activations (>3 GB) exceed the 126 MB L2"},
+                "e2e": {"value": audio_s / (ms_e2e * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_e2e,
+                        "h2d_bytes_per_step": B * n_samples * 4 + B * T_DEC * 8, "d2h_bytes_per_step": 4},
+                "gpu_launches": int(launches) * args.steps,
+                "gpu_launches_per_step": int(launches),
+                "step_tflops": fl_step / (ms * 1e-3) / 1e12,
+                "clocks": sampler.summary(),
+                "roofline": roof}
+        if not args.no_cpu_baseline and world == 1:
+            val, sec, threads = time_cpu_reference(steps=2, warmup=1)
+            line["cpu_baseline"] = {"value": val, "unit": "audio-s/s", "cores": threads, "kind": "port",
+                                    "sample": "oracle OracleEED fp32 fwd+bwd+AdamW, batch %d x 15 s, 2 timed steps (%.1f s/step)"
+                                              % (CPU_SAMPLE_BATCH, sec)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

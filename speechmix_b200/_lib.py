@@ -107,7 +107,16 @@ def load():
     return lib
 
 
+# kernels launched per successful call (bench.py's gpu_launches); smx_gemm is counted by its caller
+KERNELS_PER_CALL = {"smx_attn_fwd": 1, "smx_attn_bwd": 3, "layernorm_fwd": 1, "layernorm_bwd": 1, "colsum": 1,
+                    "cast": 1, "add": 1, "dact": 1, "conv0_stats": 2, "conv0_fwd": 1, "conv0_bwd": 2,
+                    "posconv_fwd": 1, "posconv_dgrad": 1, "posconv_wgrad": 1, "embed_fwd": 1, "embed_bwd": 1,
+                    "lmhead_ce_fwd": 2, "lmhead_dlogits": 1, "wsum_fwd": 1, "wsum_bwd": 1}
+LAUNCHES = [0]
+
+
 def check(rc, what=""):
+    LAUNCHES[0] += KERNELS_PER_CALL.get(what, 0)
     if rc != 0:
         msg = load().smx_last_error()
         raise RuntimeError("libspeechmix_sm100 %s failed: %s" % (what, msg.decode() if msg else "?"))

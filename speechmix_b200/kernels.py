@@ -15,6 +15,11 @@ from ._lib import (ACT_DGELU, ACT_DRELU, ACT_GELU, ACT_NONE, ACT_RELU, GEMM_NN, 
 
 BF16 = torch.bfloat16
 
+# bookkeeping for bench.py: number of kernels of this library launched so far, and an optional
+# list collecting (tag, flops, start_event, end_event) around tagged GEMM launches.
+LAUNCHES = _lib.LAUNCHES
+TIMING = None
+
 
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -40,8 +45,16 @@ def alloc_act(batch, t, c, device, dtype=BF16, slack=None):
     return flat[:n].view(batch, t, c)
 
 
-def _run_gemm(g):
+def _run_gemm(g, tag=None, flops=0.0):
     lib = _lib.load()
+    LAUNCHES[0] += 1
+    if TIMING is not None and tag is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(lib.smx_gemm(ctypes.byref(g), _stream()), "smx_gemm")
+        e1.record()
+        TIMING.append((tag, flops, e0, e1))
+        return
     _lib.check(lib.smx_gemm(ctypes.byref(g), _stream()), "smx_gemm")
 
 
@@ -86,7 +99,7 @@ def linear_fwd(x, w, bias=None, act=ACT_NONE, residual=None, want_pre=False, out
     _set_seg(g, 1, K)
     _epilogue(g, y, y.stride(0), M * y.stride(0), bias, act, residual,
               (residual.stride(0), 0) if residual is not None else None, pre, None, alpha)
-    _run_gemm(g)
+    _run_gemm(g, "nt_%d_%d_%d" % (M, N, K), 2.0 * M * N * K)
     return (y, pre) if want_pre else y
 
 

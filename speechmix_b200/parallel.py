@@ -1,0 +1,127 @@
+"""Data parallelism for the SpeechMix hot path: one process per GPU, weights
+replicated, the global batch split by sample, ONE collective per step -- a bucketed gradient
+all-reduce over NCCL (NVLink 5 / NVSwitch) that is launched from backward as soon as every
+gradient of a bucket has been produced, so it overlaps the remaining backward kernels.
+
+The reference gets this implicitly from HF Trainer (nn.DataParallel / DDP, hf:trainer.py:2405-2430).
+"""
+import math
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+
+class GradientAllReducer:
+    """Bucketed, backward-overlapped gradient averaging.
+
+    Buckets are filled in reverse parameter-registration order (~ the order backward produces
+    gradients: LM head / decoder first, conv stack last).  When the last gradient of a bucket
+    arrives its gradients are packed into one flat buffer and ``all_reduce`` is issued
+    asynchronously on the communicator's stream; ``finish()`` waits and scatters the averaged
+    values back into ``param.grad``.  Works with any backend (``gloo`` in the CPU tests)."""
+
+    def __init__(self, module, world_size=None, bucket_mb=64, group=None):
+        self.world = world_size if world_size is not None else dist.get_world_size()
+        self.group = group
+        params = [p for p in module.parameters() if p.requires_grad]
+        params.reverse()
+        cap = int(bucket_mb * 1024 * 1024 / 4)
+        self.buckets, cur, n = [], [], 0
+        for p in params:
+            cur.append(p)
+            n += p.numel()
+            if n >= cap:
+                self.buckets.append(cur)
+                cur, n = [], 0
+        if cur:
+            self.buckets.append(cur)
+        self.flat = [torch.empty(sum(p.numel() for p in b), device=b[0].device, dtype=torch.float32)
+                     for b in self.buckets]
+        self.pending = [len(b) for b in self.buckets]
+        self.works = [None] * len(self.buckets)
+        self.owner = {}
+        self.handles = []
+        for bi, b in enumerate(self.buckets):
+            for p in b:
+                self.owner[id(p)] = bi
+                self.handles.append(p.register_post_accumulate_grad_hook(self._hook))
+
+    def _views(self, bi):
+        out, off = [], 0
+        for p in self.buckets[bi]:
+            out.append(self.flat[bi][off:off + p.numel()].view_as(p))
+            off += p.numel()
+        return out
+
+    def _hook(self, p):
+        bi = self.owner[id(p)]
+        self.pending[bi] -= 1
+        if self.pending[bi] == 0:
+            self._launch(bi)
+
+    def _launch(self, bi):
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.buckets[bi]]
+        torch._foreach_copy_(self._views(bi), grads)
+        self.works[bi] = dist.all_reduce(self.flat[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def finish(self):
+        """Call after ``loss.backward()``: flush buckets whose parameters received no gradient this
+        step, wait for the collectives and write the averaged gradients back."""
+        for bi in range(len(self.buckets)):
+            if self.works[bi] is None:
+                self._launch(bi)
+        inv = 1.0 / self.world
+        for bi, b in enumerate(self.buckets):
+            self.works[bi].wait()
+            views = self._views(bi)
+            grads = []
+            for p, v in zip(b, views):
+                if p.grad is None:
+                    p.grad = torch.empty_like(p)
+                grads.append(p.grad)
+            torch._foreach_mul_(views, inv)
+            torch._foreach_copy_(grads, views)
+            self.works[bi] = None
+            self.pending[bi] = len(b)
+
+    def remove(self):
+        for h in self.handles:
+            h.remove()
+
+
+def shard_batch(global_batch, rank, world):
+    """Contiguous per-rank slice of a global batch dimension (even split required)."""
+    assert global_batch % world == 0, "global batch must divide evenly across ranks"
+    per = global_batch // world
+    return slice(rank * per, (rank + 1) * per)
+
+
+def init_like_reference(model, seed=0):
+    """Random initialisation with the statistics of the transformers initialisers
+    (hf:...wav2vec2.py _init_weights, hf:...bart.py _init_weights) -- used for synthetic
+    benchmarks where no checkpoint exists; parity tests load the oracle's weights instead."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, m in model.named_modules():
+            if isinstance(m, nn.Linear):
+                m.weight.copy_(torch.randn(m.weight.shape, generator=g) * 0.02)
+                if m.bias is not None:
+                    m.bias.zero_()
+            elif isinstance(m, nn.Embedding):
+                m.weight.copy_(torch.randn(m.weight.shape, generator=g) * 0.02)
+            elif isinstance(m, (nn.LayerNorm, nn.GroupNorm)):
+                m.weight.fill_(1.0)
+                m.bias.zero_()
+            elif isinstance(m, nn.Conv1d) and not hasattr(m, "parametrizations"):
+                fan_in = m.in_channels // m.groups * m.kernel_size[0]
+                m.weight.copy_(torch.randn(m.weight.shape, generator=g) * math.sqrt(2.0 / fan_in))
+                if m.bias is not None:
+                    m.bias.zero_()
+            elif isinstance(m, nn.Conv1d):
+                p = m.parametrizations.weight
+                v = torch.randn(p.original1.shape, generator=g) * (2 * math.sqrt(1.0 / (m.kernel_size[0] * m.in_channels)))
+                p.original1.copy_(v)
+                p.original0.copy_(v.norm(dim=(0, 1), keepdim=True))
+                m.bias.zero_()
+    return model
