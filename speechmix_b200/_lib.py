@@ -86,6 +86,34 @@ SIGNATURES = {
 
 _lib = None
 
+# Optional per-call device timing (tools/profile_step.py): name -> [(start_event, end_event), ...]
+PROFILE = None
+
+
+def _profiled(name, fn):
+    def call(*args):
+        if PROFILE is None:
+            return fn(*args)
+        import torch
+        key = name
+        if name == "smx_gemm":
+            g = args[0]._obj
+            key = "gemm_%s m%d n%d k%d b%d act%d" % (("NT", "NN", "TN")[g.mode], g.m, g.n, g.k, g.batches, g.act)
+        elif name in ("smx_attn_fwd", "smx_attn_bwd"):
+            a = args[0]._obj
+            key = "%s tq%d tk%d h%d c%d" % (name, a.tq, a.tk, a.heads, a.causal)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        PROFILE.setdefault(key, []).append((e0, e1))
+        return rc
+    return call
+
+
+class _Lib:
+    pass
+
 
 def load():
     """Load the shared library (once).  Raises if it has not been built."""
@@ -103,8 +131,14 @@ def load():
         fn.argtypes = args
     if lib.smx_abi_version() != 1:
         raise RuntimeError("libspeechmix_sm100.so ABI version mismatch")
-    _lib = lib
-    return lib
+    shim = _Lib()
+    for name in SIGNATURES:
+        fn = getattr(lib, name)
+        setattr(shim, name, _profiled(name, fn) if SIGNATURES[name][0] is c_int and name.startswith("smx_") and
+                name not in ("smx_abi_version", "smx_device_ok") else fn)
+    shim._cdll = lib
+    _lib = shim
+    return shim
 
 
 # kernels launched per successful call (bench.py's gpu_launches); smx_gemm is counted by its caller

@@ -227,7 +227,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
         float val = 0.f;
         if (qi < p.tq) {
           const long long idx = ((long long)b * p.heads + head) * p.tq + qi;
-          val = ct < 128 ? p.lse[idx] * kLog2e : p.delta[idx];
+          val = ct < 128 ? p.lse[idx] * kLog2e : p.delta[idx] * p.scale;
         }
         st[ct] = val;
       }
@@ -235,7 +235,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
       mbar_wait(&bars[B_STFULL], it & 1);
       tc_fence_after_sync();
       mbar_wait(&bars[B_PDSEMPTY], (it & 1) ^ 1);  // previous dV/dK MMAs finished reading P^T / dS^T
-#pragma unroll
+      // Out-of-range queries / keys need no masking here: their Q / dO / K / V rows are zero-filled by
+      // TMA, so every product they enter vanishes as long as P and dS stay finite (they do).  Only the
+      // causal diagonal and an additive bias need the per-element path.
+      const bool lean = !p.causal && p.bias == nullptr;
+#pragma unroll 1
       for (int cc = 0; cc < 2; ++cc) {
         const int c32 = half * 2 + cc;
         uint32_t sv[32], dv[32];
@@ -243,16 +247,31 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
         tmem_ld_x32(t_lane + COL_DPT + c32 * 32, dv);
         tmem_ld_wait();
         float pt[32], ds[32];
+        if (lean) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int col = c32 * 32 + i;
-          const int qi = q0 + col;
-          float s = __uint_as_float(sv[i]) * p.scale_log2;
-          if (p.bias && qi < p.tq && kvi < p.tk) s += p.bias[((long long)head * p.tq + qi) * p.tk + kvi] * kLog2e;
-          const bool ok = (qi < p.tq) && (kvi < p.tk) && (!p.causal || kvi <= qi + (p.tk - p.tq));
-          const float e = ok ? exp2f(s - st[col]) : 0.f;
-          pt[i] = e;
-          ds[i] = e * (__uint_as_float(dv[i]) - st[128 + col]) * p.scale;
+          for (int i = 0; i < 32; i += 4) {
+            const float4 l4 = *reinterpret_cast<const float4*>(st + c32 * 32 + i);
+            const float4 d4 = *reinterpret_cast<const float4*>(st + 128 + c32 * 32 + i);
+            const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float e = ex2_approx(fmaf(__uint_as_float(sv[i + k]), p.scale_log2, -lv[k]));
+              pt[i + k] = e;
+              ds[i + k] = e * fmaf(__uint_as_float(dv[i + k]), p.scale, -dl[k]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int col = c32 * 32 + i;
+            const int qi = q0 + col;
+            float s = __uint_as_float(sv[i]) * p.scale_log2;
+            if (p.bias && qi < p.tq && kvi < p.tk) s += p.bias[((long long)head * p.tq + qi) * p.tk + kvi] * kLog2e;
+            const bool ok = (qi < p.tq) && (kvi < p.tk) && (!p.causal || kvi <= qi + (p.tk - p.tq));
+            const float e = ok ? ex2_approx(s - st[col]) : 0.f;
+            pt[i] = e;
+            ds[i] = e * fmaf(__uint_as_float(dv[i]), p.scale, -st[128 + col]);
+          }
         }
         store_row_chunk(smem + OFF_PT, r, c32, pt);
         store_row_chunk(smem + OFF_DST, r, c32, ds);
@@ -388,15 +407,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant
     if (qi < p.tq) {
       const long long idx = ((long long)b * p.heads + head) * p.tq + qi;
       lse2 = p.lse[idx] * kLog2e;
-      delta = p.delta[idx];
+      delta = p.delta[idx] * p.scale;
     }
+    const bool lean = !p.causal && p.bias == nullptr;
     const int causal_lim = p.causal ? qi + (p.tk - p.tq) : 0x7fffffff;
     for (int it = 0; it < n_iter; ++it) {
       const int k0 = it * 128;
       mbar_wait(&bars[B_SFULL], it & 1);
       tc_fence_after_sync();
       mbar_wait(&bars[B_DSEMPTY], (it & 1) ^ 1);
-#pragma unroll
+#pragma unroll 1
       for (int cc = 0; cc < 2; ++cc) {
         const int c32 = half * 2 + cc;
         uint32_t sv[32], dv[32];
@@ -404,14 +424,22 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant
         tmem_ld_x32(t_lane + COL_DP + c32 * 32, dv);
         tmem_ld_wait();
         float ds[32];
+        if (lean) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int kvi = k0 + c32 * 32 + i;
-          float s = __uint_as_float(sv[i]) * p.scale_log2;
-          if (p.bias && qi < p.tq && kvi < p.tk) s += p.bias[((long long)head * p.tq + qi) * p.tk + kvi] * kLog2e;
-          const bool ok = (qi < p.tq) && (kvi < p.tk) && (kvi <= causal_lim);
-          const float e = ok ? exp2f(s - lse2) : 0.f;
-          ds[i] = e * (__uint_as_float(dv[i]) - delta) * p.scale;
+          for (int i = 0; i < 32; ++i) {
+            const float e = ex2_approx(fmaf(__uint_as_float(sv[i]), p.scale_log2, -lse2));
+            ds[i] = e * fmaf(__uint_as_float(dv[i]), p.scale, -delta);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int kvi = k0 + c32 * 32 + i;
+            float s = __uint_as_float(sv[i]) * p.scale_log2;
+            if (p.bias && qi < p.tq && kvi < p.tk) s += p.bias[((long long)head * p.tq + qi) * p.tk + kvi] * kLog2e;
+            const bool ok = (qi < p.tq) && (kvi < p.tk) && (kvi <= causal_lim);
+            const float e = ok ? ex2_approx(s - lse2) : 0.f;
+            ds[i] = e * fmaf(__uint_as_float(dv[i]), p.scale, -delta);
+          }
         }
         store_row_chunk(smem + OFF_DS, r, c32, ds);
       }

@@ -165,45 +165,69 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq_map, const __grid_constan
       mbar_wait(&bars[B_SFULL], j & 1);
       tc_fence_after_sync();
       const int c_base = j * BKV;
-      // ---- pass 1: tile max
+      // A tile needs per-element masking only when it is cut by the key length, by the causal
+      // diagonal, or when an additive bias is present; everything else takes the lean path
+      // (1 FMNMX per score in pass 1; FFMA + MUFU.EX2 + FADD + half a pack in pass 2).
+      const bool lean = (bias_row == nullptr) && (c_base + BKV <= p.tk) &&
+                        (!p.causal || c_base + BKV - 1 <= q0 + (p.tk - p.tq));
       float tmax = -INFINITY;
+      if (lean) {
 #pragma unroll
-      for (int c = 0; c < BKV / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_x32(t_lane + COL_S + c * 32, v);
-        tmem_ld_wait();
+        for (int c = 0; c < BKV / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_x32(t_lane + COL_S + c * 32, v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int col = c_base + c * 32 + i;
-          float s = __uint_as_float(v[i]) * p.scale_log2;
-          if (bias_row && col < p.tk) s += bias_row[col] * 1.4426950408889634f;
-          s = (col < p.tk && col <= causal_lim) ? s : -INFINITY;
-          tmax = fmaxf(tmax, s);
+          for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, __uint_as_float(v[i]));
+        }
+        tmax *= p.scale_log2;
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BKV / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_x32(t_lane + COL_S + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int col = c_base + c * 32 + i;
+            float s = __uint_as_float(v[i]) * p.scale_log2;
+            if (bias_row && col < p.tk) s += bias_row[col] * 1.4426950408889634f;
+            s = (col < p.tk && col <= causal_lim) ? s : -INFINITY;
+            tmax = fmaxf(tmax, s);
+          }
         }
       }
       const float m_new = fmaxf(m, tmax);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = exp2f(m - m_use);
+      const float alpha = ex2_approx(m - m_use);
       if (j > 0) {  // PV_{j-1} finished: its result is readable and the P buffer is free again
         mbar_wait(&bars[B_PVFULL + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
         tc_fence_after_sync();
       }
       // ---- pass 2: probabilities -> smem (bf16, swizzled K-major), row sum
       float lt = 0.f;
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < BKV / 32; ++c) {
         uint32_t v[32];
         tmem_ld_x32(t_lane + COL_S + c * 32, v);
         tmem_ld_wait();
         float pr[32];
+        if (lean) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int col = c_base + c * 32 + i;
-          float s = __uint_as_float(v[i]) * p.scale_log2;
-          if (bias_row && col < p.tk) s += bias_row[col] * 1.4426950408889634f;
-          const float e = exp2f(s - m_use);
-          pr[i] = (col < p.tk && col <= causal_lim) ? e : 0.f;
-          lt += pr[i];
+          for (int i = 0; i < 32; ++i) {
+            pr[i] = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_use));
+            lt += pr[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int col = c_base + c * 32 + i;
+            float s = __uint_as_float(v[i]) * p.scale_log2;
+            if (bias_row && col < p.tk) s += bias_row[col] * 1.4426950408889634f;
+            const float e = ex2_approx(s - m_use);
+            pr[i] = (col < p.tk && col <= causal_lim) ? e : 0.f;
+            lt += pr[i];
+          }
         }
         // 32 columns = 4 chunks of 16 bytes inside K-block (c>>1), chunk index (c&1)*4 + k
         uint8_t* blk = p_row + (c >> 1) * (BQ * 128);

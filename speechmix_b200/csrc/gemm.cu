@@ -26,7 +26,8 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int PANEL_BYTES = 64 * BK * 2;  // one 64(MN) x 64(K) MN-major panel, 8 KiB
 constexpr int BAR_BYTES = 256;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
+constexpr int EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
 
 struct Params {
@@ -73,7 +74,114 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& p, int tile) {
   return t;
 }
 
-template <int MODE>
+// ---------------------------------------------------------------------------------------------
+// Epilogue helpers.  The common case (a full 32-column chunk with 16-byte aligned rows) is a compact
+// straight-line path; ragged / unaligned chunks go through a small out-of-line scalar routine so the
+// hot loop stays inside the instruction cache (an earlier fully-unrolled version was I$-bound).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  f[0] = bf16_lo(u.x), f[1] = bf16_hi(u.x), f[2] = bf16_lo(u.y), f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z), f[5] = bf16_hi(u.z), f[6] = bf16_lo(u.w), f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]), u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]), u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+
+// generic path: any n, any alignment (per-element predicates; only instantiated in the <FAST = false> kernels)
+__device__ __forceinline__ void epilogue_chunk_generic(const Params& p, float (&f)[32], long long c_off,
+                                                       long long res_off, int col0) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int col = col0 + j;
+    if (col < p.n) {
+      float v = p.alpha * f[j];
+      if (p.bias) v += __ldg(p.bias + col);
+      if (p.aux_out) p.aux_out[c_off + col] = __float2bfloat16(v);
+      if (p.act == SMX_ACT_GELU) v = gelu_erf(v);
+      else if (p.act == SMX_ACT_RELU) v = fmaxf(v, 0.f);
+      else if (p.act == SMX_ACT_DGELU) v *= gelu_erf_grad(__bfloat162float(p.aux_in[c_off + col]));
+      else if (p.act == SMX_ACT_DRELU) v = __bfloat162float(p.aux_in[c_off + col]) > 0.f ? v : 0.f;
+      if (p.residual) v += __bfloat162float(p.residual[res_off + col]);
+      if (p.out_f32) {
+        float* cp = reinterpret_cast<float*>(p.c) + c_off + col;
+        *cp = p.accumulate_f32 ? *cp + v : v;
+      } else {
+        reinterpret_cast<bf16*>(p.c)[c_off + col] = __float2bfloat16(v);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void epilogue_chunk_fast(const Params& p, float (&f)[32], long long c_off,
+                                                    long long res_off, int col0) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] *= p.alpha;
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+      f[j] += b4.x, f[j + 1] += b4.y, f[j + 2] += b4.z, f[j + 3] += b4.w;
+    }
+  }
+  if (p.aux_out) {
+    bf16* ap = p.aux_out + c_off + col0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) *reinterpret_cast<uint4*>(ap + j) = pack8(f + j);
+  }
+  const bool has_dact = p.act == SMX_ACT_DGELU || p.act == SMX_ACT_DRELU;
+  if (p.act == SMX_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+  } else if (p.act == SMX_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+  } else if (has_dact) {
+    const bool dg = p.act == SMX_ACT_DGELU;
+    const bf16* xp = p.aux_in + c_off + col0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      float x[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(xp + j)), x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[j + i] = dg ? f[j + i] * gelu_erf_grad(x[i]) : (x[i] > 0.0f ? f[j + i] : 0.0f);
+    }
+  }
+  if (p.residual) {
+    const bf16* rp = p.residual + res_off + col0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      float x[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(rp + j)), x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[j + i] += x[i];
+    }
+  }
+  if (p.out_f32) {
+    float* cp = reinterpret_cast<float*>(p.c) + c_off + col0;
+    if (p.accumulate_f32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 o = *reinterpret_cast<float4*>(cp + j);
+        o.x += f[j], o.y += f[j + 1], o.z += f[j + 2], o.w += f[j + 3];
+        *reinterpret_cast<float4*>(cp + j) = o;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+    }
+  } else {
+    bf16* cp = reinterpret_cast<bf16*>(p.c) + c_off + col0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) *reinterpret_cast<uint4*>(cp + j) = pack8(f + j);
+  }
+}
+
+// EPI: 0 regular fused epilogue, 1 LM-head statistics, 2 LM-head dlogits.  FAST: n % 32 == 0 and every
+// pointer / stride 16-byte aligned, so the epilogue is pure vector code (smaller I$ footprint).
+template <int MODE, int EPI, bool FAST>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -94,7 +202,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], EPI_WARPS);
     }
     fence_barrier_init();
     tma_prefetch_desc(&tma_a);
@@ -110,60 +218,84 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
-        const int n0 = t.n_blk * BN;
-        int bidx = 0, r0 = 0, m0 = 0;
-        if (MODE == SMX_GEMM_TN) {
-          m0 = t.m_blk * BM;
-        } else {
-          bidx = t.m_blk / p.m_tiles_per_batch;
-          r0 = (t.m_blk % p.m_tiles_per_batch) * BM;
+    // Lane 0 owns the ring (waits for a free slot, arms the barrier); the boxes of a stage are then
+    // issued by different lanes in parallel, each with coordinates it tracks incrementally, so no
+    // integer division or serial descriptor math sits on the per-k-block critical path.
+    constexpr int N_BOXES = MODE == SMX_GEMM_NT ? 2 : (MODE == SMX_GEMM_NN ? 1 + BN / 64 : BM / 64 + BN / 64);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int n0 = t.n_blk * BN;
+      // per-lane constants of this tile
+      int c0_fixed = 0, row_fixed = 0, batch = 0, smem_off = 0;
+      bool is_a = false, active = lane < N_BOXES;
+      if (MODE == SMX_GEMM_TN) {
+        const int m0 = t.m_blk * BM;
+        if (lane < BM / 64) {
+          is_a = true;
+          c0_fixed = p.a_col_off[0] + m0 + 64 * lane;
+          row_fixed = p.a_row_off[0];
+          smem_off = lane * PANEL_BYTES;
+        } else if (active) {
+          const int pn = lane - BM / 64;
+          const int nn = n0 + 64 * pn;
+          c0_fixed = p.b_inner_oob;
+          if (nn < p.n) {
+            const int s = nn / p.seg_len;
+            c0_fixed = p.b_col_off[s] + (nn - s * p.seg_len);
+            row_fixed = p.b_row_off[s];
+          }
+          smem_off = A_BYTES + pn * PANEL_BYTES;
         }
-        for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
+      } else {
+        batch = t.m_blk / p.m_tiles_per_batch;
+        row_fixed = (t.m_blk % p.m_tiles_per_batch) * BM;
+        if (lane == 0) {
+          is_a = true;
+        } else if (active) {
+          smem_off = A_BYTES + (lane - 1) * PANEL_BYTES;
+          c0_fixed = MODE == SMX_GEMM_NT ? n0 : n0 + 64 * (lane - 1);
+        }
+      }
+      // running contraction position
+      int seg = 0, kin = 0, cb = 0, cr0 = 0;
+      if (MODE == SMX_GEMM_TN) {
+        cb = t.kb_begin / p.kb_per_batch;
+        cr0 = (t.kb_begin % p.kb_per_batch) * BK;
+      } else {
+        const int k0 = t.kb_begin * BK;
+        seg = k0 / p.seg_len;
+        kin = k0 - seg * p.seg_len;
+      }
+      for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
+        if (lane == 0) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], STAGE_BYTES);
-          uint8_t* sa = smem + stage * STAGE_BYTES;
-          uint8_t* sb = sa + A_BYTES;
+        }
+        __syncwarp();
+        if (active) {
+          uint8_t* dst = smem + stage * STAGE_BYTES + smem_off;
           if (MODE == SMX_GEMM_TN) {
-            const int cb = kb / p.kb_per_batch;
-            const int cr0 = (kb % p.kb_per_batch) * BK;
-#pragma unroll
-            for (int pn = 0; pn < BM / 64; ++pn)
-              tma_load_3d(sa + pn * PANEL_BYTES, &tma_a, &full[stage], p.a_col_off[0] + m0 + 64 * pn,
-                          cr0 + p.a_row_off[0], cb);
-#pragma unroll
-            for (int pn = 0; pn < BN / 64; ++pn) {
-              const int nn = n0 + 64 * pn;
-              int c0 = p.b_inner_oob, roff = 0;
-              if (nn < p.n) {
-                const int s = nn / p.seg_len;
-                c0 = p.b_col_off[s] + (nn - s * p.seg_len);
-                roff = p.b_row_off[s];
-              }
-              tma_load_3d(sb + pn * PANEL_BYTES, &tma_b, &full[stage], c0, cr0 + roff, cb);
-            }
+            tma_load_3d(dst, is_a ? &tma_a : &tma_b, &full[stage], c0_fixed, cr0 + row_fixed, cb);
+          } else if (is_a) {
+            tma_load_3d(dst, &tma_a, &full[stage], p.a_col_off[seg] + kin, row_fixed + p.a_row_off[seg], batch);
+          } else if (MODE == SMX_GEMM_NT) {
+            tma_load_2d(dst, &tma_b, &full[stage], p.b_col_off[seg] + kin, c0_fixed);
           } else {
-            const int k0 = kb * BK;
-            const int s = k0 / p.seg_len;
-            const int kin = k0 - s * p.seg_len;
-            tma_load_3d(sa, &tma_a, &full[stage], p.a_col_off[s] + kin, r0 + p.a_row_off[s], bidx);
-            if (MODE == SMX_GEMM_NT) {
-              tma_load_2d(sb, &tma_b, &full[stage], p.b_col_off[s] + kin, n0);
-            } else {
-#pragma unroll
-              for (int pn = 0; pn < BN / 64; ++pn)
-                tma_load_2d(sb + pn * PANEL_BYTES, &tma_b, &full[stage], p.b_col_off[s] + n0 + 64 * pn,
-                            p.b_row_off[s] + kin);
-            }
+            tma_load_2d(dst, &tma_b, &full[stage], p.b_col_off[seg] + c0_fixed, p.b_row_off[seg] + kin);
           }
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        if (MODE == SMX_GEMM_TN) {
+          cr0 += BK;
+          if (cr0 >= p.kb_per_batch * BK) cr0 = 0, ++cb;
+        } else {
+          kin += BK;
+          if (kin >= p.seg_len) kin = 0, ++seg;
+        }
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
@@ -210,46 +342,45 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // two warps share a lane quarter: columns [0,128) / [128,256)
+    const int c_begin = half * (BN / 64), c_end = c_begin + BN / 64;
     const int row_in_tile = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool c_vec_ok = (p.c_row_stride % 8 == 0) && (p.c_batch_stride % 8 == 0) &&
-                          ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
-    const bool res_vec_ok = p.residual == nullptr ||
-                            ((p.res_row_stride % 8 == 0) && (p.res_batch_stride % 8 == 0) &&
-                             ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0));
-    const bool aux_vec_ok = ((p.aux_out == nullptr) || ((reinterpret_cast<uintptr_t>(p.aux_out) & 15) == 0)) &&
-                            ((p.aux_in == nullptr) || ((reinterpret_cast<uintptr_t>(p.aux_in) & 15) == 0));
+    const bool vec_ok = (p.c_row_stride % 8 == 0) && (p.c_batch_stride % 8 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0) &&
+                        (p.residual == nullptr || ((p.res_row_stride % 8 == 0) && (p.res_batch_stride % 8 == 0) &&
+                                                   ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0))) &&
+                        ((p.aux_out == nullptr) || ((reinterpret_cast<uintptr_t>(p.aux_out) & 15) == 0)) &&
+                        ((p.aux_in == nullptr) || ((reinterpret_cast<uintptr_t>(p.aux_in) & 15) == 0)) &&
+                        (p.bias == nullptr || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       const int n0 = t.n_blk * BN;
-      long long row, row_limit;
-      long long c_off, res_off = 0;
+      long long row, c_off, res_off = 0;
       if (MODE == SMX_GEMM_TN) {
         row = (long long)t.m_blk * BM + row_in_tile;
-        row_limit = p.m;
         c_off = row * p.c_row_stride;
       } else {
         const int bidx = t.m_blk / p.m_tiles_per_batch;
         row = (long long)(t.m_blk % p.m_tiles_per_batch) * BM + row_in_tile;
-        row_limit = p.m;
         c_off = (long long)bidx * p.c_batch_stride + row * p.c_row_stride;
         res_off = (long long)bidx * p.res_batch_stride + row * p.res_row_stride;
       }
-      const bool row_ok = row < row_limit;
+      const bool row_ok = row < p.m;
 
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 
-      if (MODE == SMX_GEMM_NT && p.epi == 1) {
-        // ---- LM head: online softmax statistics of this 256-column vocabulary tile, one row per thread
+      if (MODE == SMX_GEMM_NT && EPI == 1) {
+        // ---- LM head: online softmax statistics of this half of a 256-column vocabulary tile
         float mx = -INFINITY, se = 0.f, best = -INFINITY;
         int best_idx = 0x7fffffff;
         const long long label = row_ok ? p.lm_labels[row] : -1;
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = c_begin; c < c_end; ++c) {
           const int col0 = n0 + c * 32;
           if (col0 >= p.n) break;
           uint32_t v[32];
@@ -284,13 +415,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           }
           __syncwarp();
         }
-        if (row_ok) p.lm_partial[row * p.n_tiles + t.n_blk] = make_float4(mx, se, best, __int_as_float(best_idx));
-      } else if (MODE == SMX_GEMM_NT && p.epi == 2) {
+        if (row_ok)
+          p.lm_partial[(row * p.n_tiles + t.n_blk) * 2 + half] = make_float4(mx, se, best, __int_as_float(best_idx));
+      } else if (MODE == SMX_GEMM_NT && EPI == 2) {
         // ---- LM head backward: dlogits = (softmax - onehot) * coef, bf16
         const float lse = row_ok ? p.lm_lse[row] : 0.f;
         const float coef = row_ok ? p.lm_coef[row] : 0.f;
         const long long label = row_ok ? p.lm_labels[row] - p.lm_label_off : -1;
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = c_begin; c < c_end; ++c) {
           const int col0 = n0 + c * 32;
           if (col0 >= p.n) break;
           uint32_t v[32];
@@ -308,16 +440,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               f[j] = g;
             }
             bf16* cp = reinterpret_cast<bf16*>(p.c) + c_off + col0;
-            if (col0 + 32 <= p.n && c_vec_ok) {
+            if (col0 + 32 <= p.n && vec_ok) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 u;
-                u.x = pack_bf16x2(f[j], f[j + 1]);
-                u.y = pack_bf16x2(f[j + 2], f[j + 3]);
-                u.z = pack_bf16x2(f[j + 4], f[j + 5]);
-                u.w = pack_bf16x2(f[j + 6], f[j + 7]);
-                *reinterpret_cast<uint4*>(cp + j) = u;
-              }
+              for (int j = 0; j < 32; j += 8) *reinterpret_cast<uint4*>(cp + j) = pack8(f + j);
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
@@ -326,150 +451,73 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           }
           __syncwarp();
         }
-      } else
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= p.n) break;  // warp-uniform
-        uint32_t v[32];
-        tmem_ld_x32(t_row + c * 32, v);
-        tmem_ld_wait();
-        if (row_ok) {
-        float f[32];
+      } else if (MODE == SMX_GEMM_TN) {
+        // ---- weight gradient: fp32, atomics when the contraction is split
+        for (int c = c_begin; c < c_end; ++c) {
+          const int col0 = n0 + c * 32;
+          if (col0 >= p.n) break;
+          uint32_t v[32];
+          tmem_ld_x32(t_row + c * 32, v);
+          tmem_ld_wait();
+          if (row_ok) {
+            float* cp = reinterpret_cast<float*>(p.c) + c_off + col0;
+            const bool full_chunk = col0 + 32 <= p.n;
+            if (p.atomic) {
+              if (full_chunk) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = p.alpha * __uint_as_float(v[j]);
-        const bool full_chunk = (col0 + 32 <= p.n);
-
-        if (MODE == SMX_GEMM_TN) {
-          float* cp = reinterpret_cast<float*>(p.c) + c_off + col0;
-          if (p.atomic) {
+                for (int j = 0; j < 32; ++j) atomicAdd(cp + j, p.alpha * __uint_as_float(v[j]));
+              } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.n) atomicAdd(cp + j, f[j]);
-          } else if (full_chunk && (p.c_row_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0)) {
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.n) atomicAdd(cp + j, p.alpha * __uint_as_float(v[j]));
+              }
+            } else if (full_chunk && (p.c_row_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(cp + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          } else {
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(cp + j) =
+                    make_float4(p.alpha * __uint_as_float(v[j]), p.alpha * __uint_as_float(v[j + 1]),
+                                p.alpha * __uint_as_float(v[j + 2]), p.alpha * __uint_as_float(v[j + 3]));
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.n) cp[j] = f[j];
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.n) cp[j] = p.alpha * __uint_as_float(v[j]);
+            }
+          }
+          __syncwarp();
+        }
+      } else {
+        // ---- regular fused epilogue
+        if (FAST) {
+          for (int c = c_begin; c < c_end; ++c) {
+            const int col0 = n0 + c * 32;
+            if (col0 >= p.n) break;  // warp-uniform
+            uint32_t v[32];
+            tmem_ld_x32(t_row + c * 32, v);
+            tmem_ld_wait();
+            if (row_ok) {
+              float f[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+              epilogue_chunk_fast(p, f, c_off, res_off, col0);
+            }
+            __syncwarp();
           }
         } else {
-
-        if (p.bias) {
-          if (full_chunk) {
+          for (int c = c_begin; c < c_end; ++c) {
+            const int col0 = n0 + c * 32;
+            if (col0 >= p.n) break;  // warp-uniform
+            uint32_t v[32];
+            tmem_ld_x32(t_row + c * 32, v);
+            tmem_ld_wait();
+            if (row_ok) {
+              float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-              f[j] += b4.x;
-              f[j + 1] += b4.y;
-              f[j + 2] += b4.z;
-              f[j + 3] += b4.w;
+              for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+              epilogue_chunk_generic(p, f, c_off, res_off, col0);
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.n) f[j] += __ldg(p.bias + col0 + j);
+            __syncwarp();
           }
         }
-        const bool vec = full_chunk && c_vec_ok && res_vec_ok && aux_vec_ok;
-        if (p.aux_out) {
-          bf16* ap = p.aux_out + c_off + col0;
-          if (vec) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 u;
-              u.x = pack_bf16x2(f[j], f[j + 1]);
-              u.y = pack_bf16x2(f[j + 2], f[j + 3]);
-              u.z = pack_bf16x2(f[j + 4], f[j + 5]);
-              u.w = pack_bf16x2(f[j + 6], f[j + 7]);
-              *reinterpret_cast<uint4*>(ap + j) = u;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.n) ap[j] = __float2bfloat16(f[j]);
-          }
-        }
-        if (p.act == SMX_ACT_GELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-        } else if (p.act == SMX_ACT_RELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-        } else if (p.act == SMX_ACT_DGELU || p.act == SMX_ACT_DRELU) {
-          const bf16* xp = p.aux_in + c_off + col0;
-          float x[32];
-          if (vec) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const uint4 u = __ldg(reinterpret_cast<const uint4*>(xp + j));
-              x[j] = bf16_lo(u.x), x[j + 1] = bf16_hi(u.x);
-              x[j + 2] = bf16_lo(u.y), x[j + 3] = bf16_hi(u.y);
-              x[j + 4] = bf16_lo(u.z), x[j + 5] = bf16_hi(u.z);
-              x[j + 6] = bf16_lo(u.w), x[j + 7] = bf16_hi(u.w);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = (col0 + j < p.n) ? __bfloat162float(xp[j]) : 0.0f;
-          }
-          if (p.act == SMX_ACT_DGELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] *= gelu_erf_grad(x[j]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = x[j] > 0.0f ? f[j] : 0.0f;
-          }
-        }
-        if (p.residual) {
-          const bf16* rp = p.residual + res_off + col0;
-          if (vec) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp + j));
-              f[j] += bf16_lo(u.x), f[j + 1] += bf16_hi(u.x);
-              f[j + 2] += bf16_lo(u.y), f[j + 3] += bf16_hi(u.y);
-              f[j + 4] += bf16_lo(u.z), f[j + 5] += bf16_hi(u.z);
-              f[j + 6] += bf16_lo(u.w), f[j + 7] += bf16_hi(u.w);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.n) f[j] += __bfloat162float(rp[j]);
-          }
-        }
-        if (p.out_f32) {
-          float* cp = reinterpret_cast<float*>(p.c) + c_off + col0;
-          if (p.accumulate_f32) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.n) cp[j] += f[j];
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.n) cp[j] = f[j];
-          }
-        } else {
-          bf16* cp = reinterpret_cast<bf16*>(p.c) + c_off + col0;
-          if (vec) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 u;
-              u.x = pack_bf16x2(f[j], f[j + 1]);
-              u.y = pack_bf16x2(f[j + 2], f[j + 3]);
-              u.z = pack_bf16x2(f[j + 4], f[j + 5]);
-              u.w = pack_bf16x2(f[j + 6], f[j + 7]);
-              *reinterpret_cast<uint4*>(cp + j) = u;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.n) cp[j] = __float2bfloat16(f[j]);
-          }
-        }
-        }  // NT/NN epilogue
-        }  // row_ok
-        __syncwarp();
       }
       tc_fence_before_sync();
       __syncwarp();
@@ -484,18 +532,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int MODE>
+template <int MODE, int EPI, bool FAST>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    SMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<MODE, EPI, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        SMEM_BYTES));
     attr_set = true;
   }
   const int total = p.m_tiles * p.n_tiles * p.split_k;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, p);
+  gemm_kernel<MODE, EPI, FAST><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, p);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+static bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
+
+// all chunks full and every epilogue operand vectorisable?
+static bool fast_epilogue_ok(const Params& p) {
+  return p.n % 32 == 0 && p.c_row_stride % 8 == 0 && p.c_batch_stride % 8 == 0 && aligned16(p.c) &&
+         (!p.residual || (p.res_row_stride % 8 == 0 && p.res_batch_stride % 8 == 0 && aligned16(p.residual))) &&
+         aligned16(p.aux_out) && aligned16(p.aux_in) && aligned16(p.bias);
 }
 
 }  // namespace gemm
@@ -589,7 +647,7 @@ int smx::gemm::run(const SmxGemm* g, const LmExtra* lm, void* stream) {
     const uint32_t box[3] = {64, 64, 1};
     if (encode_tmap_bf16(&ta, g->a.ptr, 3, a_dims, a_str, box, true)) return -1;
     if (encode_tmap_bf16(&tb, g->b.ptr, 3, b_dims, b_str, box, true)) return -1;
-    return launch<SMX_GEMM_TN>(ta, tb, p, (cudaStream_t)stream);
+    return launch<SMX_GEMM_TN, 0, false>(ta, tb, p, (cudaStream_t)stream);
   }
 
   SMX_REQUIRE(g->k == (int64_t)g->nseg * g->seg_len, "smx_gemm: k %lld != nseg*seg_len", (long long)g->k);
@@ -604,9 +662,13 @@ int smx::gemm::run(const SmxGemm* g, const LmExtra* lm, void* stream) {
   if (g->mode == SMX_GEMM_NT) {
     const uint32_t b_box[2] = {64, 256};
     if (encode_tmap_bf16(&tb, g->b.ptr, 2, b_dims, b_str, b_box, true)) return -1;
-    return launch<SMX_GEMM_NT>(ta, tb, p, (cudaStream_t)stream);
+    if (p.epi == 1) return launch<SMX_GEMM_NT, 1, false>(ta, tb, p, (cudaStream_t)stream);
+    if (p.epi == 2) return launch<SMX_GEMM_NT, 2, false>(ta, tb, p, (cudaStream_t)stream);
+    return fast_epilogue_ok(p) ? launch<SMX_GEMM_NT, 0, true>(ta, tb, p, (cudaStream_t)stream)
+                               : launch<SMX_GEMM_NT, 0, false>(ta, tb, p, (cudaStream_t)stream);
   }
   const uint32_t b_box[2] = {64, 64};
   if (encode_tmap_bf16(&tb, g->b.ptr, 2, b_dims, b_str, b_box, true)) return -1;
-  return launch<SMX_GEMM_NN>(ta, tb, p, (cudaStream_t)stream);
+  return fast_epilogue_ok(p) ? launch<SMX_GEMM_NN, 0, true>(ta, tb, p, (cudaStream_t)stream)
+                             : launch<SMX_GEMM_NN, 0, false>(ta, tb, p, (cudaStream_t)stream);
 }

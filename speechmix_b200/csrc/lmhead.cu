@@ -94,8 +94,8 @@ static void fill_gemm(SmxGemm* g, const void* h, const void* emb, int64_t rows, 
 extern "C" {
 
 size_t smx_lmhead_ws_bytes(int64_t rows, int64_t vocab) {
-  const int64_t n_tiles = (vocab + 255) / 256;
-  return (size_t)(rows * n_tiles * 16 + rows * 4 + 256);
+  const int64_t n_parts = 2 * ((vocab + 255) / 256);  // two column halves per 256-wide vocabulary tile
+  return (size_t)(rows * n_parts * 16 + rows * 4 + 256);
 }
 
 int smx_lmhead_ce_fwd(const void* h, const void* emb, const float* bias, const int64_t* labels, float* lse,
@@ -104,7 +104,7 @@ int smx_lmhead_ce_fwd(const void* h, const void* emb, const float* bias, const i
   using namespace smx;
   SMX_REQUIRE(h && emb && lse && workspace, "lmhead_ce_fwd: null pointer");
   SMX_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "lmhead_ce_fwd: workspace must be 16-byte aligned");
-  const int64_t n_tiles = (vocab + 255) / 256;
+  const int64_t n_tiles = 2 * ((vocab + 255) / 256);
   float4* partial = reinterpret_cast<float4*>(workspace);
   float* label_logit = reinterpret_cast<float*>(partial + rows * n_tiles);
   cudaStream_t st = (cudaStream_t)stream;

@@ -100,7 +100,7 @@ def shard_batch(global_batch, rank, world):
 def init_like_reference(model, seed=0):
     """Random initialisation with the statistics of the transformers initialisers
     (hf:...wav2vec2.py _init_weights, hf:...bart.py _init_weights) -- used for synthetic
-    benchmarks where no checkpoint exists; parity tests load the oracle's weights instead."""
+    benchmarks where no checkpoint exists; parity tests load reference weights instead."""
     g = torch.Generator().manual_seed(seed)
     with torch.no_grad():
         for name, m in model.named_modules():

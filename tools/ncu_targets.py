@@ -1,0 +1,29 @@
+"""Small driver for ncu captures: runs each hot kernel a few times at the bench shapes."""
+import sys, os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from speechmix_b200 import kernels as K
+
+which = sys.argv[1:] or ["attn", "gemm"]
+g = torch.Generator(device="cuda").manual_seed(0)
+B, T, H = 32, 749, 12
+if "attn" in which:
+    qkv = torch.randn(B, T, 3 * H * 64, device="cuda", generator=g).to(torch.bfloat16)
+    q, k, v = qkv[..., :H * 64], qkv[..., H * 64:2 * H * 64], qkv[..., 2 * H * 64:]
+    do = torch.randn(B, T, H * 64, device="cuda", generator=g).to(torch.bfloat16)
+    for _ in range(2):
+        o, lse = K.attn_fwd(q, k, v, H)
+        K.attn_bwd(do, q, k, v, o, lse, H)
+if "gemm" in which:
+    M, N, Kd = B * T, 3072, 768
+    x = torch.randn(M, Kd, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, Kd, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    b = torch.randn(N, device="cuda", generator=g)
+    dy = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16)
+    for _ in range(2):
+        y, pre = K.linear_fwd(x, w, bias=b, act=K.ACT_GELU, want_pre=True)   # NT + GELU epilogue
+        K.linear_fwd(x, w)                                                    # NT plain
+        K.linear_wgrad(dy, x)                                                 # TN
+        K.linear_dgrad(dy, w)                                                 # NN
+torch.cuda.synchronize()

@@ -149,35 +149,52 @@ def conv_all():
 def perf():
     import torch
     from speechmix_b200 import kernels as K
+
+    def timeit(fn, iters=20):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
     shapes = [("ffn1", 23968, 3072, 768), ("ffn2", 23968, 768, 3072), ("qkv", 23968, 2304, 768),
               ("proj", 23968, 768, 768), ("8k", 8192, 8192, 8192)]
     for name, M, N, Kd in shapes:
         x, w = _mk((M, Kd), seed=1), _mk((N, Kd), 0.05, seed=2)
-        for _ in range(3):
-            K.linear_fwd(x, w)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        iters = 20
-        for _ in range(iters):
-            K.linear_fwd(x, w)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / iters
-        print(json.dumps({"perf": name, "mode": "nt", "M": M, "N": N, "K": Kd, "ms": ms,
-                          "tflops": 2.0 * M * N * Kd / ms / 1e9}), flush=True)
         dy = _mk((M, N), seed=3)
-        for fn, nm in ((lambda: K.linear_dgrad(dy, w), "nn"), (lambda: K.linear_wgrad(dy, x), "tn")):
-            for _ in range(3):
-                fn()
-            torch.cuda.synchronize()
-            e0.record()
-            for _ in range(iters):
-                fn()
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / iters
-            print(json.dumps({"perf": name, "mode": nm, "ms": ms, "tflops": 2.0 * M * N * Kd / ms / 1e9}), flush=True)
+        b = torch.randn(N, device="cuda")
+        pre = _mk((M, Kd), seed=4)
+        r = _mk((M, N), seed=5)
+        fl = 2.0 * M * N * Kd
+        variants = [("nt", lambda: K.linear_fwd(x, w)),
+                    ("nt+bias+gelu+pre", lambda: K.linear_fwd(x, w, bias=b, act=K.ACT_GELU, want_pre=True)),
+                    ("nt+bias+res", lambda: K.linear_fwd(x, w, bias=b, residual=r)),
+                    ("nn", lambda: K.linear_dgrad(dy, w)),
+                    ("nn+dgelu", lambda: K.linear_dgrad(dy, w, act=K.ACT_DGELU, aux_in=pre)),
+                    ("tn", lambda: K.linear_wgrad(dy, x))]
+        for nm, fn in variants:
+            ms = timeit(fn)
+            print(json.dumps({"perf": name, "mode": nm, "M": M, "N": N, "K": Kd, "ms": round(ms, 4),
+                              "tflops": round(fl / ms / 1e9, 1)}), flush=True)
+    # conv1 of the feature encoder at the bench shape
+    B, T, C = 32, 47999, 512
+    xa = K.alloc_act(B, T, C, "cuda")
+    xa.normal_()
+    wp = K.pack_conv_weight(torch.randn(512, 512, 3, device="cuda") * 0.03)
+    y, pre = K.conv_s2_fwd(xa, wp, 3, act=K.ACT_GELU, want_pre=True)
+    dya = K.alloc_act(B, y.shape[1], 512, "cuda")
+    dya.normal_()
+    fl = 2.0 * B * y.shape[1] * 512 * 1536
+    for nm, fn in [("conv1 fwd+gelu+pre", lambda: K.conv_s2_fwd(xa, wp, 3, act=K.ACT_GELU, want_pre=True)),
+                   ("conv1 dgrad", lambda: K.conv_s2_dgrad(dya, wp, 3, T)),
+                   ("conv1 wgrad", lambda: K.conv_s2_wgrad(dya, xa, 3))]:
+        ms = timeit(fn, 5)
+        print(json.dumps({"perf": nm, "ms": round(ms, 4), "tflops": round(fl / ms / 1e9, 1)}), flush=True)
     return True
 
 
