@@ -25,7 +25,10 @@ constexpr int B_BYTES = BN * BK * 2;  // 32 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int PANEL_BYTES = 64 * BK * 2;  // one 64(MN) x 64(K) MN-major panel, 8 KiB
 constexpr int BAR_BYTES = 256;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+constexpr int STG_BYTES = 32 * 128;  // per epilogue warp: 32 rows x 64 bf16, 128B-swizzled, TMA-store staging
+constexpr int OFF_STG = STAGES * STAGE_BYTES;
+constexpr int OFF_BAR = OFF_STG + 8 * STG_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + BAR_BYTES + 1024;
 constexpr int NUM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;
@@ -57,6 +60,8 @@ struct Params {
   const float* lm_lse;       // [rows]
   const float* lm_coef;      // [rows]
   long long lm_label_off;    // vocab index of column 0 of this launch
+  int tma_store;             // bf16 C (and aux_out) leave through smem staging + TMA stores
+  int tma_in;                // 1: aux_in, 2: residual arrives through a TMA load into the staging tile
 };
 
 struct TileCoord {
@@ -179,18 +184,101 @@ __device__ __forceinline__ void epilogue_chunk_fast(const Params& p, float (&f)[
   }
 }
 
+// ---- pieces of the fast epilogue used by the TMA-store variant (64 columns per step) ----
+__device__ __forceinline__ void epi_scale_bias(const Params& p, float (&f)[64], int col0) {
+#pragma unroll
+  for (int j = 0; j < 64; ++j) f[j] *= p.alpha;
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < 64; j += 4) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+      f[j] += b4.x, f[j + 1] += b4.y, f[j + 2] += b4.z, f[j + 3] += b4.w;
+    }
+  }
+}
+__device__ __forceinline__ void epi_act_res(const Params& p, float (&f)[64], long long c_off, long long res_off,
+                                            int col0) {
+  if (p.act == SMX_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) f[j] = gelu_erf(f[j]);
+  } else if (p.act == SMX_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) f[j] = fmaxf(f[j], 0.0f);
+  } else if (p.act == SMX_ACT_DGELU || p.act == SMX_ACT_DRELU) {
+    const bool dg = p.act == SMX_ACT_DGELU;
+    const bf16* xp = p.aux_in + c_off + col0;
+#pragma unroll
+    for (int j = 0; j < 64; j += 8) {
+      float x[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(xp + j)), x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[j + i] = dg ? f[j + i] * gelu_erf_grad(x[i]) : (x[i] > 0.0f ? f[j + i] : 0.0f);
+    }
+  }
+  if (p.residual) {
+    const bf16* rp = p.residual + res_off + col0;
+#pragma unroll
+    for (int j = 0; j < 64; j += 8) {
+      float x[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(rp + j)), x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[j + i] += x[i];
+    }
+  }
+}
+// same, with the 64 bf16 of aux_in (tma_in == 1) or residual (tma_in == 2) already in registers
+__device__ __forceinline__ void epi_act_res_pre(const Params& p, float (&f)[64], const uint4 (&pre)[8], long long c_off,
+                                                long long res_off, int col0) {
+  if (p.act == SMX_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) f[j] = gelu_erf(f[j]);
+  } else if (p.act == SMX_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) f[j] = fmaxf(f[j], 0.0f);
+  } else if (p.act == SMX_ACT_DGELU || p.act == SMX_ACT_DRELU) {
+    const bool dg = p.act == SMX_ACT_DGELU;
+#pragma unroll
+    for (int j = 0; j < 64; j += 8) {
+      float x[8];
+      unpack8(pre[j >> 3], x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[j + i] = dg ? f[j + i] * gelu_erf_grad(x[i]) : (x[i] > 0.0f ? f[j + i] : 0.0f);
+    }
+  }
+  if (p.residual) {
+    const bf16* rp = p.residual + res_off + col0;
+#pragma unroll
+    for (int j = 0; j < 64; j += 8) {
+      float x[8];
+      unpack8(p.tma_in == 2 ? pre[j >> 3] : __ldg(reinterpret_cast<const uint4*>(rp + j)), x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[j + i] += x[i];
+    }
+  }
+}
+// one row (64 bf16 = 128 B) of the staging tile, 16-byte chunks XOR-swizzled with the row index
+__device__ __forceinline__ void stage_row(uint8_t* stg, int r, const float (&f)[64]) {
+  uint8_t* row = stg + r * 128;
+  const int sw = r & 7;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) *reinterpret_cast<uint4*>(row + ((k ^ sw) << 4)) = pack8(f + k * 8);
+}
+
 // EPI: 0 regular fused epilogue, 1 LM-head statistics, 2 LM-head dlogits.  FAST: n % 32 == 0 and every
 // pointer / stride 16-byte aligned, so the epilogue is pure vector code (smaller I$ footprint).
 template <int MODE, int EPI, bool FAST>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const Params p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+            const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_aux,
+            const __grid_constant__ CUtensorMap tma_in, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* inbar = tempty + 2;  // one per epilogue warp: staged epilogue-input tile has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(inbar + EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -204,6 +292,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], EPI_WARPS);
     }
+    for (int i = 0; i < EPI_WARPS; ++i) mbar_init(&inbar[i], 1);
     fence_barrier_init();
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
@@ -349,6 +438,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const int row_in_tile = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t in_phase = 0;
     const bool vec_ok = (p.c_row_stride % 8 == 0) && (p.c_batch_stride % 8 == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0) &&
                         (p.residual == nullptr || ((p.res_row_stride % 8 == 0) && (p.res_batch_stride % 8 == 0) &&
@@ -370,6 +460,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         res_off = (long long)bidx * p.res_batch_stride + row * p.res_row_stride;
       }
       const bool row_ok = row < p.m;
+
+      const bool use_in = FAST && EPI == 0 && MODE != SMX_GEMM_TN && p.tma_store && p.tma_in != 0;
+      uint8_t* stg = smem + OFF_STG + (warp - 2) * STG_BYTES;
+      int ep_bidx = 0, ep_row0 = 0;
+      if (MODE != SMX_GEMM_TN) {
+        ep_bidx = t.m_blk / p.m_tiles_per_batch;
+        ep_row0 = (t.m_blk % p.m_tiles_per_batch) * BM + q * 32;
+      }
+      if (use_in) {  // prefetch the first 64-column input tile while the accumulator is still being produced
+        const int col0 = n0 + c_begin * 32;
+        if (col0 + 32 < p.n && lane == 0) {
+          tma_store_wait_read<0>();
+          mbar_expect_tx(&inbar[warp - 2], STG_BYTES);
+          tma_load_3d(stg, &tma_in, &inbar[warp - 2], col0, ep_row0, ep_bidx);
+        }
+      }
 
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after_sync();
@@ -487,7 +593,82 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
       } else {
         // ---- regular fused epilogue
-        if (FAST) {
+        if (FAST && p.tma_store) {
+          // 64 columns per step: TMEM -> registers -> fused math -> swizzled smem tile -> one TMA store of
+          // full 128-byte row segments (coalesced; rows / columns past the edge are clipped by the map).
+          const int bidx = ep_bidx, row0 = ep_row0;
+#pragma unroll 1
+          for (int pr = 0; pr < BN / 128; ++pr) {
+            const int c = c_begin + 2 * pr;
+            const int col0 = n0 + c * 32;
+            if (col0 >= p.n) break;  // warp-uniform
+            float f[64];
+            {
+              uint32_t v[32];
+              tmem_ld_x32(t_row + c * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+              if (col0 + 32 < p.n) {
+                tmem_ld_x32(t_row + (c + 1) * 32, v);
+                tmem_ld_wait();
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[32 + j] = __uint_as_float(v[j]);
+            }
+            const bool two = col0 + 32 < p.n;  // n % 32 == 0 here, so the second chunk is all-or-nothing
+            if (row_ok) {
+              if (two) {
+                epi_scale_bias(p, f, col0);
+              } else {
+                float g[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) g[j] = f[j];
+                epilogue_chunk_fast(p, g, c_off, res_off, col0);  // lone trailing chunk: direct path
+              }
+            }
+            if (two) {
+              if (p.aux_out) {
+                if (lane == 0) tma_store_wait_read<0>();
+                __syncwarp();
+                stage_row(stg, lane, f);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  tma_store_3d(&tma_aux, stg, col0, row0, bidx);
+                  tma_store_commit();
+                }
+              }
+              if (use_in) {
+                mbar_wait(&inbar[warp - 2], in_phase);
+                in_phase ^= 1;
+                uint4 pre[8];
+                const uint8_t* rowp = stg + lane * 128;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) pre[k] = *reinterpret_cast<const uint4*>(rowp + ((k ^ (lane & 7)) << 4));
+                __syncwarp();  // every lane has its input row before the tile is overwritten with the output
+                if (row_ok) epi_act_res_pre(p, f, pre, c_off, res_off, col0);
+              } else {
+                if (row_ok) epi_act_res(p, f, c_off, res_off, col0);
+                if (lane == 0) tma_store_wait_read<0>();
+                __syncwarp();
+              }
+              stage_row(stg, lane, f);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_3d(&tma_c, stg, col0, row0, bidx);
+                tma_store_commit();
+                if (use_in && pr + 1 < BN / 128 && col0 + 64 + 32 < p.n) {  // next input tile of this warp
+                  tma_store_wait_read<0>();
+                  mbar_expect_tx(&inbar[warp - 2], STG_BYTES);
+                  tma_load_3d(stg, &tma_in, &inbar[warp - 2], col0 + 64, row0, bidx);
+                }
+              }
+            }
+            __syncwarp();
+          }
+        } else if (FAST) {
           for (int c = c_begin; c < c_end; ++c) {
             const int col0 = n0 + c * 32;
             if (col0 >= p.n) break;  // warp-uniform
@@ -527,13 +708,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
   }
 
+  if (warp >= 2 && lane == 0) tma_store_wait_read<0>();  // staging smem must outlive the last bulk store's read
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 template <int MODE, int EPI, bool FAST>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t st) {
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tx,
+                  const CUtensorMap& ti, const Params& p, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     SMX_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<MODE, EPI, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -542,7 +725,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
   }
   const int total = p.m_tiles * p.n_tiles * p.split_k;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_kernel<MODE, EPI, FAST><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, p);
+  gemm_kernel<MODE, EPI, FAST><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, tc, tx, ti, p);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -575,6 +758,43 @@ int run(const SmxGemm* g, const LmExtra* lm, void* stream);
 }  // namespace smx
 
 extern "C" int smx_gemm(const SmxGemm* g, void* stream) { return smx::gemm::run(g, nullptr, stream); }
+
+// Tensor maps for the epilogue's TMA stores of C (and aux_out): bf16 [batches][m][n] with C's strides,
+// box 64 columns x 32 rows, 128-byte swizzle.  Falls back to direct stores for fp32 / accumulate outputs.
+static int make_store_maps(const SmxGemm* g, smx::gemm::Params* p, CUtensorMap* tc, CUtensorMap* tx, CUtensorMap* ti) {
+  using namespace smx;
+  p->tma_store = 0;
+  p->tma_in = 0;
+  *tc = CUtensorMap();
+  *tx = CUtensorMap();
+  *ti = CUtensorMap();
+  if (p->out_f32 || p->n < 64) return 0;
+  const uint64_t dims[3] = {(uint64_t)g->n, (uint64_t)g->m, (uint64_t)g->batches};
+  const uint64_t str[2] = {(uint64_t)g->c_row_stride,
+                           (uint64_t)(g->batches > 1 ? g->c_batch_stride : g->c_row_stride * g->m)};
+  const uint32_t box[3] = {64, 32, 1};
+  if (encode_tmap_bf16(tc, g->c, 3, dims, str, box, true)) return -1;
+  if (g->aux_out) {
+    if (encode_tmap_bf16(tx, g->aux_out, 3, dims, str, box, true)) return -1;
+  } else {
+    *tx = *tc;
+  }
+  *ti = *tc;
+  if (!g->aux_out) {  // the staging tile is free for an input: activation-gradient operand first, else the residual
+    const bool dact = g->act == SMX_ACT_DGELU || g->act == SMX_ACT_DRELU;
+    if (dact) {
+      if (encode_tmap_bf16(ti, g->aux_in, 3, dims, str, box, true)) return -1;
+      p->tma_in = 1;
+    } else if (g->residual) {
+      const uint64_t rstr[2] = {(uint64_t)g->res_row_stride,
+                                (uint64_t)(g->batches > 1 ? g->res_batch_stride : g->res_row_stride * g->m)};
+      if (encode_tmap_bf16(ti, g->residual, 3, dims, rstr, box, true)) return -1;
+      p->tma_in = 2;
+    }
+  }
+  p->tma_store = 1;
+  return 0;
+}
 
 int smx::gemm::run(const SmxGemm* g, const LmExtra* lm, void* stream) {
   using namespace smx;
@@ -625,7 +845,7 @@ int smx::gemm::run(const SmxGemm* g, const LmExtra* lm, void* stream) {
     p.lm_label_off = lm->label_off;
   }
 
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tc, tx, ti;
   const uint64_t a_dims[3] = {(uint64_t)g->a.inner, (uint64_t)g->a.rows, (uint64_t)g->a.batches};
   const uint64_t a_str[2] = {(uint64_t)g->a.row_stride,
                              (uint64_t)(g->a.batches > 1 ? g->a.batch_stride : g->a.row_stride * g->a.rows)};
@@ -647,7 +867,7 @@ int smx::gemm::run(const SmxGemm* g, const LmExtra* lm, void* stream) {
     const uint32_t box[3] = {64, 64, 1};
     if (encode_tmap_bf16(&ta, g->a.ptr, 3, a_dims, a_str, box, true)) return -1;
     if (encode_tmap_bf16(&tb, g->b.ptr, 3, b_dims, b_str, box, true)) return -1;
-    return launch<SMX_GEMM_TN, 0, false>(ta, tb, p, (cudaStream_t)stream);
+    return launch<SMX_GEMM_TN, 0, false>(ta, tb, ta, ta, ta, p, (cudaStream_t)stream);
   }
 
   SMX_REQUIRE(g->k == (int64_t)g->nseg * g->seg_len, "smx_gemm: k %lld != nseg*seg_len", (long long)g->k);
@@ -662,13 +882,15 @@ int smx::gemm::run(const SmxGemm* g, const LmExtra* lm, void* stream) {
   if (g->mode == SMX_GEMM_NT) {
     const uint32_t b_box[2] = {64, 256};
     if (encode_tmap_bf16(&tb, g->b.ptr, 2, b_dims, b_str, b_box, true)) return -1;
-    if (p.epi == 1) return launch<SMX_GEMM_NT, 1, false>(ta, tb, p, (cudaStream_t)stream);
-    if (p.epi == 2) return launch<SMX_GEMM_NT, 2, false>(ta, tb, p, (cudaStream_t)stream);
-    return fast_epilogue_ok(p) ? launch<SMX_GEMM_NT, 0, true>(ta, tb, p, (cudaStream_t)stream)
-                               : launch<SMX_GEMM_NT, 0, false>(ta, tb, p, (cudaStream_t)stream);
+    if (p.epi == 1) return launch<SMX_GEMM_NT, 1, false>(ta, tb, ta, ta, ta, p, (cudaStream_t)stream);
+    if (p.epi == 2) return launch<SMX_GEMM_NT, 2, false>(ta, tb, ta, ta, ta, p, (cudaStream_t)stream);
+    if (!fast_epilogue_ok(p)) return launch<SMX_GEMM_NT, 0, false>(ta, tb, ta, ta, ta, p, (cudaStream_t)stream);
+    if (make_store_maps(g, &p, &tc, &tx, &ti)) return -1;
+    return launch<SMX_GEMM_NT, 0, true>(ta, tb, tc, tx, ti, p, (cudaStream_t)stream);
   }
   const uint32_t b_box[2] = {64, 64};
   if (encode_tmap_bf16(&tb, g->b.ptr, 2, b_dims, b_str, b_box, true)) return -1;
-  return fast_epilogue_ok(p) ? launch<SMX_GEMM_NN, 0, true>(ta, tb, p, (cudaStream_t)stream)
-                             : launch<SMX_GEMM_NN, 0, false>(ta, tb, p, (cudaStream_t)stream);
+  if (!fast_epilogue_ok(p)) return launch<SMX_GEMM_NN, 0, false>(ta, tb, ta, ta, ta, p, (cudaStream_t)stream);
+  if (make_store_maps(g, &p, &tc, &tx, &ti)) return -1;
+  return launch<SMX_GEMM_NN, 0, true>(ta, tb, tc, tx, ti, p, (cudaStream_t)stream);
 }
