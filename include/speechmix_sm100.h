@@ -101,18 +101,19 @@ int smx_gemm(const SmxGemm* g, void* stream);
 /* ------------------------------------------------------------------------
  * Row-wise kernels (HBM-bound)
  * ------------------------------------------------------------------------ */
-/* y = LayerNorm(x (+ res)) * gamma + beta over the last dim (cols), eps as
- * given; optionally also writes sum = x + res (bf16) and per-row mean / rstd.
+/* y = act(LayerNorm(x (+ res)) * gamma + beta) over the last dim (cols), eps as
+ * given (act: SMX_ACT_NONE or SMX_ACT_GELU -- the "layer" feature-encoder convs,
+ * hf:...wav2vec2.py:275-299); optionally also writes sum = x + res (bf16) and per-row mean / rstd.
  * hf:...wav2vec2.py:422-434 (feature projection), :576-655 (encoder layers),
  * hf:...bart.py:261-391.  rms_only=1 gives T5 RMSNorm (hf:models/t5/modeling_t5.py:46-69). */
 int smx_layernorm_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* y,
                       void* sum_out, float* mean, float* rstd, int64_t rows, int64_t cols, float eps,
-                      int rms_only, void* stream);
+                      int rms_only, int act, void* stream);
 /* dx (+= dres_in) for the op above; dgamma/dbeta are ACCUMULATED (fp32 atomics)
  * into zero-initialised buffers. */
-int smx_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
-                      const void* dres_in, void* dx, float* dgamma, float* dbeta, int64_t rows, int64_t cols,
-                      int rms_only, void* stream);
+int smx_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* beta, const float* mean,
+                      const float* rstd, const void* dres_in, void* dx, float* dgamma, float* dbeta,
+                      int64_t rows, int64_t cols, int rms_only, int act, void* stream);
 
 /* out[n] (+)= sum_r x[r, n]   (bias gradients). fp32 accumulate via atomics into a zeroed buffer. */
 int smx_colsum(const void* x, float* out, int64_t rows, int64_t cols, int64_t row_stride, void* stream);
@@ -147,6 +148,20 @@ int smx_conv0_gn_gelu_bwd(const float* audio, const float* w, const float* gamma
                           const float* stats, const float* moments, const void* dy, float* partial, float* dw,
                           float* dgamma, float* dbeta, int64_t batch, int64_t n_samples, int64_t t_out,
                           int channels, int ksize, int stride, void* stream);
+
+/* feat_extract_norm="layer" variant of layer 0 (HuBERT-large / wav2vec2-large-lv60,
+ * hf:...wav2vec2.py:275-299): Conv1d(1->C,k,s,bias) -> LayerNorm over channels -> GELU, one warp per frame. */
+int smx_conv0_ln_gelu_fwd(const float* audio, const float* w, const float* conv_bias, const float* gamma,
+                          const float* beta, void* y, int64_t batch, int64_t n_samples, int64_t t_out,
+                          int channels, int ksize, int stride, float eps, void* stream);
+/* dconv = gradient w.r.t. the (biased) conv output, bf16 [B,T,C]; dgamma/dbeta accumulated into zeroed buffers */
+int smx_conv0_ln_gelu_bwd(const float* audio, const float* w, const float* conv_bias, const float* gamma,
+                          const float* beta, const void* dy, void* dconv, float* dgamma, float* dbeta,
+                          int64_t batch, int64_t n_samples, int64_t t_out, int channels, int ksize, int stride,
+                          float eps, void* stream);
+/* dw[C][k], dbias[C] (zeroed, accumulated) = correlation of dconv with the waveform windows */
+int smx_conv0_wgrad(const float* audio, const void* dconv, float* dw, float* dbias, int64_t batch,
+                    int64_t n_samples, int64_t t_out, int channels, int ksize, int stride, void* stream);
 
 /* ------------------------------------------------------------------------
  * Positional conv embedding: grouped Conv1d(H->H, k=128, pad=64, groups=16),

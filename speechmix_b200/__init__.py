@@ -6,8 +6,8 @@
 
 The CUDA library must be built first (``python -m speechmix_b200.build``); there is no fallback.
 """
-from .model import (HFSpeechMixEED, HFSpeechMixFixed, SpeechMixConfig, SpeechMixEED, SpeechMixFixed,  # noqa: F401
-                    handle_decoder_input_none, shift_tokens_right)
+from .model import (HFSpeechMixAdapter, HFSpeechMixEED, HFSpeechMixFixed, SpeechMixAdapter,  # noqa: F401
+                    SpeechMixConfig, SpeechMixEED, SpeechMixFixed, handle_decoder_input_none, shift_tokens_right)
 
-__all__ = ["SpeechMixEED", "SpeechMixFixed", "HFSpeechMixEED", "HFSpeechMixFixed", "SpeechMixConfig",
-           "shift_tokens_right", "handle_decoder_input_none"]
+__all__ = ["SpeechMixEED", "SpeechMixFixed", "SpeechMixAdapter", "HFSpeechMixEED", "HFSpeechMixFixed",
+           "HFSpeechMixAdapter", "SpeechMixConfig", "shift_tokens_right", "handle_decoder_input_none"]

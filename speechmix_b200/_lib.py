@@ -58,8 +58,8 @@ SIGNATURES = {
     "smx_abi_version": (c_int, []),
     "smx_device_ok": (c_int, []),
     "smx_gemm": (c_int, [POINTER(SmxGemm), _P]),
-    "smx_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, c_float, c_int, _P]),
-    "smx_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, c_int, _P]),
+    "smx_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, c_float, c_int, c_int, _P]),
+    "smx_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, c_int, c_int, _P]),
     "smx_colsum": (c_int, [_P, _P, _I64, _I64, _I64, _P]),
     "smx_cast_f32_to_bf16": (c_int, [_P, _P, _I64, _P]),
     "smx_add_bf16": (c_int, [_P, _P, _P, _I64, _P]),
@@ -70,6 +70,9 @@ SIGNATURES = {
     "smx_conv0_stats": (c_int, [_P, _P, _P, _P, _I64, _I64, _I64, c_int, c_int, c_int, c_float, _P]),
     "smx_conv0_gn_gelu_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, c_int, c_int, c_int, _P]),
     "smx_conv0_gn_gelu_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, c_int, c_int, c_int, _P]),
+    "smx_conv0_ln_gelu_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, c_int, c_int, c_int, c_float, _P]),
+    "smx_conv0_ln_gelu_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, c_int, c_int, c_int, c_float, _P]),
+    "smx_conv0_wgrad": (c_int, [_P, _P, _P, _P, _I64, _I64, _I64, c_int, c_int, c_int, _P]),
     "smx_posconv_fwd": (c_int, [_P, _P, _P, _P, _P, _I64, _I64, c_int, c_int, c_int, c_int, _P]),
     "smx_posconv_dgrad": (c_int, [_P, _P, _P, _P, _I64, _I64, c_int, c_int, c_int, _P]),
     "smx_posconv_wgrad": (c_int, [_P, _P, _P, _I64, _I64, c_int, c_int, c_int, _P]),
@@ -143,7 +146,7 @@ def load():
 
 # kernels launched per successful call (bench.py's gpu_launches); smx_gemm is counted by its caller
 KERNELS_PER_CALL = {"smx_attn_fwd": 1, "smx_attn_bwd": 3, "layernorm_fwd": 1, "layernorm_bwd": 1, "colsum": 1,
-                    "cast": 1, "add": 1, "dact": 1, "conv0_stats": 2, "conv0_fwd": 1, "conv0_bwd": 2,
+                    "cast": 1, "add": 1, "dact": 1, "conv0_stats": 2, "conv0_fwd": 1, "conv0_bwd": 2, "conv0_ln_fwd": 1, "conv0_ln_bwd": 1, "conv0_wgrad": 1,
                     "posconv_fwd": 1, "posconv_dgrad": 1, "posconv_wgrad": 1, "embed_fwd": 1, "embed_bwd": 1,
                     "lmhead_ce_fwd": 2, "lmhead_dlogits": 1, "wsum_fwd": 1, "wsum_bwd": 1}
 LAUNCHES = [0]

@@ -242,6 +242,160 @@ __global__ void bwd_finalize_kernel(const float* __restrict__ w, const float* __
   else dw[c * K + j] = (float)out;
 }
 
+
+// =====================================================================================
+// feat_extract_norm = "layer" variant (HuBERT-large / wav2vec2-large-lv60):
+//   Conv1d(1 -> C, k = 10, s = 5, bias) -> LayerNorm over the C channels of each frame -> GELU
+//   hf:models/wav2vec2/modeling_wav2vec2.py:275-299 (Wav2Vec2LayerNormConvLayer), layer 0.
+// One warp per frame, each lane owns C/32 channels; the conv is recomputed from the waveform in
+// backward, so only the activated output is ever stored.
+// =====================================================================================
+constexpr int LN_MAXC = 16;  // channels per lane (C <= 512)
+
+template <bool BWD>
+__global__ void __launch_bounds__(256) ln_variant_kernel(const float* __restrict__ audio, const float* __restrict__ w,
+                                                         const float* __restrict__ cbias, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, bf16* __restrict__ y,
+                                                         const bf16* __restrict__ dy, bf16* __restrict__ dconv,
+                                                         float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                         long long n_samples, long long t_out, long long total_frames,
+                                                         int channels, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int cpl = channels / 32;  // channels per lane, contiguous: [lane*cpl, lane*cpl + cpl)
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  float wl[LN_MAXC][K], bl[LN_MAXC], gl[LN_MAXC], btl[LN_MAXC];
+  float ag[LN_MAXC], ab[LN_MAXC];
+#pragma unroll
+  for (int j = 0; j < LN_MAXC; ++j) {
+    ag[j] = ab[j] = 0.f;
+    if (j < cpl) {
+      const int c = lane * cpl + j;
+#pragma unroll
+      for (int k = 0; k < K; ++k) wl[j][k] = w[c * K + k];
+      bl[j] = cbias ? cbias[c] : 0.f;
+      gl[j] = gamma[c];
+      btl[j] = beta[c];
+    }
+  }
+  for (long long fr = warp_global; fr < total_frames; fr += nwarps) {
+    const long long b = fr / t_out, t = fr % t_out;
+    const float* x = audio + b * n_samples + t * S;
+    float win[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) win[k] = __ldg(x + k);
+    float v[LN_MAXC];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_MAXC; ++j) {
+      if (j < cpl) {
+        float a = bl[j];
+#pragma unroll
+        for (int k = 0; k < K; ++k) a = fmaf(wl[j][k], win[k], a);
+        v[j] = a;
+        s += a;
+      }
+    }
+    const float mean = warp_sum(s) / channels;
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_MAXC; ++j)
+      if (j < cpl) sq += (v[j] - mean) * (v[j] - mean);
+    const float rstd = rsqrtf(warp_sum(sq) / channels + eps);
+    const long long off = fr * channels + lane * cpl;
+    if (!BWD) {
+      float o[LN_MAXC];
+#pragma unroll
+      for (int j = 0; j < LN_MAXC; ++j)
+        if (j < cpl) o[j] = gelu_erf(fmaf((v[j] - mean) * rstd, gl[j], btl[j]));
+#pragma unroll
+      for (int j = 0; j < LN_MAXC; j += 2)
+        if (j < cpl) *reinterpret_cast<uint32_t*>(y + off + j) = pack_bf16x2(o[j], o[j + 1]);
+    } else {
+      float g[LN_MAXC], xh[LN_MAXC];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < LN_MAXC; j += 2) {
+        if (j < cpl) {
+          const uint32_t u = *reinterpret_cast<const uint32_t*>(dy + off + j);
+          g[j] = bf16_lo(u);
+          g[j + 1] = bf16_hi(u);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < LN_MAXC; ++j) {
+        if (j < cpl) {
+          xh[j] = (v[j] - mean) * rstd;
+          const float dz = g[j] * gelu_erf_grad(fmaf(xh[j], gl[j], btl[j]));
+          ag[j] += dz * xh[j];
+          ab[j] += dz;
+          g[j] = dz * gl[j];
+          s1 += g[j];
+          s2 += g[j] * xh[j];
+        }
+      }
+      s1 = warp_sum(s1) / channels;
+      s2 = warp_sum(s2) / channels;
+      float o[LN_MAXC];
+#pragma unroll
+      for (int j = 0; j < LN_MAXC; ++j)
+        if (j < cpl) o[j] = rstd * (g[j] - s1 - xh[j] * s2);
+#pragma unroll
+      for (int j = 0; j < LN_MAXC; j += 2)
+        if (j < cpl) *reinterpret_cast<uint32_t*>(dconv + off + j) = pack_bf16x2(o[j], o[j + 1]);
+    }
+  }
+  if (BWD) {
+#pragma unroll
+    for (int j = 0; j < LN_MAXC; ++j) {
+      if (j < cpl) {
+        atomicAdd(dgamma + lane * cpl + j, ag[j]);
+        atomicAdd(dbeta + lane * cpl + j, ab[j]);
+      }
+    }
+  }
+}
+
+// dw[c][k] += sum_{b,t} dconv[b,t,c] * x[b, S t + k],  dbias[c] += sum dconv   (fp32 atomics into zeroed buffers)
+__global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ audio, const bf16* __restrict__ dconv,
+                                                    float* __restrict__ dw, float* __restrict__ dbias,
+                                                    long long n_samples, long long t_out, int channels) {
+  __shared__ float xs[BWD_FR * S + K];
+  const int b = blockIdx.y;
+  const long long t0 = (long long)blockIdx.x * BWD_FR;
+  const long long nfr = (t_out - t0) < BWD_FR ? (t_out - t0) : BWD_FR;
+  const float* x = audio + (long long)b * n_samples + t0 * S;
+  const int nload = (int)nfr * S + (K - S);
+  for (int i = threadIdx.x; i < nload; i += blockDim.x) xs[i] = x[i];
+  __syncthreads();
+  const int quads = channels / 4;
+  const int lanes = blockDim.x / 128;
+  for (int qg = threadIdx.x % 128; qg < quads; qg += 128) {
+    const int c0 = qg * 4;
+    float acc[4][K + 1];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < K + 1; ++k) acc[j][k] = 0.f;
+    for (int f = threadIdx.x / 128; f < nfr; f += lanes) {
+      const uint2 u = *reinterpret_cast<const uint2*>(dconv + ((long long)b * t_out + t0 + f) * channels + c0);
+      const float d[4] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y)};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[j][K] += d[j];
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[j][k] = fmaf(d[j], xs[f * S + k], acc[j][k]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) atomicAdd(dw + (c0 + j) * K + k, acc[j][k]);
+      if (dbias) atomicAdd(dbias + c0 + j, acc[j][K]);
+    }
+  }
+}
+
 }  // namespace conv0
 }  // namespace smx
 
@@ -289,6 +443,52 @@ int smx_conv0_gn_gelu_bwd(const float* audio, const float* w, const float* gamma
   SMX_CHECK_CUDA(cudaGetLastError());
   bwd_finalize_kernel<<<(int)ceil_div(channels * (K + 2), 128), 128, 0, st>>>(w, gamma, stats, moments, partial, dw,
                                                                              dgamma, dbeta, (int)batch, channels, t_out);
+  SMX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+}
+
+extern "C" {
+
+int smx_conv0_ln_gelu_fwd(const float* audio, const float* w, const float* conv_bias, const float* gamma,
+                          const float* beta, void* y, int64_t batch, int64_t n_samples, int64_t t_out, int channels,
+                          int ksize, int stride, float eps, void* stream) {
+  SMX_REQUIRE(ksize == K && stride == S, "conv0: only kernel 10 / stride 5 is supported");
+  SMX_REQUIRE(channels % 64 == 0 && channels <= 32 * LN_MAXC, "conv0 (layer norm): channels must be a multiple of 64, <= 512");
+  const long long frames = batch * t_out;
+  long long grid = ceil_div(frames, 8 * 16);
+  if (grid > (long long)num_sms() * 8) grid = (long long)num_sms() * 8;
+  ln_variant_kernel<false><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+      audio, w, conv_bias, gamma, beta, (bf16*)y, nullptr, nullptr, nullptr, nullptr, n_samples, t_out, frames,
+      channels, eps);
+  SMX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+/* dconv (bf16 [B,T,C], gradient w.r.t. the biased conv output) + dgamma/dbeta (zero-initialised, accumulated) */
+int smx_conv0_ln_gelu_bwd(const float* audio, const float* w, const float* conv_bias, const float* gamma,
+                          const float* beta, const void* dy, void* dconv, float* dgamma, float* dbeta, int64_t batch,
+                          int64_t n_samples, int64_t t_out, int channels, int ksize, int stride, float eps,
+                          void* stream) {
+  SMX_REQUIRE(ksize == K && stride == S, "conv0: only kernel 10 / stride 5 is supported");
+  SMX_REQUIRE(channels % 64 == 0 && channels <= 32 * LN_MAXC, "conv0 (layer norm): channels must be a multiple of 64, <= 512");
+  const long long frames = batch * t_out;
+  long long grid = ceil_div(frames, 8 * 16);
+  if (grid > (long long)num_sms() * 4) grid = (long long)num_sms() * 4;
+  ln_variant_kernel<true><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+      audio, w, conv_bias, gamma, beta, nullptr, (const bf16*)dy, (bf16*)dconv, dgamma, dbeta, n_samples, t_out,
+      frames, channels, eps);
+  SMX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+/* dw [C][k] and dbias [C] (zero-initialised, accumulated) from dconv */
+int smx_conv0_wgrad(const float* audio, const void* dconv, float* dw, float* dbias, int64_t batch, int64_t n_samples,
+                    int64_t t_out, int channels, int ksize, int stride, void* stream) {
+  SMX_REQUIRE(ksize == K && stride == S, "conv0: only kernel 10 / stride 5 is supported");
+  SMX_REQUIRE(channels % 4 == 0, "conv0: channels must be a multiple of 4");
+  wgrad_kernel<<<dim3((unsigned)ceil_div(t_out, BWD_FR), (unsigned)batch), 256, 0, (cudaStream_t)stream>>>(
+      audio, (const bf16*)dconv, dw, dbias, n_samples, t_out, channels);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

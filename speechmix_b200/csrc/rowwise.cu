@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      bf16* __restrict__ y, bf16* __restrict__ sum_out,
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                                     long long rows, int cols, float eps, int rms_only) {
+                                                     long long rows, int cols, float eps, int rms_only, int act) {
   const int lane = threadIdx.x & 31;
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -94,6 +94,10 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
         if (beta) loadf8(beta + c, b);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + (beta ? b[j] : 0.f);
+        if (act == SMX_ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = gelu_erf(o[j]);
+        }
         store8(y + row * cols + c, o);
       }
     }
@@ -103,10 +107,12 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
 // ------------------------------------------------------------------ LayerNorm backward
 template <int VPL>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
-                                                     const float* __restrict__ gamma, const float* __restrict__ mean_in,
+                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                     const float* __restrict__ mean_in,
                                                      const float* __restrict__ rstd_in, const bf16* __restrict__ dres,
                                                      bf16* __restrict__ dx, float* __restrict__ dgamma,
-                                                     float* __restrict__ dbeta, long long rows, int cols, int rms_only) {
+                                                     float* __restrict__ dbeta, long long rows, int cols, int rms_only,
+                                                     int act) {
   __shared__ float red[8][32 * 8 + 1];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -131,6 +137,12 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
         load8(dy + row * cols + c, d);
         load8(x + row * cols + c, xh[i]);
         loadf8(gamma + c, gm);
+        if (act == SMX_ACT_GELU) {  // y = gelu(z), z = xhat*gamma + beta: fold gelu'(z) into dy first
+          float bt[8];
+          loadf8(beta + c, bt);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[j] *= gelu_erf_grad(fmaf((xh[i][j] - mean) * rstd, gm[j], bt[j]));
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           xh[i][j] = (xh[i][j] - mean) * rstd;
@@ -403,7 +415,9 @@ using namespace smx::rw;
 extern "C" {
 
 int smx_layernorm_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* y, void* sum_out,
-                      float* mean, float* rstd, int64_t rows, int64_t cols, float eps, int rms_only, void* stream) {
+                      float* mean, float* rstd, int64_t rows, int64_t cols, float eps, int rms_only, int act,
+                      void* stream) {
+  SMX_REQUIRE(act == SMX_ACT_NONE || act == SMX_ACT_GELU, "layernorm: unsupported fused activation %d", act);
   SMX_REQUIRE(cols % 8 == 0 && cols <= 2048 && cols > 0, "layernorm: cols %lld must be a multiple of 8 and <= 2048",
               (long long)cols);
   if (rows == 0) return 0;
@@ -412,14 +426,15 @@ int smx_layernorm_fwd(const void* x, const void* res, const float* gamma, const 
   cudaStream_t st = (cudaStream_t)stream;
   LN_DISPATCH(vpl, ln_fwd_kernel,
               <<<grid, 256, 0, st>>>((const bf16*)x, (const bf16*)res, gamma, beta, (bf16*)y, (bf16*)sum_out, mean,
-                                     rstd, rows, (int)cols, eps, rms_only));
+                                     rstd, rows, (int)cols, eps, rms_only, act));
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-int smx_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
-                      const void* dres_in, void* dx, float* dgamma, float* dbeta, int64_t rows, int64_t cols,
-                      int rms_only, void* stream) {
+int smx_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* beta, const float* mean,
+                      const float* rstd, const void* dres_in, void* dx, float* dgamma, float* dbeta, int64_t rows,
+                      int64_t cols, int rms_only, int act, void* stream) {
+  SMX_REQUIRE(act == SMX_ACT_NONE || (act == SMX_ACT_GELU && beta != nullptr), "layernorm_bwd: bad fused activation");
   SMX_REQUIRE(cols % 8 == 0 && cols <= 2048 && cols > 0, "layernorm_bwd: cols %lld unsupported", (long long)cols);
   SMX_REQUIRE(dgamma != nullptr, "layernorm_bwd: dgamma required");
   if (rows == 0) return 0;
@@ -427,8 +442,8 @@ int smx_layernorm_bwd(const void* dy, const void* x, const float* gamma, const f
   int grid = grid_for(rows, 8, 2);
   cudaStream_t st = (cudaStream_t)stream;
   LN_DISPATCH(vpl, ln_bwd_kernel,
-              <<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)x, gamma, mean, rstd, (const bf16*)dres_in,
-                                     (bf16*)dx, dgamma, dbeta, rows, (int)cols, rms_only));
+              <<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)x, gamma, beta, mean, rstd, (const bf16*)dres_in,
+                                     (bf16*)dx, dgamma, dbeta, rows, (int)cols, rms_only, act));
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

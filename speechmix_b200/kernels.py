@@ -294,28 +294,28 @@ def _L():
     return _lib.load()
 
 
-def layernorm_fwd(x, gamma, beta, eps=1e-5, res=None, want_sum=False, rms_only=False):
+def layernorm_fwd(x, gamma, beta, eps=1e-5, res=None, want_sum=False, rms_only=False, act=ACT_NONE, out=None):
     """x: [..., C] bf16 contiguous.  Returns y, (sum or x), mean, rstd."""
     C = x.shape[-1]
     rows = x.numel() // C
-    y = torch.empty_like(x)
+    y = torch.empty_like(x) if out is None else out
     s = torch.empty_like(x) if (want_sum and res is not None) else None
     mean = torch.empty(rows, device=x.device, dtype=torch.float32)
     rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
     _lib.check(_L().smx_layernorm_fwd(_ptr(x), _ptr(res), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(s), _ptr(mean),
-                                      _ptr(rstd), rows, C, eps, 1 if rms_only else 0, _stream()), "layernorm_fwd")
+                                      _ptr(rstd), rows, C, eps, 1 if rms_only else 0, act, _stream()), "layernorm_fwd")
     return y, (s if s is not None else x), mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, rms_only=False, want_dbeta=True):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, rms_only=False, want_dbeta=True, act=ACT_NONE, beta=None):
     C = x.shape[-1]
     rows = x.numel() // C
     dx = torch.empty_like(x)
     dgamma = torch.zeros(C, device=x.device, dtype=torch.float32)
     dbeta = torch.zeros(C, device=x.device, dtype=torch.float32) if want_dbeta else None
-    _lib.check(_L().smx_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dres), _ptr(dx),
-                                      _ptr(dgamma), _ptr(dbeta), rows, C, 1 if rms_only else 0, _stream()),
-               "layernorm_bwd")
+    _lib.check(_L().smx_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), _ptr(dres),
+                                      _ptr(dx), _ptr(dgamma), _ptr(dbeta), rows, C, 1 if rms_only else 0, act,
+                                      _stream()), "layernorm_bwd")
     return dx, dgamma, dbeta
 
 
@@ -383,6 +383,34 @@ def conv0_bwd(audio, w, gamma, beta, stats, moments, dy):
                                           _ptr(dy), _ptr(partial), _ptr(dw), _ptr(dgamma), _ptr(dbeta), B, n, T, C,
                                           k, 5, _stream()), "conv0_bwd")
     return dw, dgamma, dbeta
+
+
+def conv0_ln_fwd(audio, w, conv_bias, gamma, beta, eps=1e-5):
+    B, n = audio.shape
+    C, _, k = w.shape
+    T = (n - k) // 5 + 1
+    y = alloc_act(B, T, C, audio.device)
+    _lib.check(_L().smx_conv0_ln_gelu_fwd(_ptr(audio), _ptr(w), _ptr(conv_bias), _ptr(gamma), _ptr(beta), _ptr(y), B, n,
+                                          T, C, k, 5, eps, _stream()), "conv0_ln_fwd")
+    return y
+
+
+def conv0_ln_bwd(audio, w, conv_bias, gamma, beta, dy, eps=1e-5):
+    B, n = audio.shape
+    C, _, k = w.shape
+    T = dy.shape[1]
+    dconv = torch.empty(B, T, C, device=audio.device, dtype=BF16)
+    dgamma = torch.zeros(C, device=audio.device, dtype=torch.float32)
+    dbeta = torch.zeros(C, device=audio.device, dtype=torch.float32)
+    L = _L()
+    _lib.check(L.smx_conv0_ln_gelu_bwd(_ptr(audio), _ptr(w), _ptr(conv_bias), _ptr(gamma), _ptr(beta), _ptr(dy),
+                                       _ptr(dconv), _ptr(dgamma), _ptr(dbeta), B, n, T, C, k, 5, eps, _stream()),
+               "conv0_ln_bwd")
+    dw = torch.zeros_like(w)
+    dcb = torch.zeros(C, device=audio.device, dtype=torch.float32) if conv_bias is not None else None
+    _lib.check(L.smx_conv0_wgrad(_ptr(audio), _ptr(dconv), _ptr(dw), _ptr(dcb), B, n, T, C, k, 5, _stream()),
+               "conv0_wgrad")
+    return dw, dcb, dgamma, dbeta
 
 
 # ---------------------------------------------------------------------------

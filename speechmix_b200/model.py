@@ -248,5 +248,44 @@ class SpeechMixFixed(SpeechMixEED):
                 p.requires_grad = False
 
 
+class SpeechMixAdapter(SpeechMixEED):
+    """ref:speechmix/hf_model.py:465-502.  Text encoder/decoder layers are frozen and every layer's output is
+    REPLACED by ``adapter(output)`` with adapter = LayerNorm -> Linear(D, D/2) -> ReLU -> Linear(D/2, D).
+
+    ``adapter_indexing="reference"`` (default) reproduces the reference's effective behaviour: its hook lambda
+    late-binds the loop indices, so every layer runs ``adapters[-1]`` (SURVEY.md section 8c caveat A);
+    ``"per_layer"`` gives each layer its own adapter."""
+
+    def custom_modules(self, adapter_indexing="reference", **kwargs):
+        self.encoder_model.eval()
+        self.decoder_model.eval()
+        base = self.decoder_model.base_model
+        stacks = [base.encoder, base.decoder]
+        for st in stacks:
+            for _, p in st.layers.named_parameters():
+                p.requires_grad = False
+        d = self.decoder_model.config.d_model
+        self.adapters = nn.ModuleList()
+        for st in stacks:
+            for _ in st.layers:
+                self.adapters.append(nn.Sequential(nn.LayerNorm(d), nn.Linear(d, d // 2), nn.ReLU(),
+                                                   nn.Linear(d // 2, d)))
+        self.adapter_indexing = adapter_indexing
+        self._adapter_cfg = dict(pre_ln=True, eps=1e-5, act="relu", no_residual=True)
+        offset = 0
+        for st in stacks:
+            st.layer_output_hook = self._make_hook(offset)
+            offset += len(st.layers)
+
+    def _make_hook(self, offset):
+        def hook(layer_index, hidden):
+            j = offset + layer_index if self.adapter_indexing == "per_layer" else len(self.adapters) - 1
+            a = self.adapters[j]
+            return ops.FFNBlockFn.apply(hidden, self._adapter_cfg, a[1].weight, a[1].bias, a[3].weight, a[3].bias,
+                                        a[0].weight, a[0].bias)
+        return hook
+
+
 HFSpeechMixEED = SpeechMixEED
 HFSpeechMixFixed = SpeechMixFixed
+HFSpeechMixAdapter = SpeechMixAdapter

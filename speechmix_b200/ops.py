@@ -268,7 +268,8 @@ class FFNBlockFn(torch.autograd.Function):
         else:
             a_in = x2
         h, pre = K.linear_fwd(a_in, w16(w1), None if b1 is None else b1.detach(), act=act, want_pre=True)
-        s = K.linear_fwd(h, w16(w2), None if b2 is None else b2.detach(), residual=x2)
+        no_res = bool(cfg.get("no_residual", False))  # adapter blocks: y = W2.act(W1 LN(x) + b1) + b2
+        s = K.linear_fwd(h, w16(w2), None if b2 is None else b2.detach(), residual=None if no_res else x2)
         if pre_ln:
             y = s
             ctx.save_for_backward(x2, n, mean, rstd, pre, h, ln_w)
@@ -276,6 +277,7 @@ class FFNBlockFn(torch.autograd.Function):
             y, _, mean, rstd = K.layernorm_fwd(s, ln_w.detach(), ln_b.detach(), eps)
             ctx.save_for_backward(x2, s, mean, rstd, pre, h, ln_w)
         ctx.pre_ln, ctx.dact, ctx.shp = pre_ln, dact, shp
+        ctx.no_res = no_res
         ctx.wrefs = (w1, w2)
         ctx.has_bias = b1 is not None
         return y.view(shp)
@@ -296,9 +298,9 @@ class FFNBlockFn(torch.autograd.Function):
         dpre = K.linear_dgrad(ds, w16(w2), act=ctx.dact, aux_in=pre)
         db1 = K.colsum(dpre) if ctx.has_bias else None
         dw1 = K.linear_wgrad(dpre, a_in) if _need(ctx, 2) else None
-        d_in = K.linear_dgrad(dpre, w16(w1), residual=None if ctx.pre_ln else ds)
+        d_in = K.linear_dgrad(dpre, w16(w1), residual=None if (ctx.pre_ln or ctx.no_res) else ds)
         if ctx.pre_ln:
-            dx, dlnw, dlnb = K.layernorm_bwd(d_in, x2, ln_w.detach(), mean, rstd, dres=ds)
+            dx, dlnw, dlnb = K.layernorm_bwd(d_in, x2, ln_w.detach(), mean, rstd, dres=None if ctx.no_res else ds)
         else:
             dx = d_in
         return dx.view(ctx.shp), None, dw1, db1, dw2, db2, dlnw, dlnb
@@ -343,6 +345,62 @@ class FeatureEncoderGroupFn(torch.autograd.Function):
                 dpre = K.conv_s2_dgrad(dpre, conv_packed16(w), k, x_in.shape[1])
         dw0, dg, db = K.conv0_bwd(audio, w0.detach().contiguous(), gn_w.detach(), gn_b.detach(), stats, moments, dpre)
         return (None, None, dw0, dg, db, *dws)
+
+
+class FeatureEncoderLayerNormFn(torch.autograd.Function):
+    """Conv feature encoder with feat_extract_norm="layer", conv_bias=True (HuBERT-large,
+    wav2vec2-large-lv60): every layer is Conv1d + bias -> LayerNorm over channels -> GELU
+    (hf:...wav2vec2.py:275-299).  Layer 0 is one fused CUDA-core kernel; layers 1.. are implicit
+    tcgen05 GEMMs with the bias in the epilogue followed by a fused LayerNorm+GELU pass.
+    inputs: audio, kernel sizes, (w, b, ln_w, ln_b) x n_layers  ->  [B, T, C] bf16"""
+
+    @staticmethod
+    def forward(ctx, audio, ks, *params):
+        audio = audio.contiguous().float()
+        n = len(params) // 4
+        w0, b0, g0, be0 = params[:4]
+        y = K.conv0_ln_fwd(audio, w0.detach().contiguous(), b0.detach(), g0.detach(), be0.detach())
+        saved = [audio, y]
+        for i in range(1, n):
+            w, b, g, be = params[4 * i:4 * i + 4]
+            z = K.conv_s2_fwd(y, conv_packed16(w), ks[i - 1], bias=b.detach())
+            B, T, C = z.shape
+            out = K.alloc_act(B, T, C, z.device)
+            y, _, mean, rstd = K.layernorm_fwd(z.view(B * T, C), g.detach(), be.detach(), 1e-5, act=ACT_GELU,
+                                               out=out.view(B * T, C))
+            y = out
+            saved += [z, mean, rstd, y]
+        ctx.save_for_backward(*saved[:-1])  # the last activation is the output
+        ctx.params, ctx.ks, ctx.n = params, ks, n
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        sv = ctx.saved_tensors
+        audio, n, params = sv[0], ctx.n, ctx.params
+        # layout of sv: audio, y0, (z1, mean1, rstd1, y1), ..., (z_{n-1}, mean, rstd)  [y_{n-1} not saved]
+        grads = [None] * (4 * n)
+        d = dy.contiguous()
+        for i in range(n - 1, 0, -1):
+            w, b, g, be = params[4 * i:4 * i + 4]
+            base = 2 + 4 * (i - 1)
+            z, mean, rstd = sv[base], sv[base + 1], sv[base + 2]
+            x_in = sv[1] if i == 1 else sv[2 + 4 * (i - 2) + 3]
+            B, T, C = z.shape
+            dz, dg, dbe = K.layernorm_bwd(d.view(B * T, C), z.view(B * T, C), g.detach(), mean, rstd, act=ACT_GELU,
+                                          beta=be.detach())
+            dz3 = dz.view(B, T, C)
+            k = ctx.ks[i - 1]
+            grads[4 * i + 2], grads[4 * i + 3] = dg, dbe
+            if ctx.needs_input_grad[2 + 4 * i + 1]:
+                grads[4 * i + 1] = K.colsum(dz)
+            if ctx.needs_input_grad[2 + 4 * i]:
+                grads[4 * i] = K.unpack_conv_wgrad(K.conv_s2_wgrad(dz3, x_in, k), x_in.shape[2], k)
+            d = K.conv_s2_dgrad(dz3, conv_packed16(w), k, x_in.shape[1])
+        w0, b0, g0, be0 = params[:4]
+        dw0, db0, dg0, dbe0 = K.conv0_ln_bwd(audio, w0.detach().contiguous(), b0.detach(), g0.detach(), be0.detach(), d)
+        grads[0], grads[1], grads[2], grads[3] = dw0, db0, dg0, dbe0
+        return (None, None, *grads)
 
 
 class ConvS2Fn(torch.autograd.Function):

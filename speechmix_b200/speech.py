@@ -55,14 +55,20 @@ class FeatureEncoder(nn.Module):
 
     def forward(self, input_values):
         cfg = self.config
-        if cfg.feat_extract_norm != "group" or cfg.conv_bias:
-            raise NotImplementedError(
-                "feat_extract_norm='layer' / conv_bias=True feature encoders are not wired to the sm_100a kernels yet")
         if cfg.feat_extract_activation != "gelu":
             raise NotImplementedError("only GELU feature encoders are supported")
         if self._ks[0] != 10 or self._ss[0] != 5 or any(s != 2 for s in self._ss[1:]) or \
                 any(k not in (2, 3) for k in self._ks[1:]):
             raise NotImplementedError("unsupported conv feature-encoder geometry %r / %r" % (self._ks, self._ss))
+        if cfg.feat_extract_norm == "layer":
+            if not cfg.conv_bias:
+                raise NotImplementedError("feat_extract_norm='layer' is only wired for conv_bias=True (the HF large presets)")
+            flat = []
+            for l in self.conv_layers:
+                flat += [l.conv.weight, l.conv.bias, l.layer_norm.weight, l.layer_norm.bias]
+            return ops.FeatureEncoderLayerNormFn.apply(input_values, tuple(self._ks[1:]), *flat)
+        if cfg.conv_bias:
+            raise NotImplementedError("feat_extract_norm='group' with conv_bias=True is not wired to the kernels")
         l0 = self.conv_layers[0]
         ws = [l.conv.weight for l in self.conv_layers[1:]]
         return ops.FeatureEncoderGroupFn.apply(input_values, tuple(self._ks[1:]), l0.conv.weight, l0.layer_norm.weight,

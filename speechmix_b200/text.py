@@ -82,6 +82,7 @@ class _Stack(nn.Module):
         if pre_ln:
             self.layer_norm = nn.LayerNorm(d)
         self.pre_ln = pre_ln
+        self.layer_output_hook = None  # callable(layer_index, hidden) -> hidden (SpeechMixAdapter)
 
     def embed(self, input_ids=None, inputs_embeds=None, t_start=0):
         """tokens*scale (or given embeddings, unscaled: hf:...bart.py:520-524) + learned positions, then LN."""
@@ -92,8 +93,10 @@ class _Stack(nn.Module):
     def forward(self, input_ids=None, inputs_embeds=None, encoder_hidden_states=None, output_hidden_states=False):
         x = self.embed(input_ids, inputs_embeds)
         hs = [x] if output_hidden_states else None
-        for layer in self.layers:
+        for li, layer in enumerate(self.layers):
             x = layer(x, encoder_hidden_states) if self.is_decoder else layer(x)
+            if self.layer_output_hook is not None:
+                x = self.layer_output_hook(li, x)
             if output_hidden_states:
                 hs.append(x)
         if self.pre_ln:

@@ -10,11 +10,11 @@ from tests._cases import build_oracle, load_fixture
 pytestmark = pytest.mark.gpu
 
 
-def _mine_from(ora, fx, cuda_device):
+def _mine_from(ora, fx, cuda_device, cls=None):
     from oracle import hf_oracle as O
     from speechmix_b200 import SpeechMixEED
-    m = SpeechMixEED(O.speech_config(fx["speech"], model_type=fx["speech_type"]), O.text_config(fx["text"]),
-                     **fx["kwargs"])
+    m = (cls or SpeechMixEED)(O.speech_config(fx["speech"], model_type=fx["speech_type"]), O.text_config(fx["text"]),
+                              **fx["kwargs"])
     m.load_state_dict(ora.state_dict())
     return m.to(cuda_device).train(fx["train_mode"])
 
@@ -24,7 +24,7 @@ def _rel(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-12))
 
 
-@pytest.mark.parametrize("name", ["mini_eed_ds2", "mini_eed_ds8_ws", "mini_eed_share"])
+@pytest.mark.parametrize("name", ["mini_eed_ds2", "mini_eed_ds8_ws", "mini_eed_share", "mini_large_mbart"])
 def test_eed_matches_oracle(name, cuda_device):
     fx = load_fixture(name)
     ora, x, labels = build_oracle(fx)
@@ -111,3 +111,28 @@ def test_frozen_parameters_get_no_gradient(cuda_device):
             assert p.grad is None, n
     assert m.enc_to_dec_proj.weight.grad is not None
     assert m.encoder_model.feature_extractor.conv_layers[0].conv.weight.grad is not None
+
+
+@pytest.mark.parametrize("indexing", ["reference", "per_layer"])
+def test_adapter_matches_oracle(indexing, cuda_device):
+    """SpeechMixAdapter (ref:speechmix/hf_model.py:465-502) incl. the reference's late-binding hook quirk."""
+    from oracle import hf_oracle as O
+    from speechmix_b200 import SpeechMixAdapter
+    fx = dict(load_fixture("mini_eed_ds2"), kwargs={"down_scale": 2, "adapter_indexing": indexing})
+    ora, x, labels = build_oracle(fx, cls=O.OracleAdapter)
+    mine = _mine_from(ora, fx, cuda_device, cls=SpeechMixAdapter)
+    assert mine.list_no_grad == ora.list_no_grad
+    ref = ora(x, labels=labels, keep_full_logits=True)
+    out = mine(x.to(cuda_device), labels=labels.to(cuda_device))
+    assert abs(float(out["loss"]) - float(ref["loss"])) < 3e-3
+    assert _rel(mine.decoder_model.full_logits(out["decoder_last_hidden_state"]), ref["full_logits"]) < 2e-2
+    ref["loss"].backward()
+    out["loss"].backward()
+    po, pm = dict(ora.named_parameters()), dict(mine.named_parameters())
+    for k, p in po.items():
+        if p.grad is None:
+            assert pm[k].grad is None, k      # reference quirk: unused adapters get no gradient
+        elif k.startswith("adapters") or k.startswith("enc_to_dec_proj"):
+            g = pm[k].grad.cpu()
+            cos = float((g * p.grad).sum() / (g.norm() * p.grad.norm() + 1e-20))
+            assert cos > 0.97, (k, cos)      # 12 stacked replace-adapters amplify bf16 noise; direction must agree

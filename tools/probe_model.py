@@ -23,13 +23,15 @@ def rel_l2(got, ref):
 
 
 def run(sp_kind, sp_type, tx_kind, kw, B, secs, t_dec, ignore_tail=False, backward=True, cls="eed"):
-    from speechmix_b200 import SpeechMixEED
+    import speechmix_b200 as P
     spc, txc = O.speech_config(sp_kind, model_type=sp_type), O.text_config(tx_kind)
     s, t = O.build_backbones(spc, txc, seed=0)
-    ora = O.OracleEED(s, t, **kw)
+    ocls, mcls = {"eed": (O.OracleEED, P.SpeechMixEED), "adapter": (O.OracleAdapter, P.SpeechMixAdapter),
+                  "fixed": (O.OracleFixed, P.SpeechMixFixed)}[cls]
+    ora = ocls(s, t, **kw)
     O.reinit_glue(ora, 1)
     ora.train(backward)
-    mine = SpeechMixEED(spc, txc, **kw)
+    mine = mcls(spc, txc, **kw)
     mine.load_state_dict(ora.state_dict())
     mine = mine.cuda()
     mine.train(backward)
@@ -40,7 +42,7 @@ def run(sp_kind, sp_type, tx_kind, kw, B, secs, t_dec, ignore_tail=False, backwa
     out_m = mine(x.cuda(), labels=labels.cuda())
     torch.cuda.synchronize()
     logits_m = mine.decoder_model.full_logits(out_m["decoder_last_hidden_state"])
-    rec = {"case": f"{sp_kind}/{tx_kind} {kw} B{B} {secs}s",
+    rec = {"case": f"{cls} {sp_kind}/{tx_kind} {kw} B{B} {secs}s",
            "loss_ref": float(out_o["loss"]), "loss": float(out_m["loss"]),
            "loss_abs_err": abs(float(out_o["loss"]) - float(out_m["loss"])),
            "speech_rel": rel(out_m["speech_last_hidden_state"], out_o["speech_last_hidden_state"]),
@@ -79,6 +81,12 @@ if __name__ == "__main__":
         run("mini", "wav2vec2", "bart-mini", dict(down_scale=2), 2, 1.0, 8, ignore_tail=True)
         run("mini", "wav2vec2", "bart-mini", dict(down_scale=8, weighted_sum=True), 2, 1.5, 8)
         run("mini", "wav2vec2", "mbart-mini", dict(down_scale=4, share_layer_ratio=0.5), 3, 1.0, 6)
+    if "variants" in which:
+        run("mini_large", "hubert", "mbart-mini", dict(down_scale=2), 2, 1.0, 8)
+        run("mini_large", "wav2vec2", "bart-mini", dict(down_scale=8), 2, 1.5, 8)
+        run("mini", "wav2vec2", "bart-mini", dict(down_scale=2), 2, 1.0, 8, cls="adapter")
+        run("mini", "wav2vec2", "mbart-mini", dict(down_scale=2, adapter_indexing="per_layer"), 2, 1.0, 8, cls="adapter")
+        run("mini", "wav2vec2", "bart-mini", dict(down_scale=2, fixed_speech=True, fixed_nlp=False), 2, 1.0, 8, cls="fixed")
     if "base" in which:
         run("base", "wav2vec2", "bart-base", dict(down_scale=2), 1, 5.0, 24, backward=False)
         run("base", "wav2vec2", "bart-base", dict(down_scale=2), 2, 3.0, 16, backward=True)
