@@ -1,10 +1,15 @@
-// Persistent, warp-specialised bf16 GEMM for sm_100a:
-//   warp 0     : TMA producer (one thread) -> 4-stage smem ring
-//   warp 1     : tcgen05.mma issuer (one thread), accumulators in TMEM (2 x 256 columns,
+// Persistent, warp-specialised bf16 GEMM for sm_100a on CTA PAIRS (tcgen05 cta_group::2):
+// a cluster of two CTAs (two SMs of one TPC) owns a 256 x 256 output tile.  Each CTA loads its 128
+// rows of A and HALF of B (128 of the 256 columns) per 64-deep k-block, the leader CTA's single MMA
+// thread issues 256x256x16 MMAs that read both CTAs' shared memory, and each CTA keeps its 128 rows
+// of the accumulator in its own TMEM.  Halving B per SM is what lifts the shared-memory bandwidth
+// bound of the single-CTA 128x256 tile (TMA fill + MMA operand reads ~192 B/clk vs 128 B/clk).
+//   warp 0     : TMA producer (lanes issue the boxes of a stage in parallel) -> 6-stage smem ring
+//   warp 1     : tcgen05.mma issuer (leader CTA only), accumulators in TMEM (2 x 256 columns,
 //                so the epilogue of tile i overlaps the MMAs of tile i+1)
-//   warps 2..5 : epilogue, TMEM -> registers -> fused bias/activation/residual -> HBM
-// Tile 128 x 256 x 64, 128-byte swizzled operands, K-major or MN-major via the
-// shared-memory descriptors (no transpose copies for dgrad / wgrad).
+//   warps 2..9 : epilogue, TMEM -> registers -> fused bias/activation/residual -> swizzled smem -> TMA store
+// 128-byte swizzled operands, K-major or MN-major via the shared-memory descriptors (no transpose
+// copies for dgrad / wgrad).
 //
 // Modes (see include/speechmix_sm100.h): NT forward (+ implicit-GEMM conv taps),
 // NN data gradient, TN weight gradient (fp32 out, split-K with atomics).
@@ -18,10 +23,12 @@ namespace smx {
 
 namespace gemm {
 
-constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int STAGES = 4;
-constexpr int A_BYTES = BM * BK * 2;  // 16 KiB
-constexpr int B_BYTES = BN * BK * 2;  // 32 KiB
+constexpr int BM = 128, BN = 256, BK = 64;   // per CTA: 128 rows; the pair covers PAIR_M = 256 rows
+constexpr int PAIR_M = 2 * BM;
+constexpr int BN_HALF = BN / 2;              // columns of B each CTA of the pair loads
+constexpr int STAGES = 6;
+constexpr int A_BYTES = BM * BK * 2;       // 16 KiB
+constexpr int B_BYTES = BN_HALF * BK * 2;  // 16 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int PANEL_BYTES = 64 * BK * 2;  // one 64(MN) x 64(K) MN-major panel, 8 KiB
 constexpr int BAR_BYTES = 256;
@@ -282,24 +289,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();  // 0 = leader of the pair
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&full[i], 1);    // leader only: one arrive.expect_tx covering both CTAs' loads
+      mbar_init(&empty[i], 1);   // multicast tcgen05.commit, one arrival per CTA
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], EPI_WARPS);
+      mbar_init(&tempty[i], 2 * EPI_WARPS);  // leader only: epilogue warps of BOTH CTAs
     }
     for (int i = 0; i < EPI_WARPS; ++i) mbar_init(&inbar[i], 1);
     fence_barrier_init();
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) tmem_alloc2(tmem_slot, TMEM_COLS);
   tc_fence_before_sync();
-  __syncthreads();
+  cluster_sync_all();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -310,17 +320,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     // Lane 0 owns the ring (waits for a free slot, arms the barrier); the boxes of a stage are then
     // issued by different lanes in parallel, each with coordinates it tracks incrementally, so no
     // integer division or serial descriptor math sits on the per-k-block critical path.
-    constexpr int N_BOXES = MODE == SMX_GEMM_NT ? 2 : (MODE == SMX_GEMM_NN ? 1 + BN / 64 : BM / 64 + BN / 64);
+    constexpr int N_BOXES = MODE == SMX_GEMM_NT ? 2 : (MODE == SMX_GEMM_NN ? 1 + BN_HALF / 64 : BM / 64 + BN_HALF / 64);
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
       const TileCoord t = decode_tile(p, tile);
-      const int n0 = t.n_blk * BN;
+      const int n0 = t.n_blk * BN + (int)cta_rank * BN_HALF;  // this CTA's half of the B columns
       // per-lane constants of this tile
       int c0_fixed = 0, row_fixed = 0, batch = 0, smem_off = 0;
       bool is_a = false, active = lane < N_BOXES;
       if (MODE == SMX_GEMM_TN) {
-        const int m0 = t.m_blk * BM;
+        const int m0 = t.m_blk * PAIR_M + (int)cta_rank * BM;
         if (lane < BM / 64) {
           is_a = true;
           c0_fixed = p.a_col_off[0] + m0 + 64 * lane;
@@ -339,7 +349,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
       } else {
         batch = t.m_blk / p.m_tiles_per_batch;
-        row_fixed = (t.m_blk % p.m_tiles_per_batch) * BM;
+        row_fixed = (t.m_blk % p.m_tiles_per_batch) * PAIR_M + (int)cta_rank * BM;
         if (lane == 0) {
           is_a = true;
         } else if (active) {
@@ -360,19 +370,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
         if (lane == 0) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], STAGE_BYTES);
+          if (cta_rank == 0) mbar_expect_tx(&full[stage], 2 * STAGE_BYTES);  // bytes of both CTAs
         }
         __syncwarp();
         if (active) {
           uint8_t* dst = smem + stage * STAGE_BYTES + smem_off;
           if (MODE == SMX_GEMM_TN) {
-            tma_load_3d(dst, is_a ? &tma_a : &tma_b, &full[stage], c0_fixed, cr0 + row_fixed, cb);
+            tma2_load_3d(dst, is_a ? &tma_a : &tma_b, &full[stage], c0_fixed, cr0 + row_fixed, cb);
           } else if (is_a) {
-            tma_load_3d(dst, &tma_a, &full[stage], p.a_col_off[seg] + kin, row_fixed + p.a_row_off[seg], batch);
+            tma2_load_3d(dst, &tma_a, &full[stage], p.a_col_off[seg] + kin, row_fixed + p.a_row_off[seg], batch);
           } else if (MODE == SMX_GEMM_NT) {
-            tma_load_2d(dst, &tma_b, &full[stage], p.b_col_off[seg] + kin, c0_fixed);
+            tma2_load_2d(dst, &tma_b, &full[stage], p.b_col_off[seg] + kin, c0_fixed);
           } else {
-            tma_load_2d(dst, &tma_b, &full[stage], p.b_col_off[seg] + c0_fixed, p.b_row_off[seg] + kin);
+            tma2_load_2d(dst, &tma_b, &full[stage], p.b_col_off[seg] + c0_fixed, p.b_row_off[seg] + kin);
           }
         }
         if (MODE == SMX_GEMM_TN) {
@@ -390,10 +400,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && cta_rank == 0) {
       constexpr bool A_MN = (MODE == SMX_GEMM_TN);
       constexpr bool B_MN = (MODE != SMX_GEMM_NT);
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      constexpr uint32_t idesc = umma_idesc_bf16(PAIR_M, BN, A_MN, B_MN);
       // K-major SW128: 8-row groups 1024 B apart, 16 K-elements = +32 B inside the swizzle atom.
       // MN-major SW128: 64-wide panels LBO = 8 KiB apart, 8-row K groups 1024 B apart, 16 K = +2 KiB.
       constexpr uint32_t a_lbo = A_MN ? PANEL_BYTES : 16, a_kstep = A_MN ? 2048 : 32;
@@ -402,30 +412,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const uint32_t smem_base = smem_u32(smem);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      // The issuing thread is on the critical path (one MMA per 128 tensor-pipe cycles), so the
+      // descriptors are reduced to one 32-bit add per operand per MMA: the high word (SBO, version,
+      // swizzle mode) is constant and the low word is (address >> 4) | LBO << 16.
+      constexpr uint32_t desc_hi = ((1024u >> 4) & 0x3fffu) | (1u << 14) | (static_cast<uint32_t>(kLayoutSW128) << 29);
+      const uint32_t a_lo0 = (smem_u32(smem) >> 4) | ((a_lbo >> 4) << 16);
+      const uint32_t b_lo0 = ((smem_u32(smem) + A_BYTES) >> 4) | ((b_lbo >> 4) << 16);
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
         const TileCoord t = decode_tile(p, tile);
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * BN;
+        uint32_t accum = 0;
         for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after_sync();
-          const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          const uint32_t sb = sa + A_BYTES;
+          const uint32_t a_lo = a_lo0 + stage * (STAGE_BYTES >> 4);
+          const uint32_t b_lo = b_lo0 + stage * (STAGE_BYTES >> 4);
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
-            const uint64_t adesc = umma_smem_desc(sa + kk * a_kstep, a_lbo, 1024, kLayoutSW128);
-            const uint64_t bdesc = umma_smem_desc(sb + kk * b_kstep, b_lbo, 1024, kLayoutSW128);
-            umma_ss(d_tmem, adesc, bdesc, idesc, (kb > t.kb_begin || kk > 0) ? 1u : 0u);
+            const uint64_t adesc = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + kk * (a_kstep >> 4));
+            const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + kk * (b_kstep >> 4));
+            umma2_ss(d_tmem, adesc, bdesc, idesc, accum);
+            accum = 1;
           }
-          umma_commit(&empty[stage]);
+          umma2_commit_mc(&empty[stage], 3);  // frees the stage in both CTAs
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull[acc]);
+        umma2_commit_mc(&tfull[acc], 3);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -446,16 +463,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         ((p.aux_out == nullptr) || ((reinterpret_cast<uintptr_t>(p.aux_out) & 15) == 0)) &&
                         ((p.aux_in == nullptr) || ((reinterpret_cast<uintptr_t>(p.aux_in) & 15) == 0)) &&
                         (p.bias == nullptr || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
       const TileCoord t = decode_tile(p, tile);
       const int n0 = t.n_blk * BN;
       long long row, c_off, res_off = 0;
       if (MODE == SMX_GEMM_TN) {
-        row = (long long)t.m_blk * BM + row_in_tile;
+        row = (long long)t.m_blk * PAIR_M + cta_rank * BM + row_in_tile;
         c_off = row * p.c_row_stride;
       } else {
         const int bidx = t.m_blk / p.m_tiles_per_batch;
-        row = (long long)(t.m_blk % p.m_tiles_per_batch) * BM + row_in_tile;
+        row = (long long)(t.m_blk % p.m_tiles_per_batch) * PAIR_M + cta_rank * BM + row_in_tile;
         c_off = (long long)bidx * p.c_batch_stride + row * p.c_row_stride;
         res_off = (long long)bidx * p.res_batch_stride + row * p.res_row_stride;
       }
@@ -466,7 +483,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       int ep_bidx = 0, ep_row0 = 0;
       if (MODE != SMX_GEMM_TN) {
         ep_bidx = t.m_blk / p.m_tiles_per_batch;
-        ep_row0 = (t.m_blk % p.m_tiles_per_batch) * BM + q * 32;
+        ep_row0 = (t.m_blk % p.m_tiles_per_batch) * PAIR_M + (int)cta_rank * BM + q * 32;
       }
       if (use_in) {  // prefetch the first 64-column input tile while the accumulator is still being produced
         const int col0 = n0 + c_begin * 32;
@@ -702,7 +719,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       }
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) mbar_arrive_cluster(&tempty[acc], 0);  // the leader's MMA thread owns both accumulators
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -710,8 +727,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 
   if (warp >= 2 && lane == 0) tma_store_wait_read<0>();  // staging smem must outlive the last bulk store's read
   tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  cluster_sync_all();  // the peer's smem / TMEM must stay alive until the leader's last MMA has retired
+  if (warp == 1) tmem_dealloc2(tmem_base, TMEM_COLS);
 }
 
 template <int MODE, int EPI, bool FAST>
@@ -724,9 +741,21 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     attr_set = true;
   }
   const int total = p.m_tiles * p.n_tiles * p.split_k;
-  const int grid = total < num_sms() ? total : num_sms();
-  gemm_kernel<MODE, EPI, FAST><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, tc, tx, ti, p);
-  SMX_CHECK_CUDA(cudaGetLastError());
+  const int pairs = num_sms() / 2;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * (total < pairs ? total : pairs));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 2;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  SMX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<MODE, EPI, FAST>, ta, tb, tc, tx, ti, p));
   return 0;
 }
 
@@ -857,7 +886,7 @@ int smx::gemm::run(const SmxGemm* g, const LmExtra* lm, void* stream) {
     SMX_REQUIRE(g->n == (int64_t)g->nseg * g->seg_len, "smx_gemm TN: n %lld != nseg*seg_len", (long long)g->n);
     p.out_f32 = 1;
     p.m_tiles_per_batch = 0;
-    p.m_tiles = (int)ceil_div(g->m, BM);
+    p.m_tiles = (int)ceil_div(g->m, PAIR_M);
     p.kb_per_batch = (int)ceil_div(g->k, BK);
     p.kblocks = p.kb_per_batch * (int)g->batches;
     p.split_k = g->split_k > 1 ? g->split_k : 1;
@@ -873,14 +902,14 @@ int smx::gemm::run(const SmxGemm* g, const LmExtra* lm, void* stream) {
   SMX_REQUIRE(g->k == (int64_t)g->nseg * g->seg_len, "smx_gemm: k %lld != nseg*seg_len", (long long)g->k);
   SMX_REQUIRE(g->act != SMX_ACT_DGELU && g->act != SMX_ACT_DRELU || g->aux_in, "smx_gemm: DGELU/DRELU need aux_in");
   p.out_f32 = g->out_dtype == SMX_OUT_F32;
-  p.m_tiles_per_batch = (int)ceil_div(g->m, BM);
+  p.m_tiles_per_batch = (int)ceil_div(g->m, PAIR_M);
   p.m_tiles = p.m_tiles_per_batch * (int)g->batches;
   p.kblocks = (int)ceil_div(g->k, BK);
   p.kb_per_batch = p.kblocks;
   const uint32_t a_box[3] = {64, 128, 1};
   if (encode_tmap_bf16(&ta, g->a.ptr, 3, a_dims, a_str, a_box, true)) return -1;
   if (g->mode == SMX_GEMM_NT) {
-    const uint32_t b_box[2] = {64, 256};
+    const uint32_t b_box[2] = {64, 128};  // each CTA of the pair loads half of the 256 B rows
     if (encode_tmap_bf16(&tb, g->b.ptr, 2, b_dims, b_str, b_box, true)) return -1;
     if (p.epi == 1) return launch<SMX_GEMM_NT, 1, false>(ta, tb, ta, ta, ta, p, (cudaStream_t)stream);
     if (p.epi == 2) return launch<SMX_GEMM_NT, 2, false>(ta, tb, ta, ta, ta, p, (cudaStream_t)stream);

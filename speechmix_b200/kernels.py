@@ -121,10 +121,12 @@ def linear_dgrad(dy, w, act=ACT_NONE, aux_in=None, residual=None, alpha=1.0):
     return dx
 
 
-def _pick_split(out_tiles, kblocks, sms=148):
-    if out_tiles >= sms:
+def _pick_split(out_tiles, kblocks, pairs=74):
+    """contraction splits for the weight-gradient GEMM: enough 256x256 tiles x splits to occupy the
+    74 CTA pairs of a B200."""
+    if out_tiles >= pairs:
         return 1
-    s = max(1, sms // out_tiles)
+    s = max(1, pairs // out_tiles)
     return int(max(1, min(s, kblocks, 32)))
 
 
@@ -140,7 +142,7 @@ def linear_wgrad(dy, x, out=None, accumulate=False):
     g.b = _view(x, K, M, 1, K, M * K)
     g.m, g.n, g.k, g.batches = N, K, M, 1
     _set_seg(g, 1, K)
-    tiles = math.ceil(N / 128) * math.ceil(K / 256)
+    tiles = math.ceil(N / 256) * math.ceil(K / 256)
     g.split_k = _pick_split(tiles, math.ceil(M / 64))
     g.accumulate = 1 if accumulate else 0
     if out is None:
@@ -220,7 +222,7 @@ def conv_s2_wgrad(dy, x, k):
     g.b = _pair_view(x)
     g.m, g.n, g.k, g.batches = N, k * C, T_out, B
     _set_seg(g, k, C, b_row=[t >> 1 for t in range(k)], b_col=[(t & 1) * C for t in range(k)])
-    tiles = math.ceil(N / 128) * math.ceil(k * C / 256)
+    tiles = math.ceil(N / 256) * math.ceil(k * C / 256)
     g.split_k = _pick_split(tiles, B * math.ceil(T_out / 64))
     dw = (torch.zeros if g.split_k > 1 else torch.empty)(N, k * C, device=dy.device, dtype=torch.float32)
     g.c = _ptr(dw)
