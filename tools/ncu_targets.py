@@ -8,11 +8,21 @@ from speechmix_b200 import kernels as K
 which = sys.argv[1:] or ["attn", "gemm"]
 g = torch.Generator(device="cuda").manual_seed(0)
 B, T, H = 32, 749, 12
+def rounds():
+    """one warm-up pass outside the capture range, one pass inside (ncu --profile-from-start off)"""
+    yield 0
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    yield 1
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+
+
 if "attn" in which:
     qkv = torch.randn(B, T, 3 * H * 64, device="cuda", generator=g).to(torch.bfloat16)
     q, k, v = qkv[..., :H * 64], qkv[..., H * 64:2 * H * 64], qkv[..., 2 * H * 64:]
     do = torch.randn(B, T, H * 64, device="cuda", generator=g).to(torch.bfloat16)
-    for _ in range(2):
+    for _ in rounds():
         o, lse = K.attn_fwd(q, k, v, H)
         K.attn_bwd(do, q, k, v, o, lse, H)
 if "gemm" in which:
@@ -21,7 +31,7 @@ if "gemm" in which:
     w = (torch.randn(N, Kd, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
     b = torch.randn(N, device="cuda", generator=g)
     dy = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16)
-    for _ in range(2):
+    for _ in rounds():
         y, pre = K.linear_fwd(x, w, bias=b, act=K.ACT_GELU, want_pre=True)   # NT + GELU epilogue
         K.linear_fwd(x, w)                                                    # NT plain
         K.linear_wgrad(dy, x)                                                 # TN
