@@ -120,6 +120,19 @@ int smx_colsum(const void* x, float* out, int64_t rows, int64_t cols, int64_t ro
 
 /* elementwise helpers */
 int smx_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* Multi-tensor refresh of the bf16 (or fp32) working copies of all parameters in ONE launch: entry i copies
+ * src[i][0..n[i]) (fp32) to dst[i] as bf16 (dst_f32[i]=0) or fp32 (=1).  `table` is a DEVICE array of
+ * SmxCastEntry sorted by first_chunk (chunk = SMX_CAST_CHUNK elements; first_chunk = running chunk count);
+ * total_chunks = sum of ceil(n/chunk).  Replaces the per-parameter `.to(bf16)` an autocast reference run performs. */
+#define SMX_CAST_CHUNK 4096
+typedef struct {
+  const float* src;
+  void* dst;
+  int64_t n;
+  int32_t dst_f32;
+  int32_t first_chunk;
+} SmxCastEntry;
+int smx_multi_cast(const SmxCastEntry* table, int32_t n_entries, int32_t total_chunks, void* stream);
 int smx_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
 int smx_act_bf16(const void* x, void* y, int64_t n, int act, void* stream);
 /* out = dy * act'(pre), act in {SMX_ACT_GELU, SMX_ACT_RELU} */
@@ -249,6 +262,40 @@ int smx_weighted_sum_fwd(const void* const* xs, const float* w, void* out, int n
 /* dw[l] += sum(dout * x_l) */
 int smx_weighted_sum_bwd_w(const void* const* xs, const void* dout, float* dw, int n_layers, int64_t n,
                            void* stream);
+
+/* ------------------------------------------------------------------------
+ * SpeechMixSelf auxiliary losses (ref:speechmix/hf_model.py:551-581, HFSpeechMixSelf.cal_loss).
+ * KL(softmax(teacher) || softmax(student)) with reduction "batchmean" is evaluated per vocabulary chunk on
+ * fp32 logit chunks s / t [rows][vn] (row stride ld) written by smx_gemm:
+ *   cross[row] += sum_v exp(t_v - lse_t) (t_v - s_v);   kld = sum_row (cross - lse_t + lse_s) * inv_batch
+ *   dlogits    = coef_ce[row] (softmax(s) - onehot(label)) + coef_kl[0] (softmax(s) - softmax(t))    (bf16)
+ * ------------------------------------------------------------------------ */
+int smx_kl_chunk_fwd(const float* s, const float* t, int64_t ld, int64_t rows, int64_t vn, const float* lse_t,
+                     float* cross, void* stream);
+int smx_kl_finalize(const float* cross, const float* lse_s, const float* lse_t, int64_t rows, float inv_batch,
+                    float* out, void* stream);
+int smx_kl_chunk_bwd(const float* s, const float* t, int64_t ld, int64_t rows, int64_t vn, int64_t v0,
+                     const int64_t* labels, const float* lse_s, const float* lse_t, const float* coef_ce,
+                     const float* coef_kl, void* dlogits, int64_t ld_out, void* stream);
+/* attention-projection MSE (ref :561-570): A = softmax(T . view(S,[dim,ts]) / sqrt(dim)) -- view() is the
+ * reference's memory reinterpretation of the [ts, dim] matrix --, P = A . S, loss[0] += mean((P - T)^2).
+ * text_h [batch,tt,dim], speech_h [batch,ts,dim] bf16; attn [batch,tt,ts], diff [batch,tt,dim] fp32 are
+ * kept for the backward, which writes d_speech_h = gscale[0] * dLoss/dS (gscale = upstream grad * 2/N). */
+int smx_self_mse_fwd(const void* text_h, const void* speech_h, float* attn, float* diff, float* loss, int64_t batch,
+                     int64_t tt, int64_t ts, int64_t dim, void* stream);
+int smx_self_mse_bwd(const void* text_h, const void* speech_h, const float* attn, const float* diff, float* dscores,
+                     const float* gscale, void* d_speech_h, int64_t batch, int64_t tt, int64_t ts, int64_t dim,
+                     void* stream);
+
+/* ------------------------------------------------------------------------
+ * T5 relative position bias (hf:models/t5/modeling_t5.py:188-247): bias[h][i][j] = weight[bucket][h] with
+ * bucket = table[(j - (i + q_offset)) + (tq + q_offset - 1)]; the bucket table (tq + q_offset + tk - 1 int32)
+ * is built on the host with the reference's own formula.  bwd accumulates into a zeroed dweight.
+ * ------------------------------------------------------------------------ */
+int smx_relpos_bias_fwd(const float* weight, const int32_t* table, float* bias, int64_t heads, int64_t tq, int64_t tk,
+                        int64_t q_offset, void* stream);
+int smx_relpos_bias_bwd(const float* dbias, const int32_t* table, float* dweight, int64_t heads, int64_t tq, int64_t tk,
+                        int64_t q_offset, int64_t n_buckets, void* stream);
 
 #ifdef __cplusplus
 }

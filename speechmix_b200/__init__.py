@@ -6,8 +6,10 @@
 
 The CUDA library must be built first (``python -m speechmix_b200.build``); there is no fallback.
 """
-from .model import (HFSpeechMixAdapter, HFSpeechMixEED, HFSpeechMixFixed, SpeechMixAdapter,  # noqa: F401
-                    SpeechMixConfig, SpeechMixEED, SpeechMixFixed, handle_decoder_input_none, shift_tokens_right)
+from .model import (HFSpeechMixAdapter, HFSpeechMixEED, HFSpeechMixFixed, HFSpeechMixSelf,  # noqa: F401
+                    SpeechMixAdapter, SpeechMixConfig, SpeechMixEED, SpeechMixFixed, SpeechMixSelf,
+                    handle_decoder_input_none, shift_tokens_right)
 
-__all__ = ["SpeechMixEED", "SpeechMixFixed", "SpeechMixAdapter", "HFSpeechMixEED", "HFSpeechMixFixed",
-           "HFSpeechMixAdapter", "SpeechMixConfig", "shift_tokens_right", "handle_decoder_input_none"]
+__all__ = ["SpeechMixEED", "SpeechMixFixed", "SpeechMixAdapter", "SpeechMixSelf", "HFSpeechMixEED", "HFSpeechMixFixed",
+           "HFSpeechMixAdapter", "HFSpeechMixSelf", "SpeechMixConfig", "shift_tokens_right",
+           "handle_decoder_input_none"]

@@ -62,6 +62,7 @@ SIGNATURES = {
     "smx_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, c_int, c_int, _P]),
     "smx_colsum": (c_int, [_P, _P, _I64, _I64, _I64, _P]),
     "smx_cast_f32_to_bf16": (c_int, [_P, _P, _I64, _P]),
+    "smx_multi_cast": (c_int, [_P, c_int32, c_int32, _P]),
     "smx_add_bf16": (c_int, [_P, _P, _P, _I64, _P]),
     "smx_act_bf16": (c_int, [_P, _P, _I64, c_int, _P]),
     "smx_dact_bf16": (c_int, [_P, _P, _P, _I64, c_int, _P]),
@@ -85,6 +86,13 @@ SIGNATURES = {
     "smx_lmhead_dlogits": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, c_float, _P]),
     "smx_weighted_sum_fwd": (c_int, [_P, _P, _P, c_int, _I64, _P]),
     "smx_weighted_sum_bwd_w": (c_int, [_P, _P, _P, c_int, _I64, _P]),
+    "smx_kl_chunk_fwd": (c_int, [_P, _P, _I64, _I64, _I64, _P, _P, _P]),
+    "smx_kl_finalize": (c_int, [_P, _P, _P, _I64, c_float, _P, _P]),
+    "smx_kl_chunk_bwd": (c_int, [_P, _P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _I64, _P]),
+    "smx_self_mse_fwd": (c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _P]),
+    "smx_self_mse_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _P]),
+    "smx_relpos_bias_fwd": (c_int, [_P, _P, _P, _I64, _I64, _I64, _I64, _P]),
+    "smx_relpos_bias_bwd": (c_int, [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _P]),
 }
 
 _lib = None
@@ -145,7 +153,8 @@ def load():
 
 
 # kernels launched per successful call (bench.py's gpu_launches); smx_gemm is counted by its caller
-KERNELS_PER_CALL = {"smx_attn_fwd": 1, "smx_attn_bwd": 3, "layernorm_fwd": 1, "layernorm_bwd": 1, "colsum": 1,
+KERNELS_PER_CALL = {"multi_cast": 1, "kl_chunk_fwd": 1, "kl_finalize": 1, "kl_chunk_bwd": 1, "self_mse_fwd": 1,
+                    "self_mse_bwd": 2, "relpos_fwd": 1, "relpos_bwd": 1, "smx_attn_fwd": 1, "smx_attn_bwd": 3, "layernorm_fwd": 1, "layernorm_bwd": 1, "colsum": 1,
                     "cast": 1, "add": 1, "dact": 1, "conv0_stats": 2, "conv0_fwd": 1, "conv0_bwd": 2, "conv0_ln_fwd": 1, "conv0_ln_bwd": 1, "conv0_wgrad": 1,
                     "posconv_fwd": 1, "posconv_dgrad": 1, "posconv_wgrad": 1, "embed_fwd": 1, "embed_bwd": 1,
                     "lmhead_ce_fwd": 2, "lmhead_dlogits": 1, "wsum_fwd": 1, "wsum_bwd": 1}

@@ -28,6 +28,8 @@ struct BwdParams {
   const float* lse;
   const float* delta;
   const float* bias;
+  float* dbias;      // [heads, tq, tk] fp32, accumulated with atomics over the batch (T5 relative position bias)
+  float inv_scale;
   bf16 *dq, *dk, *dv;
   long long dq_row_stride, dq_batch_stride, dk_row_stride, dk_batch_stride, dv_row_stride, dv_batch_stride;
   int batch, heads, tq, tk, causal;
@@ -439,6 +441,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant
             const bool ok = (qi < p.tq) && (kvi < p.tk) && (kvi <= causal_lim);
             const float e = ok ? ex2_approx(s - lse2) : 0.f;
             ds[i] = e * fmaf(__uint_as_float(dv[i]), p.scale, -delta);
+            if (p.dbias && ok) atomicAdd(p.dbias + ((long long)head * p.tq + qi) * p.tk + kvi, ds[i] * p.inv_scale);
           }
         }
         store_row_chunk(smem + OFF_DS, r, c32, ds);
@@ -468,7 +471,7 @@ extern "C" int smx_attn_bwd(const SmxAttn* a, void* stream) {
   using namespace smx::attn;
   SMX_REQUIRE(a && a->q && a->k && a->v && a->o && a->d_o && a->dq && a->dk && a->dv && a->lse && a->delta,
               "attn_bwd: null pointer");
-  SMX_REQUIRE(a->dbias == nullptr, "attn_bwd: dbias not supported yet");
+  SMX_REQUIRE(a->dbias == nullptr || a->bias != nullptr, "attn_bwd: dbias needs the additive bias it differentiates");
   cudaStream_t st = (cudaStream_t)stream;
   CUtensorMap mq, mk, mv, mdo;
   if (make_head_map(&mq, a->q, a->tq, a->heads, a->batch, a->q_row_stride, a->q_batch_stride)) return -1;
@@ -487,6 +490,7 @@ extern "C" int smx_attn_bwd(const SmxAttn* a, void* stream) {
   BwdParams p;
   memset(&p, 0, sizeof(p));
   p.lse = a->lse, p.delta = a->delta, p.bias = a->bias;
+  p.dbias = a->dbias, p.inv_scale = 1.0f / a->scale;
   p.dq = (bf16*)a->dq, p.dk = (bf16*)a->dk, p.dv = (bf16*)a->dv;
   p.dq_row_stride = a->dq_row_stride, p.dq_batch_stride = a->dq_batch_stride;
   p.dk_row_stride = a->dk_row_stride, p.dk_batch_stride = a->dk_batch_stride;

@@ -45,7 +45,7 @@ struct Params {
   long long m, n;
   int batches;
   int kblocks, kb_per_batch;
-  int m_tiles_per_batch, m_tiles, n_tiles, split_k;
+  int m_tiles_per_batch, m_tiles, n_tiles, split_k, n_fastest;
   int nseg, seg_len;
   int a_row_off[SMX_MAX_SEG], a_col_off[SMX_MAX_SEG];
   int b_row_off[SMX_MAX_SEG], b_col_off[SMX_MAX_SEG];
@@ -77,10 +77,19 @@ struct TileCoord {
 
 __device__ __forceinline__ TileCoord decode_tile(const Params& p, int tile) {
   TileCoord t;
-  t.m_blk = tile % p.m_tiles;
-  const int rest = tile / p.m_tiles;
-  t.n_blk = rest % p.n_tiles;
-  t.split = rest / p.n_tiles;
+  if (p.n_fastest) {
+    // the n-tiles of one row block run concurrently: the (large) A operand is fetched from DRAM once
+    // and re-served from L2, the (small) weight operand stays L2-resident across waves
+    t.n_blk = tile % p.n_tiles;
+    const int rest = tile / p.n_tiles;
+    t.m_blk = rest % p.m_tiles;
+    t.split = rest / p.m_tiles;
+  } else {
+    t.m_blk = tile % p.m_tiles;
+    const int rest = tile / p.m_tiles;
+    t.n_blk = rest % p.n_tiles;
+    t.split = rest / p.n_tiles;
+  }
   t.kb_begin = (int)(((long long)p.kblocks * t.split) / p.split_k);
   t.kb_end = (int)(((long long)p.kblocks * (t.split + 1)) / p.split_k);
   return t;
@@ -906,6 +915,8 @@ int smx::gemm::run(const SmxGemm* g, const LmExtra* lm, void* stream) {
   p.m_tiles = p.m_tiles_per_batch * (int)g->batches;
   p.kblocks = (int)ceil_div(g->k, BK);
   p.kb_per_batch = p.kblocks;
+  // raster order: the LARGER operand should stream from DRAM once (see decode_tile)
+  p.n_fastest = (g->m * (int64_t)g->batches > g->n) ? 1 : 0;
   const uint32_t a_box[3] = {64, 128, 1};
   if (encode_tmap_bf16(&ta, g->a.ptr, 3, a_dims, a_str, a_box, true)) return -1;
   if (g->mode == SMX_GEMM_NT) {

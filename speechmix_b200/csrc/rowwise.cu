@@ -230,6 +230,37 @@ __global__ void cast_kernel(const float* __restrict__ s, bf16* __restrict__ d, l
   if (i < n && i + 8 > n)
     for (long long j = i; j < n; ++j) d[j] = __float2bfloat16(s[j]);
 }
+// one block per 4096-element chunk of one table entry (binary search block -> entry)
+__global__ void __launch_bounds__(256) multi_cast_kernel(const SmxCastEntry* __restrict__ table, int n_entries) {
+  int lo = 0, hi = n_entries - 1;
+  const int b = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (table[mid].first_chunk <= b) lo = mid; else hi = mid - 1;
+  }
+  const SmxCastEntry e = table[lo];
+  const long long base = (long long)(b - e.first_chunk) * SMX_CAST_CHUNK;
+  const long long end = (base + SMX_CAST_CHUNK < e.n) ? base + SMX_CAST_CHUNK : e.n;
+  const float* s = e.src;
+  if (e.dst_f32) {
+    float* d = reinterpret_cast<float*>(e.dst);
+    for (long long i = base + threadIdx.x; i < end; i += 256) d[i] = s[i];
+    return;
+  }
+  bf16* d = reinterpret_cast<bf16*>(e.dst);
+  const bool vec = ((reinterpret_cast<uintptr_t>(s) & 15) == 0) && ((reinterpret_cast<uintptr_t>(d) & 15) == 0);
+  if (vec && end - base == SMX_CAST_CHUNK) {
+#pragma unroll
+    for (int j = 0; j < SMX_CAST_CHUNK / (256 * 8); ++j) {
+      const long long i = base + (long long)(j * 256 + threadIdx.x) * 8;
+      float f[8];
+      loadf8(s + i, f);
+      store8(d + i, f);
+    }
+  } else {
+    for (long long i = base + threadIdx.x; i < end; i += 256) d[i] = __float2bfloat16(s[i]);
+  }
+}
 __global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ o, long long n) {
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   const long long stride = (long long)gridDim.x * blockDim.x * 8;
@@ -466,6 +497,12 @@ int smx_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
   SMX_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
               "cast: pointers must be 16-byte aligned");
   cast_kernel<<<grid_for(ceil_div(n, 8), 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
+  SMX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int smx_multi_cast(const SmxCastEntry* table, int32_t n_entries, int32_t total_chunks, void* stream) {
+  if (n_entries <= 0 || total_chunks <= 0) return 0;
+  multi_cast_kernel<<<total_chunks, 256, 0, (cudaStream_t)stream>>>(table, n_entries);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -45,6 +45,39 @@ def alloc_act(batch, t, c, device, dtype=BF16, slack=None):
     return flat[:n].view(batch, t, c)
 
 
+class _ZeroArena:
+    """fp32 zero-initialised scratch for accumulate-by-atomics outputs (split-K weight gradients, bias /
+    affine gradients): one memset per 128 MiB chunk instead of one fill launch per tensor (~360 per step).
+    Views keep their chunk alive; a chunk is dropped here once it is exhausted."""
+    CHUNK = 32 * 1024 * 1024  # fp32 elements
+
+    def __init__(self):
+        self.buf, self.off = {}, {}
+
+    def zeros(self, shape, device):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        if n * 2 > self.CHUNK:
+            return torch.zeros(shape, device=device, dtype=torch.float32)
+        dev = torch.device(device)
+        buf = self.buf.get(dev)
+        off = self.off.get(dev, 0)
+        n_al = (n + 63) // 64 * 64          # keep every carve-out 256-byte aligned
+        if buf is None or off + n_al > self.CHUNK:
+            buf = torch.zeros(self.CHUNK, device=dev, dtype=torch.float32)
+            self.buf[dev], off = buf, 0
+        self.off[dev] = off + n_al
+        return buf[off:off + n].view(shape)
+
+
+_ARENA = _ZeroArena()
+
+
+def zeros_f32(*shape, device):
+    return _ARENA.zeros(shape, device)
+
+
 def _run_gemm(g, tag=None, flops=0.0):
     lib = _lib.load()
     LAUNCHES[0] += 1
@@ -146,7 +179,7 @@ def linear_wgrad(dy, x, out=None, accumulate=False):
     g.split_k = _pick_split(tiles, math.ceil(M / 64))
     g.accumulate = 1 if accumulate else 0
     if out is None:
-        dw = (torch.zeros if g.split_k > 1 else torch.empty)(N, K, device=dy.device, dtype=torch.float32)
+        dw = zeros_f32(N, K, device=dy.device) if g.split_k > 1 else torch.empty(N, K, device=dy.device, dtype=torch.float32)
     else:
         dw = out
     g.c = _ptr(dw)
@@ -224,7 +257,7 @@ def conv_s2_wgrad(dy, x, k):
     _set_seg(g, k, C, b_row=[t >> 1 for t in range(k)], b_col=[(t & 1) * C for t in range(k)])
     tiles = math.ceil(N / 256) * math.ceil(k * C / 256)
     g.split_k = _pick_split(tiles, B * math.ceil(T_out / 64))
-    dw = (torch.zeros if g.split_k > 1 else torch.empty)(N, k * C, device=dy.device, dtype=torch.float32)
+    dw = zeros_f32(N, k * C, device=dy.device) if g.split_k > 1 else torch.empty(N, k * C, device=dy.device, dtype=torch.float32)
     g.c = _ptr(dw)
     g.c_row_stride, g.c_batch_stride = k * C, N * k * C
     g.alpha = 1.0
@@ -271,7 +304,8 @@ def attn_fwd(q, k, v, heads, causal=False, scale=None, bias=None):
     return o, lse
 
 
-def attn_bwd(do, q, k, v, o, lse, heads, causal=False, scale=None, bias=None, dq=None, dk=None, dv=None):
+def attn_bwd(do, q, k, v, o, lse, heads, causal=False, scale=None, bias=None, dq=None, dk=None, dv=None, dbias=None):
+    """dbias: optional zero-initialised fp32 [heads, Tq, Tk]; receives sum_b dS (gradient of the additive bias)."""
     B, Tq, HD = q.shape
     Tk = k.shape[1]
     scale = (1.0 / math.sqrt(64)) if scale is None else scale
@@ -282,6 +316,7 @@ def attn_bwd(do, q, k, v, o, lse, heads, causal=False, scale=None, bias=None, dq
     delta = torch.empty(B, heads, Tq, device=q.device, dtype=torch.float32)
     a = _attn_desc(q, k, v, o, lse, heads, causal, scale, bias)
     a.d_o, a.dq, a.dk, a.dv, a.delta = _ptr(do), _ptr(dq), _ptr(dk), _ptr(dv), _ptr(delta)
+    a.dbias = _ptr(dbias)
     a.do_row_stride, a.do_batch_stride = do.stride(1), do.stride(0)
     a.dq_row_stride, a.dk_row_stride, a.dv_row_stride = dq.stride(1), dk.stride(1), dv.stride(1)
     a.dq_batch_stride, a.dk_batch_stride, a.dv_batch_stride = dq.stride(0), dk.stride(0), dv.stride(0)
@@ -313,8 +348,8 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, rms_only=False, want_dbet
     C = x.shape[-1]
     rows = x.numel() // C
     dx = torch.empty_like(x)
-    dgamma = torch.zeros(C, device=x.device, dtype=torch.float32)
-    dbeta = torch.zeros(C, device=x.device, dtype=torch.float32) if want_dbeta else None
+    dgamma = zeros_f32(C, device=x.device)
+    dbeta = zeros_f32(C, device=x.device) if want_dbeta else None
     _lib.check(_L().smx_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), _ptr(dres),
                                       _ptr(dx), _ptr(dgamma), _ptr(dbeta), rows, C, 1 if rms_only else 0, act,
                                       _stream()), "layernorm_bwd")
@@ -324,7 +359,7 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, rms_only=False, want_dbet
 def colsum(x2d):
     """fp32 column sums of a [rows, cols] bf16 matrix (row stride may exceed cols)."""
     rows, cols = x2d.shape
-    out = torch.zeros(cols, device=x2d.device, dtype=torch.float32)
+    out = zeros_f32(cols, device=x2d.device)
     assert x2d.stride(1) == 1
     _lib.check(_L().smx_colsum(_ptr(x2d), _ptr(out), rows, cols, x2d.stride(0), _stream()), "colsum")
     return out
@@ -339,6 +374,23 @@ def to_bf16(src):
     else:
         dst.copy_(src)
     return dst
+
+
+def build_cast_table(rows, device):
+    """rows: [(src_ptr, dst_ptr, n, dst_is_f32)] -> (device table of SmxCastEntry, n_entries, total_chunks)."""
+    import numpy as np
+    dt = np.dtype([("src", "<u8"), ("dst", "<u8"), ("n", "<i8"), ("f32", "<i4"), ("first", "<i4")])
+    tab = np.zeros(len(rows), dtype=dt)
+    chunk, first = 4096, 0
+    for i, (s, d, n, f) in enumerate(rows):
+        tab[i] = (s, d, n, f, first)
+        first += (n + chunk - 1) // chunk
+    t = torch.from_numpy(tab.view(np.uint8).copy()).to(device)
+    return t, len(rows), first
+
+
+def multi_cast(table, n_entries, total_chunks):
+    _lib.check(_L().smx_multi_cast(_ptr(table), n_entries, total_chunks, _stream()), "multi_cast")
 
 
 def add_bf16(a, b):
@@ -455,7 +507,7 @@ def posconv_wgrad(dpre, x, groups, ksize):
     """Returns dweight in Conv1d layout [H, cg, k] fp32."""
     B, T, H = x.shape
     cg = H // groups
-    dw = torch.zeros(groups, ksize, cg, cg, device=x.device, dtype=torch.float32)  # [g][tap][o][c]
+    dw = zeros_f32(groups, ksize, cg, cg, device=x.device)  # [g][tap][o][c]
     _lib.check(_L().smx_posconv_wgrad(_ptr(dpre), _ptr(x), _ptr(dw), B, T, H, groups, ksize, _stream()),
                "posconv_wgrad")
     return dw.permute(0, 2, 3, 1).reshape(H, cg, ksize).contiguous()
@@ -552,4 +604,66 @@ def weighted_sum_bwd_w(xs, dout):
     dw = torch.zeros(len(xs), device=dout.device, dtype=torch.float32)
     arr = (ctypes.c_void_p * len(xs))(*[x.data_ptr() for x in xs])
     _lib.check(_L().smx_weighted_sum_bwd_w(arr, _ptr(dout), _ptr(dw), len(xs), n, _stream()), "wsum_bwd")
+    return dw
+
+
+# ---------------------------------------------------------------------------
+# SpeechMixSelf losses, T5 relative position bias
+# ---------------------------------------------------------------------------
+def logits_chunk_f32(h, emb16_rows, bias_rows, alpha, out):
+    """out[M, vn] fp32 = alpha * h @ emb16_rows^T + bias_rows  (one vocabulary chunk of the LM head)."""
+    return linear_fwd(h, emb16_rows, bias=bias_rows, out_f32=True, alpha=alpha, out=out)
+
+
+def kl_chunk_fwd(s, t, vn, lse_t, cross):
+    _lib.check(_L().smx_kl_chunk_fwd(_ptr(s), _ptr(t), s.stride(0), s.shape[0], vn, _ptr(lse_t), _ptr(cross), _stream()),
+               "kl_chunk_fwd")
+
+
+def kl_finalize(cross, lse_s, lse_t, inv_batch):
+    out = torch.empty(1, device=cross.device, dtype=torch.float32)
+    _lib.check(_L().smx_kl_finalize(_ptr(cross), _ptr(lse_s), _ptr(lse_t), cross.numel(), inv_batch, _ptr(out), _stream()),
+               "kl_finalize")
+    return out
+
+
+def kl_chunk_bwd(s, t, vn, v0, labels, lse_s, lse_t, coef_ce, coef_kl, dlogits):
+    _lib.check(_L().smx_kl_chunk_bwd(_ptr(s), _ptr(t), s.stride(0), s.shape[0], vn, v0, _ptr(labels), _ptr(lse_s),
+                                     _ptr(lse_t), _ptr(coef_ce), _ptr(coef_kl), _ptr(dlogits), dlogits.stride(0),
+                                     _stream()), "kl_chunk_bwd")
+
+
+def self_mse_fwd(text_h, speech_h):
+    """text_h [B,Tt,D], speech_h [B,Ts,D] bf16 contiguous -> (loss[1] fp32, attn, diff)"""
+    B, Tt, D = text_h.shape
+    Ts = speech_h.shape[1]
+    attn = torch.empty(B, Tt, Ts, device=text_h.device, dtype=torch.float32)
+    diff = torch.empty(B, Tt, D, device=text_h.device, dtype=torch.float32)
+    loss = torch.zeros(1, device=text_h.device, dtype=torch.float32)
+    _lib.check(_L().smx_self_mse_fwd(_ptr(text_h), _ptr(speech_h), _ptr(attn), _ptr(diff), _ptr(loss), B, Tt, Ts, D,
+                                     _stream()), "self_mse_fwd")
+    return loss, attn, diff
+
+
+def self_mse_bwd(text_h, speech_h, attn, diff, gscale):
+    B, Tt, D = text_h.shape
+    Ts = speech_h.shape[1]
+    dsc = torch.empty(B, Tt, Ts, device=text_h.device, dtype=torch.float32)
+    ds = torch.empty_like(speech_h)
+    _lib.check(_L().smx_self_mse_bwd(_ptr(text_h), _ptr(speech_h), _ptr(attn), _ptr(diff), _ptr(dsc), _ptr(gscale),
+                                     _ptr(ds), B, Tt, Ts, D, _stream()), "self_mse_bwd")
+    return ds
+
+
+def relpos_bias_fwd(weight, table, heads, tq, tk, q_offset=0):
+    bias = torch.empty(heads, tq, tk, device=weight.device, dtype=torch.float32)
+    _lib.check(_L().smx_relpos_bias_fwd(_ptr(weight), _ptr(table), _ptr(bias), heads, tq, tk, q_offset, _stream()),
+               "relpos_fwd")
+    return bias
+
+
+def relpos_bias_bwd(dbias, table, heads, tq, tk, n_buckets, q_offset=0):
+    dw = torch.zeros(n_buckets, heads, device=dbias.device, dtype=torch.float32)
+    _lib.check(_L().smx_relpos_bias_bwd(_ptr(dbias), _ptr(table), _ptr(dw), heads, tq, tk, q_offset, n_buckets,
+                                        _stream()), "relpos_bwd")
     return dw

@@ -117,6 +117,10 @@ class SpeechMixEED(nn.Module):
         self.decoder_outputs = None
 
     # ------------------------------------------------------------------ reference API surface
+    def train(self, mode=True):
+        ops.CACHE.invalidate()   # bf16 working copies are re-derived from the fp32 masters after a mode switch
+        return super().train(mode)
+
     @property
     def device(self):
         return next(self.parameters()).device
@@ -185,6 +189,10 @@ class SpeechMixEED(nn.Module):
         """ref:speechmix/hf_model.py:378-447.  Returns a mapping with ``loss`` and ``logits`` (= argmax
         token ids, as the reference returns them at :446) plus the model-detail breadcrumbs."""
         detail = {} if return_model_detail else None
+        if encoder_outputs is None and torch.is_grad_enabled():
+            # a training pass: the optimizer may have moved the fp32 masters since the last pass (fused
+            # optimizers do not bump tensor versions) -> refresh all bf16 working copies in one launch
+            ops.CACHE.new_step()
         if encoder_outputs is None:
             encoder_outputs = self.encoder_model(input_values, output_hidden_states=True)
         if decoder_input_ids is None and labels is None:
@@ -199,7 +207,7 @@ class SpeechMixEED(nn.Module):
                 ids = self.tokenizer(decoder_text_prompt, return_tensors="pt")["input_ids"].to(self.device)
             else:
                 ids = decoder_text_prompt.to(self.device)
-            prompt = ops.EmbedFn.apply(ids, None, self.nlp_emb.weight, None, self.decoder_model.model.encoder.embed_scale, 0, 0)
+            prompt = ops.EmbedFn.apply(ids, None, self.nlp_emb.weight, None, self.decoder_model.get_encoder().embed_scale, 0, 0)
             inputs_embeds = torch.cat((prompt.expand(inputs_embeds.shape[0], -1, -1), inputs_embeds), 1)
         outputs = self.cal_loss(inputs_embeds=inputs_embeds, decoder_outputs=decoder_outputs,
                                 text_input_ids=text_input_ids, decoder_input_ids=decoder_input_ids, labels=labels,
@@ -286,6 +294,46 @@ class SpeechMixAdapter(SpeechMixEED):
         return hook
 
 
+class SpeechMixSelf(SpeechMixEED):
+    """ref:speechmix/hf_model.py:505-583 (HFSpeechMixSelf): the text model is frozen and used twice per step --
+    on the speech embeddings (student) and on ``text_input_ids`` (teacher) -- and the loss is
+    ``CE(student) + KLDiv(student || teacher, batchmean) + MSE(attention-projected speech states, text states)``.
+
+    The reference's ``cal_loss`` rejects the keyword arguments its own ``forward`` passes (SURVEY.md section 8c
+    caveat S), so this follows the body of that method literally, including the
+    ``.view`` memory reinterpretation of the speech states at :563-565."""
+
+    def custom_modules(self, **kwargs):
+        self.encoder_model.eval()
+        self.decoder_model.eval()
+        for _, p in self.decoder_model.named_parameters():
+            p.requires_grad = False
+
+    def cal_loss(self, inputs_embeds=None, text_input_ids=None, attention_mask=None, decoder_outputs=None,
+                 decoder_input_ids=None, labels=None, past_key_values=None, use_cache=None):
+        if labels is None or text_input_ids is None:
+            return super().cal_loss(inputs_embeds=inputs_embeds, text_input_ids=None, attention_mask=attention_mask,
+                                    decoder_outputs=decoder_outputs, decoder_input_ids=decoder_input_ids, labels=labels,
+                                    past_key_values=past_key_values, use_cache=use_cache)
+        lm = self.decoder_model
+        lm.eval()                                                              # ref :543
+        enc_s, hs_s = lm.encode(inputs_embeds=inputs_embeds, output_hidden_states=True)
+        hid_s = lm.decode_hidden(decoder_input_ids, enc_s)
+        with torch.no_grad():                                                  # frozen teacher on token ids: no gradient path
+            enc_t, _ = lm.encode(input_ids=text_input_ids, output_hidden_states=True)
+            hid_t = lm.decode_hidden(decoder_input_ids, enc_t)
+        w, b, scale = lm.lm_head_params()
+        B = hid_s.shape[0]
+        ce, kld, ids = ops.SelfDistillHeadFn.apply(hid_s, hid_t, w, b, labels, scale, B)
+        mse = ops.SelfMSEFn.apply(enc_t, enc_s)
+        loss = kld + ce + mse
+        self.decoder_outputs = [enc_s]
+        return SpeechOutput(loss=loss, logits=ids, argmax_ids=ids, ce_loss=ce, kld_loss=kld, mse_loss=mse,
+                            encoder_last_hidden_state=enc_s, decoder_last_hidden_state=hid_s,
+                            teacher_decoder_last_hidden_state=hid_t, encoder_hidden_states=tuple(hs_s))
+
+
 HFSpeechMixEED = SpeechMixEED
+HFSpeechMixSelf = SpeechMixSelf
 HFSpeechMixFixed = SpeechMixFixed
 HFSpeechMixAdapter = SpeechMixAdapter

@@ -17,44 +17,105 @@ from .kernels import ACT_DGELU, ACT_DRELU, ACT_GELU, ACT_NONE, ACT_RELU, BF16
 
 
 class WeightCache:
-    """bf16 / packed copies of fp32 parameters, keyed by tensor identity + version.
-    Entries hold weak references, so a recycled ``id()`` can never alias a dead tensor."""
+    """bf16 / packed working copies of the fp32 parameters.
+
+    An entry is valid while (a) the cache epoch has not moved, (b) the source tensors are the same
+    objects at the same address with the same ``_version``.  (b) alone is NOT enough: fused optimizers
+    (``torch.optim.AdamW(fused=True)``, ``_fused_adamw_``) update parameters without bumping
+    ``_version``, so every training forward starts a new epoch (``new_step``) and refreshes all plain
+    casts in ONE multi-tensor launch (``smx_multi_cast``); packed layouts (conv tap-major, pos-conv
+    core-matrix order) are rebuilt lazily on first use in the epoch.  Entries hold weak references,
+    so a recycled ``id()`` can never alias a dead tensor."""
 
     def __init__(self):
         self._store = {}
+        self.epoch = 0
+        self._tables = {}   # device -> (signature, device table tensor, n_entries, total_chunks)
 
-    def get(self, key_tensors, kind, build):
+    def get(self, key_tensors, kind, build, simple=None):
         if not isinstance(key_tensors, (tuple, list)):
             key_tensors = (key_tensors,)
         key = (kind,) + tuple(id(t) for t in key_tensors)
         ver = tuple((t._version, t.data_ptr()) for t in key_tensors)
         hit = self._store.get(key)
-        if hit is not None and hit[0] == ver and all(r() is t for r, t in zip(hit[2], key_tensors)):
+        if hit is not None and hit[3] == self.epoch and hit[0] == ver and \
+                all(r() is t for r, t in zip(hit[2], key_tensors)):
             return hit[1]
         with torch.no_grad():
             val = build(*key_tensors)
         if len(self._store) > 4096:
             self._store = {k: v for k, v in self._store.items() if all(r() is not None for r in v[2])}
-        self._store[key] = (ver, val, tuple(weakref.ref(t) for t in key_tensors))
+        self._store[key] = [ver, val, tuple(weakref.ref(t) for t in key_tensors), self.epoch,
+                            simple(val, key_tensors) if simple is not None else None]
         return val
+
+    def invalidate(self):
+        """Forget every copy (lazy rebuild); called on train()/eval() switches."""
+        self.epoch += 1
+
+    def new_step(self):
+        """Start a new epoch and refresh every plain cast from its fp32 master in one launch."""
+        self.epoch += 1
+        per_dev = {}
+        for key, ent in list(self._store.items()):
+            spec = ent[4]
+            if spec is None:
+                continue
+            srcs = [r() for r in ent[2]]
+            if any(t is None for t in srcs):
+                del self._store[key]
+                continue
+            ok = all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == n
+                     for t, (_, n, _) in zip(srcs, spec))
+            if not ok:
+                continue
+            per_dev.setdefault(srcs[0].device, []).append((ent, srcs, spec))
+        for dev, items in per_dev.items():
+            rows = []
+            for ent, srcs, spec in items:
+                for t, (dst, n, f32) in zip(srcs, spec):
+                    if n:
+                        rows.append((t.data_ptr(), dst.data_ptr(), n, f32))
+            sig = tuple(rows)
+            tab = self._tables.get(dev)
+            if tab is None or tab[0] != sig:
+                tab = (sig,) + K.build_cast_table(rows, dev)
+                self._tables[dev] = tab
+            with torch.cuda.device(dev):
+                K.multi_cast(tab[1], tab[2], tab[3])
+            for ent, srcs, _ in items:
+                ent[0] = tuple((t._version, t.data_ptr()) for t in srcs)
+                ent[3] = self.epoch
 
     def clear(self):
         self._store.clear()
+        self._tables.clear()
 
 
 CACHE = WeightCache()
 
 
+def _rows_spec(val, srcs, f32):
+    out, r = [], 0
+    for t in srcs:
+        n = t.shape[0]
+        out.append((val[r:r + n], t.numel(), f32))
+        r += n
+    return out
+
+
 def w16(p):
-    return CACHE.get(p, "bf16", lambda t: K.to_bf16(t))
+    return CACHE.get(p, "bf16", lambda t: K.to_bf16(t), simple=lambda v, ts: [(v, ts[0].numel(), 0)])
 
 
 def cat16(ps):
-    return CACHE.get(tuple(ps), "cat16", lambda *ts: K.to_bf16(torch.cat([t.detach() for t in ts], 0)))
+    return CACHE.get(tuple(ps), "cat16", lambda *ts: K.to_bf16(torch.cat([t.detach() for t in ts], 0)),
+                     simple=lambda v, ts: _rows_spec(v, ts, 0))
 
 
 def cat32(ps):
-    return CACHE.get(tuple(ps), "cat32", lambda *ts: torch.cat([t.detach().float() for t in ts], 0).contiguous())
+    return CACHE.get(tuple(ps), "cat32", lambda *ts: torch.cat([t.detach().float() for t in ts], 0).contiguous(),
+                     simple=lambda v, ts: _rows_spec(v, ts, 1))
 
 
 def conv_packed16(p):
@@ -142,24 +203,26 @@ class AttnBlockFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, src, cfg, q_w, q_b, k_w, k_b, v_w, v_b, o_w, o_b, ln_w, ln_b):
+    def forward(ctx, x, src, cfg, q_w, q_b, k_w, k_b, v_w, v_b, o_w, o_b, ln_w, ln_b, pos_bias=None):
         heads, causal, pre_ln, eps = cfg["heads"], cfg["causal"], cfg["pre_ln"], cfg["eps"]
+        rms = bool(cfg.get("rms", False))          # T5: RMSNorm (no mean, no beta)
         scale = cfg.get("scale", 1.0 / math.sqrt(64))
         B, T, H = x.shape
+        Hi = q_w.shape[0]                          # heads * 64 (== H except for some T5 sizes)
         x2 = x.reshape(B * T, H)
         if not x2.is_contiguous():
             x2 = x2.contiguous()
-        saved = {}
+        ln_b_d = None if ln_b is None else ln_b.detach()
         if pre_ln:
-            n, _, mean, rstd = K.layernorm_fwd(x2, ln_w.detach(), ln_b.detach(), eps)
+            n, _, mean, rstd = K.layernorm_fwd(x2, ln_w.detach(), ln_b_d, eps, rms_only=rms)
             a_in = n
         else:
             a_in = x2
         if src is None:
             wqkv = cat16((q_w, k_w, v_w))
             bqkv = cat32((q_b, k_b, v_b)) if q_b is not None else None
-            qkv = K.linear_fwd(a_in, wqkv, bqkv).view(B, T, 3 * H)
-            q, k, v = qkv[..., :H], qkv[..., H:2 * H], qkv[..., 2 * H:]
+            qkv = K.linear_fwd(a_in, wqkv, bqkv).view(B, T, 3 * Hi)
+            q, k, v = qkv[..., :Hi], qkv[..., Hi:2 * Hi], qkv[..., 2 * Hi:]
             kv_src2 = None
             Ts = T
         else:
@@ -167,86 +230,92 @@ class AttnBlockFn(torch.autograd.Function):
             src2 = src.reshape(Bs * Ts, Hs)
             if not src2.is_contiguous():
                 src2 = src2.contiguous()
-            q = K.linear_fwd(a_in, w16(q_w), None if q_b is None else q_b.detach()).view(B, T, H)
+            q = K.linear_fwd(a_in, w16(q_w), None if q_b is None else q_b.detach()).view(B, T, Hi)
             wkv = cat16((k_w, v_w))
             bkv = cat32((k_b, v_b)) if k_b is not None else None
-            kv = K.linear_fwd(src2, wkv, bkv).view(Bs, Ts, 2 * H)
-            k, v = kv[..., :H], kv[..., H:]
+            kv = K.linear_fwd(src2, wkv, bkv).view(Bs, Ts, 2 * Hi)
+            k, v = kv[..., :Hi], kv[..., Hi:]
             qkv = (q, kv)
             kv_src2 = src2
-        o, lse = K.attn_fwd(q, k, v, heads, causal=causal, scale=scale)
-        s = K.linear_fwd(o.view(B * T, H), w16(o_w), None if o_b is None else o_b.detach(), residual=x2)
+        pb = None if pos_bias is None else pos_bias.detach().float().contiguous()
+        o, lse = K.attn_fwd(q, k, v, heads, causal=causal, scale=scale, bias=pb)
+        s = K.linear_fwd(o.view(B * T, Hi), w16(o_w), None if o_b is None else o_b.detach(), residual=x2)
         if pre_ln:
             y = s
-            ctx.save_for_backward(x2, n, mean, rstd, o, lse, kv_src2, ln_w, *(qkv if src is not None else (qkv,)))
+            ctx.save_for_backward(x2, n, mean, rstd, o, lse, kv_src2, ln_w, pb, *(qkv if src is not None else (qkv,)))
         else:
-            y, _, mean, rstd = K.layernorm_fwd(s, ln_w.detach(), ln_b.detach(), eps)
-            ctx.save_for_backward(x2, s, mean, rstd, o, lse, kv_src2, ln_w, *(qkv if src is not None else (qkv,)))
-        ctx.cfg = dict(cfg, scale=scale)
-        ctx.dims = (B, T, H, Ts)
+            y, _, mean, rstd = K.layernorm_fwd(s, ln_w.detach(), ln_b_d, eps, rms_only=rms)
+            ctx.save_for_backward(x2, s, mean, rstd, o, lse, kv_src2, ln_w, pb, *(qkv if src is not None else (qkv,)))
+        ctx.cfg = dict(cfg, scale=scale, rms=rms)
+        ctx.dims = (B, T, H, Ts, Hi)
         ctx.cross = src is not None
         ctx.wrefs = (q_w, k_w, v_w, o_w)
         ctx.has_bias = q_b is not None
+        ctx.has_obias = o_b is not None
+        ctx.has_lnb = ln_b is not None
         return y.view(B, T, H)
 
     @staticmethod
     def backward(ctx, dy):
         cfg = ctx.cfg
-        heads, causal, pre_ln, scale = cfg["heads"], cfg["causal"], cfg["pre_ln"], cfg["scale"]
-        B, T, H, Ts = ctx.dims
+        heads, causal, pre_ln, scale, rms = cfg["heads"], cfg["causal"], cfg["pre_ln"], cfg["scale"], cfg["rms"]
+        B, T, H, Ts, Hi = ctx.dims
         q_w, k_w, v_w, o_w = ctx.wrefs
         sv = ctx.saved_tensors
-        x2, a, mean, rstd, o, lse, kv_src2, ln_w = sv[:8]
+        x2, a, mean, rstd, o, lse, kv_src2, ln_w, pb = sv[:9]
         dy2 = dy.reshape(B * T, H).contiguous()
         if pre_ln:
             ds = dy2
             a_in = a          # normalised input
         else:
-            ds, dlnw, dlnb = K.layernorm_bwd(dy2, a, ln_w.detach(), mean, rstd)
+            ds, dlnw, dlnb = K.layernorm_bwd(dy2, a, ln_w.detach(), mean, rstd, rms_only=rms, want_dbeta=ctx.has_lnb)
             a_in = x2
-        o2 = o.view(B * T, H)
-        d_ob = K.colsum(ds) if ctx.has_bias else None
+        o2 = o.view(B * T, Hi)
+        d_ob = K.colsum(ds) if ctx.has_obias else None
         d_ow = K.linear_wgrad(ds, o2) if _need(ctx, 9) else None
-        do = K.linear_dgrad(ds, w16(o_w)).view(B, T, H)
+        do = K.linear_dgrad(ds, w16(o_w)).view(B, T, Hi)
         dsrc = None
+        dpb = K.zeros_f32(*pb.shape, device=pb.device) if (pb is not None and _need(ctx, 13)) else None
         if not ctx.cross:
-            qkv = sv[8]
-            q, k, v = qkv[..., :H], qkv[..., H:2 * H], qkv[..., 2 * H:]
+            qkv = sv[9]
+            q, k, v = qkv[..., :Hi], qkv[..., Hi:2 * Hi], qkv[..., 2 * Hi:]
             dqkv = torch.empty_like(qkv)
-            K.attn_bwd(do, q, k, v, o, lse, heads, causal=causal, scale=scale, dq=dqkv[..., :H],
-                       dk=dqkv[..., H:2 * H], dv=dqkv[..., 2 * H:])
-            dqkv2 = dqkv.view(B * T, 3 * H)
+            K.attn_bwd(do, q, k, v, o, lse, heads, causal=causal, scale=scale, bias=pb, dq=dqkv[..., :Hi],
+                       dk=dqkv[..., Hi:2 * Hi], dv=dqkv[..., 2 * Hi:], dbias=dpb)
+            dqkv2 = dqkv.view(B * T, 3 * Hi)
             need_w = _need(ctx, 3) or _need(ctx, 5) or _need(ctx, 7)
             dwqkv = K.linear_wgrad(dqkv2, a_in) if need_w else None
             dbqkv = K.colsum(dqkv2) if (ctx.has_bias and need_w) else None
             wqkv = cat16((q_w, k_w, v_w))
             d_in = K.linear_dgrad(dqkv2, wqkv, residual=None if pre_ln else ds)
-            dq_w, dk_w, dv_w = (dwqkv[:H], dwqkv[H:2 * H], dwqkv[2 * H:]) if need_w else (None, None, None)
-            dq_b, dk_b, dv_b = (dbqkv[:H], dbqkv[H:2 * H], dbqkv[2 * H:]) if dbqkv is not None else (None, None, None)
+            dq_w, dk_w, dv_w = (dwqkv[:Hi], dwqkv[Hi:2 * Hi], dwqkv[2 * Hi:]) if need_w else (None, None, None)
+            dq_b, dk_b, dv_b = (dbqkv[:Hi], dbqkv[Hi:2 * Hi], dbqkv[2 * Hi:]) if dbqkv is not None else (None, None, None)
         else:
-            q, kv = sv[8], sv[9]
-            k, v = kv[..., :H], kv[..., H:]
+            q, kv = sv[9], sv[10]
+            k, v = kv[..., :Hi], kv[..., Hi:]
             dq = torch.empty_like(q)
             dkv = torch.empty_like(kv)
-            K.attn_bwd(do, q, k, v, o, lse, heads, causal=causal, scale=scale, dq=dq, dk=dkv[..., :H], dv=dkv[..., H:])
-            dq2 = dq.view(B * T, H)
-            dkv2 = dkv.view(-1, 2 * H)
+            K.attn_bwd(do, q, k, v, o, lse, heads, causal=causal, scale=scale, bias=pb, dq=dq, dk=dkv[..., :Hi],
+                       dv=dkv[..., Hi:], dbias=dpb)
+            dq2 = dq.view(B * T, Hi)
+            dkv2 = dkv.view(-1, 2 * Hi)
             need_q = _need(ctx, 3)
             need_kv = _need(ctx, 5) or _need(ctx, 7)
             dq_w = K.linear_wgrad(dq2, a_in) if need_q else None
             dq_b = K.colsum(dq2) if (ctx.has_bias and need_q) else None
             dwkv = K.linear_wgrad(dkv2, kv_src2) if need_kv else None
             dbkv = K.colsum(dkv2) if (ctx.has_bias and need_kv) else None
-            dk_w, dv_w = (dwkv[:H], dwkv[H:]) if need_kv else (None, None)
-            dk_b, dv_b = (dbkv[:H], dbkv[H:]) if dbkv is not None else (None, None)
+            dk_w, dv_w = (dwkv[:Hi], dwkv[Hi:]) if need_kv else (None, None)
+            dk_b, dv_b = (dbkv[:Hi], dbkv[Hi:]) if dbkv is not None else (None, None)
             d_in = K.linear_dgrad(dq2, w16(q_w), residual=None if pre_ln else ds)
             if _need(ctx, 1):
                 dsrc = K.linear_dgrad(dkv2, cat16((k_w, v_w))).view(-1, Ts, kv_src2.shape[1])
         if pre_ln:
-            dx, dlnw, dlnb = K.layernorm_bwd(d_in, x2, ln_w.detach(), mean, rstd, dres=ds)
+            dx, dlnw, dlnb = K.layernorm_bwd(d_in, x2, ln_w.detach(), mean, rstd, dres=ds, rms_only=rms,
+                                             want_dbeta=ctx.has_lnb)
         else:
             dx = d_in
-        return (dx.view(B, T, H), dsrc, None, dq_w, dq_b, dk_w, dk_b, dv_w, dv_b, d_ow, d_ob, dlnw, dlnb)
+        return (dx.view(B, T, H), dsrc, None, dq_w, dq_b, dk_w, dk_b, dv_w, dv_b, d_ow, d_ob, dlnw, dlnb, dpb)
 
 
 class FFNBlockFn(torch.autograd.Function):
@@ -262,8 +331,10 @@ class FFNBlockFn(torch.autograd.Function):
         x2 = x.reshape(-1, H)
         if not x2.is_contiguous():
             x2 = x2.contiguous()
+        rms = bool(cfg.get("rms", False))
+        ln_b_d = None if ln_b is None else ln_b.detach()
         if pre_ln:
-            n, _, mean, rstd = K.layernorm_fwd(x2, ln_w.detach(), ln_b.detach(), eps)
+            n, _, mean, rstd = K.layernorm_fwd(x2, ln_w.detach(), ln_b_d, eps, rms_only=rms)
             a_in = n
         else:
             a_in = x2
@@ -274,9 +345,10 @@ class FFNBlockFn(torch.autograd.Function):
             y = s
             ctx.save_for_backward(x2, n, mean, rstd, pre, h, ln_w)
         else:
-            y, _, mean, rstd = K.layernorm_fwd(s, ln_w.detach(), ln_b.detach(), eps)
+            y, _, mean, rstd = K.layernorm_fwd(s, ln_w.detach(), ln_b_d, eps, rms_only=rms)
             ctx.save_for_backward(x2, s, mean, rstd, pre, h, ln_w)
         ctx.pre_ln, ctx.dact, ctx.shp = pre_ln, dact, shp
+        ctx.rms, ctx.has_lnb = rms, ln_b is not None
         ctx.no_res = no_res
         ctx.wrefs = (w1, w2)
         ctx.has_bias = b1 is not None
@@ -291,7 +363,7 @@ class FFNBlockFn(torch.autograd.Function):
         if ctx.pre_ln:
             ds, a_in = dy2, a
         else:
-            ds, dlnw, dlnb = K.layernorm_bwd(dy2, a, ln_w.detach(), mean, rstd)
+            ds, dlnw, dlnb = K.layernorm_bwd(dy2, a, ln_w.detach(), mean, rstd, rms_only=ctx.rms, want_dbeta=ctx.has_lnb)
             a_in = x2
         db2 = K.colsum(ds) if ctx.has_bias else None
         dw2 = K.linear_wgrad(ds, h) if _need(ctx, 4) else None
@@ -300,7 +372,8 @@ class FFNBlockFn(torch.autograd.Function):
         dw1 = K.linear_wgrad(dpre, a_in) if _need(ctx, 2) else None
         d_in = K.linear_dgrad(dpre, w16(w1), residual=None if (ctx.pre_ln or ctx.no_res) else ds)
         if ctx.pre_ln:
-            dx, dlnw, dlnb = K.layernorm_bwd(d_in, x2, ln_w.detach(), mean, rstd, dres=None if ctx.no_res else ds)
+            dx, dlnw, dlnb = K.layernorm_bwd(d_in, x2, ln_w.detach(), mean, rstd, dres=None if ctx.no_res else ds,
+                                             rms_only=ctx.rms, want_dbeta=ctx.has_lnb)
         else:
             dx = d_in
         return dx.view(ctx.shp), None, dw1, db1, dw2, db2, dlnw, dlnb
@@ -470,7 +543,7 @@ class EmbedFn(torch.autograd.Function):
         else:
             B, T = x_in.shape[:2]
             dev = x_in.device
-        D = pos.shape[1] if pos is not None else tok.shape[1]
+        D = pos.shape[1] if pos is not None else (tok.shape[1] if tok is not None else x_in.shape[2])
         out = K.embed_fwd(ids, None if tok is None else tok.detach(), None if pos is None else pos.detach(),
                           None if x_in is None else x_in.contiguous(), B, T, D, scale, pos_offset, t_start, device=dev)
         ctx.save_for_backward(ids)
@@ -556,3 +629,137 @@ class WeightedSumFn(torch.autograd.Function):
         wl = norm_w.detach().float()
         dxs = [K.weighted_sum_fwd([dout], wl[l:l + 1].contiguous()) for l in range(len(xs))]
         return (dw, *dxs)
+
+
+# ---------------------------------------------------------------------------
+_BUCKET_TABLES = {}
+
+
+def t5_bucket_table(tq, tk, bidirectional, num_buckets, max_distance, device, q_offset=0):
+    """int32 table: index (j - (i + q_offset)) + (tq + q_offset - 1) -> relative-attention bucket.  Built on the
+    host with the reference's own arithmetic (hf:models/t5/modeling_t5.py:188-233, fp32 log on CPU) so that
+    bucket boundaries agree bit for bit with the CPU reference."""
+    key = (tq, tk, bool(bidirectional), num_buckets, max_distance, str(device), q_offset)
+    tab = _BUCKET_TABLES.get(key)
+    if tab is not None:
+        return tab
+    rel = torch.arange(-(tq + q_offset - 1), tk, dtype=torch.long)
+    nb = num_buckets
+    buckets = torch.zeros_like(rel)
+    if bidirectional:
+        nb //= 2
+        buckets += (rel > 0).to(torch.long) * nb
+        rel = torch.abs(rel)
+    else:
+        rel = -torch.min(rel, torch.zeros_like(rel))
+    max_exact = nb // 2
+    is_small = rel < max_exact
+    large = max_exact + (torch.log(rel.float() / max_exact) / math.log(max_distance / max_exact)
+                         * (nb - max_exact)).to(torch.long)
+    large = torch.min(large, torch.full_like(large, nb - 1))
+    buckets += torch.where(is_small, rel, large)
+    tab = buckets.to(torch.int32).to(device)
+    _BUCKET_TABLES[key] = tab
+    return tab
+
+
+class RelPosBiasFn(torch.autograd.Function):
+    """bias[h, i, j] = weight[bucket(j - i), h]   (hf:models/t5/modeling_t5.py:235-247, compute_bias)."""
+
+    @staticmethod
+    def forward(ctx, weight, table, tq, tk, q_offset):
+        nb, heads = weight.shape
+        ctx.save_for_backward(table)
+        ctx.meta = (heads, tq, tk, q_offset, nb)
+        return K.relpos_bias_fwd(weight.detach().float().contiguous(), table, heads, tq, tk, q_offset)
+
+    @staticmethod
+    def backward(ctx, dbias):
+        (table,) = ctx.saved_tensors
+        heads, tq, tk, q_offset, nb = ctx.meta
+        return K.relpos_bias_bwd(dbias.contiguous(), table, heads, tq, tk, nb, q_offset), None, None, None, None
+
+
+# ---------------------------------------------------------------------------
+KL_CHUNK = 4096
+
+
+class SelfDistillHeadFn(torch.autograd.Function):
+    """SpeechMixSelf output losses in one vocabulary sweep (ref:speechmix/hf_model.py:551-581):
+       ce  = CrossEntropy(student logits, labels)                       (ignore_index -100, mean)
+       kld = KLDiv(log_softmax(student logits), softmax(teacher logits), reduction="batchmean")
+    plus the student's argmax ids.  Student / teacher logits (h E^T * s + b) only ever exist as fp32
+    [rows, 4096] chunks that stay L2-resident between the GEMM and the reduction kernels."""
+
+    @staticmethod
+    def forward(ctx, h_s, h_t, emb, bias, labels, logit_scale, batch):
+        shp = h_s.shape
+        hs2 = h_s.reshape(-1, shp[-1]).contiguous()
+        ht2 = h_t.detach().reshape(-1, shp[-1]).contiguous()
+        e16 = w16(emb)
+        lab = labels.reshape(-1).contiguous()
+        b = None if bias is None else bias.detach().reshape(-1).float().contiguous()
+        M, V = hs2.shape[0], e16.shape[0]
+        lse_s, argmax, _, acc = K.lmhead_ce_fwd(hs2, e16, b, lab, logit_scale)
+        lse_t, _, _, _ = K.lmhead_ce_fwd(ht2, e16, b, torch.full_like(lab, -100), logit_scale)
+        cross = torch.zeros(M, device=hs2.device, dtype=torch.float32)
+        bs = torch.empty(M, KL_CHUNK, device=hs2.device, dtype=torch.float32)
+        bt = torch.empty(M, KL_CHUNK, device=hs2.device, dtype=torch.float32)
+        for v0 in range(0, V, KL_CHUNK):
+            vn = min(KL_CHUNK, V - v0)
+            bb = None if b is None else b[v0:v0 + vn]
+            K.logits_chunk_f32(hs2, e16[v0:v0 + vn], bb, logit_scale, bs[:, :vn])
+            K.logits_chunk_f32(ht2, e16[v0:v0 + vn], bb, logit_scale, bt[:, :vn])
+            K.kl_chunk_fwd(bs, bt, vn, lse_t, cross)
+        kld = K.kl_finalize(cross, lse_s, lse_t, 1.0 / batch)[0]
+        ce = acc[0] / acc[1]
+        ctx.save_for_backward(hs2, ht2, e16, lab, lse_s, lse_t, acc)
+        ctx.bias, ctx.scale, ctx.shp, ctx.batch = b, logit_scale, shp, batch
+        ctx.mark_non_differentiable(argmax)
+        return ce, kld, argmax.view(shp[:-1])
+
+    @staticmethod
+    def backward(ctx, d_ce, d_kl, _unused):
+        hs2, ht2, e16, lab, lse_s, lse_t, acc = ctx.saved_tensors
+        M, D = hs2.shape
+        V = e16.shape[0]
+        b = ctx.bias
+        coef_ce = ((lab != -100).float() * (d_ce.float() / acc[1])).contiguous()
+        coef_kl = (d_kl.float() / ctx.batch).reshape(1).contiguous()
+        need_h, need_e = _need(ctx, 0), _need(ctx, 2)
+        dh = torch.zeros(M, D, device=hs2.device, dtype=torch.float32) if need_h else None
+        dE = torch.empty(V, D, device=hs2.device, dtype=torch.float32) if need_e else None
+        bs = torch.empty(M, KL_CHUNK, device=hs2.device, dtype=torch.float32)
+        bt = torch.empty(M, KL_CHUNK, device=hs2.device, dtype=torch.float32)
+        buf = torch.empty(M, KL_CHUNK, device=hs2.device, dtype=BF16)
+        for v0 in range(0, V, KL_CHUNK):
+            vn = min(KL_CHUNK, V - v0)
+            bb = None if b is None else b[v0:v0 + vn]
+            K.logits_chunk_f32(hs2, e16[v0:v0 + vn], bb, ctx.scale, bs[:, :vn])
+            K.logits_chunk_f32(ht2, e16[v0:v0 + vn], bb, ctx.scale, bt[:, :vn])
+            K.kl_chunk_bwd(bs, bt, vn, v0, lab, lse_s, lse_t, coef_ce, coef_kl, buf)
+            if need_h:
+                K.gemm_nn_acc_f32(buf, vn, e16[v0:v0 + vn], dh, alpha=ctx.scale, accumulate=True)
+            if need_e:
+                K.gemm_tn_into(buf, vn, hs2, dE[v0:v0 + vn], alpha=ctx.scale)
+        dh16 = K.to_bf16(dh).view(ctx.shp) if need_h else None
+        return dh16, None, dE, None, None, None, None
+
+
+class SelfMSEFn(torch.autograd.Function):
+    """mse(softmax(T . view(S, [D, Ts]) / sqrt(D)) . S, T)   (ref:speechmix/hf_model.py:561-570);
+    T = teacher text-encoder states (no gradient), S = text-encoder states of the speech path."""
+
+    @staticmethod
+    def forward(ctx, text_h, speech_h):
+        t = text_h.detach().contiguous()
+        s = speech_h.contiguous()
+        loss, attn, diff = K.self_mse_fwd(t, s)
+        ctx.save_for_backward(t, s, attn, diff)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        t, s, attn, diff = ctx.saved_tensors
+        gscale = (g.float() * (2.0 / diff.numel())).reshape(1).contiguous()
+        return None, K.self_mse_bwd(t, s, attn, diff, gscale)

@@ -142,6 +142,10 @@ class Seq2SeqLM(nn.Module):
     def get_encoder(self):
         return self.model.encoder
 
+    def lm_head_params(self):
+        """(weight [V, D], bias [1, V], logit scale)  hf:...bart.py:940-942"""
+        return self.model.shared.weight, self.final_logits_bias, 1.0
+
     def encode(self, input_ids=None, inputs_embeds=None, output_hidden_states=False):
         return self.model.encoder(input_ids=input_ids, inputs_embeds=inputs_embeds,
                                   output_hidden_states=output_hidden_states)
@@ -173,7 +177,8 @@ class Seq2SeqLM(nn.Module):
         hidden = self.decode_hidden(decoder_input_ids, enc)
         B, T, _ = hidden.shape
         lab = labels if labels is not None else torch.full((B, T), -100, device=hidden.device, dtype=torch.long)
-        loss, ids = ops.LMHeadCEFn.apply(hidden, self.model.shared.weight, self.final_logits_bias, lab, 1.0)
+        w, b, scale = self.lm_head_params()
+        loss, ids = ops.LMHeadCEFn.apply(hidden, w, b, lab, scale)
         out = SpeechOutput(loss=loss if labels is not None else None, logits=ids, argmax_ids=ids,
                            encoder_last_hidden_state=enc, decoder_last_hidden_state=hidden)
         if output_hidden_states:
@@ -181,24 +186,202 @@ class Seq2SeqLM(nn.Module):
         return out
 
 
+
+# =============================================================================================
+# T5 (hf:models/t5/modeling_t5.py): RMSNorm pre-norm blocks, bias-free linears, UNSCALED attention
+# scores plus a bucketed relative position bias owned by block 0 of each stack and shared by all of
+# its blocks, ReLU feed-forward, tied LM head scaled by d_model**-0.5.
+# =============================================================================================
+class _RMSNorm(nn.Module):
+    """hf:...t5.py:46-69 (T5LayerNorm): weight only."""
+
+    def __init__(self, d):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(d))
+
+
+class _T5Attention(nn.Module):
+    """hf:...t5.py:153-345; parameter container (q, k, v, o without bias, optional bucket embedding)."""
+
+    def __init__(self, config, has_relative_attention_bias):
+        super().__init__()
+        inner = config.num_heads * config.d_kv
+        self.q = nn.Linear(config.d_model, inner, bias=False)
+        self.k = nn.Linear(config.d_model, inner, bias=False)
+        self.v = nn.Linear(config.d_model, inner, bias=False)
+        self.o = nn.Linear(inner, config.d_model, bias=False)
+        if has_relative_attention_bias:
+            self.relative_attention_bias = nn.Embedding(config.relative_attention_num_buckets, config.num_heads)
+
+    def params(self):
+        return (self.q.weight, None, self.k.weight, None, self.v.weight, None, self.o.weight, None)
+
+
+class _T5LayerSelfAttention(nn.Module):
+    def __init__(self, config, has_relative_attention_bias):
+        super().__init__()
+        self.SelfAttention = _T5Attention(config, has_relative_attention_bias)
+        self.layer_norm = _RMSNorm(config.d_model)
+
+
+class _T5LayerCrossAttention(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.EncDecAttention = _T5Attention(config, False)
+        self.layer_norm = _RMSNorm(config.d_model)
+
+
+class _T5DenseActDense(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.wi = nn.Linear(config.d_model, config.d_ff, bias=False)
+        self.wo = nn.Linear(config.d_ff, config.d_model, bias=False)
+
+
+class _T5LayerFF(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.DenseReluDense = _T5DenseActDense(config)
+        self.layer_norm = _RMSNorm(config.d_model)
+
+
+class _T5Block(nn.Module):
+    """hf:...t5.py:411-500"""
+
+    def __init__(self, config, is_decoder, has_relative_attention_bias):
+        super().__init__()
+        self.is_decoder = is_decoder
+        self.layer = nn.ModuleList([_T5LayerSelfAttention(config, has_relative_attention_bias)])
+        if is_decoder:
+            self.layer.append(_T5LayerCrossAttention(config))
+        self.layer.append(_T5LayerFF(config))
+        eps = config.layer_norm_epsilon
+        base = dict(heads=config.num_heads, pre_ln=True, rms=True, eps=eps, scale=1.0, act=config.dense_act_fn)
+        self.cfg_self = dict(base, causal=is_decoder)
+        self.cfg_cross = dict(base, causal=False)
+
+    def forward(self, x, pos_bias, enc=None):
+        sa = self.layer[0]
+        x = ops.AttnBlockFn.apply(x, None, self.cfg_self, *sa.SelfAttention.params(), sa.layer_norm.weight, None, pos_bias)
+        if self.is_decoder:
+            ca = self.layer[1]
+            x = ops.AttnBlockFn.apply(x, enc, self.cfg_cross, *ca.EncDecAttention.params(), ca.layer_norm.weight, None,
+                                      None)
+        ff = self.layer[-1]
+        return ops.FFNBlockFn.apply(x, self.cfg_cross, ff.DenseReluDense.wi.weight, None, ff.DenseReluDense.wo.weight,
+                                    None, ff.layer_norm.weight, None)
+
+
+class _T5Stack(nn.Module):
+    """hf:...t5.py:617-770"""
+
+    def __init__(self, config, shared, is_decoder):
+        super().__init__()
+        self.config = config
+        self.is_decoder = is_decoder
+        self.embed_tokens = shared
+        self.embed_scale = 1.0
+        n = config.num_decoder_layers if is_decoder else config.num_layers
+        self.block = nn.ModuleList([_T5Block(config, is_decoder, i == 0) for i in range(n)])
+        self.final_layer_norm = _RMSNorm(config.d_model)
+        self.layer_output_hook = None
+
+    def forward(self, input_ids=None, inputs_embeds=None, encoder_hidden_states=None, output_hidden_states=False):
+        cfg = self.config
+        if input_ids is not None:
+            x = ops.EmbedFn.apply(input_ids, None, self.embed_tokens.weight, None, 1.0, 0, 0)
+        else:
+            x = inputs_embeds if inputs_embeds.dtype == K.BF16 else ops.EmbedFn.apply(None, inputs_embeds, None, None, 1.0, 0, 0)
+        T = x.shape[1]
+        table = ops.t5_bucket_table(T, T, not self.is_decoder, cfg.relative_attention_num_buckets,
+                                    cfg.relative_attention_max_distance, x.device)
+        rel = self.block[0].layer[0].SelfAttention.relative_attention_bias.weight
+        pos_bias = ops.RelPosBiasFn.apply(rel, table, T, T, 0)
+        hs = [x] if output_hidden_states else None
+        for li, blk in enumerate(self.block):
+            x = blk(x, pos_bias, encoder_hidden_states)
+            if self.layer_output_hook is not None:
+                x = self.layer_output_hook(li, x)
+            if output_hidden_states:
+                hs.append(x)
+        x = ops.layer_norm(x, self.final_layer_norm.weight, None, cfg.layer_norm_epsilon, rms_only=True)
+        if output_hidden_states:
+            hs[-1] = x
+        return x, hs
+
+
+class T5Seq2SeqLM(nn.Module):
+    """Drop-in for ``AutoModelForSeq2SeqLM.from_pretrained(<t5>)`` on the SpeechMix path
+    (hf:...t5.py:940-1130, call site ref:speechmix/hf_model.py:357-374)."""
+
+    def __init__(self, config):
+        super().__init__()
+        if config.is_gated_act or config.dense_act_fn != "relu":
+            raise NotImplementedError("gated / non-ReLU T5 feed-forward (t5 v1.1) is not wired to the kernels")
+        if config.d_kv != 64:
+            raise NotImplementedError("attention kernels are specialised for head_dim 64")
+        self.config = config
+        self.shared = nn.Embedding(config.vocab_size, config.d_model)
+        self.encoder = _T5Stack(config, self.shared, is_decoder=False)
+        self.decoder = _T5Stack(config, self.shared, is_decoder=True)
+        self.lm_head = nn.Linear(config.d_model, config.vocab_size, bias=False)
+        if config.tie_word_embeddings:
+            self.lm_head.weight = self.shared.weight
+
+    base_model = property(lambda self: self)
+    device = property(lambda self: self.shared.weight.device)
+
+    def get_input_embeddings(self):
+        return self.shared
+
+    def get_encoder(self):
+        return self.encoder
+
+    def lm_head_params(self):
+        """(weight [V, D], bias or None, logit scale)  hf:...t5.py:1105-1110"""
+        return self.lm_head.weight, None, (self.config.d_model ** -0.5) if self.config.tie_word_embeddings else 1.0
+
+    def encode(self, input_ids=None, inputs_embeds=None, output_hidden_states=False):
+        return self.encoder(input_ids=input_ids, inputs_embeds=inputs_embeds, output_hidden_states=output_hidden_states)
+
+    def decode_hidden(self, decoder_input_ids, encoder_hidden_states):
+        x, _ = self.decoder(input_ids=decoder_input_ids, encoder_hidden_states=encoder_hidden_states)
+        return x
+
+    def full_logits(self, hidden):
+        w, _, scale = self.lm_head_params()
+        h2 = hidden.reshape(-1, hidden.shape[-1]).contiguous()
+        return K.linear_fwd(h2, ops.w16(w), None, out_f32=True, alpha=scale).view(*hidden.shape[:-1], -1)
+
+    forward = None  # assigned below (shared with the BART-family class)
+
+
+T5Seq2SeqLM.forward = Seq2SeqLM.forward
+
+
 def text_from_pretrained(path_or_config):
     from transformers import AutoConfig, PretrainedConfig
 
+    def build(config):
+        return T5Seq2SeqLM(config) if config.model_type == "t5" else Seq2SeqLM(config)
+
     if isinstance(path_or_config, PretrainedConfig):
-        return Seq2SeqLM(path_or_config)
+        return build(path_or_config)
     config = AutoConfig.from_pretrained(path_or_config)
-    model = Seq2SeqLM(config)
+    model = build(config)
     sd = dict(load_checkpoint_state(path_or_config))
     # tied aliases may be stored once
+    pre = "" if config.model_type == "t5" else "model."
+    aliases = [pre + "shared.weight", pre + "encoder.embed_tokens.weight", pre + "decoder.embed_tokens.weight"]
+    if getattr(config, "tie_word_embeddings", True):
+        aliases.append("lm_head.weight")
     base = None
-    for k in ("model.shared.weight", "model.encoder.embed_tokens.weight", "model.decoder.embed_tokens.weight",
-              "lm_head.weight"):
+    for k in aliases:
         if k in sd:
             base = sd[k]
             break
     own = model.state_dict()
-    for k in ("model.shared.weight", "model.encoder.embed_tokens.weight", "model.decoder.embed_tokens.weight",
-              "lm_head.weight"):
+    for k in aliases:
         sd.setdefault(k, base)
     missing = [k for k in own if k not in sd]
     if missing:

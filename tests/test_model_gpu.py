@@ -32,7 +32,7 @@ def _rel(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-12))
 
 
-@pytest.mark.parametrize("name", ["mini_eed_ds2", "mini_eed_ds8_ws", "mini_eed_share", "mini_large_mbart"])
+@pytest.mark.parametrize("name", ["mini_eed_ds2", "mini_eed_ds8_ws", "mini_eed_share", "mini_large_mbart", "mini_t5"])
 def test_eed_matches_oracle(name, cuda_device):
     fx = load_fixture(name)
     ora, x, labels = build_oracle(fx)
@@ -144,3 +144,63 @@ def test_adapter_matches_oracle(indexing, cuda_device):
             g = pm[k].grad.cpu()
             cos = float((g * p.grad).sum() / (g.norm() * p.grad.norm() + 1e-20))
             assert cos > 0.97, (k, cos)      # 12 stacked replace-adapters amplify bf16 noise; direction must agree
+
+
+def test_fused_optimizer_updates_reach_the_kernels(cuda_device):
+    """Fused optimizers (AdamW(fused=True)) move the fp32 masters WITHOUT bumping tensor versions; the bf16
+    working copies must still follow (ops.WeightCache.new_step).  Three SGD-like steps on our model (fused
+    AdamW) vs the oracle (plain AdamW): the losses must fall together."""
+    fx = load_fixture("mini_eed_ds2")
+    ora, x, labels = build_oracle(fx)
+    mine = _mine_from(ora, fx, cuda_device)
+    xo, lo = x, labels
+    xm, lm = x.to(cuda_device), labels.to(cuda_device)
+    opt_o = torch.optim.AdamW(ora.parameters(), lr=2e-4, weight_decay=0.0)
+    opt_m = torch.optim.AdamW(mine.parameters(), lr=2e-4, weight_decay=0.0, fused=True)
+    lo_hist, lm_hist = [], []
+    for _ in range(4):
+        opt_o.zero_grad(set_to_none=True)
+        l = ora(xo, labels=lo)["loss"]
+        l.backward()
+        opt_o.step()
+        lo_hist.append(float(l))
+        opt_m.zero_grad(set_to_none=True)
+        l = mine(xm, labels=lm)["loss"]
+        l.backward()
+        opt_m.step()
+        lm_hist.append(float(l))
+    drop_o, drop_m = lo_hist[0] - lo_hist[-1], lm_hist[0] - lm_hist[-1]
+    assert drop_o > 0.05, lo_hist
+    assert abs(drop_m - drop_o) < 0.35 * drop_o, (lo_hist, lm_hist)
+
+
+@pytest.mark.parametrize("text", ["t5-mini", "bart-mini"])
+def test_self_matches_oracle(text, cuda_device):
+    """SpeechMixSelf (ref:speechmix/hf_model.py:505-583): CE + KLDiv(batchmean) + attention-projection MSE against
+    the literal CPU restatement (oracle.OracleSelf, SURVEY.md 8c caveat S), losses and speech-side gradients."""
+    from oracle import hf_oracle as O
+    from speechmix_b200 import SpeechMixSelf
+    fx = dict(load_fixture("mini_t5"), text=text, kwargs={"down_scale": 2})
+    ora, x, labels = build_oracle(fx, cls=O.OracleSelf)
+    mine = _mine_from(ora, fx, cuda_device, cls=SpeechMixSelf)
+    assert mine.list_no_grad == ora.list_no_grad and mine.list_grad == ora.list_grad
+    g = torch.Generator().manual_seed(5)
+    text_ids = torch.randint(4, O.text_config(text).vocab_size, (fx["batch"], 11), generator=g)
+    ref = ora(x, labels=labels, text_input_ids=text_ids)
+    out = mine(x.to(cuda_device), labels=labels.to(cuda_device), text_input_ids=text_ids.to(cuda_device))
+    for k, tol in (("ce_loss", 3e-3), ("kld_loss", 3e-3), ("mse_loss", 3e-3), ("loss", 6e-3)):
+        assert abs(float(out[k]) - float(ref[k])) < tol + 1e-2 * abs(float(ref[k])), (k, float(out[k]), float(ref[k]))
+    assert _ids_agree(out["logits"], ref["logits"])
+    ref["loss"].backward()
+    out["loss"].backward()
+    po, pm = dict(ora.named_parameters()), dict(mine.named_parameters())
+    scale = max(float(p.grad.norm()) for p in po.values() if p.grad is not None)
+    checked = 0
+    for k, p in po.items():
+        if p.grad is None:
+            assert pm[k].grad is None, k
+            continue
+        err = float((pm[k].grad.cpu() - p.grad).norm())
+        assert err <= 6e-2 * float(p.grad.norm()) + 3e-4 * scale, (k, err, float(p.grad.norm()))
+        checked += 1
+    assert checked == len(mine.list_grad)
