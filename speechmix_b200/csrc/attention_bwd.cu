@@ -11,6 +11,7 @@
 #include "host_common.h"
 #include "sm100_prims.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace smx {
@@ -18,6 +19,8 @@ namespace attn {
 
 int make_head_map(CUtensorMap* m, const void* ptr, int t, int heads, int batch, long long row_stride,
                   long long batch_stride);
+int make_head_map_rows(CUtensorMap* m, const void* ptr, int t, int heads, int batch, long long row_stride,
+                       long long batch_stride, int box_rows);
 
 constexpr int D = 64;
 constexpr int TILE = 128 * D * 2;   // 16 KiB
@@ -30,6 +33,7 @@ struct BwdParams {
   const float* bias;
   float* dbias;      // [heads, tq, tk] fp32, accumulated with atomics over the batch (T5 relative position bias)
   float inv_scale;
+  long long* prof;    // optional [8] cycle counters (development): see tools/probe_attn.py prof
   bf16 *dq, *dk, *dv;
   long long dq_row_stride, dq_batch_stride, dk_row_stride, dk_batch_stride, dv_row_stride, dv_batch_stride;
   int batch, heads, tq, tk, causal;
@@ -463,6 +467,478 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+
+// =====================================================================================
+// Pipelined TMEM-operand variants (the default).  What v1 above loses:
+//   * it alternates strictly between the tensor pipe and the exponentials (single score buffer), and
+//   * every MMA reads BOTH operands from shared memory while the compute warps also write P / dS there:
+//     measured 114 clk per 128x64x16 MMA inside the kernel against 45 clk in isolation (tools/micro/mma_rate.cu).
+// Here the stationary tile (K,V for dK/dV; Q,dO for dQ) is copied ONCE into TMEM and used as the A operand
+// (tcgen05.mma with A in TMEM), the streamed dimension is walked in 64-wide sub-tiles whose score / dP
+// accumulators are double-buffered in TMEM, P^T / dS^T are written back to TMEM as bf16 (aliasing the fp32
+// scores they came from, FA4-style) and consumed from there as A operands of the gradient MMAs, and two groups
+// of four compute warps alternate on the sub-tiles.  Shared memory only carries the streamed 64-row tiles.
+// TMEM columns: [0,32) [32,64) stationary A operands | buffer b: scores [64+128b, +64), dP [128+128b, +64)
+//               | accumulators from 320.
+// =====================================================================================
+#ifdef SMX_ATTN_PROF
+#define SMX_PROF(...) __VA_ARGS__
+#else
+#define SMX_PROF(...)
+#endif
+constexpr int SUB = 64;                  // streamed rows per sub-tile
+constexpr int SUBTILE = SUB * D * 2;     // 8 KiB: a [64 x 64] bf16 tile
+constexpr int NST = 4;                   // TMA ring depth
+constexpr int COL_A0 = 0, COL_A1 = 32, COL_BUF = 64, COL_ACC = 320;
+
+__device__ __forceinline__ void tmem_st_x32_raw(uint32_t taddr, const uint32_t (&v)[32]) { tmem_st_x32(taddr, v); }
+
+// Lean descriptor form (the issuing thread shares its scheduler with MUFU-bound compute warps, so every
+// instruction in front of a tcgen05.mma costs issue slots): the high descriptor word (SBO = 1024 B, version,
+// 128B swizzle) is a constant, the low word is (address >> 4) | (LBO >> 4) << 16 plus a per-K-step immediate.
+constexpr uint32_t kDescHi = ((1024u >> 4) & 0x3fffu) | (1u << 14) | (static_cast<uint32_t>(kLayoutSW128) << 29);
+__device__ __forceinline__ uint64_t lean_desc(uint32_t lo) { return (static_cast<uint64_t>(kDescHi) << 32) | lo; }
+// D[128 x 64] = A (TMEM, bf16 [128 x 64] in 32 columns) x B^T, B = K-major [64 x 64] smem sub-tile; 4 K-steps
+__device__ __forceinline__ void mma_tA_x_subT(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_sub, uint32_t idesc) {
+  const uint32_t lo = (b_sub >> 4) | ((16u >> 4) << 16);
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) umma_ts(d_tmem, a_tmem + kk * 8, lean_desc(lo + kk * 2), idesc, kk > 0 ? 1u : 0u);
+}
+// D[128 x 64] (+)= A (TMEM, bf16 [128 x 64]) x B, B = MN-major [64 rows(K) x 64] smem sub-tile; 4 K-steps
+__device__ __forceinline__ void mma_tA_x_sub(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_sub, uint32_t idesc,
+                                             bool accumulate) {
+  const uint32_t lo = (b_sub >> 4) | ((static_cast<uint32_t>(SUBTILE) >> 4) << 16);
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk)
+    umma_ts(d_tmem, a_tmem + kk * 8, lean_desc(lo + kk * 128), idesc, (accumulate || kk > 0) ? 1u : 0u);
+}
+// copy row r of a K-major 128B-swizzled [128 x 64] bf16 smem tile into 32 TMEM columns of this thread's lane
+__device__ __forceinline__ void smem_row_to_tmem(const uint8_t* tile, int r, uint32_t taddr) {
+  uint32_t v[32];
+  const uint8_t* row = tile + r * 128;
+  const int sw = r & 7;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + ((c ^ sw) << 4));
+    v[c * 4 + 0] = u.x, v[c * 4 + 1] = u.y, v[c * 4 + 2] = u.z, v[c * 4 + 3] = u.w;
+  }
+  tmem_st_x32(taddr, v);
+}
+
+namespace kv2 {
+constexpr int OFF_K = 0, OFF_V = TILE, OFF_Q = 2 * TILE, OFF_DO = OFF_Q + NST * SUBTILE,
+              OFF_STAT = OFF_DO + NST * SUBTILE;  // stat: [group][buf][128] floats
+constexpr int OFF_BAR = OFF_STAT + 2 * 2 * 128 * 4;
+constexpr int SMEM_BYTES = OFF_BAR + 256;
+constexpr int COL_DV = COL_ACC, COL_DK = COL_ACC + 64;
+enum { B_KV = 0, B_KVT = 1, B_QFULL = 2, B_QEMPTY = B_QFULL + NST, B_STFULL = B_QEMPTY + NST,
+       B_PDSFULL = B_STFULL + 2, B_DONE = B_PDSFULL + 2, B_COUNT = B_DONE + 1 };
+}  // namespace kv2
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
+                     const __grid_constant__ CUtensorMap mv, const __grid_constant__ CUtensorMap mdo,
+                     const BwdParams p) {
+  using namespace kv2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kv0 = blockIdx.x * 128;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int nq_sub = (p.tq + SUB - 1) / SUB;
+  int i_start = 0;
+  if (p.causal) {  // first query row that can see key kv0:  q >= kv0 - (tk - tq)
+    int qmin = kv0 - (p.tk - p.tq);
+    if (qmin < 0) qmin = 0;
+    i_start = qmin / SUB;
+    if (i_start > nq_sub) i_start = nq_sub;
+  }
+  const int n_iter = nq_sub - i_start;
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    mbar_init(&bars[B_KV], 1);
+    mbar_init(&bars[B_KVT], 256);
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(&bars[B_QFULL + s], 1);
+      mbar_init(&bars[B_QEMPTY + s], 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&bars[B_STFULL + g], 1);
+      mbar_init(&bars[B_PDSFULL + g], 128);
+    }
+    mbar_init(&bars[B_DONE], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t sbase = smem_u32(smem);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&bars[B_KV], 2 * TILE);
+      tma_load_4d(smem + OFF_K, &mk, &bars[B_KV], 0, kv0, head, b);
+      tma_load_4d(smem + OFF_V, &mv, &bars[B_KV], 0, kv0, head, b);
+      for (int it = 0; it < n_iter; ++it) {
+        const int st = it % NST;
+        const uint32_t par = (it / NST) & 1;
+        const int qr = (i_start + it) * SUB;
+        mbar_wait(&bars[B_QEMPTY + st], par ^ 1);
+        mbar_expect_tx(&bars[B_QFULL + st], 2 * SUBTILE);
+        tma_load_4d(smem + OFF_Q + st * SUBTILE, &mq, &bars[B_QFULL + st], 0, qr, head, b);
+        tma_load_4d(smem + OFF_DO + st * SUBTILE, &mdo, &bars[B_QFULL + st], 0, qr, head, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, SUB, false, false);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, D, false, true);
+      mbar_wait(&bars[B_KVT], 0);   // K, V sit in TMEM as A operands
+      tc_fence_after_sync();
+      // The tensor pipe executes MMAs in issue order, so the scores of sub-tile it may overwrite the P^T / dS^T
+      // of sub-tile it-2 (same buffer) without a barrier: the gradient MMAs that read them were issued before.
+      for (int it = 0; it <= n_iter; ++it) {
+        if (it < n_iter) {  // scores of sub-tile `it` into TMEM buffer it & 1
+          const int st = it % NST, g = it & 1;
+          mbar_wait(&bars[B_QFULL + st], (it / NST) & 1);
+          tc_fence_after_sync();
+          const uint32_t buf = tmem_base + COL_BUF + g * 128;
+          mma_tA_x_subT(buf, tmem_base + COL_A0, sbase + OFF_Q + st * SUBTILE, idesc_s);
+          mma_tA_x_subT(buf + 64, tmem_base + COL_A1, sbase + OFF_DO + st * SUBTILE, idesc_s);
+          umma_commit(&bars[B_STFULL + g]);
+        }
+        if (it > 0) {       // gradient MMAs of sub-tile it - 1
+          const int j = it - 1, st = j % NST, g = j & 1, u = j >> 1;
+          mbar_wait(&bars[B_PDSFULL + g], u & 1);
+          tc_fence_after_sync();
+          const uint32_t buf = tmem_base + COL_BUF + g * 128;
+          mma_tA_x_sub(tmem_base + COL_DV, buf, sbase + OFF_DO + st * SUBTILE, idesc_o, j > 0);        // P^T . dO
+          mma_tA_x_sub(tmem_base + COL_DK, buf + 64, sbase + OFF_Q + st * SUBTILE, idesc_o, j > 0);    // dS^T . Q
+          umma_commit(&bars[B_QEMPTY + st]);
+        }
+      }
+      umma_commit(&bars[B_DONE]);
+    }
+  } else {
+    const int cw = warp - 2;        // 0..7
+    const int g = cw >> 2;          // compute group: sub-tiles with (it & 1) == g
+    const int q = warp & 3;         // TMEM lane quarter
+    const int r = q * 32 + lane;    // key row inside the tile
+    const int kvi = kv0 + r;
+    const int gt = (cw & 3) * 32 + lane;  // 0..127 inside the group
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t t_buf = t_row + COL_BUF + g * 128;
+    float* stat = reinterpret_cast<float*>(smem + OFF_STAT) + g * 256;
+    const bool lean = !p.causal && p.bias == nullptr;
+    // lse (log2 domain) / delta*scale of the 64 queries of a sub-tile: thread gt < 64 owns lse[gt], the others
+    // delta[gt - 64].  The global load for the group's NEXT sub-tile is issued one sub-tile ahead so its latency
+    // hides behind the exponentials of the current one.
+    const float* stat_src = (gt < 64 ? p.lse : p.delta) + ((long long)b * p.heads + head) * p.tq;
+    const float stat_mul = gt < 64 ? kLog2e : p.scale;
+    auto load_stat = [&](int it) -> float {
+      const int qi = (i_start + it) * SUB + (gt & 63);
+      return (it < n_iter && qi < p.tq) ? stat_src[qi] * stat_mul : 0.f;
+    };
+    float stat_next = load_stat(g);
+    // stationary operands -> TMEM (group 0: K, group 1: V)
+    mbar_wait(&bars[B_KV], 0);
+    smem_row_to_tmem(smem + (g == 0 ? OFF_K : OFF_V), r, t_row + (g == 0 ? COL_A0 : COL_A1));
+    tmem_st_wait();
+    tc_fence_before_sync();
+    mbar_arrive(&bars[B_KVT]);
+    for (int it = g; it < n_iter; it += 2) {
+      const int u = it >> 1;
+      const int q0 = (i_start + it) * SUB;
+      float* st = stat + (u & 1) * 128;
+      st[gt] = stat_next;
+      stat_next = load_stat(it + 2);
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+      mbar_wait(&bars[B_STFULL + g], u & 1);
+      tc_fence_after_sync();
+      uint32_t pk[32], dk[32];   // P^T and dS^T of this row, bf16 pairs
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t sv[32], dv[32];
+        tmem_ld_x32(t_buf + cc * 32, sv);
+        tmem_ld_x32(t_buf + 64 + cc * 32, dv);
+        tmem_ld_wait();
+        if (lean) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 l4 = *reinterpret_cast<const float4*>(st + cc * 32 + i);
+            const float4 d4 = *reinterpret_cast<const float4*>(st + 64 + cc * 32 + i);
+            const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
+            float e[4], d[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              e[k] = ex2_approx(fmaf(__uint_as_float(sv[i + k]), p.scale_log2, -lv[k]));
+              d[k] = e[k] * fmaf(__uint_as_float(dv[i + k]), p.scale, -dl[k]);
+            }
+            pk[cc * 16 + (i >> 1)] = pack_bf16x2(e[0], e[1]);
+            pk[cc * 16 + (i >> 1) + 1] = pack_bf16x2(e[2], e[3]);
+            dk[cc * 16 + (i >> 1)] = pack_bf16x2(d[0], d[1]);
+            dk[cc * 16 + (i >> 1) + 1] = pack_bf16x2(d[2], d[3]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float e[2], d[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const int col = cc * 32 + i + k;
+              const int qi = q0 + col;
+              float s = __uint_as_float(sv[i + k]) * p.scale_log2;
+              if (p.bias && qi < p.tq && kvi < p.tk) s += p.bias[((long long)head * p.tq + qi) * p.tk + kvi] * kLog2e;
+              const bool ok = (qi < p.tq) && (kvi < p.tk) && (!p.causal || kvi <= qi + (p.tk - p.tq));
+              e[k] = ok ? ex2_approx(s - st[col]) : 0.f;
+              d[k] = e[k] * fmaf(__uint_as_float(dv[i + k]), p.scale, -st[64 + col]);
+            }
+            pk[cc * 16 + (i >> 1)] = pack_bf16x2(e[0], e[1]);
+            dk[cc * 16 + (i >> 1)] = pack_bf16x2(d[0], d[1]);
+          }
+        }
+      }
+      tmem_st_x32(t_buf, pk);        // P^T  over the first 32 columns of the scores it came from
+      tmem_st_x32(t_buf + 64, dk);   // dS^T over the first 32 columns of dP^T
+      tmem_st_wait();
+      tc_fence_before_sync();
+      mbar_arrive(&bars[B_PDSFULL + g]);
+    }
+    mbar_wait(&bars[B_DONE], 0);
+    tc_fence_after_sync();
+    const bool valid = kvi < p.tk;
+    if (g == 0) {
+      bf16* dst = p.dv + (long long)b * p.dv_batch_stride + (long long)kvi * p.dv_row_stride + head * D;
+      if (n_iter == 0) {
+        if (valid)
+          for (int i = 0; i < D; i += 8) *reinterpret_cast<uint4*>(dst + i) = make_uint4(0, 0, 0, 0);
+      } else {
+        store_out_row(dst, t_row + COL_DV, valid);
+      }
+    } else {
+      bf16* dst = p.dk + (long long)b * p.dk_batch_stride + (long long)kvi * p.dk_row_stride + head * D;
+      if (n_iter == 0) {
+        if (valid)
+          for (int i = 0; i < D; i += 8) *reinterpret_cast<uint4*>(dst + i) = make_uint4(0, 0, 0, 0);
+      } else {
+        store_out_row(dst, t_row + COL_DK, valid);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+namespace dq2 {
+constexpr int OFF_Q = 0, OFF_DO = TILE, OFF_K = 2 * TILE, OFF_V = OFF_K + NST * SUBTILE;
+constexpr int OFF_BAR = OFF_V + NST * SUBTILE;
+constexpr int SMEM_BYTES = OFF_BAR + 256;
+constexpr int NBUF = 3;                       // score / dP buffers: [64 + 128 i, +128), i < 3
+constexpr int COL_DQ = COL_BUF + NBUF * 128;  // 448
+enum { B_Q = 0, B_QT = 1, B_KFULL = 2, B_KEMPTY = B_KFULL + NST, B_SFULL = B_KEMPTY + NST, B_DSFULL = B_SFULL + NBUF,
+       B_DONE = B_DSFULL + NBUF, B_COUNT = B_DONE + 1 };
+}  // namespace dq2
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
+                    const __grid_constant__ CUtensorMap mv, const __grid_constant__ CUtensorMap mdo,
+                    const BwdParams p) {
+  using namespace dq2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128;
+  const int head = blockIdx.y, b = blockIdx.z;
+  int n_iter = (p.tk + SUB - 1) / SUB;
+  if (p.causal) {
+    const int last_col = q0 + 127 + (p.tk - p.tq);
+    int nc = last_col / SUB + 1;
+    if (nc < 1) nc = 1;
+    if (nc < n_iter) n_iter = nc;
+  }
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    mbar_init(&bars[B_Q], 1);
+    mbar_init(&bars[B_QT], 256);
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(&bars[B_KFULL + s], 1);
+      mbar_init(&bars[B_KEMPTY + s], 1);
+    }
+    for (int i = 0; i < NBUF; ++i) {
+      mbar_init(&bars[B_SFULL + i], 1);
+      mbar_init(&bars[B_DSFULL + i], 128);
+    }
+    mbar_init(&bars[B_DONE], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t sbase = smem_u32(smem);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&bars[B_Q], 2 * TILE);
+      tma_load_4d(smem + OFF_Q, &mq, &bars[B_Q], 0, q0, head, b);
+      tma_load_4d(smem + OFF_DO, &mdo, &bars[B_Q], 0, q0, head, b);
+      for (int it = 0; it < n_iter; ++it) {
+        const int st = it % NST;
+        const uint32_t par = (it / NST) & 1;
+        mbar_wait(&bars[B_KEMPTY + st], par ^ 1);
+        mbar_expect_tx(&bars[B_KFULL + st], 2 * SUBTILE);
+        tma_load_4d(smem + OFF_K + st * SUBTILE, &mk, &bars[B_KFULL + st], 0, it * SUB, head, b);
+        tma_load_4d(smem + OFF_V + st * SUBTILE, &mv, &bars[B_KFULL + st], 0, it * SUB, head, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, SUB, false, false);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, D, false, true);
+      SMX_PROF(long long pm_kfull = 0, pm_dsfull = 0, pm_issue_s = 0, pm_issue_dq = 0;)
+      SMX_PROF(const long long pm_start = clock64();)
+      mbar_wait(&bars[B_QT], 0);    // Q, dO sit in TMEM as A operands
+      tc_fence_after_sync();
+      for (int it = 0; it <= n_iter; ++it) {
+        if (it < n_iter) {
+          // sub-tile `it` uses buffer it % 3: its scores are issued while the compute groups still work on
+          // sub-tiles it-1 and it-2 (in-order tensor pipe: the dQ MMA of sub-tile it-3 that read this buffer's
+          // dS was issued earlier)
+          const int st = it % NST, g = it % NBUF;
+          SMX_PROF(const long long t0 = clock64();)
+          mbar_wait(&bars[B_KFULL + st], (it / NST) & 1);
+          SMX_PROF(const long long t1 = clock64();)
+          SMX_PROF(pm_kfull += t1 - t0;)
+          tc_fence_after_sync();
+          const uint32_t buf = tmem_base + COL_BUF + g * 128;
+          mma_tA_x_subT(buf, tmem_base + COL_A0, sbase + OFF_K + st * SUBTILE, idesc_s);
+          mma_tA_x_subT(buf + 64, tmem_base + COL_A1, sbase + OFF_V + st * SUBTILE, idesc_s);
+          umma_commit(&bars[B_SFULL + g]);
+          SMX_PROF(pm_issue_s += clock64() - t1;)
+        }
+        if (it > 1 || it == n_iter) {   // dQ of sub-tile it-2 (and the tail) -- one extra sub-tile of slack
+          for (int j = (it > 1 ? it - 2 : 0); j < (it == n_iter ? n_iter : it - 1); ++j) {
+          const int st = j % NST, g = j % NBUF, u = j / NBUF;
+          SMX_PROF(const long long t0 = clock64();)
+          mbar_wait(&bars[B_DSFULL + g], u & 1);
+          SMX_PROF(const long long t1 = clock64();)
+          SMX_PROF(pm_dsfull += t1 - t0;)
+          tc_fence_after_sync();
+          mma_tA_x_sub(tmem_base + COL_DQ, tmem_base + COL_BUF + g * 128, sbase + OFF_K + st * SUBTILE, idesc_o, j > 0);
+          umma_commit(&bars[B_KEMPTY + st]);
+          SMX_PROF(pm_issue_dq += clock64() - t1;)
+          }
+        }
+      }
+      umma_commit(&bars[B_DONE]);
+      SMX_PROF(
+      if (p.prof) {
+        atomicAdd((unsigned long long*)p.prof + 0, (unsigned long long)pm_kfull);
+        atomicAdd((unsigned long long*)p.prof + 2, (unsigned long long)pm_dsfull);
+        atomicAdd((unsigned long long*)p.prof + 1, (unsigned long long)pm_issue_s);
+        atomicAdd((unsigned long long*)p.prof + 5, (unsigned long long)pm_issue_dq);
+        atomicAdd((unsigned long long*)p.prof + 3, (unsigned long long)(clock64() - pm_start));
+      }
+      )
+    }
+  } else {
+    const int cw = warp - 2;
+    const int g = cw >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int qi = q0 + r;
+    SMX_PROF(long long pc_sfull = 0, pc_comp = 0;)
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    float lse2 = 0.f, delta = 0.f;
+    if (qi < p.tq) {
+      const long long idx = ((long long)b * p.heads + head) * p.tq + qi;
+      lse2 = p.lse[idx] * kLog2e;
+      delta = p.delta[idx] * p.scale;
+    }
+    const bool lean = !p.causal && p.bias == nullptr;
+    const int causal_lim = p.causal ? qi + (p.tk - p.tq) : 0x7fffffff;
+    // stationary operands -> TMEM (group 0: Q, group 1: dO)
+    mbar_wait(&bars[B_Q], 0);
+    smem_row_to_tmem(smem + (g == 0 ? OFF_Q : OFF_DO), r, t_row + (g == 0 ? COL_A0 : COL_A1));
+    tmem_st_wait();
+    tc_fence_before_sync();
+    mbar_arrive(&bars[B_QT]);
+    for (int it = g; it < n_iter; it += 2) {
+      const int bi = it % NBUF, u = it / NBUF;
+      const uint32_t t_buf = t_row + COL_BUF + bi * 128;
+      const int k0 = it * SUB;
+      SMX_PROF(const long long t0 = clock64();)
+      mbar_wait(&bars[B_SFULL + bi], u & 1);
+      tc_fence_after_sync();
+      SMX_PROF(const long long t2 = clock64();)
+      SMX_PROF(pc_sfull += t2 - t0;)
+      uint32_t dk[32];   // dS of this row, bf16 pairs
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t sv[32], dv[32];
+        tmem_ld_x32(t_buf + cc * 32, sv);
+        tmem_ld_x32(t_buf + 64 + cc * 32, dv);
+        tmem_ld_wait();
+        if (lean) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float e0 = ex2_approx(fmaf(__uint_as_float(sv[i]), p.scale_log2, -lse2));
+            const float e1 = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), p.scale_log2, -lse2));
+            dk[cc * 16 + (i >> 1)] = pack_bf16x2(e0 * fmaf(__uint_as_float(dv[i]), p.scale, -delta),
+                                                 e1 * fmaf(__uint_as_float(dv[i + 1]), p.scale, -delta));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float d[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const int kvi = k0 + cc * 32 + i + k;
+              float s = __uint_as_float(sv[i + k]) * p.scale_log2;
+              if (p.bias && qi < p.tq && kvi < p.tk) s += p.bias[((long long)head * p.tq + qi) * p.tk + kvi] * kLog2e;
+              const bool ok = (qi < p.tq) && (kvi < p.tk) && (kvi <= causal_lim);
+              const float e = ok ? ex2_approx(s - lse2) : 0.f;
+              d[k] = e * fmaf(__uint_as_float(dv[i + k]), p.scale, -delta);
+              if (p.dbias && ok) atomicAdd(p.dbias + ((long long)head * p.tq + qi) * p.tk + kvi, d[k] * p.inv_scale);
+            }
+            dk[cc * 16 + (i >> 1)] = pack_bf16x2(d[0], d[1]);
+          }
+        }
+      }
+      tmem_st_x32(t_buf, dk);   // dS over the first 32 columns of the scores
+      tmem_st_wait();
+      tc_fence_before_sync();
+      mbar_arrive(&bars[B_DSFULL + bi]);
+      SMX_PROF(pc_comp += clock64() - t2;)
+    }
+    SMX_PROF(
+    if (p.prof && (threadIdx.x & 127) == 64) {
+      atomicAdd((unsigned long long*)p.prof + 4, (unsigned long long)pc_sfull);
+      atomicAdd((unsigned long long*)p.prof + 6, (unsigned long long)pc_comp);
+    }
+    )
+    mbar_wait(&bars[B_DONE], 0);
+    tc_fence_after_sync();
+    if (g == 0) {
+      bf16* dst = p.dq + (long long)b * p.dq_batch_stride + (long long)qi * p.dq_row_stride + head * D;
+      store_out_row(dst, t_row + COL_DQ, qi < p.tq);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace attn
 }  // namespace smx
 
@@ -491,6 +967,7 @@ extern "C" int smx_attn_bwd(const SmxAttn* a, void* stream) {
   memset(&p, 0, sizeof(p));
   p.lse = a->lse, p.delta = a->delta, p.bias = a->bias;
   p.dbias = a->dbias, p.inv_scale = 1.0f / a->scale;
+  p.prof = reinterpret_cast<long long*>(a->prof);
   p.dq = (bf16*)a->dq, p.dk = (bf16*)a->dk, p.dv = (bf16*)a->dv;
   p.dq_row_stride = a->dq_row_stride, p.dq_batch_stride = a->dq_batch_stride;
   p.dk_row_stride = a->dk_row_stride, p.dk_batch_stride = a->dk_batch_stride;
@@ -502,13 +979,29 @@ extern "C" int smx_attn_bwd(const SmxAttn* a, void* stream) {
   if (!attr_set) {
     SMX_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kv::SMEM_BYTES));
     SMX_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dq::SMEM_BYTES));
+    SMX_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kv2::SMEM_BYTES));
+    SMX_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dq2::SMEM_BYTES));
     attr_set = true;
   }
+  static const bool use_v1 = getenv("SMX_ATTN_BWD_V1") != nullptr;
   dim3 gkv((a->tk + 127) / 128, a->heads, a->batch);
-  attn_bwd_dkv_kernel<<<gkv, BWD_THREADS, kv::SMEM_BYTES, st>>>(mq, mk, mv, mdo, p);
-  SMX_CHECK_CUDA(cudaGetLastError());
   dim3 gq((a->tq + 127) / 128, a->heads, a->batch);
-  attn_bwd_dq_kernel<<<gq, BWD_THREADS, dq::SMEM_BYTES, st>>>(mq, mk, mv, mdo, p);
+  if (use_v1) {
+    attn_bwd_dkv_kernel<<<gkv, BWD_THREADS, kv::SMEM_BYTES, st>>>(mq, mk, mv, mdo, p);
+    SMX_CHECK_CUDA(cudaGetLastError());
+    attn_bwd_dq_kernel<<<gq, BWD_THREADS, dq::SMEM_BYTES, st>>>(mq, mk, mv, mdo, p);
+    SMX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
+  // v2: the streamed operands arrive as 64-row sub-tiles
+  CUtensorMap sq, sk, sv, sdo;
+  if (make_head_map_rows(&sq, a->q, a->tq, a->heads, a->batch, a->q_row_stride, a->q_batch_stride, SUB)) return -1;
+  if (make_head_map_rows(&sdo, a->d_o, a->tq, a->heads, a->batch, a->do_row_stride, a->do_batch_stride, SUB)) return -1;
+  if (make_head_map_rows(&sk, a->k, a->tk, a->heads, a->batch, a->k_row_stride, a->k_batch_stride, SUB)) return -1;
+  if (make_head_map_rows(&sv, a->v, a->tk, a->heads, a->batch, a->v_row_stride, a->v_batch_stride, SUB)) return -1;
+  attn_bwd_dkv2_kernel<<<gkv, BWD_THREADS, kv2::SMEM_BYTES, st>>>(sq, mk, mv, sdo, p);
+  SMX_CHECK_CUDA(cudaGetLastError());
+  attn_bwd_dq2_kernel<<<gq, BWD_THREADS, dq2::SMEM_BYTES, st>>>(mq, sk, sv, mdo, p);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

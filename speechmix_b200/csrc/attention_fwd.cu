@@ -306,6 +306,14 @@ int make_head_map(CUtensorMap* m, const void* ptr, int t, int heads, int batch, 
   return encode_tmap_bf16(m, ptr, 4, dims, str, box, true);
 }
 
+int make_head_map_rows(CUtensorMap* m, const void* ptr, int t, int heads, int batch, long long row_stride,
+                       long long batch_stride, int box_rows) {
+  const uint64_t dims[4] = {(uint64_t)D, (uint64_t)t, (uint64_t)heads, (uint64_t)batch};
+  const uint64_t str[3] = {(uint64_t)row_stride, (uint64_t)D, (uint64_t)(batch > 1 ? batch_stride : row_stride * t)};
+  const uint32_t box[4] = {64, (uint32_t)box_rows, 1, 1};
+  return encode_tmap_bf16(m, ptr, 4, dims, str, box, true);
+}
+
 }  // namespace attn
 }  // namespace smx
 

@@ -91,6 +91,37 @@ def bwd_small():
 
 
 @case
+def bias_dbias():
+    """additive [H, Tq, Tk] bias with scale 1 (T5) incl. its gradient, self (causal / not) and ragged shapes"""
+    import torch
+    from speechmix_b200 import kernels as K
+    ok = True
+    for (B, Tq, Tk, H, causal) in [(2, 93, 93, 4, False), (2, 64, 64, 4, True), (3, 200, 200, 2, False), (2, 130, 130, 2, True)]:
+        g = torch.Generator(device="cuda").manual_seed(1)
+        q, k, v, do = (torch.randn(B, t, H * 64, device="cuda", generator=g).mul(0.35).to(torch.bfloat16)
+                       for t in (Tq, Tk, Tk, Tq))
+        bias = torch.randn(H, Tq, Tk, device="cuda", generator=g)
+        name = f"bias B{B} Tq{Tq} Tk{Tk} H{H} causal{int(causal)}"
+        o, lse = K.attn_fwd(q, k, v, H, causal=causal, scale=1.0, bias=bias)
+        dbias = torch.zeros_like(bias)
+        dq, dk, dv = K.attn_bwd(do, q, k, v, o, lse, H, causal=causal, scale=1.0, bias=bias, dbias=dbias)
+        qr, kr, vr, br = (t.float().clone().requires_grad_(True) for t in (q, k, v, bias))
+        qh, kh, vh = (t.view(B, -1, H, 64).transpose(1, 2) for t in (qr, kr, vr))
+        sc = qh @ kh.transpose(-1, -2) + br[None]
+        if causal:
+            mask = torch.ones(Tq, Tk, device="cuda", dtype=torch.bool).tril(Tk - Tq)
+            sc = sc.masked_fill(~mask, float("-inf"))
+        o_ref = (torch.softmax(sc, -1) @ vh).transpose(1, 2).reshape(B, Tq, H * 64)
+        o_ref.backward(do.float())
+        ok &= _rep("fwd o " + name, o, o_ref.detach())
+        ok &= _rep("bwd dq " + name, dq, qr.grad)
+        ok &= _rep("bwd dk " + name, dk, kr.grad)
+        ok &= _rep("bwd dv " + name, dv, vr.grad)
+        ok &= _rep("bwd dbias " + name, dbias, br.grad)
+    return ok
+
+
+@case
 def full_size():
     ok = _run(4, 749, 749, 12, False, fused=True)
     ok &= _run(2, 1499, 1499, 16, False, fused=True)
@@ -119,6 +150,30 @@ def perf():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
         print(json.dumps({"perf": nm, "ms": ms, "tflops_alg": mult * B * H * T * T * 64 / ms / 1e9}), flush=True)
+    return True
+
+
+@case
+def prof():
+    """pipeline cycle counters of the dQ backward kernel (SmxAttn.prof)"""
+    import torch
+    from speechmix_b200 import kernels as K
+    B, T, H = 32, 749, 12
+    g = torch.Generator(device="cuda").manual_seed(0)
+    qkv = torch.randn(B, T, 3 * H * 64, device="cuda", generator=g).to(torch.bfloat16)
+    q, k, v = qkv[..., :H * 64], qkv[..., H * 64:2 * H * 64], qkv[..., 2 * H * 64:]
+    do = torch.randn(B, T, H * 64, device="cuda", generator=g).to(torch.bfloat16)
+    o, lse = K.attn_fwd(q, k, v, H)
+    K.attn_bwd(do, q, k, v, o, lse, H)
+    prof = torch.zeros(8, device="cuda", dtype=torch.int64)
+    K.attn_bwd(do, q, k, v, o, lse, H, prof=prof)
+    torch.cuda.synchronize()
+    c = prof.tolist()
+    ctas = 6 * H * B
+    names = ["mma wait KFULL", "mma issue S+dP (8 MMA)", "mma wait DSFULL", "mma total", "cmp wait SFULL", "mma issue dQ (4 MMA)", "cmp compute"]
+    for n, v_ in zip(names, c):
+        per = v_ / ctas / (1 if n.startswith("mma") else 2)   # two compute groups report
+        print(json.dumps({"prof": n, "cycles_per_cta": per}), flush=True)
     return True
 
 
