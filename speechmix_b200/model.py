@@ -203,12 +203,7 @@ class SpeechMixEED(nn.Module):
                                                    self.decoder_model.config.decoder_start_token_id)
         inputs_embeds = self.bridge(encoder_outputs, detail)
         if decoder_text_prompt is not None:
-            if isinstance(decoder_text_prompt, str):
-                ids = self.tokenizer(decoder_text_prompt, return_tensors="pt")["input_ids"].to(self.device)
-            else:
-                ids = decoder_text_prompt.to(self.device)
-            prompt = ops.EmbedFn.apply(ids, None, self.nlp_emb.weight, None, self.decoder_model.get_encoder().embed_scale, 0, 0)
-            inputs_embeds = torch.cat((prompt.expand(inputs_embeds.shape[0], -1, -1), inputs_embeds), 1)
+            inputs_embeds = self._prepend_prompt(inputs_embeds, decoder_text_prompt)
         outputs = self.cal_loss(inputs_embeds=inputs_embeds, decoder_outputs=decoder_outputs,
                                 text_input_ids=text_input_ids, decoder_input_ids=decoder_input_ids, labels=labels,
                                 past_key_values=past_key_values, use_cache=use_cache)
@@ -220,13 +215,22 @@ class SpeechMixEED(nn.Module):
         return outputs
 
     @torch.no_grad()
-    def generate(self, input_values, max_length=32, decoder_text_prompt=None, eos_token_id=None, **kwargs):
-        """Greedy decode (ref:eval.py:12-13; loop semantics of ref:eval.ipynb cell 6): the speech
-        encoder, bridge and text encoder run once, the decoder is re-run on the growing prefix."""
+    def generate(self, input_values, max_length=32, decoder_text_prompt=None, eos_token_id=None, use_cache=True,
+                 **kwargs):
+        """Greedy decode (ref:eval.py:12-13; loop semantics of ref:eval.ipynb cell 6).  The speech encoder, bridge
+        and text encoder run once.  ``use_cache=True`` (default): KV-cached decoder, one pass per new token
+        (the role of ref:speechmix/hf_model.py:314-338 ``prepare_inputs_for_generation`` + ``past_key_values``);
+        ``use_cache=False``: the notebook's full-prefix recompute.  Both return the same ids."""
         cfg = self.decoder_model.config
         eos = cfg.eos_token_id if eos_token_id is None else eos_token_id
         enc = self.encoder_model(input_values, output_hidden_states=True)
         B = input_values.shape[0]
+        if use_cache:
+            inputs_embeds = self.bridge(enc)
+            if decoder_text_prompt is not None:
+                inputs_embeds = self._prepend_prompt(inputs_embeds, decoder_text_prompt)
+            text_enc, _ = self.decoder_model.encode(inputs_embeds=inputs_embeds)
+            return self.decoder_model.greedy_decode(text_enc, max_length, eos_token_id=eos)
         dec = torch.full((B, 1), cfg.decoder_start_token_id, dtype=torch.long, device=self.device)
         done = torch.zeros(B, dtype=torch.bool, device=self.device)
         text_enc = None
@@ -240,6 +244,15 @@ class SpeechMixEED(nn.Module):
             if bool(done.all()):
                 break
         return dec
+
+    def _prepend_prompt(self, inputs_embeds, decoder_text_prompt):
+        """ref:speechmix/hf_model.py:433-436"""
+        if isinstance(decoder_text_prompt, str):
+            ids = self.tokenizer(decoder_text_prompt, return_tensors="pt")["input_ids"].to(self.device)
+        else:
+            ids = decoder_text_prompt.to(self.device)
+        prompt = ops.EmbedFn.apply(ids, None, self.nlp_emb.weight, None, self.decoder_model.get_encoder().embed_scale, 0, 0)
+        return torch.cat((prompt.expand(inputs_embeds.shape[0], -1, -1), inputs_embeds), 1)
 
 
 class SpeechMixFixed(SpeechMixEED):

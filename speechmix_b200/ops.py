@@ -763,3 +763,68 @@ class SelfMSEFn(torch.autograd.Function):
         t, s, attn, diff = ctx.saved_tensors
         gscale = (g.float() * (2.0 / diff.numel())).reshape(1).contiguous()
         return None, K.self_mse_bwd(t, s, attn, diff, gscale)
+
+
+# ---------------------------------------------------------------------------
+# Incremental decoding (no autograd): one new token per call, self-attention keys / values appended to a
+# preallocated cache, cross-attention keys / values projected once per utterance.
+# hf:models/bart/modeling_bart.py:143-258 (past_key_values branch), ref:speechmix/hf_model.py:314-338.
+# ---------------------------------------------------------------------------
+def _ln_maybe(x2, w, b, eps, rms):
+    return K.layernorm_fwd(x2, w.detach(), None if b is None else b.detach(), eps, rms_only=rms)[0]
+
+
+@torch.no_grad()
+def decode_self_attn_step(x2, cfg, q_w, q_b, k_w, k_b, v_w, v_b, o_w, o_b, ln_w, ln_b, cache, t, pos_bias=None):
+    """x2 [B, H] bf16 (the new token), cache [B, Tmax, 2*Hi] bf16 (k | v).  Returns the sub-block output [B, H]."""
+    heads, pre_ln, eps, rms = cfg["heads"], cfg["pre_ln"], cfg["eps"], bool(cfg.get("rms", False))
+    scale = cfg.get("scale", 1.0 / math.sqrt(64))
+    B, H = x2.shape
+    Hi = q_w.shape[0]
+    a_in = _ln_maybe(x2, ln_w, ln_b, eps, rms) if pre_ln else x2
+    q = K.linear_fwd(a_in, w16(q_w), None if q_b is None else q_b.detach())
+    K.linear_fwd(a_in, cat16((k_w, v_w)), cat32((k_b, v_b)) if k_b is not None else None, out=cache[:, t, :])
+    kv = cache[:, :t + 1]
+    o, _ = K.attn_fwd(q.view(B, 1, Hi), kv[..., :Hi], kv[..., Hi:], heads, causal=False, scale=scale, bias=pos_bias)
+    s = K.linear_fwd(o.view(B, Hi), w16(o_w), None if o_b is None else o_b.detach(), residual=x2)
+    return s if pre_ln else _ln_maybe(s, ln_w, ln_b, eps, rms)
+
+
+@torch.no_grad()
+def cross_kv(src, k_w, k_b, v_w, v_b):
+    """keys | values of the encoder states for one decoder layer: [B, Ts, 2*Hi] bf16 (computed once)."""
+    Bs, Ts, Hs = src.shape
+    kv = K.linear_fwd(src.reshape(Bs * Ts, Hs).contiguous(), cat16((k_w, v_w)),
+                      cat32((k_b, v_b)) if k_b is not None else None)
+    return kv.view(Bs, Ts, -1)
+
+
+@torch.no_grad()
+def decode_cross_attn_step(x2, cfg, q_w, q_b, o_w, o_b, ln_w, ln_b, kv):
+    heads, pre_ln, eps, rms = cfg["heads"], cfg["pre_ln"], cfg["eps"], bool(cfg.get("rms", False))
+    scale = cfg.get("scale", 1.0 / math.sqrt(64))
+    B, H = x2.shape
+    Hi = q_w.shape[0]
+    a_in = _ln_maybe(x2, ln_w, ln_b, eps, rms) if pre_ln else x2
+    q = K.linear_fwd(a_in, w16(q_w), None if q_b is None else q_b.detach())
+    o, _ = K.attn_fwd(q.view(B, 1, Hi), kv[..., :Hi], kv[..., Hi:], heads, causal=False, scale=scale)
+    s = K.linear_fwd(o.view(B, Hi), w16(o_w), None if o_b is None else o_b.detach(), residual=x2)
+    return s if pre_ln else _ln_maybe(s, ln_w, ln_b, eps, rms)
+
+
+@torch.no_grad()
+def decode_ffn_step(x2, cfg, w1, b1, w2, b2, ln_w, ln_b):
+    pre_ln, eps, rms = cfg["pre_ln"], cfg["eps"], bool(cfg.get("rms", False))
+    act, _ = _act_codes(cfg.get("act", "gelu"))
+    a_in = _ln_maybe(x2, ln_w, ln_b, eps, rms) if pre_ln else x2
+    h = K.linear_fwd(a_in, w16(w1), None if b1 is None else b1.detach(), act=act)
+    s = K.linear_fwd(h, w16(w2), None if b2 is None else b2.detach(), residual=x2)
+    return s if pre_ln else _ln_maybe(s, ln_w, ln_b, eps, rms)
+
+
+@torch.no_grad()
+def lm_head_argmax(h2, emb, bias, logit_scale):
+    """argmax_v (h E^T * s + b) per row, lowest index wins ties (torch.argmax); no logits in HBM."""
+    b = None if bias is None else bias.detach().reshape(-1).float().contiguous()
+    lab = torch.full((h2.shape[0],), -100, device=h2.device, dtype=torch.long)
+    return K.lmhead_ce_fwd(h2.contiguous(), w16(emb), b, lab, logit_scale)[1]

@@ -154,6 +154,42 @@ class Seq2SeqLM(nn.Module):
         x, _ = self.model.decoder(input_ids=decoder_input_ids, encoder_hidden_states=encoder_hidden_states)
         return x
 
+    @torch.no_grad()
+    def greedy_decode(self, enc, max_length, eos_token_id=None, start_ids=None):
+        """KV-cached greedy decode over encoder states ``enc`` [B, Ts, D]: one decoder pass per new token
+        (hf:...bart.py:143-258 cache branch; loop semantics of ref:eval.ipynb cell 6).  Returns ids [B, <=max_length]."""
+        cfg, dec = self.config, self.model.decoder
+        B, dev = enc.shape[0], enc.device
+        eos = cfg.eos_token_id if eos_token_id is None else eos_token_id
+        ids = torch.full((B, 1), cfg.decoder_start_token_id, dtype=torch.long, device=dev) if start_ids is None else start_ids
+        D = cfg.d_model
+        caches = [torch.empty(B, max_length, 2 * D, device=dev, dtype=K.BF16) for _ in dec.layers]
+        cross = [ops.cross_kv(enc, l.encoder_attn.k_proj.weight, l.encoder_attn.k_proj.bias, l.encoder_attn.v_proj.weight,
+                              l.encoder_attn.v_proj.bias) for l in dec.layers]
+        w, b, scale = self.lm_head_params()
+        done = torch.zeros(B, dtype=torch.bool, device=dev)
+        for t in range(max_length - 1):
+            x = dec.embed(ids[:, t:t + 1].contiguous(), None, t_start=t).view(B, D)
+            for li, l in enumerate(dec.layers):
+                x = ops.decode_self_attn_step(x, l.cfg_self, *l.self_attn.params(), l.self_attn_layer_norm.weight,
+                                              l.self_attn_layer_norm.bias, caches[li], t)
+                ea = l.encoder_attn
+                x = ops.decode_cross_attn_step(x, l.cfg_cross, ea.q_proj.weight, ea.q_proj.bias, ea.out_proj.weight,
+                                               ea.out_proj.bias, l.encoder_attn_layer_norm.weight,
+                                               l.encoder_attn_layer_norm.bias, cross[li])
+                x = ops.decode_ffn_step(x, l.cfg_cross, l.fc1.weight, l.fc1.bias, l.fc2.weight, l.fc2.bias,
+                                        l.final_layer_norm.weight, l.final_layer_norm.bias)
+                if dec.layer_output_hook is not None:
+                    x = dec.layer_output_hook(li, x.view(B, 1, D)).reshape(B, D)
+            if dec.pre_ln:
+                x = ops._ln_maybe(x, dec.layer_norm.weight, dec.layer_norm.bias, 1e-5, False)
+            nxt = ops.lm_head_argmax(x, w, b, scale)
+            ids = torch.cat([ids, nxt[:, None]], dim=1)
+            done |= nxt == eos
+            if bool(done.all()):
+                break
+        return ids
+
     def full_logits(self, hidden):
         """fp32 [.., V] logits, materialised -- parity tests / debugging only, never on the training path."""
         h2 = hidden.reshape(-1, hidden.shape[-1]).contiguous()
@@ -283,6 +319,8 @@ class _T5Stack(nn.Module):
         self.embed_scale = 1.0
         n = config.num_decoder_layers if is_decoder else config.num_layers
         self.block = nn.ModuleList([_T5Block(config, is_decoder, i == 0) for i in range(n)])
+        for i, blk in enumerate(self.block):
+            blk._index = i
         self.final_layer_norm = _RMSNorm(config.d_model)
         self.layer_output_hook = None
 
@@ -352,6 +390,43 @@ class T5Seq2SeqLM(nn.Module):
         w, _, scale = self.lm_head_params()
         h2 = hidden.reshape(-1, hidden.shape[-1]).contiguous()
         return K.linear_fwd(h2, ops.w16(w), None, out_f32=True, alpha=scale).view(*hidden.shape[:-1], -1)
+
+    @torch.no_grad()
+    def greedy_decode(self, enc, max_length, eos_token_id=None, start_ids=None):
+        """KV-cached greedy decode (hf:...t5.py:248-345 cache branch): the relative position bias of step t is
+        row t of the causal bucket table (query offset t, keys 0..t)."""
+        cfg, dec = self.config, self.decoder
+        B, dev = enc.shape[0], enc.device
+        eos = cfg.eos_token_id if eos_token_id is None else eos_token_id
+        ids = torch.full((B, 1), cfg.decoder_start_token_id, dtype=torch.long, device=dev) if start_ids is None else start_ids
+        D, Hi = cfg.d_model, cfg.num_heads * cfg.d_kv
+        caches = [torch.empty(B, max_length, 2 * Hi, device=dev, dtype=K.BF16) for _ in dec.block]
+        cross = [ops.cross_kv(enc, blk.layer[1].EncDecAttention.k.weight, None, blk.layer[1].EncDecAttention.v.weight, None)
+                 for blk in dec.block]
+        rel = dec.block[0].layer[0].SelfAttention.relative_attention_bias.weight.detach().float().contiguous()
+        w, b, scale = self.lm_head_params()
+        done = torch.zeros(B, dtype=torch.bool, device=dev)
+        for t in range(max_length - 1):
+            x = ops.EmbedFn.apply(ids[:, t:t + 1].contiguous(), None, dec.embed_tokens.weight, None, 1.0, 0, 0).view(B, D)
+            table = ops.t5_bucket_table(1, t + 1, False, cfg.relative_attention_num_buckets,
+                                        cfg.relative_attention_max_distance, dev, q_offset=t)
+            pos_bias = K.relpos_bias_fwd(rel, table, cfg.num_heads, 1, t + 1, q_offset=t)
+            for blk in dec.block:
+                sa, ca, ff = blk.layer[0], blk.layer[1], blk.layer[2]
+                x = ops.decode_self_attn_step(x, blk.cfg_self, *sa.SelfAttention.params(), sa.layer_norm.weight, None,
+                                              caches[blk._index], t, pos_bias)
+                a = ca.EncDecAttention
+                x = ops.decode_cross_attn_step(x, blk.cfg_cross, a.q.weight, None, a.o.weight, None, ca.layer_norm.weight,
+                                               None, cross[blk._index])
+                x = ops.decode_ffn_step(x, blk.cfg_cross, ff.DenseReluDense.wi.weight, None, ff.DenseReluDense.wo.weight,
+                                        None, ff.layer_norm.weight, None)
+            x = ops._ln_maybe(x, dec.final_layer_norm.weight, None, cfg.layer_norm_epsilon, True)
+            nxt = ops.lm_head_argmax(x, w, b, scale)
+            ids = torch.cat([ids, nxt[:, None]], dim=1)
+            done |= nxt == eos
+            if bool(done.all()):
+                break
+        return ids
 
     forward = None  # assigned below (shared with the BART-family class)
 

@@ -209,3 +209,17 @@ def test_self_matches_oracle(text, cuda_device):
         assert err <= 6e-2 * float(p.grad.norm()) + 3e-4 * scale, (k, err, float(p.grad.norm()))
         checked += 1
     assert checked == len(mine.list_grad)
+
+
+@pytest.mark.parametrize("text", ["bart-mini", "mbart-mini", "t5-mini"])
+def test_generate_kv_cache_equals_full_recompute(text, cuda_device):
+    """KV-cached greedy decode (one decoder pass per token) must return exactly the ids of the notebook-style
+    full-prefix recompute loop (ref:eval.ipynb cell 6) -- same kernels, same reduction order per row."""
+    fx = dict(load_fixture("mini_eed_ds2"), text=text, kwargs={"down_scale": 2}, train_mode=False)
+    ora, x, _ = build_oracle(fx)
+    mine = _mine_from(ora, fx, cuda_device).eval()
+    xs = x.to(cuda_device)
+    a = mine.generate(xs, max_length=12, eos_token_id=-1, use_cache=True).cpu()
+    b = mine.generate(xs, max_length=12, eos_token_id=-1, use_cache=False).cpu()
+    assert a.shape == b.shape == (fx["batch"], 12)
+    assert torch.equal(a, b), (a.tolist(), b.tolist())
