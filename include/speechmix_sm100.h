@@ -298,6 +298,36 @@ int smx_relpos_bias_fwd(const float* weight, const int32_t* table, float* bias, 
 int smx_relpos_bias_bwd(const float* dbias, const int32_t* table, float* dweight, int64_t heads, int64_t tq, int64_t tk,
                         int64_t q_offset, int64_t n_buckets, void* stream);
 
+/* ------------------------------------------------------------------------
+ * fp32 verification path (inference only; csrc/fp32.cu): the forward graph of ref:speechmix/hf_model.py:378-447
+ * with fp32 activations and fp32 CUDA-core arithmetic, used to compare greedy-decoded ids bit for bit with the
+ * reference's fp32 run.  c[m,n] = act(alpha * sum_k a[m,k] w[n,k] + bias[n]) + residual[m,n]; `lda` may be
+ * smaller than k (overlapping rows): a k-tap stride-s convolution over channels-last frames is this GEMM with
+ * lda = s*C, k = taps*C and w = weight[out][tap][in].  act: SMX_ACT_NONE / GELU (exact erf) / RELU.
+ * ------------------------------------------------------------------------ */
+int smx_f32_gemm_nt(const float* a, int64_t lda, int64_t a_batch_stride, const float* w, const float* bias,
+                    const float* residual, int64_t ldr, int64_t r_batch_stride, float* c, int64_t ldc,
+                    int64_t c_batch_stride, int64_t m, int64_t n, int64_t k, int64_t batches, int act, float alpha,
+                    void* stream);
+int smx_f32_layernorm(const float* x, const float* gamma, const float* beta, float* y, int64_t rows, int64_t cols,
+                      float eps, int rms_only, int act, void* stream);
+/* in place: x[b,t,c] = gelu(GroupNorm_{groups == channels}(x)); stats_ws: batch*channels*2 doubles */
+int smx_f32_groupnorm_gelu(float* x, double* stats_ws, const float* gamma, const float* beta, int64_t batch, int64_t t,
+                           int64_t channels, float eps, void* stream);
+/* y = x*add_input + gelu(grouped_conv(x) + bias), weight [hidden][hidden/groups][ksize], padding ksize/2 */
+int smx_f32_posconv(const float* x, const float* w, const float* bias, float* y, int64_t batch, int64_t t,
+                    int64_t hidden, int64_t groups, int64_t ksize, int add_input, void* stream);
+int smx_f32_attn(const float* q, const float* k, const float* v, float* o, int64_t q_rs, int64_t q_bs, int64_t k_rs,
+                 int64_t k_bs, int64_t v_rs, int64_t v_bs, int64_t o_rs, int64_t o_bs, int64_t batch, int64_t heads,
+                 int64_t tq, int64_t tk, int causal, float scale, const float* bias, void* stream);
+int smx_f32_embed(const int64_t* ids, const float* tok, const float* pos, const float* x_in, float* out, int64_t batch,
+                  int64_t t, int64_t dim, float scale, int64_t pos_offset, void* stream);
+/* running argmax over ascending vocabulary chunks (lowest index wins ties, like torch.argmax) */
+int smx_f32_argmax_chunk(const float* logits, int64_t ld, int64_t rows, int64_t vn, int64_t v0, float* best, int64_t* idx,
+                         void* stream);
+/* y = (first ? 0 : y) + w[wi] * x */
+int smx_f32_axpy(const float* x, const float* w, int32_t wi, float* y, int64_t n, int first, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

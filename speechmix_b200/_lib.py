@@ -92,6 +92,14 @@ SIGNATURES = {
     "smx_kl_chunk_bwd": (c_int, [_P, _P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _I64, _P]),
     "smx_self_mse_fwd": (c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _P]),
     "smx_self_mse_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _P]),
+    "smx_f32_gemm_nt": (c_int, [_P, _I64, _I64, _P, _P, _P, _I64, _I64, _P, _I64, _I64, _I64, _I64, _I64, _I64, c_int, c_float, _P]),
+    "smx_f32_layernorm": (c_int, [_P, _P, _P, _P, _I64, _I64, c_float, c_int, c_int, _P]),
+    "smx_f32_groupnorm_gelu": (c_int, [_P, _P, _P, _P, _I64, _I64, _I64, c_float, _P]),
+    "smx_f32_posconv": (c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, c_int, _P]),
+    "smx_f32_attn": (c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _I64, c_int, c_float, _P, _P]),
+    "smx_f32_embed": (c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I64, c_float, _I64, _P]),
+    "smx_f32_argmax_chunk": (c_int, [_P, _I64, _I64, _I64, _I64, _P, _P, _P]),
+    "smx_f32_axpy": (c_int, [_P, _P, c_int32, _P, _I64, c_int, _P]),
     "smx_relpos_bias_fwd": (c_int, [_P, _P, _P, _I64, _I64, _I64, _I64, _P]),
     "smx_relpos_bias_bwd": (c_int, [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _P]),
 }

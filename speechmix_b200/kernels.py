@@ -15,6 +15,13 @@ from ._lib import (ACT_DGELU, ACT_DRELU, ACT_GELU, ACT_NONE, ACT_RELU, GEMM_NN, 
 
 BF16 = torch.bfloat16
 
+# fp32 verification mode (ops.fp32_verification()): activations fp32, every call below is routed to fp32path.py
+FP32_MODE = False
+
+
+def act_dtype():
+    return torch.float32 if FP32_MODE else BF16
+
 # bookkeeping for bench.py: number of kernels of this library launched so far, and an optional
 # list collecting (tag, flops, start_event, end_event) around tagged GEMM launches.
 LAUNCHES = _lib.LAUNCHES
@@ -35,10 +42,11 @@ def _view(t, inner, rows, batches, row_stride, batch_stride, offset=0):
     return SmxView3(_ptr(t, offset), inner, rows, batches, row_stride, batch_stride)
 
 
-def alloc_act(batch, t, c, device, dtype=BF16, slack=None):
+def alloc_act(batch, t, c, device, dtype=None, slack=None):
     """[batch, t, c] activation with ``slack`` (default c) zeroed elements after
     the end, so frame-pair TMA views of an odd-length signal stay in bounds."""
     slack = c if slack is None else slack
+    dtype = act_dtype() if dtype is None else dtype
     n = batch * t * c
     flat = torch.empty(n + slack, device=device, dtype=dtype)
     flat[n:].zero_()
@@ -118,6 +126,9 @@ def _epilogue(g, c, c_row_stride, c_batch_stride, bias, act, residual, res_strid
 # linear layers  (x: [M, K] bf16 row-major, w: [N, K] bf16 = torch Linear layout)
 # ---------------------------------------------------------------------------
 def linear_fwd(x, w, bias=None, act=ACT_NONE, residual=None, want_pre=False, out_f32=False, alpha=1.0, out=None):
+    if FP32_MODE:
+        from . import fp32path
+        return fp32path.linear_fwd(x, w, bias, act, residual, want_pre, out_f32, alpha, out)
     assert x.dtype == BF16 and w.dtype == BF16 and x.is_contiguous() and w.is_contiguous()
     M, K = x.shape
     N = w.shape[0]
@@ -203,6 +214,9 @@ def _pair_view(x):
 
 
 def conv_s2_fwd(x, w_packed, k, bias=None, act=ACT_NONE, want_pre=False):
+    if FP32_MODE:
+        from . import fp32path
+        return fp32path.conv_s2_fwd(x, w_packed, k, bias, act, want_pre)
     B, T_in, C = x.shape
     N = w_packed.shape[0]
     assert w_packed.shape[1] == k * C and C % 64 == 0 and x.is_contiguous()
@@ -267,6 +281,9 @@ def conv_s2_wgrad(dy, x, k):
 
 def pack_conv_weight(w):
     """[out, in, k] fp32 -> [out, k*in] bf16 (tap-major)."""
+    if FP32_MODE:
+        from . import fp32path
+        return fp32path.pack_conv_weight(w)
     out_c, in_c, k = w.shape
     return w.detach().permute(0, 2, 1).reshape(out_c, k * in_c).to(BF16).contiguous()
 
@@ -295,6 +312,9 @@ def _attn_desc(q, k, v, o, lse, heads, causal, scale, bias):
 
 
 def attn_fwd(q, k, v, heads, causal=False, scale=None, bias=None):
+    if FP32_MODE:
+        from . import fp32path
+        return fp32path.attn_fwd(q, k, v, heads, causal, (1.0 / math.sqrt(64)) if scale is None else scale, bias)
     B, Tq, HD = q.shape
     scale = (1.0 / math.sqrt(64)) if scale is None else scale
     o = torch.empty(B, Tq, HD, device=q.device, dtype=BF16)
@@ -334,6 +354,9 @@ def _L():
 
 
 def layernorm_fwd(x, gamma, beta, eps=1e-5, res=None, want_sum=False, rms_only=False, act=ACT_NONE, out=None):
+    if FP32_MODE:
+        from . import fp32path
+        return fp32path.layernorm_fwd(x, gamma, beta, eps, res, want_sum, rms_only, act, out)
     """x: [..., C] bf16 contiguous.  Returns y, (sum or x), mean, rstd."""
     C = x.shape[-1]
     rows = x.numel() // C
@@ -412,6 +435,9 @@ def dact(dy, pre, act=ACT_GELU):
 # ---------------------------------------------------------------------------
 def conv0_fwd(audio, w, gamma, beta, eps=1e-5):
     """audio [B, n] fp32, w [C, 1, 10] fp32.  Returns y [B, T, C] bf16 (slack-padded), stats, moments."""
+    if FP32_MODE:
+        from . import fp32path
+        return fp32path.conv0_fwd(audio, w, gamma, beta, eps=eps)
     B, n = audio.shape
     C, _, k = w.shape
     s = 5
@@ -442,6 +468,9 @@ def conv0_bwd(audio, w, gamma, beta, stats, moments, dy):
 
 
 def conv0_ln_fwd(audio, w, conv_bias, gamma, beta, eps=1e-5):
+    if FP32_MODE:
+        from . import fp32path
+        return fp32path.conv0_ln_fwd(audio, w, conv_bias, gamma, beta, eps)
     B, n = audio.shape
     C, _, k = w.shape
     T = (n - k) // 5 + 1
@@ -489,6 +518,9 @@ def posconv_pack(weight, groups):
 
 
 def posconv_fwd(x, w_fwd, bias, groups, ksize, add_input=True):
+    if FP32_MODE:
+        from . import fp32path
+        return fp32path.posconv_fwd(x, w_fwd, bias, groups, ksize, add_input)
     B, T, H = x.shape
     y = torch.empty_like(x)
     pre = torch.empty_like(x)
@@ -519,6 +551,9 @@ def posconv_wgrad(dpre, x, groups, ksize):
 # embeddings
 # ---------------------------------------------------------------------------
 def embed_fwd(ids, tok_emb, pos_emb, x_in, batch, t, dim, scale=1.0, pos_offset=0, t_start=0, device=None):
+    if FP32_MODE:
+        from . import fp32path
+        return fp32path.embed_fwd(ids, tok_emb, pos_emb, x_in, batch, t, dim, scale, pos_offset, t_start, device)
     out = torch.empty(batch, t, dim, device=device, dtype=BF16)
     _lib.check(_L().smx_embed_fwd(_ptr(ids), _ptr(tok_emb), _ptr(pos_emb), _ptr(x_in), _ptr(out), batch, t, dim, scale,
                                   pos_offset, t_start, _stream()), "embed_fwd")
@@ -535,6 +570,9 @@ def embed_bwd(ids, dout, d_tok, d_pos, scale=1.0, pos_offset=0):
 # LM head + cross entropy
 # ---------------------------------------------------------------------------
 def lmhead_ce_fwd(h, emb16, bias, labels, logit_scale=1.0, ignore_index=-100):
+    if FP32_MODE:
+        from . import fp32path
+        return fp32path.lmhead_ce_fwd(h, emb16, bias, labels, logit_scale, ignore_index)
     """h [M, D] bf16, emb16 [V, D] bf16, labels [M] int64 -> lse, argmax, row_loss, loss_sum, count"""
     M, D = h.shape
     V = emb16.shape[0]
@@ -594,6 +632,9 @@ def gemm_tn_into(a, a_cols, x, out_rows_view, alpha=1.0):
 # weighted layer sum
 # ---------------------------------------------------------------------------
 def weighted_sum_fwd(xs, w):
+    if FP32_MODE:
+        from . import fp32path
+        return fp32path.weighted_sum_fwd(xs, w)
     n = xs[0].numel()
     out = torch.empty_like(xs[0])
     arr = (ctypes.c_void_p * len(xs))(*[x.data_ptr() for x in xs])

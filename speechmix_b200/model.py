@@ -185,7 +185,11 @@ class SpeechMixEED(nn.Module):
     def forward(self, input_values=None, decoder_text_prompt=None, text_input_ids=None, decoder_input_ids=None,
                 labels=None, encoder_outputs=None, decoder_outputs=None, past_key_values=None, use_cache=None,
                 return_model_detail=True, output_attentions=None, output_hidden_states=None, return_dict=None,
-                **kwargs):
+                precision=None, **kwargs):
+        if precision == "fp32":   # verification run: fp32 activations + fp32 arithmetic, inference only
+            with torch.no_grad(), ops.fp32_verification():
+                return self.forward(input_values, decoder_text_prompt, text_input_ids, decoder_input_ids, labels,
+                                    encoder_outputs, decoder_outputs, past_key_values, use_cache, return_model_detail)
         """ref:speechmix/hf_model.py:378-447.  Returns a mapping with ``loss`` and ``logits`` (= argmax
         token ids, as the reference returns them at :446) plus the model-detail breadcrumbs."""
         detail = {} if return_model_detail else None
@@ -216,11 +220,14 @@ class SpeechMixEED(nn.Module):
 
     @torch.no_grad()
     def generate(self, input_values, max_length=32, decoder_text_prompt=None, eos_token_id=None, use_cache=True,
-                 **kwargs):
+                 precision=None, **kwargs):
         """Greedy decode (ref:eval.py:12-13; loop semantics of ref:eval.ipynb cell 6).  The speech encoder, bridge
         and text encoder run once.  ``use_cache=True`` (default): KV-cached decoder, one pass per new token
         (the role of ref:speechmix/hf_model.py:314-338 ``prepare_inputs_for_generation`` + ``past_key_values``);
         ``use_cache=False``: the notebook's full-prefix recompute.  Both return the same ids."""
+        if precision == "fp32":
+            with ops.fp32_verification():
+                return self.generate(input_values, max_length, decoder_text_prompt, eos_token_id, use_cache)
         cfg = self.decoder_model.config
         eos = cfg.eos_token_id if eos_token_id is None else eos_token_id
         enc = self.encoder_model(input_values, output_hidden_states=True)

@@ -104,11 +104,31 @@ def _rows_spec(val, srcs, f32):
     return out
 
 
+class fp32_verification:
+    """Context manager: run the forward graph with fp32 activations and fp32 CUDA-core arithmetic (csrc/fp32.cu)
+    -- inference only; used to check greedy-decoded ids bit for bit against the reference's fp32 run."""
+
+    def __enter__(self):
+        if torch.is_grad_enabled():
+            raise RuntimeError("fp32 verification mode is inference-only: wrap the call in torch.no_grad()")
+        self._prev = K.FP32_MODE
+        K.FP32_MODE = True
+        return self
+
+    def __exit__(self, *exc):
+        K.FP32_MODE = self._prev
+        return False
+
+
 def w16(p):
+    if K.FP32_MODE:
+        return p.detach()
     return CACHE.get(p, "bf16", lambda t: K.to_bf16(t), simple=lambda v, ts: [(v, ts[0].numel(), 0)])
 
 
 def cat16(ps):
+    if K.FP32_MODE:
+        return cat32(ps)
     return CACHE.get(tuple(ps), "cat16", lambda *ts: K.to_bf16(torch.cat([t.detach() for t in ts], 0)),
                      simple=lambda v, ts: _rows_spec(v, ts, 0))
 
@@ -119,7 +139,7 @@ def cat32(ps):
 
 
 def conv_packed16(p):
-    return CACHE.get(p, "convpack", lambda t: K.pack_conv_weight(t))
+    return CACHE.get(p, "convpack32" if K.FP32_MODE else "convpack", lambda t: K.pack_conv_weight(t))
 
 
 def _act_codes(name):
@@ -513,6 +533,8 @@ class PosConvFn(torch.autograd.Function):
         ksize = weight.shape[2]
         # `weight` is usually recomputed every step from its weight-norm factors; the packed bf16
         # copies are cached on the leaf parameters it derives from.
+        if K.FP32_MODE:
+            return K.posconv_fwd(x, weight.detach(), bias.detach(), groups, ksize, add_input=True)[0]
         wf, wd = CACHE.get(tuple(key_params), "posconv%d" % groups, lambda *_: K.posconv_pack(weight, groups))
         y, pre = K.posconv_fwd(x, wf, bias.detach(), groups, ksize, add_input=True)
         ctx.save_for_backward(x, pre, wd)

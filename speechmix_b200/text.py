@@ -163,7 +163,7 @@ class Seq2SeqLM(nn.Module):
         eos = cfg.eos_token_id if eos_token_id is None else eos_token_id
         ids = torch.full((B, 1), cfg.decoder_start_token_id, dtype=torch.long, device=dev) if start_ids is None else start_ids
         D = cfg.d_model
-        caches = [torch.empty(B, max_length, 2 * D, device=dev, dtype=K.BF16) for _ in dec.layers]
+        caches = [torch.empty(B, max_length, 2 * D, device=dev, dtype=K.act_dtype()) for _ in dec.layers]
         cross = [ops.cross_kv(enc, l.encoder_attn.k_proj.weight, l.encoder_attn.k_proj.bias, l.encoder_attn.v_proj.weight,
                               l.encoder_attn.v_proj.bias) for l in dec.layers]
         w, b, scale = self.lm_head_params()
@@ -329,7 +329,7 @@ class _T5Stack(nn.Module):
         if input_ids is not None:
             x = ops.EmbedFn.apply(input_ids, None, self.embed_tokens.weight, None, 1.0, 0, 0)
         else:
-            x = inputs_embeds if inputs_embeds.dtype == K.BF16 else ops.EmbedFn.apply(None, inputs_embeds, None, None, 1.0, 0, 0)
+            x = inputs_embeds if inputs_embeds.dtype == K.act_dtype() else ops.EmbedFn.apply(None, inputs_embeds, None, None, 1.0, 0, 0)
         T = x.shape[1]
         table = ops.t5_bucket_table(T, T, not self.is_decoder, cfg.relative_attention_num_buckets,
                                     cfg.relative_attention_max_distance, x.device)
@@ -400,7 +400,7 @@ class T5Seq2SeqLM(nn.Module):
         eos = cfg.eos_token_id if eos_token_id is None else eos_token_id
         ids = torch.full((B, 1), cfg.decoder_start_token_id, dtype=torch.long, device=dev) if start_ids is None else start_ids
         D, Hi = cfg.d_model, cfg.num_heads * cfg.d_kv
-        caches = [torch.empty(B, max_length, 2 * Hi, device=dev, dtype=K.BF16) for _ in dec.block]
+        caches = [torch.empty(B, max_length, 2 * Hi, device=dev, dtype=K.act_dtype()) for _ in dec.block]
         cross = [ops.cross_kv(enc, blk.layer[1].EncDecAttention.k.weight, None, blk.layer[1].EncDecAttention.v.weight, None)
                  for blk in dec.block]
         rel = dec.block[0].layer[0].SelfAttention.relative_attention_bias.weight.detach().float().contiguous()

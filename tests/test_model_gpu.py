@@ -223,3 +223,44 @@ def test_generate_kv_cache_equals_full_recompute(text, cuda_device):
     b = mine.generate(xs, max_length=12, eos_token_id=-1, use_cache=False).cpu()
     assert a.shape == b.shape == (fx["batch"], 12)
     assert torch.equal(a, b), (a.tolist(), b.tolist())
+
+
+@pytest.mark.parametrize("name", ["mini_eed_ds2", "mini_eed_ds8_ws", "mini_large_mbart", "mini_t5"])
+def test_fp32_verification_forward_and_greedy_ids_bit_exact(name, cuda_device):
+    """BASELINE.json north_star: "Greedy-decoded token ids must be bit-exact on fp32 verification runs".
+    precision="fp32" runs the same graph with fp32 activations / fp32 CUDA-core arithmetic; argmax ids of the
+    teacher-forced pass and the ids of a greedy decode (KV-cached and full-recompute) must equal the fp32 CPU
+    reference exactly, and the loss must agree to 1e-4."""
+    from oracle import hf_oracle as O
+    fx = dict(load_fixture(name), train_mode=False)
+    ora, x, labels = build_oracle(fx)
+    mine = _mine_from(ora, fx, cuda_device).eval()
+    with torch.no_grad():
+        ref = ora(x, labels=labels)
+        out = mine(x.to(cuda_device), labels=labels.to(cuda_device), precision="fp32")
+        ref_ids = O.greedy_full_recompute(ora, x, max_length=10, eos_token_id=-1)
+    assert abs(float(out["loss"]) - float(ref["loss"])) < 1e-4, (float(out["loss"]), float(ref["loss"]))
+    assert torch.equal(out["logits"].cpu(), ref["logits"])
+    assert _rel(out["encoder_last_hidden_state"], ref["encoder_last_hidden_state"]) < 1e-4
+    for use_cache in (True, False):
+        ids = mine.generate(x.to(cuda_device), max_length=10, eos_token_id=-1, use_cache=use_cache, precision="fp32").cpu()
+        assert torch.equal(ids, ref_ids), (use_cache, ids.tolist(), ref_ids.tolist())
+
+
+def test_fp32_verification_reference_greedy_fixture(cuda_device):
+    """ids recorded from the UNMODIFIED reference's notebook-style greedy loop (tests/golden/mini_eed_share.json)."""
+    fx = load_fixture("mini_eed_share")
+    ora, x, _ = build_oracle(fx)
+    mine = _mine_from(ora, fx, cuda_device).eval()
+    ids = mine.generate(x.to(cuda_device), max_length=8, eos_token_id=-1, precision="fp32").cpu()
+    assert torch.equal(ids, torch.tensor(fx["greedy_ids"]))
+
+
+def test_fp32_verification_cfg1_full_size(cuda_device):
+    """BASELINE.json configs[0] at full size in fp32: loss within 1e-4 of the reference golden, argmax ids equal."""
+    fx = load_fixture("cfg1_base")
+    ora, x, labels = build_oracle(fx)
+    mine = _mine_from(ora, fx, cuda_device).eval()
+    out = mine(x.to(cuda_device), labels=labels.to(cuda_device), precision="fp32")
+    assert abs(float(out["loss"]) - fx["loss"]) < 1e-4
+    assert torch.equal(out["logits"].cpu(), torch.tensor(fx["argmax_ids"]))
