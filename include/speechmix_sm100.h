@@ -109,10 +109,11 @@ int smx_gemm(const SmxGemm* g, void* stream);
 int smx_layernorm_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* y,
                       void* sum_out, float* mean, float* rstd, int64_t rows, int64_t cols, float eps,
                       int rms_only, int act, void* stream);
-/* dx (+= dres_in) for the op above; dgamma/dbeta are ACCUMULATED (fp32 atomics)
- * into zero-initialised buffers. */
+/* dx (+= dres_in) for the op above; dgamma/dbeta and the optional dx_colsum[c] = sum_rows dx[r, c] (the bias
+ * gradient of the linear layer feeding a post-LN block) are ACCUMULATED (fp32 atomics) into zero-initialised
+ * buffers. */
 int smx_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* beta, const float* mean,
-                      const float* rstd, const void* dres_in, void* dx, float* dgamma, float* dbeta,
+                      const float* rstd, const void* dres_in, void* dx, float* dgamma, float* dbeta, float* dx_colsum,
                       int64_t rows, int64_t cols, int rms_only, int act, void* stream);
 
 /* out[n] (+)= sum_r x[r, n]   (bias gradients). fp32 accumulate via atomics into a zeroed buffer. */

@@ -60,7 +60,7 @@ SIGNATURES = {
     "smx_device_ok": (c_int, []),
     "smx_gemm": (c_int, [POINTER(SmxGemm), _P]),
     "smx_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, c_float, c_int, c_int, _P]),
-    "smx_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, c_int, c_int, _P]),
+    "smx_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, c_int, c_int, _P]),
     "smx_colsum": (c_int, [_P, _P, _I64, _I64, _I64, _P]),
     "smx_cast_f32_to_bf16": (c_int, [_P, _P, _I64, _P]),
     "smx_multi_cast": (c_int, [_P, c_int32, c_int32, _P]),

@@ -20,6 +20,16 @@ __device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
   u.z = pack_bf16x2(f[4], f[5]), u.w = pack_bf16x2(f[6], f[7]);
   *reinterpret_cast<uint4*>(p) = u;
 }
+__device__ __forceinline__ void unpack_bf16x8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x), f[1] = bf16_hi(u.x), f[2] = bf16_lo(u.y), f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z), f[5] = bf16_hi(u.z), f[6] = bf16_lo(u.w), f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack_bf16x8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]), u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]), u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
 __device__ __forceinline__ void loadf8(const float* p, float (&f)[8]) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p));
   const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
@@ -105,52 +115,68 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
 }
 
 // ------------------------------------------------------------------ LayerNorm backward
-template <int VPL>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
-                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                     const float* __restrict__ mean_in,
-                                                     const float* __restrict__ rstd_in, const bf16* __restrict__ dres,
-                                                     bf16* __restrict__ dx, float* __restrict__ dgamma,
-                                                     float* __restrict__ dbeta, long long rows, int cols, int rms_only,
-                                                     int act) {
+// One warp per row, rows strided over a persistent grid; parameter gradients (and, optionally, the column sums
+// of dx = the bias gradient of the linear layer in front of a post-LN block) accumulate in registers and are
+// reduced once per block.  Between the statistics pass and the dx pass a row is held as the PACKED bf16 it was
+// loaded as (2 x 4 registers per 8 elements) instead of two fp32 copies, which is what keeps the kernel at
+// two resident 256-thread blocks per SM -- an HBM-bound row kernel needs the
+// warps to cover the memory latency (the first version: 159 registers, 8 warps per SM, 29 % of HBM peak).
+template <int VPL, bool WITH_CS>
+__global__ void __launch_bounds__(256, (VPL <= 3 ? 2 : 1))
+ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ gamma,
+              const float* __restrict__ beta, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+              const bf16* __restrict__ dres, bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+              float* __restrict__ dx_colsum, long long rows, int cols, int rms_only, int act) {
   __shared__ float red[8][32 * 8 + 1];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const long long warp_global = (long long)blockIdx.x * 8 + warp;
   const long long nwarps = (long long)gridDim.x * 8;
-  float ag[VPL][8], ab[VPL][8];
+  float ag[VPL][8], ab[VPL][8], ac[WITH_CS ? VPL : 1][8];
 #pragma unroll
   for (int i = 0; i < VPL; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) ag[i][j] = 0.f, ab[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) {
+      ag[i][j] = 0.f, ab[i][j] = 0.f;
+      if (WITH_CS) ac[i][j] = 0.f;
+    }
 
   for (long long row = warp_global; row < rows; row += nwarps) {
     const float mean = rms_only ? 0.f : mean_in[row];
     const float rstd = rstd_in[row];
-    float xh[VPL][8], g[VPL][8];
+    uint4 dp[VPL], xp[VPL];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int c = (i * 32 + lane) * 8;
       if (c < cols) {
-        float d[8], gm[8];
-        load8(dy + row * cols + c, d);
-        load8(x + row * cols + c, xh[i]);
+        dp[i] = *reinterpret_cast<const uint4*>(dy + row * cols + c);
+        xp[i] = *reinterpret_cast<const uint4*>(x + row * cols + c);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      if (c < cols) {
+        float d[8], xh[8], gm[8];
+        unpack_bf16x8(dp[i], d);
+        unpack_bf16x8(xp[i], xh);
         loadf8(gamma + c, gm);
         if (act == SMX_ACT_GELU) {  // y = gelu(z), z = xhat*gamma + beta: fold gelu'(z) into dy first
           float bt[8];
           loadf8(beta + c, bt);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) d[j] *= gelu_erf_grad(fmaf((xh[i][j] - mean) * rstd, gm[j], bt[j]));
+          for (int j = 0; j < 8; ++j) d[j] *= gelu_erf_grad(fmaf((xh[j] - mean) * rstd, gm[j], bt[j]));
+          dp[i] = pack_bf16x8(d);   // the dx pass re-reads the folded gradient
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          xh[i][j] = (xh[i][j] - mean) * rstd;
-          ag[i][j] += d[j] * xh[i][j];
+          const float h = (xh[j] - mean) * rstd;
+          ag[i][j] = fmaf(d[j], h, ag[i][j]);
           ab[i][j] += d[j];
-          g[i][j] = d[j] * gm[j];
-          s1 += g[i][j];
-          s2 += g[i][j] * xh[i][j];
+          const float gj = d[j] * gm[j];
+          s1 += gj;
+          s2 = fmaf(gj, h, s2);
         }
       }
     }
@@ -160,9 +186,12 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
     for (int i = 0; i < VPL; ++i) {
       const int c = (i * 32 + lane) * 8;
       if (c < cols) {
-        float o[8];
+        float d[8], xh[8], gm[8], o[8];
+        unpack_bf16x8(dp[i], d);
+        unpack_bf16x8(xp[i], xh);
+        loadf8(gamma + c, gm);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rstd * (g[i][j] - s1 - xh[i][j] * s2);
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (d[j] * gm[j] - s1 - (xh[j] - mean) * rstd * s2);
         if (dres) {
           float r[8];
           load8(dres + row * cols + c, r);
@@ -170,25 +199,30 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
           for (int j = 0; j < 8; ++j) o[j] += r[j];
         }
         store8(dx + row * cols + c, o);
+        if (WITH_CS) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ac[i][j] += o[j];
+        }
       }
     }
   }
-  // block reduction of the parameter gradients, then one atomic per column per block
+  // block reduction of the column accumulators, then one atomic per column per block
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    for (int pass = 0; pass < 2; ++pass) {
-      if (pass == 1 && dbeta == nullptr) continue;
+#pragma unroll
+    for (int pass = 0; pass < (WITH_CS ? 3 : 2); ++pass) {
+      float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : dx_colsum);
+      if (dst == nullptr) continue;
       __syncthreads();
 #pragma unroll
-      for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = pass == 0 ? ag[i][j] : ab[i][j];
+      for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = pass == 0 ? ag[i][j] : (pass == 1 ? ab[i][j] : ac[WITH_CS ? i : 0][j]);
       __syncthreads();
-      // 256 threads, 256 columns of this vector slot
-      const int col_local = threadIdx.x;
+      const int col_local = threadIdx.x;  // 256 threads, 256 columns of this vector slot
       float t = 0.f;
 #pragma unroll
       for (int w = 0; w < 8; ++w) t += red[w][col_local];
       const int c = i * 256 + col_local;
-      if (c < cols) atomicAdd((pass == 0 ? dgamma : dbeta) + c, t);
+      if (c < cols) atomicAdd(dst + c, t);
     }
   }
 }
@@ -463,18 +497,28 @@ int smx_layernorm_fwd(const void* x, const void* res, const float* gamma, const 
 }
 
 int smx_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* beta, const float* mean,
-                      const float* rstd, const void* dres_in, void* dx, float* dgamma, float* dbeta, int64_t rows,
-                      int64_t cols, int rms_only, int act, void* stream) {
+                      const float* rstd, const void* dres_in, void* dx, float* dgamma, float* dbeta, float* dx_colsum,
+                      int64_t rows, int64_t cols, int rms_only, int act, void* stream) {
   SMX_REQUIRE(act == SMX_ACT_NONE || (act == SMX_ACT_GELU && beta != nullptr), "layernorm_bwd: bad fused activation");
   SMX_REQUIRE(cols % 8 == 0 && cols <= 2048 && cols > 0, "layernorm_bwd: cols %lld unsupported", (long long)cols);
   SMX_REQUIRE(dgamma != nullptr, "layernorm_bwd: dgamma required");
   if (rows == 0) return 0;
   const int vpl = (int)ceil_div(cols, 256);
-  int grid = grid_for(rows, 8, 2);
+  const bool cs = dx_colsum != nullptr;
+  int grid = grid_for(rows, 8, vpl <= 3 ? 2 : 1);   // resident blocks per SM: one persistent wave
   cudaStream_t st = (cudaStream_t)stream;
-  LN_DISPATCH(vpl, ln_bwd_kernel,
-              <<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)x, gamma, beta, mean, rstd, (const bf16*)dres_in,
-                                     (bf16*)dx, dgamma, dbeta, rows, (int)cols, rms_only, act));
+#define LN_BWD_ARGS                                                                                              \
+  <<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)x, gamma, beta, mean, rstd, (const bf16*)dres_in, (bf16*)dx, \
+                         dgamma, dbeta, dx_colsum, rows, (int)cols, rms_only, act)
+  switch (vpl) {
+    case 1: if (cs) ln_bwd_kernel<1, true> LN_BWD_ARGS; else ln_bwd_kernel<1, false> LN_BWD_ARGS; break;
+    case 2: if (cs) ln_bwd_kernel<2, true> LN_BWD_ARGS; else ln_bwd_kernel<2, false> LN_BWD_ARGS; break;
+    case 3: if (cs) ln_bwd_kernel<3, true> LN_BWD_ARGS; else ln_bwd_kernel<3, false> LN_BWD_ARGS; break;
+    case 4: if (cs) ln_bwd_kernel<4, true> LN_BWD_ARGS; else ln_bwd_kernel<4, false> LN_BWD_ARGS; break;
+    case 5: case 6: if (cs) ln_bwd_kernel<6, true> LN_BWD_ARGS; else ln_bwd_kernel<6, false> LN_BWD_ARGS; break;
+    default: if (cs) ln_bwd_kernel<8, true> LN_BWD_ARGS; else ln_bwd_kernel<8, false> LN_BWD_ARGS; break;
+  }
+#undef LN_BWD_ARGS
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

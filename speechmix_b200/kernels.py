@@ -369,16 +369,19 @@ def layernorm_fwd(x, gamma, beta, eps=1e-5, res=None, want_sum=False, rms_only=F
     return y, (s if s is not None else x), mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, rms_only=False, want_dbeta=True, act=ACT_NONE, beta=None):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, rms_only=False, want_dbeta=True, act=ACT_NONE, beta=None,
+                  want_colsum=False):
+    """Returns dx, dgamma, dbeta (and, with want_colsum, the fp32 column sums of dx)."""
     C = x.shape[-1]
     rows = x.numel() // C
     dx = torch.empty_like(x)
     dgamma = zeros_f32(C, device=x.device)
     dbeta = zeros_f32(C, device=x.device) if want_dbeta else None
+    csum = zeros_f32(C, device=x.device) if want_colsum else None
     _lib.check(_L().smx_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), _ptr(dres),
-                                      _ptr(dx), _ptr(dgamma), _ptr(dbeta), rows, C, 1 if rms_only else 0, act,
+                                      _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(csum), rows, C, 1 if rms_only else 0, act,
                                       _stream()), "layernorm_bwd")
-    return dx, dgamma, dbeta
+    return (dx, dgamma, dbeta, csum) if want_colsum else (dx, dgamma, dbeta)
 
 
 def colsum(x2d):

@@ -288,10 +288,12 @@ class AttnBlockFn(torch.autograd.Function):
             ds = dy2
             a_in = a          # normalised input
         else:
-            ds, dlnw, dlnb = K.layernorm_bwd(dy2, a, ln_w.detach(), mean, rstd, rms_only=rms, want_dbeta=ctx.has_lnb)
+            ds, dlnw, dlnb, d_ob = K.layernorm_bwd(dy2, a, ln_w.detach(), mean, rstd, rms_only=rms, want_dbeta=ctx.has_lnb,
+                                                   want_colsum=True)   # colsum(ds) = out-proj bias gradient, fused
             a_in = x2
         o2 = o.view(B * T, Hi)
-        d_ob = K.colsum(ds) if ctx.has_obias else None
+        if pre_ln or not ctx.has_obias:
+            d_ob = K.colsum(ds) if ctx.has_obias else None
         d_ow = K.linear_wgrad(ds, o2) if _need(ctx, 9) else None
         do = K.linear_dgrad(ds, w16(o_w)).view(B, T, Hi)
         dsrc = None
@@ -383,9 +385,11 @@ class FFNBlockFn(torch.autograd.Function):
         if ctx.pre_ln:
             ds, a_in = dy2, a
         else:
-            ds, dlnw, dlnb = K.layernorm_bwd(dy2, a, ln_w.detach(), mean, rstd, rms_only=ctx.rms, want_dbeta=ctx.has_lnb)
+            ds, dlnw, dlnb, db2 = K.layernorm_bwd(dy2, a, ln_w.detach(), mean, rstd, rms_only=ctx.rms, want_dbeta=ctx.has_lnb,
+                                                  want_colsum=True)    # colsum(ds) = fc2 bias gradient, fused
             a_in = x2
-        db2 = K.colsum(ds) if ctx.has_bias else None
+        if ctx.pre_ln or not ctx.has_bias:
+            db2 = K.colsum(ds) if ctx.has_bias else None
         dw2 = K.linear_wgrad(ds, h) if _need(ctx, 4) else None
         dpre = K.linear_dgrad(ds, w16(w2), act=ctx.dact, aux_in=pre)
         db1 = K.colsum(dpre) if ctx.has_bias else None

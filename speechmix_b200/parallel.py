@@ -18,12 +18,15 @@ class GradientAllReducer:
     Buckets are filled in reverse parameter-registration order (~ the order backward produces
     gradients: LM head / decoder first, conv stack last).  When the last gradient of a bucket
     arrives its gradients are packed into one flat buffer and ``all_reduce`` is issued
-    asynchronously on the communicator's stream; ``finish()`` waits and scatters the averaged
-    values back into ``param.grad``.  Works with any backend (``gloo`` in the CPU tests)."""
+    asynchronously on the communicator's stream and ``param.grad`` is re-pointed at its slice of the
+    bucket (no copy back); ``finish()`` only waits.  Works with any backend (``gloo`` in the CPU tests)."""
 
     def __init__(self, module, world_size=None, bucket_mb=64, group=None):
         self.world = world_size if world_size is not None else dist.get_world_size()
         self.group = group
+        # NCCL averages inside the collective; gloo (CPU tests) has no AVG -> scale after the wait
+        self.avg_in_collective = dist.get_backend(group) == "nccl"
+        self.enabled = True
         params = [p for p in module.parameters() if p.requires_grad]
         params.reverse()
         cap = int(bucket_mb * 1024 * 1024 / 4)
@@ -55,15 +58,21 @@ class GradientAllReducer:
         return out
 
     def _hook(self, p):
+        if not self.enabled:    # gradient accumulation micro-step (no_sync): keep local gradients
+            return
         bi = self.owner[id(p)]
         self.pending[bi] -= 1
         if self.pending[bi] == 0:
             self._launch(bi)
 
     def _launch(self, bi):
+        views = self._views(bi)
         grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.buckets[bi]]
-        torch._foreach_copy_(self._views(bi), grads)
-        self.works[bi] = dist.all_reduce(self.flat[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        torch._foreach_copy_(views, grads)
+        for p, v in zip(self.buckets[bi], views):
+            p.grad = v          # gradients live in the bucket from here on: no copy back after the collective
+        op = dist.ReduceOp.AVG if self.avg_in_collective else dist.ReduceOp.SUM
+        self.works[bi] = dist.all_reduce(self.flat[bi], op=op, group=self.group, async_op=True)
 
     def finish(self):
         """Call after ``loss.backward()``: flush buckets whose parameters received no gradient this
@@ -71,19 +80,26 @@ class GradientAllReducer:
         for bi in range(len(self.buckets)):
             if self.works[bi] is None:
                 self._launch(bi)
-        inv = 1.0 / self.world
         for bi, b in enumerate(self.buckets):
             self.works[bi].wait()
-            views = self._views(bi)
-            grads = []
-            for p, v in zip(b, views):
-                if p.grad is None:
-                    p.grad = torch.empty_like(p)
-                grads.append(p.grad)
-            torch._foreach_mul_(views, inv)
-            torch._foreach_copy_(grads, views)
+            if not self.avg_in_collective:
+                self.flat[bi].mul_(1.0 / self.world)
             self.works[bi] = None
             self.pending[bi] = len(b)
+
+    def no_sync(self):
+        """Context manager for gradient-accumulation micro-steps (ref:train.py:295 gradient_accumulation_steps):
+        gradients accumulate locally; the first backward outside the context reduces the accumulated sum."""
+        red = self
+
+        class _Ctx:
+            def __enter__(self):
+                red.enabled = False
+
+            def __exit__(self, *exc):
+                red.enabled = True
+                return False
+        return _Ctx()
 
     def remove(self):
         for h in self.handles:

@@ -87,7 +87,7 @@ def rowwise():
     from speechmix_b200 import kernels as K
     ok = True
     g = torch.Generator(device="cuda").manual_seed(0)
-    for (R, C) in [(1000, 768), (333, 512), (100, 1024), (64, 256)]:
+    for (R, C) in [(1000, 768), (333, 512), (100, 1024), (64, 256), (5000, 768)]:
         x = torch.randn(R, C, device="cuda", generator=g).to(torch.bfloat16)
         r = torch.randn(R, C, device="cuda", generator=g).to(torch.bfloat16)
         gamma = (1 + 0.1 * torch.randn(C, device="cuda", generator=g)).requires_grad_(True)
@@ -99,8 +99,9 @@ def rowwise():
         ok &= _rep("ln sum", s, sr)
         dy = torch.randn(R, C, device="cuda", generator=g).to(torch.bfloat16)
         y_ref.backward(dy.float())
-        dx, dg, db = K.layernorm_bwd(dy, s, gamma.detach(), mean, rstd)
+        dx, dg, db, cs = K.layernorm_bwd(dy, s, gamma.detach(), mean, rstd, want_colsum=True)
         ok &= _rep("ln dx", dx, sr.grad)
+        ok &= _rep("ln dx colsum", cs, dx.float().sum(0), 5e-3)  # kernel sums the unrounded fp32 dx
         ok &= _rep("ln dgamma", dg, gamma.grad, 5e-3)
         ok &= _rep("ln dbeta", db, beta.grad, 5e-3)
         ok &= _rep("colsum", K.colsum(dy), dy.float().sum(0), 1e-3)
