@@ -8,6 +8,7 @@ N > 1 is launched by torchrun (one rank per GPU, NCCL); data parallel, weak scal
 Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for what every key means.
 """
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -78,6 +79,14 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
+def _ncu_traffic():
+    """dram__bytes_read + write per launch of the dominant kernel, from the committed ncu --set full capture."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def build_cpu_reference(batch):
     """The reference's CPU path, restated (oracle/hf_oracle.py; /root/reference does not exist on the
     GPU box): HFSpeechMixEED glue over transformers' Wav2Vec2Model + BartForConditionalGeneration, fp32."""
@@ -85,7 +94,8 @@ def build_cpu_reference(batch):
     from oracle import hf_oracle as O
     spc, txc = O.speech_config("base"), O.text_config("bart-base")
     s, t = O.build_backbones(spc, txc, seed=0)
-    model = O.OracleEED(s, t, down_scale=2).train()
+    with contextlib.redirect_stdout(sys.stderr):
+        model = O.OracleEED(s, t, down_scale=2).train()
     x, labels = O.synthetic_batch(batch, SECONDS, T_DEC, txc.vocab_size, seed=0)
     return model, x, labels
 
@@ -158,7 +168,8 @@ def main():
 
     spc, txc = O.speech_config("base"), O.text_config("bart-base")
     torch.manual_seed(0)
-    model = SpeechMixEED(spc, txc, down_scale=2)
+    with contextlib.redirect_stdout(sys.stderr):   # the reference-compatible ctor prints its layer-sharing summary
+        model = SpeechMixEED(spc, txc, down_scale=2)
     parallel.init_like_reference(model, seed=0)
     model = model.to(dev).train()
     B = args.batch
@@ -245,7 +256,7 @@ def main():
             roof = {"bound": "tensor", "kernel": "gemm_kernel<NT> M=%d N=3072 K=768 (FFN up-projection + bias + GELU)" % (B * 749),
                     "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
-                    "launches_timed": len(dom), "traffic": None,
+                    "launches_timed": len(dom), "traffic": _ncu_traffic(),
                     "step_frac_of_peak": fl_step / (ms * 1e-3) / 1e12 / peak_tf}
         line = {"metric": "train audio-sec/s", "value": audio_s / (ms * 1e-3), "unit": "audio-s/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,

@@ -20,5 +20,7 @@ if [ "${SKIP_NCU:-0}" != "1" ]; then
   wc -l $OUT/${TAG}_launches.csv
   timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -c 12 \
       -o $OUT/${TAG}_top -f python tools/ncu_targets.py attn gemm > $OUT/${TAG}_ncu_top.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -c 12 \
+      -o $OUT/${TAG}_rowwise -f python tools/ncu_targets.py rowwise > $OUT/${TAG}_ncu_rowwise.log 2>&1
   tail -3 $OUT/${TAG}_ncu_top.log
 fi

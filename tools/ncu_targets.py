@@ -37,3 +37,24 @@ if "gemm" in which:
         K.linear_wgrad(dy, x)                                                 # TN
         K.linear_dgrad(dy, w)                                                 # NN
 torch.cuda.synchronize()
+if "rowwise" in which:
+    # HBM-bound kernels at the bench shapes: LayerNorm fwd/bwd over [B*749, 768], bias-gradient column sums,
+    # weighted layer sum over 13 hidden states, conv0 + GroupNorm + GELU fwd/bwd over [B, 47999, 512]
+    M, C = B * T, 768
+    x = torch.randn(M, C, device="cuda", generator=g).to(torch.bfloat16)
+    dy = torch.randn(M, C, device="cuda", generator=g).to(torch.bfloat16)
+    gamma = torch.ones(C, device="cuda")
+    beta = torch.zeros(C, device="cuda")
+    xs = [torch.randn(B, T, C, device="cuda", generator=g).to(torch.bfloat16) for _ in range(13)]
+    w13 = torch.softmax(torch.zeros(13, device="cuda"), 0)
+    audio = torch.randn(B, 240000, device="cuda", generator=g)
+    w0 = torch.randn(512, 1, 10, device="cuda", generator=g) * 0.3
+    g0, b0 = torch.ones(512, device="cuda"), torch.zeros(512, device="cuda")
+    for _ in rounds():
+        y, _, mean, rstd = K.layernorm_fwd(x, gamma, beta)
+        K.layernorm_bwd(dy, x, gamma, mean, rstd, want_colsum=True)
+        K.colsum(dy)
+        K.weighted_sum_fwd(xs, w13)
+        y0, stats, mom = K.conv0_fwd(audio, w0, g0, b0)
+        K.conv0_bwd(audio, w0, g0, b0, stats, mom, y0)
+torch.cuda.synchronize()

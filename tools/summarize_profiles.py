@@ -57,6 +57,20 @@ for rep in sorted(f for f in os.listdir(G) if f.startswith(tag) and f.endswith("
     for w in want:
         m = [i for i, h in enumerate(hdr) if h == w] or [i for i, h in enumerate(hdr) if h.startswith(w)]
         idx += m[:12] if w.startswith("smsp__average_warp") or w.startswith("smsp__warp_issue") else m[:1]
+    if rep == tag + "_top.ncu-rep":
+        # DRAM traffic of the dominant kernel (first NT GEMM launch of tools/ncu_targets.py = FFN up-projection
+        # + bias + GELU at the bench shape) -> bench.py's roofline.traffic
+        import json
+        ki = hdr.index("Kernel Name")
+        ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for d in data:
+            if "gemm_kernel<0, 0, 1>" in d[ki]:
+                tb = float(d[ri]) * scale[units[ri]] + float(d[wi]) * scale[units[wi]]
+                json.dump({"kernel": "gemm_kernel<NT> M=23968 N=3072 K=768 (+bias+GELU, 2 bf16 outputs)",
+                           "dram_bytes_per_launch": tb, "source": "profiles/%s_ncu_top.txt (ncu --set full)" % tag},
+                          open(os.path.join(P, "roofline_traffic.json"), "w"))
+                break
     with open(os.path.join(P, rep.replace(".ncu-rep", ".txt").replace(tag + "_", tag + "_ncu_")), "w") as f:
         f.write("# ncu --set full --clock-control none --import-source on (extract of %s)\n" % rep)
         for d in data:
