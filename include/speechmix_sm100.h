@@ -50,7 +50,11 @@ typedef struct SmxView3 {
 #define SMX_MAX_SEG 4
 
 enum { SMX_GEMM_NT = 0, SMX_GEMM_NN = 1, SMX_GEMM_TN = 2 };
-enum { SMX_ACT_NONE = 0, SMX_ACT_GELU = 1, SMX_ACT_RELU = 2, SMX_ACT_DGELU = 3, SMX_ACT_DRELU = 4 };
+enum { SMX_ACT_NONE = 0, SMX_ACT_GELU = 1, SMX_ACT_RELU = 2, SMX_ACT_DGELU = 3, SMX_ACT_DRELU = 4,
+       /* forward: c = gelu(v) and aux_out = gelu'(v) (instead of v), so that the backward epilogue is ... */
+       SMX_ACT_GELU_G = 5,
+       /* ... c = v * aux_in (aux_in = the stored derivative) */
+       SMX_ACT_MULAUX = 6 };
 enum { SMX_OUT_BF16 = 0, SMX_OUT_F32 = 1 };
 
 /* One descriptor covers every contraction on the path:

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libspeechmix_sm100.so")
 SMX_MAX_SEG = 4
 
 GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2
-ACT_NONE, ACT_GELU, ACT_RELU, ACT_DGELU, ACT_DRELU = 0, 1, 2, 3, 4
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_DGELU, ACT_DRELU, ACT_GELU_G, ACT_MULAUX = 0, 1, 2, 3, 4, 5, 6
 OUT_BF16, OUT_F32 = 0, 1
 
 

@@ -111,6 +111,13 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return u;
 }
 
+// v * act'(x) for the three backward epilogue flavours (x = stored pre-activation, or the stored derivative)
+__device__ __forceinline__ float dact_apply(int act, float v, float x) {
+  if (act == SMX_ACT_MULAUX) return v * x;
+  if (act == SMX_ACT_DGELU) return v * gelu_erf_grad(x);
+  return x > 0.0f ? v : 0.0f;
+}
+
 // generic path: any n, any alignment (per-element predicates; only instantiated in the <FAST = false> kernels)
 __device__ __forceinline__ void epilogue_chunk_generic(const Params& p, float (&f)[32], long long c_off,
                                                        long long res_off, int col0) {
@@ -120,8 +127,16 @@ __device__ __forceinline__ void epilogue_chunk_generic(const Params& p, float (&
     if (col < p.n) {
       float v = p.alpha * f[j];
       if (p.bias) v += __ldg(p.bias + col);
-      if (p.aux_out) p.aux_out[c_off + col] = __float2bfloat16(v);
+      if (p.act == SMX_ACT_GELU_G) {
+        float y, dy;
+        gelu_erf_both(v, y, dy);
+        p.aux_out[c_off + col] = __float2bfloat16(dy);
+        v = y;
+      } else if (p.aux_out) {
+        p.aux_out[c_off + col] = __float2bfloat16(v);
+      }
       if (p.act == SMX_ACT_GELU) v = gelu_erf(v);
+      else if (p.act == SMX_ACT_MULAUX) v *= __bfloat162float(p.aux_in[c_off + col]);
       else if (p.act == SMX_ACT_RELU) v = fmaxf(v, 0.f);
       else if (p.act == SMX_ACT_DGELU) v *= gelu_erf_grad(__bfloat162float(p.aux_in[c_off + col]));
       else if (p.act == SMX_ACT_DRELU) v = __bfloat162float(p.aux_in[c_off + col]) > 0.f ? v : 0.f;
@@ -147,12 +162,21 @@ __device__ __forceinline__ void epilogue_chunk_fast(const Params& p, float (&f)[
       f[j] += b4.x, f[j + 1] += b4.y, f[j + 2] += b4.z, f[j + 3] += b4.w;
     }
   }
-  if (p.aux_out) {
+  if (p.act == SMX_ACT_GELU_G) {
+    bf16* ap = p.aux_out + c_off + col0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      float d[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) gelu_erf_both(f[j + i], f[j + i], d[i]);
+      *reinterpret_cast<uint4*>(ap + j) = pack8(d);
+    }
+  } else if (p.aux_out) {
     bf16* ap = p.aux_out + c_off + col0;
 #pragma unroll
     for (int j = 0; j < 32; j += 8) *reinterpret_cast<uint4*>(ap + j) = pack8(f + j);
   }
-  const bool has_dact = p.act == SMX_ACT_DGELU || p.act == SMX_ACT_DRELU;
+  const bool has_dact = p.act == SMX_ACT_DGELU || p.act == SMX_ACT_DRELU || p.act == SMX_ACT_MULAUX;
   if (p.act == SMX_ACT_GELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
@@ -160,14 +184,13 @@ __device__ __forceinline__ void epilogue_chunk_fast(const Params& p, float (&f)[
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
   } else if (has_dact) {
-    const bool dg = p.act == SMX_ACT_DGELU;
     const bf16* xp = p.aux_in + c_off + col0;
 #pragma unroll
     for (int j = 0; j < 32; j += 8) {
       float x[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(xp + j)), x);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f[j + i] = dg ? f[j + i] * gelu_erf_grad(x[i]) : (x[i] > 0.0f ? f[j + i] : 0.0f);
+      for (int i = 0; i < 8; ++i) f[j + i] = dact_apply(p.act, f[j + i], x[i]);
     }
   }
   if (p.residual) {
@@ -220,15 +243,14 @@ __device__ __forceinline__ void epi_act_res(const Params& p, float (&f)[64], lon
   } else if (p.act == SMX_ACT_RELU) {
 #pragma unroll
     for (int j = 0; j < 64; ++j) f[j] = fmaxf(f[j], 0.0f);
-  } else if (p.act == SMX_ACT_DGELU || p.act == SMX_ACT_DRELU) {
-    const bool dg = p.act == SMX_ACT_DGELU;
+  } else if (p.act == SMX_ACT_DGELU || p.act == SMX_ACT_DRELU || p.act == SMX_ACT_MULAUX) {
     const bf16* xp = p.aux_in + c_off + col0;
 #pragma unroll
     for (int j = 0; j < 64; j += 8) {
       float x[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(xp + j)), x);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f[j + i] = dg ? f[j + i] * gelu_erf_grad(x[i]) : (x[i] > 0.0f ? f[j + i] : 0.0f);
+      for (int i = 0; i < 8; ++i) f[j + i] = dact_apply(p.act, f[j + i], x[i]);
     }
   }
   if (p.residual) {
@@ -251,14 +273,13 @@ __device__ __forceinline__ void epi_act_res_pre(const Params& p, float (&f)[64],
   } else if (p.act == SMX_ACT_RELU) {
 #pragma unroll
     for (int j = 0; j < 64; ++j) f[j] = fmaxf(f[j], 0.0f);
-  } else if (p.act == SMX_ACT_DGELU || p.act == SMX_ACT_DRELU) {
-    const bool dg = p.act == SMX_ACT_DGELU;
+  } else if (p.act == SMX_ACT_DGELU || p.act == SMX_ACT_DRELU || p.act == SMX_ACT_MULAUX) {
 #pragma unroll
     for (int j = 0; j < 64; j += 8) {
       float x[8];
       unpack8(pre[j >> 3], x);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f[j + i] = dg ? f[j + i] * gelu_erf_grad(x[i]) : (x[i] > 0.0f ? f[j + i] : 0.0f);
+      for (int i = 0; i < 8; ++i) f[j + i] = dact_apply(p.act, f[j + i], x[i]);
     }
   }
   if (p.residual) {
@@ -278,6 +299,19 @@ __device__ __forceinline__ void stage_row(uint8_t* stg, int r, const float (&f)[
   const int sw = r & 7;
 #pragma unroll
   for (int k = 0; k < 8; ++k) *reinterpret_cast<uint4*>(row + ((k ^ sw) << 4)) = pack8(f + k * 8);
+}
+
+// SMX_ACT_GELU_G: stage gelu'(f) (the auxiliary output) and replace f by gelu(f) in the same sweep
+__device__ __forceinline__ void stage_row_gelu_both(uint8_t* stg, int r, float (&f)[64]) {
+  uint8_t* row = stg + r * 128;
+  const int sw = r & 7;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float d[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) gelu_erf_both(f[k * 8 + i], f[k * 8 + i], d[i]);
+    *reinterpret_cast<uint4*>(row + ((k ^ sw) << 4)) = pack8(d);
+  }
 }
 
 // EPI: 0 regular fused epilogue, 1 LM-head statistics, 2 LM-head dlogits.  FAST: n % 32 == 0 and every
@@ -657,7 +691,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               if (p.aux_out) {
                 if (lane == 0) tma_store_wait_read<0>();
                 __syncwarp();
-                stage_row(stg, lane, f);
+                if (p.act == SMX_ACT_GELU_G) stage_row_gelu_both(stg, lane, f);
+                else stage_row(stg, lane, f);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
@@ -819,7 +854,7 @@ static int make_store_maps(const SmxGemm* g, smx::gemm::Params* p, CUtensorMap* 
   }
   *ti = *tc;
   if (!g->aux_out) {  // the staging tile is free for an input: activation-gradient operand first, else the residual
-    const bool dact = g->act == SMX_ACT_DGELU || g->act == SMX_ACT_DRELU;
+    const bool dact = g->act == SMX_ACT_DGELU || g->act == SMX_ACT_DRELU || g->act == SMX_ACT_MULAUX;
     if (dact) {
       if (encode_tmap_bf16(ti, g->aux_in, 3, dims, str, box, true)) return -1;
       p->tma_in = 1;
@@ -909,7 +944,9 @@ int smx::gemm::run(const SmxGemm* g, const LmExtra* lm, void* stream) {
   }
 
   SMX_REQUIRE(g->k == (int64_t)g->nseg * g->seg_len, "smx_gemm: k %lld != nseg*seg_len", (long long)g->k);
-  SMX_REQUIRE(g->act != SMX_ACT_DGELU && g->act != SMX_ACT_DRELU || g->aux_in, "smx_gemm: DGELU/DRELU need aux_in");
+  SMX_REQUIRE((g->act != SMX_ACT_DGELU && g->act != SMX_ACT_DRELU && g->act != SMX_ACT_MULAUX) || g->aux_in,
+              "smx_gemm: DGELU/DRELU/MULAUX need aux_in");
+  SMX_REQUIRE(g->act != SMX_ACT_GELU_G || g->aux_out, "smx_gemm: GELU_G needs aux_out");
   p.out_f32 = g->out_dtype == SMX_OUT_F32;
   p.m_tiles_per_batch = (int)ceil_div(g->m, PAIR_M);
   p.m_tiles = p.m_tiles_per_batch * (int)g->batches;

@@ -330,7 +330,8 @@ __global__ void dact_kernel(const bf16* __restrict__ dy, const bf16* __restrict_
     load8(dy + i, d);
     load8(pre + i, x);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) d[j] = act == SMX_ACT_GELU ? d[j] * gelu_erf_grad(x[j]) : (x[j] > 0.f ? d[j] : 0.f);
+    for (int j = 0; j < 8; ++j)
+      d[j] = act == SMX_ACT_MULAUX ? d[j] * x[j] : (act == SMX_ACT_GELU ? d[j] * gelu_erf_grad(x[j]) : (x[j] > 0.f ? d[j] : 0.f));
     store8(o + i, d);
   }
 }

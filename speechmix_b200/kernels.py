@@ -10,7 +10,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import (ACT_DGELU, ACT_DRELU, ACT_GELU, ACT_NONE, ACT_RELU, GEMM_NN, GEMM_NT, GEMM_TN, OUT_BF16,
+from ._lib import (ACT_DGELU, ACT_DRELU, ACT_GELU, ACT_GELU_G, ACT_MULAUX, ACT_NONE, ACT_RELU, GEMM_NN, GEMM_NT, GEMM_TN, OUT_BF16,
                    OUT_F32, SmxAttn, SmxGemm, SmxView3)
 
 BF16 = torch.bfloat16
@@ -130,6 +130,8 @@ def linear_fwd(x, w, bias=None, act=ACT_NONE, residual=None, want_pre=False, out
         from . import fp32path
         return fp32path.linear_fwd(x, w, bias, act, residual, want_pre, out_f32, alpha, out)
     assert x.dtype == BF16 and w.dtype == BF16 and x.is_contiguous() and w.is_contiguous()
+    if act == ACT_GELU_G and not want_pre:
+        act = ACT_GELU      # no auxiliary output requested: plain GELU epilogue
     M, K = x.shape
     N = w.shape[0]
     assert w.shape[1] == K and K % 8 == 0
@@ -220,6 +222,8 @@ def conv_s2_fwd(x, w_packed, k, bias=None, act=ACT_NONE, want_pre=False):
     B, T_in, C = x.shape
     N = w_packed.shape[0]
     assert w_packed.shape[1] == k * C and C % 64 == 0 and x.is_contiguous()
+    if act == ACT_GELU_G and not want_pre:
+        act = ACT_GELU
     T_out = conv_out_len(T_in, k, 2)
     y = alloc_act(B, T_out, N, x.device)
     pre = alloc_act(B, T_out, N, x.device) if want_pre else None

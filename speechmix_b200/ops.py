@@ -13,7 +13,7 @@ import weakref
 import torch
 
 from . import kernels as K
-from .kernels import ACT_DGELU, ACT_DRELU, ACT_GELU, ACT_NONE, ACT_RELU, BF16
+from .kernels import ACT_DGELU, ACT_DRELU, ACT_GELU, ACT_GELU_G, ACT_MULAUX, ACT_NONE, ACT_RELU, BF16
 
 
 class WeightCache:
@@ -143,8 +143,12 @@ def conv_packed16(p):
 
 
 def _act_codes(name):
+    """(forward epilogue code, backward epilogue code).  For GELU the forward GEMM stores gelu'(pre) as its
+    auxiliary output (ACT_GELU_G) so the data-gradient GEMM's epilogue is one multiply (ACT_MULAUX) -- the
+    derivative costs ~22 issue slots + 2 MUFU per element, which made those epilogues slower than their
+    K = 768 main loops."""
     if name in ("gelu", "gelu_new"):
-        return ACT_GELU, ACT_DGELU
+        return (ACT_GELU if K.FP32_MODE else ACT_GELU_G), ACT_MULAUX
     if name == "relu":
         return ACT_RELU, ACT_DRELU
     raise ValueError("unsupported activation %r" % (name,))
@@ -416,7 +420,8 @@ class FeatureEncoderGroupFn(torch.autograd.Function):
         y, stats, moments = K.conv0_fwd(audio, w0.detach().contiguous(), gn_w.detach(), gn_b.detach())
         acts, pres = [y], []
         for w, k in zip(ws, ks):
-            y, pre = K.conv_s2_fwd(y, conv_packed16(w), k, act=ACT_GELU, want_pre=True)
+            # `pre` holds gelu'(pre-activation) (ACT_GELU_G), consumed by ACT_MULAUX in backward
+            y, pre = K.conv_s2_fwd(y, conv_packed16(w), k, act=ACT_GELU if K.FP32_MODE else ACT_GELU_G, want_pre=True)
             acts.append(y)
             pres.append(pre)
         ctx.save_for_backward(audio, w0, gn_w, gn_b, stats, moments, *acts[:-1], *pres)
@@ -429,7 +434,7 @@ class FeatureEncoderGroupFn(torch.autograd.Function):
         audio, w0, gn_w, gn_b, stats, moments = sv[:6]
         n = ctx.n
         acts, pres = sv[6:6 + n], sv[6 + n:6 + 2 * n]
-        dpre = K.dact(dy.contiguous(), pres[n - 1], ACT_GELU)
+        dpre = K.dact(dy.contiguous(), pres[n - 1], ACT_MULAUX)
         dws = [None] * n
         for i in range(n - 1, -1, -1):
             w, k = ctx.ws[i], ctx.ks[i]
@@ -437,7 +442,7 @@ class FeatureEncoderGroupFn(torch.autograd.Function):
             if ctx.needs_input_grad[5 + i]:
                 dws[i] = K.unpack_conv_wgrad(K.conv_s2_wgrad(dpre, x_in, k), x_in.shape[2], k)
             if i > 0:
-                dpre = K.conv_s2_dgrad(dpre, conv_packed16(w), k, x_in.shape[1], act=ACT_DGELU, aux_in=pres[i - 1])
+                dpre = K.conv_s2_dgrad(dpre, conv_packed16(w), k, x_in.shape[1], act=ACT_MULAUX, aux_in=pres[i - 1])
             else:
                 dpre = K.conv_s2_dgrad(dpre, conv_packed16(w), k, x_in.shape[1])
         dw0, dg, db = K.conv0_bwd(audio, w0.detach().contiguous(), gn_w.detach(), gn_b.detach(), stats, moments, dpre)

@@ -77,6 +77,16 @@ def nt_epilogue():
     ok &= _report("nt gelu+res", y, F.gelu(ref_pre) + r.float())
     y = K.linear_fwd(x, w, bias=b, act=K.ACT_RELU, out_f32=True, alpha=0.5)
     ok &= _report("nt relu f32 alpha", y, F.relu(0.5 * (x.float() @ w.float().t()) + b))
+    # GELU with the derivative as auxiliary output (ACT_GELU_G), TMA-store path (M, N large) and ragged path
+    for (M2, N2) in [(520, 768), (130, 72)]:
+        x2, w2 = _mk((M2, Kd), seed=5), _mk((N2, Kd), 0.05, seed=6)
+        b2 = torch.randn(N2, device="cuda")
+        y, gp = K.linear_fwd(x2, w2, bias=b2, act=K.ACT_GELU_G, want_pre=True)
+        pr = (x2.float() @ w2.float().t() + b2).requires_grad_(True)
+        yr = F.gelu(pr)
+        yr.sum().backward()
+        ok &= _report(f"nt gelu_g y {M2}x{N2}", y, yr.detach())
+        ok &= _report(f"nt gelu_g dgelu {M2}x{N2}", gp, pr.grad)
     return ok
 
 
@@ -97,6 +107,10 @@ def nn_basic():
     p = pre.float().requires_grad_(True)
     torch.nn.functional.gelu(p).backward(dy.float() @ w.float())
     ok &= _report("nn dgelu", dx, p.grad)
+    for (M2, N2, K2) in [(300, 256, 512), (130, 72, 200)]:
+        dy, w, aux = _mk((M2, N2), seed=1), _mk((N2, K2), 0.05, seed=2), _mk((M2, K2), seed=4)
+        dx = K.linear_dgrad(dy, w, act=K.ACT_MULAUX, aux_in=aux)
+        ok &= _report(f"nn mulaux {M2}x{N2}->{K2}", dx, (dy.float() @ w.float()) * aux.float())
     return ok
 
 
