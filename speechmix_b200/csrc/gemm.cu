@@ -629,7 +629,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             float* cp = reinterpret_cast<float*>(p.c) + c_off + col0;
             const bool full_chunk = col0 + 32 <= p.n;
             if (p.atomic) {
-              if (full_chunk) {
+              if (full_chunk && (p.c_row_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0)) {
+                // 16-byte vector reductions: 8 instead of 32 L2 atomics per row chunk (split-K partial sums)
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  red_add_v4(cp + j, p.alpha * __uint_as_float(v[j]), p.alpha * __uint_as_float(v[j + 1]),
+                             p.alpha * __uint_as_float(v[j + 2]), p.alpha * __uint_as_float(v[j + 3]));
+              } else if (full_chunk) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) atomicAdd(cp + j, p.alpha * __uint_as_float(v[j]));
               } else {

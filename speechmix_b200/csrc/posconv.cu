@@ -282,7 +282,9 @@ posconv_wgrad_kernel(const __grid_constant__ CUtensorMap dmap, const __grid_cons
           if (o < cg && any) {
             float* dst = p.dw + (((long long)g * p.ksize + tap0 + tl) * cg + o) * cg + c16 * 16;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) atomicAdd(dst + i, __uint_as_float(v[i]));
+            for (int i = 0; i < 16; i += 4)
+              red_add_v4(dst + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                         __uint_as_float(v[i + 3]));
           }
           __syncwarp();
         }
