@@ -158,14 +158,16 @@ int smx_unpack_conv_wgrad(const float* src, float* dst, int64_t cout, int64_t ci
 int smx_conv0_stats(const float* audio, const float* w, float* moments, float* stats, int64_t batch,
                     int64_t n_samples, int64_t t_out, int channels, int ksize, int stride, float eps,
                     void* stream);
+/* y = gelu(z) (bf16 [batch][t_out][channels]); gprime (optional, training) = gelu'(z) in the same layout, so
+ * that the backward pass is a pure stream over dy and gprime (no convolution / activation recompute). */
 int smx_conv0_gn_gelu_fwd(const float* audio, const float* w, const float* gamma, const float* beta,
-                          const float* stats, void* y, int64_t batch, int64_t n_samples, int64_t t_out,
-                          int channels, int ksize, int stride, void* stream);
-/* one pass over dy; partial: workspace [batch][channels][ksize+2] fp32; writes dw [C][k], dgamma, dbeta */
+                          const float* stats, void* y, void* gprime, int64_t batch, int64_t n_samples,
+                          int64_t t_out, int channels, int ksize, int stride, void* stream);
+/* one pass over dy and gprime; partial: workspace [batch][channels][ksize+2] fp32; writes dw [C][k], dgamma, dbeta */
 int smx_conv0_gn_gelu_bwd(const float* audio, const float* w, const float* gamma, const float* beta,
-                          const float* stats, const float* moments, const void* dy, float* partial, float* dw,
-                          float* dgamma, float* dbeta, int64_t batch, int64_t n_samples, int64_t t_out,
-                          int channels, int ksize, int stride, void* stream);
+                          const float* stats, const float* moments, const void* dy, const void* gprime,
+                          float* partial, float* dw, float* dgamma, float* dbeta, int64_t batch, int64_t n_samples,
+                          int64_t t_out, int channels, int ksize, int stride, void* stream);
 
 /* feat_extract_norm="layer" variant of layer 0 (HuBERT-large / wav2vec2-large-lv60,
  * hf:...wav2vec2.py:275-299): Conv1d(1->C,k,s,bias) -> LayerNorm over channels -> GELU, one warp per frame. */

@@ -70,8 +70,8 @@ SIGNATURES = {
     "smx_pack_conv_weight": (c_int, [_P, _P, _I64, _I64, _I64, _P]),
     "smx_unpack_conv_wgrad": (c_int, [_P, _P, _I64, _I64, _I64, _P]),
     "smx_conv0_stats": (c_int, [_P, _P, _P, _P, _I64, _I64, _I64, c_int, c_int, c_int, c_float, _P]),
-    "smx_conv0_gn_gelu_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, c_int, c_int, c_int, _P]),
-    "smx_conv0_gn_gelu_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, c_int, c_int, c_int, _P]),
+    "smx_conv0_gn_gelu_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, c_int, c_int, c_int, _P]),
+    "smx_conv0_gn_gelu_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, c_int, c_int, c_int, _P]),
     "smx_conv0_ln_gelu_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, c_int, c_int, c_int, c_float, _P]),
     "smx_conv0_ln_gelu_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, c_int, c_int, c_int, c_float, _P]),
     "smx_conv0_wgrad": (c_int, [_P, _P, _P, _P, _I64, _I64, _I64, c_int, c_int, c_int, _P]),

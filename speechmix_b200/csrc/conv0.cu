@@ -98,12 +98,13 @@ __global__ void stats_kernel(const float* __restrict__ w, const float* __restric
 }
 
 // ------------------------------------------------------------------ forward
-// block: 64 channel-octets x 4 frame lanes; FR frames per block staged through smem
+// block: 128 channel quads x 2 frame lanes; FR frames per block staged through smem
 constexpr int FWD_FR = 256;
-__global__ void __launch_bounds__(256) fwd_kernel(const float* __restrict__ audio, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, 2) fwd_kernel(const float* __restrict__ audio, const float* __restrict__ w,
                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                   const float* __restrict__ stats, bf16* __restrict__ y,
-                                                  long long n_samples, long long t_out, int channels) {
+                                                  bf16* __restrict__ gprime, long long n_samples, long long t_out,
+                                                  int channels) {
   __shared__ float xs[FWD_FR * S + K];
   const int b = blockIdx.y;
   const long long t0 = (long long)blockIdx.x * FWD_FR;
@@ -112,13 +113,15 @@ __global__ void __launch_bounds__(256) fwd_kernel(const float* __restrict__ audi
   const int nload = (int)nfr * S + (K - S);
   for (int i = threadIdx.x; i < nload; i += blockDim.x) xs[i] = x[i];
   __syncthreads();
-  const int octs = channels / 8;
-  const int lanes = blockDim.x / 64;
-  for (int og = threadIdx.x % 64; og < octs; og += 64) {
-    const int c0 = og * 8;
-    float wf[8][K], bf[8];
+  // 4 channels per thread (40 weight registers instead of 80: two resident blocks per SM), 128 channel quads x
+  // 2 frame lanes per block; a warp writes 256 contiguous bytes per frame and output tensor
+  const int quads = channels / 4;
+  const int lanes = blockDim.x / 128;
+  for (int qg = threadIdx.x % 128; qg < quads; qg += 128) {
+    const int c0 = qg * 4;
+    float wf[4][K], bf[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 4; ++j) {
       const int c = c0 + j;
       const float mean = stats[2 * ((long long)b * channels + c)];
       const float rstd = stats[2 * ((long long)b * channels + c) + 1];
@@ -127,34 +130,38 @@ __global__ void __launch_bounds__(256) fwd_kernel(const float* __restrict__ audi
       for (int k = 0; k < K; ++k) wf[j][k] = w[c * K + k] * g;
       bf[j] = beta[c] - mean * g;
     }
-    for (int f = threadIdx.x / 64; f < nfr; f += lanes) {
+    const long long base = ((long long)b * t_out + t0) * channels + c0;
+#pragma unroll 2
+    for (int f = threadIdx.x / 128; f < nfr; f += lanes) {
       float win[K];
 #pragma unroll
       for (int k = 0; k < K; ++k) win[k] = xs[f * S + k];
-      float o[8];
+      float o[4], d[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 4; ++j) {
         float z = bf[j];
 #pragma unroll
         for (int k = 0; k < K; ++k) z = fmaf(wf[j][k], win[k], z);
-        o[j] = gelu_erf(z);
+        if (gprime) gelu_erf_both(z, o[j], d[j]);   // training: also keep gelu'(z) so backward never recomputes the conv
+        else o[j] = gelu_erf(z);
       }
-      uint4 u;
-      u.x = pack_bf16x2(o[0], o[1]), u.y = pack_bf16x2(o[2], o[3]);
-      u.z = pack_bf16x2(o[4], o[5]), u.w = pack_bf16x2(o[6], o[7]);
-      *reinterpret_cast<uint4*>(y + ((long long)b * t_out + t0 + f) * channels + c0) = u;
+      *reinterpret_cast<uint2*>(y + base + (long long)f * channels) =
+          make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+      if (gprime)
+        *reinterpret_cast<uint2*>(gprime + base + (long long)f * channels) =
+            make_uint2(pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]));
     }
   }
 }
 
-// ------------------------------------------------------------------ backward (single pass over dy)
-// partial[b][c][0] = sum dz, [1] = sum dz*xhat, [2+k] = sum_t dz * x[S t + k]
+// ------------------------------------------------------------------ backward (single pass over dy and gelu'(z))
+// dz = dy * gelu'(z) with gelu'(z) stored by the forward pass (bf16): no convolution / activation recompute, the
+// kernel is two streaming reads plus 11 FMAs per element.
+// partial[b][c][0] = sum dz, [2+k] = sum_t dz * x[S t + k]; [1] (= sum dz*xhat) follows algebraically in finalize.
 constexpr int BWD_FR = 1024;
-__global__ void __launch_bounds__(256) bwd_kernel(const float* __restrict__ audio, const float* __restrict__ w,
-                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                  const float* __restrict__ stats, const bf16* __restrict__ dy,
-                                                  float* __restrict__ partial, long long n_samples, long long t_out,
-                                                  int channels) {
+__global__ void __launch_bounds__(256, 3) bwd_kernel(const float* __restrict__ audio, const bf16* __restrict__ dy,
+                                                  const bf16* __restrict__ gprime, float* __restrict__ partial,
+                                                  long long n_samples, long long t_out, int channels) {
   __shared__ float xs[BWD_FR * S + K];
   const int b = blockIdx.y;
   const long long t0 = (long long)blockIdx.x * BWD_FR;
@@ -167,45 +174,34 @@ __global__ void __launch_bounds__(256) bwd_kernel(const float* __restrict__ audi
   const int lanes = blockDim.x / 128;  // 2 frame lanes
   for (int qg = threadIdx.x % 128; qg < quads; qg += 128) {
     const int c0 = qg * 4;
-    float wn[4][K], mn[4], gm[4], bt[4];
-    float acc[4][K + 2];
+    float acc[4][K + 1];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = c0 + j;
-      const float mean = stats[2 * ((long long)b * channels + c)];
-      const float rstd = stats[2 * ((long long)b * channels + c) + 1];
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int k = 0; k < K; ++k) wn[j][k] = w[c * K + k] * rstd;
-      mn[j] = mean * rstd;
-      gm[j] = gamma[c];
-      bt[j] = beta[c];
-#pragma unroll
-      for (int k = 0; k < K + 2; ++k) acc[j][k] = 0.f;
-    }
+      for (int k = 0; k < K + 1; ++k) acc[j][k] = 0.f;
+    const long long base = ((long long)b * t_out + t0) * channels + c0;
+#pragma unroll 4
     for (int f = threadIdx.x / 128; f < nfr; f += lanes) {
+      const uint2 u = *reinterpret_cast<const uint2*>(dy + base + (long long)f * channels);
+      const uint2 g = *reinterpret_cast<const uint2*>(gprime + base + (long long)f * channels);
       float win[K];
 #pragma unroll
       for (int k = 0; k < K; ++k) win[k] = xs[f * S + k];
-      const uint2 u = *reinterpret_cast<const uint2*>(dy + ((long long)b * t_out + t0 + f) * channels + c0);
-      const float d[4] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y)};
+      const float dz[4] = {bf16_lo(u.x) * bf16_lo(g.x), bf16_hi(u.x) * bf16_hi(g.x), bf16_lo(u.y) * bf16_lo(g.y),
+                           bf16_hi(u.y) * bf16_hi(g.y)};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float xh = -mn[j];
+        acc[j][0] += dz[j];
 #pragma unroll
-        for (int k = 0; k < K; ++k) xh = fmaf(wn[j][k], win[k], xh);
-        const float z = fmaf(gm[j], xh, bt[j]);
-        const float dz = d[j] * gelu_erf_grad(z);
-        acc[j][0] += dz;
-        acc[j][1] = fmaf(dz, xh, acc[j][1]);
-#pragma unroll
-        for (int k = 0; k < K; ++k) acc[j][2 + k] = fmaf(dz, win[k], acc[j][2 + k]);
+        for (int k = 0; k < K; ++k) acc[j][1 + k] = fmaf(dz[j], win[k], acc[j][1 + k]);
       }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float* pp = partial + ((long long)b * channels + c0 + j) * (K + 2);
+      atomicAdd(pp, acc[j][0]);
 #pragma unroll
-      for (int k = 0; k < K + 2; ++k) atomicAdd(pp + k, acc[j][k]);
+      for (int k = 0; k < K; ++k) atomicAdd(pp + 2 + k, acc[j][1 + k]);
     }
   }
 }
@@ -223,8 +219,13 @@ __global__ void bwd_finalize_kernel(const float* __restrict__ w, const float* __
   double out = 0.0;
   for (int b = 0; b < batch; ++b) {
     const float* pp = partial + ((long long)b * channels + c) * (K + 2);
+    // sum_t dz*xhat = rstd * (sum_k w_k sum_t dz x[St+k] - mean * sum_t dz)   (xhat = (w.win - mean) * rstd)
+    double pp1 = 0.0;
+    for (int l = 0; l < K; ++l) pp1 += (double)w[c * K + l] * (double)pp[2 + l];
+    pp1 = (pp1 - (double)stats[2 * ((long long)b * channels + c)] * (double)pp[0]) *
+          (double)stats[2 * ((long long)b * channels + c) + 1];
     if (j == K) {
-      out += pp[1];  // dgamma
+      out += pp1;  // dgamma
     } else if (j == K + 1) {
       out += pp[0];  // dbeta
     } else {
@@ -234,7 +235,7 @@ __global__ void bwd_finalize_kernel(const float* __restrict__ w, const float* __
       double wr = 0.0;
       for (int l = 0; l < K; ++l) wr += (double)w[c * K + l] * mo[K + l * K + j];
       const double sum_xhat_x = rstd * (wr - mean * mo[j]);
-      out += (double)gamma[c] * rstd * ((double)pp[2 + j] - (double)pp[0] * inv_t * mo[j] - (double)pp[1] * inv_t * sum_xhat_x);
+      out += (double)gamma[c] * rstd * ((double)pp[2 + j] - (double)pp[0] * inv_t * mo[j] - pp1 * inv_t * sum_xhat_x);
     }
   }
   if (j == K) dgamma[c] = (float)out;
@@ -420,26 +421,27 @@ int smx_conv0_stats(const float* audio, const float* w, float* moments, float* s
 }
 
 int smx_conv0_gn_gelu_fwd(const float* audio, const float* w, const float* gamma, const float* beta,
-                          const float* stats, void* y, int64_t batch, int64_t n_samples, int64_t t_out, int channels,
-                          int ksize, int stride, void* stream) {
+                          const float* stats, void* y, void* gprime, int64_t batch, int64_t n_samples, int64_t t_out,
+                          int channels, int ksize, int stride, void* stream) {
   SMX_REQUIRE(ksize == K && stride == S, "conv0: only kernel 10 / stride 5 is supported");
   SMX_REQUIRE(channels % 8 == 0, "conv0: channels must be a multiple of 8");
   fwd_kernel<<<dim3((unsigned)ceil_div(t_out, FWD_FR), (unsigned)batch), 256, 0, (cudaStream_t)stream>>>(
-      audio, w, gamma, beta, stats, (bf16*)y, n_samples, t_out, channels);
+      audio, w, gamma, beta, stats, (bf16*)y, (bf16*)gprime, n_samples, t_out, channels);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int smx_conv0_gn_gelu_bwd(const float* audio, const float* w, const float* gamma, const float* beta,
-                          const float* stats, const float* moments, const void* dy, float* partial, float* dw,
-                          float* dgamma, float* dbeta, int64_t batch, int64_t n_samples, int64_t t_out, int channels,
-                          int ksize, int stride, void* stream) {
+                          const float* stats, const float* moments, const void* dy, const void* gprime,
+                          float* partial, float* dw, float* dgamma, float* dbeta, int64_t batch, int64_t n_samples,
+                          int64_t t_out, int channels, int ksize, int stride, void* stream) {
+  SMX_REQUIRE(gprime != nullptr, "conv0 bwd: needs the gelu'(z) tensor the training forward stored");
   SMX_REQUIRE(ksize == K && stride == S, "conv0: only kernel 10 / stride 5 is supported");
   SMX_REQUIRE(channels % 4 == 0, "conv0: channels must be a multiple of 4");
   cudaStream_t st = (cudaStream_t)stream;
   SMX_CHECK_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * (K + 2) * batch * channels, st));
   bwd_kernel<<<dim3((unsigned)ceil_div(t_out, BWD_FR), (unsigned)batch), 256, 0, st>>>(
-      audio, w, gamma, beta, stats, (const bf16*)dy, partial, n_samples, t_out, channels);
+      audio, (const bf16*)dy, (const bf16*)gprime, partial, n_samples, t_out, channels);
   SMX_CHECK_CUDA(cudaGetLastError());
   bwd_finalize_kernel<<<(int)ceil_div(channels * (K + 2), 128), 128, 0, st>>>(w, gamma, stats, moments, partial, dw,
                                                                              dgamma, dbeta, (int)batch, channels, t_out);

@@ -440,11 +440,12 @@ def dact(dy, pre, act=ACT_GELU):
 # ---------------------------------------------------------------------------
 # conv0 + GroupNorm + GELU
 # ---------------------------------------------------------------------------
-def conv0_fwd(audio, w, gamma, beta, eps=1e-5):
-    """audio [B, n] fp32, w [C, 1, 10] fp32.  Returns y [B, T, C] bf16 (slack-padded), stats, moments."""
+def conv0_fwd(audio, w, gamma, beta, eps=1e-5, want_gprime=False):
+    """audio [B, n] fp32, w [C, 1, 10] fp32.  Returns y [B, T, C] bf16 (slack-padded), stats, moments and, with
+    want_gprime (training), gelu'(z) [B, T, C] bf16 for the streaming backward."""
     if FP32_MODE:
         from . import fp32path
-        return fp32path.conv0_fwd(audio, w, gamma, beta, eps=eps)
+        return fp32path.conv0_fwd(audio, w, gamma, beta, eps=eps) + ((None,) if want_gprime else ())
     B, n = audio.shape
     C, _, k = w.shape
     s = 5
@@ -455,12 +456,13 @@ def conv0_fwd(audio, w, gamma, beta, eps=1e-5):
     _lib.check(L.smx_conv0_stats(_ptr(audio), _ptr(w), _ptr(moments), _ptr(stats), B, n, T, C, k, s, eps, _stream()),
                "conv0_stats")
     y = alloc_act(B, T, C, audio.device)
-    _lib.check(L.smx_conv0_gn_gelu_fwd(_ptr(audio), _ptr(w), _ptr(gamma), _ptr(beta), _ptr(stats), _ptr(y), B, n, T,
+    gp = torch.empty(B, T, C, device=audio.device, dtype=BF16) if want_gprime else None
+    _lib.check(L.smx_conv0_gn_gelu_fwd(_ptr(audio), _ptr(w), _ptr(gamma), _ptr(beta), _ptr(stats), _ptr(y), _ptr(gp), B, n, T,
                                        C, k, s, _stream()), "conv0_fwd")
-    return y, stats, moments
+    return (y, stats, moments, gp) if want_gprime else (y, stats, moments)
 
 
-def conv0_bwd(audio, w, gamma, beta, stats, moments, dy):
+def conv0_bwd(audio, w, gamma, beta, stats, moments, dy, gprime):
     B, n = audio.shape
     C, _, k = w.shape
     T = dy.shape[1]
@@ -469,8 +471,8 @@ def conv0_bwd(audio, w, gamma, beta, stats, moments, dy):
     dgamma = torch.empty(C, device=audio.device, dtype=torch.float32)
     dbeta = torch.empty(C, device=audio.device, dtype=torch.float32)
     _lib.check(_L().smx_conv0_gn_gelu_bwd(_ptr(audio), _ptr(w), _ptr(gamma), _ptr(beta), _ptr(stats), _ptr(moments),
-                                          _ptr(dy), _ptr(partial), _ptr(dw), _ptr(dgamma), _ptr(dbeta), B, n, T, C,
-                                          k, 5, _stream()), "conv0_bwd")
+                                          _ptr(dy), _ptr(gprime), _ptr(partial), _ptr(dw), _ptr(dgamma), _ptr(dbeta), B, n,
+                                          T, C, k, 5, _stream()), "conv0_bwd")
     return dw, dgamma, dbeta
 
 

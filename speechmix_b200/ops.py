@@ -417,23 +417,25 @@ class FeatureEncoderGroupFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, audio, ks, w0, gn_w, gn_b, *ws):
         audio = audio.contiguous().float()
-        y, stats, moments = K.conv0_fwd(audio, w0.detach().contiguous(), gn_w.detach(), gn_b.detach())
+        need_bwd = bool(any(ctx.needs_input_grad))   # training: the forward also stores gelu'(z) for a streaming backward
+        res = K.conv0_fwd(audio, w0.detach().contiguous(), gn_w.detach(), gn_b.detach(), want_gprime=need_bwd)
+        y, stats, moments, gp0 = res if need_bwd else (*res, None)
         acts, pres = [y], []
         for w, k in zip(ws, ks):
             # `pre` holds gelu'(pre-activation) (ACT_GELU_G), consumed by ACT_MULAUX in backward
             y, pre = K.conv_s2_fwd(y, conv_packed16(w), k, act=ACT_GELU if K.FP32_MODE else ACT_GELU_G, want_pre=True)
             acts.append(y)
             pres.append(pre)
-        ctx.save_for_backward(audio, w0, gn_w, gn_b, stats, moments, *acts[:-1], *pres)
+        ctx.save_for_backward(audio, w0, gn_w, gn_b, stats, moments, gp0, *acts[:-1], *pres)
         ctx.ks, ctx.ws, ctx.n = ks, ws, len(ws)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         sv = ctx.saved_tensors
-        audio, w0, gn_w, gn_b, stats, moments = sv[:6]
+        audio, w0, gn_w, gn_b, stats, moments, gp0 = sv[:7]
         n = ctx.n
-        acts, pres = sv[6:6 + n], sv[6 + n:6 + 2 * n]
+        acts, pres = sv[7:7 + n], sv[7 + n:7 + 2 * n]
         dpre = K.dact(dy.contiguous(), pres[n - 1], ACT_MULAUX)
         dws = [None] * n
         for i in range(n - 1, -1, -1):
@@ -445,7 +447,7 @@ class FeatureEncoderGroupFn(torch.autograd.Function):
                 dpre = K.conv_s2_dgrad(dpre, conv_packed16(w), k, x_in.shape[1], act=ACT_MULAUX, aux_in=pres[i - 1])
             else:
                 dpre = K.conv_s2_dgrad(dpre, conv_packed16(w), k, x_in.shape[1])
-        dw0, dg, db = K.conv0_bwd(audio, w0.detach().contiguous(), gn_w.detach(), gn_b.detach(), stats, moments, dpre)
+        dw0, dg, db = K.conv0_bwd(audio, w0.detach().contiguous(), gn_w.detach(), gn_b.detach(), stats, moments, dpre, gp0)
         return (None, None, dw0, dg, db, *dws)
 
 

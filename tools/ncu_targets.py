@@ -55,6 +55,6 @@ if "rowwise" in which:
         K.layernorm_bwd(dy, x, gamma, mean, rstd, want_colsum=True)
         K.colsum(dy)
         K.weighted_sum_fwd(xs, w13)
-        y0, stats, mom = K.conv0_fwd(audio, w0, g0, b0)
-        K.conv0_bwd(audio, w0, g0, b0, stats, mom, y0)
+        y0, stats, mom, gp0 = K.conv0_fwd(audio, w0, g0, b0, want_gprime=True)
+        K.conv0_bwd(audio, w0, g0, b0, stats, mom, y0, gp0)
 torch.cuda.synchronize()

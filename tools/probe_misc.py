@@ -38,12 +38,12 @@ def conv0():
         w = (torch.randn(C, 1, 10, device="cuda", generator=g) * 0.3).requires_grad_(True)
         gamma = (1 + 0.1 * torch.randn(C, device="cuda", generator=g)).requires_grad_(True)
         beta = (0.1 * torch.randn(C, device="cuda", generator=g)).requires_grad_(True)
-        y, stats, mom = K.conv0_fwd(x, w.detach(), gamma.detach(), beta.detach())
+        y, stats, mom, gp = K.conv0_fwd(x, w.detach(), gamma.detach(), beta.detach(), want_gprime=True)
         ref = F.gelu(F.group_norm(F.conv1d(x[:, None], w, stride=5), C, gamma, beta, 1e-5))
         ok &= _rep(f"conv0 fwd B{B} n{n} C{C}", y, ref.transpose(1, 2))
         dy = torch.randn(y.shape, device="cuda", generator=g).to(torch.bfloat16)
         ref.backward(dy.float().transpose(1, 2))
-        dw, dg, db = K.conv0_bwd(x, w.detach(), gamma.detach(), beta.detach(), stats, mom, dy)
+        dw, dg, db = K.conv0_bwd(x, w.detach(), gamma.detach(), beta.detach(), stats, mom, dy, gp)
         ok &= _rep("conv0 dw", dw, w.grad)
         ok &= _rep("conv0 dgamma", dg, gamma.grad)
         ok &= _rep("conv0 dbeta", db, beta.grad)
