@@ -125,6 +125,12 @@ int smx_colsum(const void* x, float* out, int64_t rows, int64_t cols, int64_t ro
 
 /* elementwise helpers */
 int smx_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* Weight norm of the positional conv (torch weight_norm(dim=2), hf:...wav2vec2.py:341-355): v [rows][k] fp32
+ * (rows = out * in/groups), g [k]; w[r][j] = g[j] v[r][j] / ||v[:, j]||.  sq_ws [k] receives ||v[:, j]||^2 (kept
+ * for the backward); bwd: dv, dg from dw (dot_ws [k] workspace). */
+int smx_weightnorm_fwd(const float* v, const float* g, float* sq_ws, float* w, int64_t rows, int64_t k, void* stream);
+int smx_weightnorm_bwd(const float* v, const float* g, const float* sq, const float* dw, float* dot_ws, float* dv,
+                       float* dg, int64_t rows, int64_t k, void* stream);
 /* Multi-tensor refresh of the bf16 (or fp32) working copies of all parameters in ONE launch: entry i copies
  * src[i][0..n[i]) (fp32) to dst[i] as bf16 (dst_f32[i]=0) or fp32 (=1).  `table` is a DEVICE array of
  * SmxCastEntry sorted by first_chunk (chunk = SMX_CAST_CHUNK elements; first_chunk = running chunk count);

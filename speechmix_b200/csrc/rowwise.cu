@@ -454,6 +454,49 @@ __global__ void __launch_bounds__(256) wsum_bwd_w_kernel(PtrPack xs, const bf16*
   }
 }
 
+// ------------------------------------------------------------------ weight norm over the last dim's complement
+// w[r][k] = g[k] * v[r][k] / ||v[:, k]||   (torch weight_norm(dim=2) of the positional conv: one norm per tap,
+// hf:models/wav2vec2/modeling_wav2vec2.py:341-355).  v viewed as [rows = out*in/groups][k].
+__global__ void __launch_bounds__(256) wn_colstat_kernel(const float* __restrict__ a, const float* __restrict__ b2,
+                                                         float* __restrict__ out, long long rows, int k) {
+  // out[j] += sum_r a[r][j] * (b2 ? b2[r][j] : a[r][j]);  blockDim.x = 256 = 8 row lanes x 32 columns
+  __shared__ float red[8][33];
+  const int cj = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + cj;
+  float acc = 0.f;
+  if (j < k)
+    for (long long r = (long long)blockIdx.y * 8 + rl; r < rows; r += (long long)gridDim.y * 8) {
+      const float x = a[r * k + j];
+      acc = fmaf(x, b2 ? b2[r * k + j] : x, acc);
+    }
+  red[rl][cj] = acc;
+  __syncthreads();
+  if (rl == 0 && j < k) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][cj];
+    atomicAdd(out + j, t);
+  }
+}
+__global__ void wn_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ sq,
+                              float* __restrict__ w, long long n, int k) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % k);
+    w[i] = v[i] * g[j] * rsqrtf(sq[j]);
+  }
+}
+// dv = g/||v|| * (dw - v * dot/||v||^2),  dg = dot / ||v||   with dot[j] = sum_r dw[r][j] v[r][j]
+__global__ void wn_bwd_kernel(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ sq,
+                              const float* __restrict__ dot, const float* __restrict__ dw, float* __restrict__ dv,
+                              float* __restrict__ dg, long long n, int k) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % k);
+    const float inv = rsqrtf(sq[j]);
+    dv[i] = g[j] * inv * (dw[i] - v[i] * dot[j] * inv * inv);
+    if (i < k) dg[i] = dot[i] * inv;
+  }
+}
+
 static int grid_for(long long work_items, int block, int max_waves = 8) {
   long long g = (work_items + block - 1) / block;
   const long long cap = (long long)num_sms() * max_waves;
@@ -548,6 +591,31 @@ int smx_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
 int smx_multi_cast(const SmxCastEntry* table, int32_t n_entries, int32_t total_chunks, void* stream) {
   if (n_entries <= 0 || total_chunks <= 0) return 0;
   multi_cast_kernel<<<total_chunks, 256, 0, (cudaStream_t)stream>>>(table, n_entries);
+  SMX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int smx_weightnorm_fwd(const float* v, const float* g, float* sq_ws, float* w, int64_t rows, int64_t k, void* stream) {
+  SMX_REQUIRE(v && g && sq_ws && w, "weightnorm_fwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  SMX_CHECK_CUDA(cudaMemsetAsync(sq_ws, 0, sizeof(float) * k, st));
+  long long gy = ceil_div(rows, 8 * 32);
+  if (gy > 512) gy = 512;
+  wn_colstat_kernel<<<dim3((unsigned)ceil_div(k, 32), (unsigned)gy), 256, 0, st>>>(v, nullptr, sq_ws, rows, (int)k);
+  SMX_CHECK_CUDA(cudaGetLastError());
+  wn_fwd_kernel<<<grid_for(rows * k, 256), 256, 0, st>>>(v, g, sq_ws, w, rows * k, (int)k);
+  SMX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int smx_weightnorm_bwd(const float* v, const float* g, const float* sq, const float* dw, float* dot_ws, float* dv,
+                       float* dg, int64_t rows, int64_t k, void* stream) {
+  SMX_REQUIRE(v && g && sq && dw && dot_ws && dv && dg, "weightnorm_bwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  SMX_CHECK_CUDA(cudaMemsetAsync(dot_ws, 0, sizeof(float) * k, st));
+  long long gy = ceil_div(rows, 8 * 32);
+  if (gy > 512) gy = 512;
+  wn_colstat_kernel<<<dim3((unsigned)ceil_div(k, 32), (unsigned)gy), 256, 0, st>>>(dw, v, dot_ws, rows, (int)k);
+  SMX_CHECK_CUDA(cudaGetLastError());
+  wn_bwd_kernel<<<grid_for(rows * k, 256), 256, 0, st>>>(v, g, sq, dot_ws, dw, dv, dg, rows * k, (int)k);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

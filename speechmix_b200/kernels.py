@@ -526,6 +526,30 @@ def posconv_pack(weight, groups):
     return pack(fwd), pack(dgr)
 
 
+def weightnorm_fwd(v, g):
+    """v [H, cg, k] fp32, g [1, 1, k] -> (w [H, cg, k], sq [k])"""
+    v = v.detach().contiguous()
+    k = v.shape[-1]
+    rows = v.numel() // k
+    w = torch.empty_like(v)
+    sq = torch.empty(k, device=v.device, dtype=torch.float32)
+    _lib.check(_L().smx_weightnorm_fwd(_ptr(v), _ptr(g.detach().reshape(-1).contiguous()), _ptr(sq), _ptr(w), rows, k,
+                                       _stream()), "weightnorm_fwd")
+    return w, sq
+
+
+def weightnorm_bwd(v, g, sq, dw):
+    v = v.detach().contiguous()
+    k = v.shape[-1]
+    rows = v.numel() // k
+    dv = torch.empty_like(v)
+    dg = torch.empty(k, device=v.device, dtype=torch.float32)
+    dot = torch.empty(k, device=v.device, dtype=torch.float32)
+    _lib.check(_L().smx_weightnorm_bwd(_ptr(v), _ptr(g.detach().reshape(-1).contiguous()), _ptr(sq), _ptr(dw.contiguous()),
+                                       _ptr(dot), _ptr(dv), _ptr(dg), rows, k, _stream()), "weightnorm_bwd")
+    return dv, dg
+
+
 def posconv_fwd(x, w_fwd, bias, groups, ksize, add_input=True):
     if FP32_MODE:
         from . import fp32path

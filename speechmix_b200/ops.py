@@ -535,6 +535,23 @@ class ConvS2Fn(torch.autograd.Function):
         return dx, dw, db, None
 
 
+class WeightNormFn(torch.autograd.Function):
+    """w = g * v / ||v||  with one norm per kernel tap (torch weight_norm(dim=2) on the positional conv,
+    hf:...wav2vec2.py:341-355); g = parametrizations.weight.original0 [1,1,k], v = original1 [H, H/groups, k]."""
+
+    @staticmethod
+    def forward(ctx, g, v):
+        w, sq = K.weightnorm_fwd(v, g)
+        ctx.save_for_backward(g, v, sq)
+        return w
+
+    @staticmethod
+    def backward(ctx, dw):
+        g, v, sq = ctx.saved_tensors
+        dv, dg = K.weightnorm_bwd(v, g, sq, dw.float())
+        return dg.view(g.shape), dv
+
+
 class PosConvFn(torch.autograd.Function):
     """y = x + GELU(grouped_conv(x) + b)[drop last frame]   hf:...wav2vec2.py:326-379, 690-693."""
 

@@ -108,7 +108,7 @@ class PositionalConvEmbedding(nn.Module):
     def forward(self, x):
         """returns x + GELU(conv(x)) (the residual add is fused into the kernel epilogue)."""
         p = self.conv.parametrizations.weight
-        weight = self.conv.weight  # g * v / ||v||, tiny tensor algebra kept in torch autograd
+        weight = ops.WeightNormFn.apply(p.original0, p.original1)  # g * v / ||v|| per tap
         return ops.PosConvFn.apply(x, weight, self.conv.bias, self.groups, (p.original0, p.original1))
 
 
