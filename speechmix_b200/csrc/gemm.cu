@@ -225,14 +225,17 @@ __device__ __forceinline__ void epilogue_chunk_fast(const Params& p, float (&f)[
 
 // ---- pieces of the fast epilogue used by the TMA-store variant (64 columns per step) ----
 __device__ __forceinline__ void epi_scale_bias(const Params& p, float (&f)[64], int col0) {
-#pragma unroll
-  for (int j = 0; j < 64; ++j) f[j] *= p.alpha;
-  if (p.bias) {
+  const float a = p.alpha;
+  if (p.bias) {  // one FMA per element
 #pragma unroll
     for (int j = 0; j < 64; j += 4) {
       const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-      f[j] += b4.x, f[j + 1] += b4.y, f[j + 2] += b4.z, f[j + 3] += b4.w;
+      f[j] = fmaf(f[j], a, b4.x), f[j + 1] = fmaf(f[j + 1], a, b4.y);
+      f[j + 2] = fmaf(f[j + 2], a, b4.z), f[j + 3] = fmaf(f[j + 3], a, b4.w);
     }
+  } else if (a != 1.0f) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) f[j] *= a;
   }
 }
 __device__ __forceinline__ void epi_act_res(const Params& p, float (&f)[64], long long c_off, long long res_off,

@@ -328,33 +328,37 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // over the reals -- far below the bf16 rounding of the stored activation.
 // ~10 issue slots (2 MUFU) instead of ~30 for erff, which is what lets the GEMM epilogue keep
 // pace with the tensor pipe.
+// The constants below fold the -2*log2(e) of the sigmoid's exponent into the polynomial:
+//   e(x) = x * (A0 + A1 x^2 + A2 x^4) = -2 log2(e) u(x),   sigmoid(2u) = 1 / (1 + 2^e)
+//   de(x) = x * (D0 + D1 x^2 + D2 x^4) with  2 x u'(x) = x * (D0 + ...)   (D_i = 2 (2i+1) c_i)
+constexpr float kGA0 = 7.97507884e-01f * -2.8853900817779268f, kGA1 = 3.70056460e-02f * -2.8853900817779268f,
+                kGA2 = -3.51516790e-04f * -2.8853900817779268f;
+constexpr float kGD0 = 2.0f * 7.97507884e-01f, kGD1 = 6.0f * 3.70056460e-02f, kGD2 = 10.0f * -3.51516790e-04f;
 __device__ __forceinline__ float gelu_erf(float x) {
   const float xc = fminf(fmaxf(x, -7.0f), 7.0f);
   const float x2 = xc * xc;
-  const float u = xc * fmaf(x2, fmaf(x2, -3.51516790e-04f, 3.70056460e-02f), 7.97507884e-01f);
-  return x * rcp_approx(1.0f + ex2_approx(u * -2.8853900817779268f));  // x * sigmoid(2u)
+  const float e = xc * fmaf(x2, fmaf(x2, kGA2, kGA1), kGA0);
+  return x * rcp_approx(1.0f + ex2_approx(e));  // x * sigmoid(2u)
 }
-// derivative of the fit itself: s + 2 x s (1 - s) u'(x), s = sigmoid(2u)   (2 MUFU; max |err| 1.1e-4)
+// derivative of the fit itself: s + x s (1 - s) 2u'(x), s = sigmoid(2u)   (2 MUFU; max |err| 1.1e-4).
+// Outside the clamp s (1 - s) < 1e-21, so the clamped x can stand in for x in the second term.
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float xc = fminf(fmaxf(x, -7.0f), 7.0f);
   const float x2 = xc * xc;
-  const float poly = fmaf(x2, fmaf(x2, -3.51516790e-04f, 3.70056460e-02f), 7.97507884e-01f);
-  const float dpoly = fmaf(x2, fmaf(x2, 5.0f * -3.51516790e-04f, 3.0f * 3.70056460e-02f), 7.97507884e-01f);
-  const float s = rcp_approx(1.0f + ex2_approx(xc * poly * -2.8853900817779268f));
-  const float tail = (fabsf(x) < 7.0f) ? 2.0f * xc * dpoly : 0.0f;
-  return fmaf(s * (1.0f - s), tail, s);
+  const float s = rcp_approx(1.0f + ex2_approx(xc * fmaf(x2, fmaf(x2, kGA2, kGA1), kGA0)));
+  const float t = xc * fmaf(x2, fmaf(x2, kGD2, kGD1), kGD0);
+  return fmaf(fmaf(-s, s, s), t, s);
 }
 // gelu and its derivative from ONE sigmoid (forward epilogue that stores gelu'(pre) for the backward pass:
-// the data-gradient GEMM's epilogue then is a single multiply instead of ~22 issue slots + 2 MUFU per element)
+// the data-gradient GEMM's epilogue then is a single multiply instead of ~22 issue slots + 2 MUFU per element).
+// 16 issue slots per element.
 __device__ __forceinline__ void gelu_erf_both(float x, float& y, float& dy) {
   const float xc = fminf(fmaxf(x, -7.0f), 7.0f);
   const float x2 = xc * xc;
-  const float poly = fmaf(x2, fmaf(x2, -3.51516790e-04f, 3.70056460e-02f), 7.97507884e-01f);
-  const float dpoly = fmaf(x2, fmaf(x2, 5.0f * -3.51516790e-04f, 3.0f * 3.70056460e-02f), 7.97507884e-01f);
-  const float s = rcp_approx(1.0f + ex2_approx(xc * poly * -2.8853900817779268f));
-  const float tail = (fabsf(x) < 7.0f) ? 2.0f * xc * dpoly : 0.0f;
+  const float s = rcp_approx(1.0f + ex2_approx(xc * fmaf(x2, fmaf(x2, kGA2, kGA1), kGA0)));
+  const float t = xc * fmaf(x2, fmaf(x2, kGD2, kGD1), kGD0);
   y = x * s;
-  dy = fmaf(s * (1.0f - s), tail, s);
+  dy = fmaf(fmaf(-s, s, s), t, s);
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
