@@ -525,17 +525,32 @@ __device__ __forceinline__ void smem_row_to_tmem(const uint8_t* tile, int r, uin
   tmem_st_x32(taddr, v);
 }
 
+// ---- co-resident variants: 192 threads (producer, MMA issuer, 4 compute warps), 256 TMEM columns and ~97 KiB of
+// shared memory per CTA, so TWO CTAs share an SM: while one CTA's compute warps turn a sub-tile into P^T / dS^T
+// (MUFU bound) the other CTA's MMAs run, and the prologue / epilogue of one CTA (TMEM alloc, first TMA round trip,
+// gradient store) hides behind the main loop of the other -- with one 512-column CTA per SM those fixed costs
+// were ~6k of ~25k cycles per 128-row tile.
+constexpr int BWD2_THREADS = 192;
+
+// D[128 x 64] = A (smem, K-major [128 x 64]) x B^T, B = K-major [64 x 64] smem sub-tile; 4 K-steps
+__device__ __forceinline__ void mma_sA_x_subT(uint32_t d_tmem, uint32_t a_tile, uint32_t b_sub, uint32_t idesc) {
+  const uint32_t alo = (a_tile >> 4) | ((16u >> 4) << 16);
+  const uint32_t blo = (b_sub >> 4) | ((16u >> 4) << 16);
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) umma_ss(d_tmem, lean_desc(alo + kk * 2), lean_desc(blo + kk * 2), idesc, kk > 0 ? 1u : 0u);
+}
+
 namespace kv2 {
 constexpr int OFF_K = 0, OFF_V = TILE, OFF_Q = 2 * TILE, OFF_DO = OFF_Q + NST * SUBTILE,
-              OFF_STAT = OFF_DO + NST * SUBTILE;  // stat: [group][buf][128] floats
-constexpr int OFF_BAR = OFF_STAT + 2 * 2 * 128 * 4;
+              OFF_STAT = OFF_DO + NST * SUBTILE;  // stat: [buf][128] floats (lse | delta of 64 queries)
+constexpr int OFF_BAR = OFF_STAT + 2 * 128 * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 256;
-constexpr int COL_DV = COL_ACC, COL_DK = COL_ACC + 64;
-enum { B_KV = 0, B_KVT = 1, B_QFULL = 2, B_QEMPTY = B_QFULL + NST, B_STFULL = B_QEMPTY + NST,
-       B_PDSFULL = B_STFULL + 2, B_DONE = B_PDSFULL + 2, B_COUNT = B_DONE + 1 };
+constexpr int COL_ST = 0, COL_DPT = 64, COL_DV = 128, COL_DK = 192;   // P^T aliases S^T, dS^T aliases dP^T
+enum { B_KV = 0, B_QFULL = 1, B_QEMPTY = B_QFULL + NST, B_STFULL = B_QEMPTY + NST, B_PDSFULL = B_STFULL + 1,
+       B_DONE = B_PDSFULL + 1, B_COUNT = B_DONE + 1 };
 }  // namespace kv2
 
-__global__ void __launch_bounds__(BWD_THREADS, 1)
+__global__ void __launch_bounds__(BWD2_THREADS, 2)
 attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
                      const __grid_constant__ CUtensorMap mv, const __grid_constant__ CUtensorMap mdo,
                      const BwdParams p) {
@@ -560,19 +575,24 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_consta
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     mbar_init(&bars[B_KV], 1);
-    mbar_init(&bars[B_KVT], 256);
     for (int s = 0; s < NST; ++s) {
       mbar_init(&bars[B_QFULL + s], 1);
       mbar_init(&bars[B_QEMPTY + s], 1);
     }
-    for (int g = 0; g < 2; ++g) {
-      mbar_init(&bars[B_STFULL + g], 1);
-      mbar_init(&bars[B_PDSFULL + g], 128);
-    }
+    mbar_init(&bars[B_STFULL], 1);
+    mbar_init(&bars[B_PDSFULL], 128);
     mbar_init(&bars[B_DONE], 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  __syncthreads();
+  if (warp == 0 && lane == 0) {
+    // the loads of this CTA start BEFORE its TMEM allocation: when the co-resident CTA still owns the other half
+    // of TMEM (or a previous CTA has not released its columns yet) the first tiles are already in flight
+    mbar_expect_tx(&bars[B_KV], 2 * TILE);
+    tma_load_4d(smem + OFF_K, &mk, &bars[B_KV], 0, kv0, head, b);
+    tma_load_4d(smem + OFF_V, &mv, &bars[B_KV], 0, kv0, head, b);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -581,9 +601,6 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_consta
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(&bars[B_KV], 2 * TILE);
-      tma_load_4d(smem + OFF_K, &mk, &bars[B_KV], 0, kv0, head, b);
-      tma_load_4d(smem + OFF_V, &mv, &bars[B_KV], 0, kv0, head, b);
       for (int it = 0; it < n_iter; ++it) {
         const int st = it % NST;
         const uint32_t par = (it / NST) & 1;
@@ -598,74 +615,55 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_consta
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, SUB, false, false);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, D, false, true);
-      mbar_wait(&bars[B_KVT], 0);   // K, V sit in TMEM as A operands
-      tc_fence_after_sync();
-      // The tensor pipe executes MMAs in issue order, so the scores of sub-tile it may overwrite the P^T / dS^T
-      // of sub-tile it-2 (same buffer) without a barrier: the gradient MMAs that read them were issued before.
-      for (int it = 0; it <= n_iter; ++it) {
-        if (it < n_iter) {  // scores of sub-tile `it` into TMEM buffer it & 1
-          const int st = it % NST, g = it & 1;
-          mbar_wait(&bars[B_QFULL + st], (it / NST) & 1);
-          tc_fence_after_sync();
-          const uint32_t buf = tmem_base + COL_BUF + g * 128;
-          mma_tA_x_subT(buf, tmem_base + COL_A0, sbase + OFF_Q + st * SUBTILE, idesc_s);
-          mma_tA_x_subT(buf + 64, tmem_base + COL_A1, sbase + OFF_DO + st * SUBTILE, idesc_s);
-          umma_commit(&bars[B_STFULL + g]);
-        }
-        if (it > 0) {       // gradient MMAs of sub-tile it - 1
-          const int j = it - 1, st = j % NST, g = j & 1, u = j >> 1;
-          mbar_wait(&bars[B_PDSFULL + g], u & 1);
-          tc_fence_after_sync();
-          const uint32_t buf = tmem_base + COL_BUF + g * 128;
-          mma_tA_x_sub(tmem_base + COL_DV, buf, sbase + OFF_DO + st * SUBTILE, idesc_o, j > 0);        // P^T . dO
-          mma_tA_x_sub(tmem_base + COL_DK, buf + 64, sbase + OFF_Q + st * SUBTILE, idesc_o, j > 0);    // dS^T . Q
-          umma_commit(&bars[B_QEMPTY + st]);
-        }
+      mbar_wait(&bars[B_KV], 0);
+      // in-order tensor pipe: the scores of sub-tile it+1 may overwrite P^T / dS^T of sub-tile it without a
+      // barrier because the gradient MMAs that read them are issued first
+      for (int it = 0; it < n_iter; ++it) {
+        const int st = it % NST;
+        mbar_wait(&bars[B_QFULL + st], (it / NST) & 1);
+        tc_fence_after_sync();
+        mma_sA_x_subT(tmem_base + COL_ST, sbase + OFF_K, sbase + OFF_Q + st * SUBTILE, idesc_s);
+        mma_sA_x_subT(tmem_base + COL_DPT, sbase + OFF_V, sbase + OFF_DO + st * SUBTILE, idesc_s);
+        umma_commit(&bars[B_STFULL]);
+        mbar_wait(&bars[B_PDSFULL], it & 1);
+        tc_fence_after_sync();
+        mma_tA_x_sub(tmem_base + COL_DV, tmem_base + COL_ST, sbase + OFF_DO + st * SUBTILE, idesc_o, it > 0);   // P^T . dO
+        mma_tA_x_sub(tmem_base + COL_DK, tmem_base + COL_DPT, sbase + OFF_Q + st * SUBTILE, idesc_o, it > 0);   // dS^T . Q
+        umma_commit(&bars[B_QEMPTY + st]);
       }
       umma_commit(&bars[B_DONE]);
     }
   } else {
-    const int cw = warp - 2;        // 0..7
-    const int g = cw >> 2;          // compute group: sub-tiles with (it & 1) == g
     const int q = warp & 3;         // TMEM lane quarter
     const int r = q * 32 + lane;    // key row inside the tile
     const int kvi = kv0 + r;
-    const int gt = (cw & 3) * 32 + lane;  // 0..127 inside the group
+    const int gt = (warp - 2) * 32 + lane;  // 0..127
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const uint32_t t_buf = t_row + COL_BUF + g * 128;
-    float* stat = reinterpret_cast<float*>(smem + OFF_STAT) + g * 256;
+    float* stat = reinterpret_cast<float*>(smem + OFF_STAT);
     const bool lean = !p.causal && p.bias == nullptr;
     // lse (log2 domain) / delta*scale of the 64 queries of a sub-tile: thread gt < 64 owns lse[gt], the others
-    // delta[gt - 64].  The global load for the group's NEXT sub-tile is issued one sub-tile ahead so its latency
-    // hides behind the exponentials of the current one.
+    // delta[gt - 64]; the global load for the NEXT sub-tile is issued one sub-tile ahead.
     const float* stat_src = (gt < 64 ? p.lse : p.delta) + ((long long)b * p.heads + head) * p.tq;
     const float stat_mul = gt < 64 ? kLog2e : p.scale;
     auto load_stat = [&](int it) -> float {
       const int qi = (i_start + it) * SUB + (gt & 63);
       return (it < n_iter && qi < p.tq) ? stat_src[qi] * stat_mul : 0.f;
     };
-    float stat_next = load_stat(g);
-    // stationary operands -> TMEM (group 0: K, group 1: V)
-    mbar_wait(&bars[B_KV], 0);
-    smem_row_to_tmem(smem + (g == 0 ? OFF_K : OFF_V), r, t_row + (g == 0 ? COL_A0 : COL_A1));
-    tmem_st_wait();
-    tc_fence_before_sync();
-    mbar_arrive(&bars[B_KVT]);
-    for (int it = g; it < n_iter; it += 2) {
-      const int u = it >> 1;
+    float stat_next = load_stat(0);
+    for (int it = 0; it < n_iter; ++it) {
       const int q0 = (i_start + it) * SUB;
-      float* st = stat + (u & 1) * 128;
+      float* st = stat + (it & 1) * 128;
       st[gt] = stat_next;
-      stat_next = load_stat(it + 2);
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
-      mbar_wait(&bars[B_STFULL + g], u & 1);
+      stat_next = load_stat(it + 1);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&bars[B_STFULL], it & 1);
       tc_fence_after_sync();
       uint32_t pk[32], dk[32];   // P^T and dS^T of this row, bf16 pairs
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         uint32_t sv[32], dv[32];
-        tmem_ld_x32(t_buf + cc * 32, sv);
-        tmem_ld_x32(t_buf + 64 + cc * 32, dv);
+        tmem_ld_x32(t_row + COL_ST + cc * 32, sv);
+        tmem_ld_x32(t_row + COL_DPT + cc * 32, dv);
         tmem_ld_wait();
         if (lean) {
 #pragma unroll
@@ -703,49 +701,43 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_consta
           }
         }
       }
-      tmem_st_x32(t_buf, pk);        // P^T  over the first 32 columns of the scores it came from
-      tmem_st_x32(t_buf + 64, dk);   // dS^T over the first 32 columns of dP^T
+      tmem_st_x32(t_row + COL_ST, pk);     // P^T  over the first 32 columns of the scores it came from
+      tmem_st_x32(t_row + COL_DPT, dk);    // dS^T over the first 32 columns of dP^T
       tmem_st_wait();
       tc_fence_before_sync();
-      mbar_arrive(&bars[B_PDSFULL + g]);
+      mbar_arrive(&bars[B_PDSFULL]);
     }
     mbar_wait(&bars[B_DONE], 0);
     tc_fence_after_sync();
     const bool valid = kvi < p.tk;
-    if (g == 0) {
-      bf16* dst = p.dv + (long long)b * p.dv_batch_stride + (long long)kvi * p.dv_row_stride + head * D;
-      if (n_iter == 0) {
-        if (valid)
-          for (int i = 0; i < D; i += 8) *reinterpret_cast<uint4*>(dst + i) = make_uint4(0, 0, 0, 0);
-      } else {
-        store_out_row(dst, t_row + COL_DV, valid);
-      }
+    bf16* dstv = p.dv + (long long)b * p.dv_batch_stride + (long long)kvi * p.dv_row_stride + head * D;
+    bf16* dstk = p.dk + (long long)b * p.dk_batch_stride + (long long)kvi * p.dk_row_stride + head * D;
+    if (n_iter == 0) {
+      if (valid)
+        for (int i = 0; i < D; i += 8) {
+          *reinterpret_cast<uint4*>(dstv + i) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(dstk + i) = make_uint4(0, 0, 0, 0);
+        }
     } else {
-      bf16* dst = p.dk + (long long)b * p.dk_batch_stride + (long long)kvi * p.dk_row_stride + head * D;
-      if (n_iter == 0) {
-        if (valid)
-          for (int i = 0; i < D; i += 8) *reinterpret_cast<uint4*>(dst + i) = make_uint4(0, 0, 0, 0);
-      } else {
-        store_out_row(dst, t_row + COL_DK, valid);
-      }
+      store_out_row(dstv, t_row + COL_DV, valid);
+      store_out_row(dstk, t_row + COL_DK, valid);
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
 }
 
 namespace dq2 {
 constexpr int OFF_Q = 0, OFF_DO = TILE, OFF_K = 2 * TILE, OFF_V = OFF_K + NST * SUBTILE;
 constexpr int OFF_BAR = OFF_V + NST * SUBTILE;
 constexpr int SMEM_BYTES = OFF_BAR + 256;
-constexpr int NBUF = 3;                       // score / dP buffers: [64 + 128 i, +128), i < 3
-constexpr int COL_DQ = COL_BUF + NBUF * 128;  // 448
-enum { B_Q = 0, B_QT = 1, B_KFULL = 2, B_KEMPTY = B_KFULL + NST, B_SFULL = B_KEMPTY + NST, B_DSFULL = B_SFULL + NBUF,
-       B_DONE = B_DSFULL + NBUF, B_COUNT = B_DONE + 1 };
+constexpr int COL_QA = 0, COL_DOA = 32, COL_S = 64, COL_DP = 128, COL_DQ = 192;   // dS aliases S
+enum { B_Q = 0, B_QT = 1, B_KFULL = 2, B_KEMPTY = B_KFULL + NST, B_SFULL = B_KEMPTY + NST, B_DSFULL = B_SFULL + 1,
+       B_DONE = B_DSFULL + 1, B_COUNT = B_DONE + 1 };
 }  // namespace dq2
 
-__global__ void __launch_bounds__(BWD_THREADS, 1)
+__global__ void __launch_bounds__(BWD2_THREADS, 2)
 attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
                     const __grid_constant__ CUtensorMap mv, const __grid_constant__ CUtensorMap mdo,
                     const BwdParams p) {
@@ -768,19 +760,23 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     mbar_init(&bars[B_Q], 1);
-    mbar_init(&bars[B_QT], 256);
+    mbar_init(&bars[B_QT], 128);
     for (int s = 0; s < NST; ++s) {
       mbar_init(&bars[B_KFULL + s], 1);
       mbar_init(&bars[B_KEMPTY + s], 1);
     }
-    for (int i = 0; i < NBUF; ++i) {
-      mbar_init(&bars[B_SFULL + i], 1);
-      mbar_init(&bars[B_DSFULL + i], 128);
-    }
+    mbar_init(&bars[B_SFULL], 1);
+    mbar_init(&bars[B_DSFULL], 128);
     mbar_init(&bars[B_DONE], 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  __syncthreads();
+  if (warp == 0 && lane == 0) {   // first loads go out before the TMEM allocation (see the dK/dV kernel)
+    mbar_expect_tx(&bars[B_Q], 2 * TILE);
+    tma_load_4d(smem + OFF_Q, &mq, &bars[B_Q], 0, q0, head, b);
+    tma_load_4d(smem + OFF_DO, &mdo, &bars[B_Q], 0, q0, head, b);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -789,9 +785,6 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(&bars[B_Q], 2 * TILE);
-      tma_load_4d(smem + OFF_Q, &mq, &bars[B_Q], 0, q0, head, b);
-      tma_load_4d(smem + OFF_DO, &mdo, &bars[B_Q], 0, q0, head, b);
       for (int it = 0; it < n_iter; ++it) {
         const int st = it % NST;
         const uint32_t par = (it / NST) & 1;
@@ -805,59 +798,26 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, SUB, false, false);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, D, false, true);
-      SMX_PROF(long long pm_kfull = 0, pm_dsfull = 0, pm_issue_s = 0, pm_issue_dq = 0;)
-      SMX_PROF(const long long pm_start = clock64();)
       mbar_wait(&bars[B_QT], 0);    // Q, dO sit in TMEM as A operands
       tc_fence_after_sync();
-      for (int it = 0; it <= n_iter; ++it) {
-        if (it < n_iter) {
-          // sub-tile `it` uses buffer it % 3: its scores are issued while the compute groups still work on
-          // sub-tiles it-1 and it-2 (in-order tensor pipe: the dQ MMA of sub-tile it-3 that read this buffer's
-          // dS was issued earlier)
-          const int st = it % NST, g = it % NBUF;
-          SMX_PROF(const long long t0 = clock64();)
-          mbar_wait(&bars[B_KFULL + st], (it / NST) & 1);
-          SMX_PROF(const long long t1 = clock64();)
-          SMX_PROF(pm_kfull += t1 - t0;)
-          tc_fence_after_sync();
-          const uint32_t buf = tmem_base + COL_BUF + g * 128;
-          mma_tA_x_subT(buf, tmem_base + COL_A0, sbase + OFF_K + st * SUBTILE, idesc_s);
-          mma_tA_x_subT(buf + 64, tmem_base + COL_A1, sbase + OFF_V + st * SUBTILE, idesc_s);
-          umma_commit(&bars[B_SFULL + g]);
-          SMX_PROF(pm_issue_s += clock64() - t1;)
-        }
-        if (it > 1 || it == n_iter) {   // dQ of sub-tile it-2 (and the tail) -- one extra sub-tile of slack
-          for (int j = (it > 1 ? it - 2 : 0); j < (it == n_iter ? n_iter : it - 1); ++j) {
-          const int st = j % NST, g = j % NBUF, u = j / NBUF;
-          SMX_PROF(const long long t0 = clock64();)
-          mbar_wait(&bars[B_DSFULL + g], u & 1);
-          SMX_PROF(const long long t1 = clock64();)
-          SMX_PROF(pm_dsfull += t1 - t0;)
-          tc_fence_after_sync();
-          mma_tA_x_sub(tmem_base + COL_DQ, tmem_base + COL_BUF + g * 128, sbase + OFF_K + st * SUBTILE, idesc_o, j > 0);
-          umma_commit(&bars[B_KEMPTY + st]);
-          SMX_PROF(pm_issue_dq += clock64() - t1;)
-          }
-        }
+      for (int it = 0; it < n_iter; ++it) {
+        const int st = it % NST;
+        mbar_wait(&bars[B_KFULL + st], (it / NST) & 1);
+        tc_fence_after_sync();
+        mma_tA_x_subT(tmem_base + COL_S, tmem_base + COL_QA, sbase + OFF_K + st * SUBTILE, idesc_s);
+        mma_tA_x_subT(tmem_base + COL_DP, tmem_base + COL_DOA, sbase + OFF_V + st * SUBTILE, idesc_s);
+        umma_commit(&bars[B_SFULL]);
+        mbar_wait(&bars[B_DSFULL], it & 1);
+        tc_fence_after_sync();
+        mma_tA_x_sub(tmem_base + COL_DQ, tmem_base + COL_S, sbase + OFF_K + st * SUBTILE, idesc_o, it > 0);
+        umma_commit(&bars[B_KEMPTY + st]);
       }
       umma_commit(&bars[B_DONE]);
-      SMX_PROF(
-      if (p.prof) {
-        atomicAdd((unsigned long long*)p.prof + 0, (unsigned long long)pm_kfull);
-        atomicAdd((unsigned long long*)p.prof + 2, (unsigned long long)pm_dsfull);
-        atomicAdd((unsigned long long*)p.prof + 1, (unsigned long long)pm_issue_s);
-        atomicAdd((unsigned long long*)p.prof + 5, (unsigned long long)pm_issue_dq);
-        atomicAdd((unsigned long long*)p.prof + 3, (unsigned long long)(clock64() - pm_start));
-      }
-      )
     }
   } else {
-    const int cw = warp - 2;
-    const int g = cw >> 2;
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const int qi = q0 + r;
-    SMX_PROF(long long pc_sfull = 0, pc_comp = 0;)
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     float lse2 = 0.f, delta = 0.f;
     if (qi < p.tq) {
@@ -867,27 +827,23 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
     }
     const bool lean = !p.causal && p.bias == nullptr;
     const int causal_lim = p.causal ? qi + (p.tk - p.tq) : 0x7fffffff;
-    // stationary operands -> TMEM (group 0: Q, group 1: dO)
+    // stationary operands -> TMEM
     mbar_wait(&bars[B_Q], 0);
-    smem_row_to_tmem(smem + (g == 0 ? OFF_Q : OFF_DO), r, t_row + (g == 0 ? COL_A0 : COL_A1));
+    smem_row_to_tmem(smem + OFF_Q, r, t_row + COL_QA);
+    smem_row_to_tmem(smem + OFF_DO, r, t_row + COL_DOA);
     tmem_st_wait();
     tc_fence_before_sync();
     mbar_arrive(&bars[B_QT]);
-    for (int it = g; it < n_iter; it += 2) {
-      const int bi = it % NBUF, u = it / NBUF;
-      const uint32_t t_buf = t_row + COL_BUF + bi * 128;
+    for (int it = 0; it < n_iter; ++it) {
       const int k0 = it * SUB;
-      SMX_PROF(const long long t0 = clock64();)
-      mbar_wait(&bars[B_SFULL + bi], u & 1);
+      mbar_wait(&bars[B_SFULL], it & 1);
       tc_fence_after_sync();
-      SMX_PROF(const long long t2 = clock64();)
-      SMX_PROF(pc_sfull += t2 - t0;)
       uint32_t dk[32];   // dS of this row, bf16 pairs
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         uint32_t sv[32], dv[32];
-        tmem_ld_x32(t_buf + cc * 32, sv);
-        tmem_ld_x32(t_buf + 64 + cc * 32, dv);
+        tmem_ld_x32(t_row + COL_S + cc * 32, sv);
+        tmem_ld_x32(t_row + COL_DP + cc * 32, dv);
         tmem_ld_wait();
         if (lean) {
 #pragma unroll
@@ -915,28 +871,19 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
           }
         }
       }
-      tmem_st_x32(t_buf, dk);   // dS over the first 32 columns of the scores
+      tmem_st_x32(t_row + COL_S, dk);   // dS over the first 32 columns of the scores
       tmem_st_wait();
       tc_fence_before_sync();
-      mbar_arrive(&bars[B_DSFULL + bi]);
-      SMX_PROF(pc_comp += clock64() - t2;)
+      mbar_arrive(&bars[B_DSFULL]);
     }
-    SMX_PROF(
-    if (p.prof && (threadIdx.x & 127) == 64) {
-      atomicAdd((unsigned long long*)p.prof + 4, (unsigned long long)pc_sfull);
-      atomicAdd((unsigned long long*)p.prof + 6, (unsigned long long)pc_comp);
-    }
-    )
     mbar_wait(&bars[B_DONE], 0);
     tc_fence_after_sync();
-    if (g == 0) {
-      bf16* dst = p.dq + (long long)b * p.dq_batch_stride + (long long)qi * p.dq_row_stride + head * D;
-      store_out_row(dst, t_row + COL_DQ, qi < p.tq);
-    }
+    bf16* dst = p.dq + (long long)b * p.dq_batch_stride + (long long)qi * p.dq_row_stride + head * D;
+    store_out_row(dst, t_row + COL_DQ, qi < p.tq);
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
 }
 
 }  // namespace attn
@@ -999,9 +946,9 @@ extern "C" int smx_attn_bwd(const SmxAttn* a, void* stream) {
   if (make_head_map_rows(&sdo, a->d_o, a->tq, a->heads, a->batch, a->do_row_stride, a->do_batch_stride, SUB)) return -1;
   if (make_head_map_rows(&sk, a->k, a->tk, a->heads, a->batch, a->k_row_stride, a->k_batch_stride, SUB)) return -1;
   if (make_head_map_rows(&sv, a->v, a->tk, a->heads, a->batch, a->v_row_stride, a->v_batch_stride, SUB)) return -1;
-  attn_bwd_dkv2_kernel<<<gkv, BWD_THREADS, kv2::SMEM_BYTES, st>>>(sq, mk, mv, sdo, p);
+  attn_bwd_dkv2_kernel<<<gkv, BWD2_THREADS, kv2::SMEM_BYTES, st>>>(sq, mk, mv, sdo, p);
   SMX_CHECK_CUDA(cudaGetLastError());
-  attn_bwd_dq2_kernel<<<gq, BWD_THREADS, dq2::SMEM_BYTES, st>>>(mq, sk, sv, mdo, p);
+  attn_bwd_dq2_kernel<<<gq, BWD2_THREADS, dq2::SMEM_BYTES, st>>>(mq, sk, sv, mdo, p);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
