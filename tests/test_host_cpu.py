@@ -1,0 +1,78 @@
+"""CPU-side checks of the host logic that surrounds the kernels (no GPU, no compute calls into the library)."""
+import torch
+
+from speechmix_b200 import ops
+from speechmix_b200.model import handle_decoder_input_none, shift_tokens_right
+
+
+def test_t5_bucket_table_matches_transformers():
+    """ops.t5_bucket_table == hf:models/t5/modeling_t5.py:188-233 for every (query, key) offset it can see."""
+    from transformers.models.t5.modeling_t5 import T5Attention
+    for (tq, tk, bidir, off) in [(93, 93, True, 0), (64, 64, False, 0), (374, 374, True, 0), (1, 17, False, 16), (5, 300, True, 3)]:
+        tab = ops.t5_bucket_table(tq, tk, bidir, 32, 128, "cpu", q_offset=off)
+        ctx = torch.arange(tq)[:, None] + off
+        mem = torch.arange(tk)[None, :]
+        ref = T5Attention._relative_position_bucket(mem - ctx, bidirectional=bidir, num_buckets=32, max_distance=128)
+        got = tab[(mem - ctx) + (tq + off - 1)]
+        assert torch.equal(got.long(), ref), (tq, tk, bidir, off)
+
+
+def test_shift_tokens_right_and_start_ids():
+    """ref:speechmix/hf_model.py:20-34"""
+    labels = torch.tensor([[5, 6, -100, -100], [7, 8, 9, 10]])
+    out = shift_tokens_right(labels, pad_token_id=1, decoder_start_token_id=2)
+    assert out.tolist() == [[2, 5, 6, 1], [2, 7, 8, 9]]
+
+    class Cfg:
+        decoder_start_token_id = 2
+    assert handle_decoder_input_none(Cfg, batch=3).tolist() == [[2], [2], [2]]
+
+
+def test_weight_cache_epochs_and_versions():
+    """A cached working copy is reused only inside one epoch and while the master's version / address is unchanged
+    (fused optimizers do not bump versions, hence the epoch)."""
+    cache = ops.WeightCache()
+    p = torch.nn.Parameter(torch.randn(4, 4))
+    builds = []
+
+    def build(t):
+        builds.append(1)
+        return t.detach().clone()
+    a = cache.get(p, "k", build)
+    assert cache.get(p, "k", build) is a and len(builds) == 1
+    with torch.no_grad():
+        p.add_(1.0)                      # version bump -> rebuilt
+    b = cache.get(p, "k", build)
+    assert b is not a and len(builds) == 2
+    cache.invalidate()                   # epoch bump -> rebuilt even though the version did not move
+    assert cache.get(p, "k", build) is not b and len(builds) == 3
+
+
+def test_fp32_verification_mode_is_inference_only():
+    import pytest
+    with pytest.raises(RuntimeError):
+        with ops.fp32_verification():
+            pass
+    with torch.no_grad(), ops.fp32_verification():
+        from speechmix_b200 import kernels as K
+        assert K.FP32_MODE and K.act_dtype() == torch.float32
+    from speechmix_b200 import kernels as K
+    assert not K.FP32_MODE
+
+
+def test_model_classes_expose_reference_surface():
+    """ctor bookkeeping of ref:speechmix/hf_model.py:222-302 and the structural asserts of ref:test/test_hf_model.py
+    (layer counts for share_layer_ratio, no frozen params by default, weighted-sum length L+1)."""
+    from oracle import hf_oracle as O
+    from speechmix_b200 import SpeechMixAdapter, SpeechMixEED, SpeechMixFixed, SpeechMixSelf
+    spc, txc = O.speech_config("mini"), O.text_config("bart-mini")
+    for ratio, kept in ((0, 2), (0.5, 1), (1, 0)):
+        m = SpeechMixEED(spc, txc, share_layer_ratio=ratio, down_scale=2, weighted_sum=True)
+        assert m.speech_encoder_layer == kept and m.nlp_encoder_layer == 2
+        assert len(m.list_no_grad) == 0
+        assert m.weights_sum.shape == (kept + 1,)
+    assert len(SpeechMixFixed(spc, txc, down_scale=2, fixed_speech=True, fixed_nlp=True).list_grad) == 4 + 0  # bridge only
+    a = SpeechMixAdapter(spc, txc, down_scale=2)
+    assert len(a.adapters) == 4 and all(n.startswith("decoder_model.model.") for n in a.list_no_grad)
+    s = SpeechMixSelf(spc, O.text_config("t5-mini"), down_scale=2)
+    assert all(n.startswith("decoder_model.") for n in s.list_no_grad) and len(s.list_no_grad) > 0
