@@ -62,6 +62,10 @@ class _ZeroArena:
     def __init__(self):
         self.buf, self.off = {}, {}
 
+    def reset(self):
+        """Drop the current chunks (around a CUDA-graph capture: captured chunks belong to the graph's pool)."""
+        self.buf, self.off = {}, {}
+
     def zeros(self, shape, device):
         n = 1
         for d in shape:
@@ -417,7 +421,9 @@ def build_cast_table(rows, device):
     for i, (s, d, n, f) in enumerate(rows):
         tab[i] = (s, d, n, f, first)
         first += (n + chunk - 1) // chunk
-    t = torch.from_numpy(tab.view(np.uint8).copy()).to(device)
+    host = torch.from_numpy(tab.view(np.uint8).copy()).pin_memory()   # pinned: the copy is legal inside a graph capture
+    t = host.to(device, non_blocking=True)
+    t._smx_host = host                                                 # keep the staging buffer alive with the table
     return t, len(rows), first
 
 

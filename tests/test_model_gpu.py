@@ -280,3 +280,32 @@ def test_loss_tolerance_at_scale(cuda_device):
         ref = ora(x, labels=labels)
         out = mine(x.to(cuda_device), labels=labels.to(cuda_device))
     assert abs(float(out["loss"]) - float(ref["loss"])) < 1e-3, (float(out["loss"]), float(ref["loss"]))
+
+
+def test_graphed_step_matches_eager(cuda_device):
+    """speechmix_b200.graph.GraphedTrainStep (whole-step CUDA graph) must train exactly like the eager step."""
+    from speechmix_b200.graph import GraphedTrainStep
+    fx = load_fixture("mini_eed_ds2")
+    ora, x, labels = build_oracle(fx)
+    xs, ys = x.to(cuda_device), labels.to(cuda_device)
+    losses = []
+    for use_graph in (False, True):
+        m = _mine_from(ora, fx, cuda_device)
+        opt = torch.optim.AdamW(m.parameters(), lr=2e-4, weight_decay=0.0, fused=True, capturable=True)
+        hist = []
+        if use_graph:
+            g = GraphedTrainStep(m, opt, xs, ys, warmup=2)      # two eager steps (optimizer state, cast table), then 3 replays
+            hist = [float(l) for l in g.warmup_losses]
+            for _ in range(3):
+                hist.append(float(g(xs, ys)))
+        else:
+            for _ in range(5):
+                opt.zero_grad(set_to_none=True)
+                l = m(xs, labels=ys, return_model_detail=False)["loss"]
+                l.backward()
+                opt.step()
+                hist.append(float(l))
+        losses.append(hist)
+    assert losses[0][0] - losses[0][-1] > 0.3                        # it trains
+    assert len(losses[0]) == len(losses[1]) == 5
+    assert max(abs(a - b) for a, b in zip(*losses)) < 5e-3, losses   # same trajectory (atomics reorder the last bits)
