@@ -1,0 +1,103 @@
+"""Host-side pieces either side of the hot path (SURVEY.md section 8f "next" rows): the batch / collation
+contract of ref:train.py:90-133, the text-teacher target construction of ref:train.py:18-34 on the KV-cached
+decoder, and the gradual-unfreeze policy of ref:speechmix/module/utility.py:6-34 without the HF Trainer.
+Nothing here launches a kernel except ``create_self_decoder_input`` (through ``Seq2SeqLM.greedy_decode``)."""
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import torch
+from torch.nn.utils.rnn import pad_sequence
+
+
+@dataclass
+class DataCollatorWithPadding:
+    """ref:train.py:90-133.  Audio is padded with the VALUE -100 and no mask is built (the reference's contract:
+    SURVEY.md headline fact 4), label padding becomes -100 (ignored by the CE), a leading bos shared by every row
+    is cut because ``shift_tokens_right`` prepends the start token anyway.  ``tokenizer`` is only used for its
+    pad / bos ids; pre-tokenised features work with ``pad_token_id`` / ``bos_token_id`` given directly."""
+
+    tokenizer: Optional[object] = None
+    pad_token_id: Optional[int] = None
+    bos_token_id: Optional[int] = None
+    pad_to_multiple_of_labels: Optional[int] = None
+    max_length_labels: Optional[int] = None
+
+    def _ids(self):
+        pad = self.pad_token_id if self.pad_token_id is not None else getattr(self.tokenizer, "pad_token_id", None)
+        bos = self.bos_token_id if self.bos_token_id is not None else getattr(self.tokenizer, "bos_token_id", None)
+        if pad is None:
+            raise ValueError("DataCollatorWithPadding needs a pad token id")
+        return pad, bos
+
+    def _pad_ids(self, rows: Sequence[Sequence[int]], pad: int):
+        n = max(len(r) for r in rows)     # tokenizer.pad(padding=True) pads to the longest row (max_length unused)
+        if self.pad_to_multiple_of_labels:
+            m = self.pad_to_multiple_of_labels
+            n = (n + m - 1) // m * m
+        ids = torch.full((len(rows), n), pad, dtype=torch.long)
+        mask = torch.zeros((len(rows), n), dtype=torch.long)
+        for i, r in enumerate(rows):
+            ids[i, :len(r)] = torch.as_tensor(list(r), dtype=torch.long)
+            mask[i, :len(r)] = 1
+        return ids, mask
+
+    def __call__(self, features: List[Dict]) -> Dict[str, torch.Tensor]:
+        pad, bos = self._ids()
+        batch = {"input_values": pad_sequence([torch.as_tensor(f["input_values"], dtype=torch.float32) for f in features],
+                                              batch_first=True, padding_value=-100)}
+        labels, mask = self._pad_ids([f["labels"] for f in features], pad)
+        if "text_input_ids" in features[0]:
+            batch["text_input_ids"], _ = self._pad_ids([f["text_input_ids"] for f in features], pad)
+        labels = labels.masked_fill(mask.ne(1), -100)
+        if bos and bool((labels[:, 0] == bos).all()):
+            labels = labels[:, 1:]
+        batch["labels"] = labels
+        return batch
+
+
+@torch.no_grad()
+def create_self_decoder_input(decoder_model, gen_input: Sequence[int], device=None, max_length: Optional[int] = None):
+    """ref:train.py:18-34: greedy text-teacher targets -- the frozen text model decodes its own continuation of the
+    (already tokenised) input sentence; returns ``(gen_input, predicted)`` without the start token and the eos.
+    The reference re-runs the whole model for every token; here the text encoder runs once and the decoder is
+    KV-cached (``Seq2SeqLM.greedy_decode``)."""
+    cfg = decoder_model.config
+    device = decoder_model.device if device is None else device
+    ids = torch.as_tensor([list(gen_input)], dtype=torch.long, device=device)
+    steps = max(int(getattr(cfg, "max_length", 20) or 20), len(gen_input)) if max_length is None else max_length
+    was_training = decoder_model.training
+    decoder_model.eval()
+    enc, _ = decoder_model.encode(input_ids=ids)
+    out = decoder_model.greedy_decode(enc, steps + 1, eos_token_id=cfg.eos_token_id)[0].tolist()
+    decoder_model.train(was_training)
+    pred = out[1:]
+    if cfg.eos_token_id in pred:
+        pred = pred[:pred.index(cfg.eos_token_id)]
+    return list(gen_input), pred
+
+
+class FreezingPolicy:
+    """ref:speechmix/module/utility.py:6-34 (FreezingCallback) as a plain object: call ``on_epoch_begin(epoch)``.
+    During the first ``freeze_epoch`` epochs only the last ``epoch * n_params / freeze_epoch`` parameters (in
+    registration order) of ``freeze_model`` keep their original ``requires_grad``; afterwards all are restored.
+    Which weight-gradient GEMMs and all-reduce buckets exist follows from ``requires_grad`` automatically."""
+
+    def __init__(self, freeze_model, freeze_epoch=3):
+        self.freeze_model, self.freeze_epoch = freeze_model, freeze_epoch
+        self.default = {n: p.requires_grad for n, p in freeze_model.named_parameters()}
+        self.names = list(self.default)
+        self.freeze_layers = int(len(self.names) / freeze_epoch)
+
+    def on_epoch_begin(self, epoch):
+        if epoch < self.freeze_epoch:
+            k = int(self.freeze_layers * epoch)
+            release = set(self.names[-k:]) if k > 0 else set(self.names)   # names[-0:] is the whole list, as in the reference
+            for n, p in self.freeze_model.named_parameters():
+                p.requires_grad = self.default[n] if n in release else False
+        else:
+            for n, p in self.freeze_model.named_parameters():
+                p.requires_grad = self.default[n]
+
+    def on_save(self, model):
+        for _, p in model.named_parameters():
+            p.requires_grad = True

@@ -76,3 +76,36 @@ def test_model_classes_expose_reference_surface():
     assert len(a.adapters) == 4 and all(n.startswith("decoder_model.model.") for n in a.list_no_grad)
     s = SpeechMixSelf(spc, O.text_config("t5-mini"), down_scale=2)
     assert all(n.startswith("decoder_model.") for n in s.list_no_grad) and len(s.list_no_grad) > 0
+
+
+def test_collator_contract():
+    """ref:train.py:90-133: audio padded with the value -100, label padding -> -100, shared leading bos cut
+    (only for a TRUTHY bos id: the reference tests ``if self.tokenizer.bos_token_id and ...``, so bos id 0 -- BART --
+    is never cut; kept as is)."""
+    from speechmix_b200.training import DataCollatorWithPadding
+    feats = [{"input_values": [0.1, 0.2, 0.3], "labels": [3, 5, 6, 2], "text_input_ids": [3, 9, 2]},
+             {"input_values": [0.5], "labels": [3, 7, 2], "text_input_ids": [3, 8, 8, 8, 2]}]
+    b = DataCollatorWithPadding(pad_token_id=1, bos_token_id=3)(feats)
+    assert torch.allclose(b["input_values"], torch.tensor([[0.1, 0.2, 0.3], [0.5, -100.0, -100.0]]))
+    assert b["labels"].tolist() == [[5, 6, 2], [7, 2, -100]]
+    assert b["text_input_ids"].tolist() == [[3, 9, 2, 1, 1], [3, 8, 8, 8, 2]]
+    b2 = DataCollatorWithPadding(pad_token_id=1, bos_token_id=3)([{"input_values": [0.0], "labels": [4, 5]},
+                                                                  {"input_values": [0.0], "labels": [3, 5]}])
+    assert b2["labels"].tolist() == [[4, 5], [3, 5]]            # bos is only cut when EVERY row starts with it
+    b3 = DataCollatorWithPadding(pad_token_id=1, bos_token_id=0)([{"input_values": [0.0], "labels": [0, 5]}])
+    assert b3["labels"].tolist() == [[0, 5]]                    # falsy bos id: reference never cuts
+
+
+def test_freezing_policy_matches_reference_callback():
+    """ref:speechmix/module/utility.py:6-34"""
+    from speechmix_b200.training import FreezingPolicy
+    net = torch.nn.Sequential(*[torch.nn.Linear(2, 2) for _ in range(3)])     # 6 parameters
+    net[0].bias.requires_grad = False
+    pol = FreezingPolicy(net, freeze_epoch=3)
+    names = [n for n, _ in net.named_parameters()]
+    pol.on_epoch_begin(1)
+    assert [n for n, p in net.named_parameters() if p.requires_grad] == names[-2:]
+    pol.on_epoch_begin(2)
+    assert [n for n, p in net.named_parameters() if p.requires_grad] == names[-4:]
+    pol.on_epoch_begin(3)
+    assert [n for n, p in net.named_parameters() if p.requires_grad] == [n for n in names if n != "0.bias"]

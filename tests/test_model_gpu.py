@@ -357,3 +357,27 @@ def test_baseline_configs_full_size_properties(case, cuda_device):
             l1 = float(m(x[1:], labels=labels[1:])["loss"])
             l2 = float(m(x, labels=labels)["loss"])
         assert abs(0.5 * (l0 + l1) - l2) < 2e-3, (l0, l1, l2)
+
+
+@pytest.mark.parametrize("text", ["bart-mini", "t5-mini"])
+def test_create_self_decoder_input_matches_reference_loop(text, cuda_device):
+    """ref:train.py:18-34 (text-teacher target construction): the reference re-runs the text model for every new
+    token; ours encodes once and decodes KV-cached.  fp32 verification mode -> identical ids."""
+    from speechmix_b200 import ops
+    from speechmix_b200.training import create_self_decoder_input
+    fx = dict(load_fixture("mini_eed_ds2"), text=text, kwargs={"down_scale": 2}, train_mode=False)
+    ora, _, _ = build_oracle(fx)
+    mine = _mine_from(ora, fx, cuda_device).eval()
+    lm = ora.decoder_model.eval()
+    gen_input = [5, 17, 99, 300, 41, 7]
+    steps = 10
+    predicted = [lm.config.decoder_start_token_id]
+    with torch.no_grad():
+        for _ in range(steps):
+            nxt = int(torch.argmax(lm(input_ids=torch.tensor([gen_input]), decoder_input_ids=torch.tensor([predicted])).logits, -1)[:, -1])
+            if nxt == lm.config.eos_token_id:
+                break
+            predicted.append(nxt)
+    with torch.no_grad(), ops.fp32_verification():
+        got_in, got = create_self_decoder_input(mine.decoder_model, gen_input, max_length=steps)
+    assert got_in == gen_input and got == predicted[1:], (got, predicted[1:])
