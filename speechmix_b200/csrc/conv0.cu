@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(256, 2) fwd_kernel(const float* __restrict__ a
 // kernel is two streaming reads plus 11 FMAs per element.
 // partial[b][c][0] = sum dz, [2+k] = sum_t dz * x[S t + k]; [1] (= sum dz*xhat) follows algebraically in finalize.
 constexpr int BWD_FR = 1024;
-__global__ void __launch_bounds__(256, 3) bwd_kernel(const float* __restrict__ audio, const bf16* __restrict__ dy,
+__global__ void __launch_bounds__(256, 2) bwd_kernel(const float* __restrict__ audio, const bf16* __restrict__ dy,
                                                   const bf16* __restrict__ gprime, float* __restrict__ partial,
                                                   long long n_samples, long long t_out, int channels) {
   __shared__ float xs[BWD_FR * S + K];
@@ -180,21 +180,46 @@ __global__ void __launch_bounds__(256, 3) bwd_kernel(const float* __restrict__ a
 #pragma unroll
       for (int k = 0; k < K + 1; ++k) acc[j][k] = 0.f;
     const long long base = ((long long)b * t_out + t0) * channels + c0;
-#pragma unroll 4
-    for (int f = threadIdx.x / 128; f < nfr; f += lanes) {
-      const uint2 u = *reinterpret_cast<const uint2*>(dy + base + (long long)f * channels);
-      const uint2 g = *reinterpret_cast<const uint2*>(gprime + base + (long long)f * channels);
-      float win[K];
+    // frames in groups of 4 with the NEXT group's 8 loads issued before the current group's FMAs: the kernel is a
+    // latency-bound stream (2 x 8 bytes per thread and frame), so bytes in flight are what sets its bandwidth
+    constexpr int G = 4;
+    uint2 cu[G], cg[G];
+    const int f_first = threadIdx.x / 128;
+    auto load_group = [&](int f0, uint2 (&u)[G], uint2 (&g)[G]) {
 #pragma unroll
-      for (int k = 0; k < K; ++k) win[k] = xs[f * S + k];
-      const float dz[4] = {bf16_lo(u.x) * bf16_lo(g.x), bf16_hi(u.x) * bf16_hi(g.x), bf16_lo(u.y) * bf16_lo(g.y),
-                           bf16_hi(u.y) * bf16_hi(g.y)};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        acc[j][0] += dz[j];
-#pragma unroll
-        for (int k = 0; k < K; ++k) acc[j][1 + k] = fmaf(dz[j], win[k], acc[j][1 + k]);
+      for (int i = 0; i < G; ++i) {
+        const int f = f0 + i * lanes;
+        if (f < nfr) {
+          u[i] = *reinterpret_cast<const uint2*>(dy + base + (long long)f * channels);
+          g[i] = *reinterpret_cast<const uint2*>(gprime + base + (long long)f * channels);
+        } else {
+          u[i] = make_uint2(0u, 0u);
+          g[i] = make_uint2(0u, 0u);
+        }
       }
+    };
+    load_group(f_first, cu, cg);
+    for (int f0 = f_first; f0 < nfr; f0 += G * lanes) {
+      uint2 nu[G], ng[G];
+      load_group(f0 + G * lanes, nu, ng);
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        const int f = f0 + i * lanes;
+        const int fs = f < nfr ? f : 0;   // out-of-range frames carry dz = 0
+        float win[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) win[k] = xs[fs * S + k];
+        const float dz[4] = {bf16_lo(cu[i].x) * bf16_lo(cg[i].x), bf16_hi(cu[i].x) * bf16_hi(cg[i].x),
+                             bf16_lo(cu[i].y) * bf16_lo(cg[i].y), bf16_hi(cu[i].y) * bf16_hi(cg[i].y)};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[j][0] += dz[j];
+#pragma unroll
+          for (int k = 0; k < K; ++k) acc[j][1 + k] = fmaf(dz[j], win[k], acc[j][1 + k]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < G; ++i) cu[i] = nu[i], cg[i] = ng[i];
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {

@@ -235,7 +235,22 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
   const int c = (blockIdx.x * 32 + lane) * 8;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (c < cols) {
-    for (long long r = (long long)blockIdx.y * 8 + warp; r < rows; r += (long long)gridDim.y * 8) {
+    // four independent 16-byte loads in flight per thread (a latency-bound stream otherwise)
+    const long long step = (long long)gridDim.y * 8;
+    long long r = (long long)blockIdx.y * 8 + warp;
+    for (; r + 3 * step < rows; r += 4 * step) {
+      uint4 u[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) u[i] = *reinterpret_cast<const uint4*>(x + (r + i * step) * row_stride + c);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float v[8];
+        unpack_bf16x8(u[i], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      }
+    }
+    for (; r < rows; r += step) {
       float v[8];
       load8(x + r * row_stride + c, v);
 #pragma unroll
