@@ -33,7 +33,10 @@ struct BwdParams {
   const float* bias;
   float* dbias;      // [heads, tq, tk] fp32, accumulated with atomics over the batch (T5 relative position bias)
   float inv_scale;
-  long long* prof;    // optional [8] cycle counters (development): see tools/probe_attn.py prof
+  long long* prof;    // unused (development hook)
+  const bf16* o;      // forward output, for delta = rowsum(dO * O) inside the dQ kernel
+  long long o_row_stride, o_batch_stride;
+  float* delta_out;   // written by the dQ kernel (read by the dK/dV kernel that runs after it)
   bf16 *dq, *dk, *dv;
   long long dq_row_stride, dq_batch_stride, dk_row_stride, dk_batch_stride, dv_row_stride, dv_batch_stride;
   int batch, heads, tq, tk, causal;
@@ -820,15 +823,35 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
     const int qi = q0 + r;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     float lse2 = 0.f, delta = 0.f;
+    uint4 orow[8];   // this thread's row of the forward output O (for delta = rowsum(dO * O))
     if (qi < p.tq) {
       const long long idx = ((long long)b * p.heads + head) * p.tq + qi;
       lse2 = p.lse[idx] * kLog2e;
-      delta = p.delta[idx] * p.scale;
+      const uint4* po = reinterpret_cast<const uint4*>(p.o + (long long)b * p.o_batch_stride + (long long)qi * p.o_row_stride + head * D);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) orow[c] = po[c];
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) orow[c] = make_uint4(0u, 0u, 0u, 0u);
     }
     const bool lean = !p.causal && p.bias == nullptr;
     const int causal_lim = p.causal ? qi + (p.tk - p.tq) : 0x7fffffff;
     // stationary operands -> TMEM
     mbar_wait(&bars[B_Q], 0);
+    {  // delta from the dO row sitting in shared memory (128B-swizzled tile) and the O row in registers
+      const uint8_t* drow = smem + OFF_DO + r * 128;
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 dd = *reinterpret_cast<const uint4*>(drow + ((c ^ (r & 7)) << 4));
+        const uint4 oo = orow[c];
+        acc += bf16_lo(dd.x) * bf16_lo(oo.x) + bf16_hi(dd.x) * bf16_hi(oo.x) + bf16_lo(dd.y) * bf16_lo(oo.y) +
+               bf16_hi(dd.y) * bf16_hi(oo.y) + bf16_lo(dd.z) * bf16_lo(oo.z) + bf16_hi(dd.z) * bf16_hi(oo.z) +
+               bf16_lo(dd.w) * bf16_lo(oo.w) + bf16_hi(dd.w) * bf16_hi(oo.w);
+      }
+      if (qi < p.tq) p.delta_out[((long long)b * p.heads + head) * p.tq + qi] = acc;
+      delta = acc * p.scale;
+    }
     smem_row_to_tmem(smem + OFF_Q, r, t_row + COL_QA);
     smem_row_to_tmem(smem + OFF_DO, r, t_row + COL_DOA);
     tmem_st_wait();
@@ -901,15 +924,6 @@ extern "C" int smx_attn_bwd(const SmxAttn* a, void* stream) {
   if (make_head_map(&mk, a->k, a->tk, a->heads, a->batch, a->k_row_stride, a->k_batch_stride)) return -1;
   if (make_head_map(&mv, a->v, a->tk, a->heads, a->batch, a->v_row_stride, a->v_batch_stride)) return -1;
   if (make_head_map(&mdo, a->d_o, a->tq, a->heads, a->batch, a->do_row_stride, a->do_batch_stride)) return -1;
-  {
-    const long long n = (long long)a->batch * a->heads * a->tq;
-    long long g = (n + 255) / 256;
-    if (g > 148 * 8) g = 148 * 8;
-    attn_delta_kernel<<<(int)g, 256, 0, st>>>((const bf16*)a->o, (const bf16*)a->d_o, a->delta, a->o_row_stride,
-                                             a->o_batch_stride, a->do_row_stride, a->do_batch_stride, a->batch,
-                                             a->heads, a->tq);
-    SMX_CHECK_CUDA(cudaGetLastError());
-  }
   BwdParams p;
   memset(&p, 0, sizeof(p));
   p.lse = a->lse, p.delta = a->delta, p.bias = a->bias;
@@ -933,7 +947,17 @@ extern "C" int smx_attn_bwd(const SmxAttn* a, void* stream) {
   static const bool use_v1 = getenv("SMX_ATTN_BWD_V1") != nullptr;
   dim3 gkv((a->tk + 127) / 128, a->heads, a->batch);
   dim3 gq((a->tq + 127) / 128, a->heads, a->batch);
+  p.o = reinterpret_cast<const bf16*>(a->o);
+  p.o_row_stride = a->o_row_stride, p.o_batch_stride = a->o_batch_stride;
+  p.delta_out = a->delta;
   if (use_v1) {
+    const long long n = (long long)a->batch * a->heads * a->tq;
+    long long g = (n + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    attn_delta_kernel<<<(int)g, 256, 0, st>>>((const bf16*)a->o, (const bf16*)a->d_o, a->delta, a->o_row_stride,
+                                             a->o_batch_stride, a->do_row_stride, a->do_batch_stride, a->batch,
+                                             a->heads, a->tq);
+    SMX_CHECK_CUDA(cudaGetLastError());
     attn_bwd_dkv_kernel<<<gkv, BWD_THREADS, kv::SMEM_BYTES, st>>>(mq, mk, mv, mdo, p);
     SMX_CHECK_CUDA(cudaGetLastError());
     attn_bwd_dq_kernel<<<gq, BWD_THREADS, dq::SMEM_BYTES, st>>>(mq, mk, mv, mdo, p);
@@ -946,9 +970,10 @@ extern "C" int smx_attn_bwd(const SmxAttn* a, void* stream) {
   if (make_head_map_rows(&sdo, a->d_o, a->tq, a->heads, a->batch, a->do_row_stride, a->do_batch_stride, SUB)) return -1;
   if (make_head_map_rows(&sk, a->k, a->tk, a->heads, a->batch, a->k_row_stride, a->k_batch_stride, SUB)) return -1;
   if (make_head_map_rows(&sv, a->v, a->tk, a->heads, a->batch, a->v_row_stride, a->v_batch_stride, SUB)) return -1;
-  attn_bwd_dkv2_kernel<<<gkv, BWD2_THREADS, kv2::SMEM_BYTES, st>>>(sq, mk, mv, sdo, p);
-  SMX_CHECK_CUDA(cudaGetLastError());
+  // the dQ kernel also produces delta = rowsum(dO * O) (its dO tile is already in shared memory), so it runs first
   attn_bwd_dq2_kernel<<<gq, BWD2_THREADS, dq2::SMEM_BYTES, st>>>(mq, sk, sv, mdo, p);
+  SMX_CHECK_CUDA(cudaGetLastError());
+  attn_bwd_dkv2_kernel<<<gkv, BWD2_THREADS, kv2::SMEM_BYTES, st>>>(sq, mk, mv, sdo, p);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

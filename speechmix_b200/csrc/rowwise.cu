@@ -47,14 +47,33 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
   const int lane = threadIdx.x & 31;
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  // the next row's vectors are requested before the current row is reduced (latency-bound stream otherwise)
+  uint4 nx[VPL];
+  if (warp_global < rows) {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      if (c < cols) nx[i] = *reinterpret_cast<const uint4*>(x + warp_global * cols + c);
+    }
+  }
   for (long long row = warp_global; row < rows; row += nwarps) {
     float v[VPL][8];
     float s = 0.f;
+    uint4 cur[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) cur[i] = nx[i];
+    if (row + nwarps < rows) {
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int c = (i * 32 + lane) * 8;
+        if (c < cols) nx[i] = *reinterpret_cast<const uint4*>(x + (row + nwarps) * cols + c);
+      }
+    }
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int c = (i * 32 + lane) * 8;
       if (c < cols) {
-        load8(x + row * cols + c, v[i]);
+        unpack_bf16x8(cur[i], v[i]);
         if (res) {
           float r[8];
           load8(res + row * cols + c, r);
