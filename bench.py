@@ -194,12 +194,12 @@ def main():
         opt.step()
         return out["loss"]
 
-    # whole-step CUDA graph (single GPU; the multi-GPU path keeps eager launches so that the gradient
-    # all-reduce hooks fire from backward) -- disable with --no-graph
+    # CUDA graph of the step (N = 1: forward + backward + optimizer in one graph; N > 1: forward + backward in the
+    # graph, bucketed NCCL all-reduce and the optimizer step eagerly after the replay) -- disable with --no-graph
     graphed = None
-    if args.graph and world == 1:
+    if args.graph:
         from speechmix_b200.graph import GraphedTrainStep
-        graphed = GraphedTrainStep(model, opt, dev_x[0], dev_y[0], warmup=max(args.warmup, 3))
+        graphed = GraphedTrainStep(model, opt, dev_x[0], dev_y[0], warmup=max(args.warmup, 3), reducer=dp)
 
     def step(x, y):
         return graphed(x, y) if graphed is not None else step_eager(x, y)
@@ -249,10 +249,11 @@ def main():
     kernels.TIMING = None
     launches = (kernels.LAUNCHES[0] - launches0) // args.steps
     ms_e2e, _ = timed(args.steps, e2e=True)
-    if graphed is not None and rank == 0:
+    if graphed is not None:
         # kernels inside a replayed graph cannot be bracketed by events: the dominant kernel is timed in two
-        # extra EAGER steps (same process, same stream, same in-step cache / clock state) right after the timed region
-        kernels.TIMING = []
+        # extra EAGER steps (same process, same stream, same in-step cache / clock state) right after the timed
+        # region -- on every rank (the steps contain the gradient all-reduce), recorded on rank 0
+        kernels.TIMING = [] if rank == 0 else None
         for i in range(2):
             step_eager(dev_x[i & 1], dev_y[i & 1])
         torch.cuda.synchronize()
@@ -287,7 +288,8 @@ def main():
                                        "T_dec=64, fwd+loss+bwd+AdamW (BASELINE.json configs[1])" % B,
                            "global_batch": B * world, "parallelism": "dp%d" % world,
                            "l2": "per-step activations (>3 GB) exceed the 126 MB L2",
-                           "launch": "whole-step CUDA graph" if graphed is not None else "eager"},
+                           "launch": ("eager" if graphed is None else "whole-step CUDA graph" if world == 1 else
+                                      "CUDA graph (fwd+bwd) + eager NCCL all-reduce + optimizer")},
                 "e2e": {"value": audio_s / (ms_e2e * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": B * n_samples * 4 + B * T_DEC * 8, "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches) * args.steps,

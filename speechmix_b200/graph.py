@@ -33,8 +33,17 @@ class GraphedTrainStep:
         K._ARENA.reset()
         launches0 = K.LAUNCHES[0]
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss = self._eager(zero=False)
+        if self.reducer is None:
+            with torch.cuda.graph(self.graph):
+                self.loss = self._eager(zero=False)
+        else:
+            # data parallel: NCCL collectives stay OUT of the capture (forward + backward are one graph, the bucketed
+            # all-reduce and the optimizer step run eagerly after the replay)
+            self.reducer.enabled = False
+            with torch.cuda.graph(self.graph):
+                out = self.model(self.x, labels=self.y, return_model_detail=False, **self.kw)
+                out["loss"].backward()
+                self.loss = out["loss"]
         self.launches_per_step = K.LAUNCHES[0] - launches0
         K._ARENA.reset()                       # the arena chunk carved during capture belongs to the graph's pool
         ops.CACHE.invalidate()
@@ -55,4 +64,7 @@ class GraphedTrainStep:
         self.y.copy_(y, non_blocking=True)
         self.graph.replay()
         K.LAUNCHES[0] += self.launches_per_step
+        if self.reducer is not None:
+            self.reducer.reduce_inplace()
+            self.opt.step()
         return self.loss

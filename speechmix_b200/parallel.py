@@ -87,6 +87,23 @@ class GradientAllReducer:
             self.works[bi] = None
             self.pending[bi] = len(b)
 
+    def reduce_inplace(self):
+        """Average the gradients that already sit in ``param.grad`` WITHOUT re-pointing them (CUDA-graph mode: a
+        captured forward+backward writes into static gradient tensors): bucket copy-in, one all-reduce per bucket
+        (all in flight together), copy-out.  Not overlapped with backward -- the replayed graph is one launch."""
+        works = []
+        for bi, b in enumerate(self.buckets):
+            grads = [p.grad for p in b]
+            assert all(g is not None for g in grads), "reduce_inplace: every bucketed parameter needs a gradient"
+            torch._foreach_copy_(self._views(bi), grads)
+            op = dist.ReduceOp.AVG if self.avg_in_collective else dist.ReduceOp.SUM
+            works.append(dist.all_reduce(self.flat[bi], op=op, group=self.group, async_op=True))
+        for bi, b in enumerate(self.buckets):
+            works[bi].wait()
+            if not self.avg_in_collective:
+                self.flat[bi].mul_(1.0 / self.world)
+            torch._foreach_copy_([p.grad for p in b], self._views(bi))
+
     def no_sync(self):
         """Context manager for gradient-accumulation micro-steps (ref:train.py:295 gradient_accumulation_steps):
         gradients accumulate locally; the first backward outside the context reduces the accumulated sum."""
