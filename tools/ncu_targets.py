@@ -32,7 +32,7 @@ if "gemm" in which:
     b = torch.randn(N, device="cuda", generator=g)
     dy = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16)
     for _ in rounds():
-        y, pre = K.linear_fwd(x, w, bias=b, act=K.ACT_GELU, want_pre=True)   # NT + GELU epilogue
+        y, pre = K.linear_fwd(x, w, bias=b, act=K.ACT_GELU_G, want_pre=True) # NT + GELU + gelu' (the step's dominant kernel)
         K.linear_fwd(x, w)                                                    # NT plain
         K.linear_wgrad(dy, x)                                                 # TN
         K.linear_dgrad(dy, w)                                                 # NN
