@@ -37,12 +37,15 @@ class GraphedTrainStep:
             with torch.cuda.graph(self.graph):
                 self.loss = self._eager(zero=False)
         else:
-            # data parallel: NCCL collectives stay OUT of the capture (forward + backward are one graph, the bucketed
-            # all-reduce and the optimizer step run eagerly after the replay)
-            self.reducer.enabled = False
+            # data parallel: NCCL collectives stay OUT of the capture.  Forward + backward are one graph that also
+            # copies each finished gradient bucket into its flat buffer and records an external event; after the
+            # replay the bucketed all-reduce runs on a side stream gated by those events (overlapping the rest of
+            # the replayed backward) and the optimizer step runs eagerly.
+            self.reducer.begin_capture()
             with torch.cuda.graph(self.graph):
                 out = self.model(self.x, labels=self.y, return_model_detail=False, **self.kw)
                 out["loss"].backward()
+                self.reducer.end_capture()
                 self.loss = out["loss"]
         self.launches_per_step = K.LAUNCHES[0] - launches0
         K._ARENA.reset()                       # the arena chunk carved during capture belongs to the graph's pool
@@ -65,6 +68,6 @@ class GraphedTrainStep:
         self.graph.replay()
         K.LAUNCHES[0] += self.launches_per_step
         if self.reducer is not None:
-            self.reducer.reduce_inplace()
+            self.reducer.reduce_after_replay()
             self.opt.step()
         return self.loss

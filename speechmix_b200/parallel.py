@@ -27,6 +27,8 @@ class GradientAllReducer:
         # NCCL averages inside the collective; gloo (CPU tests) has no AVG -> scale after the wait
         self.avg_in_collective = dist.get_backend(group) == "nccl"
         self.enabled = True
+        self.graph_mode = False      # set by graph.GraphedTrainStep while it captures forward + backward
+        self.events, self.order, self.comm_stream = None, [], None
         params = [p for p in module.parameters() if p.requires_grad]
         params.reverse()
         cap = int(bucket_mb * 1024 * 1024 / 4)
@@ -65,7 +67,53 @@ class GradientAllReducer:
         if self.pending[bi] == 0:
             self._launch(bi)
 
+    # ---- CUDA-graph mode: the capture contains, per bucket, the copy of its gradients into the flat buffer and an
+    # EXTERNAL event record; after every replay the communication stream waits for bucket i's event and
+    # all-reduces it while the rest of the replayed backward is still running (NCCL itself stays out of the graph).
+    def begin_capture(self):
+        self.graph_mode, self.enabled = True, True
+        self.events = [torch.cuda.Event(external=True) for _ in self.buckets]
+        self.order = []
+        self.pending = [len(b) for b in self.buckets]
+        if self.comm_stream is None and self.flat[0].is_cuda:
+            self.comm_stream = torch.cuda.Stream()
+
+    def end_capture(self):
+        """still inside the capture: flush buckets whose parameters produced no gradient"""
+        for bi in range(len(self.buckets)):
+            if bi not in self.order:
+                self._launch_captured(bi)
+        self.graph_mode, self.enabled = False, False
+
+    def _launch_captured(self, bi):
+        views = self._views(bi)
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.buckets[bi]]
+        torch._foreach_copy_(views, grads)
+        for p, v in zip(self.buckets[bi], views):
+            p.grad = v
+        self.events[bi].record()
+        self.order.append(bi)
+
+    def reduce_after_replay(self):
+        """call right after graph.replay(): per-bucket all-reduce on the communication stream, gated by the events
+        the replay records; returns once the main stream is ordered after every collective."""
+        main = torch.cuda.current_stream()
+        op = dist.ReduceOp.AVG if self.avg_in_collective else dist.ReduceOp.SUM
+        works = []
+        with torch.cuda.stream(self.comm_stream):
+            for bi in self.order:
+                self.comm_stream.wait_event(self.events[bi])
+                works.append(dist.all_reduce(self.flat[bi], op=op, group=self.group, async_op=True))
+            for w in works:
+                w.wait()
+            if not self.avg_in_collective:
+                for bi in self.order:
+                    self.flat[bi].mul_(1.0 / self.world)
+        main.wait_stream(self.comm_stream)
+
     def _launch(self, bi):
+        if self.graph_mode:
+            return self._launch_captured(bi)
         views = self._views(bi)
         grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.buckets[bi]]
         torch._foreach_copy_(views, grads)
