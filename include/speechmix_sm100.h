@@ -231,7 +231,6 @@ typedef struct SmxAttn {
   int64_t do_row_stride, do_batch_stride;
   int64_t dq_row_stride, dk_row_stride, dv_row_stride;
   int64_t dq_batch_stride, dk_batch_stride, dv_batch_stride;
-  void* prof; /* optional device int64[8]: pipeline cycle counters of the backward kernels (development) */
 } SmxAttn;
 int smx_attn_fwd(const SmxAttn* a, void* stream);
 int smx_attn_bwd(const SmxAttn* a, void* stream);

@@ -46,8 +46,7 @@ class SmxAttn(Structure):
                 ("delta", c_void_p), ("dbias", c_void_p),
                 ("do_row_stride", c_int64), ("do_batch_stride", c_int64),
                 ("dq_row_stride", c_int64), ("dk_row_stride", c_int64), ("dv_row_stride", c_int64),
-                ("dq_batch_stride", c_int64), ("dk_batch_stride", c_int64), ("dv_batch_stride", c_int64),
-                ("prof", c_void_p)]
+                ("dq_batch_stride", c_int64), ("dk_batch_stride", c_int64), ("dv_batch_stride", c_int64)]
 
 
 _P = c_void_p

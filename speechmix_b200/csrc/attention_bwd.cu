@@ -33,7 +33,6 @@ struct BwdParams {
   const float* bias;
   float* dbias;      // [heads, tq, tk] fp32, accumulated with atomics over the batch (T5 relative position bias)
   float inv_scale;
-  long long* prof;    // unused (development hook)
   const bf16* o;      // forward output, for delta = rowsum(dO * O) inside the dQ kernel
   long long o_row_stride, o_batch_stride;
   float* delta_out;   // written by the dQ kernel (read by the dK/dV kernel that runs after it)
@@ -484,11 +483,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant
 // TMEM columns: [0,32) [32,64) stationary A operands | buffer b: scores [64+128b, +64), dP [128+128b, +64)
 //               | accumulators from 320.
 // =====================================================================================
-#ifdef SMX_ATTN_PROF
-#define SMX_PROF(...) __VA_ARGS__
-#else
-#define SMX_PROF(...)
-#endif
 constexpr int SUB = 64;                  // streamed rows per sub-tile
 constexpr int SUBTILE = SUB * D * 2;     // 8 KiB: a [64 x 64] bf16 tile
 constexpr int NST = 4;                   // TMA ring depth
@@ -928,7 +922,6 @@ extern "C" int smx_attn_bwd(const SmxAttn* a, void* stream) {
   memset(&p, 0, sizeof(p));
   p.lse = a->lse, p.delta = a->delta, p.bias = a->bias;
   p.dbias = a->dbias, p.inv_scale = 1.0f / a->scale;
-  p.prof = reinterpret_cast<long long*>(a->prof);
   p.dq = (bf16*)a->dq, p.dk = (bf16*)a->dk, p.dv = (bf16*)a->dv;
   p.dq_row_stride = a->dq_row_stride, p.dq_batch_stride = a->dq_batch_stride;
   p.dk_row_stride = a->dk_row_stride, p.dk_batch_stride = a->dk_batch_stride;

@@ -332,8 +332,7 @@ def attn_fwd(q, k, v, heads, causal=False, scale=None, bias=None):
     return o, lse
 
 
-def attn_bwd(do, q, k, v, o, lse, heads, causal=False, scale=None, bias=None, dq=None, dk=None, dv=None, dbias=None,
-             prof=None):
+def attn_bwd(do, q, k, v, o, lse, heads, causal=False, scale=None, bias=None, dq=None, dk=None, dv=None, dbias=None):
     """dbias: optional zero-initialised fp32 [heads, Tq, Tk]; receives sum_b dS (gradient of the additive bias)."""
     B, Tq, HD = q.shape
     Tk = k.shape[1]
@@ -346,7 +345,6 @@ def attn_bwd(do, q, k, v, o, lse, heads, causal=False, scale=None, bias=None, dq
     a = _attn_desc(q, k, v, o, lse, heads, causal, scale, bias)
     a.d_o, a.dq, a.dk, a.dv, a.delta = _ptr(do), _ptr(dq), _ptr(dk), _ptr(dv), _ptr(delta)
     a.dbias = _ptr(dbias)
-    a.prof = _ptr(prof)
     a.do_row_stride, a.do_batch_stride = do.stride(1), do.stride(0)
     a.dq_row_stride, a.dk_row_stride, a.dv_row_stride = dq.stride(1), dk.stride(1), dv.stride(1)
     a.dq_batch_stride, a.dk_batch_stride, a.dv_batch_stride = dq.stride(0), dk.stride(0), dv.stride(0)

@@ -153,30 +153,6 @@ def perf():
     return True
 
 
-@case
-def prof():
-    """pipeline cycle counters of the dQ backward kernel (SmxAttn.prof)"""
-    import torch
-    from speechmix_b200 import kernels as K
-    B, T, H = 32, 749, 12
-    g = torch.Generator(device="cuda").manual_seed(0)
-    qkv = torch.randn(B, T, 3 * H * 64, device="cuda", generator=g).to(torch.bfloat16)
-    q, k, v = qkv[..., :H * 64], qkv[..., H * 64:2 * H * 64], qkv[..., 2 * H * 64:]
-    do = torch.randn(B, T, H * 64, device="cuda", generator=g).to(torch.bfloat16)
-    o, lse = K.attn_fwd(q, k, v, H)
-    K.attn_bwd(do, q, k, v, o, lse, H)
-    prof = torch.zeros(8, device="cuda", dtype=torch.int64)
-    K.attn_bwd(do, q, k, v, o, lse, H, prof=prof)
-    torch.cuda.synchronize()
-    c = prof.tolist()
-    ctas = 6 * H * B
-    names = ["mma wait KFULL", "mma issue S+dP (8 MMA)", "mma wait DSFULL", "mma total", "cmp wait SFULL", "mma issue dQ (4 MMA)", "cmp compute"]
-    for n, v_ in zip(names, c):
-        per = v_ / ctas / (1 if n.startswith("mma") else 2)   # two compute groups report
-        print(json.dumps({"prof": n, "cycles_per_cta": per}), flush=True)
-    return True
-
-
 def main():
     if len(sys.argv) > 2 and sys.argv[1] == "--case":
         ok = CASES[sys.argv[2]]()
