@@ -161,8 +161,11 @@ int smx_unpack_conv_wgrad(const float* src, float* dst, int64_t cout, int64_t ci
 /* moments: workspace [batch][110] fp32 (window sums + second-moment matrix of the raw audio);
  * stats[b][c] = {mean, rstd} of the conv output over time, derived from the moments
  * (exact algebra, one pass over the waveform). */
-int smx_conv0_stats(const float* audio, const float* w, float* moments, float* stats, int64_t batch,
-                    int64_t n_samples, int64_t t_out, int channels, int ksize, int stride, float eps,
+#define SMX_CONV0_MOMENT_BLOCKS 32
+/* partial_ws: batch * SMX_CONV0_MOMENT_BLOCKS * 65 floats (per-block partial moments, reduced in a fixed order so
+ * that the forward pass is bit-reproducible) */
+int smx_conv0_stats(const float* audio, const float* w, float* moments, float* stats, float* partial_ws,
+                    int64_t batch, int64_t n_samples, int64_t t_out, int channels, int ksize, int stride, float eps,
                     void* stream);
 /* y = gelu(z) (bf16 [batch][t_out][channels]); gprime (optional, training) = gelu'(z) in the same layout, so
  * that the backward pass is a pure stream over dy and gprime (no convolution / activation recompute). */

@@ -70,7 +70,7 @@ SIGNATURES = {
     "smx_dact_bf16": (c_int, [_P, _P, _P, _I64, c_int, _P]),
     "smx_pack_conv_weight": (c_int, [_P, _P, _I64, _I64, _I64, _P]),
     "smx_unpack_conv_wgrad": (c_int, [_P, _P, _I64, _I64, _I64, _P]),
-    "smx_conv0_stats": (c_int, [_P, _P, _P, _P, _I64, _I64, _I64, c_int, c_int, c_int, c_float, _P]),
+    "smx_conv0_stats": (c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I64, c_int, c_int, c_int, c_float, _P]),
     "smx_conv0_gn_gelu_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, c_int, c_int, c_int, _P]),
     "smx_conv0_gn_gelu_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, c_int, c_int, c_int, _P]),
     "smx_conv0_ln_gelu_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _I64, c_int, c_int, c_int, c_float, _P]),
@@ -165,7 +165,7 @@ def load():
 # kernels launched per successful call (bench.py's gpu_launches); smx_gemm is counted by its caller
 KERNELS_PER_CALL = {"multi_cast": 1, "weightnorm_fwd": 2, "weightnorm_bwd": 2, "kl_chunk_fwd": 1, "kl_finalize": 1, "kl_chunk_bwd": 1, "self_mse_fwd": 1,
                     "self_mse_bwd": 2, "relpos_fwd": 1, "relpos_bwd": 1, "smx_attn_fwd": 1, "smx_attn_bwd": 2, "layernorm_fwd": 1, "layernorm_bwd": 1, "colsum": 1,
-                    "cast": 1, "add": 1, "dact": 1, "conv0_stats": 2, "conv0_fwd": 1, "conv0_bwd": 2, "conv0_ln_fwd": 1, "conv0_ln_bwd": 1, "conv0_wgrad": 1,
+                    "cast": 1, "add": 1, "dact": 1, "conv0_stats": 3, "conv0_fwd": 1, "conv0_bwd": 2, "conv0_ln_fwd": 1, "conv0_ln_bwd": 1, "conv0_wgrad": 1,
                     "posconv_fwd": 1, "posconv_dgrad": 1, "posconv_wgrad": 1, "embed_fwd": 1, "embed_bwd": 1,
                     "lmhead_ce_fwd": 2, "lmhead_dlogits": 1, "wsum_fwd": 1, "wsum_bwd": 1}
 LAUNCHES = [0]

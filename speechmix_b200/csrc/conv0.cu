@@ -19,9 +19,10 @@ namespace conv0 {
 
 constexpr int K = 10, S = 5;
 constexpr int NMOM = K + K * K;  // window sums + full second-moment matrix
+constexpr int NPART = K + K * (K + 1) / 2;  // what one block accumulates: window sums + upper triangle
 
 // ------------------------------------------------------------------ window moments
-__global__ void __launch_bounds__(256) moments_kernel(const float* __restrict__ audio, float* __restrict__ moments,
+__global__ void __launch_bounds__(256) moments_kernel(const float* __restrict__ audio, float* __restrict__ partial,
                                                       long long n_samples, long long t_out) {
   const int b = blockIdx.y;
   const float* x = audio + (long long)b * n_samples;
@@ -58,19 +59,29 @@ __global__ void __launch_bounds__(256) moments_kernel(const float* __restrict__ 
   if (threadIdx.x < K + K * (K + 1) / 2) {
     float v = 0.f;
     for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
-    float* mo = moments + (long long)b * NMOM;
-    if (threadIdx.x < K) {
-      atomicAdd(mo + threadIdx.x, v);
-    } else {
-      int rem = threadIdx.x - K, i = 0;
-      while (rem >= K - i) {
-        rem -= K - i;
-        ++i;
-      }
-      const int j = i + rem;
-      atomicAdd(mo + K + i * K + j, v);
-      if (i != j) atomicAdd(mo + K + j * K + i, v);
+    // per-block partial (no atomics: the forward pass stays bit-reproducible from run to run)
+    partial[((long long)b * gridDim.x + blockIdx.x) * NPART + threadIdx.x] = v;
+  }
+}
+
+// moments[b] = sum over the blocks' partials in a fixed order; expands the upper triangle to the full matrix
+__global__ void moments_reduce_kernel(const float* __restrict__ partial, float* __restrict__ moments, int blocks) {
+  const int b = blockIdx.x;
+  if (threadIdx.x >= NPART) return;
+  float v = 0.f;
+  for (int k = 0; k < blocks; ++k) v += partial[((long long)b * blocks + k) * NPART + threadIdx.x];
+  float* mo = moments + (long long)b * NMOM;
+  if (threadIdx.x < K) {
+    mo[threadIdx.x] = v;
+  } else {
+    int rem = threadIdx.x - K, i = 0;
+    while (rem >= K - i) {
+      rem -= K - i;
+      ++i;
     }
+    const int j = i + rem;
+    mo[K + i * K + j] = v;
+    mo[K + j * K + i] = v;
   }
 }
 
@@ -430,15 +441,15 @@ using namespace smx::conv0;
 
 extern "C" {
 
-int smx_conv0_stats(const float* audio, const float* w, float* moments, float* stats, int64_t batch,
+int smx_conv0_stats(const float* audio, const float* w, float* moments, float* stats, float* partial_ws, int64_t batch,
                     int64_t n_samples, int64_t t_out, int channels, int ksize, int stride, float eps, void* stream) {
   SMX_REQUIRE(ksize == K && stride == S, "conv0: only kernel 10 / stride 5 is supported (got %d/%d)", ksize, stride);
   SMX_REQUIRE(t_out == (n_samples - K) / S + 1 && t_out > 0, "conv0: inconsistent t_out");
+  SMX_REQUIRE(partial_ws != nullptr, "conv0_stats: partial_ws (batch * SMX_CONV0_MOMENT_BLOCKS * 65 floats) required");
   cudaStream_t st = (cudaStream_t)stream;
-  SMX_CHECK_CUDA(cudaMemsetAsync(moments, 0, sizeof(float) * NMOM * batch, st));
-  int gx = (int)ceil_div(t_out, 256 * 8);
-  if (gx < 1) gx = 1;
-  moments_kernel<<<dim3(gx, (unsigned)batch), 256, 0, st>>>(audio, moments, n_samples, t_out);
+  moments_kernel<<<dim3(SMX_CONV0_MOMENT_BLOCKS, (unsigned)batch), 256, 0, st>>>(audio, partial_ws, n_samples, t_out);
+  SMX_CHECK_CUDA(cudaGetLastError());
+  moments_reduce_kernel<<<(unsigned)batch, 128, 0, st>>>(partial_ws, moments, SMX_CONV0_MOMENT_BLOCKS);
   SMX_CHECK_CUDA(cudaGetLastError());
   stats_kernel<<<(int)ceil_div(batch * channels, 256), 256, 0, st>>>(w, moments, stats, (int)batch, channels, t_out, eps);
   SMX_CHECK_CUDA(cudaGetLastError());

@@ -457,8 +457,9 @@ def conv0_fwd(audio, w, gamma, beta, eps=1e-5, want_gprime=False):
     moments = torch.empty(B, 110, device=audio.device, dtype=torch.float32)
     stats = torch.empty(B, C, 2, device=audio.device, dtype=torch.float32)
     L = _L()
-    _lib.check(L.smx_conv0_stats(_ptr(audio), _ptr(w), _ptr(moments), _ptr(stats), B, n, T, C, k, s, eps, _stream()),
-               "conv0_stats")
+    part = torch.empty(B, 32, 65, device=audio.device, dtype=torch.float32)    # SMX_CONV0_MOMENT_BLOCKS x partials
+    _lib.check(L.smx_conv0_stats(_ptr(audio), _ptr(w), _ptr(moments), _ptr(stats), _ptr(part), B, n, T, C, k, s, eps,
+                                 _stream()), "conv0_stats")
     y = alloc_act(B, T, C, audio.device)
     gp = torch.empty(B, T, C, device=audio.device, dtype=BF16) if want_gprime else None
     _lib.check(L.smx_conv0_gn_gelu_fwd(_ptr(audio), _ptr(w), _ptr(gamma), _ptr(beta), _ptr(stats), _ptr(y), _ptr(gp), B, n, T,
