@@ -159,15 +159,14 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from speechmix_b200 import SpeechMixEED, kernels, parallel
-    from oracle import hf_oracle as O  # configs only (shapes of wav2vec2-base / bart-base); no oracle compute here
+    from speechmix_b200 import SpeechMixEED, kernels, parallel, presets
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    spc, txc = O.speech_config("base"), O.text_config("bart-base")
+    spc, txc = presets.speech_config("base"), presets.text_config("bart-base")
     torch.manual_seed(0)
     with contextlib.redirect_stdout(sys.stderr):   # the reference-compatible ctor prints its layer-sharing summary
         model = SpeechMixEED(spc, txc, down_scale=2)

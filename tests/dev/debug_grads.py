@@ -1,6 +1,6 @@
 """Per-parameter gradient error of a golden case vs the CPU reference restatement (development tool)."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("TRANSFORMERS_OFFLINE", "1")
 import torch

@@ -1,5 +1,5 @@
 import sys, os
-sys.path.insert(0, "/root/repo"); os.environ["TRANSFORMERS_OFFLINE"]="1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))); os.environ["TRANSFORMERS_OFFLINE"] = "1"
 import torch
 from tests._cases import build_oracle, load_fixture
 from tests.test_model_gpu import _mine_from

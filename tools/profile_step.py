@@ -9,8 +9,7 @@ sys.path.insert(0, ROOT)
 os.environ.setdefault("TRANSFORMERS_OFFLINE", "1")
 import torch  # noqa: E402
 
-from oracle import hf_oracle as O  # noqa: E402  (config shapes only)
-from speechmix_b200 import SpeechMixEED, _lib, parallel  # noqa: E402
+from speechmix_b200 import SpeechMixEED, _lib, parallel, presets as O  # noqa: E402
 
 
 def main():
