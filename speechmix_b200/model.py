@@ -220,14 +220,17 @@ class SpeechMixEED(nn.Module):
 
     @torch.no_grad()
     def generate(self, input_values, max_length=32, decoder_text_prompt=None, eos_token_id=None, use_cache=True,
-                 precision=None, **kwargs):
+                 precision=None, cuda_graph=False, **kwargs):
         """Greedy decode (ref:eval.py:12-13; loop semantics of ref:eval.ipynb cell 6).  The speech encoder, bridge
         and text encoder run once.  ``use_cache=True`` (default): KV-cached decoder, one pass per new token
         (the role of ref:speechmix/hf_model.py:314-338 ``prepare_inputs_for_generation`` + ``past_key_values``);
-        ``use_cache=False``: the notebook's full-prefix recompute.  Both return the same ids."""
+        ``use_cache=False``: the notebook's full-prefix recompute.  Both return the same ids.
+        ``cuda_graph=True`` replays the whole cached decode loop as one CUDA graph (captured once per input shape
+        and ``max_length``)."""
         if precision == "fp32":
             with ops.fp32_verification():
-                return self.generate(input_values, max_length, decoder_text_prompt, eos_token_id, use_cache)
+                return self.generate(input_values, max_length, decoder_text_prompt, eos_token_id, use_cache,
+                                     cuda_graph=cuda_graph)
         cfg = self.decoder_model.config
         eos = cfg.eos_token_id if eos_token_id is None else eos_token_id
         enc = self.encoder_model(input_values, output_hidden_states=True)
@@ -237,6 +240,8 @@ class SpeechMixEED(nn.Module):
             if decoder_text_prompt is not None:
                 inputs_embeds = self._prepend_prompt(inputs_embeds, decoder_text_prompt)
             text_enc, _ = self.decoder_model.encode(inputs_embeds=inputs_embeds)
+            if cuda_graph:
+                return self.decoder_model.greedy_decode_graph(text_enc, max_length, eos_token_id=eos)
             return self.decoder_model.greedy_decode(text_enc, max_length, eos_token_id=eos)
         dec = torch.full((B, 1), cfg.decoder_start_token_id, dtype=torch.long, device=self.device)
         done = torch.zeros(B, dtype=torch.bool, device=self.device)

@@ -155,13 +155,14 @@ class Seq2SeqLM(nn.Module):
         return x
 
     @torch.no_grad()
-    def greedy_decode(self, enc, max_length, eos_token_id=None, start_ids=None):
+    def greedy_decode(self, enc, max_length, eos_token_id=None, sync_eos=True):
         """KV-cached greedy decode over encoder states ``enc`` [B, Ts, D]: one decoder pass per new token
-        (hf:...bart.py:143-258 cache branch; loop semantics of ref:eval.ipynb cell 6).  Returns ids [B, <=max_length]."""
+        (hf:...bart.py:143-258 cache branch; loop semantics of ref:eval.ipynb cell 6).  Returns ids [B, <=max_length].
+        ``sync_eos=False`` never reads the device (no early exit): the whole loop is CUDA-graph capturable."""
         cfg, dec = self.config, self.model.decoder
         B, dev = enc.shape[0], enc.device
         eos = cfg.eos_token_id if eos_token_id is None else eos_token_id
-        ids = torch.full((B, 1), cfg.decoder_start_token_id, dtype=torch.long, device=dev) if start_ids is None else start_ids
+        ids = torch.full((B, max_length), cfg.decoder_start_token_id, dtype=torch.long, device=dev)
         D = cfg.d_model
         caches = [torch.empty(B, max_length, 2 * D, device=dev, dtype=K.act_dtype()) for _ in dec.layers]
         cross = [ops.cross_kv(enc, l.encoder_attn.k_proj.weight, l.encoder_attn.k_proj.bias, l.encoder_attn.v_proj.weight,
@@ -184,10 +185,11 @@ class Seq2SeqLM(nn.Module):
             if dec.pre_ln:
                 x = ops._ln_maybe(x, dec.layer_norm.weight, dec.layer_norm.bias, 1e-5, False)
             nxt = ops.lm_head_argmax(x, w, b, scale)
-            ids = torch.cat([ids, nxt[:, None]], dim=1)
-            done |= nxt == eos
-            if bool(done.all()):
-                break
+            ids[:, t + 1] = nxt
+            if sync_eos:
+                done |= nxt == eos
+                if bool(done.all()):
+                    return ids[:, :t + 2]
         return ids
 
     def full_logits(self, hidden):
@@ -392,13 +394,13 @@ class T5Seq2SeqLM(nn.Module):
         return K.linear_fwd(h2, ops.w16(w), None, out_f32=True, alpha=scale).view(*hidden.shape[:-1], -1)
 
     @torch.no_grad()
-    def greedy_decode(self, enc, max_length, eos_token_id=None, start_ids=None):
+    def greedy_decode(self, enc, max_length, eos_token_id=None, sync_eos=True):
         """KV-cached greedy decode (hf:...t5.py:248-345 cache branch): the relative position bias of step t is
         row t of the causal bucket table (query offset t, keys 0..t)."""
         cfg, dec = self.config, self.decoder
         B, dev = enc.shape[0], enc.device
         eos = cfg.eos_token_id if eos_token_id is None else eos_token_id
-        ids = torch.full((B, 1), cfg.decoder_start_token_id, dtype=torch.long, device=dev) if start_ids is None else start_ids
+        ids = torch.full((B, max_length), cfg.decoder_start_token_id, dtype=torch.long, device=dev)
         D, Hi = cfg.d_model, cfg.num_heads * cfg.d_kv
         caches = [torch.empty(B, max_length, 2 * Hi, device=dev, dtype=K.act_dtype()) for _ in dec.block]
         cross = [ops.cross_kv(enc, blk.layer[1].EncDecAttention.k.weight, None, blk.layer[1].EncDecAttention.v.weight, None)
@@ -422,16 +424,54 @@ class T5Seq2SeqLM(nn.Module):
                                         None, ff.layer_norm.weight, None)
             x = ops._ln_maybe(x, dec.final_layer_norm.weight, None, cfg.layer_norm_epsilon, True)
             nxt = ops.lm_head_argmax(x, w, b, scale)
-            ids = torch.cat([ids, nxt[:, None]], dim=1)
-            done |= nxt == eos
-            if bool(done.all()):
-                break
+            ids[:, t + 1] = nxt
+            if sync_eos:
+                done |= nxt == eos
+                if bool(done.all()):
+                    return ids[:, :t + 2]
         return ids
 
     forward = None  # assigned below (shared with the BART-family class)
 
 
 T5Seq2SeqLM.forward = Seq2SeqLM.forward
+
+
+@torch.no_grad()
+def _greedy_decode_graph(self, enc, max_length, eos_token_id=None):
+    """The whole KV-cached decode loop (max_length - 1 decoder passes, ~85 launches each) as ONE CUDA graph, cached
+    per (shape, max_length, weight-cache epoch); the eos early exit becomes a host-side truncation of the result."""
+    cfg = self.config
+    eos = cfg.eos_token_id if eos_token_id is None else eos_token_id
+    key = (tuple(enc.shape), enc.dtype, int(max_length), ops.CACHE.epoch, K.FP32_MODE)
+    store = self.__dict__.setdefault("_decode_graphs", {})
+    hit = store.get(key)
+    if hit is None:
+        static_enc = enc.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):          # lazy initialisation (working copies of the weights, bucket tables)
+            self.greedy_decode(static_enc, max_length, eos_token_id=eos, sync_eos=False)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out_ids = self.greedy_decode(static_enc, max_length, eos_token_id=eos, sync_eos=False)
+        store.clear()                          # one resident decode graph per model
+        hit = store[key] = (graph, static_enc, out_ids)
+    graph, static_enc, out_ids = hit
+    static_enc.copy_(enc)
+    graph.replay()
+    ids = out_ids.clone()
+    done = (ids[:, 1:] == eos).cumsum(1).clamp_(max=1).bool()        # [B, L-1]: eos seen at or before this position
+    all_done = done.all(0)
+    if bool(all_done.any()):
+        ids = ids[:, :int(all_done.float().argmax()) + 2]
+    return ids
+
+
+Seq2SeqLM.greedy_decode_graph = _greedy_decode_graph
+T5Seq2SeqLM.greedy_decode_graph = _greedy_decode_graph
 
 
 def text_from_pretrained(path_or_config):

@@ -229,6 +229,12 @@ def test_generate_kv_cache_equals_full_recompute(text, cuda_device):
     b = mine.generate(xs, max_length=12, eos_token_id=-1, use_cache=False).cpu()
     assert a.shape == b.shape == (fx["batch"], 12)
     assert torch.equal(a, b), (a.tolist(), b.tolist())
+    c = mine.generate(xs, max_length=12, eos_token_id=-1, cuda_graph=True).cpu()      # whole loop as one CUDA graph
+    c2 = mine.generate(xs * 0.5, max_length=12, eos_token_id=-1, cuda_graph=True).cpu()  # replay with new input
+    assert torch.equal(c, a) and torch.equal(c2, mine.generate(xs * 0.5, max_length=12, eos_token_id=-1).cpu())
+    eos = int(a[0, 5])                                                                 # early exit == host-side truncation
+    assert torch.equal(mine.generate(xs[:1], max_length=12, eos_token_id=eos, cuda_graph=True).cpu(),
+                       mine.generate(xs[:1], max_length=12, eos_token_id=eos).cpu())
 
 
 @pytest.mark.parametrize("name", ["mini_eed_ds2", "mini_eed_ds8_ws", "mini_large_mbart", "mini_t5"])
