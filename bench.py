@@ -198,7 +198,17 @@ def main():
     graphed = None
     if args.graph:
         from speechmix_b200.graph import GraphedTrainStep
-        graphed = GraphedTrainStep(model, opt, dev_x[0], dev_y[0], warmup=max(args.warmup, 3), reducer=dp)
+        try:
+            graphed = GraphedTrainStep(model, opt, dev_x[0], dev_y[0], warmup=max(args.warmup, 3), reducer=dp)
+        except Exception as e:   # a failed capture must not cost the measurement: fall back to eager launches
+            sys.stderr.write("CUDA graph capture failed (%r); running eager\n" % (e,))
+            graphed = None
+            kernels._ARENA.reset()
+            if dp is not None:
+                dp.graph_mode, dp.enabled = False, True
+                dp.pending = [len(b) for b in dp.buckets]
+                dp.works = [None] * len(dp.buckets)
+            opt.zero_grad(set_to_none=True)
 
     def step(x, y):
         return graphed(x, y) if graphed is not None else step_eager(x, y)

@@ -6,7 +6,6 @@ reference ``state_dict`` loads unchanged; the ``torch.nn`` leaf modules are used
 parameter containers only -- all arithmetic goes through ``ops.py`` -> libspeechmix_sm100.
 """
 import os
-import types
 
 import torch
 from torch import nn
