@@ -390,3 +390,46 @@ def test_create_self_decoder_input_matches_reference_loop(text, cuda_device):
     with torch.no_grad(), ops.fp32_verification():
         got_in, got = create_self_decoder_input(mine.decoder_model, gen_input, max_length=steps)
     assert got_in == gen_input and got == predicted[1:], (got, predicted[1:])
+
+
+def test_cfg2_shape_forward_backward_vs_oracle(cuda_device):
+    """BASELINE.json configs[1] at FULL model size and audio length (wav2vec2-base + bart-base, down_scale 2, 15 s,
+    T_dec 64) with the batch cut to 2 so that the CPU oracle finishes in seconds: loss, logits, argmax ids and the
+    gradients of one parameter per kernel family against the fp32 reference restatement (T = 749 frames: the
+    attention / LayerNorm / GEMM shapes of the bench)."""
+    from oracle import hf_oracle as O
+    from speechmix_b200 import SpeechMixEED
+    spc, txc = O.speech_config("base"), O.text_config("bart-base")
+    s, t = O.build_backbones(spc, txc, seed=0)
+    ora = O.OracleEED(s, t, down_scale=2).train()
+    O.reinit_glue(ora, 1)
+    mine = SpeechMixEED(spc, txc, down_scale=2)
+    mine.load_state_dict(ora.state_dict())
+    mine = mine.to(cuda_device).train()
+    x, labels = O.synthetic_batch(2, 15.0, 64, txc.vocab_size, seed=0)
+    ref = ora(x, labels=labels, keep_full_logits=True)
+    out = mine(x.to(cuda_device), labels=labels.to(cuda_device))
+    assert abs(float(out["loss"]) - float(ref["loss"])) < 1.5e-3, (float(out["loss"]), float(ref["loss"]))   # 128 tokens
+    assert _rel(mine.decoder_model.full_logits(out["decoder_last_hidden_state"]), ref["full_logits"]) < 2e-2
+    assert _rel(out["speech_last_hidden_state"], ref["speech_last_hidden_state"]) < 4e-2
+    assert int((out["logits"].cpu() != ref["logits"]).sum()) <= 2
+    ref["loss"].backward()
+    out["loss"].backward()
+    po, pm = dict(ora.named_parameters()), dict(mine.named_parameters())
+    probes = ["encoder_model.feature_extractor.conv_layers.0.conv.weight",
+              "encoder_model.feature_extractor.conv_layers.0.layer_norm.weight",
+              "encoder_model.feature_extractor.conv_layers.3.conv.weight",
+              "encoder_model.feature_projection.projection.weight",
+              "encoder_model.encoder.pos_conv_embed.conv.parametrizations.weight.original1",
+              "encoder_model.encoder.layers.0.attention.q_proj.weight",
+              "encoder_model.encoder.layers.5.feed_forward.intermediate_dense.weight",
+              "encoder_model.encoder.layers.11.final_layer_norm.weight",
+              "length_adapters.0.weight", "enc_to_dec_proj.weight",
+              "decoder_model.model.encoder.layers.2.fc1.weight",
+              "decoder_model.model.decoder.layers.0.encoder_attn.k_proj.weight",
+              "decoder_model.model.decoder.layers.5.fc2.bias",
+              "decoder_model.model.shared.weight"]
+    for k in probes:
+        g, r = pm[k].grad.cpu(), po[k].grad
+        rel = float((g - r).norm() / (r.norm() + 1e-20))
+        assert rel < 6e-2, (k, rel)
