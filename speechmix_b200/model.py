@@ -193,6 +193,14 @@ class SpeechMixEED(nn.Module):
         """ref:speechmix/hf_model.py:378-447.  Returns a mapping with ``loss`` and ``logits`` (= argmax
         token ids, as the reference returns them at :446) plus the model-detail breadcrumbs."""
         detail = {} if return_model_detail else None
+        dev = self.device
+        if dev.type != "cuda" or (input_values is not None and not input_values.is_cuda):
+            raise RuntimeError("speechmix_b200 runs on a B200 only (model and input_values must be on the GPU); "
+                               "there is no CPU fallback")
+        # ids may arrive on the host (the reference moves them itself: ref:speechmix/hf_model.py:541-542)
+        labels = labels.to(dev) if labels is not None else None
+        decoder_input_ids = decoder_input_ids.to(dev) if decoder_input_ids is not None else None
+        text_input_ids = text_input_ids.to(dev) if text_input_ids is not None else None
         if encoder_outputs is None and torch.is_grad_enabled():
             # a training pass: the optimizer may have moved the fp32 masters since the last pass (fused
             # optimizers do not bump tensor versions) -> refresh all bf16 working copies in one launch

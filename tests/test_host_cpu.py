@@ -109,3 +109,13 @@ def test_freezing_policy_matches_reference_callback():
     assert [n for n, p in net.named_parameters() if p.requires_grad] == names[-4:]
     pol.on_epoch_begin(3)
     assert [n for n, p in net.named_parameters() if p.requires_grad] == [n for n in names if n != "0.bias"]
+
+
+def test_cpu_call_fails_loudly():
+    """No CPU fallback: calling the model on CPU tensors raises instead of computing something else."""
+    import pytest
+    from oracle import hf_oracle as O
+    from speechmix_b200 import SpeechMixEED
+    m = SpeechMixEED(O.speech_config("mini"), O.text_config("bart-mini"), down_scale=2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.randn(1, 16000), labels=torch.randint(4, 100, (1, 4)))
