@@ -8,7 +8,8 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libspeechmix_sm100.so")
+# SMX_LIB: A/B runs of two builds of the same ABI (development aid; never a fallback -- a missing file still raises)
+LIB_PATH = os.environ.get("SMX_LIB") or os.path.join(_HERE, "libspeechmix_sm100.so")
 SMX_MAX_SEG = 4
 
 GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2

@@ -115,11 +115,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq_map, const __grid_constan
       constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, D, false, true);
       const uint32_t sbase = smem_u32(smem);
       mbar_wait(&bars[B_QFULL], 0);
-      for (int j = 0; j < n_tiles; ++j) {
+      // S_{j+1} is issued BEFORE PV_j: the softmax warps get the next score tile after one 128x128x64 MMA instead of
+      // waiting behind the P.V product as well, and PV_j runs on the tensor pipe while they take the row maxima.
+      auto issue_s = [&](int j) {
         const int slot = j & 1;
-        const uint32_t par = (j >> 1) & 1;
-        // ---- S = Q . K_j^T
-        mbar_wait(&bars[B_KFULL + slot], par);
+        mbar_wait(&bars[B_KFULL + slot], (j >> 1) & 1);
         if (j > 0) mbar_wait(&bars[B_SEMPTY], (j - 1) & 1);
         tc_fence_after_sync();
 #pragma unroll
@@ -130,8 +130,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq_map, const __grid_constan
         }
         umma_commit(&bars[B_SFULL]);
         umma_commit(&bars[B_KEMPTY + slot]);
-        // ---- PV_j = P_j . V_j
+      };
+      issue_s(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int slot = j & 1;
+        const uint32_t par = (j >> 1) & 1;
+        // ---- PV_j = P_j . V_j needs P_j; by then the softmax warps have also released the score buffer
         mbar_wait(&bars[B_PFULL], j & 1);
+        if (j + 1 < n_tiles) issue_s(j + 1);
         mbar_wait(&bars[B_VFULL + slot], par);
         mbar_wait(&bars[B_PVEMPTY + (j & 1)], par ^ 1);
         tc_fence_after_sync();
@@ -165,20 +171,43 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq_map, const __grid_constan
       mbar_wait(&bars[B_SFULL], j & 1);
       tc_fence_after_sync();
       const int c_base = j * BKV;
-      // A tile needs per-element masking only when it is cut by the key length, by the causal
-      // diagonal, or when an additive bias is present; everything else takes the lean path
-      // (1 FMNMX per score in pass 1; FFMA + MUFU.EX2 + FADD + half a pack in pass 2).
-      const bool lean = (bias_row == nullptr) && (c_base + BKV <= p.tk) &&
-                        (!p.causal || c_base + BKV - 1 <= q0 + (p.tk - p.tq));
+      // Three flavours of tile.  "lean": no bias, not cut by the causal diagonal -- the common case; its chunks of 32
+      // columns are either full, cut by the key length (one chunk of the last tile: compile-time column index against a
+      // warp-uniform count) or empty (no exponentials at all).  Everything else takes the general per-element path.
+      // Lean arithmetic per score: a third of an FMNMX3 in pass 1; half an FFMA2 + MUFU.EX2 + half an FADD2 + half a
+      // pack in pass 2.  TMEM loads are issued one chunk ahead of the arithmetic (tcgen05.wait::ld is the only stall).
+      const bool plain = (bias_row == nullptr) && (!p.causal || c_base + BKV - 1 <= q0 + (p.tk - p.tq));
+      const int n_valid = p.tk - c_base;   // >= 1; columns of this tile inside the key length (may exceed BKV)
+      const bool lean = plain && n_valid >= BKV;   // full tile
+      const bool cut = plain && n_valid < BKV;     // last tile of a ragged key length
       float tmax = -INFINITY;
       if (lean) {
+        uint32_t va[32], vb[32];
+        tmem_ld_x32(t_lane + COL_S, va);
+        tmem_ld_x32(t_lane + COL_S + 32, vb);
 #pragma unroll
-        for (int c = 0; c < BKV / 32; ++c) {
+        for (int h = 0; h < 2; ++h) {
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            tmax = fmax3(tmax, __uint_as_float(va[i]), __uint_as_float(va[i + 1]));
+            tmax = fmax3(tmax, __uint_as_float(vb[i]), __uint_as_float(vb[i + 1]));
+          }
+          if (h == 0) {
+            tmem_ld_x32(t_lane + COL_S + 64, va);
+            tmem_ld_x32(t_lane + COL_S + 96, vb);
+          }
+        }
+        tmax *= p.scale_log2;   // scale > 0
+      } else if (cut) {
+#pragma unroll 1
+        for (int c = 0; c * 32 < n_valid; ++c) {
           uint32_t v[32];
           tmem_ld_x32(t_lane + COL_S + c * 32, v);
           tmem_ld_wait();
+          const int nv = n_valid - c * 32;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, i < nv ? __uint_as_float(v[i]) : -INFINITY);
         }
         tmax *= p.scale_log2;
       } else {
@@ -200,25 +229,85 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq_map, const __grid_constan
       const float m_new = fmaxf(m, tmax);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = ex2_approx(m - m_use);
-      if (j > 0) {  // PV_{j-1} finished: its result is readable and the P buffer is free again
-        mbar_wait(&bars[B_PVFULL + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
-        tc_fence_after_sync();
-      }
       // ---- pass 2: probabilities -> smem (bf16, swizzled K-major), row sum
       float lt = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < BKV / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_x32(t_lane + COL_S + c * 32, v);
-        tmem_ld_wait();
-        float pr[32];
-        if (lean) {
+      if (lean) {
+        const f32x2 sc2 = f2_rep(p.scale_log2), nm2 = f2_rep(-m_use);
+        f32x2 lt2 = f2_rep(0.f);
+        uint32_t va[16], vb[16];   // 16-column sub-chunks, one in flight while the other is consumed
+        tmem_ld_x16(t_lane + COL_S, va);
+        if (j > 0) {  // PV_{j-1} finished: its result is readable and the P buffer is free again
+          mbar_wait(&bars[B_PVFULL + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
+          tc_fence_after_sync();
+        }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            pr[i] = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_use));
-            lt += pr[i];
+        for (int c = 0; c < BKV / 16; ++c) {
+          uint32_t (&v)[16] = (c & 1) ? vb : va;
+          tmem_ld_wait();
+          if (c + 1 < BKV / 16) tmem_ld_x16(t_lane + COL_S + (c + 1) * 16, (c & 1) ? va : vb);
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            float e0, e1;
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, nm2), e0, e1);
+            e0 = ex2_approx(e0), e1 = ex2_approx(e1);
+            lt2 = f2_add(lt2, f2_pack(e0, e1));
+            pk[i >> 1] = pack_bf16x2(e0, e1);
           }
-        } else {
+          // 16 columns = 2 chunks of 16 bytes inside K-block (c>>2), chunk index (c&3)*2 + k
+          uint8_t* blk = p_row + (c >> 2) * (BQ * 128);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int chunk = ((c & 3) * 2 + k) ^ sw;
+            *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+          }
+        }
+        float l0, l1;
+        f2_unpack(lt2, l0, l1);
+        lt = l0 + l1;
+      } else if (cut) {
+        if (j > 0) {
+          mbar_wait(&bars[B_PVFULL + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
+          tc_fence_after_sync();
+        }
+#pragma unroll 1
+        for (int c = 0; c < BKV / 32; ++c) {
+          const int nv = n_valid - c * 32;   // warp-uniform; <= 0: the chunk is all padding, no exponentials
+          uint32_t pk[16];
+          if (nv > 0) {
+            uint32_t v[32];
+            tmem_ld_x32(t_lane + COL_S + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float e0 = fmaf(__uint_as_float(v[i]), p.scale_log2, -m_use);
+              float e1 = fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_use);
+              e0 = i < nv ? ex2_approx(e0) : 0.f, e1 = i + 1 < nv ? ex2_approx(e1) : 0.f;
+              lt += e0 + e1;
+              pk[i >> 1] = pack_bf16x2(e0, e1);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[i] = 0u;
+          }
+          uint8_t* blk = p_row + (c >> 1) * (BQ * 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int chunk = ((c & 1) * 4 + k) ^ sw;
+            *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+          }
+        }
+      } else {
+        if (j > 0) {
+          mbar_wait(&bars[B_PVFULL + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
+          tc_fence_after_sync();
+        }
+#pragma unroll 1
+        for (int c = 0; c < BKV / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_x32(t_lane + COL_S + c * 32, v);
+          tmem_ld_wait();
+          float pr[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int col = c_base + c * 32 + i;
@@ -228,18 +317,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq_map, const __grid_constan
             pr[i] = (col < p.tk && col <= causal_lim) ? e : 0.f;
             lt += pr[i];
           }
-        }
-        // 32 columns = 4 chunks of 16 bytes inside K-block (c>>1), chunk index (c&1)*4 + k
-        uint8_t* blk = p_row + (c >> 1) * (BQ * 128);
+          uint8_t* blk = p_row + (c >> 1) * (BQ * 128);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint4 u;
-          u.x = pack_bf16x2(pr[k * 8 + 0], pr[k * 8 + 1]);
-          u.y = pack_bf16x2(pr[k * 8 + 2], pr[k * 8 + 3]);
-          u.z = pack_bf16x2(pr[k * 8 + 4], pr[k * 8 + 5]);
-          u.w = pack_bf16x2(pr[k * 8 + 6], pr[k * 8 + 7]);
-          const int chunk = ((c & 1) * 4 + k) ^ sw;
-          *reinterpret_cast<uint4*>(blk + chunk * 16) = u;
+          for (int k = 0; k < 4; ++k) {
+            uint4 u;
+            u.x = pack_bf16x2(pr[k * 8 + 0], pr[k * 8 + 1]);
+            u.y = pack_bf16x2(pr[k * 8 + 2], pr[k * 8 + 3]);
+            u.z = pack_bf16x2(pr[k * 8 + 4], pr[k * 8 + 5]);
+            u.w = pack_bf16x2(pr[k * 8 + 6], pr[k * 8 + 7]);
+            const int chunk = ((c & 1) * 4 + k) ^ sw;
+            *reinterpret_cast<uint4*>(blk + chunk * 16) = u;
+          }
         }
       }
       tc_fence_before_sync();
@@ -256,7 +344,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq_map, const __grid_constan
           tmem_ld_x32(ta + c * 32, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * alpha_pending + __uint_as_float(v[i]);
+          for (int i = 0; i < 32; i += 2)
+            f2_unpack(f2_fma(f2_pack(o[c * 32 + i], o[c * 32 + i + 1]), f2_rep(alpha_pending),
+                             f2_pack(__uint_as_float(v[i]), __uint_as_float(v[i + 1]))), o[c * 32 + i], o[c * 32 + i + 1]);
         }
         tc_fence_before_sync();
         mbar_arrive(&bars[B_PVEMPTY + ((j - 1) & 1)]);
@@ -274,7 +364,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq_map, const __grid_constan
         tmem_ld_x32(ta + c * 32, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * alpha_pending + __uint_as_float(v[i]);
+        for (int i = 0; i < 32; i += 2)
+            f2_unpack(f2_fma(f2_pack(o[c * 32 + i], o[c * 32 + i + 1]), f2_rep(alpha_pending),
+                             f2_pack(__uint_as_float(v[i]), __uint_as_float(v[i + 1]))), o[c * 32 + i], o[c * 32 + i + 1]);
       }
     }
     if (row < p.tq) {

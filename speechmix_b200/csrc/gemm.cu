@@ -118,6 +118,21 @@ __device__ __forceinline__ float dact_apply(int act, float v, float x) {
   return x > 0.0f ? v : 0.0f;
 }
 
+// eight elements at a time; the multiply / add flavours run as packed fp32 pairs
+__device__ __forceinline__ void dact_apply8(int act, float* f, const float* x) {
+  if (act == SMX_ACT_MULAUX) {
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) f2_unpack(f2_mul(f2_pack(f[i], f[i + 1]), f2_pack(x[i], x[i + 1])), f[i], f[i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = dact_apply(act, f[i], x[i]);
+  }
+}
+__device__ __forceinline__ void add8(float* f, const float* x) {
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) f2_unpack(f2_add(f2_pack(f[i], f[i + 1]), f2_pack(x[i], x[i + 1])), f[i], f[i + 1]);
+}
+
 // generic path: any n, any alignment (per-element predicates; only instantiated in the <FAST = false> kernels)
 __device__ __forceinline__ void epilogue_chunk_generic(const Params& p, float (&f)[32], long long c_off,
                                                        long long res_off, int col0) {
@@ -226,12 +241,13 @@ __device__ __forceinline__ void epilogue_chunk_fast(const Params& p, float (&f)[
 // ---- pieces of the fast epilogue used by the TMA-store variant (64 columns per step) ----
 __device__ __forceinline__ void epi_scale_bias(const Params& p, float (&f)[64], int col0) {
   const float a = p.alpha;
-  if (p.bias) {  // one FMA per element
+  if (p.bias) {  // one packed FMA per element pair
+    const f32x2 a2 = f2_rep(a);
 #pragma unroll
     for (int j = 0; j < 64; j += 4) {
       const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-      f[j] = fmaf(f[j], a, b4.x), f[j + 1] = fmaf(f[j + 1], a, b4.y);
-      f[j + 2] = fmaf(f[j + 2], a, b4.z), f[j + 3] = fmaf(f[j + 3], a, b4.w);
+      f2_unpack(f2_fma(f2_pack(f[j], f[j + 1]), a2, f2_pack(b4.x, b4.y)), f[j], f[j + 1]);
+      f2_unpack(f2_fma(f2_pack(f[j + 2], f[j + 3]), a2, f2_pack(b4.z, b4.w)), f[j + 2], f[j + 3]);
     }
   } else if (a != 1.0f) {
 #pragma unroll
@@ -242,7 +258,7 @@ __device__ __forceinline__ void epi_act_res(const Params& p, float (&f)[64], lon
                                             int col0) {
   if (p.act == SMX_ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < 64; ++j) f[j] = gelu_erf(f[j]);
+    for (int j = 0; j < 64; j += 2) gelu_erf2(f[j], f[j + 1]);
   } else if (p.act == SMX_ACT_RELU) {
 #pragma unroll
     for (int j = 0; j < 64; ++j) f[j] = fmaxf(f[j], 0.0f);
@@ -252,8 +268,7 @@ __device__ __forceinline__ void epi_act_res(const Params& p, float (&f)[64], lon
     for (int j = 0; j < 64; j += 8) {
       float x[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(xp + j)), x);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[j + i] = dact_apply(p.act, f[j + i], x[i]);
+      dact_apply8(p.act, f + j, x);
     }
   }
   if (p.residual) {
@@ -262,8 +277,7 @@ __device__ __forceinline__ void epi_act_res(const Params& p, float (&f)[64], lon
     for (int j = 0; j < 64; j += 8) {
       float x[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(rp + j)), x);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[j + i] += x[i];
+      add8(f + j, x);
     }
   }
 }
@@ -272,7 +286,7 @@ __device__ __forceinline__ void epi_act_res_pre(const Params& p, float (&f)[64],
                                                 long long res_off, int col0) {
   if (p.act == SMX_ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < 64; ++j) f[j] = gelu_erf(f[j]);
+    for (int j = 0; j < 64; j += 2) gelu_erf2(f[j], f[j + 1]);
   } else if (p.act == SMX_ACT_RELU) {
 #pragma unroll
     for (int j = 0; j < 64; ++j) f[j] = fmaxf(f[j], 0.0f);
@@ -281,8 +295,7 @@ __device__ __forceinline__ void epi_act_res_pre(const Params& p, float (&f)[64],
     for (int j = 0; j < 64; j += 8) {
       float x[8];
       unpack8(pre[j >> 3], x);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[j + i] = dact_apply(p.act, f[j + i], x[i]);
+      dact_apply8(p.act, f + j, x);
     }
   }
   if (p.residual) {
@@ -291,8 +304,7 @@ __device__ __forceinline__ void epi_act_res_pre(const Params& p, float (&f)[64],
     for (int j = 0; j < 64; j += 8) {
       float x[8];
       unpack8(p.tma_in == 2 ? pre[j >> 3] : __ldg(reinterpret_cast<const uint4*>(rp + j)), x);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[j + i] += x[i];
+      add8(f + j, x);
     }
   }
 }
@@ -304,16 +316,26 @@ __device__ __forceinline__ void stage_row(uint8_t* stg, int r, const float (&f)[
   for (int k = 0; k < 8; ++k) *reinterpret_cast<uint4*>(row + ((k ^ sw) << 4)) = pack8(f + k * 8);
 }
 
-// SMX_ACT_GELU_G: stage gelu'(f) (the auxiliary output) and replace f by gelu(f) in the same sweep
-__device__ __forceinline__ void stage_row_gelu_both(uint8_t* stg, int r, float (&f)[64]) {
+// the same from eight already packed 16-byte chunks: all arithmetic is done BEFORE the caller waits for the previous
+// bulk store to release the staging tile, so that wait overlaps the math instead of following it
+__device__ __forceinline__ void stage_row_packed(uint8_t* stg, int r, const uint4 (&q)[8]) {
   uint8_t* row = stg + r * 128;
   const int sw = r & 7;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) *reinterpret_cast<uint4*>(row + ((k ^ sw) << 4)) = q[k];
+}
+__device__ __forceinline__ void pack_row(const float (&f)[64], uint4 (&q)[8]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) q[k] = pack8(f + k * 8);
+}
+// SMX_ACT_GELU_G: q = packed gelu'(f) (the auxiliary output), f replaced by gelu(f) in the same sweep
+__device__ __forceinline__ void gelu_both_row(float (&f)[64], uint4 (&q)[8]) {
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     float d[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) gelu_erf_both(f[k * 8 + i], f[k * 8 + i], d[i]);
-    *reinterpret_cast<uint4*>(row + ((k ^ sw) << 4)) = pack8(d);
+    for (int i = 0; i < 8; i += 2) gelu_erf_both2(f[k * 8 + i], f[k * 8 + i + 1], d[i], d[i + 1]);
+    q[k] = pack8(d);
   }
 }
 
@@ -673,17 +695,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             if (col0 >= p.n) break;  // warp-uniform
             float f[64];
             {
-              uint32_t v[32];
+              // both 32-column loads in flight before the wait (c is even, so chunk c + 1 is always inside the
+              // accumulator; past the matrix edge it holds padding that is never stored)
+              uint32_t v[32], w[32];
               tmem_ld_x32(t_row + c * 32, v);
+              tmem_ld_x32(t_row + (c + 1) * 32, w);
               tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-              if (col0 + 32 < p.n) {
-                tmem_ld_x32(t_row + (c + 1) * 32, v);
-                tmem_ld_wait();
-              }
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[32 + j] = __uint_as_float(v[j]);
+              for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]), f[32 + j] = __uint_as_float(w[j]);
             }
             const bool two = col0 + 32 < p.n;  // n % 32 == 0 here, so the second chunk is all-or-nothing
             if (row_ok) {
@@ -698,10 +717,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             }
             if (two) {
               if (p.aux_out) {
+                uint4 q[8];
+                if (p.act == SMX_ACT_GELU_G) gelu_both_row(f, q);
+                else pack_row(f, q);
                 if (lane == 0) tma_store_wait_read<0>();
                 __syncwarp();
-                if (p.act == SMX_ACT_GELU_G) stage_row_gelu_both(stg, lane, f);
-                else stage_row(stg, lane, f);
+                stage_row_packed(stg, lane, q);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
@@ -718,12 +739,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 for (int k = 0; k < 8; ++k) pre[k] = *reinterpret_cast<const uint4*>(rowp + ((k ^ (lane & 7)) << 4));
                 __syncwarp();  // every lane has its input row before the tile is overwritten with the output
                 if (row_ok) epi_act_res_pre(p, f, pre, c_off, res_off, col0);
+                stage_row(stg, lane, f);
               } else {
                 if (row_ok) epi_act_res(p, f, c_off, res_off, col0);
+                uint4 q[8];
+                pack_row(f, q);
                 if (lane == 0) tma_store_wait_read<0>();
                 __syncwarp();
+                stage_row_packed(stg, lane, q);
               }
-              stage_row(stg, lane, f);
               fence_proxy_async_smem();
               __syncwarp();
               if (lane == 0) {

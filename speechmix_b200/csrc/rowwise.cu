@@ -37,97 +37,188 @@ __device__ __forceinline__ void loadf8(const float* p, float (&f)[8]) {
 }
 
 // ------------------------------------------------------------------ LayerNorm forward
+// Row kernels below run their fp32 arithmetic on PACKED PAIRS (FFMA2 / FMUL2 / FADD2, sm100_prims.cuh): the first
+// versions were instruction-issue-bound (ln_fwd ~21, ln_bwd ~28 warp instructions per element and lane at ~50 % of
+// the HBM roofline); pairs halve every add / multiply / FMA, and the remaining per-element work is the bf16 unpack.
+__device__ __forceinline__ void unpack_pairs(const uint4& u, f32x2 (&p)[4]) {
+  p[0] = f2_pack(bf16_lo(u.x), bf16_hi(u.x)), p[1] = f2_pack(bf16_lo(u.y), bf16_hi(u.y));
+  p[2] = f2_pack(bf16_lo(u.z), bf16_hi(u.z)), p[3] = f2_pack(bf16_lo(u.w), bf16_hi(u.w));
+}
+__device__ __forceinline__ uint32_t pack_pair(f32x2 p) {
+  float lo, hi;
+  f2_unpack(p, lo, hi);
+  return pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ uint4 pack_pairs(const f32x2 (&p)[4]) {
+  return make_uint4(pack_pair(p[0]), pack_pair(p[1]), pack_pair(p[2]), pack_pair(p[3]));
+}
+__device__ __forceinline__ void loadf_pairs(const float* q, f32x2 (&p)[4]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(q));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(q + 4));
+  p[0] = f2_pack(a.x, a.y), p[1] = f2_pack(a.z, a.w), p[2] = f2_pack(b.x, b.y), p[3] = f2_pack(b.z, b.w);
+}
+__device__ __forceinline__ float pair_sum(f32x2 p) {
+  float lo, hi;
+  f2_unpack(p, lo, hi);
+  return lo + hi;
+}
+
+// Input rows reach the warps through a per-warp ring of shared-memory slots filled by 1-D bulk copies
+// (cp.async.bulk + mbarrier): lane 0 requests the rows `stages` iterations ahead, so ~100 KB per block are in flight
+// without holding a single register -- the register-prefetch versions had one 1.5 KB row in flight per warp
+// (~24 KB per SM), which is what capped them near 3 TB/s (Little's law at ~1 us of loaded DRAM latency).
+struct RowRing {
+  uint8_t* slots;      // this warp's slots
+  uint64_t* bars;      // this warp's barriers, one per slot
+  uint32_t row_bytes;  // bytes of one row of one input
+  uint32_t slot_bytes; // n_inputs * row_bytes
+  int stages, s;
+  uint32_t parity;
+};
+__device__ __forceinline__ RowRing ring_setup(uint8_t* smem, int warp, int n_warps, int stages, int n_inputs, int cols) {
+  RowRing r;
+  r.row_bytes = (uint32_t)cols * 2u;
+  r.slot_bytes = r.row_bytes * n_inputs;
+  r.slots = smem + (size_t)warp * stages * r.slot_bytes;
+  r.bars = reinterpret_cast<uint64_t*>(smem + (size_t)n_warps * stages * r.slot_bytes) + warp * stages;
+  r.stages = stages, r.s = 0, r.parity = 0;
+  return r;
+}
+// lane 0 only: request one row of up to three inputs into slot s
+__device__ __forceinline__ void ring_issue(const RowRing& r, int s, long long row, int cols, const bf16* a, const bf16* b,
+                                           const bf16* c) {
+  uint8_t* dst = r.slots + (size_t)s * r.slot_bytes;
+  mbar_expect_tx(&r.bars[s], r.slot_bytes);
+  bulk_load_1d(dst, a + row * cols, r.row_bytes, &r.bars[s]);
+  if (b) bulk_load_1d(dst + r.row_bytes, b + row * cols, r.row_bytes, &r.bars[s]);
+  if (c) bulk_load_1d(dst + (b ? 2 : 1) * r.row_bytes, c + row * cols, r.row_bytes, &r.bars[s]);
+}
+__device__ __forceinline__ void ring_prime(const RowRing& r, int lane, long long first_row, long long row_step,
+                                           long long rows, int cols, const bf16* a, const bf16* b, const bf16* c) {
+  if (lane == 0) {
+    for (int s = 0; s < r.stages; ++s) mbar_init(&r.bars[s], 1);
+    fence_barrier_init();
+    for (int s = 0; s < r.stages; ++s) {
+      const long long row = first_row + s * row_step;
+      if (row < rows) ring_issue(r, s, row, cols, a, b, c);
+    }
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ const uint8_t* ring_wait(const RowRing& r) {
+  mbar_wait(&r.bars[r.s], r.parity);
+  return r.slots + (size_t)r.s * r.slot_bytes;
+}
+// every lane has finished reading the current slot: refill it with the row `stages` iterations ahead
+__device__ __forceinline__ void ring_release(RowRing& r, int lane, long long row, long long row_step, long long rows,
+                                             int cols, const bf16* a, const bf16* b, const bf16* c) {
+  __syncwarp();
+  if (lane == 0) {
+    const long long next = row + (long long)r.stages * row_step;
+    if (next < rows) {
+      fence_proxy_async_smem();   // generic-proxy accesses of the slot are ordered before the async-proxy refill
+      ring_issue(r, r.s, next, cols, a, b, c);
+    }
+  }
+  if (++r.s == r.stages) r.s = 0, r.parity ^= 1u;
+}
+
 // one warp per row; VPL = 16-byte vectors per lane (cols <= VPL*256)
 template <int VPL>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ res,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      bf16* __restrict__ y, bf16* __restrict__ sum_out,
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                                     long long rows, int cols, float eps, int rms_only, int act) {
-  const int lane = threadIdx.x & 31;
-  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-  // the next row's vectors are requested before the current row is reduced (latency-bound stream otherwise)
-  uint4 nx[VPL];
-  if (warp_global < rows) {
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int c = (i * 32 + lane) * 8;
-      if (c < cols) nx[i] = *reinterpret_cast<const uint4*>(x + warp_global * cols + c);
-    }
-  }
+                                                     long long rows, int cols, float eps, int rms_only, int act,
+                                                     int stages) {
+  extern __shared__ __align__(128) uint8_t ring_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long warp_global = (long long)blockIdx.x * 8 + warp;
+  const long long nwarps = (long long)gridDim.x * 8;
+  const float inv_cols = 1.0f / cols;
+  RowRing ring = ring_setup(ring_smem, warp, 8, stages, res ? 2 : 1, cols);
+  ring_prime(ring, lane, warp_global, nwarps, rows, cols, x, res, nullptr);
+
   for (long long row = warp_global; row < rows; row += nwarps) {
-    float v[VPL][8];
-    float s = 0.f;
-    uint4 cur[VPL];
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) cur[i] = nx[i];
-    if (row + nwarps < rows) {
-#pragma unroll
-      for (int i = 0; i < VPL; ++i) {
-        const int c = (i * 32 + lane) * 8;
-        if (c < cols) nx[i] = *reinterpret_cast<const uint4*>(x + (row + nwarps) * cols + c);
-      }
-    }
+    const uint8_t* slot = ring_wait(ring);
+    f32x2 v[VPL][4];
+    f32x2 s2 = f2_rep(0.f);
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int c = (i * 32 + lane) * 8;
       if (c < cols) {
-        unpack_bf16x8(cur[i], v[i]);
+        unpack_pairs(*reinterpret_cast<const uint4*>(slot + c * 2), v[i]);
         if (res) {
-          float r[8];
-          load8(res + row * cols + c, r);
+          f32x2 r[4];
+          unpack_pairs(*reinterpret_cast<const uint4*>(slot + ring.row_bytes + c * 2), r);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[i][j] += r[j];
+          for (int j = 0; j < 4; ++j) v[i][j] = f2_add(v[i][j], r[j]);
         }
-        if (sum_out) {
-          store8(sum_out + row * cols + c, v[i]);
-          // keep the statistics consistent with what backward will re-read
-          float t[8];
-          load8(sum_out + row * cols + c, t);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[i][j] = t[j];
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s += v[i][j];
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) v[i][j] = f2_rep(0.f);
+      }
+    }
+    ring_release(ring, lane, row, nwarps, rows, cols, x, res, nullptr);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      if (c < cols) {
+        if (sum_out) {
+          // keep the statistics consistent with what backward will re-read: round to bf16 first
+          const uint4 u = pack_pairs(v[i]);
+          *reinterpret_cast<uint4*>(sum_out + row * cols + c) = u;
+          unpack_pairs(u, v[i]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s2 = f2_add(s2, v[i][j]);
       }
     }
     float mean = 0.f;
-    if (!rms_only) mean = warp_sum(s) / cols;
-    float sq = 0.f;
+    if (!rms_only) mean = warp_sum(pair_sum(s2)) * inv_cols;
+    const f32x2 nmean = f2_rep(-mean);
+    f32x2 sq2 = f2_rep(0.f);
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int c = (i * 32 + lane) * 8;
       if (c < cols) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float d = v[i][j] - mean;
-          sq += d * d;
+        for (int j = 0; j < 4; ++j) {
+          v[i][j] = f2_add(v[i][j], nmean);   // v now holds x - mean
+          sq2 = f2_fma(v[i][j], v[i][j], sq2);
         }
       }
     }
-    const float rstd = rsqrtf(warp_sum(sq) / cols + eps);
+    const float rstd = rsqrtf(warp_sum(pair_sum(sq2)) * inv_cols + eps);
     if (lane == 0) {
       if (mean_out) mean_out[row] = mean;
       if (rstd_out) rstd_out[row] = rstd;
     }
+    const f32x2 rstd2 = f2_rep(rstd);
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int c = (i * 32 + lane) * 8;
       if (c < cols) {
-        float g[8], b[8], o[8];
-        loadf8(gamma + c, g);
-        if (beta) loadf8(beta + c, b);
+        f32x2 g[4], b[4], o[4];
+        loadf_pairs(gamma + c, g);
+        if (beta) {
+          loadf_pairs(beta + c, b);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + (beta ? b[j] : 0.f);
+          for (int j = 0; j < 4; ++j) b[j] = f2_rep(0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = f2_fma(f2_mul(v[i][j], rstd2), g[j], b[j]);
         if (act == SMX_ACT_GELU) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = gelu_erf(o[j]);
+          for (int j = 0; j < 4; ++j) {
+            float lo, hi;
+            f2_unpack(o[j], lo, hi);
+            gelu_erf2(lo, hi);
+            o[j] = f2_pack(lo, hi);
+          }
         }
-        store8(y + row * cols + c, o);
+        *reinterpret_cast<uint4*>(y + row * cols + c) = pack_pairs(o);
       }
     }
   }
@@ -136,94 +227,100 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
 // ------------------------------------------------------------------ LayerNorm backward
 // One warp per row, rows strided over a persistent grid; parameter gradients (and, optionally, the column sums
 // of dx = the bias gradient of the linear layer in front of a post-LN block) accumulate in registers and are
-// reduced once per block.  Between the statistics pass and the dx pass a row is held as the PACKED bf16 it was
-// loaded as (2 x 4 registers per 8 elements) instead of two fp32 copies, which is what keeps the kernel at
-// two resident 256-thread blocks per SM -- an HBM-bound row kernel needs the
-// warps to cover the memory latency (the first version: 159 registers, 8 warps per SM, 29 % of HBM peak).
+// reduced once per block.  dy / x (/ the residual-branch gradient) of a row stay in the warp's ring slot between the
+// statistics pass and the dx pass, so neither pass holds a register copy of the row.
 template <int VPL, bool WITH_CS>
 __global__ void __launch_bounds__(256, (VPL <= 3 ? 2 : 1))
 ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ beta, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
               const bf16* __restrict__ dres, bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
-              float* __restrict__ dx_colsum, long long rows, int cols, int rms_only, int act) {
+              float* __restrict__ dx_colsum, long long rows, int cols, int rms_only, int act, int stages) {
+  extern __shared__ __align__(128) uint8_t ring_smem[];
   __shared__ float red[8][32 * 8 + 1];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const long long warp_global = (long long)blockIdx.x * 8 + warp;
   const long long nwarps = (long long)gridDim.x * 8;
-  float ag[VPL][8], ab[VPL][8], ac[WITH_CS ? VPL : 1][8];
+  const float inv_cols = 1.0f / cols;
+  RowRing ring = ring_setup(ring_smem, warp, 8, stages, dres ? 3 : 2, cols);
+  ring_prime(ring, lane, warp_global, nwarps, rows, cols, dy, x, dres);
+  f32x2 ag[VPL][4], ab[VPL][4], ac[WITH_CS ? VPL : 1][4];
 #pragma unroll
   for (int i = 0; i < VPL; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      ag[i][j] = 0.f, ab[i][j] = 0.f;
-      if (WITH_CS) ac[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) {
+      ag[i][j] = f2_rep(0.f), ab[i][j] = f2_rep(0.f);
+      if (WITH_CS) ac[i][j] = f2_rep(0.f);
     }
 
   for (long long row = warp_global; row < rows; row += nwarps) {
     const float mean = rms_only ? 0.f : mean_in[row];
     const float rstd = rstd_in[row];
-    uint4 dp[VPL], xp[VPL];
-    float s1 = 0.f, s2 = 0.f;
+    const f32x2 rstd2 = f2_rep(rstd), nmr = f2_rep(-mean * rstd);   // xhat = x * rstd - mean * rstd
+    uint8_t* slot = const_cast<uint8_t*>(ring_wait(ring));
+    f32x2 s1p = f2_rep(0.f), s2p = f2_rep(0.f);
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int c = (i * 32 + lane) * 8;
       if (c < cols) {
-        dp[i] = *reinterpret_cast<const uint4*>(dy + row * cols + c);
-        xp[i] = *reinterpret_cast<const uint4*>(x + row * cols + c);
-      }
-    }
+        f32x2 d[4], h[4], gm[4];
+        unpack_pairs(*reinterpret_cast<const uint4*>(slot + c * 2), d);
+        unpack_pairs(*reinterpret_cast<const uint4*>(slot + ring.row_bytes + c * 2), h);
+        loadf_pairs(gamma + c, gm);
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int c = (i * 32 + lane) * 8;
-      if (c < cols) {
-        float d[8], xh[8], gm[8];
-        unpack_bf16x8(dp[i], d);
-        unpack_bf16x8(xp[i], xh);
-        loadf8(gamma + c, gm);
+        for (int j = 0; j < 4; ++j) h[j] = f2_fma(h[j], rstd2, nmr);
         if (act == SMX_ACT_GELU) {  // y = gelu(z), z = xhat*gamma + beta: fold gelu'(z) into dy first
-          float bt[8];
-          loadf8(beta + c, bt);
+          f32x2 bt[4];
+          loadf_pairs(beta + c, bt);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) d[j] *= gelu_erf_grad(fmaf((xh[j] - mean) * rstd, gm[j], bt[j]));
-          dp[i] = pack_bf16x8(d);   // the dx pass re-reads the folded gradient
+          for (int j = 0; j < 4; ++j) {
+            float z0, z1;
+            f2_unpack(f2_fma(h[j], gm[j], bt[j]), z0, z1);
+            d[j] = f2_mul(d[j], f2_pack(gelu_erf_grad(z0), gelu_erf_grad(z1)));
+          }
+          *reinterpret_cast<uint4*>(slot + c * 2) = pack_pairs(d);   // the dx pass re-reads the folded gradient
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float h = (xh[j] - mean) * rstd;
-          ag[i][j] = fmaf(d[j], h, ag[i][j]);
-          ab[i][j] += d[j];
-          const float gj = d[j] * gm[j];
-          s1 += gj;
-          s2 = fmaf(gj, h, s2);
+        for (int j = 0; j < 4; ++j) {
+          ag[i][j] = f2_fma(d[j], h[j], ag[i][j]);
+          ab[i][j] = f2_add(ab[i][j], d[j]);
+          const f32x2 gj = f2_mul(d[j], gm[j]);
+          s1p = f2_add(s1p, gj);
+          s2p = f2_fma(gj, h[j], s2p);
         }
       }
     }
-    s1 = rms_only ? 0.f : warp_sum(s1) / cols;
-    s2 = warp_sum(s2) / cols;
+    const float s1 = rms_only ? 0.f : warp_sum(pair_sum(s1p)) * inv_cols;
+    const float s2 = warp_sum(pair_sum(s2p)) * inv_cols;
+    // dx = rstd * (dy*gamma - s1 - xhat*s2) = (dy*gamma + xhat*(-s2)) * rstd + (-s1*rstd)
+    const f32x2 ns2 = f2_rep(-s2), ns1r = f2_rep(-s1 * rstd);
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int c = (i * 32 + lane) * 8;
       if (c < cols) {
-        float d[8], xh[8], gm[8], o[8];
-        unpack_bf16x8(dp[i], d);
-        unpack_bf16x8(xp[i], xh);
-        loadf8(gamma + c, gm);
+        f32x2 d[4], h[4], gm[4], o[4];
+        unpack_pairs(*reinterpret_cast<const uint4*>(slot + c * 2), d);   // each lane re-reads its own columns
+        unpack_pairs(*reinterpret_cast<const uint4*>(slot + ring.row_bytes + c * 2), h);
+        loadf_pairs(gamma + c, gm);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rstd * (d[j] * gm[j] - s1 - (xh[j] - mean) * rstd * s2);
-        if (dres) {
-          float r[8];
-          load8(dres + row * cols + c, r);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += r[j];
+        for (int j = 0; j < 4; ++j) {
+          h[j] = f2_fma(h[j], rstd2, nmr);
+          o[j] = f2_fma(f2_fma(h[j], ns2, f2_mul(d[j], gm[j])), rstd2, ns1r);
         }
-        store8(dx + row * cols + c, o);
+        if (dres) {
+          f32x2 r[4];
+          unpack_pairs(*reinterpret_cast<const uint4*>(slot + 2 * ring.row_bytes + c * 2), r);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = f2_add(o[j], r[j]);
+        }
+        *reinterpret_cast<uint4*>(dx + row * cols + c) = pack_pairs(o);
         if (WITH_CS) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) ac[i][j] += o[j];
+          for (int j = 0; j < 4; ++j) ac[i][j] = f2_add(ac[i][j], o[j]);
         }
       }
     }
+    ring_release(ring, lane, row, nwarps, rows, cols, dy, x, dres);
   }
   // block reduction of the column accumulators, then one atomic per column per block
 #pragma unroll
@@ -234,7 +331,11 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
       if (dst == nullptr) continue;
       __syncthreads();
 #pragma unroll
-      for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = pass == 0 ? ag[i][j] : (pass == 1 ? ab[i][j] : ac[WITH_CS ? i : 0][j]);
+      for (int j = 0; j < 4; ++j) {
+        float lo, hi;
+        f2_unpack(pass == 0 ? ag[i][j] : (pass == 1 ? ab[i][j] : ac[WITH_CS ? i : 0][j]), lo, hi);
+        red[warp][lane * 8 + 2 * j] = lo, red[warp][lane * 8 + 2 * j + 1] = hi;
+      }
       __syncthreads();
       const int col_local = threadIdx.x;  // 256 threads, 256 columns of this vector slot
       float t = 0.f;
@@ -539,6 +640,35 @@ static int grid_for(long long work_items, int block, int max_waves = 8) {
   return (int)g;
 }
 
+static bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
+
+// Shared-memory ring of the LayerNorm kernels: as many row slots per warp as fit ~96 KB per block (2..8), two blocks
+// per SM -> up to ~190 KB of rows in flight per SM.  max_blocks_per_sm == 0: free grid (fwd), otherwise a persistent
+// wave of that many resident blocks (bwd keeps column accumulators in registers).
+struct RingPlan {
+  int grid, stages;
+  size_t smem;
+};
+static RingPlan ring_plan(long long rows, long long cols, int n_inputs, int max_blocks_per_sm) {
+  const size_t slot = (size_t)cols * 2 * n_inputs;       // one row of every input
+  int stages = (int)((96 * 1024) / (8 * slot));
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  RingPlan rp;
+  rp.stages = stages;
+  rp.smem = 8 * stages * slot + 8 * stages * sizeof(uint64_t);
+  int per_sm = (int)((227 * 1024) / (rp.smem + 10 * 1024));   // + the static reduction buffer and the 1 KB reserve
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 2) per_sm = 2;
+  if (max_blocks_per_sm > 0 && per_sm > max_blocks_per_sm) per_sm = max_blocks_per_sm;
+  rp.grid = grid_for(rows, 8, per_sm);
+  return rp;
+}
+template <typename K>
+static cudaError_t ring_attr(K kernel) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+
 }  // namespace rw
 }  // namespace smx
 
@@ -564,12 +694,26 @@ int smx_layernorm_fwd(const void* x, const void* res, const float* gamma, const 
   SMX_REQUIRE(cols % 8 == 0 && cols <= 2048 && cols > 0, "layernorm: cols %lld must be a multiple of 8 and <= 2048",
               (long long)cols);
   if (rows == 0) return 0;
+  SMX_REQUIRE(aligned16(x) && (res == nullptr || aligned16(res)), "layernorm: inputs must be 16-byte aligned");
   const int vpl = (int)ceil_div(cols, 256);
-  const int grid = grid_for(rows, 8);
+  RingPlan rp = ring_plan(rows, cols, res ? 2 : 1, 0);
   cudaStream_t st = (cudaStream_t)stream;
-  LN_DISPATCH(vpl, ln_fwd_kernel,
-              <<<grid, 256, 0, st>>>((const bf16*)x, (const bf16*)res, gamma, beta, (bf16*)y, (bf16*)sum_out, mean,
-                                     rstd, rows, (int)cols, eps, rms_only, act));
+#define LN_FWD_LAUNCH(V)                                                                                       \
+  do {                                                                                                         \
+    SMX_CHECK_CUDA(ring_attr(ln_fwd_kernel<V>));                                                               \
+    ln_fwd_kernel<V><<<rp.grid, 256, rp.smem, st>>>((const bf16*)x, (const bf16*)res, gamma, beta, (bf16*)y,   \
+                                                    (bf16*)sum_out, mean, rstd, rows, (int)cols, eps, rms_only, \
+                                                    act, rp.stages);                                           \
+  } while (0)
+  switch (vpl) {
+    case 1: LN_FWD_LAUNCH(1); break;
+    case 2: LN_FWD_LAUNCH(2); break;
+    case 3: LN_FWD_LAUNCH(3); break;
+    case 4: LN_FWD_LAUNCH(4); break;
+    case 5: case 6: LN_FWD_LAUNCH(6); break;
+    default: LN_FWD_LAUNCH(8); break;
+  }
+#undef LN_FWD_LAUNCH
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -581,22 +725,31 @@ int smx_layernorm_bwd(const void* dy, const void* x, const float* gamma, const f
   SMX_REQUIRE(cols % 8 == 0 && cols <= 2048 && cols > 0, "layernorm_bwd: cols %lld unsupported", (long long)cols);
   SMX_REQUIRE(dgamma != nullptr, "layernorm_bwd: dgamma required");
   if (rows == 0) return 0;
+  SMX_REQUIRE(aligned16(dy) && aligned16(x) && (dres_in == nullptr || aligned16(dres_in)),
+              "layernorm_bwd: inputs must be 16-byte aligned");
   const int vpl = (int)ceil_div(cols, 256);
   const bool cs = dx_colsum != nullptr;
-  int grid = grid_for(rows, 8, vpl <= 3 ? 2 : 1);   // resident blocks per SM: one persistent wave
+  // the column accumulators live in registers for the whole kernel: one persistent wave of resident blocks
+  RingPlan rp = ring_plan(rows, cols, dres_in ? 3 : 2, vpl <= 3 ? 2 : 1);
   cudaStream_t st = (cudaStream_t)stream;
-#define LN_BWD_ARGS                                                                                              \
-  <<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)x, gamma, beta, mean, rstd, (const bf16*)dres_in, (bf16*)dx, \
-                         dgamma, dbeta, dx_colsum, rows, (int)cols, rms_only, act)
+#define LN_BWD_LAUNCH(V, C)                                                                                      \
+  do {                                                                                                           \
+    SMX_CHECK_CUDA(ring_attr(ln_bwd_kernel<V, C>));                                                              \
+    ln_bwd_kernel<V, C><<<rp.grid, 256, rp.smem, st>>>((const bf16*)dy, (const bf16*)x, gamma, beta, mean, rstd, \
+                                                       (const bf16*)dres_in, (bf16*)dx, dgamma, dbeta, dx_colsum, \
+                                                       rows, (int)cols, rms_only, act, rp.stages);               \
+  } while (0)
+#define LN_BWD_CASE(V) if (cs) LN_BWD_LAUNCH(V, true); else LN_BWD_LAUNCH(V, false); break
   switch (vpl) {
-    case 1: if (cs) ln_bwd_kernel<1, true> LN_BWD_ARGS; else ln_bwd_kernel<1, false> LN_BWD_ARGS; break;
-    case 2: if (cs) ln_bwd_kernel<2, true> LN_BWD_ARGS; else ln_bwd_kernel<2, false> LN_BWD_ARGS; break;
-    case 3: if (cs) ln_bwd_kernel<3, true> LN_BWD_ARGS; else ln_bwd_kernel<3, false> LN_BWD_ARGS; break;
-    case 4: if (cs) ln_bwd_kernel<4, true> LN_BWD_ARGS; else ln_bwd_kernel<4, false> LN_BWD_ARGS; break;
-    case 5: case 6: if (cs) ln_bwd_kernel<6, true> LN_BWD_ARGS; else ln_bwd_kernel<6, false> LN_BWD_ARGS; break;
-    default: if (cs) ln_bwd_kernel<8, true> LN_BWD_ARGS; else ln_bwd_kernel<8, false> LN_BWD_ARGS; break;
+    case 1: LN_BWD_CASE(1);
+    case 2: LN_BWD_CASE(2);
+    case 3: LN_BWD_CASE(3);
+    case 4: LN_BWD_CASE(4);
+    case 5: case 6: LN_BWD_CASE(6);
+    default: LN_BWD_CASE(8);
   }
-#undef LN_BWD_ARGS
+#undef LN_BWD_CASE
+#undef LN_BWD_LAUNCH
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

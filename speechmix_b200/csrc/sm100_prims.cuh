@@ -317,6 +317,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// three-input maximum (FMNMX3, sm_100): NaN-free inputs assumed
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -363,6 +369,57 @@ __device__ __forceinline__ void gelu_erf_both(float x, float& y, float& dy) {
   const float t = xc * fmaf(x2, fmaf(x2, kGD2, kGD1), kGD0);
   y = x * s;
   dy = fmaf(fmaf(-s, s, s), t, s);
+}
+// ---------------------------------------------------------------------------
+// packed fp32 pairs: sm_100 executes fma/mul/add .f32x2 as ONE instruction (FFMA2 / FMUL2 / FADD2) on an aligned
+// register pair -- the same IEEE round-to-nearest results as two scalar operations in half the issue slots.
+// Issue-bound epilogues and row kernels (GELU, LayerNorm) use them for everything but min/max, MUFU and converts.
+// ---------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_rep(float a) { return f2_pack(a, a); }
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// pair versions of the GELU fits above: bit-identical to the scalar functions (same operations, same rounding)
+__device__ __forceinline__ void gelu_erf_both2(float& x0, float& x1, float& d0, float& d1) {
+  const f32x2 xc = f2_pack(fminf(fmaxf(x0, -7.0f), 7.0f), fminf(fmaxf(x1, -7.0f), 7.0f));
+  const f32x2 x2 = f2_mul(xc, xc);
+  float u0, u1;
+  f2_unpack(f2_mul(xc, f2_fma(x2, f2_fma(x2, f2_rep(kGC2), f2_rep(kGC1)), f2_rep(kGC0))), u0, u1);
+  const f32x2 s = f2_fma(f2_pack(tanh_approx(u0), tanh_approx(u1)), f2_rep(0.5f), f2_rep(0.5f));
+  const f32x2 t = f2_mul(xc, f2_fma(x2, f2_fma(x2, f2_rep(kGD2), f2_rep(kGD1)), f2_rep(kGD0)));
+  const f32x2 y = f2_mul(f2_pack(x0, x1), s);
+  const f32x2 dy = f2_fma(f2_fma(f2_mul(s, f2_rep(-1.0f)), s, s), t, s);
+  f2_unpack(y, x0, x1);
+  f2_unpack(dy, d0, d1);
+}
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  const f32x2 xc = f2_pack(fminf(fmaxf(x0, -7.0f), 7.0f), fminf(fmaxf(x1, -7.0f), 7.0f));
+  const f32x2 x2 = f2_mul(xc, xc);
+  float u0, u1;
+  f2_unpack(f2_mul(xc, f2_fma(x2, f2_fma(x2, f2_rep(kGC2), f2_rep(kGC1)), f2_rep(kGC0))), u0, u1);
+  const f32x2 s = f2_fma(f2_pack(tanh_approx(u0), tanh_approx(u1)), f2_rep(0.5f), f2_rep(0.5f));
+  f2_unpack(f2_mul(f2_pack(x0, x1), s), x0, x1);
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);

@@ -137,6 +137,49 @@ def rowwise():
 
 
 @case
+def perf():
+    """Row-kernel timings at the bench shape [23968, 768] (L2 flushed between launches by reading 256 MB -- a fill would
+    leave dirty lines whose write-back is then charged to the kernel under test)."""
+    import torch
+    from speechmix_b200 import kernels as K
+    R, C = 23968, 768
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(R, C, device="cuda", generator=g).to(torch.bfloat16)
+    r = torch.randn(R, C, device="cuda", generator=g).to(torch.bfloat16)
+    dy = torch.randn(R, C, device="cuda", generator=g).to(torch.bfloat16)
+    gamma = 1 + 0.1 * torch.randn(C, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(C, device="cuda", generator=g)
+    flush = torch.zeros(64 << 20, dtype=torch.float32, device="cuda")   # 256 MB, READ between launches: clean L2 lines
+    y, s, mean, rstd = K.layernorm_fwd(x, gamma, beta, res=r, want_sum=True)
+    mb = R * C * 2 / 1e6
+
+    def timeit(fn, iters=10, cold=True):
+        ts = []
+        for _ in range(iters + 2):
+            if cold:
+                flush.sum()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sorted(ts[2:])[len(ts[2:]) // 2]
+
+    cases = [("ln_fwd x->y", 2 * mb, lambda: K.layernorm_fwd(x, gamma, beta)),
+             ("ln_fwd x+res->sum,y", 4 * mb, lambda: K.layernorm_fwd(x, gamma, beta, res=r, want_sum=True)),
+             ("ln_bwd dy,x->dx (+colsum)", 3 * mb, lambda: K.layernorm_bwd(dy, s, gamma, mean, rstd, want_colsum=True)),
+             ("ln_bwd dy,x,dres->dx", 4 * mb, lambda: K.layernorm_bwd(dy, s, gamma, mean, rstd, dres=r)),
+             ("colsum", mb, lambda: K.colsum(dy))]
+    for name, mbytes, fn in cases:
+        for cold in (True, False):
+            ms = timeit(fn, cold=cold)
+            print(json.dumps({"perf": name, "cold_l2": cold, "us": round(ms * 1e3, 2), "algorithmic_MB": round(mbytes, 1),
+                              "GBps": round(mbytes / ms, 1)}), flush=True)
+    return True
+
+
+@case
 def lmhead():
     import torch
     import torch.nn.functional as F
