@@ -641,7 +641,7 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_consta
     // lse (log2 domain) / delta*scale of the 64 queries of a sub-tile: thread gt < 64 owns lse[gt], the others
     // delta[gt - 64]; the global load for the NEXT sub-tile is issued one sub-tile ahead.
     const float* stat_src = (gt < 64 ? p.lse : p.delta) + ((long long)b * p.heads + head) * p.tq;
-    const float stat_mul = gt < 64 ? kLog2e : p.scale;
+    const float stat_mul = gt < 64 ? -kLog2e : -p.scale;   // stored NEGATED: both are subtracted through an FMA
     auto load_stat = [&](int it) -> float {
       const int qi = (i_start + it) * SUB + (gt & 63);
       return (it < n_iter && qi < p.tq) ? stat_src[qi] * stat_mul : 0.f;
@@ -656,30 +656,47 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_consta
       mbar_wait(&bars[B_STFULL], it & 1);
       tc_fence_after_sync();
       uint32_t pk[32], dk[32];   // P^T and dS^T of this row, bf16 pairs
+      if (lean) {
+        // 16-column sub-chunks, the next one in flight while this one is turned into P^T / dS^T; fp32 pairs
+        const f32x2 sl2 = f2_rep(p.scale_log2), sc2 = f2_rep(p.scale);
+        uint32_t sa[16], da[16], sb[16], db[16];
+        tmem_ld_x16(t_row + COL_ST, sa);
+        tmem_ld_x16(t_row + COL_DPT, da);
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        uint32_t sv[32], dv[32];
-        tmem_ld_x32(t_row + COL_ST + cc * 32, sv);
-        tmem_ld_x32(t_row + COL_DPT + cc * 32, dv);
-        tmem_ld_wait();
-        if (lean) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 l4 = *reinterpret_cast<const float4*>(st + cc * 32 + i);
-            const float4 d4 = *reinterpret_cast<const float4*>(st + 64 + cc * 32 + i);
-            const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dl[4] = {d4.x, d4.y, d4.z, d4.w};
-            float e[4], d[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              e[k] = ex2_approx(fmaf(__uint_as_float(sv[i + k]), p.scale_log2, -lv[k]));
-              d[k] = e[k] * fmaf(__uint_as_float(dv[i + k]), p.scale, -dl[k]);
-            }
-            pk[cc * 16 + (i >> 1)] = pack_bf16x2(e[0], e[1]);
-            pk[cc * 16 + (i >> 1) + 1] = pack_bf16x2(e[2], e[3]);
-            dk[cc * 16 + (i >> 1)] = pack_bf16x2(d[0], d[1]);
-            dk[cc * 16 + (i >> 1) + 1] = pack_bf16x2(d[2], d[3]);
+        for (int c = 0; c < 4; ++c) {
+          uint32_t (&sv)[16] = (c & 1) ? sb : sa;
+          uint32_t (&dv)[16] = (c & 1) ? db : da;
+          tmem_ld_wait();
+          if (c + 1 < 4) {
+            tmem_ld_x16(t_row + COL_ST + (c + 1) * 16, (c & 1) ? sa : sb);
+            tmem_ld_x16(t_row + COL_DPT + (c + 1) * 16, (c & 1) ? da : db);
           }
-        } else {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 l4 = *reinterpret_cast<const float4*>(st + c * 16 + i);        // -lse (log2 domain)
+            const float4 d4 = *reinterpret_cast<const float4*>(st + 64 + c * 16 + i);   // -delta * scale
+            float e0, e1, e2, e3;
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), sl2, f2_pack(l4.x, l4.y)), e0, e1);
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3])), sl2, f2_pack(l4.z, l4.w)), e2, e3);
+            e0 = ex2_approx(e0), e1 = ex2_approx(e1), e2 = ex2_approx(e2), e3 = ex2_approx(e3);
+            float g0, g1, g2, g3;
+            f2_unpack(f2_mul(f2_pack(e0, e1), f2_fma(f2_pack(__uint_as_float(dv[i]), __uint_as_float(dv[i + 1])), sc2,
+                                                     f2_pack(d4.x, d4.y))), g0, g1);
+            f2_unpack(f2_mul(f2_pack(e2, e3), f2_fma(f2_pack(__uint_as_float(dv[i + 2]), __uint_as_float(dv[i + 3])), sc2,
+                                                     f2_pack(d4.z, d4.w))), g2, g3);
+            pk[c * 8 + (i >> 1)] = pack_bf16x2(e0, e1);
+            pk[c * 8 + (i >> 1) + 1] = pack_bf16x2(e2, e3);
+            dk[c * 8 + (i >> 1)] = pack_bf16x2(g0, g1);
+            dk[c * 8 + (i >> 1) + 1] = pack_bf16x2(g2, g3);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t sv[32], dv[32];
+          tmem_ld_x32(t_row + COL_ST + cc * 32, sv);
+          tmem_ld_x32(t_row + COL_DPT + cc * 32, dv);
+          tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             float e[2], d[2];
@@ -690,8 +707,8 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_consta
               float s = __uint_as_float(sv[i + k]) * p.scale_log2;
               if (p.bias && qi < p.tq && kvi < p.tk) s += p.bias[((long long)head * p.tq + qi) * p.tk + kvi] * kLog2e;
               const bool ok = (qi < p.tq) && (kvi < p.tk) && (!p.causal || kvi <= qi + (p.tk - p.tq));
-              e[k] = ok ? ex2_approx(s - st[col]) : 0.f;
-              d[k] = e[k] * fmaf(__uint_as_float(dv[i + k]), p.scale, -st[64 + col]);
+              e[k] = ok ? ex2_approx(s + st[col]) : 0.f;
+              d[k] = e[k] * fmaf(__uint_as_float(dv[i + k]), p.scale, st[64 + col]);
             }
             pk[cc * 16 + (i >> 1)] = pack_bf16x2(e[0], e[1]);
             dk[cc * 16 + (i >> 1)] = pack_bf16x2(d[0], d[1]);
@@ -856,21 +873,37 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
       mbar_wait(&bars[B_SFULL], it & 1);
       tc_fence_after_sync();
       uint32_t dk[32];   // dS of this row, bf16 pairs
+      if (lean) {
+        const f32x2 sl2 = f2_rep(p.scale_log2), sc2 = f2_rep(p.scale), nl2 = f2_rep(-lse2), nd2 = f2_rep(-delta);
+        uint32_t sa[16], da[16], sb[16], db[16];
+        tmem_ld_x16(t_row + COL_S, sa);
+        tmem_ld_x16(t_row + COL_DP, da);
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        uint32_t sv[32], dv[32];
-        tmem_ld_x32(t_row + COL_S + cc * 32, sv);
-        tmem_ld_x32(t_row + COL_DP + cc * 32, dv);
-        tmem_ld_wait();
-        if (lean) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float e0 = ex2_approx(fmaf(__uint_as_float(sv[i]), p.scale_log2, -lse2));
-            const float e1 = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), p.scale_log2, -lse2));
-            dk[cc * 16 + (i >> 1)] = pack_bf16x2(e0 * fmaf(__uint_as_float(dv[i]), p.scale, -delta),
-                                                 e1 * fmaf(__uint_as_float(dv[i + 1]), p.scale, -delta));
+        for (int c = 0; c < 4; ++c) {
+          uint32_t (&sv)[16] = (c & 1) ? sb : sa;
+          uint32_t (&dv)[16] = (c & 1) ? db : da;
+          tmem_ld_wait();
+          if (c + 1 < 4) {
+            tmem_ld_x16(t_row + COL_S + (c + 1) * 16, (c & 1) ? sa : sb);
+            tmem_ld_x16(t_row + COL_DP + (c + 1) * 16, (c & 1) ? da : db);
           }
-        } else {
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            float e0, e1, g0, g1;
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), sl2, nl2), e0, e1);
+            e0 = ex2_approx(e0), e1 = ex2_approx(e1);
+            f2_unpack(f2_mul(f2_pack(e0, e1), f2_fma(f2_pack(__uint_as_float(dv[i]), __uint_as_float(dv[i + 1])), sc2, nd2)),
+                      g0, g1);
+            dk[c * 8 + (i >> 1)] = pack_bf16x2(g0, g1);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t sv[32], dv[32];
+          tmem_ld_x32(t_row + COL_S + cc * 32, sv);
+          tmem_ld_x32(t_row + COL_DP + cc * 32, dv);
+          tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             float d[2];

@@ -36,7 +36,221 @@ __device__ __forceinline__ void loadf8(const float* p, float (&f)[8]) {
   f[0] = a.x, f[1] = a.y, f[2] = a.z, f[3] = a.w, f[4] = b.x, f[5] = b.y, f[6] = b.z, f[7] = b.w;
 }
 
-// ------------------------------------------------------------------ LayerNorm forward
+// ------------------------------------------------------------------ LayerNorm forward (register-prefetch variant)
+// Used when there is no residual input (forward) / no residual-branch gradient (backward): measured with ncu at
+// [23968, 768] (profiles/r01q_ln_variants.txt) these win for one / two input streams (23.2 vs 24.6 us forward,
+// 36.8 vs 41.0 us backward with column sums), the shared-memory-ring kernels further down win with one more stream
+// (30.0 vs 34.5 us forward with residual, 39.3 vs 46.9 us backward with a residual-branch gradient).
+// one warp per row; VPL = 16-byte vectors per lane (cols <= VPL*256)
+template <int VPL>
+__global__ void __launch_bounds__(256) ln_fwd_reg_kernel(const bf16* __restrict__ x, const bf16* __restrict__ res,
+                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                     bf16* __restrict__ y, bf16* __restrict__ sum_out,
+                                                     float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                     long long rows, int cols, float eps, int rms_only, int act) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  // the next row's vectors are requested before the current row is reduced (latency-bound stream otherwise)
+  uint4 nx[VPL];
+  if (warp_global < rows) {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      if (c < cols) nx[i] = *reinterpret_cast<const uint4*>(x + warp_global * cols + c);
+    }
+  }
+  for (long long row = warp_global; row < rows; row += nwarps) {
+    float v[VPL][8];
+    float s = 0.f;
+    uint4 cur[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) cur[i] = nx[i];
+    if (row + nwarps < rows) {
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int c = (i * 32 + lane) * 8;
+        if (c < cols) nx[i] = *reinterpret_cast<const uint4*>(x + (row + nwarps) * cols + c);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      if (c < cols) {
+        unpack_bf16x8(cur[i], v[i]);
+        if (res) {
+          float r[8];
+          load8(res + row * cols + c, r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[i][j] += r[j];
+        }
+        if (sum_out) {
+          store8(sum_out + row * cols + c, v[i]);
+          // keep the statistics consistent with what backward will re-read
+          float t[8];
+          load8(sum_out + row * cols + c, t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[i][j] = t[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[i][j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+      }
+    }
+    float mean = 0.f;
+    if (!rms_only) mean = warp_sum(s) / cols;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      if (c < cols) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[i][j] - mean;
+          sq += d * d;
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / cols + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      if (c < cols) {
+        float g[8], b[8], o[8];
+        loadf8(gamma + c, g);
+        if (beta) loadf8(beta + c, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + (beta ? b[j] : 0.f);
+        if (act == SMX_ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = gelu_erf(o[j]);
+        }
+        store8(y + row * cols + c, o);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm backward (register variant)
+// One warp per row, rows strided over a persistent grid; parameter gradients (and, optionally, the column sums
+// of dx = the bias gradient of the linear layer in front of a post-LN block) accumulate in registers and are
+// reduced once per block.  Between the statistics pass and the dx pass a row is held as the PACKED bf16 it was
+// loaded as (2 x 4 registers per 8 elements) instead of two fp32 copies, which is what keeps the kernel at
+// two resident 256-thread blocks per SM -- an HBM-bound row kernel needs the
+// warps to cover the memory latency (the first version: 159 registers, 8 warps per SM, 29 % of HBM peak).
+template <int VPL, bool WITH_CS>
+__global__ void __launch_bounds__(256, (VPL <= 3 ? 2 : 1))
+ln_bwd_reg_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ gamma,
+              const float* __restrict__ beta, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+              const bf16* __restrict__ dres, bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+              float* __restrict__ dx_colsum, long long rows, int cols, int rms_only, int act) {
+  __shared__ float red[8][32 * 8 + 1];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long warp_global = (long long)blockIdx.x * 8 + warp;
+  const long long nwarps = (long long)gridDim.x * 8;
+  float ag[VPL][8], ab[VPL][8], ac[WITH_CS ? VPL : 1][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ag[i][j] = 0.f, ab[i][j] = 0.f;
+      if (WITH_CS) ac[i][j] = 0.f;
+    }
+
+  for (long long row = warp_global; row < rows; row += nwarps) {
+    const float mean = rms_only ? 0.f : mean_in[row];
+    const float rstd = rstd_in[row];
+    uint4 dp[VPL], xp[VPL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      if (c < cols) {
+        dp[i] = *reinterpret_cast<const uint4*>(dy + row * cols + c);
+        xp[i] = *reinterpret_cast<const uint4*>(x + row * cols + c);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      if (c < cols) {
+        float d[8], xh[8], gm[8];
+        unpack_bf16x8(dp[i], d);
+        unpack_bf16x8(xp[i], xh);
+        loadf8(gamma + c, gm);
+        if (act == SMX_ACT_GELU) {  // y = gelu(z), z = xhat*gamma + beta: fold gelu'(z) into dy first
+          float bt[8];
+          loadf8(beta + c, bt);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[j] *= gelu_erf_grad(fmaf((xh[j] - mean) * rstd, gm[j], bt[j]));
+          dp[i] = pack_bf16x8(d);   // the dx pass re-reads the folded gradient
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float h = (xh[j] - mean) * rstd;
+          ag[i][j] = fmaf(d[j], h, ag[i][j]);
+          ab[i][j] += d[j];
+          const float gj = d[j] * gm[j];
+          s1 += gj;
+          s2 = fmaf(gj, h, s2);
+        }
+      }
+    }
+    s1 = rms_only ? 0.f : warp_sum(s1) / cols;
+    s2 = warp_sum(s2) / cols;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      if (c < cols) {
+        float d[8], xh[8], gm[8], o[8];
+        unpack_bf16x8(dp[i], d);
+        unpack_bf16x8(xp[i], xh);
+        loadf8(gamma + c, gm);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (d[j] * gm[j] - s1 - (xh[j] - mean) * rstd * s2);
+        if (dres) {
+          float r[8];
+          load8(dres + row * cols + c, r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += r[j];
+        }
+        store8(dx + row * cols + c, o);
+        if (WITH_CS) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ac[i][j] += o[j];
+        }
+      }
+    }
+  }
+  // block reduction of the column accumulators, then one atomic per column per block
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+#pragma unroll
+    for (int pass = 0; pass < (WITH_CS ? 3 : 2); ++pass) {
+      float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : dx_colsum);
+      if (dst == nullptr) continue;
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = pass == 0 ? ag[i][j] : (pass == 1 ? ab[i][j] : ac[WITH_CS ? i : 0][j]);
+      __syncthreads();
+      const int col_local = threadIdx.x;  // 256 threads, 256 columns of this vector slot
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[w][col_local];
+      const int c = i * 256 + col_local;
+      if (c < cols) atomicAdd(dst + c, t);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm forward / backward (ring variants)
 // Row kernels below run their fp32 arithmetic on PACKED PAIRS (FFMA2 / FMUL2 / FADD2, sm100_prims.cuh): the first
 // versions were instruction-issue-bound (ln_fwd ~21, ln_bwd ~28 warp instructions per element and lane at ~50 % of
 // the HBM roofline); pairs halve every add / multiply / FMA, and the remaining per-element work is the bf16 unpack.
@@ -651,7 +865,9 @@ struct RingPlan {
 };
 static RingPlan ring_plan(long long rows, long long cols, int n_inputs, int max_blocks_per_sm) {
   const size_t slot = (size_t)cols * 2 * n_inputs;       // one row of every input
-  int stages = (int)((96 * 1024) / (8 * slot));
+  // forward (58 registers): four blocks of ~48 KB per SM; backward (128 registers): two blocks of ~96 KB
+  const size_t budget = (max_blocks_per_sm == 0 ? 48 : 96) * 1024;
+  int stages = (int)(budget / (8 * slot));
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   RingPlan rp;
@@ -659,14 +875,21 @@ static RingPlan ring_plan(long long rows, long long cols, int n_inputs, int max_
   rp.smem = 8 * stages * slot + 8 * stages * sizeof(uint64_t);
   int per_sm = (int)((227 * 1024) / (rp.smem + 10 * 1024));   // + the static reduction buffer and the 1 KB reserve
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 2) per_sm = 2;
-  if (max_blocks_per_sm > 0 && per_sm > max_blocks_per_sm) per_sm = max_blocks_per_sm;
+  const int cap = max_blocks_per_sm > 0 ? max_blocks_per_sm : 4;
+  if (per_sm > cap) per_sm = cap;
   rp.grid = grid_for(rows, 8, per_sm);
   return rp;
 }
+// opt in to > 48 KB of dynamic shared memory once per kernel instantiation (one caller thread per process)
 template <typename K>
 static cudaError_t ring_attr(K kernel) {
-  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  static const void* done[64];
+  static int n_done = 0;
+  for (int i = 0; i < n_done; ++i)
+    if (done[i] == reinterpret_cast<const void*>(kernel)) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e == cudaSuccess && n_done < 64) done[n_done++] = reinterpret_cast<const void*>(kernel);
+  return e;
 }
 
 }  // namespace rw
@@ -698,12 +921,19 @@ int smx_layernorm_fwd(const void* x, const void* res, const float* gamma, const 
   const int vpl = (int)ceil_div(cols, 256);
   RingPlan rp = ring_plan(rows, cols, res ? 2 : 1, 0);
   cudaStream_t st = (cudaStream_t)stream;
-#define LN_FWD_LAUNCH(V)                                                                                       \
-  do {                                                                                                         \
-    SMX_CHECK_CUDA(ring_attr(ln_fwd_kernel<V>));                                                               \
-    ln_fwd_kernel<V><<<rp.grid, 256, rp.smem, st>>>((const bf16*)x, (const bf16*)res, gamma, beta, (bf16*)y,   \
-                                                    (bf16*)sum_out, mean, rstd, rows, (int)cols, eps, rms_only, \
-                                                    act, rp.stages);                                           \
+  const int reg_grid = grid_for(rows, 8);
+#define LN_FWD_LAUNCH(V)                                                                                         \
+  do {                                                                                                           \
+    if (res == nullptr) {                                                                                        \
+      ln_fwd_reg_kernel<V><<<reg_grid, 256, 0, st>>>((const bf16*)x, (const bf16*)res, gamma, beta, (bf16*)y,    \
+                                                     (bf16*)sum_out, mean, rstd, rows, (int)cols, eps, rms_only, \
+                                                     act);                                                       \
+    } else {                                                                                                     \
+      SMX_CHECK_CUDA(ring_attr(ln_fwd_kernel<V>));                                                               \
+      ln_fwd_kernel<V><<<rp.grid, 256, rp.smem, st>>>((const bf16*)x, (const bf16*)res, gamma, beta, (bf16*)y,   \
+                                                      (bf16*)sum_out, mean, rstd, rows, (int)cols, eps, rms_only, \
+                                                      act, rp.stages);                                           \
+    }                                                                                                            \
   } while (0)
   switch (vpl) {
     case 1: LN_FWD_LAUNCH(1); break;
@@ -732,12 +962,19 @@ int smx_layernorm_bwd(const void* dy, const void* x, const float* gamma, const f
   // the column accumulators live in registers for the whole kernel: one persistent wave of resident blocks
   RingPlan rp = ring_plan(rows, cols, dres_in ? 3 : 2, vpl <= 3 ? 2 : 1);
   cudaStream_t st = (cudaStream_t)stream;
-#define LN_BWD_LAUNCH(V, C)                                                                                      \
-  do {                                                                                                           \
-    SMX_CHECK_CUDA(ring_attr(ln_bwd_kernel<V, C>));                                                              \
-    ln_bwd_kernel<V, C><<<rp.grid, 256, rp.smem, st>>>((const bf16*)dy, (const bf16*)x, gamma, beta, mean, rstd, \
-                                                       (const bf16*)dres_in, (bf16*)dx, dgamma, dbeta, dx_colsum, \
-                                                       rows, (int)cols, rms_only, act, rp.stages);               \
+  const int reg_grid = grid_for(rows, 8, vpl <= 3 ? 2 : 1);
+#define LN_BWD_LAUNCH(V, C)                                                                                        \
+  do {                                                                                                             \
+    if (dres_in == nullptr) {                                                                                      \
+      ln_bwd_reg_kernel<V, C><<<reg_grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)x, gamma, beta, mean, rstd,  \
+                                                        (const bf16*)dres_in, (bf16*)dx, dgamma, dbeta, dx_colsum, \
+                                                        rows, (int)cols, rms_only, act);                           \
+    } else {                                                                                                       \
+      SMX_CHECK_CUDA(ring_attr(ln_bwd_kernel<V, C>));                                                              \
+      ln_bwd_kernel<V, C><<<rp.grid, 256, rp.smem, st>>>((const bf16*)dy, (const bf16*)x, gamma, beta, mean, rstd, \
+                                                         (const bf16*)dres_in, (bf16*)dx, dgamma, dbeta, dx_colsum, \
+                                                         rows, (int)cols, rms_only, act, rp.stages);               \
+    }                                                                                                              \
   } while (0)
 #define LN_BWD_CASE(V) if (cs) LN_BWD_LAUNCH(V, true); else LN_BWD_LAUNCH(V, false); break
   switch (vpl) {
