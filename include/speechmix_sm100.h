@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SMX_ABI_VERSION 1
+#define SMX_ABI_VERSION 2
 
 const char* smx_last_error(void);
 int smx_abi_version(void);
@@ -216,6 +216,10 @@ int smx_posconv_wgrad(const void* dpre, const void* x, float* dw, int64_t batch,
  * causal: 0/1.  scale: multiplies q.k (T5: 1.0).  bias: optional additive
  * [heads][tq][tk] fp32 (T5 relative position bias) or NULL.
  * lse: [batch][heads][tq] fp32 (natural log), written by fwd, read by bwd.
+ * kv_len: optional [batch] int32, 1 <= kv_len[b] <= tk: keys/values at or past kv_len[b] are masked out for
+ *   every query of sample b (key-padding mask of a padded batch, hf:...wav2vec2.py:1026-1044 turned into
+ *   per-sample frame counts).  Not combined with causal.  Contract for smx_attn_bwd: the k / v rows at or past
+ *   kv_len[b] hold ZEROS (smx_mask_rows does that on the projection output), and dk / dv come back zero there.
  * ------------------------------------------------------------------------ */
 typedef struct SmxAttn {
   const void *q, *k, *v;
@@ -234,9 +238,16 @@ typedef struct SmxAttn {
   int64_t do_row_stride, do_batch_stride;
   int64_t dq_row_stride, dk_row_stride, dv_row_stride;
   int64_t dq_batch_stride, dk_batch_stride, dv_batch_stride;
+  const int32_t* kv_len; /* optional per-sample key count (see above); NULL = all tk keys */
 } SmxAttn;
 int smx_attn_fwd(const SmxAttn* a, void* stream);
 int smx_attn_bwd(const SmxAttn* a, void* stream);
+
+/* Zero the columns [col_begin, col_begin + col_count) of every row t >= len[b] of a bf16 [batch][t][...] buffer
+ * (row / batch strides in elements; col_begin, col_count multiples of 8).  Used for "padded frames output 0"
+ * (hf:...wav2vec2.py:672-675) and for the k | v part of a fused QKV projection under a key-padding mask. */
+int smx_mask_rows(void* x, const int32_t* len, int64_t batch, int64_t t, int64_t row_stride, int64_t batch_stride,
+                  int64_t col_begin, int64_t col_count, void* stream);
 
 /* ------------------------------------------------------------------------
  * Input embeddings:  out[b,t,:] = tok_emb[ids[b,t]]*scale (if ids) + x_in[b,t,:] (if x_in)

@@ -47,7 +47,8 @@ class SmxAttn(Structure):
                 ("delta", c_void_p), ("dbias", c_void_p),
                 ("do_row_stride", c_int64), ("do_batch_stride", c_int64),
                 ("dq_row_stride", c_int64), ("dk_row_stride", c_int64), ("dv_row_stride", c_int64),
-                ("dq_batch_stride", c_int64), ("dk_batch_stride", c_int64), ("dv_batch_stride", c_int64)]
+                ("dq_batch_stride", c_int64), ("dk_batch_stride", c_int64), ("dv_batch_stride", c_int64),
+                ("kv_len", c_void_p)]
 
 
 _P = c_void_p
@@ -62,6 +63,7 @@ SIGNATURES = {
     "smx_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, c_float, c_int, c_int, _P]),
     "smx_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, c_int, c_int, _P]),
     "smx_colsum": (c_int, [_P, _P, _I64, _I64, _I64, _P]),
+    "smx_mask_rows": (c_int, [_P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _P]),
     "smx_cast_f32_to_bf16": (c_int, [_P, _P, _I64, _P]),
     "smx_weightnorm_fwd": (c_int, [_P, _P, _P, _P, _I64, _I64, _P]),
     "smx_weightnorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _P]),
@@ -151,7 +153,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.smx_abi_version() != 1:
+    if lib.smx_abi_version() != 2:
         raise RuntimeError("libspeechmix_sm100.so ABI version mismatch")
     shim = _Lib()
     for name in SIGNATURES:

@@ -40,7 +40,14 @@ struct BwdParams {
   long long dq_row_stride, dq_batch_stride, dk_row_stride, dk_batch_stride, dv_row_stride, dv_batch_stride;
   int batch, heads, tq, tk, causal;
   float scale, scale_log2;
+  const int* kv_len;  // optional [batch] key counts (v2 kernels only; k / v rows past it hold zeros, see the header)
 };
+
+__device__ __forceinline__ int effective_tk(const BwdParams& p, int b) {
+  if (p.kv_len == nullptr) return p.tk;
+  const int l = p.kv_len[b];
+  return l < 1 ? 1 : (l < p.tk ? l : p.tk);
+}
 
 // ------------------------------------------------------------------ delta = rowsum(dO * O)
 __global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, float* __restrict__ delta,
@@ -81,7 +88,8 @@ __device__ __forceinline__ void store_row_chunk(uint8_t* tile, int r, int c32, c
   }
 }
 
-__device__ __forceinline__ void store_out_row(bf16* dst, uint32_t taddr, bool valid) {
+// live == false: the row exists in memory but is masked out (key past kv_len[b]) -> its gradient is zero
+__device__ __forceinline__ void store_out_row(bf16* dst, uint32_t taddr, bool valid, bool live = true) {
 #pragma unroll
   for (int c = 0; c < D / 32; ++c) {
     uint32_t v[32];
@@ -95,7 +103,7 @@ __device__ __forceinline__ void store_out_row(bf16* dst, uint32_t taddr, bool va
         u.y = pack_bf16x2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
         u.z = pack_bf16x2(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
         u.w = pack_bf16x2(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
-        *reinterpret_cast<uint4*>(dst + c * 32 + i) = u;
+        *reinterpret_cast<uint4*>(dst + c * 32 + i) = live ? u : make_uint4(0u, 0u, 0u, 0u);
       }
     }
     __syncwarp();
@@ -560,6 +568,7 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_consta
   const int kv0 = blockIdx.x * 128;
   const int head = blockIdx.y, b = blockIdx.z;
   const int nq_sub = (p.tq + SUB - 1) / SUB;
+  const int tk = effective_tk(p, b);
   int i_start = 0;
   if (p.causal) {  // first query row that can see key kv0:  q >= kv0 - (tk - tq)
     int qmin = kv0 - (p.tk - p.tq);
@@ -567,7 +576,7 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_consta
     i_start = qmin / SUB;
     if (i_start > nq_sub) i_start = nq_sub;
   }
-  const int n_iter = nq_sub - i_start;
+  const int n_iter = kv0 >= tk ? 0 : nq_sub - i_start;   // a tile of masked keys only writes zeros
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -705,8 +714,8 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_consta
               const int col = cc * 32 + i + k;
               const int qi = q0 + col;
               float s = __uint_as_float(sv[i + k]) * p.scale_log2;
-              if (p.bias && qi < p.tq && kvi < p.tk) s += p.bias[((long long)head * p.tq + qi) * p.tk + kvi] * kLog2e;
-              const bool ok = (qi < p.tq) && (kvi < p.tk) && (!p.causal || kvi <= qi + (p.tk - p.tq));
+              if (p.bias && qi < p.tq && kvi < tk) s += p.bias[((long long)head * p.tq + qi) * p.tk + kvi] * kLog2e;
+              const bool ok = (qi < p.tq) && (kvi < tk) && (!p.causal || kvi <= qi + (p.tk - p.tq));
               e[k] = ok ? ex2_approx(s + st[col]) : 0.f;
               d[k] = e[k] * fmaf(__uint_as_float(dv[i + k]), p.scale, st[64 + col]);
             }
@@ -733,8 +742,8 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_consta
           *reinterpret_cast<uint4*>(dstk + i) = make_uint4(0, 0, 0, 0);
         }
     } else {
-      store_out_row(dstv, t_row + COL_DV, valid);
-      store_out_row(dstk, t_row + COL_DK, valid);
+      store_out_row(dstv, t_row + COL_DV, valid, kvi < tk);
+      store_out_row(dstk, t_row + COL_DK, valid, kvi < tk);
     }
   }
   tc_fence_before_sync();
@@ -763,7 +772,8 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128;
   const int head = blockIdx.y, b = blockIdx.z;
-  int n_iter = (p.tk + SUB - 1) / SUB;
+  const int tk = effective_tk(p, b);
+  int n_iter = (tk + SUB - 1) / SUB;
   if (p.causal) {
     const int last_col = q0 + 127 + (p.tk - p.tq);
     int nc = last_col / SUB + 1;
@@ -911,8 +921,8 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
             for (int k = 0; k < 2; ++k) {
               const int kvi = k0 + cc * 32 + i + k;
               float s = __uint_as_float(sv[i + k]) * p.scale_log2;
-              if (p.bias && qi < p.tq && kvi < p.tk) s += p.bias[((long long)head * p.tq + qi) * p.tk + kvi] * kLog2e;
-              const bool ok = (qi < p.tq) && (kvi < p.tk) && (kvi <= causal_lim);
+              if (p.bias && qi < p.tq && kvi < tk) s += p.bias[((long long)head * p.tq + qi) * p.tk + kvi] * kLog2e;
+              const bool ok = (qi < p.tq) && (kvi < tk) && (kvi <= causal_lim);
               const float e = ok ? ex2_approx(s - lse2) : 0.f;
               d[k] = e * fmaf(__uint_as_float(dv[i + k]), p.scale, -delta);
               if (p.dbias && ok) atomicAdd(p.dbias + ((long long)head * p.tq + qi) * p.tk + kvi, d[k] * p.inv_scale);
@@ -945,6 +955,7 @@ extern "C" int smx_attn_bwd(const SmxAttn* a, void* stream) {
   SMX_REQUIRE(a && a->q && a->k && a->v && a->o && a->d_o && a->dq && a->dk && a->dv && a->lse && a->delta,
               "attn_bwd: null pointer");
   SMX_REQUIRE(a->dbias == nullptr || a->bias != nullptr, "attn_bwd: dbias needs the additive bias it differentiates");
+  SMX_REQUIRE(a->kv_len == nullptr || !a->causal, "attn_bwd: kv_len is not combined with causal masking");
   cudaStream_t st = (cudaStream_t)stream;
   CUtensorMap mq, mk, mv, mdo;
   if (make_head_map(&mq, a->q, a->tq, a->heads, a->batch, a->q_row_stride, a->q_batch_stride)) return -1;
@@ -962,6 +973,7 @@ extern "C" int smx_attn_bwd(const SmxAttn* a, void* stream) {
   p.batch = a->batch, p.heads = a->heads, p.tq = a->tq, p.tk = a->tk, p.causal = a->causal;
   p.scale = a->scale;
   p.scale_log2 = a->scale * kLog2e;
+  p.kv_len = a->kv_len;
   static bool attr_set = false;
   if (!attr_set) {
     SMX_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kv::SMEM_BYTES));
@@ -976,6 +988,7 @@ extern "C" int smx_attn_bwd(const SmxAttn* a, void* stream) {
   p.o = reinterpret_cast<const bf16*>(a->o);
   p.o_row_stride = a->o_row_stride, p.o_batch_stride = a->o_batch_stride;
   p.delta_out = a->delta;
+  SMX_REQUIRE(!(use_v1 && a->kv_len), "attn_bwd: the first-generation kernels (SMX_ATTN_BWD_V1) have no kv_len");
   if (use_v1) {
     const long long n = (long long)a->batch * a->heads * a->tq;
     long long g = (n + 255) / 256;

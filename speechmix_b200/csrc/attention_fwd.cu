@@ -37,14 +37,15 @@ struct FwdParams {
   long long o_row_stride, o_batch_stride;
   int batch, heads, tq, tk, causal;
   float scale_log2;  // scale * log2(e)
+  const int* kv_len; // optional [batch]: keys at or past kv_len[b] are masked (never with causal)
 };
 
 // barrier indices
 enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 3, B_VFULL = 5, B_VEMPTY = 7, B_SFULL = 9, B_SEMPTY = 10, B_PFULL = 11,
        B_PVFULL = 12, B_PVEMPTY = 14, B_COUNT = 16 };
 
-__device__ __forceinline__ int num_kv_tiles(const FwdParams& p, int q0) {
-  int n = (p.tk + BKV - 1) / BKV;
+__device__ __forceinline__ int num_kv_tiles(const FwdParams& p, int q0, int tk) {
+  int n = (tk + BKV - 1) / BKV;
   if (p.causal) {
     const int last_col = q0 + BQ - 1 + (p.tk - p.tq);  // last visible key for the last row of the tile
     int nc = last_col / BKV + 1;
@@ -64,7 +65,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq_map, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ;
   const int head = blockIdx.y, b = blockIdx.z;
-  const int n_tiles = num_kv_tiles(p, q0);
+  // effective key count of this sample: tiles past it are never loaded, the tile it cuts takes the "cut" path
+  int tk = p.tk;
+  if (p.kv_len) {
+    const int l = p.kv_len[b];
+    tk = l < 1 ? 1 : (l < p.tk ? l : p.tk);
+  }
+  const int n_tiles = num_kv_tiles(p, q0, tk);
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) {
@@ -177,7 +184,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq_map, const __grid_constan
       // Lean arithmetic per score: a third of an FMNMX3 in pass 1; half an FFMA2 + MUFU.EX2 + half an FADD2 + half a
       // pack in pass 2.  TMEM loads are issued one chunk ahead of the arithmetic (tcgen05.wait::ld is the only stall).
       const bool plain = (bias_row == nullptr) && (!p.causal || c_base + BKV - 1 <= q0 + (p.tk - p.tq));
-      const int n_valid = p.tk - c_base;   // >= 1; columns of this tile inside the key length (may exceed BKV)
+      const int n_valid = tk - c_base;   // >= 1; columns of this tile inside the key length (may exceed BKV)
       const bool lean = plain && n_valid >= BKV;   // full tile
       const bool cut = plain && n_valid < BKV;     // last tile of a ragged key length
       float tmax = -INFINITY;
@@ -220,8 +227,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq_map, const __grid_constan
           for (int i = 0; i < 32; ++i) {
             const int col = c_base + c * 32 + i;
             float s = __uint_as_float(v[i]) * p.scale_log2;
-            if (bias_row && col < p.tk) s += bias_row[col] * 1.4426950408889634f;
-            s = (col < p.tk && col <= causal_lim) ? s : -INFINITY;
+            if (bias_row && col < tk) s += bias_row[col] * 1.4426950408889634f;
+            s = (col < tk && col <= causal_lim) ? s : -INFINITY;
             tmax = fmaxf(tmax, s);
           }
         }
@@ -312,9 +319,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq_map, const __grid_constan
           for (int i = 0; i < 32; ++i) {
             const int col = c_base + c * 32 + i;
             float s = __uint_as_float(v[i]) * p.scale_log2;
-            if (bias_row && col < p.tk) s += bias_row[col] * 1.4426950408889634f;
+            if (bias_row && col < tk) s += bias_row[col] * 1.4426950408889634f;
             const float e = ex2_approx(s - m_use);
-            pr[i] = (col < p.tk && col <= causal_lim) ? e : 0.f;
+            pr[i] = (col < tk && col <= causal_lim) ? e : 0.f;
             lt += pr[i];
           }
           uint8_t* blk = p_row + (c >> 1) * (BQ * 128);
@@ -415,6 +422,7 @@ extern "C" int smx_attn_fwd(const SmxAttn* a, void* stream) {
   SMX_REQUIRE(a && a->q && a->k && a->v && a->o, "attn_fwd: null pointer");
   SMX_REQUIRE(a->batch > 0 && a->heads > 0 && a->tq > 0 && a->tk > 0, "attn_fwd: empty problem");
   SMX_REQUIRE(a->o_row_stride % 8 == 0 && a->o_batch_stride % 8 == 0, "attn_fwd: o strides must be multiples of 8");
+  SMX_REQUIRE(a->kv_len == nullptr || !a->causal, "attn_fwd: kv_len is not combined with causal masking");
   CUtensorMap mq, mk, mv;
   if (make_head_map(&mq, a->q, a->tq, a->heads, a->batch, a->q_row_stride, a->q_batch_stride)) return -1;
   if (make_head_map(&mk, a->k, a->tk, a->heads, a->batch, a->k_row_stride, a->k_batch_stride)) return -1;
@@ -428,6 +436,7 @@ extern "C" int smx_attn_fwd(const SmxAttn* a, void* stream) {
   p.o_batch_stride = a->o_batch_stride;
   p.batch = a->batch, p.heads = a->heads, p.tq = a->tq, p.tk = a->tk, p.causal = a->causal;
   p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.kv_len = a->kv_len;
   static bool attr_set = false;
   if (!attr_set) {
     SMX_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

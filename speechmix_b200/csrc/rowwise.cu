@@ -601,6 +601,20 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
   if (cc < cols) atomicAdd(out + cc, t);
 }
 
+// ------------------------------------------------------------------ padded-row masking
+// x[b][t][col_begin : col_begin + col_count] = 0 for t >= len[b]; one 16-byte vector per thread
+__global__ void mask_rows_kernel(bf16* __restrict__ x, const int* __restrict__ len, long long batch, long long t,
+                                 long long row_stride, long long batch_stride, int col_begin, int vec_per_row) {
+  const long long total = batch * t * vec_per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int vc = (int)(i % vec_per_row);
+    const long long rt = i / vec_per_row;
+    const long long tt = rt % t, b = rt / t;
+    if (tt >= len[b])
+      *reinterpret_cast<uint4*>(x + b * batch_stride + tt * row_stride + col_begin + vc * 8) = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 // ------------------------------------------------------------------ elementwise
 __global__ void cast_kernel(const float* __restrict__ s, bf16* __restrict__ d, long long n) {
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
@@ -987,6 +1001,19 @@ int smx_layernorm_bwd(const void* dy, const void* x, const float* gamma, const f
   }
 #undef LN_BWD_CASE
 #undef LN_BWD_LAUNCH
+  SMX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int smx_mask_rows(void* x, const int32_t* len, int64_t batch, int64_t t, int64_t row_stride, int64_t batch_stride,
+                  int64_t col_begin, int64_t col_count, void* stream) {
+  SMX_REQUIRE(x && len, "mask_rows: null pointer");
+  SMX_REQUIRE(col_begin % 8 == 0 && col_count % 8 == 0 && row_stride % 8 == 0 && batch_stride % 8 == 0 && aligned16(x),
+              "mask_rows: columns / strides must be multiples of 8 elements and x 16-byte aligned");
+  if (batch == 0 || t == 0 || col_count == 0) return 0;
+  const int vec = (int)(col_count / 8);
+  mask_rows_kernel<<<grid_for(batch * t * vec, 256), 256, 0, (cudaStream_t)stream>>>(
+      (bf16*)x, len, batch, t, row_stride, batch_stride, (int)col_begin, vec);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -304,7 +304,7 @@ def unpack_conv_wgrad(dw_packed, in_c, k):
 # ---------------------------------------------------------------------------
 # attention (head_dim 64); q/k/v: [B, T, heads*64] views with unit inner stride
 # ---------------------------------------------------------------------------
-def _attn_desc(q, k, v, o, lse, heads, causal, scale, bias):
+def _attn_desc(q, k, v, o, lse, heads, causal, scale, bias, kv_len=None):
     B, Tq, HD = q.shape
     Tk = k.shape[1]
     assert HD == heads * 64 and q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1
@@ -316,24 +316,32 @@ def _attn_desc(q, k, v, o, lse, heads, causal, scale, bias):
     a.batch, a.heads, a.tq, a.tk, a.causal = B, heads, Tq, Tk, 1 if causal else 0
     a.scale = scale
     a.bias = _ptr(bias)
+    if kv_len is not None:
+        assert kv_len.dtype == torch.int32 and kv_len.is_cuda and kv_len.numel() == B and not causal
+    a.kv_len = _ptr(kv_len)
     return a
 
 
-def attn_fwd(q, k, v, heads, causal=False, scale=None, bias=None):
+def attn_fwd(q, k, v, heads, causal=False, scale=None, bias=None, kv_len=None):
+    """kv_len: optional int32 [B] key counts (key-padding mask): keys at or past kv_len[b] are ignored."""
     if FP32_MODE:
+        if kv_len is not None:
+            raise NotImplementedError("the fp32 verification kernels have no key-padding mask")
         from . import fp32path
         return fp32path.attn_fwd(q, k, v, heads, causal, (1.0 / math.sqrt(64)) if scale is None else scale, bias)
     B, Tq, HD = q.shape
     scale = (1.0 / math.sqrt(64)) if scale is None else scale
     o = torch.empty(B, Tq, HD, device=q.device, dtype=BF16)
     lse = torch.empty(B, heads, Tq, device=q.device, dtype=torch.float32)
-    a = _attn_desc(q, k, v, o, lse, heads, causal, scale, bias)
+    a = _attn_desc(q, k, v, o, lse, heads, causal, scale, bias, kv_len)
     _lib.check(_lib.load().smx_attn_fwd(ctypes.byref(a), _stream()), "smx_attn_fwd")
     return o, lse
 
 
-def attn_bwd(do, q, k, v, o, lse, heads, causal=False, scale=None, bias=None, dq=None, dk=None, dv=None, dbias=None):
-    """dbias: optional zero-initialised fp32 [heads, Tq, Tk]; receives sum_b dS (gradient of the additive bias)."""
+def attn_bwd(do, q, k, v, o, lse, heads, causal=False, scale=None, bias=None, dq=None, dk=None, dv=None, dbias=None,
+             kv_len=None):
+    """dbias: optional zero-initialised fp32 [heads, Tq, Tk]; receives sum_b dS (gradient of the additive bias).
+    kv_len: as in attn_fwd; the k / v rows at or past kv_len[b] must hold zeros (mask_rows), dk / dv are zero there."""
     B, Tq, HD = q.shape
     Tk = k.shape[1]
     scale = (1.0 / math.sqrt(64)) if scale is None else scale
@@ -342,7 +350,7 @@ def attn_bwd(do, q, k, v, o, lse, heads, causal=False, scale=None, bias=None, dq
     dk = torch.empty(B, Tk, HD, device=q.device, dtype=BF16) if dk is None else dk
     dv = torch.empty(B, Tk, HD, device=q.device, dtype=BF16) if dv is None else dv
     delta = torch.empty(B, heads, Tq, device=q.device, dtype=torch.float32)
-    a = _attn_desc(q, k, v, o, lse, heads, causal, scale, bias)
+    a = _attn_desc(q, k, v, o, lse, heads, causal, scale, bias, kv_len)
     a.d_o, a.dq, a.dk, a.dv, a.delta = _ptr(do), _ptr(dq), _ptr(dk), _ptr(dv), _ptr(delta)
     a.dbias = _ptr(dbias)
     a.do_row_stride, a.do_batch_stride = do.stride(1), do.stride(0)
@@ -388,6 +396,16 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, rms_only=False, want_dbet
                                       _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(csum), rows, C, 1 if rms_only else 0, act,
                                       _stream()), "layernorm_bwd")
     return (dx, dgamma, dbeta, csum) if want_colsum else (dx, dgamma, dbeta)
+
+
+def mask_rows(x, lens, col_begin=0, col_count=None):
+    """In place: x[b, t, col_begin:col_begin+col_count] = 0 for t >= lens[b]  (x: bf16 [B, T, C], lens: int32 [B])."""
+    B, T, C = x.shape
+    assert x.dtype == BF16 and x.stride(2) == 1 and lens.dtype == torch.int32 and lens.numel() == B
+    col_count = C - col_begin if col_count is None else col_count
+    _lib.check(_L().smx_mask_rows(_ptr(x), _ptr(lens), B, T, x.stride(1), x.stride(0), col_begin, col_count, _stream()),
+               "mask_rows")
+    return x
 
 
 def colsum(x2d):

@@ -122,6 +122,56 @@ def bias_dbias():
 
 
 @case
+def kv_len_mask():
+    """per-sample key counts (key-padding mask of a padded batch): fused-QKV self-attention and cross-attention,
+    with and without an additive bias; k / v rows past the count are zeroed with mask_rows as the contract asks;
+    reference = masked softmax in fp32; dk / dv must come back exactly zero on the masked rows."""
+    import torch
+    from speechmix_b200 import kernels as K
+    ok = True
+    for (B, Tq, Tk, H, lens, with_bias) in [(3, 200, 200, 2, [200, 131, 7], False), (2, 749, 749, 4, [749, 300], False),
+                                            (4, 64, 374, 4, [374, 1, 128, 129], False), (2, 130, 130, 2, [64, 130], True),
+                                            (2, 256, 256, 1, [128, 256], False)]:
+        g = torch.Generator(device="cuda").manual_seed(2)
+        if Tq == Tk:
+            qkv = torch.randn(B, Tq, 3 * H * 64, device="cuda", generator=g).mul(0.5).to(torch.bfloat16)
+            q, k, v = qkv[..., :H * 64], qkv[..., H * 64:2 * H * 64], qkv[..., 2 * H * 64:]
+            kl = torch.tensor(lens, device="cuda", dtype=torch.int32)
+            K.mask_rows(qkv, kl, col_begin=H * 64, col_count=2 * H * 64)
+        else:
+            q = torch.randn(B, Tq, H * 64, device="cuda", generator=g).mul(0.5).to(torch.bfloat16)
+            kv = torch.randn(B, Tk, 2 * H * 64, device="cuda", generator=g).mul(0.5).to(torch.bfloat16)
+            k, v = kv[..., :H * 64], kv[..., H * 64:]
+            kl = torch.tensor(lens, device="cuda", dtype=torch.int32)
+            K.mask_rows(kv, kl)
+        keep = torch.arange(Tk, device="cuda")[None, :] < kl[:, None]            # [B, Tk]
+        ok &= bool((k.float().abs().sum(-1)[~keep] == 0).all()) and bool((k.float().abs().sum(-1)[keep] > 0).all())
+        do = torch.randn(B, Tq, H * 64, device="cuda", generator=g).to(torch.bfloat16)
+        bias = torch.randn(H, Tq, Tk, device="cuda", generator=g) if with_bias else None
+        scale = 1.0 if with_bias else 0.125
+        name = f"kv_len B{B} Tq{Tq} Tk{Tk} H{H} lens{lens} bias{int(with_bias)}"
+        o, lse = K.attn_fwd(q, k, v, H, scale=scale, bias=bias, kv_len=kl)
+        dq, dk, dv = K.attn_bwd(do, q, k, v, o, lse, H, scale=scale, bias=bias, kv_len=kl)
+        qr, kr, vr = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+        qh, kh, vh = (t.view(B, -1, H, 64).transpose(1, 2) for t in (qr, kr, vr))
+        sc = qh @ kh.transpose(-1, -2) * scale
+        if bias is not None:
+            sc = sc + bias[None]
+        sc = sc.masked_fill(~keep[:, None, None, :], float("-inf"))
+        o_ref = (torch.softmax(sc, -1) @ vh).transpose(1, 2).reshape(B, Tq, H * 64)
+        o_ref.backward(do.float())
+        ok &= _rep("fwd o " + name, o, o_ref.detach())
+        ok &= _rep("fwd lse " + name, lse, torch.logsumexp(sc, -1).detach())
+        ok &= _rep("bwd dq " + name, dq, qr.grad)
+        ok &= _rep("bwd dk " + name, dk, kr.grad)
+        ok &= _rep("bwd dv " + name, dv, vr.grad)
+        zero_ok = bool((dk.float().abs().sum(-1)[~keep] == 0).all()) and bool((dv.float().abs().sum(-1)[~keep] == 0).all())
+        print(json.dumps({"case": "masked dk/dv rows exactly zero " + name, "ok": zero_ok}), flush=True)
+        ok &= zero_ok
+    return ok
+
+
+@case
 def full_size():
     ok = _run(4, 749, 749, 12, False, fused=True)
     ok &= _run(2, 1499, 1499, 16, False, fused=True)
