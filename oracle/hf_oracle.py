@@ -284,14 +284,21 @@ class OracleEED(nn.Module):
     def forward(self, input_values=None, decoder_text_prompt_ids=None, text_input_ids=None,
                 decoder_input_ids=None, labels=None, encoder_outputs=None, decoder_outputs=None,
                 past_key_values=None, use_cache=None, return_model_detail=True,
-                keep_full_logits=False, **kwargs):
-        """ref:speechmix/hf_model.py:378-447.  ``decoder_text_prompt_ids`` takes
+                keep_full_logits=False, attention_mask=None, **kwargs):
+        """ref:speechmix/hf_model.py:378-447.  ``attention_mask`` is NOT a reference argument: the reference calls the
+        speech encoder without one (:397); given, it is forwarded to exactly that call (the oracle of the
+        true-length extension is the reference with the mask passed on to HF's Wav2Vec2Model / HubertModel).
+        ``decoder_text_prompt_ids`` takes
         already-tokenised prompt ids (the reference tokenises a string at :433-435;
         there is no real tokenizer offline).  ``keep_full_logits`` additionally
         returns the pre-argmax logits under ``full_logits`` for parity checks."""
         detail = {}
         if encoder_outputs is None:
-            encoder_outputs = self.encoder_model(input_values, output_hidden_states=True)
+            if attention_mask is None:
+                encoder_outputs = self.encoder_model(input_values, output_hidden_states=True)
+            else:
+                encoder_outputs = self.encoder_model(input_values, attention_mask=attention_mask,
+                                                     output_hidden_states=True)
         if decoder_input_ids is None and labels is None:
             decoder_input_ids = handle_decoder_input_none(
                 self.decoder_model.config, encoder_outputs.last_hidden_state.shape[0], device=self.device)

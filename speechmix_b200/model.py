@@ -185,8 +185,10 @@ class SpeechMixEED(nn.Module):
     def forward(self, input_values=None, decoder_text_prompt=None, text_input_ids=None, decoder_input_ids=None,
                 labels=None, encoder_outputs=None, decoder_outputs=None, past_key_values=None, use_cache=None,
                 return_model_detail=True, output_attentions=None, output_hidden_states=None, return_dict=None,
-                precision=None, **kwargs):
+                precision=None, attention_mask=None, **kwargs):
         if precision == "fp32":   # verification run: fp32 activations + fp32 arithmetic, inference only
+            if attention_mask is not None:
+                raise NotImplementedError("fp32 verification mode has no key-padding mask")
             with torch.no_grad(), ops.fp32_verification():
                 return self.forward(input_values, decoder_text_prompt, text_input_ids, decoder_input_ids, labels,
                                     encoder_outputs, decoder_outputs, past_key_values, use_cache, return_model_detail)
@@ -206,7 +208,9 @@ class SpeechMixEED(nn.Module):
             # optimizers do not bump tensor versions) -> refresh all bf16 working copies in one launch
             ops.CACHE.new_step()
         if encoder_outputs is None:
-            encoder_outputs = self.encoder_model(input_values, output_hidden_states=True)
+            # attention_mask is an extension: the reference calls the speech encoder without one
+            # (ref:speechmix/hf_model.py:397); given, it is forwarded to that call and to nothing else
+            encoder_outputs = self.encoder_model(input_values, attention_mask=attention_mask, output_hidden_states=True)
         if decoder_input_ids is None and labels is None:
             decoder_input_ids = handle_decoder_input_none(self.decoder_model.config,
                                                           encoder_outputs.last_hidden_state.shape[0], device=self.device)

@@ -215,6 +215,25 @@ def linear(x, weight, bias=None, residual=None):
 
 
 # ---------------------------------------------------------------------------
+class MaskRowsFn(torch.autograd.Function):
+    """y[b, t, :] = x[b, t, :] for t < lens[b], else 0 ("make sure padded tokens output 0",
+    hf:models/wav2vec2/modeling_wav2vec2.py:672-675); the gradient of the zeroed rows is zero."""
+
+    @staticmethod
+    def forward(ctx, x, lens):
+        ctx.lens = lens
+        return K.mask_rows(x.clone(memory_format=torch.contiguous_format), lens)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return K.mask_rows(dy.clone(memory_format=torch.contiguous_format), ctx.lens), None
+
+
+def mask_rows(x, lens):
+    return MaskRowsFn.apply(x, lens)
+
+
+# ---------------------------------------------------------------------------
 class AttnBlockFn(torch.autograd.Function):
     """(self- or cross-) attention sub-block with its residual and LayerNorm.
 
@@ -224,6 +243,9 @@ class AttnBlockFn(torch.autograd.Function):
     hf:models/wav2vec2/modeling_wav2vec2.py:466-549,576-655 ; hf:models/bart/modeling_bart.py:143-391 ;
     hf:models/mbart/modeling_mbart.py:274-430.
     inputs: x, src (None for self-attention), cfg, q_w,q_b,k_w,k_b,v_w,v_b,o_w,o_b, ln_w, ln_b
+    cfg["kv_len"] (optional int32 [B] on the device): key-padding mask as per-sample key counts -- the keys / values
+    of the padded frames are zeroed in the projection output and ignored by the attention kernels, their
+    gradients are zero (hf:...wav2vec2.py:1026-1044 + create_bidirectional_mask).
     """
 
     @staticmethod
@@ -231,6 +253,7 @@ class AttnBlockFn(torch.autograd.Function):
         heads, causal, pre_ln, eps = cfg["heads"], cfg["causal"], cfg["pre_ln"], cfg["eps"]
         rms = bool(cfg.get("rms", False))          # T5: RMSNorm (no mean, no beta)
         scale = cfg.get("scale", 1.0 / math.sqrt(64))
+        kv_len = cfg.get("kv_len")
         B, T, H = x.shape
         Hi = q_w.shape[0]                          # heads * 64 (== H except for some T5 sizes)
         x2 = x.reshape(B * T, H)
@@ -246,6 +269,8 @@ class AttnBlockFn(torch.autograd.Function):
             wqkv = cat16((q_w, k_w, v_w))
             bqkv = cat32((q_b, k_b, v_b)) if q_b is not None else None
             qkv = K.linear_fwd(a_in, wqkv, bqkv).view(B, T, 3 * Hi)
+            if kv_len is not None:
+                K.mask_rows(qkv, kv_len, col_begin=Hi, col_count=2 * Hi)
             q, k, v = qkv[..., :Hi], qkv[..., Hi:2 * Hi], qkv[..., 2 * Hi:]
             kv_src2 = None
             Ts = T
@@ -258,11 +283,13 @@ class AttnBlockFn(torch.autograd.Function):
             wkv = cat16((k_w, v_w))
             bkv = cat32((k_b, v_b)) if k_b is not None else None
             kv = K.linear_fwd(src2, wkv, bkv).view(Bs, Ts, 2 * Hi)
+            if kv_len is not None:
+                K.mask_rows(kv, kv_len)
             k, v = kv[..., :Hi], kv[..., Hi:]
             qkv = (q, kv)
             kv_src2 = src2
         pb = None if pos_bias is None else pos_bias.detach().float().contiguous()
-        o, lse = K.attn_fwd(q, k, v, heads, causal=causal, scale=scale, bias=pb)
+        o, lse = K.attn_fwd(q, k, v, heads, causal=causal, scale=scale, bias=pb, kv_len=kv_len)
         s = K.linear_fwd(o.view(B * T, Hi), w16(o_w), None if o_b is None else o_b.detach(), residual=x2)
         if pre_ln:
             y = s
@@ -271,6 +298,7 @@ class AttnBlockFn(torch.autograd.Function):
             y, _, mean, rstd = K.layernorm_fwd(s, ln_w.detach(), ln_b_d, eps, rms_only=rms)
             ctx.save_for_backward(x2, s, mean, rstd, o, lse, kv_src2, ln_w, pb, *(qkv if src is not None else (qkv,)))
         ctx.cfg = dict(cfg, scale=scale, rms=rms)
+        ctx.kv_len = kv_len
         ctx.dims = (B, T, H, Ts, Hi)
         ctx.cross = src is not None
         ctx.wrefs = (q_w, k_w, v_w, o_w)
@@ -307,7 +335,7 @@ class AttnBlockFn(torch.autograd.Function):
             q, k, v = qkv[..., :Hi], qkv[..., Hi:2 * Hi], qkv[..., 2 * Hi:]
             dqkv = torch.empty_like(qkv)
             K.attn_bwd(do, q, k, v, o, lse, heads, causal=causal, scale=scale, bias=pb, dq=dqkv[..., :Hi],
-                       dk=dqkv[..., Hi:2 * Hi], dv=dqkv[..., 2 * Hi:], dbias=dpb)
+                       dk=dqkv[..., Hi:2 * Hi], dv=dqkv[..., 2 * Hi:], dbias=dpb, kv_len=ctx.kv_len)
             dqkv2 = dqkv.view(B * T, 3 * Hi)
             need_w = _need(ctx, 3) or _need(ctx, 5) or _need(ctx, 7)
             dwqkv = K.linear_wgrad(dqkv2, a_in) if need_w else None
@@ -322,7 +350,7 @@ class AttnBlockFn(torch.autograd.Function):
             dq = torch.empty_like(q)
             dkv = torch.empty_like(kv)
             K.attn_bwd(do, q, k, v, o, lse, heads, causal=causal, scale=scale, bias=pb, dq=dq, dk=dkv[..., :Hi],
-                       dv=dkv[..., Hi:], dbias=dpb)
+                       dv=dkv[..., Hi:], dbias=dpb, kv_len=ctx.kv_len)
             dq2 = dq.view(B * T, Hi)
             dkv2 = dkv.view(-1, 2 * Hi)
             need_q = _need(ctx, 3)

@@ -147,8 +147,9 @@ class EncoderLayer(nn.Module):
         if config.hidden_size // config.num_attention_heads != 64:
             raise NotImplementedError("attention kernels are specialised for head_dim 64")
 
-    def forward(self, x):
-        x = ops.AttnBlockFn.apply(x, None, self.cfg, *self.attention.params(), self.layer_norm.weight,
+    def forward(self, x, kv_len=None):
+        cfg = self.cfg if kv_len is None else dict(self.cfg, kv_len=kv_len)
+        x = ops.AttnBlockFn.apply(x, None, cfg, *self.attention.params(), self.layer_norm.weight,
                                   self.layer_norm.bias)
         ff = self.feed_forward
         return ops.FFNBlockFn.apply(x, self.cfg, ff.intermediate_dense.weight, ff.intermediate_dense.bias,
@@ -167,8 +168,12 @@ class Encoder(nn.Module):
         self.layers = nn.ModuleList([EncoderLayer(config) for _ in range(config.num_hidden_layers)])
         self.stable = bool(config.do_stable_layer_norm)
 
-    def forward(self, x, output_hidden_states=False):
+    def forward(self, x, output_hidden_states=False, frame_len=None):
+        """frame_len: optional int32 [B] valid-frame counts (hf :669-681): padded frames are zeroed before the
+        positional conv and masked out as attention keys in every layer."""
         hs = []
+        if frame_len is not None:
+            x = ops.mask_rows(x, frame_len)
         x = self.pos_conv_embed(x)
         if not self.stable:
             x = ops.layer_norm(x, self.layer_norm.weight, self.layer_norm.bias, self.config.layer_norm_eps)
@@ -179,7 +184,7 @@ class Encoder(nn.Module):
             # honoured on the host exactly like the reference does.
             if self.training and self.config.layerdrop > 0 and float(torch.rand([])) < self.config.layerdrop:
                 continue
-            x = layer(x)
+            x = layer(x, kv_len=frame_len)
         if self.stable:
             x = ops.layer_norm(x, self.layer_norm.weight, self.layer_norm.bias, self.config.layer_norm_eps)
         if output_hidden_states:
@@ -208,16 +213,31 @@ class SpeechEncoderModel(nn.Module):
     def device(self):
         return next(self.parameters()).device
 
+    def feat_extract_output_lengths(self, input_lengths):
+        """hf:...wav2vec2.py:1005-1018: frames left by the conv stack for each sample count."""
+        n = torch.as_tensor(input_lengths).to(torch.long)
+        for k, s in zip(self.config.conv_kernel, self.config.conv_stride):
+            n = torch.div(n - k, s, rounding_mode="floor") + 1
+        return n
+
     def forward(self, input_values, attention_mask=None, output_hidden_states=False, **kwargs):
-        if attention_mask is not None:
-            raise NotImplementedError("the SpeechMix path never passes an attention mask (SURVEY section 8)")
+        """attention_mask ([B, n] 1 = audio sample, 0 = padding; the reference itself never passes one --
+        SURVEY section 8f row 1): HF semantics, hf:...wav2vec2.py:1026-1044, :669-681 -- the conv stack runs over the
+        padded signal, frames past each sample's own length are zeroed after the projection and masked as keys.
+        (HF advises against it for feat_extract_norm="group" checkpoints, whose GroupNorm sees the padding.)"""
         x = self.feature_extractor(input_values)          # [B, T, C] channels-last (HF: [B, C, T] + transpose)
         x = self.feature_projection(x)
+        frame_len = None
+        if attention_mask is not None:
+            if ops.K.FP32_MODE:
+                raise NotImplementedError("fp32 verification mode has no key-padding mask")
+            lens = self.feat_extract_output_lengths(attention_mask.to(torch.long).sum(-1))
+            frame_len = lens.clamp(1, x.shape[1]).to(device=x.device, dtype=torch.int32)
         # SpecAugment (hf :1280-1324) only fires in training with mask_time_prob > 0.
         if self.training and getattr(self.config, "apply_spec_augment", False) and \
                 (self.config.mask_time_prob > 0 or self.config.mask_feature_prob > 0):
             raise NotImplementedError("SpecAugment masking is not implemented; set apply_spec_augment=False")
-        x, hs = self.encoder(x, output_hidden_states=output_hidden_states)
+        x, hs = self.encoder(x, output_hidden_states=output_hidden_states, frame_len=frame_len)
         return SpeechOutput(last_hidden_state=x, hidden_states=hs if output_hidden_states else None)
 
 

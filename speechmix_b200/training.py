@@ -21,6 +21,9 @@ class DataCollatorWithPadding:
     bos_token_id: Optional[int] = None
     pad_to_multiple_of_labels: Optional[int] = None
     max_length_labels: Optional[int] = None
+    # extension, off by default = the reference's contract: also emit ``attention_mask`` (1 = audio
+    # sample) and pad the audio with 0.0 the way HF's feature extractor does, for ``forward(..., attention_mask=...)``
+    return_attention_mask: bool = False
 
     def _ids(self):
         pad = self.pad_token_id if self.pad_token_id is not None else getattr(self.tokenizer, "pad_token_id", None)
@@ -43,8 +46,11 @@ class DataCollatorWithPadding:
 
     def __call__(self, features: List[Dict]) -> Dict[str, torch.Tensor]:
         pad, bos = self._ids()
-        batch = {"input_values": pad_sequence([torch.as_tensor(f["input_values"], dtype=torch.float32) for f in features],
-                                              batch_first=True, padding_value=-100)}
+        audio = [torch.as_tensor(f["input_values"], dtype=torch.float32) for f in features]
+        batch = {"input_values": pad_sequence(audio, batch_first=True,
+                                              padding_value=0.0 if self.return_attention_mask else -100)}
+        if self.return_attention_mask:
+            batch["attention_mask"] = pad_sequence([torch.ones(len(a), dtype=torch.long) for a in audio], batch_first=True)
         labels, mask = self._pad_ids([f["labels"] for f in features], pad)
         if "text_input_ids" in features[0]:
             batch["text_input_ids"], _ = self._pad_ids([f["text_input_ids"] for f in features], pad)

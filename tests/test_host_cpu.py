@@ -94,6 +94,22 @@ def test_collator_contract():
     assert b2["labels"].tolist() == [[4, 5], [3, 5]]            # bos is only cut when EVERY row starts with it
     b3 = DataCollatorWithPadding(pad_token_id=1, bos_token_id=0)([{"input_values": [0.0], "labels": [0, 5]}])
     assert b3["labels"].tolist() == [[0, 5]]                    # falsy bos id: reference never cuts
+    # extension (off by default): zero padding + attention_mask for forward(..., attention_mask=...)
+    b4 = DataCollatorWithPadding(pad_token_id=1, bos_token_id=3, return_attention_mask=True)(feats)
+    assert torch.allclose(b4["input_values"], torch.tensor([[0.1, 0.2, 0.3], [0.5, 0.0, 0.0]]))
+    assert b4["attention_mask"].tolist() == [[1, 1, 1], [1, 0, 0]]
+    assert "attention_mask" not in b
+
+
+def test_feat_extract_output_lengths_match_transformers():
+    """hf:models/wav2vec2/modeling_wav2vec2.py:1005-1018 (frame counts behind the key-padding mask)"""
+    from transformers import Wav2Vec2Config, Wav2Vec2Model
+    from speechmix_b200.speech import SpeechEncoderModel
+    cfg = Wav2Vec2Config()
+    n = torch.tensor([400, 401, 799, 16000, 80000, 240000, 123457])
+    ref = Wav2Vec2Model._get_feat_extract_output_lengths(type("M", (), {"config": cfg})(), n)
+    got = SpeechEncoderModel.feat_extract_output_lengths(type("M", (), {"config": cfg})(), n)
+    assert got.tolist() == ref.tolist() and got[3] == 49 and got[5] == 749
 
 
 def test_freezing_policy_matches_reference_callback():

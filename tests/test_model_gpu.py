@@ -433,3 +433,39 @@ def test_cfg2_shape_forward_backward_vs_oracle(cuda_device):
         g, r = pm[k].grad.cpu(), po[k].grad
         rel = float((g - r).norm() / (r.norm() + 1e-20))
         assert rel < 6e-2, (k, rel)
+
+
+@pytest.mark.parametrize("name", ["mini_large_mbart", "mini_eed_ds2"])
+def test_attention_mask_true_length_extension(name, cuda_device):
+    """variable-length audio.  Oracle = the reference glue with ``attention_mask`` forwarded to HF's
+    speech encoder (conv stack over the zero-padded signal, padded frames zeroed after the projection, key-padding mask
+    in every layer).  Checks speech / text-encoder states, logits, loss and gradients; the fused kernels skip the
+    padded key tiles and return zero k / v gradients for them."""
+    fx = load_fixture(name)
+    ora, x, labels = build_oracle(fx)
+    ora.train(True)
+    n = x.shape[1]
+    lens = [n, int(0.55 * n)] + [int(0.8 * n)] * (x.shape[0] - 2)
+    mask = torch.zeros(x.shape, dtype=torch.long)
+    for i, l in enumerate(lens[:x.shape[0]]):
+        mask[i, :l] = 1
+    x = x * mask                      # the feature extractor pads with 0.0
+    mine = _mine_from(ora, dict(fx, train_mode=True), cuda_device)
+    ref = ora(x, labels=labels, keep_full_logits=True, attention_mask=mask)
+    ref_nomask = ora(x, labels=labels)
+    assert abs(float(ref["loss"]) - float(ref_nomask["loss"])) > 1e-6      # the mask changes the result at all
+    out = mine(x.to(cuda_device), labels=labels.to(cuda_device), attention_mask=mask.to(cuda_device))
+    ltol = 6e-3 if "t5" in fx["text"] else 3e-3
+    assert abs(float(out["loss"]) - float(ref["loss"])) < ltol
+    assert _rel(out["speech_last_hidden_state"], ref["speech_last_hidden_state"]) < 4e-2
+    assert _rel(out["encoder_last_hidden_state"], ref["encoder_last_hidden_state"]) < 4e-2
+    assert _rel(mine.decoder_model.full_logits(out["decoder_last_hidden_state"]), ref["full_logits"]) < 2e-2
+    ref["loss"].backward()
+    out["loss"].backward()
+    po, pm = dict(ora.named_parameters()), dict(mine.named_parameters())
+    scale = max(float(p.grad.norm()) for p in po.values() if p.grad is not None)
+    for k, p in po.items():
+        if p.grad is None:
+            continue
+        err = float((pm[k].grad.cpu() - p.grad).norm())
+        assert err <= 5e-2 * float(p.grad.norm()) + 2e-4 * scale, (k, err, float(p.grad.norm()))
