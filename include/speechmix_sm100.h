@@ -249,6 +249,17 @@ int smx_attn_bwd(const SmxAttn* a, void* stream);
 int smx_mask_rows(void* x, const int32_t* len, int64_t batch, int64_t t, int64_t row_stride, int64_t batch_stride,
                   int64_t col_begin, int64_t col_count, void* stream);
 
+/* SpecAugment on the projected features (hf:models/wav2vec2/modeling_wav2vec2.py:1280-1324; the mask INDICES come
+ * from the host, drawn exactly like the reference's _compute_mask_indices):
+ *   y[b,t,:] = time_mask[b,t] ? embed : x[b,t,:];  y[b,t,c] = 0 where feat_mask[b,c]   (either mask may be NULL)
+ * time_mask: uint8 [batch][t]; feat_mask: uint8 [batch][hidden]; embed: fp32 [hidden] (masked_spec_embed).
+ * bwd: dx = dy outside the masks and 0 inside; dembed (fp32 [hidden], zero-initialised by the caller, may be NULL)
+ * += the column sums of dy over the time-masked rows. */
+int smx_spec_augment_fwd(const void* x, void* y, const uint8_t* time_mask, const uint8_t* feat_mask, const float* embed,
+                         int64_t batch, int64_t t, int64_t hidden, void* stream);
+int smx_spec_augment_bwd(const void* dy, void* dx, float* dembed, const uint8_t* time_mask, const uint8_t* feat_mask,
+                         int64_t batch, int64_t t, int64_t hidden, void* stream);
+
 /* ------------------------------------------------------------------------
  * Input embeddings:  out[b,t,:] = tok_emb[ids[b,t]]*scale (if ids) + x_in[b,t,:] (if x_in)
  *                                 + pos_emb[t + t_start + pos_offset] (if pos_emb)      (bf16 out)

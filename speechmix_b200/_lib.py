@@ -64,6 +64,8 @@ SIGNATURES = {
     "smx_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, c_int, c_int, _P]),
     "smx_colsum": (c_int, [_P, _P, _I64, _I64, _I64, _P]),
     "smx_mask_rows": (c_int, [_P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _P]),
+    "smx_spec_augment_fwd": (c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _P]),
+    "smx_spec_augment_bwd": (c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _P]),
     "smx_cast_f32_to_bf16": (c_int, [_P, _P, _I64, _P]),
     "smx_weightnorm_fwd": (c_int, [_P, _P, _P, _P, _I64, _I64, _P]),
     "smx_weightnorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _P]),

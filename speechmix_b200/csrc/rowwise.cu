@@ -615,6 +615,63 @@ __global__ void mask_rows_kernel(bf16* __restrict__ x, const int* __restrict__ l
   }
 }
 
+// ------------------------------------------------------------------ SpecAugment (hf:...wav2vec2.py:1280-1324)
+// y[b,t,:] = time_mask[b,t] ? embed : x[b,t,:];  then y[b,t,c] = 0 where feat_mask[b,c].  One 16-byte vector per thread.
+__global__ void spec_augment_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
+                                        const unsigned char* __restrict__ time_mask,
+                                        const unsigned char* __restrict__ feat_mask, const float* __restrict__ embed,
+                                        long long rows, long long t, int hidden) {
+  const int vec_per_row = hidden / 8;
+  const long long total = rows * vec_per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % vec_per_row) * 8;
+    const long long r = i / vec_per_row;
+    float f[8];
+    if (time_mask && time_mask[r]) loadf8(embed + c, f);
+    else load8(x + r * hidden + c, f);
+    if (feat_mask) {
+      const unsigned char* fm = feat_mask + (r / t) * hidden + c;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fm[j] ? 0.f : f[j];
+    }
+    store8(y + r * hidden + c, f);
+  }
+}
+// dx = dy outside the masks, 0 inside
+__global__ void spec_augment_bwd_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx,
+                                        const unsigned char* __restrict__ time_mask,
+                                        const unsigned char* __restrict__ feat_mask, long long rows, long long t,
+                                        int hidden) {
+  const int vec_per_row = hidden / 8;
+  const long long total = rows * vec_per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % vec_per_row) * 8;
+    const long long r = i / vec_per_row;
+    float f[8];
+    load8(dy + r * hidden + c, f);
+    const bool tm = time_mask && time_mask[r];
+    const unsigned char* fm = feat_mask ? feat_mask + (r / t) * hidden + c : nullptr;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = (tm || (fm && fm[j])) ? 0.f : f[j];
+    store8(dx + r * hidden + c, f);
+  }
+}
+// dembed[c] += sum over time-masked rows of dy[r][c] (zero where the feature mask cleared the value afterwards)
+__global__ void __launch_bounds__(256) spec_augment_dembed_kernel(const bf16* __restrict__ dy, float* __restrict__ dembed,
+                                                                  const unsigned char* __restrict__ time_mask,
+                                                                  const unsigned char* __restrict__ feat_mask,
+                                                                  long long rows, long long t, int hidden) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= hidden) return;
+  float acc = 0.f;
+  for (long long r = blockIdx.y; r < rows; r += gridDim.y) {
+    if (!time_mask[r]) continue;   // block-uniform
+    if (feat_mask && feat_mask[(r / t) * hidden + c]) continue;
+    acc += __bfloat162float(dy[r * hidden + c]);
+  }
+  if (acc != 0.f) atomicAdd(dembed + c, acc);
+}
+
 // ------------------------------------------------------------------ elementwise
 __global__ void cast_kernel(const float* __restrict__ s, bf16* __restrict__ d, long long n) {
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
@@ -1015,6 +1072,33 @@ int smx_mask_rows(void* x, const int32_t* len, int64_t batch, int64_t t, int64_t
   mask_rows_kernel<<<grid_for(batch * t * vec, 256), 256, 0, (cudaStream_t)stream>>>(
       (bf16*)x, len, batch, t, row_stride, batch_stride, (int)col_begin, vec);
   SMX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int smx_spec_augment_fwd(const void* x, void* y, const uint8_t* time_mask, const uint8_t* feat_mask, const float* embed,
+                         int64_t batch, int64_t t, int64_t hidden, void* stream) {
+  SMX_REQUIRE(x && y && hidden % 8 == 0 && aligned16(x) && aligned16(y), "spec_augment: bad arguments");
+  SMX_REQUIRE(time_mask == nullptr || (embed != nullptr && aligned16(embed)), "spec_augment: time mask needs the embedding");
+  if (batch * t == 0) return 0;
+  spec_augment_fwd_kernel<<<grid_for(batch * t * (hidden / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, (bf16*)y, time_mask, feat_mask, embed, batch * t, t, (int)hidden);
+  SMX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int smx_spec_augment_bwd(const void* dy, void* dx, float* dembed, const uint8_t* time_mask, const uint8_t* feat_mask,
+                         int64_t batch, int64_t t, int64_t hidden, void* stream) {
+  SMX_REQUIRE(dy && dx && hidden % 8 == 0 && aligned16(dy) && aligned16(dx), "spec_augment_bwd: bad arguments");
+  if (batch * t == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  spec_augment_bwd_kernel<<<grid_for(batch * t * (hidden / 8), 256), 256, 0, st>>>(
+      (const bf16*)dy, (bf16*)dx, time_mask, feat_mask, batch * t, t, (int)hidden);
+  SMX_CHECK_CUDA(cudaGetLastError());
+  if (dembed && time_mask) {   // dembed is zero-initialised by the caller
+    long long gy = batch * t < 592 ? batch * t : 592;
+    spec_augment_dembed_kernel<<<dim3((unsigned)ceil_div(hidden, 256), (unsigned)gy), 256, 0, st>>>(
+        (const bf16*)dy, dembed, time_mask, feat_mask, batch * t, t, (int)hidden);
+    SMX_CHECK_CUDA(cudaGetLastError());
+  }
   return 0;
 }
 

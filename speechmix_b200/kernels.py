@@ -408,6 +408,24 @@ def mask_rows(x, lens, col_begin=0, col_count=None):
     return x
 
 
+def spec_augment_fwd(x, time_mask, feat_mask, embed):
+    """x: bf16 [B, T, H] contiguous; time_mask: uint8 [B, T] or None; feat_mask: uint8 [B, H] or None; embed: fp32 [H]."""
+    B, T, H = x.shape
+    y = torch.empty_like(x)
+    _lib.check(_L().smx_spec_augment_fwd(_ptr(x), _ptr(y), _ptr(time_mask), _ptr(feat_mask), _ptr(embed), B, T, H,
+                                         _stream()), "spec_augment_fwd")
+    return y
+
+
+def spec_augment_bwd(dy, time_mask, feat_mask, want_dembed=True):
+    B, T, H = dy.shape
+    dx = torch.empty_like(dy)
+    dembed = zeros_f32(H, device=dy.device) if (want_dembed and time_mask is not None) else None
+    _lib.check(_L().smx_spec_augment_bwd(_ptr(dy), _ptr(dx), _ptr(dembed), _ptr(time_mask), _ptr(feat_mask), B, T, H,
+                                         _stream()), "spec_augment_bwd")
+    return dx, dembed
+
+
 def colsum(x2d):
     """fp32 column sums of a [rows, cols] bf16 matrix (row stride may exceed cols)."""
     rows, cols = x2d.shape

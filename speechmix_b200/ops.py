@@ -233,6 +233,26 @@ def mask_rows(x, lens):
     return MaskRowsFn.apply(x, lens)
 
 
+class SpecAugmentFn(torch.autograd.Function):
+    """hf:models/wav2vec2/modeling_wav2vec2.py:1280-1324: time-masked frames are replaced by ``masked_spec_embed``,
+    feature-masked channels are cleared.  The masks (uint8, on the device) are drawn on the host by the caller."""
+
+    @staticmethod
+    def forward(ctx, x, embed, time_mask, feat_mask):
+        ctx.masks = (time_mask, feat_mask)
+        return K.spec_augment_fwd(x.contiguous(), time_mask, feat_mask, embed.detach().float().contiguous())
+
+    @staticmethod
+    def backward(ctx, dy):
+        time_mask, feat_mask = ctx.masks
+        dx, dembed = K.spec_augment_bwd(dy.contiguous(), time_mask, feat_mask, want_dembed=ctx.needs_input_grad[1])
+        return dx, dembed, None, None
+
+
+def spec_augment(x, embed, time_mask, feat_mask):
+    return SpecAugmentFn.apply(x, embed, time_mask, feat_mask)
+
+
 # ---------------------------------------------------------------------------
 class AttnBlockFn(torch.autograd.Function):
     """(self- or cross-) attention sub-block with its residual and LayerNorm.

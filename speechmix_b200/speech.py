@@ -220,6 +220,35 @@ class SpeechEncoderModel(nn.Module):
             n = torch.div(n - k, s, rounding_mode="floor") + 1
         return n
 
+    def _mask_hidden_states(self, x, frame_len=None):
+        """SpecAugment, hf:...wav2vec2.py:1280-1324 (hubert: same code): training only, ``apply_spec_augment`` and a
+        positive ``mask_time_prob`` / ``mask_feature_prob``.  The span indices are drawn on the host by the SAME
+        function the reference's backbone calls (transformers' ``_compute_mask_indices``, numpy's global RNG), so a
+        seeded run masks the same frames as the reference; the replacement itself is a CUDA kernel."""
+        cfg = self.config
+        if not self.training or not getattr(cfg, "apply_spec_augment", True):
+            return x
+        if cfg.mask_time_prob <= 0 and cfg.mask_feature_prob <= 0:
+            return x
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("SpecAugment draws a new mask on the host every step and cannot be captured in a CUDA "
+                               "graph; set apply_spec_augment=False for graphed steps")
+        from transformers.models.wav2vec2.modeling_wav2vec2 import _compute_mask_indices
+        B, T, H = x.shape
+        time_mask = feat_mask = None
+        if cfg.mask_time_prob > 0:
+            frames = None
+            if frame_len is not None and cfg.model_type != "hubert":   # HubertModel draws over all T frames (hf hubert :1020)
+                frames = (torch.arange(T)[None, :] < frame_len.cpu()[:, None]).long()
+            idx = _compute_mask_indices((B, T), mask_prob=cfg.mask_time_prob, mask_length=cfg.mask_time_length,
+                                        attention_mask=frames, min_masks=cfg.mask_time_min_masks)
+            time_mask = torch.from_numpy(idx).to(device=x.device, dtype=torch.uint8)
+        if cfg.mask_feature_prob > 0:
+            idx = _compute_mask_indices((B, H), mask_prob=cfg.mask_feature_prob, mask_length=cfg.mask_feature_length,
+                                        min_masks=cfg.mask_feature_min_masks)
+            feat_mask = torch.from_numpy(idx).to(device=x.device, dtype=torch.uint8)
+        return ops.spec_augment(x, self.masked_spec_embed, time_mask, feat_mask)
+
     def forward(self, input_values, attention_mask=None, output_hidden_states=False, **kwargs):
         """attention_mask ([B, n] 1 = audio sample, 0 = padding; the reference itself never passes one --
         SURVEY section 8f row 1): HF semantics, hf:...wav2vec2.py:1026-1044, :669-681 -- the conv stack runs over the
@@ -233,10 +262,7 @@ class SpeechEncoderModel(nn.Module):
                 raise NotImplementedError("fp32 verification mode has no key-padding mask")
             lens = self.feat_extract_output_lengths(attention_mask.to(torch.long).sum(-1))
             frame_len = lens.clamp(1, x.shape[1]).to(device=x.device, dtype=torch.int32)
-        # SpecAugment (hf :1280-1324) only fires in training with mask_time_prob > 0.
-        if self.training and getattr(self.config, "apply_spec_augment", False) and \
-                (self.config.mask_time_prob > 0 or self.config.mask_feature_prob > 0):
-            raise NotImplementedError("SpecAugment masking is not implemented; set apply_spec_augment=False")
+        x = self._mask_hidden_states(x, frame_len)
         x, hs = self.encoder(x, output_hidden_states=output_hidden_states, frame_len=frame_len)
         return SpeechOutput(last_hidden_state=x, hidden_states=hs if output_hidden_states else None)
 

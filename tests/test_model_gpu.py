@@ -469,3 +469,61 @@ def test_attention_mask_true_length_extension(name, cuda_device):
             continue
         err = float((pm[k].grad.cpu() - p.grad).norm())
         assert err <= 5e-2 * float(p.grad.norm()) + 2e-4 * scale, (k, err, float(p.grad.norm()))
+
+
+@pytest.mark.parametrize("kind,model_type,with_mask", [("mini", "wav2vec2", False), ("mini_large", "hubert", False),
+                                                       ("mini_large", "wav2vec2", True)])
+def test_spec_augment_matches_reference_backbone(kind, model_type, with_mask, cuda_device):
+    """SpecAugment is ON in the stock wav2vec2 / HuBERT configs the reference trains with
+    (hf:models/wav2vec2/modeling_wav2vec2.py:1280-1324).  The span indices come from the same transformers function
+    under the same numpy seed on both sides, so the masked frames are identical; checked: speech states, loss, and the
+    gradients incl. ``masked_spec_embed`` (which only the masked frames feed)."""
+    import numpy as np
+    from oracle import hf_oracle as O
+    from speechmix_b200 import SpeechMixEED
+    sp_cfg = O.speech_config(kind, model_type=model_type)
+    sp_cfg.apply_spec_augment = True
+    sp_cfg.mask_time_prob, sp_cfg.mask_time_length, sp_cfg.mask_time_min_masks = 0.3, 3, 2
+    sp_cfg.mask_feature_prob, sp_cfg.mask_feature_length, sp_cfg.mask_feature_min_masks = 0.2, 8, 1
+    tx_cfg = O.text_config("bart-mini")
+    speech, text = O.build_backbones(sp_cfg, tx_cfg, seed=0)
+    ora = O.OracleEED(speech, text, down_scale=2)
+    O.reinit_glue(ora, seed=1)
+    ora.train(True)
+    assert "encoder_model.masked_spec_embed" in ora.state_dict()
+    x, labels = O.synthetic_batch(3, 1.0, 8, tx_cfg.vocab_size, seed=0)
+    kw_o, kw_m = {}, {}
+    if with_mask:
+        mask = torch.ones(x.shape, dtype=torch.long)
+        mask[1, 9000:] = 0
+        x = x * mask
+        kw_o, kw_m = {"attention_mask": mask}, {"attention_mask": mask.to(cuda_device)}
+    mine = SpeechMixEED(sp_cfg, tx_cfg, down_scale=2)
+    mine.load_state_dict(ora.state_dict())
+    mine = mine.to(cuda_device).train(True)
+    np.random.seed(1234)
+    ref = ora(x, labels=labels, keep_full_logits=True, **kw_o)
+    np.random.seed(1234)
+    out = mine(x.to(cuda_device), labels=labels.to(cuda_device), **kw_m)
+    np.random.seed(99)
+    ref_other = ora(x, labels=labels, **kw_o)
+    assert abs(float(ref["loss"]) - float(ref_other["loss"])) > 1e-6          # the masks matter
+    assert abs(float(out["loss"]) - float(ref["loss"])) < 3e-3
+    assert _rel(out["speech_last_hidden_state"], ref["speech_last_hidden_state"]) < 4e-2
+    ref["loss"].backward()
+    out["loss"].backward()
+    po, pm = dict(ora.named_parameters()), dict(mine.named_parameters())
+    scale = max(float(p.grad.norm()) for p in po.values() if p.grad is not None)
+    assert po["encoder_model.masked_spec_embed"].grad is not None
+    assert float(po["encoder_model.masked_spec_embed"].grad.norm()) > 0
+    for k, p in po.items():
+        if p.grad is None:
+            continue
+        err = float((pm[k].grad.cpu() - p.grad).norm())
+        assert err <= 5e-2 * float(p.grad.norm()) + 2e-4 * scale, (k, err, float(p.grad.norm()))
+    mine.eval()                                                                # inference: no masking
+    np.random.seed(5)
+    a = mine(x.to(cuda_device), labels=labels.to(cuda_device), **kw_m)["speech_last_hidden_state"]
+    np.random.seed(6)
+    b = mine(x.to(cuda_device), labels=labels.to(cuda_device), **kw_m)["speech_last_hidden_state"]
+    assert _rel(a, b) < 2e-2      # a masked frame would differ by O(1); run-to-run noise is a bf16 ulp (atomics)
