@@ -50,6 +50,20 @@ DEFAULT_FIXED_EXCEPT = ["layer_norm", "encoder_attn", "enc_to_dec_proj", "length
                         "attention"]
 
 
+def _warn_ignored_dropout(speech_cfg, text_cfg):
+    """Dropout is the one regulariser of the reference's training recipe that the fused kernels do not apply yet
+    (DESIGN.md section 7): say so once instead of silently training without it.  LayerDrop and SpecAugment are
+    honoured."""
+    knobs = [("speech", speech_cfg, ("hidden_dropout", "attention_dropout", "activation_dropout", "feat_proj_dropout")),
+             ("text", text_cfg, ("dropout", "attention_dropout", "activation_dropout", "dropout_rate"))]
+    live = ["%s.%s=%g" % (side, k, getattr(cfg, k)) for side, cfg, ks in knobs for k in ks
+            if isinstance(getattr(cfg, k, 0.0), float) and getattr(cfg, k, 0.0) > 0.0]
+    if live:
+        import warnings
+        warnings.warn("speechmix_b200 does not implement dropout: training behaves as if these were 0 -> " +
+                      ", ".join(live), stacklevel=3)
+
+
 class SpeechMixEED(nn.Module):
     """ref:speechmix/hf_model.py:185-447 (HFSpeechMixEED)."""
 
@@ -63,6 +77,7 @@ class SpeechMixEED(nn.Module):
         # names in the reference; config objects (random init) are accepted too for offline use.
         self.encoder_model = speech_from_pretrained(speech_model_config)
         self.decoder_model = text_from_pretrained(nlp_model_config)
+        _warn_ignored_dropout(self.encoder_model.config, self.decoder_model.config)
         self.config = SpeechMixConfig(self.encoder_model.config, self.decoder_model.config)
         self.tokenizer = tokenizer
         if tokenizer is None and isinstance(nlp_model_config, str):

@@ -135,3 +135,19 @@ def test_cpu_call_fails_loudly():
     m = SpeechMixEED(O.speech_config("mini"), O.text_config("bart-mini"), down_scale=2)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.randn(1, 16000), labels=torch.randint(4, 100, (1, 4)))
+
+
+def test_ignored_dropout_is_reported_once_not_silently():
+    """dropout is not implemented; a config that asks for it gets a warning naming the knobs."""
+    import warnings
+    from transformers import BartConfig, Wav2Vec2Config
+    from speechmix_b200.model import _warn_ignored_dropout
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        _warn_ignored_dropout(Wav2Vec2Config(), BartConfig())
+        assert len(w) == 1 and "speech.hidden_dropout=0.1" in str(w[0].message) and "text.dropout=0.1" in str(w[0].message)
+    quiet = Wav2Vec2Config(hidden_dropout=0.0, attention_dropout=0.0, activation_dropout=0.0, feat_proj_dropout=0.0)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        _warn_ignored_dropout(quiet, BartConfig(dropout=0.0, attention_dropout=0.0, activation_dropout=0.0))
+        assert len(w) == 0
