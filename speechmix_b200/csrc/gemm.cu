@@ -26,7 +26,17 @@ namespace gemm {
 constexpr int BM = 128, BN = 256, BK = 64;   // per CTA: 128 rows; the pair covers PAIR_M = 256 rows
 constexpr int PAIR_M = 2 * BM;
 constexpr int BN_HALF = BN / 2;              // columns of B each CTA of the pair loads
-constexpr int STAGES = 6;
+// Ring depth / staging banks are compile-time knobs.  Measured on B200 (gpurun_out/r01s_gemm_*.log, tools/probe_gemm.py):
+// 5 stages + two staging tiles per epilogue warp (bulk store of one tile overlapping the fill of the other) is
+// within noise of 6 stages + one tile on the K = 768 shapes and no better on the step, so the deeper ring stays.
+#ifndef SMX_GEMM_STAGES
+#define SMX_GEMM_STAGES 6
+#endif
+#ifndef SMX_GEMM_STG_BANKS
+#define SMX_GEMM_STG_BANKS 1
+#endif
+constexpr int STAGES = SMX_GEMM_STAGES;
+constexpr int STG_BANKS = SMX_GEMM_STG_BANKS;  // staging tiles per epilogue warp
 constexpr int A_BYTES = BM * BK * 2;       // 16 KiB
 constexpr int B_BYTES = BN_HALF * BK * 2;  // 16 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -34,7 +44,7 @@ constexpr int PANEL_BYTES = 64 * BK * 2;  // one 64(MN) x 64(K) MN-major panel, 
 constexpr int BAR_BYTES = 256;
 constexpr int STG_BYTES = 32 * 128;  // per epilogue warp: 32 rows x 64 bf16, 128B-swizzled, TMA-store staging
 constexpr int OFF_STG = STAGES * STAGE_BYTES;
-constexpr int OFF_BAR = OFF_STG + 8 * STG_BYTES;
+constexpr int OFF_BAR = OFF_STG + 8 * STG_BANKS * STG_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + BAR_BYTES + 1024;
 constexpr int NUM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int EPI_WARPS = 8;
@@ -531,6 +541,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                         ((p.aux_out == nullptr) || ((reinterpret_cast<uintptr_t>(p.aux_out) & 15) == 0)) &&
                         ((p.aux_in == nullptr) || ((reinterpret_cast<uintptr_t>(p.aux_in) & 15) == 0)) &&
                         (p.bias == nullptr || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
+    int bank = 0;   // two-bank mode: toggles after EVERY bulk store of this warp, across tiles (store k uses bank k & 1,
+                    // and waiting until at most one store is pending means store k - 2 has released that bank)
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
       const TileCoord t = decode_tile(p, tile);
       const int n0 = t.n_blk * BN;
@@ -547,7 +559,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const bool row_ok = row < p.m;
 
       const bool use_in = FAST && EPI == 0 && MODE != SMX_GEMM_TN && p.tma_store && p.tma_in != 0;
-      uint8_t* stg = smem + OFF_STG + (warp - 2) * STG_BYTES;
+      uint8_t* stg = smem + OFF_STG + (warp - 2) * STG_BANKS * STG_BYTES;
       int ep_bidx = 0, ep_row0 = 0;
       if (MODE != SMX_GEMM_TN) {
         ep_bidx = t.m_blk / p.m_tiles_per_batch;
@@ -720,16 +732,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 uint4 q[8];
                 if (p.act == SMX_ACT_GELU_G) gelu_both_row(f, q);
                 else pack_row(f, q);
-                if (lane == 0) tma_store_wait_read<0>();
+                // two banks (and no TMA-loaded input sharing the tile): only the store BEFORE the previous one has to
+                // have released its tile, so the wait no longer serialises behind the store just issued
+                uint8_t* sa = stg;
+                if (STG_BANKS == 2 && !use_in) {
+                  sa = stg + bank * STG_BYTES;
+                  bank ^= 1;
+                  if (lane == 0) tma_store_wait_read<1>();
+                } else {
+                  if (lane == 0) tma_store_wait_read<0>();
+                }
                 __syncwarp();
-                stage_row_packed(stg, lane, q);
+                stage_row_packed(sa, lane, q);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                  tma_store_3d(&tma_aux, stg, col0, row0, bidx);
+                  tma_store_3d(&tma_aux, sa, col0, row0, bidx);
                   tma_store_commit();
                 }
               }
+              uint8_t* sc = stg;
               if (use_in) {
                 mbar_wait(&inbar[warp - 2], in_phase);
                 in_phase ^= 1;
@@ -744,14 +766,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 if (row_ok) epi_act_res(p, f, c_off, res_off, col0);
                 uint4 q[8];
                 pack_row(f, q);
-                if (lane == 0) tma_store_wait_read<0>();
+                if (STG_BANKS == 2) {
+                  sc = stg + bank * STG_BYTES;
+                  bank ^= 1;
+                  if (lane == 0) tma_store_wait_read<1>();
+                } else {
+                  if (lane == 0) tma_store_wait_read<0>();
+                }
                 __syncwarp();
-                stage_row_packed(stg, lane, q);
+                stage_row_packed(sc, lane, q);
               }
               fence_proxy_async_smem();
               __syncwarp();
               if (lane == 0) {
-                tma_store_3d(&tma_c, stg, col0, row0, bidx);
+                tma_store_3d(&tma_c, sc, col0, row0, bidx);
                 tma_store_commit();
                 if (use_in && pr + 1 < BN / 128 && col0 + 64 + 32 < p.n) {  // next input tile of this warp
                   tma_store_wait_read<0>();
