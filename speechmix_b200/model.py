@@ -247,20 +247,22 @@ class SpeechMixEED(nn.Module):
 
     @torch.no_grad()
     def generate(self, input_values, max_length=32, decoder_text_prompt=None, eos_token_id=None, use_cache=True,
-                 precision=None, cuda_graph=False, **kwargs):
+                 precision=None, cuda_graph=False, attention_mask=None, **kwargs):
         """Greedy decode (ref:eval.py:12-13; loop semantics of ref:eval.ipynb cell 6).  The speech encoder, bridge
         and text encoder run once.  ``use_cache=True`` (default): KV-cached decoder, one pass per new token
         (the role of ref:speechmix/hf_model.py:314-338 ``prepare_inputs_for_generation`` + ``past_key_values``);
         ``use_cache=False``: the notebook's full-prefix recompute.  Both return the same ids.
         ``cuda_graph=True`` replays the whole cached decode loop as one CUDA graph (captured once per input shape
-        and ``max_length``)."""
+        and ``max_length``).  ``attention_mask``: the variable-length extension of ``forward`` (speech encoder only)."""
         if precision == "fp32":
+            if attention_mask is not None:
+                raise NotImplementedError("fp32 verification mode has no key-padding mask")
             with ops.fp32_verification():
                 return self.generate(input_values, max_length, decoder_text_prompt, eos_token_id, use_cache,
                                      cuda_graph=cuda_graph)
         cfg = self.decoder_model.config
         eos = cfg.eos_token_id if eos_token_id is None else eos_token_id
-        enc = self.encoder_model(input_values, output_hidden_states=True)
+        enc = self.encoder_model(input_values, attention_mask=attention_mask, output_hidden_states=True)
         B = input_values.shape[0]
         if use_cache:
             inputs_embeds = self.bridge(enc)

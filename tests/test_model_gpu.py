@@ -469,6 +469,17 @@ def test_attention_mask_true_length_extension(name, cuda_device):
             continue
         err = float((pm[k].grad.cpu() - p.grad).norm())
         assert err <= 5e-2 * float(p.grad.norm()) + 2e-4 * scale, (k, err, float(p.grad.norm()))
+    # generate() takes the same mask: the cached and the full-recompute decode agree with each other, and the mask
+    # reaches the encoder (the padded sample's speech states differ from the unmasked run's)
+    mine.eval()
+    xm, mm = x.to(cuda_device), mask.to(cuda_device)
+    with torch.no_grad():
+        ids_c = mine.generate(xm, max_length=8, attention_mask=mm)
+        ids_f = mine.generate(xm, max_length=8, attention_mask=mm, use_cache=False)
+        e_m = mine.encoder_model(xm, attention_mask=mm).last_hidden_state
+        e_n = mine.encoder_model(xm).last_hidden_state
+    assert torch.equal(ids_c[:, :ids_f.shape[1]], ids_f[:, :ids_c.shape[1]])
+    assert _rel(e_m[0], e_n[0]) < 2e-2 and _rel(e_m[1], e_n[1]) > 5e-2     # sample 0 is unpadded, sample 1 is not
 
 
 @pytest.mark.parametrize("kind,model_type,with_mask", [("mini", "wav2vec2", False), ("mini_large", "hubert", False),

@@ -106,6 +106,52 @@ def rowwise():
         ok &= _rep("ln dbeta", db, beta.grad, 5e-3)
         ok &= _rep("colsum", K.colsum(dy), dy.float().sum(0), 1e-3)
         ok &= _rep("dact", K.dact(dy, x), dy.float() * torch.autograd.functional.jvp(F.gelu, x.float(), torch.ones_like(x.float()))[1])
+    # LayerNorm backward with a residual-branch gradient (shared-memory-ring kernel) incl. a ragged width
+    for (R, C) in [(777, 768), (300, 1024), (64, 264)]:
+        x = torch.randn(R, C, device="cuda", generator=g).to(torch.bfloat16)
+        gamma = (1 + 0.1 * torch.randn(C, device="cuda", generator=g)).requires_grad_(True)
+        beta = (0.1 * torch.randn(C, device="cuda", generator=g)).requires_grad_(True)
+        dy = torch.randn(R, C, device="cuda", generator=g).to(torch.bfloat16)
+        dres = torch.randn(R, C, device="cuda", generator=g).to(torch.bfloat16)
+        y, _, mean, rstd = K.layernorm_fwd(x, gamma.detach(), beta.detach())
+        xr = x.float().requires_grad_(True)
+        F.layer_norm(xr, (C,), gamma, beta, 1e-5).backward(dy.float())
+        dx, dg, db = K.layernorm_bwd(dy, x, gamma.detach(), mean, rstd, dres=dres)
+        ok &= _rep(f"ln bwd+dres dx {R}x{C}", dx, xr.grad + dres.float())
+        ok &= _rep("ln bwd+dres dgamma", dg, gamma.grad, 5e-3)
+        ok &= _rep("ln bwd+dres dbeta", db, beta.grad, 5e-3)
+    # padded-row masking and SpecAugment replacement / gradient
+    B, T, C = 3, 50, 256
+    x = torch.randn(B, T, C, device="cuda", generator=g).to(torch.bfloat16)
+    lens = torch.tensor([50, 17, 1], device="cuda", dtype=torch.int32)
+    keep = (torch.arange(T, device="cuda")[None, :] < lens[:, None])
+    ok &= _rep("mask_rows", K.mask_rows(x.clone(), lens), x.float() * keep[..., None])
+    part = K.mask_rows(x.clone(), lens, col_begin=64, col_count=128).float()
+    ref = x.float().clone()
+    ref[:, :, 64:192] *= keep[..., None]
+    ok &= _rep("mask_rows column range", part, ref)
+    tm = (torch.rand(B, T, device="cuda", generator=g) < 0.3).to(torch.uint8)
+    fm = (torch.rand(B, C, device="cuda", generator=g) < 0.2).to(torch.uint8)
+    emb = torch.randn(C, device="cuda", generator=g)
+    for (t_, f_) in [(tm, fm), (tm, None), (None, fm)]:
+        y = K.spec_augment_fwd(x, t_, f_, emb)
+        ref = x.float().clone()
+        if t_ is not None:
+            ref[t_.bool()] = emb.to(torch.bfloat16).float()
+        if f_ is not None:
+            ref = ref * (1 - f_.float())[:, None, :]
+        ok &= _rep("spec_augment fwd", y, ref)
+        dy = torch.randn(B, T, C, device="cuda", generator=g).to(torch.bfloat16)
+        dx, de = K.spec_augment_bwd(dy, t_, f_)
+        live = torch.ones(B, T, C, device="cuda")
+        if t_ is not None:
+            live = live * (1 - t_.float())[..., None]
+        if f_ is not None:
+            live = live * (1 - f_.float())[:, None, :]
+        ok &= _rep("spec_augment dx", dx, dy.float() * live)
+        if t_ is not None:
+            w = t_.float()[..., None] * (1.0 if f_ is None else (1 - f_.float())[:, None, :])
+            ok &= _rep("spec_augment dembed", de, (dy.float() * w).sum((0, 1)), 1e-3)
     # rms
     x = torch.randn(200, 768, device="cuda", generator=g).to(torch.bfloat16)
     gamma = 1 + 0.1 * torch.randn(768, device="cuda", generator=g)
