@@ -144,6 +144,36 @@ typedef struct {
   int32_t first_chunk;
 } SmxCastEntry;
 int smx_multi_cast(const SmxCastEntry* table, int32_t n_entries, int32_t total_chunks, void* stream);
+/* ------------------------------------------------------------------------
+ * Multi-tensor Adafactor step -- the optimizer of the reference recipe (ref:train.py:298 optim="adafactor" =
+ * transformers.optimization.Adafactor.step with relative_step=False, scale_parameter=False, beta1=None, as the HF
+ * Trainer configures it).  One call updates every listed fp32 parameter:
+ *   tensors with len(shape) >= 2 are factored over their last two dims [rows][cols], leading dims = `batch`
+ *   independent slices: row = exp_avg_sq_row [batch][rows], col = exp_avg_sq_col [batch][cols];
+ *   vectors (factored = 0): row = exp_avg_sq [numel], col unused, batch = rows = 1, cols = numel.
+ * row_acc / col_acc / sumsq are per-tensor scratch carved out of ONE block `scratch` (zeroed by the call);
+ * rmean is [batch] scratch.  tiles: 64 x 256 element tiles covering every slice once (vectors are viewed as
+ * [ceil(numel/256)][256]); slices: one (tensor, b) pair per factored slice.  All three tables are DEVICE arrays.
+ * beta2t = 1 - step^decay_rate is computed by the caller; eps1 = eps[0].
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  float* p;
+  const float* g;
+  float *row, *col, *row_acc, *col_acc, *rmean, *sumsq;
+  int64_t batch, rows, cols, numel;
+  int32_t factored, pad_;
+} SmxAdafactorTensor;
+typedef struct {
+  int32_t tensor, b, r0, c0;
+} SmxAdafactorTile;
+typedef struct {
+  int32_t tensor, b;
+} SmxAdafactorSlice;
+int smx_adafactor_step(const SmxAdafactorTensor* tensors, int32_t n_tensors, const SmxAdafactorTile* tiles,
+                       int32_t n_tiles, const SmxAdafactorSlice* slices, int32_t n_slices, void* scratch,
+                       int64_t scratch_bytes, float beta2t, float eps1, float lr, float clip_threshold,
+                       float weight_decay, void* stream);
+
 int smx_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
 int smx_act_bf16(const void* x, void* y, int64_t n, int act, void* stream);
 /* out = dy * act'(pre), act in {SMX_ACT_GELU, SMX_ACT_RELU} */

@@ -51,6 +51,13 @@ class SmxAttn(Structure):
                 ("kv_len", c_void_p)]
 
 
+class SmxAdafactorTensor(Structure):
+    _fields_ = [("p", c_void_p), ("g", c_void_p), ("row", c_void_p), ("col", c_void_p), ("row_acc", c_void_p),
+                ("col_acc", c_void_p), ("rmean", c_void_p), ("sumsq", c_void_p),
+                ("batch", c_int64), ("rows", c_int64), ("cols", c_int64), ("numel", c_int64),
+                ("factored", c_int32), ("pad_", c_int32)]
+
+
 _P = c_void_p
 _I64 = c_int64
 
@@ -64,6 +71,8 @@ SIGNATURES = {
     "smx_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, c_int, c_int, _P]),
     "smx_colsum": (c_int, [_P, _P, _I64, _I64, _I64, _P]),
     "smx_mask_rows": (c_int, [_P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _P]),
+    "smx_adafactor_step": (c_int, [_P, c_int32, _P, c_int32, _P, c_int32, _P, _I64, c_float, c_float, c_float, c_float,
+                                   c_float, _P]),
     "smx_spec_augment_fwd": (c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _P]),
     "smx_spec_augment_bwd": (c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _P]),
     "smx_cast_f32_to_bf16": (c_int, [_P, _P, _I64, _P]),

@@ -151,3 +151,42 @@ def test_ignored_dropout_is_reported_once_not_silently():
         warnings.simplefilter("always")
         _warn_ignored_dropout(quiet, BartConfig(dropout=0.0, attention_dropout=0.0, activation_dropout=0.0))
         assert len(w) == 0
+
+
+def test_adafactor_tile_table_covers_every_element_once():
+    """speechmix_b200/optim.py: the 64 x 256 tile table of the fused Adafactor step (host logic, no GPU)."""
+    import numpy as np
+    from speechmix_b200.optim import TILE_C, TILE_R, factored_dims, tile_table
+    shapes = [(768,), (1,), (1000, 768), (512, 512, 3), (512, 1, 10), (768, 48, 128), (1, 50265), (7, 3, 65, 257), (300,)]
+    tiles, slices = tile_table(shapes)
+    assert tiles.dtype == np.int32 and slices.dtype == np.int32
+    for i, shape in enumerate(shapes):
+        factored, batch, rows, cols = factored_dims(shape)
+        n = int(np.prod(shape))
+        cover = np.zeros(n, np.int64)
+        for (_, b, r0, c0) in tiles[tiles[:, 0] == i]:
+            if factored:
+                rr = np.arange(r0, min(r0 + TILE_R, rows))
+                cc = np.arange(c0, min(c0 + TILE_C, cols))
+                idx = ((b * rows + rr)[:, None] * cols + cc[None, :]).ravel()
+            else:
+                idx = np.arange(r0 * TILE_C, min((r0 + TILE_R) * TILE_C, n))
+            cover[idx] += 1
+        assert (cover == 1).all(), shape
+        assert (slices[:, 0] == i).sum() == (batch if factored else 0)
+    assert factored_dims((4, 5, 6)) == (True, 4, 5, 6) and factored_dims((9,)) == (False, 1, 1, 9)
+
+
+def test_fused_adafactor_rejects_unsupported_modes():
+    import pytest
+    import torch
+    from speechmix_b200.optim import FusedAdafactor
+    w = torch.nn.Parameter(torch.zeros(4, 4))
+    for kw in ({"lr": None}, {"lr": 1e-3, "relative_step": True}, {"lr": 1e-3, "scale_parameter": True},
+               {"lr": 1e-3, "beta1": 0.9}):
+        with pytest.raises(NotImplementedError):
+            FusedAdafactor([w], **kw)
+    opt = FusedAdafactor([w], lr=1e-3)
+    w.grad = torch.ones(4, 4)
+    with pytest.raises(RuntimeError):      # CPU parameter: no fallback
+        opt.step()

@@ -33,3 +33,48 @@ def test_attention(name, cuda_device):
 @pytest.mark.parametrize("name", _cases(probe_misc))
 def test_rowwise_conv0_posconv_lmhead(name, cuda_device):
     _run(probe_misc, name, cuda_device)
+
+
+@pytest.mark.parametrize("weight_decay", [0.0, 0.01])
+def test_fused_adafactor_matches_transformers(weight_decay, cuda_device):
+    """ref:train.py:298 optim="adafactor" -> transformers.optimization.Adafactor(scale_parameter=False,
+    relative_step=False): parameters and second-moment state after 4 steps, every shape family of the model
+    (matrices, conv weights with leading dims, tall / wide / tiny, vectors), one launch group per step."""
+    import torch
+    from transformers.optimization import Adafactor
+    from speechmix_b200.optim import FusedAdafactor
+    g = torch.Generator(device="cuda").manual_seed(0)
+    shapes = [(768,), (1,), (1000, 768), (512, 64, 3), (128, 1, 10), (96, 48, 128), (1, 5000), (3072, 768), (300,),
+              (2, 3, 65, 257)]
+    ref_p = [torch.nn.Parameter(torch.randn(s, device="cuda", generator=g) * 0.1) for s in shapes]
+    my_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+    ref = Adafactor(ref_p, lr=5e-4, scale_parameter=False, relative_step=False, weight_decay=weight_decay)
+    mine = FusedAdafactor(my_p, lr=5e-4, weight_decay=weight_decay)
+    for step in range(4):
+        for a, b in zip(ref_p, my_p):
+            gr = torch.randn(a.shape, device="cuda", generator=g) * (10.0 if step == 2 else 0.01)   # clipped / unclipped
+            a.grad, b.grad = gr, gr.clone()
+        ref.step()
+        mine.step()
+    for a, b, s in zip(ref_p, my_p, shapes):
+        d = float((a - b).abs().max())
+        upd = float((a - torch.zeros_like(a)).abs().max()) + 1e-12
+        assert d <= 2e-6 + 1e-5 * upd, (s, d)
+        sa, sb = ref.state[a], mine.state[b]
+        assert sa["step"] == sb["step"] == 4
+        for k in ("exp_avg_sq_row", "exp_avg_sq_col", "exp_avg_sq"):
+            if k in sa:
+                assert sb[k].shape == sa[k].shape
+                assert float(((sa[k] - sb[k]).abs() / (sa[k].abs() + 1e-20)).max()) < 1e-4, (s, k)
+    # a parameter that starts receiving gradients later has its own step count -> its own launch group
+    late = torch.nn.Parameter(torch.randn(64, 64, device="cuda", generator=g))
+    late_ref = torch.nn.Parameter(late.detach().clone())
+    mine.add_param_group({"params": [late]})
+    ref.add_param_group({"params": [late_ref]})
+    for a, b in zip(ref_p + [late_ref], my_p + [late]):
+        gr = torch.randn(a.shape, device="cuda", generator=g) * 0.01
+        a.grad, b.grad = gr, gr.clone()
+    ref.step()
+    mine.step()
+    assert float((late - late_ref).abs().max()) < 2e-6 and mine.state[late]["step"] == 1
+    assert float((ref_p[2] - my_p[2]).abs().max()) < 5e-6
