@@ -9,7 +9,8 @@ The CUDA library must be built first (``python -m speechmix_b200.build``); there
 from .model import (HFSpeechMixAdapter, HFSpeechMixEED, HFSpeechMixFixed, HFSpeechMixSelf,  # noqa: F401
                     SpeechMixAdapter, SpeechMixConfig, SpeechMixEED, SpeechMixFixed, SpeechMixSelf,
                     handle_decoder_input_none, shift_tokens_right)
+from .optim import FusedAdafactor  # noqa: F401
 
 __all__ = ["SpeechMixEED", "SpeechMixFixed", "SpeechMixAdapter", "SpeechMixSelf", "HFSpeechMixEED", "HFSpeechMixFixed",
            "HFSpeechMixAdapter", "HFSpeechMixSelf", "SpeechMixConfig", "shift_tokens_right",
-           "handle_decoder_input_none"]
+           "handle_decoder_input_none", "FusedAdafactor"]
