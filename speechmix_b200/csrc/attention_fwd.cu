@@ -4,10 +4,13 @@
 //   warp 0      TMA producer: Q once, K/V tiles double-buffered (128-byte swizzle)
 //   warp 1      tcgen05.mma issuer: S = Q.K^T  (128x128x64, TMEM cols 0..127)
 //                                   PV = P.V   (128x64x128, TMEM cols 128..255, double-buffered)
-//   warps 2..5  softmax: one query row per thread; S row read from TMEM, online max / sum in
-//               fp32, P written to smem as bf16 in the UMMA K-major swizzled layout, running O
-//               kept in registers and rescaled as PV tiles arrive.
-// Scores and probabilities never reach HBM; LSE is written for the backward pass.
+//               issue order S_0, [S_{j+1}, PV_j]...: the next score tile goes out as soon as the softmax warps
+//               have released the score buffer, BEFORE the P.V product of the current tile
+//   warps 2..5  softmax: one query row per thread; S row read from TMEM (loads one chunk ahead of the
+//               arithmetic), online max / sum in fp32 (packed fp32 pairs), P written to smem as bf16 in the
+//               UMMA K-major swizzled layout, running O kept in registers and rescaled as PV tiles arrive.
+// Scores and probabilities never reach HBM; LSE is written for the backward pass.  Optional per-sample key
+// counts (kv_len): tiles past the count are neither loaded nor computed, the tile it cuts is masked per chunk.
 #include "../../include/speechmix_sm100.h"
 #include "host_common.h"
 #include "sm100_prims.cuh"
