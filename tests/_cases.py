@@ -16,6 +16,8 @@ def load_fixture(name):
 
 def build_oracle(fx, cls=None):
     sp_cfg = O.speech_config(fx["speech"], model_type=fx["speech_type"])
+    for k, v in fx.get("speech_overrides", {}).items():     # e.g. SpecAugment switched on (mini_specaug)
+        setattr(sp_cfg, k, v)
     tx_cfg = O.text_config(fx["text"])
     speech, text = O.build_backbones(sp_cfg, tx_cfg, seed=0)
     model = (cls or O.OracleEED)(speech, text, **fx["kwargs"])

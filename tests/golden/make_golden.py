@@ -43,6 +43,17 @@ CASES = {
     "mini_large_mbart": ("mini_large", "hubert", "mbart-mini", dict(down_scale=2), 2, 1.0, 8, False, True),
     "mini_t5": ("mini", "wav2vec2", "t5-mini", dict(down_scale=2), 2, 1.0, 8, False, True),
     "cfg1_base": ("base", "wav2vec2", "bart-base", dict(down_scale=2), 1, 5.0, 24, False, False),
+    # paths beyond the plain call: SpecAugment (ON in the stock backbone configs; span indices from numpy's global RNG,
+    # seeded right before the forward) and the decoder text prompt (ref :433-436, tokenised by the reference itself)
+    "mini_specaug": ("mini", "wav2vec2", "bart-mini", dict(down_scale=2), 3, 1.0, 8, False, True),
+    "mini_prompt": ("mini", "wav2vec2", "bart-mini", dict(down_scale=2), 2, 1.0, 8, False, True),
+}
+EXTRAS = {
+    "mini_specaug": {"speech_overrides": {"apply_spec_augment": True, "mask_time_prob": 0.3, "mask_time_length": 3,
+                                          "mask_time_min_masks": 2, "mask_feature_prob": 0.2, "mask_feature_length": 8,
+                                          "mask_feature_min_masks": 1},
+                     "np_seed": 1234},
+    "mini_prompt": {"prompt": "w5 w9 w4 w17 w6"},
 }
 
 
@@ -80,7 +91,10 @@ def sample(t, n=64):
 def run_case(name):
     sp_kind, sp_type, tx_kind, kw, B, secs, t_dec, ignore_tail, backward = CASES[name]
     speechmix = import_reference()
+    extra = EXTRAS.get(name, {})
     sp_cfg = O.speech_config(sp_kind, model_type=sp_type)
+    for k, v in extra.get("speech_overrides", {}).items():
+        setattr(sp_cfg, k, v)
     tx_cfg = O.text_config(tx_kind)
     speech, text = O.build_backbones(sp_cfg, tx_cfg, seed=0)
     tmp = tempfile.mkdtemp(prefix="smx_golden_")
@@ -109,9 +123,18 @@ def run_case(name):
     cap = {}
     h = ref.decoder_model.register_forward_hook(lambda m, i, o: cap.__setitem__("logits", o.logits.detach().clone()))
     h2 = ref.encoder_model.register_forward_hook(lambda m, i, o: cap.__setitem__("speech", o.last_hidden_state.detach().clone()))
-    out_ref = ref(x, labels=labels)
+    import numpy as np
+    kw_ref, kw_ora = {}, {}
+    if "prompt" in extra:   # the reference tokenises the string itself; the oracle (no tokenizer offline) takes the ids
+        prompt_ids = ref.tokenizer(extra["prompt"], return_tensors="pt")["input_ids"]
+        kw_ref, kw_ora = {"decoder_text_prompt": extra["prompt"]}, {"decoder_text_prompt_ids": prompt_ids}
+    if "np_seed" in extra:
+        np.random.seed(extra["np_seed"])
+    out_ref = ref(x, labels=labels, **kw_ref)
     h.remove(); h2.remove()
-    out_ora = ora(x, labels=labels, keep_full_logits=True)
+    if "np_seed" in extra:
+        np.random.seed(extra["np_seed"])
+    out_ora = ora(x, labels=labels, keep_full_logits=True, **kw_ora)
 
     assert torch.equal(out_ref["loss"], out_ora["loss"]), (out_ref["loss"], out_ora["loss"])
     assert torch.equal(out_ref["logits"], out_ora["logits"])
@@ -135,12 +158,17 @@ def run_case(name):
         "speech_last_hidden_state": sample(cap["speech"]),
         "encoder_last_hidden_state": sample(out_ref["encoder_last_hidden_state"]),
     }
+    for k in ("speech_overrides", "np_seed"):
+        if k in extra:
+            fixture[k] = extra[k]
+    if "prompt" in extra:
+        fixture["prompt"], fixture["prompt_ids"] = extra["prompt"], prompt_ids.tolist()
     if backward:
         out_ref["loss"].backward()
         out_ora["loss"].backward()
         grads = {}
         pr, po = dict(ref.named_parameters()), dict(ora.named_parameters())
-        picks = ["enc_to_dec_proj.weight", "length_adapters.0.weight",
+        picks = ["enc_to_dec_proj.weight", "length_adapters.0.weight", "encoder_model.masked_spec_embed",
                  "encoder_model.feature_extractor.conv_layers.0.conv.weight",
                  "encoder_model.feature_extractor.conv_layers.1.conv.weight",
                  "encoder_model.encoder.layers.0.attention.q_proj.weight",

@@ -8,7 +8,7 @@ import torch
 
 from tests._cases import build_oracle, check_sample, load_fixture
 
-MINI = ["mini_eed_ds2", "mini_eed_ds8_ws", "mini_eed_share", "mini_large_mbart", "mini_t5"]
+MINI = ["mini_eed_ds2", "mini_eed_ds8_ws", "mini_eed_share", "mini_large_mbart", "mini_t5", "mini_specaug", "mini_prompt"]
 
 
 @pytest.mark.parametrize("name", MINI)
@@ -20,7 +20,13 @@ def test_oracle_matches_reference_golden(name):
     assert len(model.list_no_grad) == fx["list_no_grad"]
     assert model.speech_encoder_layer == fx["speech_encoder_layer"]
     assert model.nlp_encoder_layer == fx["nlp_encoder_layer"]
-    out = model(x, labels=labels, keep_full_logits=True)
+    kw = {}
+    if "prompt_ids" in fx:        # ids as the reference's own tokenizer produced them from fx["prompt"]
+        kw["decoder_text_prompt_ids"] = torch.tensor(fx["prompt_ids"])
+    if "np_seed" in fx:           # SpecAugment spans come from numpy's global RNG (transformers' _compute_mask_indices)
+        import numpy as np
+        np.random.seed(fx["np_seed"])
+    out = model(x, labels=labels, keep_full_logits=True, **kw)
     assert abs(float(out["loss"]) - fx["loss"]) < 2e-5
     assert out["logits"].tolist() == fx["argmax_ids"]
     check_sample(out["full_logits"], fx["logits"], atol=2e-4)
