@@ -20,7 +20,7 @@ def build_oracle(fx, cls=None):
         setattr(sp_cfg, k, v)
     tx_cfg = O.text_config(fx["text"])
     speech, text = O.build_backbones(sp_cfg, tx_cfg, seed=0)
-    model = (cls or O.OracleEED)(speech, text, **fx["kwargs"])
+    model = (cls or getattr(O, "Oracle" + fx.get("cls", "EED")))(speech, text, **fx["kwargs"])
     O.reinit_glue(model, seed=1)
     model.train(fx["train_mode"])
     x, labels = O.synthetic_batch(fx["batch"], fx["seconds"], fx["t_dec"], tx_cfg.vocab_size,

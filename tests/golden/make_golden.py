@@ -47,6 +47,10 @@ CASES = {
     # seeded right before the forward) and the decoder text prompt (ref :433-436, tokenised by the reference itself)
     "mini_specaug": ("mini", "wav2vec2", "bart-mini", dict(down_scale=2), 3, 1.0, 8, False, True),
     "mini_prompt": ("mini", "wav2vec2", "bart-mini", dict(down_scale=2), 2, 1.0, 8, False, True),
+    # HFSpeechMixFixed (ref :450-462): frozen text model, trainable speech encoder + bridge; and fixed_parameters with
+    # the default fixed_except list on the EED class (ref :226-244)
+    "mini_fixed": ("mini", "wav2vec2", "bart-mini", dict(down_scale=2, fixed_speech=False, fixed_nlp=True), 2, 1.0, 8, False, True),
+    "mini_fixed_params": ("mini", "wav2vec2", "bart-mini", dict(down_scale=2, fixed_parameters=True), 2, 1.0, 8, False, True),
 }
 EXTRAS = {
     "mini_specaug": {"speech_overrides": {"apply_spec_augment": True, "mask_time_prob": 0.3, "mask_time_length": 3,
@@ -54,6 +58,7 @@ EXTRAS = {
                                           "mask_feature_min_masks": 1},
                      "np_seed": 1234},
     "mini_prompt": {"prompt": "w5 w9 w4 w17 w6"},
+    "mini_fixed": {"cls": "Fixed"},
 }
 
 
@@ -105,17 +110,21 @@ def run_case(name):
     text.save_pretrained(tx_dir)
     save_tokenizer(tx_dir, tx_cfg.vocab_size)
 
-    ref = speechmix.HFSpeechMixEED(sp_dir, tx_dir, **kw)
+    ref_cls = getattr(speechmix, "HFSpeechMix" + extra.get("cls", "EED"))
+    ora_cls = getattr(O, "Oracle" + extra.get("cls", "EED"))
+    ref = ref_cls(sp_dir, tx_dir, **kw)
     O.reinit_glue(ref, seed=1)  # glue parameters: deterministic re-draw (see oracle.reinit_glue)
     ref.train(False) if not backward else ref.train(True)
 
     # oracle restatement on the same weights
     speech2, text2 = O.build_backbones(sp_cfg, tx_cfg, seed=0)
-    ora = O.OracleEED(speech2, text2, **kw)
+    ora = ora_cls(speech2, text2, **kw)
     O.reinit_glue(ora, seed=1)
     for (ka, va), (kb, vb) in zip(sorted(ref.state_dict().items()), sorted(ora.state_dict().items())):
         assert ka == kb and torch.equal(va, vb), (ka, kb)  # seeded rebuild == saved checkpoints
     ora.train(ref.training)
+    assert [k for k, p in ref.named_parameters() if p.requires_grad] == [k for k, p in ora.named_parameters() if p.requires_grad]
+    assert ref.list_grad == ora.list_grad and ref.list_no_grad == ora.list_no_grad
 
     x, labels = O.synthetic_batch(B, secs, t_dec, tx_cfg.vocab_size, seed=0, ignore_tail=ignore_tail)
 
@@ -158,9 +167,10 @@ def run_case(name):
         "speech_last_hidden_state": sample(cap["speech"]),
         "encoder_last_hidden_state": sample(out_ref["encoder_last_hidden_state"]),
     }
-    for k in ("speech_overrides", "np_seed"):
+    for k in ("speech_overrides", "np_seed", "cls"):
         if k in extra:
             fixture[k] = extra[k]
+    fixture["list_grad"] = len(ref.list_grad)
     if "prompt" in extra:
         fixture["prompt"], fixture["prompt_ids"] = extra["prompt"], prompt_ids.tolist()
     if backward:
@@ -186,6 +196,9 @@ def run_case(name):
                 assert torch.equal(pr[k].grad, po[k].grad), k
                 grads[k] = {"norm": float(pr[k].grad.double().norm()), **sample(pr[k].grad, 16)}
         fixture["grads"] = grads
+        for k in pr:   # frozen parameters get no gradient on either side
+            assert (pr[k].grad is None) == (po[k].grad is None), k
+        fixture["n_grads"] = sum(p.grad is not None for p in pr.values())
 
     # greedy decode the way eval.ipynb does, on the reference forward itself
     if name.startswith("mini") and not backward:

@@ -106,3 +106,20 @@ def test_share_layer_ratio_and_helpers():
         assert m.speech_encoder_layer == kept and m.nlp_encoder_layer == 2 and len(m.list_no_grad) == 0
     lab = torch.tensor([[5, 6, -100, -100], [7, 8, 9, 10]])
     assert torch.equal(shift_tokens_right(lab, 1, 2), O.shift_tokens_right(lab, 1, 2))
+
+
+def test_freezing_variants_mark_the_same_parameters_as_the_reference():
+    """SpeechMixFixed (ref:speechmix/hf_model.py:450-462) and fixed_parameters (ref :226-244): the product freezes the
+    same parameters as the oracle, which the mini_fixed / mini_fixed_params goldens pin to the unmodified reference."""
+    from oracle import hf_oracle as O
+    from speechmix_b200 import SpeechMixEED, SpeechMixFixed
+    from tests._cases import load_fixture
+    for name, mine_cls in (("mini_fixed", SpeechMixFixed), ("mini_fixed_params", SpeechMixEED)):
+        fx = load_fixture(name)
+        spc, txc = O.speech_config(fx["speech"], model_type=fx["speech_type"]), O.text_config(fx["text"])
+        mine = mine_cls(spc, txc, **fx["kwargs"])
+        assert len(mine.list_no_grad) == fx["list_no_grad"] and len(mine.list_grad) == fx["list_grad"]
+        s, t = O.build_backbones(spc, txc)
+        ora = getattr(O, "Oracle" + fx.get("cls", "EED"))(s, t, **fx["kwargs"])
+        assert mine.list_grad == ora.list_grad and mine.list_no_grad == ora.list_no_grad
+        assert [k for k, p in mine.named_parameters() if p.requires_grad] == [k for k, p in ora.named_parameters() if p.requires_grad]

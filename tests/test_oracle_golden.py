@@ -8,7 +8,8 @@ import torch
 
 from tests._cases import build_oracle, check_sample, load_fixture
 
-MINI = ["mini_eed_ds2", "mini_eed_ds8_ws", "mini_eed_share", "mini_large_mbart", "mini_t5", "mini_specaug", "mini_prompt"]
+MINI = ["mini_eed_ds2", "mini_eed_ds8_ws", "mini_eed_share", "mini_large_mbart", "mini_t5", "mini_specaug", "mini_prompt",
+        "mini_fixed", "mini_fixed_params"]
 
 
 @pytest.mark.parametrize("name", MINI)
@@ -39,6 +40,9 @@ def test_oracle_matches_reference_golden(name):
             g = params[k].grad
             assert abs(float(g.double().norm()) - rec["norm"]) <= 1e-3 * rec["norm"] + 1e-7, k
             check_sample(g, rec, atol=1e-5, rtol=1e-3)
+        if "n_grads" in fx:      # freezing variants: the same parameters are trainable as in the reference
+            assert sum(p.grad is not None for p in params.values()) == fx["n_grads"]
+            assert len(model.list_grad) == fx["list_grad"]
 
 
 def test_oracle_greedy_matches_reference_loop():
