@@ -49,6 +49,8 @@ CASES = {
     "mini_prompt": ("mini", "wav2vec2", "bart-mini", dict(down_scale=2), 2, 1.0, 8, False, True),
     # HFSpeechMixFixed (ref :450-462): frozen text model, trainable speech encoder + bridge; and fixed_parameters with
     # the default fixed_except list on the EED class (ref :226-244)
+    # layer sharing with a T5 text model (the `.block` branch of the layer bookkeeping, ref :232-251; BASELINE cfg4 style)
+    "mini_t5_share": ("mini_large", "wav2vec2", "t5-mini", dict(down_scale=4, share_layer_ratio=0.5), 2, 1.0, 8, True, True),
     "mini_fixed": ("mini", "wav2vec2", "bart-mini", dict(down_scale=2, fixed_speech=False, fixed_nlp=True), 2, 1.0, 8, False, True),
     "mini_fixed_params": ("mini", "wav2vec2", "bart-mini", dict(down_scale=2, fixed_parameters=True), 2, 1.0, 8, False, True),
 }

@@ -123,3 +123,18 @@ def test_freezing_variants_mark_the_same_parameters_as_the_reference():
         ora = getattr(O, "Oracle" + fx.get("cls", "EED"))(s, t, **fx["kwargs"])
         assert mine.list_grad == ora.list_grad and mine.list_no_grad == ora.list_no_grad
         assert [k for k, p in mine.named_parameters() if p.requires_grad] == [k for k, p in ora.named_parameters() if p.requires_grad]
+
+
+def test_t5_layer_sharing_bookkeeping_matches_reference_golden():
+    """`.block` branch of the layer bookkeeping (ref:speechmix/hf_model.py:232-251) on the product class, against the
+    numbers the unmodified reference produced for the mini_t5_share golden."""
+    from oracle import hf_oracle as O
+    from speechmix_b200 import SpeechMixEED
+    from tests._cases import build_oracle, load_fixture
+    fx = load_fixture("mini_t5_share")
+    mine = SpeechMixEED(O.speech_config(fx["speech"], model_type=fx["speech_type"]), O.text_config(fx["text"]), **fx["kwargs"])
+    assert mine.speech_encoder_layer == fx["speech_encoder_layer"] and mine.nlp_encoder_layer == fx["nlp_encoder_layer"]
+    assert len(mine.state_dict()) == fx["n_state_keys"] and len(mine.list_no_grad) == fx["list_no_grad"]
+    assert sum(p.numel() for p in mine.parameters()) == fx["n_params"]
+    ora, _, _ = build_oracle(fx)
+    mine.load_state_dict(ora.state_dict())

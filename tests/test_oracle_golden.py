@@ -9,7 +9,7 @@ import torch
 from tests._cases import build_oracle, check_sample, load_fixture
 
 MINI = ["mini_eed_ds2", "mini_eed_ds8_ws", "mini_eed_share", "mini_large_mbart", "mini_t5", "mini_specaug", "mini_prompt",
-        "mini_fixed", "mini_fixed_params"]
+        "mini_fixed", "mini_fixed_params", "mini_t5_share"]
 
 
 @pytest.mark.parametrize("name", MINI)
