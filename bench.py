@@ -1,15 +1,19 @@
 #!/usr/bin/env python
-"""Headline benchmark: SpeechMixEED wav2vec2-base + bart-base, down_scale=2, batch 32 x 15 s per GPU,
-bf16 forward + loss + backward + optimizer step  ->  train audio-seconds / second (BASELINE.json configs[1]).
+"""Benchmark of the SpeechMix speech-to-text training step on B200 -> train audio-seconds / second.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2|cfg3|cfg4|cfg5]
 
+Default workload (the headline, BASELINE.json configs[1]): SpeechMixEED wav2vec2-base + bart-base, down_scale=2,
+batch 32 x 15 s per GPU, bf16 forward + loss + backward + optimizer step.  --config selects the other BASELINE
+configurations (cfg3 Adapter hubert-large + bart-large with frozen backbones, cfg4 Self wav2vec2-large + t5-base
+share_layer_ratio 0.5, cfg5 EED hubert-large + mbart-large-50 at 8 x 30 s per GPU).
 N > 1 is launched by torchrun (one rank per GPU, NCCL); data parallel, weak scaling.
 Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for what every key means.
 """
 import argparse
 import contextlib
 import json
+import math
 import os
 import subprocess
 import sys
@@ -21,32 +25,89 @@ sys.path.insert(0, ROOT)
 os.environ.setdefault("TRANSFORMERS_OFFLINE", "1")
 os.environ.setdefault("TOKENIZERS_PARALLELISM", "false")
 
-SECONDS, BATCH_PER_GPU, T_DEC, RATE = 15.0, 32, 64, 16000
-CPU_SAMPLE_BATCH = 2
+RATE = 16000
+# name -> model class suffix, speech preset (kind, model_type), text preset, ctor kwargs, per-GPU batch, seconds, T_dec,
+#         CPU-baseline sample batch, description.  Shapes: SURVEY.md section 8(d).
+WORKLOADS = {
+    "cfg2": dict(cls="EED", speech=("base", "wav2vec2"), text="bart-base", kwargs=dict(down_scale=2), batch=32,
+                 seconds=15.0, t_dec=64, cpu_batch=2,
+                 desc="SpeechMixEED wav2vec2-base + bart-base down_scale=2 (BASELINE.json configs[1])"),
+    "cfg3": dict(cls="Adapter", speech=("large", "hubert"), text="bart-large",
+                 kwargs=dict(down_scale=8, fixed_parameters=True, fixed_except=[]), batch=32, seconds=15.0, t_dec=64,
+                 cpu_batch=1,
+                 desc="SpeechMixAdapter hubert-large + bart-large down_scale=8, frozen backbones, adapter tuning "
+                      "(BASELINE.json configs[2])"),
+    "cfg4": dict(cls="Self", speech=("large", "wav2vec2"), text="t5-base",
+                 kwargs=dict(down_scale=8, share_layer_ratio=0.5), batch=32, seconds=15.0, t_dec=64, cpu_batch=1,
+                 desc="SpeechMixSelf wav2vec2-large + t5-base share_layer_ratio=0.5 down_scale=8, CE + KL + MSE "
+                      "(BASELINE.json configs[3])"),
+    "cfg5": dict(cls="EED", speech=("large", "hubert"), text="mbart-large-50", kwargs=dict(down_scale=8), batch=8,
+                 seconds=30.0, t_dec=128, cpu_batch=1,
+                 desc="SpeechMixEED hubert-large + mbart-large-50 (V=250054) down_scale=8, 8 x 30 s per GPU = 64 x 30 s "
+                      "at 8 GPUs (BASELINE.json configs[4])"),
+}
+SHAPES = {   # speech: (H, FF, L); text: (D, DFF, Le, Ld, V)
+    ("base", "wav2vec2"): (768, 3072, 12), ("large", "hubert"): (1024, 4096, 24), ("large", "wav2vec2"): (1024, 4096, 24),
+    "bart-base": (768, 3072, 6, 6, 50265), "bart-large": (1024, 4096, 12, 12, 50265),
+    "t5-base": (768, 3072, 12, 12, 32128), "mbart-large-50": (1024, 4096, 12, 12, 250054),
+}
 
 
-def fwd_flops_per_sample(secs=SECONDS, t_dec=T_DEC, H=768, FF=3072, L=12, D=768, DFF=3072, Le=6, Ld=6, V=50265, ds=2):
-    """BASELINE.md section 3 formulas (2*MAC, dense attention)."""
+def frames(secs):
     T = int(secs * RATE)
-    ks, ss = (10, 3, 3, 3, 3, 2, 2), (5, 2, 2, 2, 2, 2, 2)
-    fl, cin = 0.0, 1
-    for k, s in zip(ks, ss):
+    for k, s in zip((10, 3, 3, 3, 3, 2, 2), (5, 2, 2, 2, 2, 2, 2)):
         T = (T - k) // s + 1
-        fl += 2.0 * T * 512 * cin * k
+    return T
+
+
+def fwd_flops_parts(w):
+    """BASELINE.md section 3 formulas (2*MAC, dense attention), per sample, split by stage."""
+    H, FF, L = SHAPES[w["speech"]]
+    D, DFF, Le, Ld, V = SHAPES[w["text"]]
+    L = L - int(L * w["kwargs"].get("share_layer_ratio", 0))
+    ds, t_dec = w["kwargs"]["down_scale"], w["t_dec"]
+    T = int(w["seconds"] * RATE)
+    conv, cin = 0.0, 1
+    for k, s in zip((10, 3, 3, 3, 3, 2, 2), (5, 2, 2, 2, 2, 2, 2)):
+        T = (T - k) // s + 1
+        conv += 2.0 * T * 512 * cin * k
         cin = 512
-    fl += 2.0 * T * 512 * H
-    fl += 2.0 * T * H * (H // 16) * 128
-    fl += L * (8.0 * T * H * H + 4.0 * T * T * H + 4.0 * T * H * FF)
-    Tds = T
-    for _ in range(int(round(__import__("math").log2(ds)))):
+    speech = conv + 2.0 * T * 512 * H + 2.0 * T * H * (H // 16) * 128
+    speech += L * (8.0 * T * H * H + 4.0 * T * T * H + 4.0 * T * H * FF)
+    bridge, Tds = 0.0, T
+    for _ in range(int(round(math.log2(ds)))):
         Tds = (Tds - 2) // 2 + 1
-        fl += 4.0 * Tds * H * H
-    fl += 2.0 * Tds * H * D
-    fl += Le * (8.0 * Tds * D * D + 4.0 * Tds * Tds * D + 4.0 * Tds * D * DFF)
-    fl += Ld * (8.0 * t_dec * D * D + 4.0 * t_dec * t_dec * D + 4.0 * t_dec * D * D + 4.0 * Tds * D * D +
-                4.0 * t_dec * Tds * D + 4.0 * t_dec * D * DFF)
-    fl += 2.0 * t_dec * D * V
-    return fl
+        bridge += 4.0 * Tds * H * H
+    bridge += 2.0 * Tds * H * D
+    tenc = Le * (8.0 * Tds * D * D + 4.0 * Tds * Tds * D + 4.0 * Tds * D * DFF)
+    tdec = Ld * (8.0 * t_dec * D * D + 4.0 * t_dec * t_dec * D + 4.0 * t_dec * D * D + 4.0 * Tds * D * D +
+                 4.0 * t_dec * Tds * D + 4.0 * t_dec * D * DFF)
+    head = 2.0 * t_dec * D * V
+    adapters = (Le * Tds + Ld * t_dec) * 2.0 * D * D if w["cls"] == "Adapter" else 0.0   # two D x D/2 GEMMs per layer
+    return dict(speech=speech, bridge=bridge, text_enc=tenc, text_dec=tdec, head=head, adapters=adapters,
+                frames=T, frames_ds=Tds)
+
+
+def fwd_flops_per_sample(w=None):
+    p = fwd_flops_parts(w or WORKLOADS["cfg2"])
+    return p["speech"] + p["bridge"] + p["text_enc"] + p["text_dec"] + p["head"]
+
+
+def step_flops_per_sample(w):
+    """Algorithmic FLOPs of one training step per sample: 3 x forward where everything
+    trains; forward + data gradient (2 x) for frozen layers above a trainable tensor; forward only below the lowest
+    trainable tensor."""
+    p = fwd_flops_parts(w)
+    if w["cls"] == "EED":
+        return 3.0 * (p["speech"] + p["bridge"] + p["text_enc"] + p["text_dec"] + p["head"])
+    if w["cls"] == "Adapter":   # frozen speech (forward only), frozen text layers (fwd + dgrad), trainable bridge / adapters
+        return p["speech"] + 3.0 * (p["bridge"] + p["adapters"]) + 2.0 * (p["text_enc"] + p["text_dec"] + p["head"])
+    if w["cls"] == "Self":      # trainable speech + bridge, frozen text model run twice (student: fwd + dgrad; teacher: fwd)
+        D, DFF, Le, Ld, V = SHAPES[w["text"]]
+        t_txt = w["t_dec"]
+        teacher = Le * (8.0 * t_txt * D * D + 4.0 * t_txt * t_txt * D + 4.0 * t_txt * D * DFF) + p["text_dec"] + p["head"]
+        return 3.0 * (p["speech"] + p["bridge"]) + 2.0 * (p["text_enc"] + p["text_dec"] + p["head"]) + teacher
+    raise ValueError(w["cls"])
 
 
 class ClockSampler(threading.Thread):
@@ -87,50 +148,57 @@ def _ncu_traffic():
         return None
 
 
-def build_cpu_reference(batch):
+def build_cpu_reference(w, batch):
     """The reference's CPU path, restated (oracle/hf_oracle.py; /root/reference does not exist on the
-    GPU box): HFSpeechMixEED glue over transformers' Wav2Vec2Model + BartForConditionalGeneration, fp32."""
+    GPU box): HFSpeechMix{EED,Adapter,Self} glue over the transformers backbones, fp32."""
     import torch
     from oracle import hf_oracle as O
-    spc, txc = O.speech_config("base"), O.text_config("bart-base")
+    spc, txc = O.speech_config(w["speech"][0], model_type=w["speech"][1]), O.text_config(w["text"])
+    if w["text"] == "t5-base":
+        txc.decoder_start_token_id = 0
     s, t = O.build_backbones(spc, txc, seed=0)
     with contextlib.redirect_stdout(sys.stderr):
-        model = O.OracleEED(s, t, down_scale=2).train()
-    x, labels = O.synthetic_batch(batch, SECONDS, T_DEC, txc.vocab_size, seed=0)
-    return model, x, labels
+        model = getattr(O, "Oracle" + w["cls"])(s, t, **w["kwargs"]).train()
+    x, labels = O.synthetic_batch(batch, w["seconds"], w["t_dec"], txc.vocab_size, seed=0)
+    extra = {}
+    if w["cls"] == "Self":
+        extra["text_input_ids"] = torch.randint(4, txc.vocab_size, (batch, w["t_dec"]))
+    return model, x, labels, extra
 
 
-def time_cpu_reference(steps, warmup, batch=CPU_SAMPLE_BATCH):
+def time_cpu_reference(w, steps, warmup, batch=None):
     import torch
+    batch = batch or w["cpu_batch"]
     torch.set_num_threads(os.cpu_count())
-    model, x, labels = build_cpu_reference(batch)
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-5)
+    model, x, labels, extra = build_cpu_reference(w, batch)
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-5)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         opt.zero_grad(set_to_none=True)
-        out = model(x, labels=labels)
+        out = model(x, labels=labels, **extra)
         out["loss"].backward()
         opt.step()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     sec = sum(times) / len(times)
-    return batch * SECONDS / sec, sec, torch.get_num_threads()
+    return batch * w["seconds"] / sec, sec, torch.get_num_threads()
 
 
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    val, sec, threads = time_cpu_reference(args.steps, args.warmup)
+    w = WORKLOADS[args.config]
+    val, sec, threads = time_cpu_reference(w, args.steps, args.warmup)
     line = {"impl": "reference", "metric": "train audio-sec/s", "value": val, "unit": "audio-s/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "SpeechMixEED wav2vec2-base + bart-base down_scale=2, fwd+bwd+AdamW",
-                       "sample": "batch %d x 15 s per step on host CPU" % CPU_SAMPLE_BATCH},
+            "config": {"workload": w["desc"] + ", fwd+bwd+AdamW", "name": args.config,
+                       "sample": "batch %d x %g s per step on host CPU" % (w["cpu_batch"], w["seconds"])},
             "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": threads, "kind": "port",
-                             "sample": "oracle/hf_oracle.py OracleEED (restated reference glue over transformers), "
-                                       "batch %d x 15 s, %d timed steps" % (CPU_SAMPLE_BATCH, args.steps)},
+                             "sample": "oracle/hf_oracle.py Oracle%s (restated reference glue over transformers), "
+                                       "batch %d x %g s, %d timed steps" % (w["cls"], w["cpu_batch"], w["seconds"], args.steps)},
             "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -142,7 +210,12 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
+    ap.add_argument("--config", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--optimizer", default="adamw", choices=["adamw", "adafactor"],
+                    help="adamw = torch fused AdamW; adafactor = the recipe's optimizer (ref:train.py:298) as one fused kernel set")
+    ap.add_argument("--grad-payload", default="bf16", choices=["fp32", "bf16"],
+                    help="wire format of the data-parallel gradient all-reduce (N > 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="eager launches instead of a whole-step CUDA graph")
     args = ap.parse_args()
@@ -159,34 +232,46 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from speechmix_b200 import SpeechMixEED, kernels, parallel, presets
+    import speechmix_b200
+    from speechmix_b200 import kernels, parallel, presets
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    spc, txc = presets.speech_config("base"), presets.text_config("bart-base")
+    w = WORKLOADS[args.config]
+    SECONDS, T_DEC = w["seconds"], w["t_dec"]
+    spc = presets.speech_config(w["speech"][0], model_type=w["speech"][1])
+    txc = presets.text_config(w["text"])
     torch.manual_seed(0)
     with contextlib.redirect_stdout(sys.stderr):   # the reference-compatible ctor prints its layer-sharing summary
-        model = SpeechMixEED(spc, txc, down_scale=2)
+        model = getattr(speechmix_b200, "SpeechMix" + w["cls"])(spc, txc, **w["kwargs"])
     parallel.init_like_reference(model, seed=0)
     model = model.to(dev).train()
-    B = args.batch
+    B = args.batch or w["batch"]
     n_samples = int(SECONDS * RATE)
     g = torch.Generator().manual_seed(1234 + rank)
     host_x = [torch.randn(B, n_samples, generator=g).pin_memory() for _ in range(2)]
     host_y = [torch.randint(4, txc.vocab_size, (B, T_DEC), generator=g).pin_memory() for _ in range(2)]
     dev_x = [t.to(dev) for t in host_x]
     dev_y = [t.to(dev) for t in host_y]
+    fkw = {}
+    if w["cls"] == "Self":      # text-teacher input (ref:speechmix/hf_model.py:541-546); resident on the device
+        fkw["text_input_ids"] = torch.randint(4, txc.vocab_size, (B, T_DEC), generator=g).to(dev)
 
     params = [p for p in model.parameters() if p.requires_grad]
-    opt = torch.optim.AdamW(params, lr=1e-5, fused=True, capturable=bool(args.graph and world == 1))
-    dp = parallel.GradientAllReducer(model, world) if world > 1 else None
+    n_train = sum(p.numel() for p in params)
+    if args.optimizer == "adafactor":
+        from speechmix_b200.optim import FusedAdafactor
+        opt = FusedAdafactor(params, lr=1e-5)
+    else:
+        opt = torch.optim.AdamW(params, lr=1e-5, fused=True, capturable=bool(args.graph and world == 1))
+    dp = parallel.GradientAllReducer(model, world, payload=args.grad_payload) if world > 1 else None
 
     def step_eager(x, y):
         opt.zero_grad(set_to_none=True)
-        out = model(x, labels=y, return_model_detail=False)
+        out = model(x, labels=y, return_model_detail=False, **fkw)
         out["loss"].backward()
         if dp is not None:
             dp.finish()
@@ -199,7 +284,8 @@ def main():
     if args.graph:
         from speechmix_b200.graph import GraphedTrainStep
         try:
-            graphed = GraphedTrainStep(model, opt, dev_x[0], dev_y[0], warmup=max(args.warmup, 3), reducer=dp)
+            graphed = GraphedTrainStep(model, opt, dev_x[0], dev_y[0], warmup=max(args.warmup, 3), reducer=dp,
+                                       forward_kwargs=fkw)
         except Exception as e:   # a failed capture must not cost the measurement: fall back to eager launches
             sys.stderr.write("CUDA graph capture failed (%r); running eager\n" % (e,))
             graphed = None
@@ -208,6 +294,7 @@ def main():
                 dp.graph_mode, dp.enabled = False, True
                 dp.pending = [len(b) for b in dp.buckets]
                 dp.works = [None] * len(dp.buckets)
+                dp.ready, dp.next_bucket = [False] * len(dp.buckets), 0
             opt.zero_grad(set_to_none=True)
 
     def step(x, y):
@@ -287,30 +374,36 @@ def main():
 
     if rank == 0:
         audio_s = B * world * SECONDS
-        fl_step = 3.0 * fwd_flops_per_sample() * B
+        fl_step = step_flops_per_sample(w) * B
+        H_sp, FF_sp, _ = SHAPES[w["speech"]]
+        M_dom = B * frames(SECONDS)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
-        # dominant kernel: the FFN up-projection GEMM (M = B*749, N = 3072, K = 768), timed live with CUDA events
-        dom = [(a.elapsed_time(b), fl) for (tag, fl, a, b) in (gemm_events or []) if tag == "nt_%d_3072_768" % (B * 749)]
+        # dominant kernel: the speech FFN up-projection GEMM (M = B*frames, N = FF, K = H), timed live with CUDA events
+        dom = [(a.elapsed_time(b), fl) for (tag, fl, a, b) in (gemm_events or [])
+               if tag == "nt_%d_%d_%d" % (M_dom, FF_sp, H_sp)]
         roof = None
         if dom:
             avg_ms = sum(d for d, _ in dom) / len(dom)
             ach = dom[0][1] / avg_ms / 1e9
-            roof = {"bound": "tensor", "kernel": "gemm_kernel<NT> M=%d N=3072 K=768 (FFN up-projection + bias + GELU)" % (B * 749),
+            roof = {"bound": "tensor", "kernel": "gemm_kernel<NT> M=%d N=%d K=%d (FFN up-projection + bias + GELU)" % (M_dom, FF_sp, H_sp),
                     "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
-                    "launches_timed": len(dom), "traffic": _ncu_traffic(),
+                    "launches_timed": len(dom), "traffic": _ncu_traffic() if args.config == "cfg2" and B == 32 else None,
                     "step_frac_of_peak": fl_step / (ms * 1e-3) / 1e12 / peak_tf}
         line = {"metric": "train audio-sec/s", "value": audio_s / (ms * 1e-3), "unit": "audio-s/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": "SpeechMixEED wav2vec2-base + bart-base down_scale=2, batch %d x 15 s per GPU, "
-                                       "T_dec=64, fwd+loss+bwd+AdamW (BASELINE.json configs[1])" % B,
-                           "global_batch": B * world, "parallelism": "dp%d" % world,
+                "config": {"workload": "%s, batch %d x %g s per GPU, T_dec=%d, fwd+loss+bwd+%s"
+                                       % (w["desc"], B, SECONDS, T_DEC, "AdamW" if args.optimizer == "adamw" else "Adafactor"),
+                           "name": args.config, "global_batch": B * world, "parallelism": "dp%d" % world,
+                           "trainable_parameters": n_train,
+                           "allreduce_bytes_per_step": dp.payload_bytes() if dp is not None else 0,
+                           "grad_payload": args.grad_payload if dp is not None else None,
                            "l2": "per-step activations (>3 GB) exceed the 126 MB L2",
                            "launch": ("eager" if graphed is None else "whole-step CUDA graph" if world == 1 else
                                       "CUDA graph (fwd+bwd) + eager NCCL all-reduce + optimizer")},
@@ -322,10 +415,10 @@ def main():
                 "clocks": sampler.summary(),
                 "roofline": roof}
         if not args.no_cpu_baseline and world == 1:
-            val, sec, threads = time_cpu_reference(steps=2, warmup=1)
+            val, sec, threads = time_cpu_reference(w, steps=2, warmup=1)
             line["cpu_baseline"] = {"value": val, "unit": "audio-s/s", "cores": threads, "kind": "port",
-                                    "sample": "oracle OracleEED fp32 fwd+bwd+AdamW, batch %d x 15 s, 2 timed steps (%.1f s/step)"
-                                              % (CPU_SAMPLE_BATCH, sec)}
+                                    "sample": "oracle Oracle%s fp32 fwd+bwd+AdamW, batch %d x %g s, 2 timed steps (%.1f s/step)"
+                                              % (w["cls"], w["cpu_batch"], SECONDS, sec)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

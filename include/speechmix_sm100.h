@@ -272,6 +272,10 @@ typedef struct SmxAttn {
 } SmxAttn;
 int smx_attn_fwd(const SmxAttn* a, void* stream);
 int smx_attn_bwd(const SmxAttn* a, void* stream);
+/* Development hook (tools/probe_attn.py trace): a device buffer of 3 x 64 uint64 receives SM-clock stamps of CTA (0,0,0)
+ * of the following plain-attention forward launches -- [MMA thread | softmax group 0 | softmax group 1][event];
+ * NULL switches tracing off.  Not used by the product path. */
+int smx_debug_attn_trace(void* device_buffer);
 
 /* Zero the columns [col_begin, col_begin + col_count) of every row t >= len[b] of a bf16 [batch][t][...] buffer
  * (row / batch strides in elements; col_begin, col_count multiples of 8).  Used for "padded frames output 0"

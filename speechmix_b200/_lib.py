@@ -66,6 +66,7 @@ SIGNATURES = {
     "smx_last_error": (c_char_p, []),
     "smx_abi_version": (c_int, []),
     "smx_device_ok": (c_int, []),
+    "smx_debug_attn_trace": (c_int, [_P]),
     "smx_gemm": (c_int, [POINTER(SmxGemm), _P]),
     "smx_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, c_float, c_int, c_int, _P]),
     "smx_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, c_int, c_int, _P]),

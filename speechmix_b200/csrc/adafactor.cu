@@ -94,111 +94,6 @@ __global__ void __launch_bounds__(256) finalize_kernel(const SmxAdafactorTensor*
   }
 }
 
-#if defined(SMX_ADAFACTOR_V2) && SMX_ADAFACTOR_V2
-// Round-2 candidate (NOT the default, not yet run on a GPU: compile with -DSMX_ADAFACTOR_V2=1 and run
-// tests/test_kernels_gpu.py -k adafactor + tools/bench_adafactor.py before switching): the v1 loop below interleaves
-// loads of g / p with stores to p (or exp_avg_sq) through pointers the compiler cannot prove distinct, so each thread's
-// 64 load -> store pairs serialise (profiles/r01z_adafactor.txt).  Here every row first issues its 8 (+8) loads through
-// __restrict__ locals, then computes, then stores; factored tensors and vectors take separate loops.
-template <bool APPLY>
-__global__ void __launch_bounds__(256) update_kernel(const SmxAdafactorTensor* __restrict__ tensors,
-                                                     const SmxAdafactorTile* __restrict__ tiles, Hyper h) {
-  __shared__ float red[8];
-  const SmxAdafactorTile tl = tiles[blockIdx.x];
-  const SmxAdafactorTensor t = tensors[tl.tensor];
-  const float* __restrict__ gp = t.g;
-  float* __restrict__ pp = t.p;
-  float* __restrict__ vp = t.row;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float scale = 0.f, decay = 1.f;
-  if (APPLY) {
-    const float rms = sqrtf(*t.sumsq / (float)t.numel);
-    scale = h.lr / fmaxf(1.0f, rms / h.clip);
-    decay = 1.0f - h.weight_decay * h.lr;
-  }
-  const float om = 1.0f - h.beta2t;
-  float ss = 0.f;
-  if (t.factored) {
-    float cf[8], rf[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const long long c = tl.c0 + lane + 32 * j;
-      cf[j] = c < t.cols ? t.col[(long long)tl.b * t.cols + c] : 1.f;
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const long long r = tl.r0 + warp + 8 * k;
-      rf[k] = r < t.rows ? vp[(long long)tl.b * t.rows + r] : 1.f;
-    }
-    const float inv_rmean = 1.0f / t.rmean[tl.b];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) cf[j] = 1.0f / sqrtf(cf[j]);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) rf[k] = 1.0f / sqrtf(rf[k] * inv_rmean);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const long long r = tl.r0 + warp + 8 * k;
-      if (r >= t.rows) continue;   // warp-uniform
-      const long long base = ((long long)tl.b * t.rows + r) * t.cols + tl.c0 + lane;
-      float gl[8], pl[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const bool ok = tl.c0 + lane + 32 * j < t.cols;
-        gl[j] = ok ? gp[base + 32 * j] : 0.f;
-        if (APPLY) pl[j] = ok ? pp[base + 32 * j] : 0.f;
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float u = gl[j] * (rf[k] * cf[j]);
-        if (APPLY) {
-          if (tl.c0 + lane + 32 * j < t.cols) pp[base + 32 * j] = pl[j] * decay - scale * u;
-        } else {
-          ss = fmaf(u, u, ss);
-        }
-      }
-    }
-  } else {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const long long base = (long long)(tl.r0 + warp + 8 * k) * TILE_C + lane;
-      float gl[8], vl[8], pl[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const bool ok = base + 32 * j < t.numel;
-        gl[j] = ok ? gp[base + 32 * j] : 0.f;
-        vl[j] = ok ? vp[base + 32 * j] : 1.f;      // exp_avg_sq of a vector lives in `row`
-        if (APPLY) pl[j] = ok ? pp[base + 32 * j] : 0.f;
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const bool ok = base + 32 * j < t.numel;
-        float v = vl[j];
-        if (!APPLY) {
-          v = h.beta2t * v + om * (gl[j] * gl[j] + h.eps1);
-          if (ok) vp[base + 32 * j] = v;
-        }
-        const float u = ok ? gl[j] / sqrtf(v) : 0.f;
-        if (APPLY) {
-          if (ok) pp[base + 32 * j] = pl[j] * decay - scale * u;
-        } else {
-          ss = fmaf(u, u, ss);
-        }
-      }
-    }
-  }
-  if (!APPLY) {
-    ss = warp_sum(ss);
-    if (lane == 0) red[warp] = ss;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float tot = 0.f;
-      for (int w = 0; w < 8; ++w) tot += red[w];
-      atomicAdd(t.sumsq, tot);
-    }
-  }
-}
-
-#else
 // APPLY = false: accumulate sum(u^2) per tensor (and update exp_avg_sq of vectors); APPLY = true: write the parameters
 template <bool APPLY>
 __global__ void __launch_bounds__(256) update_kernel(const SmxAdafactorTensor* __restrict__ tensors,
@@ -260,7 +155,6 @@ __global__ void __launch_bounds__(256) update_kernel(const SmxAdafactorTensor* _
   }
 }
 
-#endif
 
 }  // namespace adafactor
 }  // namespace smx

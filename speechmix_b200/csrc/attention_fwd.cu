@@ -15,6 +15,7 @@
 #include "host_common.h"
 #include "sm100_prims.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace smx {
@@ -416,6 +417,8 @@ int make_head_map_rows(CUtensorMap* m, const void* ptr, int t, int heads, int ba
   return encode_tmap_bf16(m, ptr, 4, dims, str, box, true);
 }
 
+int launch_fwd2(const SmxAttn* a, cudaStream_t stream);   // attention_fwd2.cu: two query tiles per CTA, P / O in TMEM
+
 }  // namespace attn
 }  // namespace smx
 
@@ -426,6 +429,10 @@ extern "C" int smx_attn_fwd(const SmxAttn* a, void* stream) {
   SMX_REQUIRE(a->batch > 0 && a->heads > 0 && a->tq > 0 && a->tk > 0, "attn_fwd: empty problem");
   SMX_REQUIRE(a->o_row_stride % 8 == 0 && a->o_batch_stride % 8 == 0, "attn_fwd: o strides must be multiples of 8");
   SMX_REQUIRE(a->kv_len == nullptr || !a->causal, "attn_fwd: kv_len is not combined with causal masking");
+  // plain attention over more than one query tile (speech / text encoder self-attention): the ping-pong kernel;
+  // causal, biased (T5) and short-query (decoder, incremental decoding) problems stay on the general kernel
+  static const bool force_v1 = getenv("SMX_ATTN_FWD_V1") != nullptr;
+  if (!force_v1 && !a->causal && a->bias == nullptr && a->tq > BQ) return launch_fwd2(a, (cudaStream_t)stream);
   CUtensorMap mq, mk, mv;
   if (make_head_map(&mq, a->q, a->tq, a->heads, a->batch, a->q_row_stride, a->q_batch_stride)) return -1;
   if (make_head_map(&mk, a->k, a->tk, a->heads, a->batch, a->k_row_stride, a->k_batch_stride)) return -1;

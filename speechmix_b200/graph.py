@@ -11,12 +11,36 @@ from . import kernels as K
 from . import ops
 
 
+def _capturable(opt):
+    """True when ``opt.step()`` may be recorded into a CUDA graph: torch optimizers built with ``capturable=True``
+    keep their step counters on the device; anything else (FusedAdafactor passes beta2(t) as a kernel argument and
+    synchronises an event, plain torch optimizers read host-side step counts) must run eagerly after the replay."""
+    return bool(opt.param_groups) and all(bool(g.get("capturable", False)) for g in opt.param_groups)
+
+
+def _check_no_host_randomness(model):
+    """Host-drawn randomness would be frozen into the graph (the same layers skipped / the same frames masked on
+    every replay): refuse instead of training silently wrong."""
+    enc = getattr(model, "encoder_model", None)
+    cfg = getattr(enc, "config", None)
+    if enc is None or cfg is None or not enc.training:
+        return
+    if float(getattr(cfg, "layerdrop", 0.0) or 0.0) > 0.0:
+        raise RuntimeError("GraphedTrainStep: config.layerdrop=%g draws its per-layer decisions on the host; a captured "
+                           "step would skip the same layers on every replay -- set layerdrop=0 or run eagerly"
+                           % cfg.layerdrop)
+
+
 class GraphedTrainStep:
     def __init__(self, model, optimizer, x, y, warmup=3, reducer=None, forward_kwargs=None):
         self.model, self.opt, self.reducer = model, optimizer, reducer
         self.kw = dict(forward_kwargs or {})
         self.x = x.clone()
         self.y = y.clone()
+        _check_no_host_randomness(model)
+        # the optimizer step is captured only when it is capturable and nothing (a collective) sits between
+        # backward and the step; otherwise it runs eagerly after every replay
+        self.opt_in_graph = reducer is None and _capturable(optimizer)
         # At least one eager step must run BEFORE the capture: optimizers create their state (moments, step
         # counters) lazily in the first step(), and a capture that contains that initialisation would reset the
         # state on every replay.
@@ -35,7 +59,11 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         if self.reducer is None:
             with torch.cuda.graph(self.graph):
-                self.loss = self._eager(zero=False)
+                out = self.model(self.x, labels=self.y, return_model_detail=False, **self.kw)
+                out["loss"].backward()
+                if self.opt_in_graph:
+                    self.opt.step()
+                self.loss = out["loss"]
         else:
             # data parallel: NCCL collectives stay OUT of the capture.  Forward + backward are one graph that also
             # copies each finished gradient bucket into its flat buffer and records an external event; after the
@@ -49,6 +77,12 @@ class GraphedTrainStep:
                 self.loss = out["loss"]
         self.launches_per_step = K.LAUNCHES[0] - launches0
         K._ARENA.reset()                       # the arena chunk carved during capture belongs to the graph's pool
+        # The capture holds raw pointers into the weight cache (the bf16 working copies refreshed by the captured
+        # multi-tensor cast, and its pointer table): keep them alive for the lifetime of the graph, and let eager
+        # calls (eval / generate between replays) build their own fresh copies.
+        self._pinned = ([ent[1] for ent in ops.CACHE._store.values()] + list(ops.CACHE._tables.values()))
+        ops.CACHE._store = {}
+        ops.CACHE._tables = {}
         ops.CACHE.invalidate()
 
     def _eager(self, zero=True):
@@ -69,5 +103,6 @@ class GraphedTrainStep:
         K.LAUNCHES[0] += self.launches_per_step
         if self.reducer is not None:
             self.reducer.reduce_after_replay()
+        if not self.opt_in_graph:
             self.opt.step()
         return self.loss

@@ -323,13 +323,16 @@ class SpeechMixAdapter(SpeechMixEED):
         self.decoder_model.eval()
         base = self.decoder_model.base_model
         stacks = [base.encoder, base.decoder]
+
+        def layers_of(st):      # BART / mBART: .layers, T5: .block (the reference branches the same way, :470-478)
+            return st.layers if hasattr(st, "layers") else st.block
         for st in stacks:
-            for _, p in st.layers.named_parameters():
+            for _, p in layers_of(st).named_parameters():
                 p.requires_grad = False
         d = self.decoder_model.config.d_model
         self.adapters = nn.ModuleList()
         for st in stacks:
-            for _ in st.layers:
+            for _ in layers_of(st):
                 self.adapters.append(nn.Sequential(nn.LayerNorm(d), nn.Linear(d, d // 2), nn.ReLU(),
                                                    nn.Linear(d // 2, d)))
         self.adapter_indexing = adapter_indexing
@@ -337,7 +340,7 @@ class SpeechMixAdapter(SpeechMixEED):
         offset = 0
         for st in stacks:
             st.layer_output_hook = self._make_hook(offset)
-            offset += len(st.layers)
+            offset += len(layers_of(st))
 
     def _make_hook(self, offset):
         def hook(layer_index, hidden):

@@ -19,13 +19,33 @@ class GradientAllReducer:
     gradients: LM head / decoder first, conv stack last).  When the last gradient of a bucket
     arrives its gradients are packed into one flat buffer and ``all_reduce`` is issued
     asynchronously on the communicator's stream and ``param.grad`` is re-pointed at its slice of the
-    bucket (no copy back); ``finish()`` only waits.  Works with any backend (``gloo`` in the CPU tests)."""
+    bucket (no copy back); ``finish()`` only waits.  Works with any backend (``gloo`` in the CPU tests).
 
-    def __init__(self, module, world_size=None, bucket_mb=64, group=None):
+    Collectives are always issued in bucket-index order (bucket i only after bucket i-1), whatever order the
+    gradients arrive in: which parameters receive a gradient may differ between ranks (LayerDrop draws per
+    process), and NCCL requires every rank to issue the same sequence of collectives.
+
+    ``payload="bf16"`` halves the bytes on the wire: gradients are packed into a bf16 bucket, summed by NCCL in
+    bf16 and unpacked into the fp32 gradient slices (one rounding per rank + log2(N) in the ring; the optimizer
+    state stays fp32).  ``payload="fp32"`` (default) is bit-comparable with a single-process run."""
+
+    def __init__(self, module, world_size=None, bucket_mb=64, group=None, payload="fp32"):
         self.world = world_size if world_size is not None else dist.get_world_size()
         self.group = group
+        self.bucket_mb = bucket_mb
+        self.handles = []
+        self._build(module, payload)
+
+    def rebuild(self, module):
+        """Re-bucket after the trainable set changed (gradual unfreezing, training.FreezingPolicy): hooks follow
+        ``requires_grad`` as it is NOW.  Must be called at the same point on every rank."""
+        self.remove()
+        self._build(module, self.payload)
+
+    def _build(self, module, payload):
+        bucket_mb = self.bucket_mb
         # NCCL averages inside the collective; gloo (CPU tests) has no AVG -> scale after the wait
-        self.avg_in_collective = dist.get_backend(group) == "nccl"
+        self.avg_in_collective = dist.get_backend(self.group) == "nccl"
         self.enabled = True
         self.graph_mode = False      # set by graph.GraphedTrainStep while it captures forward + backward
         self.events, self.order, self.comm_stream = None, [], None
@@ -43,14 +63,23 @@ class GradientAllReducer:
             self.buckets.append(cur)
         self.flat = [torch.empty(sum(p.numel() for p in b), device=b[0].device, dtype=torch.float32)
                      for b in self.buckets]
+        assert payload in ("fp32", "bf16"), payload
+        self.payload = payload
+        self.wire = ([torch.empty_like(f, dtype=torch.bfloat16) for f in self.flat] if payload == "bf16" else self.flat)
         self.pending = [len(b) for b in self.buckets]
         self.works = [None] * len(self.buckets)
+        self.ready = [False] * len(self.buckets)
+        self.next_bucket = 0          # lowest bucket index not launched yet (in-order launching)
         self.owner = {}
         self.handles = []
         for bi, b in enumerate(self.buckets):
             for p in b:
                 self.owner[id(p)] = bi
                 self.handles.append(p.register_post_accumulate_grad_hook(self._hook))
+
+    def payload_bytes(self):
+        """bytes each rank hands to the collective per step"""
+        return sum(w.numel() * w.element_size() for w in self.wire)
 
     def _views(self, bi):
         out, off = [], 0
@@ -65,7 +94,10 @@ class GradientAllReducer:
         bi = self.owner[id(p)]
         self.pending[bi] -= 1
         if self.pending[bi] == 0:
-            self._launch(bi)
+            self.ready[bi] = True
+            while self.next_bucket < len(self.buckets) and self.ready[self.next_bucket]:
+                self._launch(self.next_bucket)
+                self.next_bucket += 1
 
     # ---- CUDA-graph mode: the capture contains, per bucket, the copy of its gradients into the flat buffer and an
     # EXTERNAL event record; after every replay the communication stream waits for bucket i's event and
@@ -75,6 +107,8 @@ class GradientAllReducer:
         self.events = [torch.cuda.Event(external=True) for _ in self.buckets]
         self.order = []
         self.pending = [len(b) for b in self.buckets]
+        self.ready = [False] * len(self.buckets)
+        self.next_bucket = 0
         if self.comm_stream is None and self.flat[0].is_cuda:
             self.comm_stream = torch.cuda.Stream()
 
@@ -83,6 +117,7 @@ class GradientAllReducer:
         for bi in range(len(self.buckets)):
             if bi not in self.order:
                 self._launch_captured(bi)
+        self.order = sorted(self.order)     # collectives go out in index order on every rank
         self.graph_mode, self.enabled = False, False
 
     def _launch_captured(self, bi):
@@ -91,6 +126,8 @@ class GradientAllReducer:
         torch._foreach_copy_(views, grads)
         for p, v in zip(self.buckets[bi], views):
             p.grad = v
+        if self.payload == "bf16":
+            self.wire[bi].copy_(self.flat[bi])
         self.events[bi].record()
         self.order.append(bi)
 
@@ -103,13 +140,19 @@ class GradientAllReducer:
         with torch.cuda.stream(self.comm_stream):
             for bi in self.order:
                 self.comm_stream.wait_event(self.events[bi])
-                works.append(dist.all_reduce(self.flat[bi], op=op, group=self.group, async_op=True))
+                works.append(dist.all_reduce(self.wire[bi], op=op, group=self.group, async_op=True))
             for w in works:
                 w.wait()
-            if not self.avg_in_collective:
-                for bi in self.order:
-                    self.flat[bi].mul_(1.0 / self.world)
+            for bi in self.order:
+                self._unpack(bi)
         main.wait_stream(self.comm_stream)
+
+    def _unpack(self, bi):
+        """after the collective: wire -> fp32 gradient slices (bf16 payload), mean for backends without AVG"""
+        if self.payload == "bf16":
+            self.flat[bi].copy_(self.wire[bi])
+        if not self.avg_in_collective:
+            self.flat[bi].mul_(1.0 / self.world)
 
     def _launch(self, bi):
         if self.graph_mode:
@@ -119,21 +162,23 @@ class GradientAllReducer:
         torch._foreach_copy_(views, grads)
         for p, v in zip(self.buckets[bi], views):
             p.grad = v          # gradients live in the bucket from here on: no copy back after the collective
+        if self.payload == "bf16":
+            self.wire[bi].copy_(self.flat[bi])
         op = dist.ReduceOp.AVG if self.avg_in_collective else dist.ReduceOp.SUM
-        self.works[bi] = dist.all_reduce(self.flat[bi], op=op, group=self.group, async_op=True)
+        self.works[bi] = dist.all_reduce(self.wire[bi], op=op, group=self.group, async_op=True)
 
     def finish(self):
         """Call after ``loss.backward()``: flush buckets whose parameters received no gradient this
         step, wait for the collectives and write the averaged gradients back."""
-        for bi in range(len(self.buckets)):
-            if self.works[bi] is None:
-                self._launch(bi)
+        for bi in range(self.next_bucket, len(self.buckets)):
+            self._launch(bi)
         for bi, b in enumerate(self.buckets):
             self.works[bi].wait()
-            if not self.avg_in_collective:
-                self.flat[bi].mul_(1.0 / self.world)
+            self._unpack(bi)
             self.works[bi] = None
             self.pending[bi] = len(b)
+            self.ready[bi] = False
+        self.next_bucket = 0
 
     def reduce_inplace(self):
         """Average the gradients that already sit in ``param.grad`` WITHOUT re-pointing them (CUDA-graph mode: a
@@ -144,12 +189,13 @@ class GradientAllReducer:
             grads = [p.grad for p in b]
             assert all(g is not None for g in grads), "reduce_inplace: every bucketed parameter needs a gradient"
             torch._foreach_copy_(self._views(bi), grads)
+            if self.payload == "bf16":
+                self.wire[bi].copy_(self.flat[bi])
             op = dist.ReduceOp.AVG if self.avg_in_collective else dist.ReduceOp.SUM
-            works.append(dist.all_reduce(self.flat[bi], op=op, group=self.group, async_op=True))
+            works.append(dist.all_reduce(self.wire[bi], op=op, group=self.group, async_op=True))
         for bi, b in enumerate(self.buckets):
             works[bi].wait()
-            if not self.avg_in_collective:
-                self.flat[bi].mul_(1.0 / self.world)
+            self._unpack(bi)
             torch._foreach_copy_([p.grad for p in b], self._views(bi))
 
     def no_sync(self):
@@ -169,6 +215,7 @@ class GradientAllReducer:
     def remove(self):
         for h in self.handles:
             h.remove()
+        self.handles = []
 
 
 def shard_batch(global_batch, rank, world):

@@ -422,6 +422,8 @@ class T5Seq2SeqLM(nn.Module):
                                                None, cross[blk._index])
                 x = ops.decode_ffn_step(x, blk.cfg_cross, ff.DenseReluDense.wi.weight, None, ff.DenseReluDense.wo.weight,
                                         None, ff.layer_norm.weight, None)
+                if dec.layer_output_hook is not None:       # SpeechMixAdapter (ref:speechmix/hf_model.py:486-502)
+                    x = dec.layer_output_hook(blk._index, x.view(B, 1, D)).reshape(B, D)
             x = ops._ln_maybe(x, dec.final_layer_norm.weight, None, cfg.layer_norm_epsilon, True)
             nxt = ops.lm_head_argmax(x, w, b, scale)
             ids[:, t + 1] = nxt

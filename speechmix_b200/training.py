@@ -86,15 +86,25 @@ class FreezingPolicy:
     """ref:speechmix/module/utility.py:6-34 (FreezingCallback) as a plain object: call ``on_epoch_begin(epoch)``.
     During the first ``freeze_epoch`` epochs only the last ``epoch * n_params / freeze_epoch`` parameters (in
     registration order) of ``freeze_model`` keep their original ``requires_grad``; afterwards all are restored.
-    Which weight-gradient GEMMs and all-reduce buckets exist follows from ``requires_grad`` automatically."""
+    Which weight-gradient GEMMs run follows from ``requires_grad`` automatically.  A data-parallel
+    ``parallel.GradientAllReducer`` fixes its hooked parameter set when it is built: pass it as ``reducer`` and the
+    policy rebuilds its buckets whenever the trainable set changes (otherwise newly unfrozen parameters would never be
+    averaged and the replicas would drift apart)."""
 
-    def __init__(self, freeze_model, freeze_epoch=3):
+    def __init__(self, freeze_model, freeze_epoch=3, reducer=None, reducer_module=None):
         self.freeze_model, self.freeze_epoch = freeze_model, freeze_epoch
+        self.reducer, self.reducer_module = reducer, reducer_module if reducer_module is not None else freeze_model
         self.default = {n: p.requires_grad for n, p in freeze_model.named_parameters()}
         self.names = list(self.default)
         self.freeze_layers = int(len(self.names) / freeze_epoch)
 
     def on_epoch_begin(self, epoch):
+        before = [p.requires_grad for p in self.freeze_model.parameters()]
+        self._apply(epoch)
+        if self.reducer is not None and before != [p.requires_grad for p in self.freeze_model.parameters()]:
+            self.reducer.rebuild(self.reducer_module)
+
+    def _apply(self, epoch):
         if epoch < self.freeze_epoch:
             k = int(self.freeze_layers * epoch)
             release = set(self.names[-k:]) if k > 0 else set(self.names)   # names[-0:] is the whole list, as in the reference

@@ -320,6 +320,58 @@ def test_graphed_step_matches_eager(cuda_device):
     assert max(abs(a - b) for a, b in zip(*losses)) < 5e-3, losses   # same trajectory (atomics reorder the last bits)
 
 
+def test_graph_replay_survives_interleaved_eager_calls(cuda_device):
+    """the captured step holds raw pointers into the weight cache; an eval forward / generate between two
+    replays rebuilds the cache and must neither free what the graph uses nor change its trajectory."""
+    from speechmix_b200.graph import GraphedTrainStep
+    fx = load_fixture("mini_eed_ds2")
+    ora, x, labels = build_oracle(fx)
+    xs, ys = x.to(cuda_device), labels.to(cuda_device)
+    hist = []
+    for interleave in (False, True):
+        m = _mine_from(ora, fx, cuda_device)
+        opt = torch.optim.AdamW(m.parameters(), lr=2e-4, weight_decay=0.0, fused=True, capturable=True)
+        g = GraphedTrainStep(m, opt, xs, ys, warmup=2)
+        losses = []
+        for i in range(4):
+            losses.append(float(g(xs, ys)))
+            if interleave:
+                m.eval()
+                with torch.no_grad():
+                    m(xs, labels=ys)
+                    m.generate(xs, max_length=4)
+                m.train()
+                junk = [torch.full((1 << 20,), float("nan"), device=cuda_device) for _ in range(16)]   # recycle freed blocks
+                del junk
+        hist.append(losses)
+    assert all(l == l for l in hist[1]), hist
+    assert max(abs(a - b) for a, b in zip(*hist)) < 5e-3, hist
+
+
+def test_graph_capture_refuses_host_side_randomness(cuda_device):
+    """LayerDrop draws on the host: a captured step would skip the same layers forever -> raise."""
+    from oracle import hf_oracle as O
+    from speechmix_b200 import SpeechMixEED
+    from speechmix_b200.graph import GraphedTrainStep
+    spc = O.speech_config("mini")
+    spc.layerdrop = 0.1
+    m = SpeechMixEED(spc, O.text_config("bart-mini"), down_scale=2).to(cuda_device).train()
+    x, y = O.synthetic_batch(2, 1.0, 8, 1000)
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-4, fused=True, capturable=True)
+    with pytest.raises(RuntimeError, match="layerdrop"):
+        GraphedTrainStep(m, opt, x.to(cuda_device), y.to(cuda_device))
+    # a non-capturable optimizer is stepped eagerly after the replay instead of being frozen into the graph
+    spc.layerdrop = 0.0
+    m = SpeechMixEED(spc, O.text_config("bart-mini"), down_scale=2).to(cuda_device).train()
+    opt = torch.optim.SGD(m.parameters(), lr=0.05)
+    g = GraphedTrainStep(m, opt, x.to(cuda_device), y.to(cuda_device), warmup=2)
+    assert not g.opt_in_graph
+    l0 = float(g(x.to(cuda_device), y.to(cuda_device)))
+    for _ in range(4):
+        l1 = float(g(x.to(cuda_device), y.to(cuda_device)))
+    assert l1 < l0
+
+
 @pytest.mark.parametrize("case", ["cfg3_adapter_hubert_large_bart_large", "cfg4_self_w2v2_large_t5_base",
                                   "cfg5_eed_hubert_large_mbart50"])
 def test_baseline_configs_full_size_properties(case, cuda_device):

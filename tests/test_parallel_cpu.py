@@ -51,3 +51,62 @@ def test_bucketed_allreduce_matches_full_batch():
 def test_shard_batch():
     from speechmix_b200.parallel import shard_batch
     assert [shard_batch(64, r, 8) for r in (0, 7)] == [slice(0, 8), slice(56, 64)]
+
+
+def _worker_ragged(rank, world, port, ret):
+    """LayerDrop scenario: ranks skip DIFFERENT layers in the same step, so different parameters get
+    gradients on different ranks.  Collectives must still pair up (in-order bucket launching) and a parameter that
+    got no gradient on a rank contributes zeros."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from speechmix_b200.parallel import GradientAllReducer
+    torch.manual_seed(0)
+    layers = torch.nn.ModuleList([torch.nn.Linear(8, 8) for _ in range(4)])
+    red = GradientAllReducer(layers, world, bucket_mb=0.0001, payload=ret["payload"])
+    assert len(red.buckets) >= 4
+    X = torch.randn(4, 8, generator=torch.Generator().manual_seed(3))
+    ok = True
+    for step in range(3):
+        skip = (rank + step) % 4                   # every rank drops a different layer, changing every step
+        layers.zero_grad(set_to_none=True)
+        h = X
+        for i, l in enumerate(layers):
+            if i != skip:
+                h = torch.tanh(l(h))
+        h.pow(2).mean().backward()
+        red.finish()
+        got = [p.grad.clone() for p in layers.parameters()]
+        # expected: mean over ranks of each rank's own gradient (zeros where that rank skipped the layer)
+        exp = [torch.zeros_like(p) for p in layers.parameters()]
+        for r in range(world):
+            ref = torch.nn.ModuleList([torch.nn.Linear(8, 8) for _ in range(4)])
+            ref.load_state_dict(layers.state_dict())
+            sk = (r + step) % 4
+            h = X
+            for i, l in enumerate(ref):
+                if i != sk:
+                    h = torch.tanh(l(h))
+            h.pow(2).mean().backward()
+            for e, p in zip(exp, ref.parameters()):
+                if p.grad is not None:
+                    e += p.grad / world
+        tol = 1e-6 if ret["payload"] == "fp32" else 2e-2
+        ok = ok and all(float((a - b).abs().max()) <= tol * (float(b.abs().max()) + 1e-3) for a, b in zip(got, exp))
+    # gradual unfreezing: rebuild follows requires_grad
+    layers[0].weight.requires_grad = False
+    red.rebuild(layers)
+    ok = ok and all(layers[0].weight is not p for b in red.buckets for p in b)
+    ret[rank] = ok
+    dist.destroy_process_group()
+
+
+def test_rank_dependent_gradient_sets_and_bf16_payload():
+    world = 2
+    for i, payload in enumerate(("fp32", "bf16")):
+        mgr = mp.Manager()
+        ret = mgr.dict()
+        ret["payload"] = payload
+        mp.spawn(_worker_ragged, args=(world, 29613 + i, ret), nprocs=world, join=True)
+        assert all(ret[r] for r in range(world)), payload

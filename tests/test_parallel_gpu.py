@@ -22,6 +22,8 @@ def _worker(rank, world, port, mode, ret):
     from speechmix_b200 import SpeechMixEED, parallel
     from speechmix_b200.graph import GraphedTrainStep
     spc, txc = O.speech_config("mini"), O.text_config("bart-mini")
+    if mode == "layerdrop":      # every rank draws its own LayerDrop decisions: gradient sets differ between ranks
+        spc.layerdrop = 0.5
 
     def build():
         m = SpeechMixEED(spc, txc, down_scale=2)
@@ -33,7 +35,9 @@ def _worker(rank, world, port, mode, ret):
     xs, ys = x[sl].to(dev), y[sl].to(dev)
     m = build()
     opt = torch.optim.SGD(m.parameters(), lr=0.05)
-    red = parallel.GradientAllReducer(m, world, bucket_mb=1)
+    red = parallel.GradientAllReducer(m, world, bucket_mb=1, payload="bf16" if mode == "bf16" else "fp32")
+    if mode == "layerdrop":
+        torch.manual_seed(100 + rank)
     if mode == "graph":
         g = GraphedTrainStep(m, opt, xs, ys, warmup=2, reducer=red)   # 2 eager steps + 1 replay = 3 steps
         g(xs, ys)
@@ -49,7 +53,7 @@ def _worker(rank, world, port, mode, ret):
     dist.all_gather(others, w)
     same = all(torch.equal(o, others[0]) for o in others)
     ok_ref = True
-    if rank == 0:
+    if rank == 0 and mode != "layerdrop":
         ref = build()
         ropt = torch.optim.SGD(ref.parameters(), lr=0.05)
         xf, yf = x.to(dev), y.to(dev)
@@ -60,17 +64,17 @@ def _worker(rank, world, port, mode, ret):
         w0 = build().enc_to_dec_proj.weight.detach()
         d_ref, d_got = ref.enc_to_dec_proj.weight.detach() - w0, w - w0
         cos = float((d_ref * d_got).sum() / (d_ref.norm() * d_got.norm() + 1e-20))
-        ok_ref = cos > 0.98 and abs(float(d_got.norm() / d_ref.norm()) - 1.0) < 0.1
+        ok_ref = cos > (0.95 if mode == "bf16" else 0.98) and abs(float(d_got.norm() / d_ref.norm()) - 1.0) < 0.1
         ret["cos"] = cos
     ret[rank] = bool(same and ok_ref)
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["eager", "graph"])
+@pytest.mark.parametrize("mode", ["eager", "graph", "bf16", "layerdrop"])
 def test_two_gpu_data_parallel_matches_full_batch(mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     import torch.multiprocessing as mp
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(2, 29640 + (mode == "graph"), mode, ret), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, 29640 + ["eager", "graph", "bf16", "layerdrop"].index(mode), mode, ret), nprocs=2, join=True)
     assert ret[0] and ret[1], dict(ret)

@@ -172,6 +172,29 @@ def kv_len_mask():
 
 
 @case
+def fwd2_rescale():
+    """two-query-tile kernel (attention_fwd2.cu): odd tile counts, ragged tails, kv_len cuts, and inputs whose row
+    maxima keep growing along the keys so that the LAZY output rescale (threshold 2^8) fires on many tiles."""
+    import torch
+    from speechmix_b200 import kernels as K
+    ok = True
+    for (B, T, H, qs, ramp) in [(2, 749, 2, 1.0, 0.0), (2, 374, 3, 1.0, 0.0), (1, 129, 1, 1.0, 0.0), (2, 640, 2, 6.0, 3.0),
+                                (1, 1499, 2, 8.0, 5.0), (3, 257, 1, 4.0, 8.0), (2, 1000, 2, 0.2, 0.0)]:
+        g = torch.Generator(device="cuda").manual_seed(3)
+        qkv = torch.randn(B, T, 3 * H * 64, device="cuda", generator=g)
+        qkv[..., :H * 64] *= qs
+        qkv[..., H * 64:2 * H * 64] *= (1.0 + ramp * torch.arange(T, device="cuda") / T)[None, :, None]
+        qkv = qkv.to(torch.bfloat16)
+        q, k, v = qkv[..., :H * 64], qkv[..., H * 64:2 * H * 64], qkv[..., 2 * H * 64:]
+        o, lse = K.attn_fwd(q, k, v, H, scale=0.125)
+        o_ref, lse_ref = _ref(q, k, v, H, False, 0.125)
+        name = f"fwd2 B{B} T{T} H{H} qscale{qs} ramp{ramp}"
+        ok &= _rep("fwd o " + name, o, o_ref)
+        ok &= _rep("fwd lse " + name, lse, lse_ref)
+    return ok
+
+
+@case
 def full_size():
     ok = _run(4, 749, 749, 12, False, fused=True)
     ok &= _run(2, 1499, 1499, 16, False, fused=True)
@@ -199,7 +222,60 @@ def perf():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
-        print(json.dumps({"perf": nm, "ms": ms, "tflops_alg": mult * B * H * T * T * 64 / ms / 1e9}), flush=True)
+        print(json.dumps({"perf": nm, "ms": ms, "tflops_alg": mult * B * H * T * T * 64 / ms / 1e9,
+                          "env": {k_: v_ for k_, v_ in os.environ.items() if k_.startswith("SMX_")}}), flush=True)
+    # same-box library baseline: torch SDPA (bf16, [B, H, T, 64] contiguous) forward and forward+backward
+    import torch.nn.functional as F
+    qh, kh, vh = (t.view(B, T, H, 64).transpose(1, 2).contiguous().requires_grad_(True) for t in (q, k, v))
+    doh = do.view(B, T, H, 64).transpose(1, 2).contiguous()
+    for nm in ("sdpa fwd", "sdpa fwd+bwd"):
+        def fn():
+            out = F.scaled_dot_product_attention(qh, kh, vh, scale=0.125)
+            if nm.endswith("bwd"):
+                out.backward(doh)
+        if nm == "sdpa fwd":
+            ctx = torch.no_grad()
+        else:
+            ctx = torch.enable_grad()
+        with ctx:
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(10):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(json.dumps({"perf": nm, "ms": ms, "tflops_alg": (4 if nm == "sdpa fwd" else 14) * B * H * T * T * 64 / ms / 1e9}), flush=True)
+    return True
+
+
+@case
+def trace():
+    """SM-clock timeline of CTA (0,0,0) of the two-query-tile forward kernel at the bench shape: per key tile, when each
+    softmax group sees its scores / has them in registers / finishes the exponentials / publishes P, and when the MMA
+    thread sees P_i and has issued P_i.V + the next S_i."""
+    import torch
+    from speechmix_b200 import _lib, kernels as K
+    B, T, H = 32, 749, 12
+    g = torch.Generator(device="cuda").manual_seed(0)
+    qkv = torch.randn(B, T, 3 * H * 64, device="cuda", generator=g).to(torch.bfloat16)
+    q, k, v = qkv[..., :H * 64], qkv[..., H * 64:2 * H * 64], qkv[..., 2 * H * 64:]
+    for _ in range(2):
+        K.attn_fwd(q, k, v, H)
+    buf = torch.zeros(3 * 64, dtype=torch.int64, device="cuda")
+    lib = _lib.load()
+    lib.smx_debug_attn_trace(buf.data_ptr())
+    K.attn_fwd(q, k, v, H)
+    torch.cuda.synchronize()
+    lib.smx_debug_attn_trace(None)
+    t = buf.cpu().view(3, 64)
+    t0 = int(t[t > 0].min())
+    names = ["mma", "sm0", "sm1"]
+    for r in range(3):
+        row = [int(x) - t0 for x in t[r].tolist() if x > 0]
+        print(json.dumps({"trace": names[r], "clk": row}), flush=True)
     return True
 
 
