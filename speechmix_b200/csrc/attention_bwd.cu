@@ -208,27 +208,35 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, SUB, false, false);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, D, false, true);
-      mbar_wait(&bars[B_KV], 0);
-      // in-order tensor pipe: the scores of sub-tile it+1 may overwrite P^T / dS^T of sub-tile it without a
-      // barrier because the gradient MMAs that read them are issued first
-      for (int it = 0; it < n_iter; ++it) {
-        const int st = it % NST;
-        mbar_wait(&bars[B_QFULL + st], (it / NST) & 1);
-        tc_fence_after_sync();
+    // The WHOLE warp runs the loop (waits and address arithmetic are warp-uniform, so the tcgen05.mma operands sit in
+    // uniform registers); one elected lane issues.  Under `if (lane == 0)` every MMA cost ~80 clk of issue (a
+    // register -> uniform-register broadcast loop per descriptor) against ~45 clk of tensor-pipe time.
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, SUB, false, false);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, D, false, true);
+    mbar_wait(&bars[B_KV], 0);
+    // in-order tensor pipe: the scores of sub-tile it+1 may overwrite P^T / dS^T of sub-tile it without a
+    // barrier because the gradient MMAs that read them are issued first
+    for (int it = 0; it < n_iter; ++it) {
+      const int st = it % NST;
+      mbar_wait(&bars[B_QFULL + st], (it / NST) & 1);
+      tc_fence_after_sync();
+      if (elect_one()) {
         mma_sA_x_subT(tmem_base + COL_ST, sbase + OFF_K, sbase + OFF_Q + st * SUBTILE, idesc_s);
         mma_sA_x_subT(tmem_base + COL_DPT, sbase + OFF_V, sbase + OFF_DO + st * SUBTILE, idesc_s);
         umma_commit(&bars[B_STFULL]);
-        mbar_wait(&bars[B_PDSFULL], it & 1);
-        tc_fence_after_sync();
+      }
+      __syncwarp();
+      mbar_wait(&bars[B_PDSFULL], it & 1);
+      tc_fence_after_sync();
+      if (elect_one()) {
         mma_tA_x_sub(tmem_base + COL_DV, tmem_base + COL_ST, sbase + OFF_DO + st * SUBTILE, idesc_o, it > 0);   // P^T . dO
         mma_tA_x_sub(tmem_base + COL_DK, tmem_base + COL_DPT, sbase + OFF_Q + st * SUBTILE, idesc_o, it > 0);   // dS^T . Q
         umma_commit(&bars[B_QEMPTY + st]);
       }
-      umma_commit(&bars[B_DONE]);
+      __syncwarp();
     }
+    if (elect_one()) umma_commit(&bars[B_DONE]);
+    __syncwarp();
   } else {
     const int q = warp & 3;         // TMEM lane quarter
     const int r = q * 32 + lane;    // key row inside the tile
@@ -409,25 +417,31 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, SUB, false, false);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, D, false, true);
-      mbar_wait(&bars[B_QT], 0);    // Q, dO sit in TMEM as A operands
+    // warp-uniform loop, one elected lane issues (see the dK/dV kernel)
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, SUB, false, false);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, D, false, true);
+    mbar_wait(&bars[B_QT], 0);    // Q, dO sit in TMEM as A operands
+    tc_fence_after_sync();
+    for (int it = 0; it < n_iter; ++it) {
+      const int st = it % NST;
+      mbar_wait(&bars[B_KFULL + st], (it / NST) & 1);
       tc_fence_after_sync();
-      for (int it = 0; it < n_iter; ++it) {
-        const int st = it % NST;
-        mbar_wait(&bars[B_KFULL + st], (it / NST) & 1);
-        tc_fence_after_sync();
+      if (elect_one()) {
         mma_tA_x_subT(tmem_base + COL_S, tmem_base + COL_QA, sbase + OFF_K + st * SUBTILE, idesc_s);
         mma_tA_x_subT(tmem_base + COL_DP, tmem_base + COL_DOA, sbase + OFF_V + st * SUBTILE, idesc_s);
         umma_commit(&bars[B_SFULL]);
-        mbar_wait(&bars[B_DSFULL], it & 1);
-        tc_fence_after_sync();
+      }
+      __syncwarp();
+      mbar_wait(&bars[B_DSFULL], it & 1);
+      tc_fence_after_sync();
+      if (elect_one()) {
         mma_tA_x_sub(tmem_base + COL_DQ, tmem_base + COL_S, sbase + OFF_K + st * SUBTILE, idesc_o, it > 0);
         umma_commit(&bars[B_KEMPTY + st]);
       }
-      umma_commit(&bars[B_DONE]);
+      __syncwarp();
     }
+    if (elect_one()) umma_commit(&bars[B_DONE]);
+    __syncwarp();
   } else {
     const int q = warp & 3;
     const int r = q * 32 + lane;

@@ -121,18 +121,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq_map, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = umma_idesc_bf16(BQ, BKV, false, false);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, D, false, true);
-      const uint32_t sbase = smem_u32(smem);
-      mbar_wait(&bars[B_QFULL], 0);
-      // S_{j+1} is issued BEFORE PV_j: the softmax warps get the next score tile after one 128x128x64 MMA instead of
-      // waiting behind the P.V product as well, and PV_j runs on the tensor pipe while they take the row maxima.
-      auto issue_s = [&](int j) {
-        const int slot = j & 1;
-        mbar_wait(&bars[B_KFULL + slot], (j >> 1) & 1);
-        if (j > 0) mbar_wait(&bars[B_SEMPTY], (j - 1) & 1);
-        tc_fence_after_sync();
+    // The WHOLE warp runs the loop (warp-uniform waits and address arithmetic -> uniform-register operands); one elected
+    // lane issues.  Under `if (lane == 0)` every MMA cost ~80 clk of issue against 46-64 clk of tensor-pipe time.
+    constexpr uint32_t idesc_qk = umma_idesc_bf16(BQ, BKV, false, false);
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, D, false, true);
+    const uint32_t sbase = smem_u32(smem);
+    mbar_wait(&bars[B_QFULL], 0);
+    // S_{j+1} is issued BEFORE PV_j: the softmax warps get the next score tile after one 128x128x64 MMA instead of
+    // waiting behind the P.V product as well, and PV_j runs on the tensor pipe while they take the row maxima.
+    auto issue_s = [&](int j) {
+      const int slot = j & 1;
+      mbar_wait(&bars[B_KFULL + slot], (j >> 1) & 1);
+      if (j > 0) mbar_wait(&bars[B_SEMPTY], (j - 1) & 1);
+      tc_fence_after_sync();
+      if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint64_t ad = umma_smem_desc(sbase + OFF_Q + kk * 32, 16, 1024, kLayoutSW128);
@@ -141,17 +143,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq_map, const __grid_constan
         }
         umma_commit(&bars[B_SFULL]);
         umma_commit(&bars[B_KEMPTY + slot]);
-      };
-      issue_s(0);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int slot = j & 1;
-        const uint32_t par = (j >> 1) & 1;
-        // ---- PV_j = P_j . V_j needs P_j; by then the softmax warps have also released the score buffer
-        mbar_wait(&bars[B_PFULL], j & 1);
-        if (j + 1 < n_tiles) issue_s(j + 1);
-        mbar_wait(&bars[B_VFULL + slot], par);
-        mbar_wait(&bars[B_PVEMPTY + (j & 1)], par ^ 1);
-        tc_fence_after_sync();
+      }
+      __syncwarp();
+    };
+    issue_s(0);
+    for (int j = 0; j < n_tiles; ++j) {
+      const int slot = j & 1;
+      const uint32_t par = (j >> 1) & 1;
+      // ---- PV_j = P_j . V_j needs P_j; by then the softmax warps have also released the score buffer
+      mbar_wait(&bars[B_PFULL], j & 1);
+      if (j + 1 < n_tiles) issue_s(j + 1);
+      mbar_wait(&bars[B_VFULL + slot], par);
+      mbar_wait(&bars[B_PVEMPTY + (j & 1)], par ^ 1);
+      tc_fence_after_sync();
+      if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk) {
           const uint32_t pa = sbase + OFF_P + (kk >> 2) * (BQ * 128) + (kk & 3) * 32;
@@ -162,6 +167,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq_map, const __grid_constan
         umma_commit(&bars[B_PVFULL + (j & 1)]);
         umma_commit(&bars[B_VEMPTY + slot]);
       }
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;

@@ -396,7 +396,7 @@ int launch_fwd2(const SmxAttn* a, cudaStream_t stream) {
   static int poly = -1;
   if (poly < 0) {
     const char* e = getenv("SMX_ATTN_POLY");
-    poly = e ? atoi(e) : 4;
+    poly = e ? atoi(e) : 0;   // measured: the kernel is not MUFU-bound yet (profiles/r02_attn.txt), so MUFU-only is the default
     SMX_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     SMX_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   }

@@ -187,6 +187,8 @@ def perf():
         fl = 2.0 * M * N * Kd
         variants = [("nt", lambda: K.linear_fwd(x, w)),
                     ("nt+bias+gelu+pre", lambda: K.linear_fwd(x, w, bias=b, act=K.ACT_GELU, want_pre=True)),
+                    ("nt+bias+gelu_g (step's dominant)", lambda: K.linear_fwd(x, w, bias=b, act=K.ACT_GELU_G, want_pre=True)),
+                    ("nn+mulaux", lambda: K.linear_dgrad(dy, w, act=K.ACT_MULAUX, aux_in=pre)),
                     ("nt+bias+res", lambda: K.linear_fwd(x, w, bias=b, residual=r)),
                     ("nn", lambda: K.linear_dgrad(dy, w)),
                     ("nn+dgelu", lambda: K.linear_dgrad(dy, w, act=K.ACT_DGELU, aux_in=pre)),
@@ -194,7 +196,7 @@ def perf():
         for nm, fn in variants:
             ms = timeit(fn)
             print(json.dumps({"perf": name, "mode": nm, "M": M, "N": N, "K": Kd, "ms": round(ms, 4),
-                              "tflops": round(fl / ms / 1e9, 1)}), flush=True)
+                              "tflops": round(fl / ms / 1e9, 1), "ew": os.environ.get("SMX_GEMM_EW", "16")}), flush=True)
     # conv1 of the feature encoder at the bench shape
     B, T, C = 32, 47999, 512
     xa = K.alloc_act(B, T, C, "cuda")
