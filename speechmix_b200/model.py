@@ -30,20 +30,60 @@ def shift_tokens_right(input_ids, pad_token_id, decoder_start_token_id):
     return shifted
 
 
-class SpeechMixConfig:
-    """Composite config (ref:speechmix/hf_model.py:37-79): ``encoder`` / ``decoder`` sub-configs."""
+def _sub_config(c):
+    """sub-config from a config object or from the reference's dict form (``to_dict()`` incl. ``model_type``)"""
+    from transformers import AutoConfig, PretrainedConfig
+    if isinstance(c, PretrainedConfig):
+        return c
+    c = dict(c)
+    return AutoConfig.for_model(c.pop("model_type"), **c)
+
+
+try:
+    from transformers import PretrainedConfig as _PretrainedConfig
+except Exception:   # pragma: no cover - transformers is a hard dependency of the checkpoints, not of the kernels
+    _PretrainedConfig = object
+
+
+class SpeechMixConfig(_PretrainedConfig):
+    """Composite config (ref:speechmix/hf_model.py:37-79): ``encoder`` / ``decoder`` sub-configs, ``from_configs``,
+    ``to_dict``.  ``encoder`` / ``decoder`` may be config objects or the dicts the reference passes."""
 
     model_type = "speechmix"
+    is_composition = True
+    has_no_defaults_at_init = True
 
-    def __init__(self, encoder, decoder):
-        self.encoder = encoder
-        self.decoder = decoder
+    def __init__(self, encoder=None, decoder=None, **kwargs):
+        assert encoder is not None and decoder is not None, "Config has to be initialized with encoder and decoder config"
+        enc, dec = _sub_config(encoder), _sub_config(decoder)
+        if _PretrainedConfig is not object:
+            super().__init__(**kwargs)
+        self.encoder = enc
+        self.decoder = dec
         self.is_encoder_decoder = True
-        self.pad_token_id = decoder.pad_token_id
-        self.decoder_start_token_id = decoder.decoder_start_token_id
+        self.pad_token_id = dec.pad_token_id
+        self.decoder_start_token_id = dec.decoder_start_token_id
+
+    @classmethod
+    def from_configs(cls, encoder_config, decoder_config, **kwargs):
+        """ref:speechmix/hf_model.py:57-72: both arguments are checkpoint names / directories (or config objects)."""
+        from transformers import AutoConfig, PretrainedConfig
+        from .speech import resolve_checkpoint
+        if not isinstance(encoder_config, PretrainedConfig):
+            encoder_config = AutoConfig.from_pretrained(resolve_checkpoint(encoder_config))
+        if not isinstance(decoder_config, PretrainedConfig):
+            decoder_config = AutoConfig.from_pretrained(resolve_checkpoint(decoder_config))
+        decoder_config.is_decoder = True
+        decoder_config.add_cross_attention = True
+        return cls(encoder=encoder_config.to_dict(), decoder=decoder_config.to_dict(), **kwargs)
 
     def to_dict(self):
-        return {"encoder": self.encoder.to_dict(), "decoder": self.decoder.to_dict(), "model_type": self.model_type}
+        import copy
+        output = {k: copy.deepcopy(v) for k, v in self.__dict__.items() if k not in ("encoder", "decoder")}
+        output["encoder"] = self.encoder.to_dict()
+        output["decoder"] = self.decoder.to_dict()
+        output["model_type"] = self.__class__.model_type
+        return output
 
 
 DEFAULT_FIXED_EXCEPT = ["layer_norm", "encoder_attn", "enc_to_dec_proj", "length_adapter", "layernorm_embedding",
@@ -83,7 +123,8 @@ class SpeechMixEED(nn.Module):
         if tokenizer is None and isinstance(nlp_model_config, str):
             try:
                 from transformers import AutoTokenizer
-                self.tokenizer = AutoTokenizer.from_pretrained(nlp_model_config)
+                from .speech import resolve_checkpoint
+                self.tokenizer = AutoTokenizer.from_pretrained(resolve_checkpoint(nlp_model_config))
             except Exception:  # tokenizer files are optional for training on pre-tokenised labels
                 self.tokenizer = None
         self.weighted_sum = weighted_sum

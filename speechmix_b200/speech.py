@@ -268,8 +268,23 @@ class SpeechEncoderModel(nn.Module):
 
 
 # ---------------------------------------------------------------------------
+def resolve_checkpoint(name_or_path):
+    """Local checkpoint directory for ``name_or_path``: a directory is returned as is; anything else is treated as a hub
+    id the way the reference's ``from_pretrained`` calls do (ref:speechmix/hf_model.py:206-220, ref:eval.py, ref:train.py)
+    and resolved through the local hub cache / ``snapshot_download`` (which honours TRANSFORMERS_OFFLINE / HF_HUB_OFFLINE)."""
+    if os.path.isdir(name_or_path):
+        return name_or_path
+    try:
+        from huggingface_hub import snapshot_download
+        return snapshot_download(name_or_path, allow_patterns=["*.json", "*.safetensors", "*.bin", "*.model", "*.txt"])
+    except Exception as e:
+        raise FileNotFoundError("%r is neither a local checkpoint directory nor a hub id available in the local cache "
+                                "(%s: %s)" % (name_or_path, type(e).__name__, e)) from e
+
+
 def load_checkpoint_state(path):
     """state dict of a transformers checkpoint directory (safetensors or .bin)."""
+    path = resolve_checkpoint(path)
     st = os.path.join(path, "model.safetensors")
     if os.path.exists(st):
         from safetensors.torch import load_file
@@ -287,6 +302,7 @@ def speech_from_pretrained(path_or_config):
 
     if isinstance(path_or_config, PretrainedConfig):
         return SpeechEncoderModel(path_or_config)
+    path_or_config = resolve_checkpoint(path_or_config)
     config = AutoConfig.from_pretrained(path_or_config)
     model = SpeechEncoderModel(config)
     sd = load_checkpoint_state(path_or_config)

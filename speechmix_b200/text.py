@@ -13,7 +13,7 @@ from torch import nn
 
 from . import kernels as K
 from . import ops
-from .speech import SpeechOutput, _Attention, load_checkpoint_state
+from .speech import SpeechOutput, _Attention, load_checkpoint_state, resolve_checkpoint
 
 
 class _EncoderLayer(nn.Module):
@@ -484,6 +484,7 @@ def text_from_pretrained(path_or_config):
 
     if isinstance(path_or_config, PretrainedConfig):
         return build(path_or_config)
+    path_or_config = resolve_checkpoint(path_or_config)
     config = AutoConfig.from_pretrained(path_or_config)
     model = build(config)
     sd = dict(load_checkpoint_state(path_or_config))

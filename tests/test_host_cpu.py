@@ -190,3 +190,70 @@ def test_fused_adafactor_rejects_unsupported_modes():
     w.grad = torch.ones(4, 4)
     with pytest.raises(RuntimeError):      # CPU parameter: no fallback
         opt.step()
+
+
+def test_speechmix_alias_package_and_composite_config(tmp_path):
+    """`import speechmix` call sites (ref:train.py:15, ref:eval.py) resolve to this implementation, and
+    SpeechMixConfig keeps the reference's behaviour (ref:speechmix/hf_model.py:37-79): a PretrainedConfig built from
+    encoder / decoder dicts, ``from_configs`` on two checkpoint directories marks the decoder as a cross-attending
+    decoder, ``to_dict`` nests both sub-configs."""
+    import speechmix
+    import speechmix_b200
+    from transformers import BartConfig, PretrainedConfig, Wav2Vec2Config
+    assert speechmix.SpeechMixEED is speechmix_b200.SpeechMixEED and speechmix.HFSpeechMixSelf is speechmix_b200.SpeechMixSelf
+    enc_dir, dec_dir = tmp_path / "w2v2", tmp_path / "bart"
+    Wav2Vec2Config(hidden_size=256, num_hidden_layers=2, num_attention_heads=4, intermediate_size=512).save_pretrained(enc_dir)
+    BartConfig(d_model=256, encoder_layers=2, decoder_layers=2, encoder_attention_heads=4, decoder_attention_heads=4,
+               encoder_ffn_dim=512, decoder_ffn_dim=512, vocab_size=1000).save_pretrained(dec_dir)
+    cfg = speechmix.SpeechMixConfig.from_configs(str(enc_dir), str(dec_dir))
+    assert isinstance(cfg, PretrainedConfig) and cfg.model_type == "speechmix" and cfg.is_encoder_decoder
+    assert cfg.encoder.model_type == "wav2vec2" and cfg.encoder.hidden_size == 256
+    assert cfg.decoder.model_type == "bart" and cfg.decoder.is_decoder and cfg.decoder.add_cross_attention
+    d = cfg.to_dict()
+    assert d["model_type"] == "speechmix" and d["encoder"]["hidden_size"] == 256 and d["decoder"]["d_model"] == 256
+    again = speechmix.SpeechMixConfig(encoder=d["encoder"], decoder=d["decoder"])     # the reference's dict form
+    assert again.decoder.vocab_size == 1000 and again.decoder_start_token_id == cfg.decoder.decoder_start_token_id
+
+
+def test_checkpoint_directories_and_legacy_keys_load(tmp_path):
+    """SURVEY 8f row 2 (ref:eval.py:10, ref:speechmix/hf_model.py:206-220): the constructor takes transformers
+    checkpoint DIRECTORIES (safetensors or pytorch_model.bin); files from the weight_g / weight_v era of the positional
+    conv and checkpoints that store the tied embedding once load too; a full-model ``pytorch_model.bin`` written by the
+    reference loads with ``load_state_dict(torch.load(...))``; an unknown name fails with a clear error."""
+    import torch
+    from oracle import hf_oracle as O
+    from speechmix_b200 import SpeechMixEED
+    from speechmix_b200.speech import speech_from_pretrained
+    spc, txc = O.speech_config("mini"), O.text_config("bart-mini")
+    speech, text = O.build_backbones(spc, txc, seed=0)
+    sp_dir, tx_dir = tmp_path / "wav2vec2-mini", tmp_path / "bart-mini"
+    speech.save_pretrained(sp_dir)                       # model.safetensors
+    text.save_pretrained(tx_dir)
+    m = SpeechMixEED(str(sp_dir), str(tx_dir), down_scale=2)
+    ora = O.OracleEED(speech, text, down_scale=2)
+    sd_m, sd_o = m.state_dict(), ora.state_dict()
+    assert list(sd_m) == list(sd_o)
+    for k in sd_o:
+        if not k.startswith(O.GLUE_PREFIXES):            # glue parameters are freshly initialised on both sides
+            assert torch.equal(sd_m[k], sd_o[k]), k
+    # legacy file: pytorch_model.bin with weight_g / weight_v and a "wav2vec2." prefix
+    legacy = {}
+    for k, v in speech.state_dict().items():
+        k = k.replace("parametrizations.weight.original0", "weight_g").replace("parametrizations.weight.original1", "weight_v")
+        legacy["wav2vec2." + k] = v
+    leg_dir = tmp_path / "wav2vec2-legacy"
+    leg_dir.mkdir()
+    spc.save_pretrained(leg_dir)
+    torch.save(legacy, leg_dir / "pytorch_model.bin")
+    sp2 = speech_from_pretrained(str(leg_dir))
+    for k, v in sp2.state_dict().items():
+        assert torch.equal(v, sd_o["encoder_model." + k]), k
+    # the reference's own full-model file (ref:eval.py:10)
+    torch.save(ora.state_dict(), tmp_path / "pytorch_model.bin")
+    m2 = SpeechMixEED(spc, txc, down_scale=2)
+    res = m2.load_state_dict(torch.load(tmp_path / "pytorch_model.bin"))
+    assert not res.missing_keys and not res.unexpected_keys
+    assert torch.equal(m2.state_dict()["enc_to_dec_proj.weight"], sd_o["enc_to_dec_proj.weight"])
+    import pytest
+    with pytest.raises(FileNotFoundError):
+        SpeechMixEED("voidful/definitely-not-cached-wav2vec2", str(tx_dir))
