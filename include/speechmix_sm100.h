@@ -269,6 +269,11 @@ typedef struct SmxAttn {
   int64_t dq_row_stride, dk_row_stride, dv_row_stride;
   int64_t dq_batch_stride, dk_batch_stride, dv_batch_stride;
   const int32_t* kv_len; /* optional per-sample key count (see above); NULL = all tk keys */
+  /* dropout on the attention probabilities (hf eager_attention_forward: F.dropout(attn_weights, p)); the mask is a
+   * function of (state, call, b, h, q, k) and is regenerated by the backward kernels.  NULL / p = 0: off. */
+  const uint64_t* dropout_state; /* device: {seed, step} (see smx_dropout) */
+  uint32_t dropout_call;
+  float dropout_p;
 } SmxAttn;
 int smx_attn_fwd(const SmxAttn* a, void* stream);
 int smx_attn_bwd(const SmxAttn* a, void* stream);
@@ -282,6 +287,18 @@ int smx_debug_attn_trace(void* device_buffer);
  * (hf:...wav2vec2.py:672-675) and for the k | v part of a fused QKV projection under a key-padding mask. */
 int smx_mask_rows(void* x, const int32_t* len, int64_t batch, int64_t t, int64_t row_stride, int64_t batch_stride,
                   int64_t col_begin, int64_t col_count, void* stream);
+
+/* Counter-based dropout at the elementwise positions of the HF modules (hidden / activation / embedding dropout):
+ *   out = residual + (keep ? x / (1 - p) : 0)     bf16, n elements (multiple of 8), residual optional
+ *   aux_mode 1: aux_out = keep ? aux_in / (1 - p) : 0;   2: aux_out = (keep && aux_in > 0) ? 1 / (1 - p) : 0
+ * keep is a pure function of (state[0] = seed, state[1] = step, call, element index): the backward pass calls the same
+ * function on the gradient, and `state` lives in device memory so that a replayed CUDA graph draws new masks.
+ * smx_dropout_mask writes the keep decisions as bytes (mode 0: the elementwise numbering; mode 1: attention
+ * probabilities [rows][tk] as numbered by the attention kernels) -- used by the parity tests. */
+int smx_dropout(const void* x, const void* residual, void* out, const void* aux_in, void* aux_out, int aux_mode, int64_t n,
+                const uint64_t* state, uint32_t call, float p, void* stream);
+int smx_dropout_mask(uint8_t* mask, int64_t n, int64_t tk, int mode, const uint64_t* state, uint32_t call, float p,
+                     void* stream);
 
 /* SpecAugment on the projected features (hf:models/wav2vec2/modeling_wav2vec2.py:1280-1324; the mask INDICES come
  * from the host, drawn exactly like the reference's _compute_mask_indices):

@@ -48,7 +48,8 @@ class SmxAttn(Structure):
                 ("do_row_stride", c_int64), ("do_batch_stride", c_int64),
                 ("dq_row_stride", c_int64), ("dk_row_stride", c_int64), ("dv_row_stride", c_int64),
                 ("dq_batch_stride", c_int64), ("dk_batch_stride", c_int64), ("dv_batch_stride", c_int64),
-                ("kv_len", c_void_p)]
+                ("kv_len", c_void_p), ("dropout_state", c_void_p), ("dropout_call", ctypes.c_uint32),
+                ("dropout_p", c_float)]
 
 
 class SmxAdafactorTensor(Structure):
@@ -72,6 +73,8 @@ SIGNATURES = {
     "smx_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, c_int, c_int, _P]),
     "smx_colsum": (c_int, [_P, _P, _I64, _I64, _I64, _P]),
     "smx_mask_rows": (c_int, [_P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _P]),
+    "smx_dropout": (c_int, [_P, _P, _P, _P, _P, c_int, _I64, _P, ctypes.c_uint32, c_float, _P]),
+    "smx_dropout_mask": (c_int, [_P, _I64, _I64, c_int, _P, ctypes.c_uint32, c_float, _P]),
     "smx_adafactor_step": (c_int, [_P, c_int32, _P, c_int32, _P, c_int32, _P, _I64, c_float, c_float, c_float, c_float,
                                    c_float, _P]),
     "smx_spec_augment_fwd": (c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _P]),
@@ -179,7 +182,7 @@ def load():
 
 # kernels launched per successful call (bench.py's gpu_launches); smx_gemm is counted by its caller
 KERNELS_PER_CALL = {"multi_cast": 1, "weightnorm_fwd": 2, "weightnorm_bwd": 2, "kl_chunk_fwd": 1, "kl_finalize": 1, "kl_chunk_bwd": 1, "self_mse_fwd": 1,
-                    "self_mse_bwd": 2, "relpos_fwd": 1, "relpos_bwd": 1, "smx_attn_fwd": 1, "smx_attn_bwd": 2, "layernorm_fwd": 1, "layernorm_bwd": 1, "colsum": 1,
+                    "self_mse_bwd": 2, "relpos_fwd": 1, "relpos_bwd": 1, "smx_attn_fwd": 1, "smx_attn_bwd": 2, "dropout": 1, "dropout_mask": 1, "layernorm_fwd": 1, "layernorm_bwd": 1, "colsum": 1,
                     "cast": 1, "add": 1, "dact": 1, "conv0_stats": 3, "conv0_fwd": 1, "conv0_bwd": 2, "conv0_ln_fwd": 1, "conv0_ln_bwd": 1, "conv0_wgrad": 1,
                     "posconv_fwd": 1, "posconv_dgrad": 1, "posconv_wgrad": 1, "embed_fwd": 1, "embed_bwd": 1,
                     "lmhead_ce_fwd": 2, "lmhead_dlogits": 1, "wsum_fwd": 1, "wsum_bwd": 1}

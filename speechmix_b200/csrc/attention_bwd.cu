@@ -38,7 +38,10 @@ struct BwdParams {
   long long dq_row_stride, dq_batch_stride, dk_row_stride, dk_batch_stride, dv_row_stride, dv_batch_stride;
   int batch, heads, tq, tk, causal;
   float scale, scale_log2;
-  const int* kv_len;  // optional [batch] key counts (v2 kernels only; k / v rows past it hold zeros, see the header)
+  const int* kv_len;  // optional [batch] key counts (k / v rows past it hold zeros, see the header)
+  const unsigned long long* drop_state;   // dropout on the probabilities, regenerated here: {seed, step}, call, p
+  uint32_t drop_call;
+  float drop_p;
 };
 
 __device__ __forceinline__ int effective_tk(const BwdParams& p, int b) {
@@ -244,7 +247,10 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_consta
     const int gt = (warp - 2) * 32 + lane;  // 0..127
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     float* stat = reinterpret_cast<float*>(smem + OFF_STAT);
-    const bool lean = !p.causal && p.bias == nullptr;
+    const DropKey dkey = drop_key(p.drop_state, p.drop_call, p.drop_p);   // thresh 0: off
+    const uint32_t drop_hp = static_cast<uint32_t>((p.tk + 1) >> 1);
+    const uint32_t drop_bh = static_cast<uint32_t>((long long)b * p.heads + head) * static_cast<uint32_t>(p.tq);
+    const bool lean = !p.causal && p.bias == nullptr && dkey.thresh == 0u;
     // lse (log2 domain) / delta*scale of the 64 queries of a sub-tile: thread gt < 64 owns lse[gt], the others
     // delta[gt - 64]; the global load for the NEXT sub-tile is issued one sub-tile ahead.
     const float* stat_src = (gt < 64 ? p.lse : p.delta) + ((long long)b * p.heads + head) * p.tq;
@@ -315,7 +321,11 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_consta
               if (p.bias && qi < p.tq && kvi < tk) s += p.bias[((long long)head * p.tq + qi) * p.tk + kvi] * kLog2e;
               const bool ok = (qi < p.tq) && (kvi < tk) && (!p.causal || kvi <= qi + (p.tk - p.tq));
               e[k] = ok ? ex2_approx(s + st[col]) : 0.f;
-              d[k] = e[k] * fmaf(__uint_as_float(dv[i + k]), p.scale, st[64 + col]);
+              // dropout (mask regenerated): dP_eff = keep ? dP / (1 - p) : 0, and dV sees P_drop = keep ? P / (1 - p) : 0
+              const uint32_t bits = drop_bits(dkey, (drop_bh + static_cast<uint32_t>(qi)) * drop_hp + static_cast<uint32_t>(kvi >> 1));
+              const bool keep = (kvi & 1) ? drop_keep_hi(dkey, bits) : drop_keep_lo(dkey, bits);
+              d[k] = e[k] * fmaf(__uint_as_float(dv[i + k]), keep ? p.scale * dkey.scale : 0.f, st[64 + col]);
+              e[k] = keep ? e[k] * dkey.scale : 0.f;
             }
             pk[cc * 16 + (i >> 1)] = pack_bf16x2(e[0], e[1]);
             dk[cc * 16 + (i >> 1)] = pack_bf16x2(d[0], d[1]);
@@ -459,7 +469,9 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
 #pragma unroll
       for (int c = 0; c < 8; ++c) orow[c] = make_uint4(0u, 0u, 0u, 0u);
     }
-    const bool lean = !p.causal && p.bias == nullptr;
+    const DropKey dkey = drop_key(p.drop_state, p.drop_call, p.drop_p);   // thresh 0: off
+    const uint32_t drop_row = static_cast<uint32_t>(((long long)b * p.heads + head) * p.tq + qi) * static_cast<uint32_t>((p.tk + 1) >> 1);
+    const bool lean = !p.causal && p.bias == nullptr && dkey.thresh == 0u;
     const int causal_lim = p.causal ? qi + (p.tk - p.tq) : 0x7fffffff;
     // stationary operands -> TMEM
     mbar_wait(&bars[B_Q], 0);
@@ -528,7 +540,9 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
               if (p.bias && qi < p.tq && kvi < tk) s += p.bias[((long long)head * p.tq + qi) * p.tk + kvi] * kLog2e;
               const bool ok = (qi < p.tq) && (kvi < tk) && (kvi <= causal_lim);
               const float e = ok ? ex2_approx(s - lse2) : 0.f;
-              d[k] = e * fmaf(__uint_as_float(dv[i + k]), p.scale, -delta);
+              const uint32_t bits = drop_bits(dkey, drop_row + static_cast<uint32_t>(kvi >> 1));
+              const bool keep = (kvi & 1) ? drop_keep_hi(dkey, bits) : drop_keep_lo(dkey, bits);
+              d[k] = e * fmaf(__uint_as_float(dv[i + k]), keep ? p.scale * dkey.scale : 0.f, -delta);
               if (p.dbias && ok) atomicAdd(p.dbias + ((long long)head * p.tq + qi) * p.tk + kvi, d[k] * p.inv_scale);
             }
             dk[cc * 16 + (i >> 1)] = pack_bf16x2(d[0], d[1]);
@@ -578,6 +592,9 @@ extern "C" int smx_attn_bwd(const SmxAttn* a, void* stream) {
   p.scale = a->scale;
   p.scale_log2 = a->scale * kLog2e;
   p.kv_len = a->kv_len;
+  p.drop_state = reinterpret_cast<const unsigned long long*>(a->dropout_state);
+  p.drop_call = a->dropout_call;
+  p.drop_p = a->dropout_state ? a->dropout_p : 0.0f;
   static bool attr_set = false;
   if (!attr_set) {
     SMX_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kv2::SMEM_BYTES));

@@ -42,6 +42,9 @@ struct FwdParams {
   int batch, heads, tq, tk, causal;
   float scale_log2;  // scale * log2(e)
   const int* kv_len; // optional [batch]: keys at or past kv_len[b] are masked (never with causal)
+  const unsigned long long* drop_state;   // dropout on the probabilities (general path only): {seed, step}, call, p
+  uint32_t drop_call;
+  float drop_p;
 };
 
 // barrier indices
@@ -180,6 +183,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq_map, const __grid_constan
     const int sw = r & 7;
 
     float m = -INFINITY, l = 0.f, alpha_pending = 0.f;
+    const DropKey dkey = drop_key(p.drop_state, p.drop_call, p.drop_p);   // thresh 0: every element is kept
+    const uint32_t drop_row = static_cast<uint32_t>(((long long)b * p.heads + head) * p.tq + row) * static_cast<uint32_t>((p.tk + 1) >> 1);
     float o[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) o[i] = 0.f;
@@ -193,7 +198,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq_map, const __grid_constan
       // warp-uniform count) or empty (no exponentials at all).  Everything else takes the general per-element path.
       // Lean arithmetic per score: a third of an FMNMX3 in pass 1; half an FFMA2 + MUFU.EX2 + half an FADD2 + half a
       // pack in pass 2.  TMEM loads are issued one chunk ahead of the arithmetic (tcgen05.wait::ld is the only stall).
-      const bool plain = (bias_row == nullptr) && (!p.causal || c_base + BKV - 1 <= q0 + (p.tk - p.tq));
+      const bool plain = (bias_row == nullptr) && dkey.thresh == 0u && (!p.causal || c_base + BKV - 1 <= q0 + (p.tk - p.tq));
       const int n_valid = tk - c_base;   // >= 1; columns of this tile inside the key length (may exceed BKV)
       const bool lean = plain && n_valid >= BKV;   // full tile
       const bool cut = plain && n_valid < BKV;     // last tile of a ragged key length
@@ -330,9 +335,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq_map, const __grid_constan
             const int col = c_base + c * 32 + i;
             float s = __uint_as_float(v[i]) * p.scale_log2;
             if (bias_row && col < tk) s += bias_row[col] * 1.4426950408889634f;
-            const float e = ex2_approx(s - m_use);
-            pr[i] = (col < tk && col <= causal_lim) ? e : 0.f;
-            lt += pr[i];
+            const float e = (col < tk && col <= causal_lim) ? ex2_approx(s - m_use) : 0.f;
+            lt += e;
+            // dropout: the row sum stays that of the full probabilities, P.V sees the kept ones (scaled at the end)
+            const uint32_t bits = drop_bits(dkey, drop_row + static_cast<uint32_t>(col >> 1));
+            pr[i] = ((col & 1) ? drop_keep_hi(dkey, bits) : drop_keep_lo(dkey, bits)) ? e : 0.f;
           }
           uint8_t* blk = p_row + (c >> 1) * (BQ * 128);
 #pragma unroll
@@ -387,7 +394,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq_map, const __grid_constan
       }
     }
     if (row < p.tq) {
-      const float inv = l > 0.f ? 1.f / l : 0.f;
+      const float inv = l > 0.f ? dkey.scale / l : 0.f;
       bf16* op = p.o + (long long)b * p.o_batch_stride + (long long)row * p.o_row_stride + head * D;
 #pragma unroll
       for (int i = 0; i < D; i += 8) {
@@ -435,6 +442,10 @@ extern "C" int smx_attn_fwd(const SmxAttn* a, void* stream) {
   SMX_REQUIRE(a->batch > 0 && a->heads > 0 && a->tq > 0 && a->tk > 0, "attn_fwd: empty problem");
   SMX_REQUIRE(a->o_row_stride % 8 == 0 && a->o_batch_stride % 8 == 0, "attn_fwd: o strides must be multiples of 8");
   SMX_REQUIRE(a->kv_len == nullptr || !a->causal, "attn_fwd: kv_len is not combined with causal masking");
+  SMX_REQUIRE(a->dropout_p >= 0.0f && a->dropout_p < 1.0f, "attn_fwd: dropout p outside [0, 1)");
+  SMX_REQUIRE(a->dropout_state == nullptr || a->dropout_p == 0.0f ||
+                  (long long)a->batch * a->heads * a->tq * ((a->tk + 1) / 2) < (1ll << 32),
+              "attn_fwd: problem too large for the 32-bit dropout pair index");
   // plain attention over more than one query tile (speech / text encoder self-attention): the ping-pong kernel;
   // causal, biased (T5) and short-query (decoder, incremental decoding) problems stay on the general kernel
   static const bool force_v1 = getenv("SMX_ATTN_FWD_V1") != nullptr;
@@ -453,6 +464,9 @@ extern "C" int smx_attn_fwd(const SmxAttn* a, void* stream) {
   p.batch = a->batch, p.heads = a->heads, p.tq = a->tq, p.tk = a->tk, p.causal = a->causal;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.kv_len = a->kv_len;
+  p.drop_state = reinterpret_cast<const unsigned long long*>(a->dropout_state);
+  p.drop_call = a->dropout_call;
+  p.drop_p = a->dropout_state ? a->dropout_p : 0.0f;
   static bool attr_set = false;
   if (!attr_set) {
     SMX_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

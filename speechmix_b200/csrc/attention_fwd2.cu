@@ -67,6 +67,9 @@ struct Params {
   int batch, heads, tq, tk;
   float scale_log2;  // scale * log2(e)
   const int* kv_len;
+  const unsigned long long* drop_state;   // dropout on the probabilities: {seed, step} on the device, call index, p
+  uint32_t drop_call;
+  float drop_p;
   unsigned long long* trace;   // debug: SM clock stamps of CTA (0,0,0) -- [role][64] (smx_debug_attn_trace)
 };
 
@@ -103,7 +106,8 @@ __device__ __forceinline__ void ex2_poly2(float& a, float& b) {
 constexpr uint32_t kDescHi = ((1024u >> 4) & 0x3fffu) | (1u << 14) | (static_cast<uint32_t>(kLayoutSW128) << 29);
 __device__ __forceinline__ uint64_t lean_desc(uint32_t lo) { return (static_cast<uint64_t>(kDescHi) << 32) | lo; }
 
-template <int POLY_EVERY>   // every POLY_EVERY-th pair of exponentials is evaluated on the FMA pipe (0: none)
+// DROP: dropout on the probabilities -- P_drop = keep ? P / (1 - p) : 0 feeds P.V, the row sum stays that of P
+template <int POLY_EVERY, bool DROP>   // every POLY_EVERY-th pair of exponentials is evaluated on the FMA pipe (0: none)
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tq_map, const __grid_constant__ CUtensorMap tk_map,
                  const __grid_constant__ CUtensorMap tv_map, const Params p) {
@@ -244,6 +248,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tq_map, const __grid_consta
     int tr_n = 0;
     const bool tr_on = (warp & 3) == 0 && lane == 0;
     const int tr_role = 1 + h;
+    const DropKey dkey = DROP ? drop_key(p.drop_state, p.drop_call, p.drop_p) : DropKey{0u, 0u, 1.0f};
+    // pairs of keys are numbered per query row: row * ceil(tk / 2) + (k >> 1)  (rows past tq are never stored)
+    const uint32_t drop_row = DROP ? static_cast<uint32_t>(((long long)b * p.heads + head) * p.tq + row) * static_cast<uint32_t>((p.tk + 1) >> 1) : 0u;
 
     for (int j = 0; j < n_tiles; ++j) {
       F2_TRACE(tr_role, tr_on);   // start waiting for S(j)
@@ -317,6 +324,14 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tq_map, const __grid_consta
         }
         la = f2_add(la, f2_add(f2_pack(e[0], e[1]), f2_pack(e[2], e[3])));
         lb = f2_add(lb, f2_add(f2_pack(e[4], e[5]), f2_pack(e[6], e[7])));
+        if (DROP) {
+#pragma unroll
+          for (int k = 0; k < 8; k += 2) {
+            const uint32_t bits = drop_bits(dkey, drop_row + static_cast<uint32_t>((j * BKV + h * HALF + c + k) >> 1));
+            e[k] = drop_keep_lo(dkey, bits) ? e[k] : 0.f;
+            e[k + 1] = drop_keep_hi(dkey, bits) ? e[k + 1] : 0.f;
+          }
+        }
         pk[(c >> 1) + 0] = pack_bf16x2(e[0], e[1]);
         pk[(c >> 1) + 1] = pack_bf16x2(e[2], e[3]);
         pk[(c >> 1) + 2] = pack_bf16x2(e[4], e[5]);
@@ -340,7 +355,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tq_map, const __grid_consta
     const float mm = fmaxf(m, other.x);
     const float w_self = ex2_approx(m - mm), w_other = ex2_approx(other.x - mm);
     const float lt = l * w_self + other.y * w_other;
-    const float inv = lt > 0.f ? 1.f / lt : 0.f;
+    const float inv = lt > 0.f ? dkey.scale / lt : 0.f;
     const float wa = (h == 0 ? w_self : w_other) * inv, wb = (h == 0 ? w_other : w_self) * inv;   // weights of O_0, O_1
     mbar_wait(&bars[B_ODONE + 0], (n_tiles - 1) & 1);
     mbar_wait(&bars[B_ODONE + 1], (n_tiles - 1) & 1);
@@ -392,19 +407,26 @@ int launch_fwd2(const SmxAttn* a, cudaStream_t stream) {
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.kv_len = a->kv_len;
   p.trace = g_trace;
+  const bool drop = a->dropout_state != nullptr && a->dropout_p > 0.0f;
+  p.drop_state = reinterpret_cast<const unsigned long long*>(a->dropout_state);
+  p.drop_call = a->dropout_call;
+  p.drop_p = a->dropout_p;
 
   static int poly = -1;
   if (poly < 0) {
     const char* e = getenv("SMX_ATTN_POLY");
     poly = e ? atoi(e) : 0;   // measured: the kernel is not MUFU-bound yet (profiles/r02_attn.txt), so MUFU-only is the default
-    SMX_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    SMX_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SMX_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SMX_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SMX_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   }
   dim3 grid((a->tq + BQ - 1) / BQ, a->heads, a->batch);
-  if (poly == 0)
-    attn_fwd2_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(mq, mk, mv, p);
+  if (drop)
+    attn_fwd2_kernel<0, true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(mq, mk, mv, p);
+  else if (poly == 0)
+    attn_fwd2_kernel<0, false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(mq, mk, mv, p);
   else
-    attn_fwd2_kernel<4><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(mq, mk, mv, p);
+    attn_fwd2_kernel<4, false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(mq, mk, mv, p);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

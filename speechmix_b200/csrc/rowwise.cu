@@ -615,6 +615,62 @@ __global__ void mask_rows_kernel(bf16* __restrict__ x, const int* __restrict__ l
   }
 }
 
+// ------------------------------------------------------------------ dropout (elementwise positions of the HF modules)
+// out = residual + keep ? x / (1 - p) : 0          (residual optional; backward: the same kernel on dy, no residual)
+// aux_mode 1: aux_out = keep ? aux_in / (1 - p) : 0       (aux_in = act'(pre): the multiplier of the MULAUX epilogue)
+// aux_mode 2: aux_out = (keep && aux_in > 0) ? 1 / (1 - p) : 0   (ReLU: aux_in = pre-activation)
+// One 16-byte vector (8 elements = 4 hashed pairs) per thread; element numbering = linear index of the tensor.
+__global__ void dropout_kernel(const bf16* __restrict__ x, const bf16* __restrict__ residual, bf16* __restrict__ out,
+                               const bf16* __restrict__ aux_in, bf16* __restrict__ aux_out, int aux_mode, long long n_vec,
+                               const unsigned long long* __restrict__ state, uint32_t call, float p) {
+  const DropKey key = drop_key(state, call, p);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x) {
+    float f[8], r[8], a[8];
+    load8(x + i * 8, f);
+    if (residual) load8(residual + i * 8, r);
+    if (aux_mode) load8(aux_in + i * 8, a);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t bits = drop_bits(key, static_cast<uint32_t>(i) * 4u + j);
+      const bool k0 = drop_keep_lo(key, bits), k1 = drop_keep_hi(key, bits);
+      f[2 * j] = k0 ? f[2 * j] * key.scale : 0.f;
+      f[2 * j + 1] = k1 ? f[2 * j + 1] * key.scale : 0.f;
+      if (aux_mode == 1) {
+        a[2 * j] = k0 ? a[2 * j] * key.scale : 0.f;
+        a[2 * j + 1] = k1 ? a[2 * j + 1] * key.scale : 0.f;
+      } else if (aux_mode == 2) {
+        a[2 * j] = (k0 && a[2 * j] > 0.f) ? key.scale : 0.f;
+        a[2 * j + 1] = (k1 && a[2 * j + 1] > 0.f) ? key.scale : 0.f;
+      }
+    }
+    if (residual) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += r[j];
+    }
+    store8(out + i * 8, f);
+    if (aux_mode) store8(aux_out + i * 8, a);
+  }
+}
+// keep mask as bytes (tests: the same decisions fed to the CPU oracle).  mode 0: linear numbering (elementwise
+// dropout); mode 1: attention probabilities [rows][tk] -- pairs are numbered per row, row * ceil(tk / 2) + (k >> 1)
+__global__ void dropout_mask_kernel(unsigned char* __restrict__ mask, long long n, long long tk, int mode,
+                                    const unsigned long long* __restrict__ state, uint32_t call, float p) {
+  const DropKey key = drop_key(state, call, p);
+  const long long hp = (tk + 1) / 2;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    uint32_t pair;
+    bool hi;
+    if (mode == 0) {
+      pair = static_cast<uint32_t>(e >> 1), hi = (e & 1) != 0;
+    } else {
+      const long long row = e / tk, k = e - row * tk;
+      pair = static_cast<uint32_t>(row * hp + (k >> 1)), hi = (k & 1) != 0;
+    }
+    const uint32_t bits = drop_bits(key, pair);
+    mask[e] = (hi ? drop_keep_hi(key, bits) : drop_keep_lo(key, bits)) ? 1 : 0;
+  }
+}
+
 // ------------------------------------------------------------------ SpecAugment (hf:...wav2vec2.py:1280-1324)
 // y[b,t,:] = time_mask[b,t] ? embed : x[b,t,:];  then y[b,t,c] = 0 where feat_mask[b,c].  One 16-byte vector per thread.
 __global__ void spec_augment_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
@@ -1071,6 +1127,32 @@ int smx_mask_rows(void* x, const int32_t* len, int64_t batch, int64_t t, int64_t
   const int vec = (int)(col_count / 8);
   mask_rows_kernel<<<grid_for(batch * t * vec, 256), 256, 0, (cudaStream_t)stream>>>(
       (bf16*)x, len, batch, t, row_stride, batch_stride, (int)col_begin, vec);
+  SMX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int smx_dropout(const void* x, const void* residual, void* out, const void* aux_in, void* aux_out, int aux_mode, int64_t n,
+                const uint64_t* state, uint32_t call, float p, void* stream) {
+  SMX_REQUIRE(x && out && state, "dropout: null pointer");
+  SMX_REQUIRE(p >= 0.0f && p < 1.0f, "dropout: p = %g outside [0, 1)", (double)p);
+  SMX_REQUIRE(n % 8 == 0 && n / 2 < (1ll << 32), "dropout: n = %lld must be a multiple of 8 below 2^33", (long long)n);
+  SMX_REQUIRE(aux_mode == 0 || (aux_mode >= 1 && aux_mode <= 2 && aux_in && aux_out), "dropout: bad auxiliary operand");
+  SMX_REQUIRE(aligned16(x) && aligned16(out) && aligned16(residual) && aligned16(aux_in) && aligned16(aux_out),
+              "dropout: operands must be 16-byte aligned");
+  if (n == 0) return 0;
+  dropout_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)residual, (bf16*)out,
+                                                                       (const bf16*)aux_in, (bf16*)aux_out, aux_mode, n / 8,
+                                                                       (const unsigned long long*)state, call, p);
+  SMX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int smx_dropout_mask(uint8_t* mask, int64_t n, int64_t tk, int mode, const uint64_t* state, uint32_t call, float p,
+                     void* stream) {
+  SMX_REQUIRE(mask && state && (mode == 0 || (mode == 1 && tk > 0)), "dropout_mask: bad arguments");
+  if (n == 0) return 0;
+  dropout_mask_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(mask, n, tk, mode, (const unsigned long long*)state,
+                                                                         call, p);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

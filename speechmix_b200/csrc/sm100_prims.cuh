@@ -428,6 +428,43 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
+// ---------------------------------------------------------------------------
+// Counter-based dropout (the train-mode dropout of the HF modules the reference runs, ref:speechmix/hf_model.py:397,
+// 357-365).  A keep decision is a pure function of (seed, step, call, element), so the backward kernels REGENERATE
+// the mask instead of storing it, and a replayed CUDA graph draws new masks because `step` lives in device memory
+// (state[0] = seed, state[1] = step counter, advanced on the device once per training step).
+// One 32-bit hash serves the two elements of an aligned pair, 16 bits each: keep <=> bits >= round(p * 65536).
+// ---------------------------------------------------------------------------
+struct DropKey {
+  uint32_t key, thresh;   // thresh = 0 <=> dropout off
+  float scale;            // 1 / (1 - p)
+};
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ DropKey drop_key(const unsigned long long* state, uint32_t call, float p) {
+  DropKey k;
+  k.thresh = 0u, k.key = 0u, k.scale = 1.0f;
+  if (state != nullptr && p > 0.0f) {
+    const unsigned long long seed = state[0], step = state[1];
+    const uint32_t a = mix32(static_cast<uint32_t>(seed) ^ 0x9e3779b9u) + mix32(static_cast<uint32_t>(seed >> 32) + 0x7f4a7c15u);
+    const uint32_t b = mix32(static_cast<uint32_t>(step) * 0x85ebca6bu + static_cast<uint32_t>(step >> 32) + 0x165667b1u);
+    k.key = mix32(a ^ b ^ mix32(call * 0xc2b2ae35u + 0x27d4eb2fu));
+    k.thresh = static_cast<uint32_t>(p * 65536.0f + 0.5f);
+    k.scale = 1.0f / (1.0f - p);
+  }
+  return k;
+}
+// 2 x 16 random bits for the element pair `pair` (elements 2 pair, 2 pair + 1 of the tensor's own numbering)
+__device__ __forceinline__ uint32_t drop_bits(const DropKey& k, uint32_t pair) { return mix32(pair * 0x9e3779b1u + k.key); }
+__device__ __forceinline__ bool drop_keep_lo(const DropKey& k, uint32_t bits) { return (bits & 0xffffu) >= k.thresh; }
+__device__ __forceinline__ bool drop_keep_hi(const DropKey& k, uint32_t bits) { return (bits >> 16) >= k.thresh; }
+
 // fire-and-forget fp32 x4 reduction into global memory (address 16-byte aligned)
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");

@@ -322,8 +322,15 @@ def _attn_desc(q, k, v, o, lse, heads, causal, scale, bias, kv_len=None):
     return a
 
 
-def attn_fwd(q, k, v, heads, causal=False, scale=None, bias=None, kv_len=None):
-    """kv_len: optional int32 [B] key counts (key-padding mask): keys at or past kv_len[b] are ignored."""
+def _set_dropout(a, dropout):
+    """dropout = (state tensor int64 [2] on the device, call index, p) or None"""
+    if dropout is not None and dropout[2] > 0.0:
+        a.dropout_state, a.dropout_call, a.dropout_p = _ptr(dropout[0]), int(dropout[1]), float(dropout[2])
+
+
+def attn_fwd(q, k, v, heads, causal=False, scale=None, bias=None, kv_len=None, dropout=None):
+    """kv_len: optional int32 [B] key counts (key-padding mask): keys at or past kv_len[b] are ignored.
+    dropout: optional (state, call, p) -- dropout on the probabilities, regenerated by attn_bwd from the same triple."""
     if FP32_MODE:
         if kv_len is not None:
             raise NotImplementedError("the fp32 verification kernels have no key-padding mask")
@@ -334,12 +341,13 @@ def attn_fwd(q, k, v, heads, causal=False, scale=None, bias=None, kv_len=None):
     o = torch.empty(B, Tq, HD, device=q.device, dtype=BF16)
     lse = torch.empty(B, heads, Tq, device=q.device, dtype=torch.float32)
     a = _attn_desc(q, k, v, o, lse, heads, causal, scale, bias, kv_len)
+    _set_dropout(a, dropout)
     _lib.check(_lib.load().smx_attn_fwd(ctypes.byref(a), _stream()), "smx_attn_fwd")
     return o, lse
 
 
 def attn_bwd(do, q, k, v, o, lse, heads, causal=False, scale=None, bias=None, dq=None, dk=None, dv=None, dbias=None,
-             kv_len=None):
+             kv_len=None, dropout=None):
     """dbias: optional zero-initialised fp32 [heads, Tq, Tk]; receives sum_b dS (gradient of the additive bias).
     kv_len: as in attn_fwd; the k / v rows at or past kv_len[b] must hold zeros (mask_rows), dk / dv are zero there."""
     B, Tq, HD = q.shape
@@ -356,6 +364,7 @@ def attn_bwd(do, q, k, v, o, lse, heads, causal=False, scale=None, bias=None, dq
     a.do_row_stride, a.do_batch_stride = do.stride(1), do.stride(0)
     a.dq_row_stride, a.dk_row_stride, a.dv_row_stride = dq.stride(1), dk.stride(1), dv.stride(1)
     a.dq_batch_stride, a.dk_batch_stride, a.dv_batch_stride = dq.stride(0), dk.stride(0), dv.stride(0)
+    _set_dropout(a, dropout)
     _lib.check(_lib.load().smx_attn_bwd(ctypes.byref(a), _stream()), "smx_attn_bwd")
     return dq, dk, dv
 
@@ -406,6 +415,29 @@ def mask_rows(x, lens, col_begin=0, col_count=None):
     _lib.check(_L().smx_mask_rows(_ptr(x), _ptr(lens), B, T, x.stride(1), x.stride(0), col_begin, col_count, _stream()),
                "mask_rows")
     return x
+
+
+def dropout(x, state, call, p, residual=None, aux_in=None, aux_mode=0):
+    """out = residual + keep ? x / (1 - p) : 0 (bf16, any shape, numel % 8 == 0); with aux_mode 1 / 2 also returns the
+    masked multiplier tensor for the activation-gradient epilogue (see smx_dropout).  state: int64 [2] on the device."""
+    x = x.contiguous()
+    assert x.dtype == BF16 and state.dtype == torch.int64 and state.numel() == 2
+    out = torch.empty_like(x)
+    aux_out = torch.empty_like(x) if aux_mode else None
+    res = None if residual is None else residual.contiguous()
+    aux = None if aux_in is None else aux_in.contiguous()
+    _lib.check(_L().smx_dropout(_ptr(x), _ptr(res), _ptr(out), _ptr(aux), _ptr(aux_out), aux_mode, x.numel(), _ptr(state),
+                                int(call), float(p), _stream()), "dropout")
+    return (out, aux_out) if aux_mode else out
+
+
+def dropout_mask(shape, state, call, p, attention=False):
+    """keep decisions (uint8, `shape`) of dropout call `call` -- tests feed them to the CPU reference run.  attention=True:
+    shape [B, H, Tq, Tk], numbered the way the attention kernels number their probabilities."""
+    mask = torch.empty(shape, dtype=torch.uint8, device=state.device)
+    _lib.check(_L().smx_dropout_mask(_ptr(mask), mask.numel(), shape[-1] if attention else 0, 1 if attention else 0,
+                                     _ptr(state), int(call), float(p), _stream()), "dropout_mask")
+    return mask
 
 
 def spec_augment_fwd(x, time_mask, feat_mask, embed):

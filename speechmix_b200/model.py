@@ -90,18 +90,12 @@ DEFAULT_FIXED_EXCEPT = ["layer_norm", "encoder_attn", "enc_to_dec_proj", "length
                         "attention"]
 
 
-def _warn_ignored_dropout(speech_cfg, text_cfg):
-    """Dropout is the one regulariser of the reference's training recipe that the fused kernels do not apply yet
-    (DESIGN.md section 7): say so once instead of silently training without it.  LayerDrop and SpecAugment are
-    honoured."""
+def _dropout_knobs(speech_cfg, text_cfg):
+    """names of the dropout probabilities that are switched on in the two backbone configs"""
     knobs = [("speech", speech_cfg, ("hidden_dropout", "attention_dropout", "activation_dropout", "feat_proj_dropout")),
              ("text", text_cfg, ("dropout", "attention_dropout", "activation_dropout", "dropout_rate"))]
-    live = ["%s.%s=%g" % (side, k, getattr(cfg, k)) for side, cfg, ks in knobs for k in ks
+    return ["%s.%s=%g" % (side, k, getattr(cfg, k)) for side, cfg, ks in knobs for k in ks
             if isinstance(getattr(cfg, k, 0.0), float) and getattr(cfg, k, 0.0) > 0.0]
-    if live:
-        import warnings
-        warnings.warn("speechmix_b200 does not implement dropout: training behaves as if these were 0 -> " +
-                      ", ".join(live), stacklevel=3)
 
 
 class SpeechMixEED(nn.Module):
@@ -117,7 +111,9 @@ class SpeechMixEED(nn.Module):
         # names in the reference; config objects (random init) are accepted too for offline use.
         self.encoder_model = speech_from_pretrained(speech_model_config)
         self.decoder_model = text_from_pretrained(nlp_model_config)
-        _warn_ignored_dropout(self.encoder_model.config, self.decoder_model.config)
+        # train-mode dropout of the backbones (the reference trains under .train(): ref:train.py:315-330) is applied by
+        # the kernels with counter-based masks; this only records whether any site is live
+        self.dropout_sites = _dropout_knobs(self.encoder_model.config, self.decoder_model.config)
         self.config = SpeechMixConfig(self.encoder_model.config, self.decoder_model.config)
         self.tokenizer = tokenizer
         if tokenizer is None and isinstance(nlp_model_config, str):
@@ -259,6 +255,8 @@ class SpeechMixEED(nn.Module):
         labels = labels.to(dev) if labels is not None else None
         decoder_input_ids = decoder_input_ids.to(dev) if decoder_input_ids is not None else None
         text_input_ids = text_input_ids.to(dev) if text_input_ids is not None else None
+        if self.training and self.dropout_sites:
+            ops.DROPOUT.begin_step(dev)      # new masks for this pass (device-side counter: survives CUDA-graph replay)
         if encoder_outputs is None and torch.is_grad_enabled():
             # a training pass: the optimizer may have moved the fp32 masters since the last pass (fused
             # optimizers do not bump tensor versions) -> refresh all bf16 working copies in one launch

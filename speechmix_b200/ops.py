@@ -120,6 +120,74 @@ class fp32_verification:
         return False
 
 
+class DropoutState:
+    """Device-resident {seed, step} pair behind every dropout mask (csrc/sm100_prims.cuh ``drop_key``) plus the host-side
+    call counter that numbers the dropout sites of one forward pass in execution order (the same order in which the HF
+    modules call ``F.dropout``, which is what lets the parity tests feed OUR masks to the CPU reference run).
+
+    ``begin_step()`` -- called by the model at the start of every training forward -- advances ``step`` ON THE DEVICE, so
+    a replayed CUDA graph (which re-executes that increment) draws fresh masks on every replay; the backward pass of the
+    same step regenerates the masks from the unchanged pair."""
+
+    def __init__(self):
+        self._state = {}
+        self.calls = 0
+        self.seed = 0x5eed
+        self.trace = None     # tests: list of (call, p, kind, shape) of the sites of a forward pass, in call order
+
+    def state(self, device):
+        device = torch.device(device)
+        st = self._state.get(device)
+        if st is None:
+            st = torch.tensor([self.seed, 0], dtype=torch.int64, device=device)
+            self._state[device] = st
+        return st
+
+    def manual_seed(self, seed):
+        self.seed = int(seed)
+        for st in self._state.values():
+            st.copy_(torch.tensor([self.seed, 0], dtype=torch.int64))
+
+    def begin_step(self, device):
+        self.state(device)[1:2].add_(1)
+        self.calls = 0
+
+    def next_call(self, p=None, kind=None, shape=None):
+        self.calls += 1
+        if self.trace is not None:
+            self.trace.append((self.calls - 1, p, kind, tuple(shape) if shape is not None else None))
+        return self.calls - 1
+
+
+DROPOUT = DropoutState()
+
+
+class DropoutFn(torch.autograd.Function):
+    """y = keep ? x / (1 - p) : 0 at an elementwise dropout site (embedding / encoder-level dropout of the HF modules)."""
+
+    @staticmethod
+    def forward(ctx, x, p):
+        ctx.call, ctx.p, ctx.state = DROPOUT.next_call(p, "elementwise", x.shape), p, DROPOUT.state(x.device)
+        return K.dropout(x, ctx.state, ctx.call, p)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return K.dropout(dy, ctx.state, ctx.call, ctx.p), None
+
+
+def dropout(x, p, training):
+    if not training or p <= 0.0 or K.FP32_MODE:
+        return x
+    return DropoutFn.apply(x, float(p))
+
+
+def _drop_site(p, device, kind="elementwise", shape=None):
+    """(state, call, p) of a dropout site inside a fused block, or None when it is off"""
+    if p is None or p <= 0.0 or K.FP32_MODE:
+        return None
+    return (DROPOUT.state(device), DROPOUT.next_call(float(p), kind, shape), float(p))
+
+
 def w16(p):
     if K.FP32_MODE:
         return p.detach()
@@ -309,8 +377,16 @@ class AttnBlockFn(torch.autograd.Function):
             qkv = (q, kv)
             kv_src2 = src2
         pb = None if pos_bias is None else pos_bias.detach().float().contiguous()
-        o, lse = K.attn_fwd(q, k, v, heads, causal=causal, scale=scale, bias=pb, kv_len=kv_len)
-        s = K.linear_fwd(o.view(B * T, Hi), w16(o_w), None if o_b is None else o_b.detach(), residual=x2)
+        # train-mode dropout of the HF blocks, in their call order: attention probabilities, then the block output
+        # before the residual add (hf:...wav2vec2.py:466-549,590-596 ; hf:...bart.py:143-258,280-290)
+        drop_a = _drop_site(cfg.get("p_attn"), x.device, "attention", (B, heads, T, Ts))
+        drop_h = _drop_site(cfg.get("p_hidden"), x.device, "elementwise", (B, T, H))
+        o, lse = K.attn_fwd(q, k, v, heads, causal=causal, scale=scale, bias=pb, kv_len=kv_len, dropout=drop_a)
+        if drop_h is None:
+            s = K.linear_fwd(o.view(B * T, Hi), w16(o_w), None if o_b is None else o_b.detach(), residual=x2)
+        else:
+            s0 = K.linear_fwd(o.view(B * T, Hi), w16(o_w), None if o_b is None else o_b.detach())
+            s = K.dropout(s0, *drop_h, residual=x2)
         if pre_ln:
             y = s
             ctx.save_for_backward(x2, n, mean, rstd, o, lse, kv_src2, ln_w, pb, *(qkv if src is not None else (qkv,)))
@@ -318,6 +394,7 @@ class AttnBlockFn(torch.autograd.Function):
             y, _, mean, rstd = K.layernorm_fwd(s, ln_w.detach(), ln_b_d, eps, rms_only=rms)
             ctx.save_for_backward(x2, s, mean, rstd, o, lse, kv_src2, ln_w, pb, *(qkv if src is not None else (qkv,)))
         ctx.cfg = dict(cfg, scale=scale, rms=rms)
+        ctx.drop_a, ctx.drop_h = drop_a, drop_h
         ctx.kv_len = kv_len
         ctx.dims = (B, T, H, Ts, Hi)
         ctx.cross = src is not None
@@ -344,10 +421,14 @@ class AttnBlockFn(torch.autograd.Function):
                                                    want_colsum=True)   # colsum(ds) = out-proj bias gradient, fused
             a_in = x2
         o2 = o.view(B * T, Hi)
-        if pre_ln or not ctx.has_obias:
+        ds_res = ds                      # gradient of the residual branch (not dropped)
+        if ctx.drop_h is not None:       # gradient through the block-output dropout: the same mask on ds
+            ds = K.dropout(ds, *ctx.drop_h)
+        if pre_ln or not ctx.has_obias or ctx.drop_h is not None:
             d_ob = K.colsum(ds) if ctx.has_obias else None
         d_ow = K.linear_wgrad(ds, o2) if _need(ctx, 9) else None
         do = K.linear_dgrad(ds, w16(o_w)).view(B, T, Hi)
+        ds = ds_res
         dsrc = None
         dpb = K.zeros_f32(*pb.shape, device=pb.device) if (pb is not None and _need(ctx, 13)) else None
         if not ctx.cross:
@@ -355,7 +436,7 @@ class AttnBlockFn(torch.autograd.Function):
             q, k, v = qkv[..., :Hi], qkv[..., Hi:2 * Hi], qkv[..., 2 * Hi:]
             dqkv = torch.empty_like(qkv)
             K.attn_bwd(do, q, k, v, o, lse, heads, causal=causal, scale=scale, bias=pb, dq=dqkv[..., :Hi],
-                       dk=dqkv[..., Hi:2 * Hi], dv=dqkv[..., 2 * Hi:], dbias=dpb, kv_len=ctx.kv_len)
+                       dk=dqkv[..., Hi:2 * Hi], dv=dqkv[..., 2 * Hi:], dbias=dpb, kv_len=ctx.kv_len, dropout=ctx.drop_a)
             dqkv2 = dqkv.view(B * T, 3 * Hi)
             need_w = _need(ctx, 3) or _need(ctx, 5) or _need(ctx, 7)
             dwqkv = K.linear_wgrad(dqkv2, a_in) if need_w else None
@@ -370,7 +451,7 @@ class AttnBlockFn(torch.autograd.Function):
             dq = torch.empty_like(q)
             dkv = torch.empty_like(kv)
             K.attn_bwd(do, q, k, v, o, lse, heads, causal=causal, scale=scale, bias=pb, dq=dq, dk=dkv[..., :Hi],
-                       dv=dkv[..., Hi:], dbias=dpb, kv_len=ctx.kv_len)
+                       dv=dkv[..., Hi:], dbias=dpb, kv_len=ctx.kv_len, dropout=ctx.drop_a)
             dq2 = dq.view(B * T, Hi)
             dkv2 = dkv.view(-1, 2 * Hi)
             need_q = _need(ctx, 3)
@@ -414,7 +495,20 @@ class FFNBlockFn(torch.autograd.Function):
             a_in = x2
         h, pre = K.linear_fwd(a_in, w16(w1), None if b1 is None else b1.detach(), act=act, want_pre=True)
         no_res = bool(cfg.get("no_residual", False))  # adapter blocks: y = W2.act(W1 LN(x) + b1) + b2
-        s = K.linear_fwd(h, w16(w2), None if b2 is None else b2.detach(), residual=None if no_res else x2)
+        # train-mode dropout of the HF feed-forward blocks, in their call order: after the activation, then on the block
+        # output before the residual add (hf:...wav2vec2.py:552-573 ; hf:...bart.py:296-309 ; hf:...t5.py:80-101)
+        drop_act = _drop_site(cfg.get("p_act"), x.device, "elementwise", tuple(shp[:-1]) + (w1.shape[0],))
+        drop_h = _drop_site(cfg.get("p_hidden"), x.device, "elementwise", shp)
+        if drop_act is not None:
+            # the dropped activation feeds fc2 (and its weight gradient); the stored activation-gradient operand becomes
+            # the masked multiplier keep * act'(pre) / (1 - p), so the backward epilogue stays a single multiply
+            h, pre = K.dropout(h, *drop_act, aux_in=pre, aux_mode=2 if dact == ACT_DRELU else 1)
+            dact = ACT_MULAUX
+        if drop_h is None:
+            s = K.linear_fwd(h, w16(w2), None if b2 is None else b2.detach(), residual=None if no_res else x2)
+        else:
+            s0 = K.linear_fwd(h, w16(w2), None if b2 is None else b2.detach())
+            s = K.dropout(s0, *drop_h, residual=None if no_res else x2)
         if pre_ln:
             y = s
             ctx.save_for_backward(x2, n, mean, rstd, pre, h, ln_w)
@@ -424,6 +518,7 @@ class FFNBlockFn(torch.autograd.Function):
         ctx.pre_ln, ctx.dact, ctx.shp = pre_ln, dact, shp
         ctx.rms, ctx.has_lnb = rms, ln_b is not None
         ctx.no_res = no_res
+        ctx.drop_h = drop_h
         ctx.wrefs = (w1, w2)
         ctx.has_bias = b1 is not None
         return y.view(shp)
@@ -440,10 +535,14 @@ class FFNBlockFn(torch.autograd.Function):
             ds, dlnw, dlnb, db2 = K.layernorm_bwd(dy2, a, ln_w.detach(), mean, rstd, rms_only=ctx.rms, want_dbeta=ctx.has_lnb,
                                                   want_colsum=True)    # colsum(ds) = fc2 bias gradient, fused
             a_in = x2
-        if ctx.pre_ln or not ctx.has_bias:
+        ds_res = ds
+        if ctx.drop_h is not None:       # gradient through the block-output dropout
+            ds = K.dropout(ds, *ctx.drop_h)
+        if ctx.pre_ln or not ctx.has_bias or ctx.drop_h is not None:
             db2 = K.colsum(ds) if ctx.has_bias else None
         dw2 = K.linear_wgrad(ds, h) if _need(ctx, 4) else None
         dpre = K.linear_dgrad(ds, w16(w2), act=ctx.dact, aux_in=pre)
+        ds = ds_res
         db1 = K.colsum(dpre) if ctx.has_bias else None
         dw1 = K.linear_wgrad(dpre, a_in) if _need(ctx, 2) else None
         d_in = K.linear_dgrad(dpre, w16(w1), residual=None if (ctx.pre_ln or ctx.no_res) else ds)

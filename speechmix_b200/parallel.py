@@ -119,6 +119,8 @@ class GradientAllReducer:
                 self._launch_captured(bi)
         self.order = sorted(self.order)     # collectives go out in index order on every rank
         self.graph_mode, self.enabled = False, False
+        self.ready, self.next_bucket = [False] * len(self.buckets), 0
+        self.pending = [len(b) for b in self.buckets]
 
     def _launch_captured(self, bi):
         views = self._views(bi)
@@ -170,8 +172,9 @@ class GradientAllReducer:
     def finish(self):
         """Call after ``loss.backward()``: flush buckets whose parameters received no gradient this
         step, wait for the collectives and write the averaged gradients back."""
-        for bi in range(self.next_bucket, len(self.buckets)):
-            self._launch(bi)
+        for bi in range(len(self.buckets)):      # in index order: the same sequence of collectives on every rank
+            if self.works[bi] is None:
+                self._launch(bi)
         for bi, b in enumerate(self.buckets):
             self.works[bi].wait()
             self._unpack(bi)

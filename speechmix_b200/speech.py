@@ -84,11 +84,13 @@ class FeatureProjection(nn.Module):
             self.layer_norm = nn.LayerNorm(config.conv_dim[-1], eps=config.layer_norm_eps)
         self.projection = nn.Linear(config.conv_dim[-1], config.hidden_size)
         self.eps = config.layer_norm_eps
+        self.p_drop = float(getattr(config, "feat_proj_dropout", 0.0) or 0.0)
 
     def forward(self, x):
         if self.with_layer_norm:
             x = ops.layer_norm(x, self.layer_norm.weight, self.layer_norm.bias, self.eps)
-        return ops.linear(x, self.projection.weight, self.projection.bias)
+        x = ops.linear(x, self.projection.weight, self.projection.bias)
+        return ops.dropout(x, self.p_drop, self.training)      # hf:...wav2vec2.py:432 (feat_proj_dropout)
 
 
 class PositionalConvEmbedding(nn.Module):
@@ -144,15 +146,19 @@ class EncoderLayer(nn.Module):
         self.final_layer_norm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
         self.cfg = dict(heads=config.num_attention_heads, causal=False, pre_ln=bool(config.do_stable_layer_norm),
                         eps=config.layer_norm_eps, act=config.hidden_act)
+        # train-mode dropout (hf:...wav2vec2.py:466-573): attention probabilities / block outputs / FFN activation
+        self.drop = dict(p_attn=float(config.attention_dropout), p_hidden=float(config.hidden_dropout),
+                         p_act=float(config.activation_dropout))
         if config.hidden_size // config.num_attention_heads != 64:
             raise NotImplementedError("attention kernels are specialised for head_dim 64")
 
     def forward(self, x, kv_len=None):
-        cfg = self.cfg if kv_len is None else dict(self.cfg, kv_len=kv_len)
+        base = dict(self.cfg, **self.drop) if (self.training and any(v > 0 for v in self.drop.values())) else self.cfg
+        cfg = base if kv_len is None else dict(base, kv_len=kv_len)
         x = ops.AttnBlockFn.apply(x, None, cfg, *self.attention.params(), self.layer_norm.weight,
                                   self.layer_norm.bias)
         ff = self.feed_forward
-        return ops.FFNBlockFn.apply(x, self.cfg, ff.intermediate_dense.weight, ff.intermediate_dense.bias,
+        return ops.FFNBlockFn.apply(x, base, ff.intermediate_dense.weight, ff.intermediate_dense.bias,
                                     ff.output_dense.weight, ff.output_dense.bias, self.final_layer_norm.weight,
                                     self.final_layer_norm.bias)
 
@@ -177,6 +183,7 @@ class Encoder(nn.Module):
         x = self.pos_conv_embed(x)
         if not self.stable:
             x = ops.layer_norm(x, self.layer_norm.weight, self.layer_norm.bias, self.config.layer_norm_eps)
+        x = ops.dropout(x, float(self.config.hidden_dropout), self.training)   # hf:...wav2vec2.py:695 / :770
         for layer in self.layers:
             if output_hidden_states:
                 hs.append(x)

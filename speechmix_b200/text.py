@@ -16,10 +16,25 @@ from . import ops
 from .speech import SpeechOutput, _Attention, load_checkpoint_state, resolve_checkpoint
 
 
+def _with_dropout(cfg, drop, training):
+    """block configuration with the train-mode dropout probabilities of the HF layer (p_attn on the attention
+    probabilities, p_hidden on the block outputs before the residual add, p_act after the FFN activation)"""
+    if training and drop and any(v > 0 for v in drop.values()):
+        return dict(cfg, **drop)
+    return cfg
+
+
+def _drop_probs(config):
+    if config.model_type == "t5":
+        p = float(config.dropout_rate)
+        return dict(p_attn=p, p_hidden=p, p_act=p)
+    return dict(p_attn=float(config.attention_dropout), p_hidden=float(config.dropout), p_act=float(config.activation_dropout))
+
+
 class _EncoderLayer(nn.Module):
     """hf:...bart.py:261-309 (post-LN) / hf:...mbart.py:274-328 (pre-LN)"""
 
-    def __init__(self, d, heads, ffn, act, pre_ln):
+    def __init__(self, d, heads, ffn, act, pre_ln, drop=None):
         super().__init__()
         self.self_attn = _Attention(d)
         self.self_attn_layer_norm = nn.LayerNorm(d)
@@ -27,19 +42,22 @@ class _EncoderLayer(nn.Module):
         self.fc2 = nn.Linear(ffn, d)
         self.final_layer_norm = nn.LayerNorm(d)
         self.cfg = dict(heads=heads, causal=False, pre_ln=pre_ln, eps=1e-5, act=act)
+        self.drop = drop or {}
 
     def forward(self, x):
-        x = ops.AttnBlockFn.apply(x, None, self.cfg, *self.self_attn.params(), self.self_attn_layer_norm.weight,
+        cfg = _with_dropout(self.cfg, self.drop, self.training)
+        x = ops.AttnBlockFn.apply(x, None, cfg, *self.self_attn.params(), self.self_attn_layer_norm.weight,
                                   self.self_attn_layer_norm.bias)
-        return ops.FFNBlockFn.apply(x, self.cfg, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias,
+        return ops.FFNBlockFn.apply(x, cfg, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias,
                                     self.final_layer_norm.weight, self.final_layer_norm.bias)
 
 
 class _DecoderLayer(nn.Module):
     """hf:...bart.py:312-391 / hf:...mbart.py:331-430"""
 
-    def __init__(self, d, heads, ffn, act, pre_ln):
+    def __init__(self, d, heads, ffn, act, pre_ln, drop=None):
         super().__init__()
+        self.drop = drop or {}
         self.self_attn = _Attention(d)
         self.self_attn_layer_norm = nn.LayerNorm(d)
         self.encoder_attn = _Attention(d)
@@ -51,11 +69,13 @@ class _DecoderLayer(nn.Module):
         self.cfg_cross = dict(heads=heads, causal=False, pre_ln=pre_ln, eps=1e-5, act=act)
 
     def forward(self, x, enc):
-        x = ops.AttnBlockFn.apply(x, None, self.cfg_self, *self.self_attn.params(), self.self_attn_layer_norm.weight,
+        cfg_self = _with_dropout(self.cfg_self, self.drop, self.training)
+        cfg_cross = _with_dropout(self.cfg_cross, self.drop, self.training)
+        x = ops.AttnBlockFn.apply(x, None, cfg_self, *self.self_attn.params(), self.self_attn_layer_norm.weight,
                                   self.self_attn_layer_norm.bias)
-        x = ops.AttnBlockFn.apply(x, enc, self.cfg_cross, *self.encoder_attn.params(),
+        x = ops.AttnBlockFn.apply(x, enc, cfg_cross, *self.encoder_attn.params(),
                                   self.encoder_attn_layer_norm.weight, self.encoder_attn_layer_norm.bias)
-        return ops.FFNBlockFn.apply(x, self.cfg_cross, self.fc1.weight, self.fc1.bias, self.fc2.weight,
+        return ops.FFNBlockFn.apply(x, cfg_cross, self.fc1.weight, self.fc1.bias, self.fc2.weight,
                                     self.fc2.bias, self.final_layer_norm.weight, self.final_layer_norm.bias)
 
 
@@ -77,7 +97,8 @@ class _Stack(nn.Module):
         if d // heads != 64:
             raise NotImplementedError("attention kernels are specialised for head_dim 64")
         cls = _DecoderLayer if is_decoder else _EncoderLayer
-        self.layers = nn.ModuleList([cls(d, heads, ffn, config.activation_function, pre_ln) for _ in range(n)])
+        self.layers = nn.ModuleList([cls(d, heads, ffn, config.activation_function, pre_ln, _drop_probs(config))
+                                     for _ in range(n)])
         self.layernorm_embedding = nn.LayerNorm(d)
         if pre_ln:
             self.layer_norm = nn.LayerNorm(d)
@@ -88,7 +109,8 @@ class _Stack(nn.Module):
         """tokens*scale (or given embeddings, unscaled: hf:...bart.py:520-524) + learned positions, then LN."""
         x = ops.EmbedFn.apply(input_ids, inputs_embeds, self.embed_tokens.weight if input_ids is not None else None,
                               self.embed_positions.weight, self.embed_scale, self.POS_OFFSET, t_start)
-        return ops.layer_norm(x, self.layernorm_embedding.weight, self.layernorm_embedding.bias, 1e-5)
+        x = ops.layer_norm(x, self.layernorm_embedding.weight, self.layernorm_embedding.bias, 1e-5)
+        return ops.dropout(x, float(self.config.dropout), self.training)    # hf:...bart.py:530 / :640
 
     def forward(self, input_ids=None, inputs_embeds=None, encoder_hidden_states=None, output_hidden_states=False):
         x = self.embed(input_ids, inputs_embeds)
@@ -297,16 +319,19 @@ class _T5Block(nn.Module):
         base = dict(heads=config.num_heads, pre_ln=True, rms=True, eps=eps, scale=1.0, act=config.dense_act_fn)
         self.cfg_self = dict(base, causal=is_decoder)
         self.cfg_cross = dict(base, causal=False)
+        self.drop = _drop_probs(config)
 
     def forward(self, x, pos_bias, enc=None):
+        cfg_self = _with_dropout(self.cfg_self, self.drop, self.training)
+        cfg_cross = _with_dropout(self.cfg_cross, self.drop, self.training)
         sa = self.layer[0]
-        x = ops.AttnBlockFn.apply(x, None, self.cfg_self, *sa.SelfAttention.params(), sa.layer_norm.weight, None, pos_bias)
+        x = ops.AttnBlockFn.apply(x, None, cfg_self, *sa.SelfAttention.params(), sa.layer_norm.weight, None, pos_bias)
         if self.is_decoder:
             ca = self.layer[1]
-            x = ops.AttnBlockFn.apply(x, enc, self.cfg_cross, *ca.EncDecAttention.params(), ca.layer_norm.weight, None,
+            x = ops.AttnBlockFn.apply(x, enc, cfg_cross, *ca.EncDecAttention.params(), ca.layer_norm.weight, None,
                                       None)
         ff = self.layer[-1]
-        return ops.FFNBlockFn.apply(x, self.cfg_cross, ff.DenseReluDense.wi.weight, None, ff.DenseReluDense.wo.weight,
+        return ops.FFNBlockFn.apply(x, cfg_cross, ff.DenseReluDense.wi.weight, None, ff.DenseReluDense.wo.weight,
                                     None, ff.layer_norm.weight, None)
 
 
@@ -332,6 +357,7 @@ class _T5Stack(nn.Module):
             x = ops.EmbedFn.apply(input_ids, None, self.embed_tokens.weight, None, 1.0, 0, 0)
         else:
             x = inputs_embeds if inputs_embeds.dtype == K.act_dtype() else ops.EmbedFn.apply(None, inputs_embeds, None, None, 1.0, 0, 0)
+        x = ops.dropout(x, float(cfg.dropout_rate), self.training)          # hf:...t5.py:700 (embedding dropout)
         T = x.shape[1]
         table = ops.t5_bucket_table(T, T, not self.is_decoder, cfg.relative_attention_num_buckets,
                                     cfg.relative_attention_max_distance, x.device)
@@ -345,6 +371,7 @@ class _T5Stack(nn.Module):
             if output_hidden_states:
                 hs.append(x)
         x = ops.layer_norm(x, self.final_layer_norm.weight, None, cfg.layer_norm_epsilon, rms_only=True)
+        x = ops.dropout(x, float(cfg.dropout_rate), self.training)          # hf:...t5.py:765 (after the final norm)
         if output_hidden_states:
             hs[-1] = x
         return x, hs

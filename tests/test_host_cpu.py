@@ -137,20 +137,15 @@ def test_cpu_call_fails_loudly():
         m(torch.randn(1, 16000), labels=torch.randint(4, 100, (1, 4)))
 
 
-def test_ignored_dropout_is_reported_once_not_silently():
-    """dropout is not implemented; a config that asks for it gets a warning naming the knobs."""
-    import warnings
+def test_dropout_sites_are_discovered_from_the_configs():
+    """the stock configs of the reference recipe switch dropout on; the model records the live sites (the kernels apply
+    them with counter-based masks -- tests/test_dropout_gpu.py)"""
     from transformers import BartConfig, Wav2Vec2Config
-    from speechmix_b200.model import _warn_ignored_dropout
-    with warnings.catch_warnings(record=True) as w:
-        warnings.simplefilter("always")
-        _warn_ignored_dropout(Wav2Vec2Config(), BartConfig())
-        assert len(w) == 1 and "speech.hidden_dropout=0.1" in str(w[0].message) and "text.dropout=0.1" in str(w[0].message)
+    from speechmix_b200.model import _dropout_knobs
+    live = _dropout_knobs(Wav2Vec2Config(), BartConfig())
+    assert "speech.hidden_dropout=0.1" in live and "text.dropout=0.1" in live
     quiet = Wav2Vec2Config(hidden_dropout=0.0, attention_dropout=0.0, activation_dropout=0.0, feat_proj_dropout=0.0)
-    with warnings.catch_warnings(record=True) as w:
-        warnings.simplefilter("always")
-        _warn_ignored_dropout(quiet, BartConfig(dropout=0.0, attention_dropout=0.0, activation_dropout=0.0))
-        assert len(w) == 0
+    assert _dropout_knobs(quiet, BartConfig(dropout=0.0, attention_dropout=0.0, activation_dropout=0.0)) == []
 
 
 def test_adafactor_tile_table_covers_every_element_once():
