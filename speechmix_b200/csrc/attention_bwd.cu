@@ -72,6 +72,33 @@ __device__ __forceinline__ void store_out_row(bf16* dst, uint32_t taddr, bool va
   }
 }
 
+// 32 fp32 accumulator columns of this thread's TMEM lane -> 32 bf16 of one output row
+__device__ __forceinline__ void store_out_half(bf16* dst, uint32_t taddr, bool valid, bool live = true) {
+  uint32_t v[32];
+  tmem_ld_x32(taddr, v);
+  tmem_ld_wait();
+  if (valid) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      uint4 u;
+      u.x = pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+      u.y = pack_bf16x2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+      u.z = pack_bf16x2(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+      u.w = pack_bf16x2(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
+      *reinterpret_cast<uint4*>(dst + i) = live ? u : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::
+          "r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+
 // =====================================================================================
 // Pipelined TMEM-operand kernels.  (A first generation with 128-wide single-buffered score tiles and every operand in
 // shared memory measured 114 clk per 128x64x16 MMA inside the kernel against 45 clk in isolation,
@@ -110,6 +137,15 @@ __device__ __forceinline__ void mma_tA_x_sub(uint32_t d_tmem, uint32_t a_tmem, u
   for (int kk = 0; kk < 4; ++kk)
     umma_ts(d_tmem, a_tmem + kk * 8, lean_desc(lo + kk * 128), idesc, (accumulate || kk > 0) ? 1u : 0u);
 }
+// the same with the bf16 A operand stored as two K halves of 32 elements: K steps 0,1 at a_tmem + {0, 8}, K steps 2,3
+// at a_tmem + 32 + {0, 8} (each half over the first 16 columns of the 32 fp32 columns it was computed from)
+__device__ __forceinline__ void mma_tA2_x_sub(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_sub, uint32_t idesc,
+                                              bool accumulate) {
+  const uint32_t lo = (b_sub >> 4) | ((static_cast<uint32_t>(SUBTILE) >> 4) << 16);
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk)
+    umma_ts(d_tmem, a_tmem + (kk >> 1) * 32 + (kk & 1) * 8, lean_desc(lo + kk * 128), idesc, (accumulate || kk > 0) ? 1u : 0u);
+}
 // copy row r of a K-major 128B-swizzled [128 x 64] bf16 smem tile into 32 TMEM columns of this thread's lane
 __device__ __forceinline__ void smem_row_to_tmem(const uint8_t* tile, int r, uint32_t taddr) {
   uint32_t v[32];
@@ -123,12 +159,15 @@ __device__ __forceinline__ void smem_row_to_tmem(const uint8_t* tile, int r, uin
   tmem_st_x32(taddr, v);
 }
 
-// ---- co-resident variants: 192 threads (producer, MMA issuer, 4 compute warps), 256 TMEM columns and ~97 KiB of
-// shared memory per CTA, so TWO CTAs share an SM: while one CTA's compute warps turn a sub-tile into P^T / dS^T
+// ---- co-resident variants: 320 threads (8 compute warps, producer, MMA issuer), 256 TMEM columns and ~97 KiB of
+// shared memory per CTA, so TWO CTAs share an SM.  A row of a 64-wide sub-tile is split between TWO threads (32
+// columns each; warps 0-3 / 4-7), so four compute warps share every scheduler: with one thread per row the MUFU / FMA
+// chains of two warps per scheduler left ~65 % of the issue slots empty (round-1 ncu: issue active 27 %).
+// Two CTAs per SM: while one CTA's compute warps turn a sub-tile into P^T / dS^T
 // (MUFU bound) the other CTA's MMAs run, and the prologue / epilogue of one CTA (TMEM alloc, first TMA round trip,
 // gradient store) hides behind the main loop of the other -- with one 512-column CTA per SM those fixed costs
 // were ~6k of ~25k cycles per 128-row tile.
-constexpr int BWD2_THREADS = 192;
+constexpr int BWD2_THREADS = 320;   // 8 compute warps (lane quarter x column half), TMA producer, MMA issuer
 
 // D[128 x 64] = A (smem, K-major [128 x 64]) x B^T, B = K-major [64 x 64] smem sub-tile; 4 K-steps
 __device__ __forceinline__ void mma_sA_x_subT(uint32_t d_tmem, uint32_t a_tile, uint32_t b_sub, uint32_t idesc) {
@@ -179,26 +218,26 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_consta
       mbar_init(&bars[B_QEMPTY + s], 1);
     }
     mbar_init(&bars[B_STFULL], 1);
-    mbar_init(&bars[B_PDSFULL], 128);
+    mbar_init(&bars[B_PDSFULL], 256);
     mbar_init(&bars[B_DONE], 1);
     fence_barrier_init();
   }
   __syncthreads();
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     // the loads of this CTA start BEFORE its TMEM allocation: when the co-resident CTA still owns the other half
     // of TMEM (or a previous CTA has not released its columns yet) the first tiles are already in flight
     mbar_expect_tx(&bars[B_KV], 2 * TILE);
     tma_load_4d(smem + OFF_K, &mk, &bars[B_KV], 0, kv0, head, b);
     tma_load_4d(smem + OFF_V, &mv, &bars[B_KV], 0, kv0, head, b);
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  if (warp == 9) tmem_alloc(tmem_slot, 256);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t sbase = smem_u32(smem);
 
-  if (warp == 0) {
+  if (warp == 8) {
     if (lane == 0) {
       for (int it = 0; it < n_iter; ++it) {
         const int st = it % NST;
@@ -210,7 +249,7 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_consta
         tma_load_4d(smem + OFF_DO + st * SUBTILE, &mdo, &bars[B_QFULL + st], 0, qr, head, b);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     // The WHOLE warp runs the loop (waits and address arithmetic are warp-uniform, so the tcgen05.mma operands sit in
     // uniform registers); one elected lane issues.  Under `if (lane == 0)` every MMA cost ~80 clk of issue (a
     // register -> uniform-register broadcast loop per descriptor) against ~45 clk of tensor-pipe time.
@@ -232,8 +271,8 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_consta
       mbar_wait(&bars[B_PDSFULL], it & 1);
       tc_fence_after_sync();
       if (elect_one()) {
-        mma_tA_x_sub(tmem_base + COL_DV, tmem_base + COL_ST, sbase + OFF_DO + st * SUBTILE, idesc_o, it > 0);   // P^T . dO
-        mma_tA_x_sub(tmem_base + COL_DK, tmem_base + COL_DPT, sbase + OFF_Q + st * SUBTILE, idesc_o, it > 0);   // dS^T . Q
+        mma_tA2_x_sub(tmem_base + COL_DV, tmem_base + COL_ST, sbase + OFF_DO + st * SUBTILE, idesc_o, it > 0);   // P^T . dO
+        mma_tA2_x_sub(tmem_base + COL_DK, tmem_base + COL_DPT, sbase + OFF_Q + st * SUBTILE, idesc_o, it > 0);   // dS^T . Q
         umma_commit(&bars[B_QEMPTY + st]);
       }
       __syncwarp();
@@ -242,9 +281,10 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_consta
     __syncwarp();
   } else {
     const int q = warp & 3;         // TMEM lane quarter
+    const int hf = warp >> 2;       // column half of the 64-wide sub-tile this thread owns: queries [32 hf, 32 hf + 32)
     const int r = q * 32 + lane;    // key row inside the tile
     const int kvi = kv0 + r;
-    const int gt = (warp - 2) * 32 + lane;  // 0..127
+    const int gt = warp * 32 + lane;  // 0..255; the first 128 threads stage lse / delta
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     float* stat = reinterpret_cast<float*>(smem + OFF_STAT);
     const DropKey dkey = drop_key(p.drop_state, p.drop_call, p.drop_p);   // thresh 0: off
@@ -257,33 +297,28 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_consta
     const float stat_mul = gt < 64 ? -kLog2e : -p.scale;   // stored NEGATED: both are subtracted through an FMA
     auto load_stat = [&](int it) -> float {
       const int qi = (i_start + it) * SUB + (gt & 63);
-      return (it < n_iter && qi < p.tq) ? stat_src[qi] * stat_mul : 0.f;
+      return (gt < 128 && it < n_iter && qi < p.tq) ? stat_src[qi] * stat_mul : 0.f;
     };
     float stat_next = load_stat(0);
     for (int it = 0; it < n_iter; ++it) {
       const int q0 = (i_start + it) * SUB;
       float* st = stat + (it & 1) * 128;
-      st[gt] = stat_next;
+      if (gt < 128) st[gt] = stat_next;
       stat_next = load_stat(it + 1);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&bars[B_STFULL], it & 1);
       tc_fence_after_sync();
-      uint32_t pk[32], dk[32];   // P^T and dS^T of this row, bf16 pairs
+      uint32_t pk[16], dk[16];   // P^T and dS^T of this thread's 32 queries, bf16 pairs
       if (lean) {
-        // 16-column sub-chunks, the next one in flight while this one is turned into P^T / dS^T; fp32 pairs
+        // two 16-column chunks; fp32 pairs
         const f32x2 sl2 = f2_rep(p.scale_log2), sc2 = f2_rep(p.scale);
-        uint32_t sa[16], da[16], sb[16], db[16];
-        tmem_ld_x16(t_row + COL_ST, sa);
-        tmem_ld_x16(t_row + COL_DPT, da);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t (&sv)[16] = (c & 1) ? sb : sa;
-          uint32_t (&dv)[16] = (c & 1) ? db : da;
+        for (int c2 = 0; c2 < 2; ++c2) {
+          const int c = 2 * hf + c2;
+          uint32_t sv[16], dv[16];
+          tmem_ld_x16(t_row + COL_ST + c * 16, sv);
+          tmem_ld_x16(t_row + COL_DPT + c * 16, dv);
           tmem_ld_wait();
-          if (c + 1 < 4) {
-            tmem_ld_x16(t_row + COL_ST + (c + 1) * 16, (c & 1) ? sa : sb);
-            tmem_ld_x16(t_row + COL_DPT + (c + 1) * 16, (c & 1) ? da : db);
-          }
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
             const float4 l4 = *reinterpret_cast<const float4*>(st + c * 16 + i);        // -lse (log2 domain)
@@ -297,15 +332,15 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_consta
                                                      f2_pack(d4.x, d4.y))), g0, g1);
             f2_unpack(f2_mul(f2_pack(e2, e3), f2_fma(f2_pack(__uint_as_float(dv[i + 2]), __uint_as_float(dv[i + 3])), sc2,
                                                      f2_pack(d4.z, d4.w))), g2, g3);
-            pk[c * 8 + (i >> 1)] = pack_bf16x2(e0, e1);
-            pk[c * 8 + (i >> 1) + 1] = pack_bf16x2(e2, e3);
-            dk[c * 8 + (i >> 1)] = pack_bf16x2(g0, g1);
-            dk[c * 8 + (i >> 1) + 1] = pack_bf16x2(g2, g3);
+            pk[c2 * 8 + (i >> 1)] = pack_bf16x2(e0, e1);
+            pk[c2 * 8 + (i >> 1) + 1] = pack_bf16x2(e2, e3);
+            dk[c2 * 8 + (i >> 1)] = pack_bf16x2(g0, g1);
+            dk[c2 * 8 + (i >> 1) + 1] = pack_bf16x2(g2, g3);
           }
         }
       } else {
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
+        {
+          const int cc = hf;
           uint32_t sv[32], dv[32];
           tmem_ld_x32(t_row + COL_ST + cc * 32, sv);
           tmem_ld_x32(t_row + COL_DPT + cc * 32, dv);
@@ -327,13 +362,15 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_consta
               d[k] = e[k] * fmaf(__uint_as_float(dv[i + k]), keep ? p.scale * dkey.scale : 0.f, st[64 + col]);
               e[k] = keep ? e[k] * dkey.scale : 0.f;
             }
-            pk[cc * 16 + (i >> 1)] = pack_bf16x2(e[0], e[1]);
-            dk[cc * 16 + (i >> 1)] = pack_bf16x2(d[0], d[1]);
+            pk[(i >> 1)] = pack_bf16x2(e[0], e[1]);
+            dk[(i >> 1)] = pack_bf16x2(d[0], d[1]);
           }
         }
       }
-      tmem_st_x32(t_row + COL_ST, pk);     // P^T  over the first 32 columns of the scores it came from
-      tmem_st_x32(t_row + COL_DPT, dk);    // dS^T over the first 32 columns of dP^T
+      // each half writes its 32 bf16 (16 columns) over the first columns of ITS OWN 32 fp32 scores, so the two threads
+      // of a row never touch each other's columns; the gradient MMAs address the two K halves separately
+      tmem_st_x16(t_row + COL_ST + 32 * hf, pk);     // P^T  of queries [32 hf, 32 hf + 32)
+      tmem_st_x16(t_row + COL_DPT + 32 * hf, dk);    // dS^T of the same queries
       tmem_st_wait();
       tc_fence_before_sync();
       mbar_arrive(&bars[B_PDSFULL]);
@@ -341,22 +378,19 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_consta
     mbar_wait(&bars[B_DONE], 0);
     tc_fence_after_sync();
     const bool valid = kvi < p.tk;
-    bf16* dstv = p.dv + (long long)b * p.dv_batch_stride + (long long)kvi * p.dv_row_stride + head * D;
-    bf16* dstk = p.dk + (long long)b * p.dk_batch_stride + (long long)kvi * p.dk_row_stride + head * D;
+    // the two halves share the epilogue: half 0 stores the dV row, half 1 the dK row
+    bf16* dst = (hf == 0 ? p.dv + (long long)b * p.dv_batch_stride + (long long)kvi * p.dv_row_stride
+                         : p.dk + (long long)b * p.dk_batch_stride + (long long)kvi * p.dk_row_stride) + head * D;
     if (n_iter == 0) {
       if (valid)
-        for (int i = 0; i < D; i += 8) {
-          *reinterpret_cast<uint4*>(dstv + i) = make_uint4(0, 0, 0, 0);
-          *reinterpret_cast<uint4*>(dstk + i) = make_uint4(0, 0, 0, 0);
-        }
+        for (int i = 0; i < D; i += 8) *reinterpret_cast<uint4*>(dst + i) = make_uint4(0, 0, 0, 0);
     } else {
-      store_out_row(dstv, t_row + COL_DV, valid, kvi < tk);
-      store_out_row(dstk, t_row + COL_DK, valid, kvi < tk);
+      store_out_row(dst, t_row + (hf == 0 ? COL_DV : COL_DK), valid, kvi < tk);
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (warp == 9) tmem_dealloc(tmem_base, 256);
 }
 
 namespace dq2 {
@@ -392,30 +426,30 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     mbar_init(&bars[B_Q], 1);
-    mbar_init(&bars[B_QT], 128);
+    mbar_init(&bars[B_QT], 256);
     for (int s = 0; s < NST; ++s) {
       mbar_init(&bars[B_KFULL + s], 1);
       mbar_init(&bars[B_KEMPTY + s], 1);
     }
     mbar_init(&bars[B_SFULL], 1);
-    mbar_init(&bars[B_DSFULL], 128);
+    mbar_init(&bars[B_DSFULL], 256);
     mbar_init(&bars[B_DONE], 1);
     fence_barrier_init();
   }
   __syncthreads();
-  if (warp == 0 && lane == 0) {   // first loads go out before the TMEM allocation (see the dK/dV kernel)
+  if (warp == 8 && lane == 0) {   // first loads go out before the TMEM allocation (see the dK/dV kernel)
     mbar_expect_tx(&bars[B_Q], 2 * TILE);
     tma_load_4d(smem + OFF_Q, &mq, &bars[B_Q], 0, q0, head, b);
     tma_load_4d(smem + OFF_DO, &mdo, &bars[B_Q], 0, q0, head, b);
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  if (warp == 9) tmem_alloc(tmem_slot, 256);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t sbase = smem_u32(smem);
 
-  if (warp == 0) {
+  if (warp == 8) {
     if (lane == 0) {
       for (int it = 0; it < n_iter; ++it) {
         const int st = it % NST;
@@ -426,7 +460,7 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
         tma_load_4d(smem + OFF_V + st * SUBTILE, &mv, &bars[B_KFULL + st], 0, it * SUB, head, b);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     // warp-uniform loop, one elected lane issues (see the dK/dV kernel)
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, SUB, false, false);
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, D, false, true);
@@ -445,7 +479,7 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
       mbar_wait(&bars[B_DSFULL], it & 1);
       tc_fence_after_sync();
       if (elect_one()) {
-        mma_tA_x_sub(tmem_base + COL_DQ, tmem_base + COL_S, sbase + OFF_K + st * SUBTILE, idesc_o, it > 0);
+        mma_tA2_x_sub(tmem_base + COL_DQ, tmem_base + COL_S, sbase + OFF_K + st * SUBTILE, idesc_o, it > 0);
         umma_commit(&bars[B_KEMPTY + st]);
       }
       __syncwarp();
@@ -454,6 +488,7 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
     __syncwarp();
   } else {
     const int q = warp & 3;
+    const int hf = warp >> 2;       // column half of the 64-wide sub-tile this thread owns: keys [32 hf, 32 hf + 32)
     const int r = q * 32 + lane;
     const int qi = q0 + r;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
@@ -486,11 +521,12 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
                bf16_hi(dd.y) * bf16_hi(oo.y) + bf16_lo(dd.z) * bf16_lo(oo.z) + bf16_hi(dd.z) * bf16_hi(oo.z) +
                bf16_lo(dd.w) * bf16_lo(oo.w) + bf16_hi(dd.w) * bf16_hi(oo.w);
       }
-      if (qi < p.tq) p.delta_out[((long long)b * p.heads + head) * p.tq + qi] = acc;
+      if (hf == 0 && qi < p.tq) p.delta_out[((long long)b * p.heads + head) * p.tq + qi] = acc;
       delta = acc * p.scale;
     }
-    smem_row_to_tmem(smem + OFF_Q, r, t_row + COL_QA);
-    smem_row_to_tmem(smem + OFF_DO, r, t_row + COL_DOA);
+    // the two threads of a row share the copy of the stationary operands into TMEM
+    if (hf == 0) smem_row_to_tmem(smem + OFF_Q, r, t_row + COL_QA);
+    else smem_row_to_tmem(smem + OFF_DO, r, t_row + COL_DOA);
     tmem_st_wait();
     tc_fence_before_sync();
     mbar_arrive(&bars[B_QT]);
@@ -498,21 +534,16 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
       const int k0 = it * SUB;
       mbar_wait(&bars[B_SFULL], it & 1);
       tc_fence_after_sync();
-      uint32_t dk[32];   // dS of this row, bf16 pairs
+      uint32_t dk[16];   // dS of this thread's 32 keys, bf16 pairs
       if (lean) {
         const f32x2 sl2 = f2_rep(p.scale_log2), sc2 = f2_rep(p.scale), nl2 = f2_rep(-lse2), nd2 = f2_rep(-delta);
-        uint32_t sa[16], da[16], sb[16], db[16];
-        tmem_ld_x16(t_row + COL_S, sa);
-        tmem_ld_x16(t_row + COL_DP, da);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t (&sv)[16] = (c & 1) ? sb : sa;
-          uint32_t (&dv)[16] = (c & 1) ? db : da;
+        for (int c2 = 0; c2 < 2; ++c2) {
+          const int c = 2 * hf + c2;
+          uint32_t sv[16], dv[16];
+          tmem_ld_x16(t_row + COL_S + c * 16, sv);
+          tmem_ld_x16(t_row + COL_DP + c * 16, dv);
           tmem_ld_wait();
-          if (c + 1 < 4) {
-            tmem_ld_x16(t_row + COL_S + (c + 1) * 16, (c & 1) ? sa : sb);
-            tmem_ld_x16(t_row + COL_DP + (c + 1) * 16, (c & 1) ? da : db);
-          }
 #pragma unroll
           for (int i = 0; i < 16; i += 2) {
             float e0, e1, g0, g1;
@@ -520,12 +551,12 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
             e0 = ex2_approx(e0), e1 = ex2_approx(e1);
             f2_unpack(f2_mul(f2_pack(e0, e1), f2_fma(f2_pack(__uint_as_float(dv[i]), __uint_as_float(dv[i + 1])), sc2, nd2)),
                       g0, g1);
-            dk[c * 8 + (i >> 1)] = pack_bf16x2(g0, g1);
+            dk[c2 * 8 + (i >> 1)] = pack_bf16x2(g0, g1);
           }
         }
       } else {
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
+        {
+          const int cc = hf;
           uint32_t sv[32], dv[32];
           tmem_ld_x32(t_row + COL_S + cc * 32, sv);
           tmem_ld_x32(t_row + COL_DP + cc * 32, dv);
@@ -545,23 +576,23 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
               d[k] = e * fmaf(__uint_as_float(dv[i + k]), keep ? p.scale * dkey.scale : 0.f, -delta);
               if (p.dbias && ok) atomicAdd(p.dbias + ((long long)head * p.tq + qi) * p.tk + kvi, d[k] * p.inv_scale);
             }
-            dk[cc * 16 + (i >> 1)] = pack_bf16x2(d[0], d[1]);
+            dk[(i >> 1)] = pack_bf16x2(d[0], d[1]);
           }
         }
       }
-      tmem_st_x32(t_row + COL_S, dk);   // dS over the first 32 columns of the scores
+      tmem_st_x16(t_row + COL_S + 32 * hf, dk);   // dS of keys [32 hf, 32 hf + 32) over the first columns of their own scores
       tmem_st_wait();
       tc_fence_before_sync();
       mbar_arrive(&bars[B_DSFULL]);
     }
     mbar_wait(&bars[B_DONE], 0);
     tc_fence_after_sync();
-    bf16* dst = p.dq + (long long)b * p.dq_batch_stride + (long long)qi * p.dq_row_stride + head * D;
-    store_out_row(dst, t_row + COL_DQ, qi < p.tq);
+    bf16* dst = p.dq + (long long)b * p.dq_batch_stride + (long long)qi * p.dq_row_stride + head * D + 32 * hf;
+    store_out_half(dst, t_row + COL_DQ + 32 * hf, qi < p.tq);
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (warp == 9) tmem_dealloc(tmem_base, 256);
 }
 
 }  // namespace attn
