@@ -29,6 +29,12 @@ __device__ __forceinline__ long long offset(const SmxAdafactorTensor& t, int b, 
   return t.factored ? ((long long)b * t.rows + r) * t.cols + c : r * TILE_C + c;
 }
 
+// Fast path of a tile: factored tensor, cols % 4 == 0 -> every lane owns two float4 per row (columns 4 lane + 128 j),
+// a warp reads 512 contiguous bytes per request, and the 16 loads of a thread (8 rows x 2) are all in flight before the
+// first use.  (The first version issued 64 scalar loads per thread, each behind a 64-bit index computation, and the
+// update kernel interleaved them with stores: ~1 TB/s, profiles/r01z_adafactor.txt.)
+__device__ __forceinline__ bool vec_tile(const SmxAdafactorTensor& t) { return t.factored && (t.cols & 3) == 0; }
+
 __global__ void __launch_bounds__(256) stats_kernel(const SmxAdafactorTensor* __restrict__ tensors,
                                                     const SmxAdafactorTile* __restrict__ tiles) {
   __shared__ float red[8][TILE_C + 1];
@@ -37,26 +43,62 @@ __global__ void __launch_bounds__(256) stats_kernel(const SmxAdafactorTensor* __
   if (!t.factored) return;   // vectors need no factored statistics (their tiles are skipped uniformly)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float colp[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (vec_tile(t)) {
+    const float* __restrict__ gp = t.g + ((long long)tl.b * t.rows) * t.cols;
+    float4 v[8][2];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const long long r = tl.r0 + warp + 8 * k;
-    float rs = 0.f;
-    if (r < t.rows) {
+    for (int k = 0; k < 8; ++k) {
+      const long long r = tl.r0 + warp + 8 * k;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const long long c = tl.c0 + lane + 32 * j;
-        if (c < t.cols) {
-          const float g = t.g[offset(t, tl.b, r, c)];
-          rs = fmaf(g, g, rs);
-          colp[j] = fmaf(g, g, colp[j]);
-        }
+      for (int j = 0; j < 2; ++j) {
+        const long long c = tl.c0 + 4 * lane + 128 * j;
+        v[k][j] = (r < t.rows && c < t.cols) ? __ldg(reinterpret_cast<const float4*>(gp + r * t.cols + c))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    rs = warp_sum(rs);
-    if (lane == 0 && r < t.rows) atomicAdd(t.row_acc + (long long)tl.b * t.rows + r, rs);
-  }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) red[warp][lane + 32 * j] = colp[j];
+    for (int k = 0; k < 8; ++k) {
+      const long long r = tl.r0 + warp + 8 * k;
+      float rs = 0.f;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float4 g = v[k][j];
+        colp[4 * j + 0] = fmaf(g.x, g.x, colp[4 * j + 0]);
+        colp[4 * j + 1] = fmaf(g.y, g.y, colp[4 * j + 1]);
+        colp[4 * j + 2] = fmaf(g.z, g.z, colp[4 * j + 2]);
+        colp[4 * j + 3] = fmaf(g.w, g.w, colp[4 * j + 3]);
+        rs += g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w;
+      }
+      rs = warp_sum(rs);
+      if (lane == 0 && r < t.rows) atomicAdd(t.row_acc + (long long)tl.b * t.rows + r, rs);
+    }
+    // column c0 + 4 lane + 128 j + e lives in colp[4 j + e]
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) red[warp][4 * lane + 128 * j + e] = colp[4 * j + e];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const long long r = tl.r0 + warp + 8 * k;
+      float rs = 0.f;
+      if (r < t.rows) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const long long c = tl.c0 + lane + 32 * j;
+          if (c < t.cols) {
+            const float g = t.g[offset(t, tl.b, r, c)];
+            rs = fmaf(g, g, rs);
+            colp[j] = fmaf(g, g, colp[j]);
+          }
+        }
+      }
+      rs = warp_sum(rs);
+      if (lane == 0 && r < t.rows) atomicAdd(t.row_acc + (long long)tl.b * t.rows + r, rs);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[warp][lane + 32 * j] = colp[j];
+  }
   __syncthreads();
   float cs = 0.f;
 #pragma unroll
@@ -106,7 +148,7 @@ __global__ void __launch_bounds__(256) update_kernel(const SmxAdafactorTensor* _
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const long long c = tl.c0 + lane + 32 * j;
-    cf[j] = (t.factored && c < t.cols) ? 1.0f / sqrtf(t.col[(long long)tl.b * t.cols + c]) : 0.f;
+    cf[j] = (t.factored && !vec_tile(t) && c < t.cols) ? 1.0f / sqrtf(t.col[(long long)tl.b * t.cols + c]) : 0.f;
   }
   float scale = 0.f, decay = 1.f;
   if (APPLY) {
@@ -117,6 +159,55 @@ __global__ void __launch_bounds__(256) update_kernel(const SmxAdafactorTensor* _
   const float inv_rmean = t.factored ? 1.0f / t.rmean[tl.b] : 0.f;
   const float om = 1.0f - h.beta2t;
   float ss = 0.f;
+  if (vec_tile(t)) {
+    // all loads of the tile first (g, and p when applying), then the arithmetic, then the stores
+    const float* __restrict__ gp = t.g + ((long long)tl.b * t.rows) * t.cols;
+    float* __restrict__ pp = t.p + ((long long)tl.b * t.rows) * t.cols;
+    float4 cf4[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const long long c = tl.c0 + 4 * lane + 128 * j;
+      if (c < t.cols) {
+        const float4 cv = *reinterpret_cast<const float4*>(t.col + (long long)tl.b * t.cols + c);
+        cf4[j] = make_float4(rsqrtf(cv.x), rsqrtf(cv.y), rsqrtf(cv.z), rsqrtf(cv.w));
+      } else {
+        cf4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    float4 gv[8][2], pv[8][2];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const long long r = tl.r0 + warp + 8 * k;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const long long c = tl.c0 + 4 * lane + 128 * j;
+        const bool ok = r < t.rows && c < t.cols;
+        gv[k][j] = ok ? __ldg(reinterpret_cast<const float4*>(gp + r * t.cols + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (APPLY) pv[k][j] = ok ? *reinterpret_cast<const float4*>(pp + r * t.cols + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const long long r = tl.r0 + warp + 8 * k;
+      const float rf = r < t.rows ? rsqrtf(t.row[(long long)tl.b * t.rows + r] * inv_rmean) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const long long c = tl.c0 + 4 * lane + 128 * j;
+        float4 u = gv[k][j];
+        u.x *= rf * cf4[j].x, u.y *= rf * cf4[j].y, u.z *= rf * cf4[j].z, u.w *= rf * cf4[j].w;
+        if (APPLY) {
+          if (r < t.rows && c < t.cols) {
+            float4 q = pv[k][j];
+            q.x = q.x * decay - scale * u.x, q.y = q.y * decay - scale * u.y;
+            q.z = q.z * decay - scale * u.z, q.w = q.w * decay - scale * u.w;
+            *reinterpret_cast<float4*>(pp + r * t.cols + c) = q;
+          }
+        } else {
+          ss += u.x * u.x + u.y * u.y + u.z * u.z + u.w * u.w;
+        }
+      }
+    }
+  } else
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const long long r = tl.r0 + warp + 8 * k;

@@ -117,3 +117,44 @@ class FreezingPolicy:
     def on_save(self, model):
         for _, p in model.named_parameters():
             p.requires_grad = True
+
+
+class TrainStep:
+    """The optimizer-step policy of the reference recipe (ref:train.py:291-311 -> HF ``TrainingArguments``):
+    ``gradient_accumulation_steps`` micro-batches per update (loss scaled by 1 / steps, as the Trainer does), global
+    gradient-norm clipping (``max_grad_norm``, Trainer default 1.0) and one optimizer step; under data parallelism the
+    micro-steps before the last run inside ``reducer.no_sync()`` so that ONE bucketed all-reduce carries the accumulated
+    gradients.  ``model(**batch)`` must return a mapping with ``loss`` (every SpeechMix class does)."""
+
+    def __init__(self, model, optimizer, grad_accum=1, max_grad_norm=1.0, reducer=None):
+        self.model, self.opt, self.reducer = model, optimizer, reducer
+        self.grad_accum, self.max_grad_norm = max(int(grad_accum), 1), max_grad_norm
+        self.params = [p for g in optimizer.param_groups for p in g["params"]]
+
+    def __call__(self, micro_batches):
+        """micro_batches: sequence of ``grad_accum`` keyword dicts; returns (mean loss, gradient norm before clipping)."""
+        assert len(micro_batches) == self.grad_accum, "one update = grad_accum micro-batches"
+        self.opt.zero_grad(set_to_none=True)
+        total = 0.0
+        for i, batch in enumerate(micro_batches):
+            last = i + 1 == self.grad_accum
+            ctx = self.reducer.no_sync() if (self.reducer is not None and not last) else _NullCtx()
+            with ctx:
+                loss = self.model(**batch)["loss"] / self.grad_accum
+                loss.backward()
+            total = total + loss.detach()
+        if self.reducer is not None:
+            self.reducer.finish()
+        norm = None
+        if self.max_grad_norm is not None and self.max_grad_norm > 0:
+            norm = torch.nn.utils.clip_grad_norm_([p for p in self.params if p.grad is not None], self.max_grad_norm)
+        self.opt.step()
+        return total, norm
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False

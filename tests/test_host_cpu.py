@@ -252,3 +252,31 @@ def test_checkpoint_directories_and_legacy_keys_load(tmp_path):
     import pytest
     with pytest.raises(FileNotFoundError):
         SpeechMixEED("voidful/definitely-not-cached-wav2vec2", str(tx_dir))
+
+
+def test_train_step_accumulates_and_clips_like_the_trainer():
+    """training.TrainStep (ref:train.py:291-311: gradient_accumulation_steps + the Trainer's max_grad_norm): two
+    micro-batches of 2 must give the update of one batch of 4, and the update is clipped to the global norm."""
+    import torch
+    from speechmix_b200.training import TrainStep
+
+    class Toy(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(0)
+            self.lin = torch.nn.Linear(8, 1)
+
+        def forward(self, x=None, y=None):
+            return {"loss": ((self.lin(x)[:, 0] - y) ** 2).mean()}
+
+    g = torch.Generator().manual_seed(1)
+    x, y = torch.randn(4, 8, generator=g) * 5, torch.randn(4, generator=g) * 5
+    a, b = Toy(), Toy()
+    sa = TrainStep(a, torch.optim.SGD(a.parameters(), lr=0.1), grad_accum=2, max_grad_norm=0.5)
+    sb = TrainStep(b, torch.optim.SGD(b.parameters(), lr=0.1), grad_accum=1, max_grad_norm=0.5)
+    la, na = sa([dict(x=x[:2], y=y[:2]), dict(x=x[2:], y=y[2:])])
+    lb, nb = sb([dict(x=x, y=y)])
+    assert abs(float(la) - float(lb)) < 1e-5 and abs(float(na) - float(nb)) < 1e-4 and float(na) > 0.5
+    assert torch.allclose(a.lin.weight, b.lin.weight, atol=1e-6)
+    w0 = Toy().lin.weight
+    assert abs(float((a.lin.weight - w0).norm() ** 2 + (a.lin.bias - Toy().lin.bias).norm() ** 2) ** 0.5 - 0.1 * 0.5) < 1e-4

@@ -105,16 +105,32 @@ def test_cfg1_full_size_forward(cuda_device):
 
 
 def test_greedy_generate_matches_reference_loop(cuda_device):
-    """ids of the reference's own full-recompute greedy loop (tests/golden/mini_eed_share.json); bf16 may flip
-    near-ties of a random-init model, so require the first generated tokens to match and report the rest."""
+    """ids of the reference's own full-recompute greedy loop (tests/golden/mini_eed_share.json) against the bf16 decode.
+    Rule (bit-exact ids are asserted for the fp32 verification mode below): a bf16 greedy sequence may leave the
+    reference sequence ONLY at a near-tie of the reference's own logits -- at the first position where a sample forks,
+    the fp32 oracle, fed the common prefix, must score our token within the logits tolerance (2e-2 of max |logit|) of its
+    own choice.  After a fork the two decodes condition on different prefixes and are not comparable."""
     fx = load_fixture("mini_eed_share")
     ora, x, _ = build_oracle(fx)
     mine = _mine_from(ora, fx, cuda_device).eval()
     ids = mine.generate(x.to(cuda_device), max_length=8, eos_token_id=-1).cpu()
     ref = torch.tensor(fx["greedy_ids"])
     assert ids.shape == ref.shape
-    assert torch.equal(ids[:, :2], ref[:, :2])
-    assert (ids == ref).float().mean() > 0.7
+    assert torch.equal(ids[:, 0], ref[:, 0])          # decoder_start_token_id
+    forks = 0
+    ora.eval()
+    with torch.no_grad():
+        for b in range(ids.shape[0]):
+            diff = (ids[b] != ref[b]).nonzero()
+            if diff.numel() == 0:
+                continue
+            forks += 1
+            t = int(diff[0])                           # ids[b, :t] == ref[b, :t]
+            out = ora(x[b:b + 1], decoder_input_ids=ref[b:b + 1, :t], keep_full_logits=True)
+            logit = out["full_logits"][0, -1]
+            gap = float(logit[ref[b, t]] - logit[ids[b, t]])
+            assert 0.0 <= gap < 2e-2 * float(logit.abs().max()), (b, t, gap, float(logit.abs().max()))
+    assert forks <= ids.shape[0] // 2 + 1, forks       # and forks stay the exception
 
 
 def test_frozen_parameters_get_no_gradient(cuda_device):
