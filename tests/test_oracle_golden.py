@@ -9,7 +9,10 @@ import torch
 from tests._cases import build_oracle, check_sample, load_fixture
 
 MINI = ["mini_eed_ds2", "mini_eed_ds8_ws", "mini_eed_share", "mini_large_mbart", "mini_t5", "mini_specaug", "mini_prompt",
-        "mini_fixed", "mini_fixed_params", "mini_t5_share"]
+        "mini_fixed", "mini_fixed_params", "mini_t5_share",
+        # HFSpeechMixAdapter / HFSpeechMixSelf: the reference's own hook lambda and cal_loss body, run under the documented
+        # transformers-5.x calling-convention shims of make_golden.compat_shims (no reference code edited)
+        "mini_adapter", "mini_adapter_large", "mini_self", "mini_self_t5"]
 
 
 @pytest.mark.parametrize("name", MINI)
@@ -24,12 +27,17 @@ def test_oracle_matches_reference_golden(name):
     kw = {}
     if "prompt_ids" in fx:        # ids as the reference's own tokenizer produced them from fx["prompt"]
         kw["decoder_text_prompt_ids"] = torch.tensor(fx["prompt_ids"])
+    if "text_input_ids" in fx:    # SpeechMixSelf: the frozen text teacher's input
+        kw["text_input_ids"] = torch.tensor(fx["text_input_ids"])
     if "np_seed" in fx:           # SpecAugment spans come from numpy's global RNG (transformers' _compute_mask_indices)
         import numpy as np
         np.random.seed(fx["np_seed"])
     out = model(x, labels=labels, keep_full_logits=True, **kw)
     assert abs(float(out["loss"]) - fx["loss"]) < 2e-5
     assert out["logits"].tolist() == fx["argmax_ids"]
+    for k in ("ce_loss", "kld_loss", "mse_loss"):
+        if k in fx:
+            assert abs(float(out[k]) - fx[k]) < 2e-5 * max(1.0, abs(fx[k])), k
     check_sample(out["full_logits"], fx["logits"], atol=2e-4)
     check_sample(out["speech_last_hidden_state"], fx["speech_last_hidden_state"], atol=2e-4)
     check_sample(out["encoder_last_hidden_state"], fx["encoder_last_hidden_state"], atol=2e-4)
