@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SMX_ABI_VERSION 2
+#define SMX_ABI_VERSION 3
 
 const char* smx_last_error(void);
 int smx_abi_version(void);
@@ -169,9 +169,12 @@ typedef struct {
 typedef struct {
   int32_t tensor, b;
 } SmxAdafactorSlice;
+/* small_slices: factored slices of <= 16384 elements (rows + cols <= 4096) that are NOT in `tiles` / `slices` and take
+ * the block-per-slice kernels; small_smem_floats = max over them of rows*cols + rows + cols. */
 int smx_adafactor_step(const SmxAdafactorTensor* tensors, int32_t n_tensors, const SmxAdafactorTile* tiles,
-                       int32_t n_tiles, const SmxAdafactorSlice* slices, int32_t n_slices, void* scratch,
-                       int64_t scratch_bytes, float beta2t, float eps1, float lr, float clip_threshold,
+                       int32_t n_tiles, const SmxAdafactorSlice* slices, int32_t n_slices,
+                       const SmxAdafactorSlice* small_slices, int32_t n_small, int32_t small_smem_floats,
+                       void* scratch, int64_t scratch_bytes, float beta2t, float eps1, float lr, float clip_threshold,
                        float weight_decay, void* stream);
 
 int smx_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);

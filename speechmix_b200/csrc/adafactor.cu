@@ -6,6 +6,12 @@
 //   2 finalize  per (tensor, leading index): EMA of the factored second moments, mean of the row moments
 //   3 sumsq     per tile: u = g * rsqrt(row / mean(row)) * rsqrt(col)  (or g * rsqrt(v) for vectors), sum u^2
 //   4 apply     per tile: p <- p (1 - wd lr) - lr u / max(1, rms(u) / clip)
+// Factored slices of at most 16384 elements (the [512, 512, 3] / [512, 512, 2] / [512, 1, 10] convolution weights of the
+// feature encoder and the [768, 48, 128] positional convolution: one leading index = one tiny [rows][cols] matrix) do
+// not go through the 64 x 256 tile table -- a [512][3] slice would be eight tiles of 192 useful elements each, and
+// those near-empty tiles were 64 % of all tiles of the wav2vec2-base + bart-base model.  They take two block-per-slice
+// kernels instead: `small_moments` (slice in shared memory: row / column sums, both EMAs, mean of the row moments and
+// the slice's share of sum(u^2) -- steps 1-3 with ONE read of g and no atomics but the last) and `small_apply`.
 // HBM-bound: g is read three times and p once read / once written (20 bytes per parameter); a tensor with
 // len(shape) >= 2 is factored over its last two dims exactly like the reference (leading dims = independent slices).
 #include "../../include/speechmix_sm100.h"
@@ -37,6 +43,8 @@ __device__ __forceinline__ bool vec_tile(const SmxAdafactorTensor& t) { return t
 
 __global__ void __launch_bounds__(256) stats_kernel(const SmxAdafactorTensor* __restrict__ tensors,
                                                     const SmxAdafactorTile* __restrict__ tiles) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8][TILE_C + 1];
   const SmxAdafactorTile tl = tiles[blockIdx.x];
   const SmxAdafactorTensor t = tensors[tl.tensor];
@@ -110,6 +118,8 @@ __global__ void __launch_bounds__(256) stats_kernel(const SmxAdafactorTensor* __
 // one block per (factored tensor, leading index): exp_avg_sq_row / exp_avg_sq_col EMAs and the mean of the row moments
 __global__ void __launch_bounds__(256) finalize_kernel(const SmxAdafactorTensor* __restrict__ tensors,
                                                        const SmxAdafactorSlice* __restrict__ slices, Hyper h) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8];
   const SmxAdafactorSlice s = slices[blockIdx.x];
   const SmxAdafactorTensor t = tensors[s.tensor];
@@ -140,6 +150,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(const SmxAdafactorTensor*
 template <bool APPLY>
 __global__ void __launch_bounds__(256) update_kernel(const SmxAdafactorTensor* __restrict__ tensors,
                                                      const SmxAdafactorTile* __restrict__ tiles, Hyper h) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8];
   const SmxAdafactorTile tl = tiles[blockIdx.x];
   const SmxAdafactorTensor t = tensors[tl.tensor];
@@ -247,30 +259,162 @@ __global__ void __launch_bounds__(256) update_kernel(const SmxAdafactorTensor* _
 }
 
 
+// ---- block-per-slice path for small factored slices (rows * cols <= SMALL_ELEMS, rows + cols <= SMALL_RC)
+constexpr int SMALL_ELEMS = 16384, SMALL_RC = 4096;
+
+__global__ void __launch_bounds__(256) small_moments_kernel(const SmxAdafactorTensor* __restrict__ tensors,
+                                                            const SmxAdafactorSlice* __restrict__ slices, Hyper h) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ float sm[];                 // g [rows * cols] | rowv [rows] | colv [cols] | red [8]
+  const SmxAdafactorSlice s = slices[blockIdx.x];
+  const SmxAdafactorTensor t = tensors[s.tensor];
+  const int rows = (int)t.rows, cols = (int)t.cols, n = rows * cols;
+  float* gs = sm;
+  float* rowv = sm + n;
+  float* colv = rowv + rows;
+  float* red = colv + cols;
+  const float* __restrict__ g = t.g + (long long)s.b * n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(g) & 15) == 0)) {
+    for (int i = threadIdx.x * 4; i < n; i += 1024) *reinterpret_cast<float4*>(gs + i) = __ldg(reinterpret_cast<const float4*>(g + i));
+  } else {
+    for (int i = threadIdx.x; i < n; i += 256) gs[i] = __ldg(g + i);
+  }
+  __syncthreads();
+  const float om = 1.0f - h.beta2t, inv_c = 1.0f / (float)cols, inv_r = 1.0f / (float)rows;
+  float* row = t.row + (long long)s.b * rows;
+  float* col = t.col + (long long)s.b * cols;
+  // row moments: narrow rows (cols <= 8) one thread per row, otherwise one warp per row
+  float rsum = 0.f;
+  if (cols <= 8) {
+    for (int r = threadIdx.x; r < rows; r += 256) {
+      float a = 0.f;
+      for (int c = 0; c < cols; ++c) a = fmaf(gs[r * cols + c], gs[r * cols + c], a);
+      const float v = h.beta2t * row[r] + om * (a * inv_c + h.eps1);
+      row[r] = v, rowv[r] = v, rsum += v;
+    }
+  } else {
+    for (int r = warp; r < rows; r += 8) {
+      float a = 0.f;
+      for (int c = lane; c < cols; c += 32) a = fmaf(gs[r * cols + c], gs[r * cols + c], a);
+      a = warp_sum(a);
+      if (lane == 0) {
+        const float v = h.beta2t * row[r] + om * (a * inv_c + h.eps1);
+        row[r] = v, rowv[r] = v, rsum += v;
+      }
+    }
+  }
+  // column moments: wide slices one thread per column; narrow ones one warp per column
+  if (cols >= 32) {
+    for (int c = threadIdx.x; c < cols; c += 256) {
+      float a = 0.f;
+      for (int r = 0; r < rows; ++r) a = fmaf(gs[r * cols + c], gs[r * cols + c], a);
+      const float v = h.beta2t * col[c] + om * (a * inv_r + h.eps1);
+      col[c] = v, colv[c] = v;
+    }
+  } else {
+    for (int c = warp; c < cols; c += 8) {
+      float a = 0.f;
+      for (int r = lane; r < rows; r += 32) a = fmaf(gs[r * cols + c], gs[r * cols + c], a);
+      a = warp_sum(a);
+      if (lane == 0) {
+        const float v = h.beta2t * col[c] + om * (a * inv_r + h.eps1);
+        col[c] = v, colv[c] = v;
+      }
+    }
+  }
+  rsum = warp_sum(rsum);
+  if (lane == 0) red[warp] = rsum;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += red[w];
+  const float rmean = tot * inv_r;
+  if (threadIdx.x == 0) t.rmean[s.b] = rmean;
+  __syncthreads();                                // red is reused below
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int r = i / cols, c = i - r * cols;
+    const float u = gs[i] * rsqrtf(rowv[r] / rmean) * rsqrtf(colv[c]);
+    ss = fmaf(u, u, ss);
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) red[warp] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f;
+    for (int w = 0; w < 8; ++w) a += red[w];
+    atomicAdd(t.sumsq, a);
+  }
+}
+
+__global__ void __launch_bounds__(256) small_apply_kernel(const SmxAdafactorTensor* __restrict__ tensors,
+                                                          const SmxAdafactorSlice* __restrict__ slices, Hyper h) {
+  pdl_trigger();
+  pdl_wait();
+  const SmxAdafactorSlice s = slices[blockIdx.x];
+  const SmxAdafactorTensor t = tensors[s.tensor];
+  const int rows = (int)t.rows, cols = (int)t.cols, n = rows * cols;
+  const float rms = sqrtf(*t.sumsq / (float)t.numel);
+  const float scale = h.lr / fmaxf(1.0f, rms / h.clip), decay = 1.0f - h.weight_decay * h.lr;
+  const float inv_rmean = 1.0f / t.rmean[s.b];
+  const float* __restrict__ g = t.g + (long long)s.b * n;
+  float* __restrict__ pp = t.p + (long long)s.b * n;
+  const float* __restrict__ row = t.row + (long long)s.b * rows;
+  const float* __restrict__ col = t.col + (long long)s.b * cols;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int r = i / cols, c = i - r * cols;
+    const float u = __ldg(g + i) * rsqrtf(row[r] * inv_rmean) * rsqrtf(col[c]);
+    pp[i] = pp[i] * decay - scale * u;
+  }
+}
+
 }  // namespace adafactor
 }  // namespace smx
 
 extern "C" int smx_adafactor_step(const SmxAdafactorTensor* tensors, int32_t n_tensors, const SmxAdafactorTile* tiles,
-                                  int32_t n_tiles, const SmxAdafactorSlice* slices, int32_t n_slices, void* scratch,
-                                  int64_t scratch_bytes, float beta2t, float eps1, float lr, float clip_threshold,
-                                  float weight_decay, void* stream) {
+                                  int32_t n_tiles, const SmxAdafactorSlice* slices, int32_t n_slices,
+                                  const SmxAdafactorSlice* small_slices, int32_t n_small, int32_t small_smem_floats,
+                                  void* scratch, int64_t scratch_bytes, float beta2t, float eps1, float lr,
+                                  float clip_threshold, float weight_decay, void* stream) {
   using namespace smx;
   using namespace smx::adafactor;
-  SMX_REQUIRE(tensors && tiles && (n_slices == 0 || slices) && scratch, "adafactor: null table");
-  if (n_tensors <= 0 || n_tiles <= 0) return 0;
+  SMX_REQUIRE(tensors && (n_tiles == 0 || tiles) && (n_slices == 0 || slices) && (n_small == 0 || small_slices) && scratch,
+              "adafactor: null table");
+  if (n_tensors <= 0 || (n_tiles <= 0 && n_small <= 0)) return 0;
+  const size_t small_smem = ((size_t)small_smem_floats + 8) * sizeof(float);
+  SMX_REQUIRE(n_small == 0 || (small_smem_floats > 0 && small_smem_floats <= SMALL_ELEMS + SMALL_RC),
+              "adafactor: small-slice shared memory %d floats out of range", small_smem_floats);
   cudaStream_t st = (cudaStream_t)stream;
   // row_acc / col_acc / sumsq of every tensor live in one scratch block: one memset per step
   SMX_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (size_t)scratch_bytes, st));
   Hyper h{beta2t, eps1, lr, clip_threshold, weight_decay};
-  stats_kernel<<<n_tiles, 256, 0, st>>>(tensors, tiles);
-  SMX_CHECK_CUDA(cudaGetLastError());
-  if (n_slices > 0) {
-    finalize_kernel<<<n_slices, 256, 0, st>>>(tensors, slices, h);
+  if (n_small > 0) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      SMX_CHECK_CUDA(cudaFuncSetAttribute(small_moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (SMALL_ELEMS + SMALL_RC + 8) * (int)sizeof(float)));
+      attr_set = true;
+    }
+    launch_pdl(small_moments_kernel, dim3(n_small), dim3(256), small_smem, st, tensors, small_slices, h);
     SMX_CHECK_CUDA(cudaGetLastError());
   }
-  update_kernel<false><<<n_tiles, 256, 0, st>>>(tensors, tiles, h);
-  SMX_CHECK_CUDA(cudaGetLastError());
-  update_kernel<true><<<n_tiles, 256, 0, st>>>(tensors, tiles, h);
-  SMX_CHECK_CUDA(cudaGetLastError());
+  if (n_tiles > 0) {
+    launch_pdl(stats_kernel, dim3(n_tiles), dim3(256), 0, st, tensors, tiles);
+    SMX_CHECK_CUDA(cudaGetLastError());
+    if (n_slices > 0) {
+      launch_pdl(finalize_kernel, dim3(n_slices), dim3(256), 0, st, tensors, slices, h);
+      SMX_CHECK_CUDA(cudaGetLastError());
+    }
+    launch_pdl(update_kernel<false>, dim3(n_tiles), dim3(256), 0, st, tensors, tiles, h);
+    SMX_CHECK_CUDA(cudaGetLastError());
+    launch_pdl(update_kernel<true>, dim3(n_tiles), dim3(256), 0, st, tensors, tiles, h);
+    SMX_CHECK_CUDA(cudaGetLastError());
+  }
+  if (n_small > 0) {
+    launch_pdl(small_apply_kernel, dim3(n_small), dim3(256), 0, st, tensors, small_slices, h);
+    SMX_CHECK_CUDA(cudaGetLastError());
+  }
   return 0;
 }

@@ -191,6 +191,8 @@ __global__ void __launch_bounds__(BWD2_THREADS, 2)
 attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
                      const __grid_constant__ CUtensorMap mv, const __grid_constant__ CUtensorMap mdo,
                      const BwdParams p) {
+  pdl_trigger();
+  pdl_wait();
   using namespace kv2;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -406,6 +408,8 @@ __global__ void __launch_bounds__(BWD2_THREADS, 2)
 attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
                     const __grid_constant__ CUtensorMap mv, const __grid_constant__ CUtensorMap mdo,
                     const BwdParams p) {
+  pdl_trigger();
+  pdl_wait();
   using namespace dq2;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -644,9 +648,9 @@ extern "C" int smx_attn_bwd(const SmxAttn* a, void* stream) {
   if (make_head_map_rows(&sk, a->k, a->tk, a->heads, a->batch, a->k_row_stride, a->k_batch_stride, SUB)) return -1;
   if (make_head_map_rows(&sv, a->v, a->tk, a->heads, a->batch, a->v_row_stride, a->v_batch_stride, SUB)) return -1;
   // the dQ kernel also produces delta = rowsum(dO * O) (its dO tile is already in shared memory), so it runs first
-  attn_bwd_dq2_kernel<<<gq, BWD2_THREADS, dq2::SMEM_BYTES, st>>>(mq, sk, sv, mdo, p);
+  launch_pdl(attn_bwd_dq2_kernel, dim3(gq), dim3(BWD2_THREADS), dq2::SMEM_BYTES, st, mq, sk, sv, mdo, p);
   SMX_CHECK_CUDA(cudaGetLastError());
-  attn_bwd_dkv2_kernel<<<gkv, BWD2_THREADS, kv2::SMEM_BYTES, st>>>(sq, mk, mv, sdo, p);
+  launch_pdl(attn_bwd_dkv2_kernel, dim3(gkv), dim3(BWD2_THREADS), kv2::SMEM_BYTES, st, sq, mk, mv, sdo, p);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -65,6 +65,8 @@ __device__ __forceinline__ int num_kv_tiles(const FwdParams& p, int q0, int tk) 
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tq_map, const __grid_constant__ CUtensorMap tk_map,
                 const __grid_constant__ CUtensorMap tv_map, const FwdParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
@@ -473,7 +475,7 @@ extern "C" int smx_attn_fwd(const SmxAttn* a, void* stream) {
     attr_set = true;
   }
   dim3 grid((a->tq + BQ - 1) / BQ, a->heads, a->batch);
-  attn_fwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(mq, mk, mv, p);
+  launch_pdl(attn_fwd_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, (cudaStream_t)stream, mq, mk, mv, p);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -111,6 +111,8 @@ template <int POLY_EVERY, bool DROP>   // every POLY_EVERY-th pair of exponentia
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tq_map, const __grid_constant__ CUtensorMap tk_map,
                  const __grid_constant__ CUtensorMap tv_map, const Params p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
@@ -422,11 +424,11 @@ int launch_fwd2(const SmxAttn* a, cudaStream_t stream) {
   }
   dim3 grid((a->tq + BQ - 1) / BQ, a->heads, a->batch);
   if (drop)
-    attn_fwd2_kernel<0, true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(mq, mk, mv, p);
+    launch_pdl(attn_fwd2_kernel<0, true>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, mq, mk, mv, p);
   else if (poly == 0)
-    attn_fwd2_kernel<0, false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(mq, mk, mv, p);
+    launch_pdl(attn_fwd2_kernel<0, false>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, mq, mk, mv, p);
   else
-    attn_fwd2_kernel<4, false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(mq, mk, mv, p);
+    launch_pdl(attn_fwd2_kernel<4, false>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, mq, mk, mv, p);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -24,6 +24,8 @@ constexpr int NPART = K + K * (K + 1) / 2;  // what one block accumulates: windo
 // ------------------------------------------------------------------ window moments
 __global__ void __launch_bounds__(256) moments_kernel(const float* __restrict__ audio, float* __restrict__ partial,
                                                       long long n_samples, long long t_out) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const float* x = audio + (long long)b * n_samples;
   float m[K], r[K * (K + 1) / 2];
@@ -66,6 +68,8 @@ __global__ void __launch_bounds__(256) moments_kernel(const float* __restrict__ 
 
 // moments[b] = sum over the blocks' partials in a fixed order; expands the upper triangle to the full matrix
 __global__ void moments_reduce_kernel(const float* __restrict__ partial, float* __restrict__ moments, int blocks) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x;
   if (threadIdx.x >= NPART) return;
   float v = 0.f;
@@ -87,6 +91,8 @@ __global__ void moments_reduce_kernel(const float* __restrict__ partial, float* 
 
 __global__ void stats_kernel(const float* __restrict__ w, const float* __restrict__ moments, float* __restrict__ stats,
                              int batch, int channels, long long t_out, float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= batch * channels) return;
   const int b = i / channels, c = i % channels;
@@ -116,6 +122,8 @@ __global__ void __launch_bounds__(256, 2) fwd_kernel(const float* __restrict__ a
                                                   const float* __restrict__ stats, bf16* __restrict__ y,
                                                   bf16* __restrict__ gprime, long long n_samples, long long t_out,
                                                   int channels) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float xs[FWD_FR * S + K];
   const int b = blockIdx.y;
   const long long t0 = (long long)blockIdx.x * FWD_FR;
@@ -173,6 +181,8 @@ constexpr int BWD_FR = 1024;
 __global__ void __launch_bounds__(256, 2) bwd_kernel(const float* __restrict__ audio, const bf16* __restrict__ dy,
                                                   const bf16* __restrict__ gprime, float* __restrict__ partial,
                                                   long long n_samples, long long t_out, int channels) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float xs[BWD_FR * S + K];
   const int b = blockIdx.y;
   const long long t0 = (long long)blockIdx.x * BWD_FR;
@@ -248,6 +258,8 @@ __global__ void bwd_finalize_kernel(const float* __restrict__ w, const float* __
                                     const float* __restrict__ partial, float* __restrict__ dw,
                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int batch, int channels,
                                     long long t_out) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= channels * (K + 2)) return;
   const int c = i / (K + 2), j = i % (K + 2);
@@ -297,6 +309,8 @@ __global__ void __launch_bounds__(256) ln_variant_kernel(const float* __restrict
                                                          float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                          long long n_samples, long long t_out, long long total_frames,
                                                          int channels, float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int cpl = channels / 32;  // channels per lane, contiguous: [lane*cpl, lane*cpl + cpl)
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -397,6 +411,8 @@ __global__ void __launch_bounds__(256) ln_variant_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ audio, const bf16* __restrict__ dconv,
                                                     float* __restrict__ dw, float* __restrict__ dbias,
                                                     long long n_samples, long long t_out, int channels) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float xs[BWD_FR * S + K];
   const int b = blockIdx.y;
   const long long t0 = (long long)blockIdx.x * BWD_FR;
@@ -447,11 +463,11 @@ int smx_conv0_stats(const float* audio, const float* w, float* moments, float* s
   SMX_REQUIRE(t_out == (n_samples - K) / S + 1 && t_out > 0, "conv0: inconsistent t_out");
   SMX_REQUIRE(partial_ws != nullptr, "conv0_stats: partial_ws (batch * SMX_CONV0_MOMENT_BLOCKS * 65 floats) required");
   cudaStream_t st = (cudaStream_t)stream;
-  moments_kernel<<<dim3(SMX_CONV0_MOMENT_BLOCKS, (unsigned)batch), 256, 0, st>>>(audio, partial_ws, n_samples, t_out);
+  launch_pdl(moments_kernel, dim3(dim3(SMX_CONV0_MOMENT_BLOCKS, (unsigned)batch)), dim3(256), 0, st, audio, partial_ws, n_samples, t_out);
   SMX_CHECK_CUDA(cudaGetLastError());
-  moments_reduce_kernel<<<(unsigned)batch, 128, 0, st>>>(partial_ws, moments, SMX_CONV0_MOMENT_BLOCKS);
+  launch_pdl(moments_reduce_kernel, dim3((unsigned)batch), dim3(128), 0, st, partial_ws, moments, SMX_CONV0_MOMENT_BLOCKS);
   SMX_CHECK_CUDA(cudaGetLastError());
-  stats_kernel<<<(int)ceil_div(batch * channels, 256), 256, 0, st>>>(w, moments, stats, (int)batch, channels, t_out, eps);
+  launch_pdl(stats_kernel, dim3((int)ceil_div(batch * channels, 256)), dim3(256), 0, st, w, moments, stats, (int)batch, channels, t_out, eps);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -461,7 +477,7 @@ int smx_conv0_gn_gelu_fwd(const float* audio, const float* w, const float* gamma
                           int channels, int ksize, int stride, void* stream) {
   SMX_REQUIRE(ksize == K && stride == S, "conv0: only kernel 10 / stride 5 is supported");
   SMX_REQUIRE(channels % 8 == 0, "conv0: channels must be a multiple of 8");
-  fwd_kernel<<<dim3((unsigned)ceil_div(t_out, FWD_FR), (unsigned)batch), 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(fwd_kernel, dim3(dim3((unsigned)ceil_div(t_out, FWD_FR), (unsigned)batch)), dim3(256), 0, (cudaStream_t)stream, 
       audio, w, gamma, beta, stats, (bf16*)y, (bf16*)gprime, n_samples, t_out, channels);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -476,10 +492,10 @@ int smx_conv0_gn_gelu_bwd(const float* audio, const float* w, const float* gamma
   SMX_REQUIRE(channels % 4 == 0, "conv0: channels must be a multiple of 4");
   cudaStream_t st = (cudaStream_t)stream;
   SMX_CHECK_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * (K + 2) * batch * channels, st));
-  bwd_kernel<<<dim3((unsigned)ceil_div(t_out, BWD_FR), (unsigned)batch), 256, 0, st>>>(
+  launch_pdl(bwd_kernel, dim3(dim3((unsigned)ceil_div(t_out, BWD_FR), (unsigned)batch)), dim3(256), 0, st, 
       audio, (const bf16*)dy, (const bf16*)gprime, partial, n_samples, t_out, channels);
   SMX_CHECK_CUDA(cudaGetLastError());
-  bwd_finalize_kernel<<<(int)ceil_div(channels * (K + 2), 128), 128, 0, st>>>(w, gamma, stats, moments, partial, dw,
+  launch_pdl(bwd_finalize_kernel, dim3((int)ceil_div(channels * (K + 2), 128)), dim3(128), 0, st, w, gamma, stats, moments, partial, dw,
                                                                              dgamma, dbeta, (int)batch, channels, t_out);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -496,7 +512,7 @@ int smx_conv0_ln_gelu_fwd(const float* audio, const float* w, const float* conv_
   const long long frames = batch * t_out;
   long long grid = ceil_div(frames, 8 * 16);
   if (grid > (long long)num_sms() * 8) grid = (long long)num_sms() * 8;
-  ln_variant_kernel<false><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(ln_variant_kernel<false>, dim3((unsigned)grid), dim3(256), 0, (cudaStream_t)stream, 
       audio, w, conv_bias, gamma, beta, (bf16*)y, nullptr, nullptr, nullptr, nullptr, n_samples, t_out, frames,
       channels, eps);
   SMX_CHECK_CUDA(cudaGetLastError());
@@ -513,7 +529,7 @@ int smx_conv0_ln_gelu_bwd(const float* audio, const float* w, const float* conv_
   const long long frames = batch * t_out;
   long long grid = ceil_div(frames, 8 * 16);
   if (grid > (long long)num_sms() * 4) grid = (long long)num_sms() * 4;
-  ln_variant_kernel<true><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(ln_variant_kernel<true>, dim3((unsigned)grid), dim3(256), 0, (cudaStream_t)stream, 
       audio, w, conv_bias, gamma, beta, nullptr, (const bf16*)dy, (bf16*)dconv, dgamma, dbeta, n_samples, t_out,
       frames, channels, eps);
   SMX_CHECK_CUDA(cudaGetLastError());
@@ -525,7 +541,7 @@ int smx_conv0_wgrad(const float* audio, const void* dconv, float* dw, float* dbi
                     int64_t t_out, int channels, int ksize, int stride, void* stream) {
   SMX_REQUIRE(ksize == K && stride == S, "conv0: only kernel 10 / stride 5 is supported");
   SMX_REQUIRE(channels % 4 == 0, "conv0: channels must be a multiple of 4");
-  wgrad_kernel<<<dim3((unsigned)ceil_div(t_out, BWD_FR), (unsigned)batch), 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(wgrad_kernel, dim3(dim3((unsigned)ceil_div(t_out, BWD_FR), (unsigned)batch)), dim3(256), 0, (cudaStream_t)stream, 
       audio, (const bf16*)dconv, dw, dbias, n_samples, t_out, channels);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -20,6 +20,8 @@ namespace distill {
 __global__ void __launch_bounds__(256) kl_chunk_fwd_kernel(const float* __restrict__ s, const float* __restrict__ t,
                                                            long long ld, long long rows, int vn,
                                                            const float* __restrict__ lse_t, float* __restrict__ cross) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -43,6 +45,8 @@ __global__ void __launch_bounds__(256) kl_chunk_fwd_kernel(const float* __restri
 __global__ void kl_finalize_kernel(const float* __restrict__ cross, const float* __restrict__ lse_s,
                                    const float* __restrict__ lse_t, long long rows, float inv_batch,
                                    float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   float acc = 0.f;
   for (long long r = threadIdx.x; r < rows; r += blockDim.x) acc += cross[r] - lse_t[r] + lse_s[r];
   __shared__ float red[32];
@@ -62,6 +66,8 @@ __global__ void __launch_bounds__(256) kl_chunk_bwd_kernel(const float* __restri
                                                            const float* __restrict__ lse_s, const float* __restrict__ lse_t,
                                                            const float* __restrict__ coef_ce, const float* __restrict__ coef_kl,
                                                            bf16* __restrict__ dl, long long ld_out) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -85,6 +91,8 @@ __global__ void __launch_bounds__(256) mse_fwd_kernel(const bf16* __restrict__ T
                                                       float* __restrict__ A, float* __restrict__ diff,
                                                       float* __restrict__ loss, int Tt, int Ts, int D, float inv_sqrt_d,
                                                       float inv_n) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   float* trow = sm;          // [D]
   float* prob = sm + D;      // [Ts]
@@ -151,6 +159,8 @@ __global__ void __launch_bounds__(256) mse_fwd_kernel(const bf16* __restrict__ T
 __global__ void __launch_bounds__(256) mse_bwd_scores_kernel(const bf16* __restrict__ S, const float* __restrict__ A,
                                                              const float* __restrict__ diff, float* __restrict__ dsc,
                                                              int Tt, int Ts, int D, float inv_sqrt_d) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   float* drow = sm;       // [D] diff row
   float* da = sm + D;     // [Ts]
@@ -188,6 +198,8 @@ __global__ void __launch_bounds__(256) mse_bwd_ds_kernel(const bf16* __restrict_
                                                          const float* __restrict__ diff, const float* __restrict__ dsc,
                                                          bf16* __restrict__ dS, int Tt, int Ts, int D,
                                                          const float* __restrict__ gscale) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= (long long)Ts * D) return;
@@ -208,6 +220,8 @@ __global__ void __launch_bounds__(256) mse_bwd_ds_kernel(const bf16* __restrict_
 // ------------------------------------------------------------------ relative position bias
 __global__ void relpos_fwd_kernel(const float* __restrict__ w, const int* __restrict__ table, float* __restrict__ bias,
                                   int heads, int tq, int tk, int q_offset) {
+  pdl_trigger();
+  pdl_wait();
   const long long n = (long long)heads * tq * tk;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(e % tk);
@@ -220,6 +234,8 @@ __global__ void relpos_fwd_kernel(const float* __restrict__ w, const int* __rest
 __global__ void __launch_bounds__(256) relpos_bwd_kernel(const float* __restrict__ dbias, const int* __restrict__ table,
                                                          float* __restrict__ dw, int heads, int tq, int tk, int q_offset,
                                                          int n_buckets) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float hist[256];
   const int h = blockIdx.y;
   for (int i = threadIdx.x; i < n_buckets; i += blockDim.x) hist[i] = 0.f;
@@ -244,13 +260,13 @@ extern "C" {
 int smx_kl_chunk_fwd(const float* s, const float* t, int64_t ld, int64_t rows, int64_t vn, const float* lse_t,
                      float* cross, void* stream) {
   SMX_REQUIRE(s && t && lse_t && cross && ld % 4 == 0, "kl_chunk_fwd: bad arguments");
-  kl_chunk_fwd_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(s, t, ld, rows, (int)vn, lse_t, cross);
+  launch_pdl(kl_chunk_fwd_kernel, dim3((unsigned)ceil_div(rows, 8)), dim3(256), 0, (cudaStream_t)stream, s, t, ld, rows, (int)vn, lse_t, cross);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int smx_kl_finalize(const float* cross, const float* lse_s, const float* lse_t, int64_t rows, float inv_batch,
                     float* out, void* stream) {
-  kl_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(cross, lse_s, lse_t, rows, inv_batch, out);
+  launch_pdl(kl_finalize_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, cross, lse_s, lse_t, rows, inv_batch, out);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -258,7 +274,7 @@ int smx_kl_chunk_bwd(const float* s, const float* t, int64_t ld, int64_t rows, i
                      const int64_t* labels, const float* lse_s, const float* lse_t, const float* coef_ce,
                      const float* coef_kl, void* dlogits, int64_t ld_out, void* stream) {
   SMX_REQUIRE(s && t && labels && lse_s && lse_t && coef_ce && coef_kl && dlogits, "kl_chunk_bwd: null pointer");
-  kl_chunk_bwd_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(kl_chunk_bwd_kernel, dim3((unsigned)ceil_div(rows, 8)), dim3(256), 0, (cudaStream_t)stream, 
       s, t, ld, rows, (int)vn, v0, reinterpret_cast<const long long*>(labels), lse_s, lse_t, coef_ce, coef_kl,
       reinterpret_cast<bf16*>(dlogits), ld_out);
   SMX_CHECK_CUDA(cudaGetLastError());
@@ -271,7 +287,7 @@ int smx_self_mse_fwd(const void* text_h, const void* speech_h, float* attn, floa
   const size_t smem = (size_t)(dim + ts) * 4;
   SMX_REQUIRE(smem <= 48 * 1024, "self_mse_fwd: dim + ts too large (%lld)", (long long)(dim + ts));
   dim3 grid((unsigned)tt, (unsigned)batch);
-  mse_fwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(
+  launch_pdl(mse_fwd_kernel, dim3(grid), dim3(256), smem, (cudaStream_t)stream, 
       reinterpret_cast<const bf16*>(text_h), reinterpret_cast<const bf16*>(speech_h), attn, diff, loss, (int)tt, (int)ts,
       (int)dim, 1.0f / sqrtf((float)dim), 1.0f / (float)(batch * tt * dim));
   SMX_CHECK_CUDA(cudaGetLastError());
@@ -284,12 +300,12 @@ int smx_self_mse_bwd(const void* text_h, const void* speech_h, const float* attn
   const size_t smem = (size_t)(dim + ts) * 4;
   SMX_REQUIRE(smem <= 48 * 1024, "self_mse_bwd: dim + ts too large");
   dim3 grid((unsigned)tt, (unsigned)batch);
-  mse_bwd_scores_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<const bf16*>(speech_h), attn, diff,
+  launch_pdl(mse_bwd_scores_kernel, dim3(grid), dim3(256), smem, (cudaStream_t)stream, reinterpret_cast<const bf16*>(speech_h), attn, diff,
                                                                   dscores, (int)tt, (int)ts, (int)dim,
                                                                   1.0f / sqrtf((float)dim));
   SMX_CHECK_CUDA(cudaGetLastError());
   dim3 g2((unsigned)ceil_div(ts * dim, 256), (unsigned)batch);
-  mse_bwd_ds_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const bf16*>(text_h), attn, diff, dscores,
+  launch_pdl(mse_bwd_ds_kernel, dim3(g2), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const bf16*>(text_h), attn, diff, dscores,
                                                          reinterpret_cast<bf16*>(d_speech_h), (int)tt, (int)ts, (int)dim,
                                                          gscale);
   SMX_CHECK_CUDA(cudaGetLastError());
@@ -302,7 +318,7 @@ int smx_relpos_bias_fwd(const float* weight, const int32_t* table, float* bias, 
   const long long n = heads * tq * tk;
   long long g = ceil_div(n, 256);
   if (g > 148 * 16) g = 148 * 16;
-  relpos_fwd_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(weight, table, bias, (int)heads, (int)tq, (int)tk,
+  launch_pdl(relpos_fwd_kernel, dim3((unsigned)g), dim3(256), 0, (cudaStream_t)stream, weight, table, bias, (int)heads, (int)tq, (int)tk,
                                                                   (int)q_offset);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -314,7 +330,7 @@ int smx_relpos_bias_bwd(const float* dbias, const int32_t* table, float* dweight
   if (g < 1) g = 1;
   if (g > 64) g = 64;
   dim3 grid((unsigned)g, (unsigned)heads);
-  relpos_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dbias, table, dweight, (int)heads, (int)tq, (int)tk,
+  launch_pdl(relpos_bwd_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, dbias, table, dweight, (int)heads, (int)tq, (int)tk,
                                                            (int)q_offset, (int)n_buckets);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -365,6 +365,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   uint64_t* inbar = tempty + 2;  // one per epilogue warp: staged epilogue-input tile has landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(inbar + EPI_WARPS);
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();  // 0 = leader of the pair
@@ -390,6 +391,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   cluster_sync_all();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above is on-chip setup; global memory is touched only below
 
   const int total_tiles = p.m_tiles * p.n_tiles * p.split_k;
 
@@ -853,13 +855,15 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr;
-  attr.id = cudaLaunchAttributeClusterDimension;
-  attr.val.clusterDim.x = 2;
-  attr.val.clusterDim.y = 1;
-  attr.val.clusterDim.z = 1;
-  cfg.attrs = &attr;
-  cfg.numAttrs = 1;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see sm100_prims.cuh (pdl_trigger / pdl_wait)
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   SMX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<MODE, EPI, FAST>, ta, tb, tc, tx, ti, p));
   return 0;
 }

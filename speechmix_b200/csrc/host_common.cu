@@ -1,5 +1,7 @@
 #include "host_common.h"
 
+#include <stdlib.h>
+
 #include <string.h>
 
 #include "../../include/speechmix_sm100.h"
@@ -82,6 +84,15 @@ int num_sms() {
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
   return n;
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SMX_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
 }
 
 }  // namespace smx

@@ -34,6 +34,8 @@ __global__ void __launch_bounds__(256) combine_kernel(const float4* __restrict__
                                                       long long* __restrict__ argmax_out, float* __restrict__ row_loss,
                                                       float* __restrict__ loss_sum, float* __restrict__ count,
                                                       long long rows, int n_tiles, long long ignore_index) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -122,7 +124,7 @@ int smx_lmhead_ce_fwd(const void* h, const void* emb, const float* bias, const i
   ex.labels = reinterpret_cast<const long long*>(labels);
   SMX_REQUIRE(labels != nullptr, "lmhead_ce_fwd: labels required (pass -100 rows for pure argmax)");
   if (gemm::run(&g, &ex, stream)) return -1;
-  lmhead::combine_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>(
+  launch_pdl(lmhead::combine_kernel, dim3((unsigned)ceil_div(rows, 8)), dim3(256), 0, st, 
       partial, label_logit, reinterpret_cast<const long long*>(labels), lse, reinterpret_cast<long long*>(argmax),
       row_loss, loss_sum, count, rows, (int)n_tiles, ignore_index);
   SMX_CHECK_CUDA(cudaGetLastError());

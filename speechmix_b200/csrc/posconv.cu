@@ -39,6 +39,8 @@ struct FwdParams {
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 posconv_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap xmap_tail,
                    const FwdParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(1024) uint8_t smem[];
   const int cg = p.cg, chunks = cg / 8;
   const int slab_bytes = chunks * SLAB_ROWS * 16;
@@ -179,22 +181,34 @@ posconv_fwd_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
 }
 
 // ------------------------------------------------------------------ weight gradient
-constexpr int WG_TAPS = 8;       // taps per CTA (8 x 64 TMEM columns)
-constexpr int WG_STAGES = 3;
-constexpr int WG_XROWS = 128 + WG_TAPS;  // 136
+// dW[g][tap][o][c] = sum_{b,t} dpre[b, t, g cg + o] * x[b, t + tap - pad, g cg + c]     (contraction over frames)
+//
+// One CTA owns (group g, ONE 8-channel chunk j of the group's input channels, up to 64 taps) and a share of the
+// 128-frame tiles.  Both operands are MN-major slabs in the chunk-major layout ([chunk][frame][8 channels], 16 B per
+// frame): A = dpre^T (M = output channels, chunks SBO = 2 KiB apart), B = the x chunk.  Because the B slab holds a
+// single chunk, "the window of the next tap" is the same slab 16 bytes further on -- so the N dimension of ONE MMA can
+// run over (tap, channel-in-chunk) with a stride-dimension offset of 16 B (overlapping core matrices): N = 32 taps x 8
+// channels = 256, the full-rate shape, instead of one N = cg MMA per tap (which sat on the ~45-clk floor of a small
+// MMA and re-read the 4 KiB A tile for every tap: shared-memory bound at 11 % of the tensor peak).  Two tap blocks
+// share the A tile (2 x 256 TMEM columns).  Rows of D past cg are products with the neighbouring groups' channels (A is
+// over-read to M = 128) and are never read back.  Partial sums leave through 16-byte fp32 reductions.
+constexpr int WG_STAGES = 4;
+constexpr int WG_XROWS = 128 + 64;   // 128 frames + up to 64 taps of halo
 
 struct WgParams {
   float* dw;  // [G][ksize][cg(o)][cg(c)]
   int t, cg, ksize, pad, batch, splits;
+  int tpm, nblk;   // taps per MMA (16 or 32), tap blocks per CTA (1 or 2)
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 posconv_wgrad_kernel(const __grid_constant__ CUtensorMap dmap, const __grid_constant__ CUtensorMap xmap,
                      const WgParams p) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem[];
   const int cg = p.cg, chunks = cg / 8;
   const int d_bytes = chunks * 128 * 16;
-  const int x_bytes = chunks * WG_XROWS * 16;
+  const int x_bytes = WG_XROWS * 16;
   uint8_t* dsl = smem;                                 // WG_STAGES dpre slabs first (A over-reads stay in smem)
   uint8_t* xsl = smem + WG_STAGES * d_bytes;
   const int bar_off = ((WG_STAGES * (d_bytes + x_bytes) + 1023) / 1024) * 1024;
@@ -205,7 +219,8 @@ posconv_wgrad_kernel(const __grid_constant__ CUtensorMap dmap, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tap0 = blockIdx.x * WG_TAPS, g = blockIdx.y, split = blockIdx.z;
+  const int taps_cta = p.tpm * p.nblk;
+  const int tap0 = blockIdx.x * taps_cta, g = blockIdx.y / chunks, j = blockIdx.y % chunks, split = blockIdx.z;
   const int tiles_per_batch = (p.t + 127) / 128;
   const int n_tiles = tiles_per_batch * p.batch;
 
@@ -222,6 +237,7 @@ posconv_wgrad_kernel(const __grid_constant__ CUtensorMap dmap, const __grid_cons
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -232,7 +248,7 @@ posconv_wgrad_kernel(const __grid_constant__ CUtensorMap dmap, const __grid_cons
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_expect_tx(&full[stage], d_bytes + x_bytes);
         tma_load_4d(dsl + stage * d_bytes, &dmap, &full[stage], 0, tt, g * chunks, bb);
-        tma_load_4d(xsl + stage * x_bytes, &xmap, &full[stage], 0, tt + tap0 - p.pad, g * chunks, bb);
+        tma_load_4d(xsl + stage * x_bytes, &xmap, &full[stage], 0, tt + tap0 - p.pad, g * chunks + j, bb);
         if (++stage == WG_STAGES) {
           stage = 0;
           phase ^= 1;
@@ -241,7 +257,7 @@ posconv_wgrad_kernel(const __grid_constant__ CUtensorMap dmap, const __grid_cons
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, cg, true, true);
+      const uint32_t idesc = umma_idesc_bf16(128, 8 * p.tpm, true, true);
       const uint32_t d_a = smem_u32(dsl), x_a = smem_u32(xsl);
       int stage = 0;
       uint32_t phase = 0;
@@ -249,13 +265,14 @@ posconv_wgrad_kernel(const __grid_constant__ CUtensorMap dmap, const __grid_cons
       for (int tile = split; tile < n_tiles; tile += p.splits) {
         mbar_wait(&full[stage], phase);
         tc_fence_after_sync();
-        for (int tl = 0; tl < WG_TAPS; ++tl) {
+        for (int blk = 0; blk < p.nblk; ++blk) {
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
-            // MN-major, no swizzle: 8-channel chunks SBO apart, 8-frame groups LBO = 128 B apart
+            // A: MN-major, no swizzle: 8-channel chunks SBO = 2 KiB apart, 8-frame groups LBO = 128 B apart.
+            // B: same frame stepping; the "next chunk" of N is the next TAP = the same chunk one frame (16 B) later.
             const uint64_t ad = umma_smem_desc(d_a + stage * d_bytes + kk * 256, 128, 128 * 16, kLayoutNone);
-            const uint64_t bd = umma_smem_desc(x_a + stage * x_bytes + (kk * 16 + tl) * 16, 128, WG_XROWS * 16, kLayoutNone);
-            umma_ss(tmem_base + tl * 64, ad, bd, idesc, (!first || kk > 0) ? 1u : 0u);
+            const uint64_t bd = umma_smem_desc(x_a + stage * x_bytes + (kk * 16 + blk * p.tpm) * 16, 128, 16, kLayoutNone);
+            umma_ss(tmem_base + blk * 256, ad, bd, idesc, (!first || kk > 0) ? 1u : 0u);
           }
         }
         first = false;
@@ -274,17 +291,20 @@ posconv_wgrad_kernel(const __grid_constant__ CUtensorMap dmap, const __grid_cons
     tc_fence_after_sync();
     const bool any = split < n_tiles;
     if (q * 32 < cg) {
-      for (int tl = 0; tl < WG_TAPS; ++tl) {
-        for (int c16 = 0; c16 < cg / 16; ++c16) {
+      for (int blk = 0; blk < p.nblk; ++blk) {
+        for (int t2 = 0; t2 < p.tpm; t2 += 2) {     // 16 columns = 2 taps x 8 input channels
           uint32_t v[16];
-          tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tl * 64 + c16 * 16, v);
+          tmem_ld_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + blk * 256 + t2 * 8, v);
           tmem_ld_wait();
           if (o < cg && any) {
-            float* dst = p.dw + (((long long)g * p.ksize + tap0 + tl) * cg + o) * cg + c16 * 16;
 #pragma unroll
-            for (int i = 0; i < 16; i += 4)
-              red_add_v4(dst + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
-                         __uint_as_float(v[i + 3]));
+            for (int h = 0; h < 2; ++h) {
+              float* dst = p.dw + (((long long)g * p.ksize + tap0 + blk * p.tpm + t2 + h) * cg + o) * cg + j * 8;
+              red_add_v4(dst, __uint_as_float(v[8 * h]), __uint_as_float(v[8 * h + 1]), __uint_as_float(v[8 * h + 2]),
+                         __uint_as_float(v[8 * h + 3]));
+              red_add_v4(dst + 4, __uint_as_float(v[8 * h + 4]), __uint_as_float(v[8 * h + 5]),
+                         __uint_as_float(v[8 * h + 6]), __uint_as_float(v[8 * h + 7]));
+            }
           }
           __syncwarp();
         }
@@ -336,7 +356,7 @@ static int fwd_like(const void* x, const void* w_packed, const float* bias, void
   }
   SMX_REQUIRE(smem_bytes <= 200 * 1024, "posconv: smem budget exceeded");
   dim3 grid((unsigned)ceil_div(t, 256), groups, (unsigned)batch);
-  posconv_fwd_kernel<<<grid, NUM_THREADS, smem_bytes, st>>>(xmap, xmap_tail, p);
+  launch_pdl(posconv_fwd_kernel, dim3(grid), dim3(NUM_THREADS), smem_bytes, st, xmap, xmap_tail, p);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -364,28 +384,35 @@ int smx_posconv_wgrad(const void* dpre, const void* x, float* dw, int64_t batch,
   using namespace smx::posconv;
   const int cg = hidden / groups;
   SMX_REQUIRE(hidden % groups == 0 && cg % 16 == 0 && cg <= 64, "posconv_wgrad: channels/group %d unsupported", cg);
-  SMX_REQUIRE(ksize % WG_TAPS == 0, "posconv_wgrad: kernel size must be a multiple of 8");
+  SMX_REQUIRE(ksize % 16 == 0 && ksize <= 128, "posconv_wgrad: kernel size %d unsupported", ksize);
   CUtensorMap dmap, xmap;
   if (make_chunk_map(&dmap, dpre, batch, t, hidden, 128, cg / 8)) return -1;
-  if (make_chunk_map(&xmap, x, batch, t, hidden, WG_XROWS, cg / 8)) return -1;
+  if (make_chunk_map(&xmap, x, batch, t, hidden, WG_XROWS, 1)) return -1;
   WgParams p;
   p.dw = dw;
   p.t = (int)t, p.cg = cg, p.ksize = ksize, p.pad = ksize / 2, p.batch = (int)batch;
-  const int n_tiles = (int)(ceil_div(t, 128) * batch);
-  const int base = (ksize / WG_TAPS) * groups;
-  int splits = (num_sms() * 3 + base - 1) / base;
-  if (splits > n_tiles) splits = n_tiles;
-  if (splits < 1) splits = 1;
-  p.splits = splits;
+  p.tpm = (ksize % 32 == 0) ? 32 : 16;
+  p.nblk = ((ksize / p.tpm) % 2 == 0) ? 2 : 1;
   const int chunks = cg / 8;
-  const int d_bytes = chunks * 128 * 16, x_bytes = chunks * WG_XROWS * 16;
+  const int n_tiles = (int)(ceil_div(t, 128) * batch);
+  const int base = (ksize / (p.tpm * p.nblk)) * groups * chunks;
+  // contraction splits: whole waves of one CTA per SM, per-CTA cost = its tiles + ~3 tiles of prologue / reduction
+  int splits = 1;
+  double best = 1e30;
+  for (int sp = 1; sp <= 16 && sp <= n_tiles; ++sp) {
+    const double waves = (double)ceil_div((int64_t)base * sp, num_sms());
+    const double cost = waves * ((double)ceil_div(n_tiles, sp) + 3.0);
+    if (cost < best - 1e-9) best = cost, splits = sp;
+  }
+  p.splits = splits;
+  const int d_bytes = chunks * 128 * 16, x_bytes = WG_XROWS * 16;
   int bar_off = ((WG_STAGES * (d_bytes + x_bytes) + 1023) / 1024) * 1024;
   const int min_off = (WG_STAGES - 1) * d_bytes + 32768;
   if (bar_off < min_off) bar_off = min_off;
   const int smem_bytes = bar_off + 256;
   SMX_CHECK_CUDA(cudaFuncSetAttribute(posconv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  dim3 grid(ksize / WG_TAPS, groups, splits);
-  posconv_wgrad_kernel<<<grid, NUM_THREADS, smem_bytes, (cudaStream_t)stream>>>(dmap, xmap, p);
+  dim3 grid(ksize / (p.tpm * p.nblk), groups * chunks, splits);
+  launch_pdl(posconv_wgrad_kernel, dim3(grid), dim3(NUM_THREADS), smem_bytes, (cudaStream_t)stream, dmap, xmap, p);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -48,6 +48,8 @@ __global__ void __launch_bounds__(256) ln_fwd_reg_kernel(const bf16* __restrict_
                                                      bf16* __restrict__ y, bf16* __restrict__ sum_out,
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                      long long rows, int cols, float eps, int rms_only, int act) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -150,6 +152,8 @@ ln_bwd_reg_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const
               const float* __restrict__ beta, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
               const bf16* __restrict__ dres, bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
               float* __restrict__ dx_colsum, long long rows, int cols, int rms_only, int act) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8][32 * 8 + 1];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -345,6 +349,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                      long long rows, int cols, float eps, int rms_only, int act,
                                                      int stages) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(128) uint8_t ring_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long warp_global = (long long)blockIdx.x * 8 + warp;
@@ -449,6 +455,8 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
               const float* __restrict__ beta, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
               const bf16* __restrict__ dres, bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
               float* __restrict__ dx_colsum, long long rows, int cols, int rms_only, int act, int stages) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(128) uint8_t ring_smem[];
   __shared__ float red[8][32 * 8 + 1];
   const int lane = threadIdx.x & 31;
@@ -564,6 +572,8 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
 // ------------------------------------------------------------------ column sums (bias grads)
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out,
                                                      long long rows, int cols, long long row_stride) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8][32 * 8 + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = (blockIdx.x * 32 + lane) * 8;
@@ -605,6 +615,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
 // x[b][t][col_begin : col_begin + col_count] = 0 for t >= len[b]; one 16-byte vector per thread
 __global__ void mask_rows_kernel(bf16* __restrict__ x, const int* __restrict__ len, long long batch, long long t,
                                  long long row_stride, long long batch_stride, int col_begin, int vec_per_row) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = batch * t * vec_per_row;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int vc = (int)(i % vec_per_row);
@@ -623,6 +635,8 @@ __global__ void mask_rows_kernel(bf16* __restrict__ x, const int* __restrict__ l
 __global__ void dropout_kernel(const bf16* __restrict__ x, const bf16* __restrict__ residual, bf16* __restrict__ out,
                                const bf16* __restrict__ aux_in, bf16* __restrict__ aux_out, int aux_mode, long long n_vec,
                                const unsigned long long* __restrict__ state, uint32_t call, float p) {
+  pdl_trigger();
+  pdl_wait();
   const DropKey key = drop_key(state, call, p);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x) {
     float f[8], r[8], a[8];
@@ -655,6 +669,8 @@ __global__ void dropout_kernel(const bf16* __restrict__ x, const bf16* __restric
 // dropout); mode 1: attention probabilities [rows][tk] -- pairs are numbered per row, row * ceil(tk / 2) + (k >> 1)
 __global__ void dropout_mask_kernel(unsigned char* __restrict__ mask, long long n, long long tk, int mode,
                                     const unsigned long long* __restrict__ state, uint32_t call, float p) {
+  pdl_trigger();
+  pdl_wait();
   const DropKey key = drop_key(state, call, p);
   const long long hp = (tk + 1) / 2;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
@@ -677,6 +693,8 @@ __global__ void spec_augment_fwd_kernel(const bf16* __restrict__ x, bf16* __rest
                                         const unsigned char* __restrict__ time_mask,
                                         const unsigned char* __restrict__ feat_mask, const float* __restrict__ embed,
                                         long long rows, long long t, int hidden) {
+  pdl_trigger();
+  pdl_wait();
   const int vec_per_row = hidden / 8;
   const long long total = rows * vec_per_row;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -698,6 +716,8 @@ __global__ void spec_augment_bwd_kernel(const bf16* __restrict__ dy, bf16* __res
                                         const unsigned char* __restrict__ time_mask,
                                         const unsigned char* __restrict__ feat_mask, long long rows, long long t,
                                         int hidden) {
+  pdl_trigger();
+  pdl_wait();
   const int vec_per_row = hidden / 8;
   const long long total = rows * vec_per_row;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -717,6 +737,8 @@ __global__ void __launch_bounds__(256) spec_augment_dembed_kernel(const bf16* __
                                                                   const unsigned char* __restrict__ time_mask,
                                                                   const unsigned char* __restrict__ feat_mask,
                                                                   long long rows, long long t, int hidden) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * 256 + threadIdx.x;
   if (c >= hidden) return;
   float acc = 0.f;
@@ -730,6 +752,8 @@ __global__ void __launch_bounds__(256) spec_augment_dembed_kernel(const bf16* __
 
 // ------------------------------------------------------------------ elementwise
 __global__ void cast_kernel(const float* __restrict__ s, bf16* __restrict__ d, long long n) {
+  pdl_trigger();
+  pdl_wait();
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   const long long stride = (long long)gridDim.x * blockDim.x * 8;
   for (; i + 8 <= n; i += stride) {
@@ -742,6 +766,8 @@ __global__ void cast_kernel(const float* __restrict__ s, bf16* __restrict__ d, l
 }
 // one block per 4096-element chunk of one table entry (binary search block -> entry)
 __global__ void __launch_bounds__(256) multi_cast_kernel(const SmxCastEntry* __restrict__ table, int n_entries) {
+  pdl_trigger();
+  pdl_wait();
   int lo = 0, hi = n_entries - 1;
   const int b = blockIdx.x;
   while (lo < hi) {
@@ -772,6 +798,8 @@ __global__ void __launch_bounds__(256) multi_cast_kernel(const SmxCastEntry* __r
   }
 }
 __global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ o, long long n) {
+  pdl_trigger();
+  pdl_wait();
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   const long long stride = (long long)gridDim.x * blockDim.x * 8;
   for (; i + 8 <= n; i += stride) {
@@ -786,6 +814,8 @@ __global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ 
     for (long long j = i; j < n; ++j) o[j] = __float2bfloat16(__bfloat162float(a[j]) + __bfloat162float(b[j]));
 }
 __global__ void act_kernel(const bf16* __restrict__ a, bf16* __restrict__ o, long long n, int act) {
+  pdl_trigger();
+  pdl_wait();
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   const long long stride = (long long)gridDim.x * blockDim.x * 8;
   for (; i + 8 <= n; i += stride) {
@@ -799,6 +829,8 @@ __global__ void act_kernel(const bf16* __restrict__ a, bf16* __restrict__ o, lon
 // out = dy * act'(pre)
 __global__ void dact_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ pre, bf16* __restrict__ o, long long n,
                             int act) {
+  pdl_trigger();
+  pdl_wait();
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   const long long stride = (long long)gridDim.x * blockDim.x * 8;
   for (; i + 8 <= n; i += stride) {
@@ -813,6 +845,8 @@ __global__ void dact_kernel(const bf16* __restrict__ dy, const bf16* __restrict_
 }
 __global__ void pack_conv_w_kernel(const float* __restrict__ s, bf16* __restrict__ d, long long cout, long long cin,
                                    long long k) {
+  pdl_trigger();
+  pdl_wait();
   const long long n = cout * cin * k;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const long long o = i / (cin * k), r = i % (cin * k), t = r / cin, c = r % cin;
@@ -821,6 +855,8 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ s, bf16* __restrict
 }
 __global__ void unpack_conv_g_kernel(const float* __restrict__ s, float* __restrict__ d, long long cout, long long cin,
                                      long long k) {
+  pdl_trigger();
+  pdl_wait();
   const long long n = cout * cin * k;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const long long o = i / (cin * k), r = i % (cin * k), c = r / k, t = r % k;
@@ -833,6 +869,8 @@ __global__ void unpack_conv_g_kernel(const float* __restrict__ s, float* __restr
 __global__ void embed_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ tok,
                                  const float* __restrict__ pos, const bf16* __restrict__ x_in, bf16* __restrict__ out,
                                  long long rows, long long t_len, int dim, float scale, long long pos_off) {
+  pdl_trigger();
+  pdl_wait();
   const int vecs = dim / 8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows * vecs;
        i += (long long)gridDim.x * blockDim.x) {
@@ -863,6 +901,8 @@ __global__ void embed_fwd_kernel(const long long* __restrict__ ids, const float*
 __global__ void embed_bwd_kernel(const long long* __restrict__ ids, const bf16* __restrict__ dout,
                                  float* __restrict__ dtok, float* __restrict__ dpos, long long rows, long long t_len,
                                  int dim, float scale, long long pos_off) {
+  pdl_trigger();
+  pdl_wait();
   const int vecs = dim / 8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows * vecs;
        i += (long long)gridDim.x * blockDim.x) {
@@ -889,6 +929,8 @@ struct PtrPack {
   const bf16* p[kMaxLayers];
 };
 __global__ void wsum_fwd_kernel(PtrPack xs, const float* __restrict__ w, bf16* __restrict__ out, int nl, long long n) {
+  pdl_trigger();
+  pdl_wait();
   float wl[kMaxLayers];
   for (int l = 0; l < nl; ++l) wl[l] = w[l];
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
@@ -906,6 +948,8 @@ __global__ void wsum_fwd_kernel(PtrPack xs, const float* __restrict__ w, bf16* _
 }
 __global__ void __launch_bounds__(256) wsum_bwd_w_kernel(PtrPack xs, const bf16* __restrict__ dout,
                                                          float* __restrict__ dw, int nl, long long n) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8];
   long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   const long long stride = (long long)gridDim.x * blockDim.x * 8;
@@ -935,6 +979,8 @@ __global__ void __launch_bounds__(256) wsum_bwd_w_kernel(PtrPack xs, const bf16*
 // hf:models/wav2vec2/modeling_wav2vec2.py:341-355).  v viewed as [rows = out*in/groups][k].
 __global__ void __launch_bounds__(256) wn_colstat_kernel(const float* __restrict__ a, const float* __restrict__ b2,
                                                          float* __restrict__ out, long long rows, int k) {
+  pdl_trigger();
+  pdl_wait();
   // out[j] += sum_r a[r][j] * (b2 ? b2[r][j] : a[r][j]);  blockDim.x = 256 = 8 row lanes x 32 columns
   __shared__ float red[8][33];
   const int cj = threadIdx.x & 31, rl = threadIdx.x >> 5;
@@ -956,6 +1002,8 @@ __global__ void __launch_bounds__(256) wn_colstat_kernel(const float* __restrict
 }
 __global__ void wn_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ sq,
                               float* __restrict__ w, long long n, int k) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(i % k);
     w[i] = v[i] * g[j] * rsqrtf(sq[j]);
@@ -965,6 +1013,8 @@ __global__ void wn_fwd_kernel(const float* __restrict__ v, const float* __restri
 __global__ void wn_bwd_kernel(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ sq,
                               const float* __restrict__ dot, const float* __restrict__ dw, float* __restrict__ dv,
                               float* __restrict__ dg, long long n, int k) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(i % k);
     const float inv = rsqrtf(sq[j]);
@@ -1052,12 +1102,12 @@ int smx_layernorm_fwd(const void* x, const void* res, const float* gamma, const 
 #define LN_FWD_LAUNCH(V)                                                                                         \
   do {                                                                                                           \
     if (res == nullptr) {                                                                                        \
-      ln_fwd_reg_kernel<V><<<reg_grid, 256, 0, st>>>((const bf16*)x, (const bf16*)res, gamma, beta, (bf16*)y,    \
+      launch_pdl(ln_fwd_reg_kernel<V>, dim3(reg_grid), dim3(256), 0, st, (const bf16*)x, (const bf16*)res, gamma, beta, (bf16*)y,    \
                                                      (bf16*)sum_out, mean, rstd, rows, (int)cols, eps, rms_only, \
                                                      act);                                                       \
     } else {                                                                                                     \
       SMX_CHECK_CUDA(ring_attr(ln_fwd_kernel<V>));                                                               \
-      ln_fwd_kernel<V><<<rp.grid, 256, rp.smem, st>>>((const bf16*)x, (const bf16*)res, gamma, beta, (bf16*)y,   \
+      launch_pdl(ln_fwd_kernel<V>, dim3(rp.grid), dim3(256), rp.smem, st, (const bf16*)x, (const bf16*)res, gamma, beta, (bf16*)y,   \
                                                       (bf16*)sum_out, mean, rstd, rows, (int)cols, eps, rms_only, \
                                                       act, rp.stages);                                           \
     }                                                                                                            \
@@ -1093,12 +1143,12 @@ int smx_layernorm_bwd(const void* dy, const void* x, const float* gamma, const f
 #define LN_BWD_LAUNCH(V, C)                                                                                        \
   do {                                                                                                             \
     if (dres_in == nullptr) {                                                                                      \
-      ln_bwd_reg_kernel<V, C><<<reg_grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)x, gamma, beta, mean, rstd,  \
+      launch_pdl(ln_bwd_reg_kernel<V, C>, dim3(reg_grid), dim3(256), 0, st, (const bf16*)dy, (const bf16*)x, gamma, beta, mean, rstd,  \
                                                         (const bf16*)dres_in, (bf16*)dx, dgamma, dbeta, dx_colsum, \
                                                         rows, (int)cols, rms_only, act);                           \
     } else {                                                                                                       \
       SMX_CHECK_CUDA(ring_attr(ln_bwd_kernel<V, C>));                                                              \
-      ln_bwd_kernel<V, C><<<rp.grid, 256, rp.smem, st>>>((const bf16*)dy, (const bf16*)x, gamma, beta, mean, rstd, \
+      launch_pdl(ln_bwd_kernel<V, C>, dim3(rp.grid), dim3(256), rp.smem, st, (const bf16*)dy, (const bf16*)x, gamma, beta, mean, rstd, \
                                                          (const bf16*)dres_in, (bf16*)dx, dgamma, dbeta, dx_colsum, \
                                                          rows, (int)cols, rms_only, act, rp.stages);               \
     }                                                                                                              \
@@ -1125,7 +1175,7 @@ int smx_mask_rows(void* x, const int32_t* len, int64_t batch, int64_t t, int64_t
               "mask_rows: columns / strides must be multiples of 8 elements and x 16-byte aligned");
   if (batch == 0 || t == 0 || col_count == 0) return 0;
   const int vec = (int)(col_count / 8);
-  mask_rows_kernel<<<grid_for(batch * t * vec, 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(mask_rows_kernel, dim3(grid_for(batch * t * vec, 256)), dim3(256), 0, (cudaStream_t)stream, 
       (bf16*)x, len, batch, t, row_stride, batch_stride, (int)col_begin, vec);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -1140,7 +1190,7 @@ int smx_dropout(const void* x, const void* residual, void* out, const void* aux_
   SMX_REQUIRE(aligned16(x) && aligned16(out) && aligned16(residual) && aligned16(aux_in) && aligned16(aux_out),
               "dropout: operands must be 16-byte aligned");
   if (n == 0) return 0;
-  dropout_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)residual, (bf16*)out,
+  launch_pdl(dropout_kernel, dim3(grid_for(n / 8, 256)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, (const bf16*)residual, (bf16*)out,
                                                                        (const bf16*)aux_in, (bf16*)aux_out, aux_mode, n / 8,
                                                                        (const unsigned long long*)state, call, p);
   SMX_CHECK_CUDA(cudaGetLastError());
@@ -1151,7 +1201,7 @@ int smx_dropout_mask(uint8_t* mask, int64_t n, int64_t tk, int mode, const uint6
                      void* stream) {
   SMX_REQUIRE(mask && state && (mode == 0 || (mode == 1 && tk > 0)), "dropout_mask: bad arguments");
   if (n == 0) return 0;
-  dropout_mask_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(mask, n, tk, mode, (const unsigned long long*)state,
+  launch_pdl(dropout_mask_kernel, dim3(grid_for(n, 256)), dim3(256), 0, (cudaStream_t)stream, mask, n, tk, mode, (const unsigned long long*)state,
                                                                          call, p);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -1162,7 +1212,7 @@ int smx_spec_augment_fwd(const void* x, void* y, const uint8_t* time_mask, const
   SMX_REQUIRE(x && y && hidden % 8 == 0 && aligned16(x) && aligned16(y), "spec_augment: bad arguments");
   SMX_REQUIRE(time_mask == nullptr || (embed != nullptr && aligned16(embed)), "spec_augment: time mask needs the embedding");
   if (batch * t == 0) return 0;
-  spec_augment_fwd_kernel<<<grid_for(batch * t * (hidden / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(spec_augment_fwd_kernel, dim3(grid_for(batch * t * (hidden / 8), 256)), dim3(256), 0, (cudaStream_t)stream, 
       (const bf16*)x, (bf16*)y, time_mask, feat_mask, embed, batch * t, t, (int)hidden);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -1172,12 +1222,12 @@ int smx_spec_augment_bwd(const void* dy, void* dx, float* dembed, const uint8_t*
   SMX_REQUIRE(dy && dx && hidden % 8 == 0 && aligned16(dy) && aligned16(dx), "spec_augment_bwd: bad arguments");
   if (batch * t == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  spec_augment_bwd_kernel<<<grid_for(batch * t * (hidden / 8), 256), 256, 0, st>>>(
+  launch_pdl(spec_augment_bwd_kernel, dim3(grid_for(batch * t * (hidden / 8), 256)), dim3(256), 0, st, 
       (const bf16*)dy, (bf16*)dx, time_mask, feat_mask, batch * t, t, (int)hidden);
   SMX_CHECK_CUDA(cudaGetLastError());
   if (dembed && time_mask) {   // dembed is zero-initialised by the caller
     long long gy = batch * t < 592 ? batch * t : 592;
-    spec_augment_dembed_kernel<<<dim3((unsigned)ceil_div(hidden, 256), (unsigned)gy), 256, 0, st>>>(
+    launch_pdl(spec_augment_dembed_kernel, dim3(dim3((unsigned)ceil_div(hidden, 256), (unsigned)gy)), dim3(256), 0, st, 
         (const bf16*)dy, dembed, time_mask, feat_mask, batch * t, t, (int)hidden);
     SMX_CHECK_CUDA(cudaGetLastError());
   }
@@ -1191,7 +1241,7 @@ int smx_colsum(const void* x, float* out, int64_t rows, int64_t cols, int64_t ro
   long long gy = ceil_div(rows, 8 * 16);
   const long long cap = (long long)num_sms() * 4 / gx + 1;
   if (gy > cap) gy = cap;
-  colsum_kernel<<<dim3(gx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, out, rows, (int)cols,
+  launch_pdl(colsum_kernel, dim3(dim3(gx, (unsigned)gy)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, out, rows, (int)cols,
                                                                           row_stride);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -1201,13 +1251,13 @@ int smx_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
   if (n == 0) return 0;
   SMX_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
               "cast: pointers must be 16-byte aligned");
-  cast_kernel<<<grid_for(ceil_div(n, 8), 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
+  launch_pdl(cast_kernel, dim3(grid_for(ceil_div(n, 8), 256)), dim3(256), 0, (cudaStream_t)stream, src, (bf16*)dst, n);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int smx_multi_cast(const SmxCastEntry* table, int32_t n_entries, int32_t total_chunks, void* stream) {
   if (n_entries <= 0 || total_chunks <= 0) return 0;
-  multi_cast_kernel<<<total_chunks, 256, 0, (cudaStream_t)stream>>>(table, n_entries);
+  launch_pdl(multi_cast_kernel, dim3(total_chunks), dim3(256), 0, (cudaStream_t)stream, table, n_entries);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1217,9 +1267,9 @@ int smx_weightnorm_fwd(const float* v, const float* g, float* sq_ws, float* w, i
   SMX_CHECK_CUDA(cudaMemsetAsync(sq_ws, 0, sizeof(float) * k, st));
   long long gy = ceil_div(rows, 8 * 32);
   if (gy > 512) gy = 512;
-  wn_colstat_kernel<<<dim3((unsigned)ceil_div(k, 32), (unsigned)gy), 256, 0, st>>>(v, nullptr, sq_ws, rows, (int)k);
+  launch_pdl(wn_colstat_kernel, dim3(dim3((unsigned)ceil_div(k, 32), (unsigned)gy)), dim3(256), 0, st, v, nullptr, sq_ws, rows, (int)k);
   SMX_CHECK_CUDA(cudaGetLastError());
-  wn_fwd_kernel<<<grid_for(rows * k, 256), 256, 0, st>>>(v, g, sq_ws, w, rows * k, (int)k);
+  launch_pdl(wn_fwd_kernel, dim3(grid_for(rows * k, 256)), dim3(256), 0, st, v, g, sq_ws, w, rows * k, (int)k);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1230,15 +1280,15 @@ int smx_weightnorm_bwd(const float* v, const float* g, const float* sq, const fl
   SMX_CHECK_CUDA(cudaMemsetAsync(dot_ws, 0, sizeof(float) * k, st));
   long long gy = ceil_div(rows, 8 * 32);
   if (gy > 512) gy = 512;
-  wn_colstat_kernel<<<dim3((unsigned)ceil_div(k, 32), (unsigned)gy), 256, 0, st>>>(dw, v, dot_ws, rows, (int)k);
+  launch_pdl(wn_colstat_kernel, dim3(dim3((unsigned)ceil_div(k, 32), (unsigned)gy)), dim3(256), 0, st, dw, v, dot_ws, rows, (int)k);
   SMX_CHECK_CUDA(cudaGetLastError());
-  wn_bwd_kernel<<<grid_for(rows * k, 256), 256, 0, st>>>(v, g, sq, dot_ws, dw, dv, dg, rows * k, (int)k);
+  launch_pdl(wn_bwd_kernel, dim3(grid_for(rows * k, 256)), dim3(256), 0, st, v, g, sq, dot_ws, dw, dv, dg, rows * k, (int)k);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int smx_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream) {
   if (n == 0) return 0;
-  add_kernel<<<grid_for(ceil_div(n, 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)a, (const bf16*)b,
+  launch_pdl(add_kernel, dim3(grid_for(ceil_div(n, 8), 256)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)a, (const bf16*)b,
                                                                               (bf16*)out, n);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -1246,25 +1296,25 @@ int smx_add_bf16(const void* a, const void* b, void* out, int64_t n, void* strea
 int smx_act_bf16(const void* x, void* y, int64_t n, int act, void* stream) {
   if (n == 0) return 0;
   SMX_REQUIRE(n % 8 == 0, "act: n must be a multiple of 8");
-  act_kernel<<<grid_for(ceil_div(n, 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, n, act);
+  launch_pdl(act_kernel, dim3(grid_for(ceil_div(n, 8), 256)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, (bf16*)y, n, act);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int smx_dact_bf16(const void* dy, const void* pre, void* out, int64_t n, int act, void* stream) {
   if (n == 0) return 0;
   SMX_REQUIRE(n % 8 == 0, "dact: n must be a multiple of 8");
-  dact_kernel<<<grid_for(ceil_div(n, 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, (const bf16*)pre,
+  launch_pdl(dact_kernel, dim3(grid_for(ceil_div(n, 8), 256)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)dy, (const bf16*)pre,
                                                                                (bf16*)out, n, act);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int smx_pack_conv_weight(const float* src, void* dst, int64_t cout, int64_t cin, int64_t k, void* stream) {
-  pack_conv_w_kernel<<<grid_for(cout * cin * k, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, cout, cin, k);
+  launch_pdl(pack_conv_w_kernel, dim3(grid_for(cout * cin * k, 256)), dim3(256), 0, (cudaStream_t)stream, src, (bf16*)dst, cout, cin, k);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int smx_unpack_conv_wgrad(const float* src, float* dst, int64_t cout, int64_t cin, int64_t k, void* stream) {
-  unpack_conv_g_kernel<<<grid_for(cout * cin * k, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, cout, cin, k);
+  launch_pdl(unpack_conv_g_kernel, dim3(grid_for(cout * cin * k, 256)), dim3(256), 0, (cudaStream_t)stream, src, dst, cout, cin, k);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1275,7 +1325,7 @@ int smx_embed_fwd(const int64_t* ids, const float* tok_emb, const float* pos_emb
   SMX_REQUIRE(dim % 8 == 0, "embed: dim must be a multiple of 8");
   const long long rows = batch * t;
   if (rows == 0) return 0;
-  embed_fwd_kernel<<<grid_for(rows * (dim / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(embed_fwd_kernel, dim3(grid_for(rows * (dim / 8), 256)), dim3(256), 0, (cudaStream_t)stream, 
       (const long long*)ids, tok_emb, pos_emb, (const bf16*)x_in, (bf16*)out, rows, t, (int)dim, scale,
       pos_offset + t_start);
   SMX_CHECK_CUDA(cudaGetLastError());
@@ -1286,7 +1336,7 @@ int smx_embed_bwd(const int64_t* ids, const void* dout, float* d_tok_emb, float*
   SMX_REQUIRE(dim % 8 == 0, "embed: dim must be a multiple of 8");
   const long long rows = batch * t;
   if (rows == 0) return 0;
-  embed_bwd_kernel<<<grid_for(rows * (dim / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(embed_bwd_kernel, dim3(grid_for(rows * (dim / 8), 256)), dim3(256), 0, (cudaStream_t)stream, 
       (const long long*)ids, (const bf16*)dout, d_tok_emb, d_pos_emb, rows, t, (int)dim, scale, pos_offset);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -1297,7 +1347,7 @@ int smx_weighted_sum_fwd(const void* const* xs, const float* w, void* out, int n
   SMX_REQUIRE(n % 8 == 0, "weighted_sum: n must be a multiple of 8");
   PtrPack pk;
   for (int l = 0; l < n_layers; ++l) pk.p[l] = (const bf16*)xs[l];
-  wsum_fwd_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(pk, w, (bf16*)out, n_layers, n);
+  launch_pdl(wsum_fwd_kernel, dim3(grid_for(n / 8, 256)), dim3(256), 0, (cudaStream_t)stream, pk, w, (bf16*)out, n_layers, n);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1307,7 +1357,7 @@ int smx_weighted_sum_bwd_w(const void* const* xs, const void* dout, float* dw, i
   SMX_REQUIRE(n % 8 == 0, "weighted_sum: n must be a multiple of 8");
   PtrPack pk;
   for (int l = 0; l < n_layers; ++l) pk.p[l] = (const bf16*)xs[l];
-  wsum_bwd_w_kernel<<<grid_for(n / 8, 256, 2), 256, 0, (cudaStream_t)stream>>>(pk, (const bf16*)dout, dw, n_layers, n);
+  launch_pdl(wsum_bwd_w_kernel, dim3(grid_for(n / 8, 256, 2)), dim3(256), 0, (cudaStream_t)stream, pk, (const bf16*)dout, dw, n_layers, n);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

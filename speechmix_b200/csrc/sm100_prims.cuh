@@ -480,4 +480,39 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  Every hot kernel is launched with the programmatic-stream-serialisation attribute
+// (launch_pdl below; captured into the whole-step CUDA graph as a programmatic edge): its CTAs may become resident while
+// the previous kernel of the stream is still draining, so launch latency, block scheduling and the on-chip prologue
+// (barrier init, TMEM allocation, descriptor prefetch) overlap the predecessor's tail.  Contract, kept by every kernel
+// launched this way:
+//   * pdl_trigger() first (lets the NEXT kernel's CTAs be scheduled once all of ours have started -- they can never
+//     displace our own pending CTAs);
+//   * pdl_wait() executed by EVERY thread before its first global-memory access of any kind (reads of the producer's
+//     output, and writes -- the predecessor may still be reading what we overwrite).  It returns when the prerequisite
+//     grid has completed and its memory is visible; since every kernel in the chain waits, ordering is transitive.
+//   Kernel parameters and __grid_constant__ tensor maps live in constant / parameter space and may be touched earlier.
+// Launched WITHOUT the attribute (SMX_PDL=0, or by anyone else) both instructions are no-ops.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();   // host_common.cu: SMX_PDL != "0" (read once)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 }  // namespace smx

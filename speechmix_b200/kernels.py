@@ -287,6 +287,70 @@ def conv_s2_wgrad(dy, x, k):
     return dw
 
 
+# ---------------------------------------------------------------------------
+# non-overlapping Conv1d (kernel = stride = S) on channels-last activations: a frame group [S*C] is contiguous, so the
+# convolution is a plain batched GEMM over the [B][T // S][S*C] view of x (batch stride T*C; the T % S tail frames are
+# never touched) -- no slack frame, no staging copy.  Used for the down_scale bridge (ops.BridgeProjFn).
+# ---------------------------------------------------------------------------
+def conv_ks_fwd(x, w, s, bias=None):
+    """y[B, T//s, N] = x-groups @ w^T + bias;  w: [N, s*C] bf16 (tap-major)."""
+    B, T, C = x.shape
+    N, KC = w.shape
+    T_out = T // s
+    assert KC == s * C and C % 8 == 0 and x.is_contiguous() and w.is_contiguous() and T_out > 0
+    y = torch.empty(B, T_out, N, device=x.device, dtype=BF16)
+    g = SmxGemm()
+    g.mode, g.out_dtype = GEMM_NT, OUT_BF16
+    g.a = _view(x, KC, T_out, B, KC, T * C)
+    g.b = _view(w, KC, N, 1, KC, N * KC)
+    g.m, g.n, g.k, g.batches = T_out, N, KC, B
+    _set_seg(g, 1, KC)
+    _epilogue(g, y, N, T_out * N, bias, ACT_NONE, None, None, None, None, 1.0)
+    _run_gemm(g, "bridge_nt_%d_%d_%d" % (B * T_out, N, KC), 2.0 * B * T_out * N * KC)
+    return y
+
+
+def conv_ks_dgrad(dy, w, s, t_in):
+    """dx[B, t_in, C] = dy[B, T_out, N] @ w[N, s*C], scattered back into frame groups; tail frames get zero."""
+    B, T_out, N = dy.shape
+    KC = w.shape[1]
+    C = KC // s
+    assert dy.is_contiguous() and w.shape[0] == N and N % 8 == 0
+    dx = torch.empty(B, t_in, C, device=dy.device, dtype=BF16)
+    if t_in > T_out * s:
+        dx[:, T_out * s:].zero_()
+    g = SmxGemm()
+    g.mode, g.out_dtype = GEMM_NN, OUT_BF16
+    g.a = _view(dy, N, T_out, B, N, T_out * N)
+    g.b = _view(w, KC, N, 1, KC, N * KC)
+    g.m, g.n, g.k, g.batches = T_out, KC, N, B
+    _set_seg(g, 1, N)
+    _epilogue(g, dx, KC, t_in * C, None, ACT_NONE, None, None, None, None, 1.0)
+    _run_gemm(g)
+    return dx
+
+
+def conv_ks_wgrad(dy, x, s):
+    """dw[N, s*C] fp32 = sum_{b,t} dy[b,t,:]^T x-group[b,t,:]."""
+    B, T_out, N = dy.shape
+    _, T, C = x.shape
+    KC = s * C
+    g = SmxGemm()
+    g.mode, g.out_dtype = GEMM_TN, OUT_F32
+    g.a = _view(dy, N, T_out, B, N, T_out * N)
+    g.b = _view(x, KC, T_out, B, KC, T * C)
+    g.m, g.n, g.k, g.batches = N, KC, T_out, B
+    _set_seg(g, 1, KC)
+    tiles = math.ceil(N / 256) * math.ceil(KC / 256)
+    g.split_k = _pick_split(tiles, B * math.ceil(T_out / 64))
+    dw = zeros_f32(N, KC, device=dy.device) if g.split_k > 1 else torch.empty(N, KC, device=dy.device, dtype=torch.float32)
+    g.c = _ptr(dw)
+    g.c_row_stride, g.c_batch_stride = KC, N * KC
+    g.alpha = 1.0
+    _run_gemm(g)
+    return dw
+
+
 def pack_conv_weight(w):
     """[out, in, k] fp32 -> [out, k*in] bf16 (tap-major)."""
     if FP32_MODE:

@@ -224,12 +224,30 @@ class SpeechMixEED(nn.Module):
             x = ops.WeightedSumFn.apply(norm_weights, *encoder_outputs.hidden_states)
         if detail is not None:
             detail["shape_before_length_adapter"] = x.shape
+        proj = self.enc_to_dec_proj
+        fused = False
         if self.downsize > 1:
-            for conv in self.length_adapters:
-                x = ops.ConvS2Fn.apply(x, conv.weight, conv.bias, 2)
+            convs = list(self.length_adapters)
+            if ops.K.FP32_MODE:                      # fp32 verification mode: the plain per-layer kernels
+                for conv in convs:
+                    x = ops.ConvS2Fn.apply(x, conv.weight, conv.bias, 2)
+            else:
+                for conv in convs[:-1]:
+                    x = ops.ConvK2Fn.apply(x, conv.weight, conv.bias)
+                last = convs[-1]
+                # last length adapter + projector: one linear map of a frame pair -> ONE GEMM launch (ops.BridgeProjFn)
+                fused = ops.bridge_fusion_pays(x.shape[0] * (x.shape[1] // 2), x.shape[2])
+                if detail is not None:
+                    detail["bridge_fused"] = fused
+                if not fused:
+                    x = ops.ConvK2Fn.apply(x, last.weight, last.bias)
         if detail is not None:
-            detail["shape_before_enc_dec_projector"] = x.shape
-        x = ops.linear(x, self.enc_to_dec_proj.weight, self.enc_to_dec_proj.bias)
+            detail["shape_before_enc_dec_projector"] = (torch.Size((x.shape[0], x.shape[1] // 2, x.shape[2])) if fused
+                                                        else x.shape)
+        if fused:
+            x = ops.BridgeProjFn.apply(x, last.weight, last.bias, proj.weight, proj.bias)
+        else:
+            x = ops.linear(x, proj.weight, proj.bias)
         if detail is not None:
             detail["shape_after_enc_dec_projector"] = x.shape
         return x

@@ -682,6 +682,88 @@ class ConvS2Fn(torch.autograd.Function):
         return dx, dw, db, None
 
 
+class ConvK2Fn(torch.autograd.Function):
+    """Conv1d(C -> N, kernel 2, stride 2, bias) on channels-last input through the copy-free frame-group view
+    (K.conv_ks_*): the non-final down_scale length adapters (ref:speechmix/hf_model.py:253-266, 426-427)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = x.contiguous()
+        wp = conv_packed16(weight)
+        y = K.conv_ks_fwd(x, wp, 2, bias=None if bias is None else bias.detach())
+        ctx.save_for_backward(x, wp)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wp = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = K.conv_ks_dgrad(dy, wp, 2, x.shape[1]) if _need(ctx, 0) else None
+        dw = K.unpack_conv_wgrad(K.conv_ks_wgrad(dy, x, 2), x.shape[2], 2) if _need(ctx, 1) else None
+        db = K.colsum(dy.view(-1, dy.shape[-1])) if _need(ctx, 2) else None
+        return dx, dw, db
+
+
+class BridgeProjFn(torch.autograd.Function):
+    """The last down_scale length adapter and the encoder-to-decoder projector as ONE kernel launch.
+
+    ref:speechmix/hf_model.py:426-430 runs ``enc_to_dec_proj(length_adapters(x))`` with NO non-linearity in between
+    (ref :253-272: bare Conv1d(k 2, s 2) layers, then nn.Linear), so the pair is a single linear map of a frame pair:
+
+        y[t] = Wp (W[:, :, 0] x[2t] + W[:, :, 1] x[2t+1] + b) + bp  =  W_eff [x[2t] ; x[2t+1]] + b_eff
+        W_eff = Wp . pack(W)   [D, 2C]          b_eff = bp + Wp b
+
+    W_eff is a weight-sized product (one small GEMM per step, D.C.2C MACs); the activations then go through ONE implicit
+    GEMM over the copy-free frame-pair view instead of conv GEMM -> HBM round trip of the [B, T/2, C] intermediate ->
+    projector GEMM: a third fewer MACs on the activations and no intermediate tensor (forward) / no intermediate
+    gradient (backward).  Backward: dx, G = dW_eff (fp32) and db_eff come from the usual NN / TN / column-sum kernels;
+    the two weight gradients follow from G with two more weight-sized GEMMs (dWp = G pack(W)^T, dpack(W) = Wp^T G).
+    The caller (model.bridge) takes this path when it saves work: rows_out >= 4 C (ops.bridge_fusion_pays)."""
+
+    @staticmethod
+    def forward(ctx, x, cw, cb, pw, pb):
+        x = x.contiguous()
+        P = conv_packed16(cw)                       # [C, 2C] bf16, tap-major
+        pw16 = w16(pw)                              # [D, C]
+        w_eff = K.linear_dgrad(pw16, P)             # [D, 2C] = pw16 @ P   (NN GEMM, fp32 accumulation, bf16 out)
+        b_eff = torch.addmv(pb.detach(), pw.detach(), cb.detach())
+        y = K.conv_ks_fwd(x, w_eff, 2, bias=b_eff)
+        ctx.save_for_backward(x, w_eff, P, pw16, cb.detach(), pw.detach())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w_eff, P, pw16, cb, pw = ctx.saved_tensors
+        dy = dy.contiguous()
+        C, D = x.shape[2], dy.shape[2]
+        dx = K.conv_ks_dgrad(dy, w_eff, 2, x.shape[1]) if _need(ctx, 0) else None
+        dcw = dcb = dpw = dpb = None
+        if any(_need(ctx, i) for i in (1, 2, 3, 4)):
+            G16 = K.to_bf16(K.conv_ks_wgrad(dy, x, 2))            # dW_eff [D, 2C]
+            db_eff = K.colsum(dy.view(-1, D))
+            if _need(ctx, 3):
+                dpw = K.linear_fwd(G16, P, out_f32=True)          # G P^T  [D, C]
+                dpw.addr_(db_eff, cb)                             # b_eff = bp + Wp b
+            if _need(ctx, 1):
+                dcw = K.unpack_conv_wgrad(K.linear_wgrad(pw16, G16), C, 2)   # Wp^T G  [C, 2C] -> [C, C, 2]
+            if _need(ctx, 2):
+                dcb = torch.mv(pw.t(), db_eff)
+            if _need(ctx, 4):
+                dpb = db_eff
+        return dx, dcw, dcb, dpw, dpb
+
+
+def bridge_fusion_pays(rows_out, channels):
+    """composing W_eff costs D.C.2C MACs forward (3x that with the two backward products); folding the projector into
+    the conv saves rows_out.D.C MACs forward (and as much again in each backward product)."""
+    if K.FP32_MODE or BRIDGE_FUSION == "never":
+        return False
+    return BRIDGE_FUSION == "always" or rows_out >= 4 * channels
+
+
+BRIDGE_FUSION = "auto"     # "auto" | "always" | "never"  (the GPU tests pin both paths on the small fixtures)
+
+
 class WeightNormFn(torch.autograd.Function):
     """w = g * v / ||v||  with one norm per kernel tap (torch weight_norm(dim=2) on the positional conv,
     hf:...wav2vec2.py:341-355); g = parametrizations.weight.original0 [1,1,k], v = original1 [H, H/groups, k]."""

@@ -1,6 +1,6 @@
 """Fused Adafactor: the optimizer of the reference recipe (ref:train.py:298 ``optim="adafactor"``; the HF Trainer builds
-``transformers.optimization.Adafactor(lr=..., scale_parameter=False, relative_step=False)``), as FOUR kernel launches
-per step over all parameters (``smx_adafactor_step``, csrc/adafactor.cu) instead of ~15 small launches per parameter.
+``transformers.optimization.Adafactor(lr=..., scale_parameter=False, relative_step=False)``), as SIX kernel launches
+per step over all parameters (four over a tile table, two block-per-slice launches for the small factored slices) (``smx_adafactor_step``, csrc/adafactor.cu) instead of ~15 small launches per parameter.
 
 State layout and names follow the transformers implementation (``step``, ``exp_avg_sq_row``, ``exp_avg_sq_col``,
 ``exp_avg_sq``, ``RMS``), so optimizer checkpoints are interchangeable.  Only the configuration the reference uses is
@@ -15,6 +15,11 @@ import torch
 from . import _lib
 
 TILE_R, TILE_C = 64, 256
+SMALL_ELEMS, SMALL_RC = 16384, 4096     # csrc/adafactor.cu: block-per-slice path for small factored slices
+
+
+def is_small_slice(rows, cols):
+    return rows * cols <= SMALL_ELEMS and rows + cols <= SMALL_RC
 
 
 def factored_dims(shape):
@@ -32,16 +37,23 @@ def factored_dims(shape):
 
 
 def tile_table(shapes):
-    """int32 [n_tiles, 4] (tensor, b, r0, c0) covering every element of every tensor exactly once with 64 x 256 tiles
-    (vectors are viewed as [ceil(n / 256), 256]); int32 [n_slices, 2] (tensor, b) for the factored tensors."""
-    tiles, slices = [], []
+    """int32 [n_tiles, 4] (tensor, b, r0, c0) covering every element of every LARGE tensor exactly once with 64 x 256
+    tiles (vectors are viewed as [ceil(n / 256), 256]); int32 [n_slices, 2] (tensor, b) for the large factored tensors;
+    int32 [n_small, 2] (tensor, b) for the factored slices that take the block-per-slice kernels instead of tiles
+    (``is_small_slice``: a [512][3] convolution-weight slice would otherwise be eight near-empty tiles); and the
+    shared-memory floats the largest of those needs."""
+    tiles, slices, small, small_floats = [], [], [], 0
     for i, shape in enumerate(shapes):
         factored, batch, rows, cols = factored_dims(shape)
+        b = np.arange(batch, dtype=np.int32)
+        if factored and is_small_slice(rows, cols):
+            small.append(np.stack([np.full(batch, i, np.int32), b], 1))
+            small_floats = max(small_floats, rows * cols + rows + cols)
+            continue
         if not factored:
             rows, cols = (cols + TILE_C - 1) // TILE_C, TILE_C
         r0 = np.arange(0, max(rows, 1), TILE_R, dtype=np.int32)
         c0 = np.arange(0, max(cols, 1), TILE_C, dtype=np.int32)
-        b = np.arange(batch, dtype=np.int32)
         bb, rr, cc = np.meshgrid(b, r0, c0, indexing="ij")
         t = np.stack([np.full(bb.size, i, np.int32), bb.ravel(), rr.ravel(), cc.ravel()], 1)
         tiles.append(t)
@@ -49,7 +61,8 @@ def tile_table(shapes):
             slices.append(np.stack([np.full(batch, i, np.int32), b], 1))
     tiles = np.concatenate(tiles, 0) if tiles else np.zeros((0, 4), np.int32)
     slices = np.concatenate(slices, 0) if slices else np.zeros((0, 2), np.int32)
-    return np.ascontiguousarray(tiles), np.ascontiguousarray(slices)
+    small = np.concatenate(small, 0) if small else np.zeros((0, 2), np.int32)
+    return np.ascontiguousarray(tiles), np.ascontiguousarray(slices), np.ascontiguousarray(small), int(small_floats)
 
 
 _TENSOR_DTYPE = np.dtype([("p", "<u8"), ("g", "<u8"), ("row", "<u8"), ("col", "<u8"), ("row_acc", "<u8"),
@@ -65,10 +78,12 @@ class _Plan:
     def __init__(self, params, states):
         dev = params[0].device
         self.shapes = [tuple(p.shape) for p in params]
-        tiles, slices = tile_table(self.shapes)
-        self.n_tiles, self.n_slices = int(tiles.shape[0]), int(slices.shape[0])
-        self.tiles = torch.from_numpy(tiles).to(dev)
-        self.slices = torch.from_numpy(slices).to(dev) if self.n_slices else torch.zeros(1, 2, dtype=torch.int32, device=dev)
+        tiles, slices, small, self.small_floats = tile_table(self.shapes)
+        self.n_tiles, self.n_slices, self.n_small = int(tiles.shape[0]), int(slices.shape[0]), int(small.shape[0])
+        pad = torch.zeros(1, 4, dtype=torch.int32, device=dev)
+        self.tiles = torch.from_numpy(tiles).to(dev) if self.n_tiles else pad
+        self.slices = torch.from_numpy(slices).to(dev) if self.n_slices else pad
+        self.small = torch.from_numpy(small).to(dev) if self.n_small else pad
         # scratch (floats): per tensor row_acc [batch*rows] | col_acc [batch*cols] | sumsq [1]; rmean separately
         dims = [factored_dims(shape) for shape in self.shapes]
         n = sum((b * r + b * c if f else 0) + 1 for f, b, r, c in dims)
@@ -166,7 +181,8 @@ class FusedAdafactor(torch.optim.Optimizer):
                 plan.uploaded.record()
                 beta2t = 1.0 - math.pow(step_no, group["decay_rate"])
                 rc = lib.smx_adafactor_step(plan.table.data_ptr(), len(params), plan.tiles.data_ptr(), plan.n_tiles,
-                                            plan.slices.data_ptr(), plan.n_slices, plan.scratch.data_ptr(),
+                                            plan.slices.data_ptr(), plan.n_slices, plan.small.data_ptr(), plan.n_small,
+                                            plan.small_floats, plan.scratch.data_ptr(),
                                             plan.scratch.numel() * 4, beta2t, group["eps"][0], group["lr"],
                                             group["clip_threshold"], group["weight_decay"],
                                             torch.cuda.current_stream().cuda_stream)

@@ -149,12 +149,15 @@ def test_dropout_sites_are_discovered_from_the_configs():
 
 
 def test_adafactor_tile_table_covers_every_element_once():
-    """speechmix_b200/optim.py: the 64 x 256 tile table of the fused Adafactor step (host logic, no GPU)."""
+    """speechmix_b200/optim.py: the 64 x 256 tile table of the fused Adafactor step plus the block-per-slice list for
+    small factored slices (host logic, no GPU): every element is owned by exactly one tile OR one small slice."""
     import numpy as np
-    from speechmix_b200.optim import TILE_C, TILE_R, factored_dims, tile_table
-    shapes = [(768,), (1,), (1000, 768), (512, 512, 3), (512, 1, 10), (768, 48, 128), (1, 50265), (7, 3, 65, 257), (300,)]
-    tiles, slices = tile_table(shapes)
-    assert tiles.dtype == np.int32 and slices.dtype == np.int32
+    from speechmix_b200.optim import TILE_C, TILE_R, factored_dims, is_small_slice, tile_table
+    shapes = [(768,), (1,), (1000, 768), (512, 512, 3), (512, 1, 10), (768, 48, 128), (1, 50265), (7, 3, 65, 257), (300,),
+              (3, 5000, 3), (2, 128, 128), (2, 129, 128)]
+    tiles, slices, small, small_floats = tile_table(shapes)
+    assert tiles.dtype == np.int32 and slices.dtype == np.int32 and small.dtype == np.int32
+    want_floats = 0
     for i, shape in enumerate(shapes):
         factored, batch, rows, cols = factored_dims(shape)
         n = int(np.prod(shape))
@@ -167,8 +170,17 @@ def test_adafactor_tile_table_covers_every_element_once():
             else:
                 idx = np.arange(r0 * TILE_C, min((r0 + TILE_R) * TILE_C, n))
             cover[idx] += 1
+        for (_, b) in small[small[:, 0] == i]:
+            cover[b * rows * cols:(b + 1) * rows * cols] += 1
         assert (cover == 1).all(), shape
-        assert (slices[:, 0] == i).sum() == (batch if factored else 0)
+        is_small = factored and is_small_slice(rows, cols)
+        assert (slices[:, 0] == i).sum() == (batch if factored and not is_small else 0)
+        assert (small[:, 0] == i).sum() == (batch if is_small else 0)
+        if is_small:
+            want_floats = max(want_floats, rows * cols + rows + cols)
+    assert small_floats == want_floats
+    assert is_small_slice(512, 3) and is_small_slice(48, 128) and is_small_slice(1, 10) and is_small_slice(128, 128)
+    assert not is_small_slice(129, 128) and not is_small_slice(5000, 3) and not is_small_slice(768, 768)
     assert factored_dims((4, 5, 6)) == (True, 4, 5, 6) and factored_dims((9,)) == (False, 1, 1, 9)
 
 

@@ -39,7 +39,7 @@ def test_binding_table_matches_header(lib_path):
     from speechmix_b200 import _lib
     assert sorted(_lib.SIGNATURES) == declared_symbols()
     lib = _lib.load()
-    assert lib.smx_abi_version() == 2
+    assert lib.smx_abi_version() == 3
 
 
 def test_struct_layout_matches_c():

@@ -73,6 +73,38 @@ def test_eed_matches_oracle(name, cuda_device):
         assert checked == len(mine.list_grad)
 
 
+@pytest.mark.parametrize("name", ["mini_eed_ds2", "mini_eed_ds8_ws", "mini_large_mbart"])
+@pytest.mark.parametrize("mode", ["always", "never"])
+def test_bridge_projector_fusion_matches_oracle(name, mode, cuda_device):
+    """ops.BridgeProjFn: last length adapter + enc_to_dec_proj as ONE GEMM with W_eff = Wp.pack(W) (exact algebra of
+    ref:speechmix/hf_model.py:426-430, which has no non-linearity between the two).  The small fixtures would take the
+    unfused path on their own (rows_out < 4 C), so both paths are forced here and held to the same bounds: loss, logits,
+    and the gradients of every bridge parameter -- the ones the chain rule through W_eff has to get right."""
+    from speechmix_b200 import ops
+    fx = load_fixture(name)
+    ora, x, labels = build_oracle(fx)
+    mine = _mine_from(ora, fx, cuda_device)
+    ref = ora(x, labels=labels, keep_full_logits=True)
+    prev, ops.BRIDGE_FUSION = ops.BRIDGE_FUSION, mode
+    try:
+        out = mine(x.to(cuda_device), labels=labels.to(cuda_device))
+        assert bool(out["bridge_fused"]) == (mode == "always")
+        assert abs(float(out["loss"]) - float(ref["loss"])) < 3e-3
+        assert _rel(mine.decoder_model.full_logits(out["decoder_last_hidden_state"]), ref["full_logits"]) < 2e-2
+        assert tuple(out["shape_before_enc_dec_projector"]) == tuple(ref["detail"]["shape_before_enc_dec_projector"])
+        ref["loss"].backward()
+        out["loss"].backward()
+    finally:
+        ops.BRIDGE_FUSION = prev
+    po, pm = dict(ora.named_parameters()), dict(mine.named_parameters())
+    keys = [k for k in po if k.startswith("length_adapters") or k.startswith("enc_to_dec_proj") or k == "weights_sum"
+            or k.endswith("layers.0.attention.q_proj.weight")]
+    assert len(keys) >= 5
+    for k in keys:
+        g, r = pm[k].grad.cpu(), po[k].grad
+        assert float((g - r).norm()) <= 5e-2 * float(r.norm()) + 1e-7, (k, float((g - r).norm()), float(r.norm()))
+
+
 def test_mbart_pre_ln_stack(cuda_device):
     fx = dict(load_fixture("mini_eed_ds2"), text="mbart-mini", kwargs={"down_scale": 4})
     ora, x, labels = build_oracle(fx)
@@ -204,22 +236,30 @@ def test_adapter_and_self_match_reference_goldens(name, cuda_device):
     hs = max(abs(v) for v in fx["speech_last_hidden_state"]["val"])
     check_sample(out["speech_last_hidden_state"].float(), fx["speech_last_hidden_state"], atol=4e-2 * hs)
     assert _ids_agree(out["logits"], fx["argmax_ids"], max_flips=2)
+    # gradients: every tensor, against the oracle run here (held bit-equal to the reference by the fixture: loss above,
+    # sampled gradients in tests/test_oracle_golden.py).  The 16-element samples of the fixture are too few for a
+    # direction check of their own; they pin the NORMS.
+    ref = ora(x, labels=labels, **kw_o)
+    assert abs(float(ref["loss"]) - fx["loss"]) < 1e-4
+    ref["loss"].backward()
     out["loss"].backward()
-    pm = dict(mine.named_parameters())
+    po, pm = dict(ora.named_parameters()), dict(mine.named_parameters())
     assert sum(p.grad is not None for p in pm.values()) == fx["n_grads"]
-    gscale = max(rec["norm"] for rec in fx["grads"].values())
+    gscale = max(float(p.grad.norm()) for p in po.values() if p.grad is not None)
+    for k, p in po.items():
+        if p.grad is None:
+            assert pm[k].grad is None, k          # reference quirk pinned by the fixture: only adapters[-1] is ever used
+            continue
+        g = pm[k].grad.float().cpu()
+        if float(p.grad.norm()) <= 1e-3 * gscale:
+            assert float((g - p.grad).norm()) <= 3e-4 * gscale, k
+            continue
+        cos = float((g * p.grad).sum() / (g.norm() * p.grad.norm() + 1e-30))
+        # stacked replace-adapters (no residual) amplify bf16 noise layer by layer: direction + norm, not rel-L2
+        assert cos > (0.97 if fx["cls"] == "Adapter" else 0.995), (k, cos)
+        assert abs(float(g.norm()) / float(p.grad.norm()) - 1.0) < (0.15 if fx["cls"] == "Adapter" or t5 else 0.06), (k, float(g.norm()), float(p.grad.norm()))
     for k, rec in fx["grads"].items():
-        g = pm[k].grad
-        assert g is not None, k
-        got = g.detach().double().cpu().reshape(-1)[torch.tensor(rec["idx"])]
-        ref = torch.tensor(rec["val"], dtype=torch.float64)
-        assert abs(float(g.double().norm()) - rec["norm"]) <= (1.2e-1 if t5 else 6e-2) * rec["norm"] + 2e-4 * gscale, (k, float(g.norm()), rec["norm"])
-        cos = float((got * ref).sum() / (got.norm() * ref.norm() + 1e-30))
-        if rec["norm"] > 1e-3 * gscale:
-            assert cos > 0.98, (k, cos)
-    for k, p in pm.items():          # reference quirk pinned by the fixture: only adapters[-1] is ever used
-        if k.startswith("adapters.") and k not in fx["grads"]:
-            assert p.grad is None, k
+        assert abs(float(po[k].grad.double().norm()) - rec["norm"]) <= 1e-3 * rec["norm"] + 1e-7, k
 
 
 def test_fused_optimizer_updates_reach_the_kernels(cuda_device):
