@@ -166,12 +166,17 @@ def build_cpu_reference(w, batch):
     return model, x, labels, extra
 
 
-def time_cpu_reference(w, steps, warmup, batch=None):
+def time_cpu_reference(w, steps, warmup, batch=None, optimizer="adafactor"):
     import torch
     batch = batch or w["cpu_batch"]
     torch.set_num_threads(os.cpu_count())
     model, x, labels, extra = build_cpu_reference(w, batch)
-    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-5)
+    params = [p for p in model.parameters() if p.requires_grad]
+    if optimizer == "adafactor":   # the recipe's optimizer exactly as the HF Trainer builds it (ref:train.py:298)
+        from transformers.optimization import Adafactor
+        opt = Adafactor(params, lr=1e-5, scale_parameter=False, relative_step=False)
+    else:
+        opt = torch.optim.AdamW(params, lr=1e-5)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
@@ -190,11 +195,12 @@ def run_reference_arm(args, rank):
     if rank != 0:
         return
     w = WORKLOADS[args.config]
-    val, sec, threads = time_cpu_reference(w, args.steps, args.warmup)
+    val, sec, threads = time_cpu_reference(w, args.steps, args.warmup, optimizer=args.optimizer)
+    oname = "Adafactor" if args.optimizer == "adafactor" else "AdamW"
     line = {"impl": "reference", "metric": "train audio-sec/s", "value": val, "unit": "audio-s/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["desc"] + ", fwd+bwd+AdamW", "name": args.config,
+            "config": {"workload": w["desc"] + ", fwd+bwd+" + oname, "name": args.config,
                        "sample": "batch %d x %g s per step on host CPU" % (w["cpu_batch"], w["seconds"])},
             "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": threads, "kind": "port",
                              "sample": "oracle/hf_oracle.py Oracle%s (restated reference glue over transformers), "
@@ -212,8 +218,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None)
-    ap.add_argument("--optimizer", default="adamw", choices=["adamw", "adafactor"],
-                    help="adamw = torch fused AdamW; adafactor = the recipe's optimizer (ref:train.py:298) as one fused kernel set")
+    ap.add_argument("--optimizer", default="adafactor", choices=["adamw", "adafactor"],
+                    help="adafactor = the recipe's optimizer (ref:train.py:298 optim=adafactor) -- ours: speechmix_b200.optim."
+                         "FusedAdafactor, reference arm: transformers' Adafactor; adamw = torch AdamW (fused on the GPU)")
     ap.add_argument("--grad-payload", default="bf16", choices=["fp32", "bf16"],
                     help="wire format of the data-parallel gradient all-reduce (N > 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -264,7 +271,7 @@ def main():
     n_train = sum(p.numel() for p in params)
     if args.optimizer == "adafactor":
         from speechmix_b200.optim import FusedAdafactor
-        opt = FusedAdafactor(params, lr=1e-5)
+        opt = FusedAdafactor(params, lr=1e-5, capturable=bool(args.graph and world == 1))
     else:
         opt = torch.optim.AdamW(params, lr=1e-5, fused=True, capturable=bool(args.graph and world == 1))
     dp = parallel.GradientAllReducer(model, world, payload=args.grad_payload) if world > 1 else None
@@ -415,10 +422,11 @@ def main():
                 "clocks": sampler.summary(),
                 "roofline": roof}
         if not args.no_cpu_baseline and world == 1:
-            val, sec, threads = time_cpu_reference(w, steps=2, warmup=1)
+            val, sec, threads = time_cpu_reference(w, steps=2, warmup=1, optimizer=args.optimizer)
             line["cpu_baseline"] = {"value": val, "unit": "audio-s/s", "cores": threads, "kind": "port",
-                                    "sample": "oracle Oracle%s fp32 fwd+bwd+AdamW, batch %d x %g s, 2 timed steps (%.1f s/step)"
-                                              % (w["cls"], w["cpu_batch"], SECONDS, sec)}
+                                    "sample": "oracle Oracle%s fp32 fwd+bwd+%s, batch %d x %g s, 2 timed steps (%.1f s/step)"
+                                              % (w["cls"], "Adafactor" if args.optimizer == "adafactor" else "AdamW",
+                                                 w["cpu_batch"], SECONDS, sec)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

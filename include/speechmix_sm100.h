@@ -154,7 +154,9 @@ int smx_multi_cast(const SmxCastEntry* table, int32_t n_entries, int32_t total_c
  * row_acc / col_acc / sumsq are per-tensor scratch carved out of ONE block `scratch` (zeroed by the call);
  * rmean is [batch] scratch.  tiles: 64 x 256 element tiles covering every slice once (vectors are viewed as
  * [ceil(numel/256)][256]); slices: one (tensor, b) pair per factored slice.  All three tables are DEVICE arrays.
- * beta2t = 1 - step^decay_rate is computed by the caller; eps1 = eps[0].
+ * beta2t = 1 - step^decay_rate is computed by the caller; eps1 = eps[0].  Capturable mode: step_dev != NULL is a
+ * DEVICE int64 step counter -- the call increments it and the kernels evaluate beta2t from it (decay_rate), so the
+ * launch sequence can be replayed from a CUDA graph; beta2t is then ignored.
  * ------------------------------------------------------------------------ */
 typedef struct {
   float* p;
@@ -175,7 +177,7 @@ int smx_adafactor_step(const SmxAdafactorTensor* tensors, int32_t n_tensors, con
                        int32_t n_tiles, const SmxAdafactorSlice* slices, int32_t n_slices,
                        const SmxAdafactorSlice* small_slices, int32_t n_small, int32_t small_smem_floats,
                        void* scratch, int64_t scratch_bytes, float beta2t, float eps1, float lr, float clip_threshold,
-                       float weight_decay, void* stream);
+                       float weight_decay, int64_t* step_dev, float decay_rate, void* stream);
 
 int smx_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
 int smx_act_bf16(const void* x, void* y, int64_t n, int act, void* stream);

@@ -25,7 +25,20 @@ constexpr int TILE_R = 64, TILE_C = 256;   // 8 warps x 8 rows, 32 lanes x 8 col
 
 struct Hyper {
   float beta2t, eps1, lr, clip, weight_decay;
+  // capturable mode (whole-step CUDA graph): the step count lives on the device and beta2(t) = 1 - t^decay_rate is
+  // evaluated by the kernels, so a replayed graph advances the schedule (a host-computed beta2t would be frozen)
+  const long long* step_dev;
+  float decay_rate;
 };
+__device__ __forceinline__ Hyper resolve(Hyper h) {
+  if (h.step_dev) h.beta2t = 1.0f - powf((float)(*h.step_dev), h.decay_rate);
+  return h;
+}
+__global__ void bump_step_kernel(long long* step) {
+  pdl_trigger();
+  pdl_wait();
+  *step += 1;
+}
 
 // element (r, c) of slice b of a tensor; vectors are viewed as [ceil(n / 256)][256] with a ragged last row
 __device__ __forceinline__ bool in_range(const SmxAdafactorTensor& t, long long r, long long c) {
@@ -117,9 +130,10 @@ __global__ void __launch_bounds__(256) stats_kernel(const SmxAdafactorTensor* __
 
 // one block per (factored tensor, leading index): exp_avg_sq_row / exp_avg_sq_col EMAs and the mean of the row moments
 __global__ void __launch_bounds__(256) finalize_kernel(const SmxAdafactorTensor* __restrict__ tensors,
-                                                       const SmxAdafactorSlice* __restrict__ slices, Hyper h) {
+                                                       const SmxAdafactorSlice* __restrict__ slices, Hyper hp) {
   pdl_trigger();
   pdl_wait();
+  const Hyper h = resolve(hp);
   __shared__ float red[8];
   const SmxAdafactorSlice s = slices[blockIdx.x];
   const SmxAdafactorTensor t = tensors[s.tensor];
@@ -149,9 +163,10 @@ __global__ void __launch_bounds__(256) finalize_kernel(const SmxAdafactorTensor*
 // APPLY = false: accumulate sum(u^2) per tensor (and update exp_avg_sq of vectors); APPLY = true: write the parameters
 template <bool APPLY>
 __global__ void __launch_bounds__(256) update_kernel(const SmxAdafactorTensor* __restrict__ tensors,
-                                                     const SmxAdafactorTile* __restrict__ tiles, Hyper h) {
+                                                     const SmxAdafactorTile* __restrict__ tiles, Hyper hp) {
   pdl_trigger();
   pdl_wait();
+  const Hyper h = resolve(hp);
   __shared__ float red[8];
   const SmxAdafactorTile tl = tiles[blockIdx.x];
   const SmxAdafactorTensor t = tensors[tl.tensor];
@@ -186,36 +201,41 @@ __global__ void __launch_bounds__(256) update_kernel(const SmxAdafactorTensor* _
         cf4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    float4 gv[8][2], pv[8][2];
+    // two halves of four rows: 8 (+8) float4 loads in flight per thread at ~90 registers, so two to three blocks share
+    // an SM (all sixteen rows at once needed 154 registers = one block per SM)
+#pragma unroll 1
+    for (int kh = 0; kh < 2; ++kh) {
+      float4 gv[4][2], pv[4][2];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const long long r = tl.r0 + warp + 8 * k;
+      for (int k = 0; k < 4; ++k) {
+        const long long r = tl.r0 + warp + 8 * (4 * kh + k);
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const long long c = tl.c0 + 4 * lane + 128 * j;
-        const bool ok = r < t.rows && c < t.cols;
-        gv[k][j] = ok ? __ldg(reinterpret_cast<const float4*>(gp + r * t.cols + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (APPLY) pv[k][j] = ok ? *reinterpret_cast<const float4*>(pp + r * t.cols + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < 2; ++j) {
+          const long long c = tl.c0 + 4 * lane + 128 * j;
+          const bool ok = r < t.rows && c < t.cols;
+          gv[k][j] = ok ? __ldg(reinterpret_cast<const float4*>(gp + r * t.cols + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (APPLY) pv[k][j] = ok ? *reinterpret_cast<const float4*>(pp + r * t.cols + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
-    }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const long long r = tl.r0 + warp + 8 * k;
-      const float rf = r < t.rows ? rsqrtf(t.row[(long long)tl.b * t.rows + r] * inv_rmean) : 0.f;
+      for (int k = 0; k < 4; ++k) {
+        const long long r = tl.r0 + warp + 8 * (4 * kh + k);
+        const float rf = r < t.rows ? rsqrtf(t.row[(long long)tl.b * t.rows + r] * inv_rmean) : 0.f;
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const long long c = tl.c0 + 4 * lane + 128 * j;
-        float4 u = gv[k][j];
-        u.x *= rf * cf4[j].x, u.y *= rf * cf4[j].y, u.z *= rf * cf4[j].z, u.w *= rf * cf4[j].w;
-        if (APPLY) {
-          if (r < t.rows && c < t.cols) {
-            float4 q = pv[k][j];
-            q.x = q.x * decay - scale * u.x, q.y = q.y * decay - scale * u.y;
-            q.z = q.z * decay - scale * u.z, q.w = q.w * decay - scale * u.w;
-            *reinterpret_cast<float4*>(pp + r * t.cols + c) = q;
+        for (int j = 0; j < 2; ++j) {
+          const long long c = tl.c0 + 4 * lane + 128 * j;
+          float4 u = gv[k][j];
+          u.x *= rf * cf4[j].x, u.y *= rf * cf4[j].y, u.z *= rf * cf4[j].z, u.w *= rf * cf4[j].w;
+          if (APPLY) {
+            if (r < t.rows && c < t.cols) {
+              float4 q = pv[k][j];
+              q.x = q.x * decay - scale * u.x, q.y = q.y * decay - scale * u.y;
+              q.z = q.z * decay - scale * u.z, q.w = q.w * decay - scale * u.w;
+              *reinterpret_cast<float4*>(pp + r * t.cols + c) = q;
+            }
+          } else {
+            ss += u.x * u.x + u.y * u.y + u.z * u.z + u.w * u.w;
           }
-        } else {
-          ss += u.x * u.x + u.y * u.y + u.z * u.z + u.w * u.w;
         }
       }
     }
@@ -263,9 +283,10 @@ __global__ void __launch_bounds__(256) update_kernel(const SmxAdafactorTensor* _
 constexpr int SMALL_ELEMS = 16384, SMALL_RC = 4096;
 
 __global__ void __launch_bounds__(256) small_moments_kernel(const SmxAdafactorTensor* __restrict__ tensors,
-                                                            const SmxAdafactorSlice* __restrict__ slices, Hyper h) {
+                                                            const SmxAdafactorSlice* __restrict__ slices, Hyper hp) {
   pdl_trigger();
   pdl_wait();
+  const Hyper h = resolve(hp);
   extern __shared__ float sm[];                 // g [rows * cols] | rowv [rows] | colv [cols] | red [8]
   const SmxAdafactorSlice s = slices[blockIdx.x];
   const SmxAdafactorTensor t = tensors[s.tensor];
@@ -350,9 +371,10 @@ __global__ void __launch_bounds__(256) small_moments_kernel(const SmxAdafactorTe
 }
 
 __global__ void __launch_bounds__(256) small_apply_kernel(const SmxAdafactorTensor* __restrict__ tensors,
-                                                          const SmxAdafactorSlice* __restrict__ slices, Hyper h) {
+                                                          const SmxAdafactorSlice* __restrict__ slices, Hyper hp) {
   pdl_trigger();
   pdl_wait();
+  const Hyper h = resolve(hp);
   const SmxAdafactorSlice s = slices[blockIdx.x];
   const SmxAdafactorTensor t = tensors[s.tensor];
   const int rows = (int)t.rows, cols = (int)t.cols, n = rows * cols;
@@ -377,7 +399,8 @@ extern "C" int smx_adafactor_step(const SmxAdafactorTensor* tensors, int32_t n_t
                                   int32_t n_tiles, const SmxAdafactorSlice* slices, int32_t n_slices,
                                   const SmxAdafactorSlice* small_slices, int32_t n_small, int32_t small_smem_floats,
                                   void* scratch, int64_t scratch_bytes, float beta2t, float eps1, float lr,
-                                  float clip_threshold, float weight_decay, void* stream) {
+                                  float clip_threshold, float weight_decay, int64_t* step_dev, float decay_rate,
+                                  void* stream) {
   using namespace smx;
   using namespace smx::adafactor;
   SMX_REQUIRE(tensors && (n_tiles == 0 || tiles) && (n_slices == 0 || slices) && (n_small == 0 || small_slices) && scratch,
@@ -389,7 +412,11 @@ extern "C" int smx_adafactor_step(const SmxAdafactorTensor* tensors, int32_t n_t
   cudaStream_t st = (cudaStream_t)stream;
   // row_acc / col_acc / sumsq of every tensor live in one scratch block: one memset per step
   SMX_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (size_t)scratch_bytes, st));
-  Hyper h{beta2t, eps1, lr, clip_threshold, weight_decay};
+  Hyper h{beta2t, eps1, lr, clip_threshold, weight_decay, reinterpret_cast<const long long*>(step_dev), decay_rate};
+  if (step_dev) {
+    launch_pdl(bump_step_kernel, dim3(1), dim3(1), 0, st, reinterpret_cast<long long*>(step_dev));
+    SMX_CHECK_CUDA(cudaGetLastError());
+  }
   if (n_small > 0) {
     static bool attr_set = false;
     if (!attr_set) {

@@ -12,9 +12,9 @@ from . import ops
 
 
 def _capturable(opt):
-    """True when ``opt.step()`` may be recorded into a CUDA graph: torch optimizers built with ``capturable=True``
-    keep their step counters on the device; anything else (FusedAdafactor passes beta2(t) as a kernel argument and
-    synchronises an event, plain torch optimizers read host-side step counts) must run eagerly after the replay."""
+    """True when ``opt.step()`` may be recorded into a CUDA graph: torch optimizers and ``optim.FusedAdafactor`` built
+    with ``capturable=True`` keep their step counters on the device; anything else (host-side step counts or
+    schedule values passed as kernel arguments) must run eagerly after the replay."""
     return bool(opt.param_groups) and all(bool(g.get("capturable", False)) for g in opt.param_groups)
 
 

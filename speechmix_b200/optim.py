@@ -112,15 +112,19 @@ class FusedAdafactor(torch.optim.Optimizer):
     """Drop-in for ``transformers.optimization.Adafactor(params, lr=lr, scale_parameter=False, relative_step=False)``."""
 
     def __init__(self, params, lr=None, eps=(1e-30, 1e-3), clip_threshold=1.0, decay_rate=-0.8, beta1=None,
-                 weight_decay=0.0, scale_parameter=False, relative_step=False, warmup_init=False):
+                 weight_decay=0.0, scale_parameter=False, relative_step=False, warmup_init=False, capturable=False):
         if lr is None or relative_step or warmup_init or scale_parameter or beta1 is not None:
             raise NotImplementedError("FusedAdafactor implements the reference recipe only: explicit lr, "
                                       "relative_step=False, scale_parameter=False, warmup_init=False, beta1=None")
         defaults = dict(lr=lr, eps=eps, clip_threshold=clip_threshold, decay_rate=decay_rate, beta1=beta1,
                         weight_decay=weight_decay, scale_parameter=scale_parameter, relative_step=relative_step,
-                        warmup_init=warmup_init)
+                        warmup_init=warmup_init, capturable=bool(capturable))
         super().__init__(params, defaults)
         self._plans = {}
+        # capturable=True (whole-step CUDA graph, graph.GraphedTrainStep): ONE step counter on the device drives
+        # beta2(t) inside the kernels and is bumped by the launch itself, so replays advance the schedule; all
+        # parameters must then share one step count, learning rate and gradient addresses (true for a captured step).
+        self._dev_step = None
 
     def _init_state(self, p):
         st = self.state[p]
@@ -173,19 +177,32 @@ class FusedAdafactor(torch.optim.Optimizer):
                 plan = self._plan_for(params)
                 grads = [p.grad if (p.grad.dtype == torch.float32 and p.grad.is_contiguous())
                          else p.grad.float().contiguous() for p in params]
-                if plan.uploaded is not None:
+                capturing = torch.cuda.is_current_stream_capturing()
+                if plan.uploaded is not None and not capturing:
                     plan.uploaded.synchronize()
                 plan.host["g"] = [g.data_ptr() for g in grads]      # the only per-step column of the table
-                plan.table.copy_(plan.pinned, non_blocking=True)
-                plan.uploaded = torch.cuda.Event()
-                plan.uploaded.record()
+                plan.table.copy_(plan.pinned, non_blocking=True)    # (captured: replays re-copy the same pointers)
+                if not capturing:
+                    plan.uploaded = torch.cuda.Event()
+                    plan.uploaded.record()
                 beta2t = 1.0 - math.pow(step_no, group["decay_rate"])
+                step_dev = 0
+                if group["capturable"]:
+                    if len(by_step) != 1:
+                        raise RuntimeError("FusedAdafactor(capturable=True): all parameters must share one step count")
+                    if self._dev_step is None:
+                        self._dev_step = torch.full((1,), step_no - 1, dtype=torch.int64, device=params[0].device)
+                    step_dev = self._dev_step.data_ptr()
                 rc = lib.smx_adafactor_step(plan.table.data_ptr(), len(params), plan.tiles.data_ptr(), plan.n_tiles,
                                             plan.slices.data_ptr(), plan.n_slices, plan.small.data_ptr(), plan.n_small,
                                             plan.small_floats, plan.scratch.data_ptr(),
                                             plan.scratch.numel() * 4, beta2t, group["eps"][0], group["lr"],
-                                            group["clip_threshold"], group["weight_decay"],
-                                            torch.cuda.current_stream().cuda_stream)
+                                            group["clip_threshold"], group["weight_decay"], step_dev,
+                                            group["decay_rate"], torch.cuda.current_stream().cuda_stream)
                 _lib.check(rc, "smx_adafactor_step")
                 del grads
         return loss
+
+    def steps_done(self):
+        """capturable mode: the device-side step count (graph replays do not pass through ``step()``)."""
+        return int(self._dev_step.item()) if self._dev_step is not None else None

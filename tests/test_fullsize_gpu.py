@@ -141,9 +141,11 @@ def test_cfg2_batch8_loss_within_1e3(cuda_device):
 
 CASES = {
     # name: (class, speech kind, speech type, text kind, ctor kwargs, batch, seconds, t_dec)
-    "cfg3_adapter_hubert_large_bart_large": ("Adapter", "large", "hubert", "bart-large", dict(down_scale=8), 2, 15.0, 64),
-    "cfg4_self_w2v2_large_t5_base": ("Self", "large", "wav2vec2", "t5-base", dict(down_scale=8, share_layer_ratio=0.5), 2, 15.0, 64),
-    "cfg5_eed_hubert_large_mbart50": ("EED", "large", "hubert", "mbart-large-50", dict(down_scale=8), 1, 30.0, 128),
+    # 512 target tokens each: with 128 the bf16 noise of the mean NLL of these 24-layer random-init stacks is ~1e-3 by
+    # itself (measured over six runs: |dloss| 1e-4 .. 1.7e-3, one 3.3e-3), which made a 1.5e-3 bound a coin toss
+    "cfg3_adapter_hubert_large_bart_large": ("Adapter", "large", "hubert", "bart-large", dict(down_scale=8), 2, 15.0, 256),
+    "cfg4_self_w2v2_large_t5_base": ("Self", "large", "wav2vec2", "t5-base", dict(down_scale=8, share_layer_ratio=0.5), 2, 15.0, 256),
+    "cfg5_eed_hubert_large_mbart50": ("EED", "large", "hubert", "mbart-large-50", dict(down_scale=8), 1, 30.0, 512),
 }
 
 
@@ -195,7 +197,7 @@ def test_baseline_config_full_size_vs_oracle(case, cuda_device):
     assert rec["n_grad_tensors"] == n_ref >= 6 and n_ref <= len(mine.list_grad)
     assert rec["logits_rel_max"] < 2e-2, rec["logits_rel_max"]
     assert rec["speech_rel_max"] < 4e-2 and rec["text_enc_rel_max"] < 4e-2, rec
-    # 128 target tokens: per-token bf16 noise of the NLL (~3e-3) averages to a few 1e-4
+    # 512 target tokens: per-token bf16 noise of the NLL averages to a few 1e-4
     if cls == "Self":
         # loss = CE + KL(batchmean) + MSE (ref:speechmix/hf_model.py:551-581): the CE term is the per-token mean the
         # north-star bound speaks about; KL "batchmean" is a SUM over T_dec x V per sample (~50 here) and the MSE a

@@ -396,16 +396,23 @@ def test_loss_tolerance_at_scale(cuda_device):
     assert abs(float(out["loss"]) - float(ref["loss"])) < 1e-3, (float(out["loss"]), float(ref["loss"]))
 
 
-def test_graphed_step_matches_eager(cuda_device):
-    """speechmix_b200.graph.GraphedTrainStep (whole-step CUDA graph) must train exactly like the eager step."""
+@pytest.mark.parametrize("optimizer", ["adamw", "adafactor"])
+def test_graphed_step_matches_eager(optimizer, cuda_device):
+    """speechmix_b200.graph.GraphedTrainStep (whole-step CUDA graph) must train exactly like the eager step -- with torch's
+    capturable fused AdamW and with the recipe's optimizer (FusedAdafactor(capturable=True): device-side step counter, so
+    the replays advance beta2(t) exactly like eager steps do)."""
     from speechmix_b200.graph import GraphedTrainStep
+    from speechmix_b200.optim import FusedAdafactor
     fx = load_fixture("mini_eed_ds2")
     ora, x, labels = build_oracle(fx)
     xs, ys = x.to(cuda_device), labels.to(cuda_device)
     losses = []
     for use_graph in (False, True):
         m = _mine_from(ora, fx, cuda_device)
-        opt = torch.optim.AdamW(m.parameters(), lr=2e-4, weight_decay=0.0, fused=True, capturable=True)
+        if optimizer == "adamw":
+            opt = torch.optim.AdamW(m.parameters(), lr=2e-4, weight_decay=0.0, fused=True, capturable=True)
+        else:
+            opt = FusedAdafactor(m.parameters(), lr=2e-3, capturable=use_graph)
         hist = []
         if use_graph:
             g = GraphedTrainStep(m, opt, xs, ys, warmup=2)      # two eager steps (optimizer state, cast table), then 3 replays
@@ -423,6 +430,8 @@ def test_graphed_step_matches_eager(cuda_device):
     assert losses[0][0] - losses[0][-1] > 0.3                        # it trains
     assert len(losses[0]) == len(losses[1]) == 5
     assert max(abs(a - b) for a, b in zip(*losses)) < 5e-3, losses   # same trajectory (atomics reorder the last bits)
+    if optimizer == "adafactor":
+        assert opt.steps_done() == 5 and g.opt_in_graph               # the device-side counter followed the replays
 
 
 def test_graph_replay_survives_interleaved_eager_calls(cuda_device):
