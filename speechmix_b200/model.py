@@ -304,19 +304,24 @@ class SpeechMixEED(nn.Module):
 
     @torch.no_grad()
     def generate(self, input_values, max_length=32, decoder_text_prompt=None, eos_token_id=None, use_cache=True,
-                 precision=None, cuda_graph=False, attention_mask=None, **kwargs):
+                 precision=None, cuda_graph=False, attention_mask=None, num_beams=1, length_penalty=1.0,
+                 early_stopping=False, forced_eos_token_id="config", **kwargs):
         """Greedy decode (ref:eval.py:12-13; loop semantics of ref:eval.ipynb cell 6).  The speech encoder, bridge
         and text encoder run once.  ``use_cache=True`` (default): KV-cached decoder, one pass per new token
         (the role of ref:speechmix/hf_model.py:314-338 ``prepare_inputs_for_generation`` + ``past_key_values``);
         ``use_cache=False``: the notebook's full-prefix recompute.  Both return the same ids.
         ``cuda_graph=True`` replays the whole cached decode loop as one CUDA graph (captured once per input shape
-        and ``max_length``).  ``attention_mask``: the variable-length extension of ``forward`` (speech encoder only)."""
+        and ``max_length``).  ``attention_mask``: the variable-length extension of ``forward`` (speech encoder only).
+        ``num_beams > 1``: KV-cached beam search with HF's semantics (``length_penalty``, ``early_stopping``,
+        ``forced_eos_token_id`` -- default: the text config's value, as GenerationMixin would apply it); the caches are
+        gathered per step by ``_reorder_cache`` (ref:speechmix/hf_model.py:337-338)."""
         if precision == "fp32":
             if attention_mask is not None:
                 raise NotImplementedError("fp32 verification mode has no key-padding mask")
             with ops.fp32_verification():
                 return self.generate(input_values, max_length, decoder_text_prompt, eos_token_id, use_cache,
-                                     cuda_graph=cuda_graph)
+                                     cuda_graph=cuda_graph, num_beams=num_beams, length_penalty=length_penalty,
+                                     early_stopping=early_stopping, forced_eos_token_id=forced_eos_token_id)
         cfg = self.decoder_model.config
         eos = cfg.eos_token_id if eos_token_id is None else eos_token_id
         enc = self.encoder_model(input_values, attention_mask=attention_mask, output_hidden_states=True)
@@ -326,9 +331,16 @@ class SpeechMixEED(nn.Module):
             if decoder_text_prompt is not None:
                 inputs_embeds = self._prepend_prompt(inputs_embeds, decoder_text_prompt)
             text_enc, _ = self.decoder_model.encode(inputs_embeds=inputs_embeds)
+            if int(num_beams) > 1:
+                feos = getattr(cfg, "forced_eos_token_id", None) if forced_eos_token_id == "config" else forced_eos_token_id
+                return self.decoder_model.beam_decode(text_enc, max_length, int(num_beams), eos_token_id=eos,
+                                                      length_penalty=length_penalty, early_stopping=early_stopping,
+                                                      forced_eos_token_id=feos)
             if cuda_graph:
                 return self.decoder_model.greedy_decode_graph(text_enc, max_length, eos_token_id=eos)
             return self.decoder_model.greedy_decode(text_enc, max_length, eos_token_id=eos)
+        if int(num_beams) > 1:
+            raise NotImplementedError("beam search runs on the KV-cached decoder (use_cache=True)")
         dec = torch.full((B, 1), cfg.decoder_start_token_id, dtype=torch.long, device=self.device)
         done = torch.zeros(B, dtype=torch.bool, device=self.device)
         text_enc = None
@@ -342,6 +354,12 @@ class SpeechMixEED(nn.Module):
             if bool(done.all()):
                 break
         return dec
+
+    def _reorder_cache(self, past, beam_idx):
+        """ref:speechmix/hf_model.py:337-338 (delegates to the decoder model's cache reorder): ``past`` = list of
+        per-layer self-attention caches [rows, T, 2D]; row i of the result continues row ``beam_idx[i]``."""
+        from .beam import reorder_cache
+        return reorder_cache(past, beam_idx)
 
     def _prepend_prompt(self, inputs_embeds, decoder_text_prompt):
         """ref:speechmix/hf_model.py:433-436"""

@@ -185,27 +185,11 @@ class Seq2SeqLM(nn.Module):
         B, dev = enc.shape[0], enc.device
         eos = cfg.eos_token_id if eos_token_id is None else eos_token_id
         ids = torch.full((B, max_length), cfg.decoder_start_token_id, dtype=torch.long, device=dev)
-        D = cfg.d_model
-        caches = [torch.empty(B, max_length, 2 * D, device=dev, dtype=K.act_dtype()) for _ in dec.layers]
-        cross = [ops.cross_kv(enc, l.encoder_attn.k_proj.weight, l.encoder_attn.k_proj.bias, l.encoder_attn.v_proj.weight,
-                              l.encoder_attn.v_proj.bias) for l in dec.layers]
+        caches, cross = self._decode_state(enc, B, max_length)
         w, b, scale = self.lm_head_params()
         done = torch.zeros(B, dtype=torch.bool, device=dev)
         for t in range(max_length - 1):
-            x = dec.embed(ids[:, t:t + 1].contiguous(), None, t_start=t).view(B, D)
-            for li, l in enumerate(dec.layers):
-                x = ops.decode_self_attn_step(x, l.cfg_self, *l.self_attn.params(), l.self_attn_layer_norm.weight,
-                                              l.self_attn_layer_norm.bias, caches[li], t)
-                ea = l.encoder_attn
-                x = ops.decode_cross_attn_step(x, l.cfg_cross, ea.q_proj.weight, ea.q_proj.bias, ea.out_proj.weight,
-                                               ea.out_proj.bias, l.encoder_attn_layer_norm.weight,
-                                               l.encoder_attn_layer_norm.bias, cross[li])
-                x = ops.decode_ffn_step(x, l.cfg_cross, l.fc1.weight, l.fc1.bias, l.fc2.weight, l.fc2.bias,
-                                        l.final_layer_norm.weight, l.final_layer_norm.bias)
-                if dec.layer_output_hook is not None:
-                    x = dec.layer_output_hook(li, x.view(B, 1, D)).reshape(B, D)
-            if dec.pre_ln:
-                x = ops._ln_maybe(x, dec.layer_norm.weight, dec.layer_norm.bias, 1e-5, False)
+            x = self._decode_step(ids[:, t:t + 1].contiguous(), t, caches, cross)
             nxt = ops.lm_head_argmax(x, w, b, scale)
             ids[:, t + 1] = nxt
             if sync_eos:
@@ -213,6 +197,34 @@ class Seq2SeqLM(nn.Module):
                 if bool(done.all()):
                     return ids[:, :t + 2]
         return ids
+
+    def _decode_step(self, tok, t, caches, cross):
+        """one KV-cached decoder pass: tok [B, 1] at position t -> last hidden state [B, D] (writes row t of the caches)"""
+        dec = self.model.decoder
+        B, D = tok.shape[0], self.config.d_model
+        x = dec.embed(tok, None, t_start=t).view(B, D)
+        for li, l in enumerate(dec.layers):
+            x = ops.decode_self_attn_step(x, l.cfg_self, *l.self_attn.params(), l.self_attn_layer_norm.weight,
+                                          l.self_attn_layer_norm.bias, caches[li], t)
+            ea = l.encoder_attn
+            x = ops.decode_cross_attn_step(x, l.cfg_cross, ea.q_proj.weight, ea.q_proj.bias, ea.out_proj.weight,
+                                           ea.out_proj.bias, l.encoder_attn_layer_norm.weight,
+                                           l.encoder_attn_layer_norm.bias, cross[li])
+            x = ops.decode_ffn_step(x, l.cfg_cross, l.fc1.weight, l.fc1.bias, l.fc2.weight, l.fc2.bias,
+                                    l.final_layer_norm.weight, l.final_layer_norm.bias)
+            if dec.layer_output_hook is not None:
+                x = dec.layer_output_hook(li, x.view(B, 1, D)).reshape(B, D)
+        if dec.pre_ln:
+            x = ops._ln_maybe(x, dec.layer_norm.weight, dec.layer_norm.bias, 1e-5, False)
+        return x
+
+    def _decode_state(self, enc, rows, max_length):
+        """(self-attention caches [rows, max_length, 2D] per layer, cross-attention k | v of ``enc`` per layer)"""
+        dec, D = self.model.decoder, self.config.d_model
+        caches = [torch.empty(rows, max_length, 2 * D, device=enc.device, dtype=K.act_dtype()) for _ in dec.layers]
+        cross = [ops.cross_kv(enc, l.encoder_attn.k_proj.weight, l.encoder_attn.k_proj.bias, l.encoder_attn.v_proj.weight,
+                              l.encoder_attn.v_proj.bias) for l in dec.layers]
+        return caches, cross
 
     def full_logits(self, hidden):
         """fp32 [.., V] logits, materialised -- parity tests / debugging only, never on the training path."""
@@ -428,30 +440,11 @@ class T5Seq2SeqLM(nn.Module):
         B, dev = enc.shape[0], enc.device
         eos = cfg.eos_token_id if eos_token_id is None else eos_token_id
         ids = torch.full((B, max_length), cfg.decoder_start_token_id, dtype=torch.long, device=dev)
-        D, Hi = cfg.d_model, cfg.num_heads * cfg.d_kv
-        caches = [torch.empty(B, max_length, 2 * Hi, device=dev, dtype=K.act_dtype()) for _ in dec.block]
-        cross = [ops.cross_kv(enc, blk.layer[1].EncDecAttention.k.weight, None, blk.layer[1].EncDecAttention.v.weight, None)
-                 for blk in dec.block]
-        rel = dec.block[0].layer[0].SelfAttention.relative_attention_bias.weight.detach().float().contiguous()
+        caches, cross = self._decode_state(enc, B, max_length)
         w, b, scale = self.lm_head_params()
         done = torch.zeros(B, dtype=torch.bool, device=dev)
         for t in range(max_length - 1):
-            x = ops.EmbedFn.apply(ids[:, t:t + 1].contiguous(), None, dec.embed_tokens.weight, None, 1.0, 0, 0).view(B, D)
-            table = ops.t5_bucket_table(1, t + 1, False, cfg.relative_attention_num_buckets,
-                                        cfg.relative_attention_max_distance, dev, q_offset=t)
-            pos_bias = K.relpos_bias_fwd(rel, table, cfg.num_heads, 1, t + 1, q_offset=t)
-            for blk in dec.block:
-                sa, ca, ff = blk.layer[0], blk.layer[1], blk.layer[2]
-                x = ops.decode_self_attn_step(x, blk.cfg_self, *sa.SelfAttention.params(), sa.layer_norm.weight, None,
-                                              caches[blk._index], t, pos_bias)
-                a = ca.EncDecAttention
-                x = ops.decode_cross_attn_step(x, blk.cfg_cross, a.q.weight, None, a.o.weight, None, ca.layer_norm.weight,
-                                               None, cross[blk._index])
-                x = ops.decode_ffn_step(x, blk.cfg_cross, ff.DenseReluDense.wi.weight, None, ff.DenseReluDense.wo.weight,
-                                        None, ff.layer_norm.weight, None)
-                if dec.layer_output_hook is not None:       # SpeechMixAdapter (ref:speechmix/hf_model.py:486-502)
-                    x = dec.layer_output_hook(blk._index, x.view(B, 1, D)).reshape(B, D)
-            x = ops._ln_maybe(x, dec.final_layer_norm.weight, None, cfg.layer_norm_epsilon, True)
+            x = self._decode_step(ids[:, t:t + 1].contiguous(), t, caches, cross)
             nxt = ops.lm_head_argmax(x, w, b, scale)
             ids[:, t + 1] = nxt
             if sync_eos:
@@ -460,10 +453,69 @@ class T5Seq2SeqLM(nn.Module):
                     return ids[:, :t + 2]
         return ids
 
+    def _decode_step(self, tok, t, caches, cross):
+        """one KV-cached decoder pass: tok [B, 1] at position t -> last hidden state [B, D] (writes row t of the caches)"""
+        cfg, dec = self.config, self.decoder
+        B, D, dev = tok.shape[0], cfg.d_model, tok.device
+        rel = dec.block[0].layer[0].SelfAttention.relative_attention_bias.weight.detach().float().contiguous()
+        x = ops.EmbedFn.apply(tok, None, dec.embed_tokens.weight, None, 1.0, 0, 0).view(B, D)
+        table = ops.t5_bucket_table(1, t + 1, False, cfg.relative_attention_num_buckets,
+                                    cfg.relative_attention_max_distance, dev, q_offset=t)
+        pos_bias = K.relpos_bias_fwd(rel, table, cfg.num_heads, 1, t + 1, q_offset=t)
+        for blk in dec.block:
+            sa, ca, ff = blk.layer[0], blk.layer[1], blk.layer[2]
+            x = ops.decode_self_attn_step(x, blk.cfg_self, *sa.SelfAttention.params(), sa.layer_norm.weight, None,
+                                          caches[blk._index], t, pos_bias)
+            a = ca.EncDecAttention
+            x = ops.decode_cross_attn_step(x, blk.cfg_cross, a.q.weight, None, a.o.weight, None, ca.layer_norm.weight,
+                                           None, cross[blk._index])
+            x = ops.decode_ffn_step(x, blk.cfg_cross, ff.DenseReluDense.wi.weight, None, ff.DenseReluDense.wo.weight,
+                                    None, ff.layer_norm.weight, None)
+            if dec.layer_output_hook is not None:       # SpeechMixAdapter (ref:speechmix/hf_model.py:486-502)
+                x = dec.layer_output_hook(blk._index, x.view(B, 1, D)).reshape(B, D)
+        return ops._ln_maybe(x, dec.final_layer_norm.weight, None, cfg.layer_norm_epsilon, True)
+
+    def _decode_state(self, enc, rows, max_length):
+        cfg, dec = self.config, self.decoder
+        Hi = cfg.num_heads * cfg.d_kv
+        caches = [torch.empty(rows, max_length, 2 * Hi, device=enc.device, dtype=K.act_dtype()) for _ in dec.block]
+        cross = [ops.cross_kv(enc, blk.layer[1].EncDecAttention.k.weight, None, blk.layer[1].EncDecAttention.v.weight, None)
+                 for blk in dec.block]
+        return caches, cross
+
     forward = None  # assigned below (shared with the BART-family class)
 
 
 T5Seq2SeqLM.forward = Seq2SeqLM.forward
+
+
+@torch.no_grad()
+def _beam_decode(self, enc, max_length, num_beams, eos_token_id=None, length_penalty=1.0, early_stopping=False,
+                 forced_eos_token_id=None):
+    """KV-cached beam search over encoder states ``enc`` [B, Ts, D] (the search of hf:generation/utils.py
+    ``_beam_search``, restated in beam.BeamState): every utterance runs ``num_beams`` decoder rows; per step the fp32
+    next-token logits of all rows are materialised ([B k, V] -- inference only), the state machine picks the surviving
+    rows and the self-attention caches are gathered accordingly (``_reorder_cache``, ref:speechmix/hf_model.py:337-338);
+    the cross-attention keys / values are projected once per utterance and repeated per beam."""
+    from .beam import BeamState, reorder_cache
+    cfg = self.config
+    B, k = enc.shape[0], int(num_beams)
+    eos = cfg.eos_token_id if eos_token_id is None else eos_token_id
+    caches, cross = self._decode_state(enc, B * k, max_length)        # cross: [B, Ts, 2 Hi] per layer
+    cross = [c.repeat_interleave(k, 0) for c in cross]
+    state = BeamState(B, k, max_length, [cfg.decoder_start_token_id] * B, eos_token_id=eos, pad_token_id=cfg.pad_token_id,
+                      length_penalty=length_penalty, early_stopping=early_stopping, forced_eos_token_id=forced_eos_token_id,
+                      device=enc.device)
+    w, b, scale = self.lm_head_params()
+    bias = None if b is None else b.detach().reshape(-1).float().contiguous()
+    t = 0
+    while not state.done:
+        x = self._decode_step(state.current_tokens().view(B * k, 1).contiguous(), t, caches, cross)
+        logits = K.linear_fwd(x.contiguous(), ops.w16(w), bias, out_f32=True, alpha=scale)
+        _, rows, _ = state.step(logits)
+        caches = reorder_cache(caches, rows)
+        t += 1
+    return state.result()
 
 
 @torch.no_grad()
@@ -501,6 +553,8 @@ def _greedy_decode_graph(self, enc, max_length, eos_token_id=None):
 
 Seq2SeqLM.greedy_decode_graph = _greedy_decode_graph
 T5Seq2SeqLM.greedy_decode_graph = _greedy_decode_graph
+Seq2SeqLM.beam_decode = _beam_decode
+T5Seq2SeqLM.beam_decode = _beam_decode
 
 
 def text_from_pretrained(path_or_config):

@@ -292,3 +292,47 @@ def test_train_step_accumulates_and_clips_like_the_trainer():
     assert torch.allclose(a.lin.weight, b.lin.weight, atol=1e-6)
     w0 = Toy().lin.weight
     assert abs(float((a.lin.weight - w0).norm() ** 2 + (a.lin.bias - Toy().lin.bias).norm() ** 2) ** 0.5 - 0.1 * 0.5) < 1e-4
+
+
+def test_beam_state_matches_transformers_beam_search():
+    """speechmix_b200/beam.py (the bookkeeping behind ``generate(num_beams=k)``, ref:speechmix/hf_model.py:304-338 ->
+    GenerationMixin) against transformers' own ``generate``: same text model, same encoder states, logits from the HF
+    decoder -- so only the search itself is compared.  Covers eos hypotheses finishing early (a frequent token is
+    declared eos), length penalties, early_stopping False / True / "never", and BART's forced-eos processor."""
+    import torch
+    from transformers import GenerationConfig
+    from oracle import hf_oracle as O
+    from speechmix_b200.beam import BeamState
+    torch.manual_seed(0)
+    for kind in ("bart-mini", "t5-mini"):
+        txc = O.text_config(kind)
+        _, text = O.build_backbones(O.speech_config("mini"), txc, seed=0)
+        text.eval()
+        B, start = 3, txc.decoder_start_token_id
+        emb = torch.randn(B, 9, txc.d_model) * 0.5
+        feos = getattr(text.generation_config, "forced_eos_token_id", None)
+        with torch.no_grad():
+            enc = text.get_encoder()(inputs_embeds=emb)
+            first = text(encoder_outputs=enc, decoder_input_ids=torch.full((B, 1), start)).logits[:, -1]
+            frequent = int(torch.topk(first[0], 3)[1][1])
+            for (k, L, eos, lp, es) in [(3, 8, txc.eos_token_id, 1.0, False), (2, 10, frequent, 1.0, False),
+                                        (4, 9, frequent, 2.0, False), (3, 9, frequent, 1.0, True), (3, 9, frequent, 0.0, "never")]:
+                gc = GenerationConfig(num_beams=k, max_length=L, do_sample=False, early_stopping=es, length_penalty=lp,
+                                      eos_token_id=eos, pad_token_id=txc.pad_token_id, decoder_start_token_id=start,
+                                      forced_bos_token_id=None, no_repeat_ngram_size=0, min_length=0, use_cache=True)
+                ref = text.generate(inputs_embeds=emb, generation_config=gc)
+                st = BeamState(B, k, L, [start] * B, eos_token_id=eos, pad_token_id=txc.pad_token_id, length_penalty=lp,
+                               early_stopping=es, forced_eos_token_id=feos)
+                enc_rep = type(enc)(last_hidden_state=enc.last_hidden_state.repeat_interleave(k, 0))
+                rows_seen = []
+                while not st.done:
+                    dec_in = st.running[:, :, :st.cur].reshape(B * k, st.cur)
+                    logits = text(encoder_outputs=enc_rep, decoder_input_ids=dec_in).logits[:, -1]
+                    prev = st.running.clone()
+                    _, rows, _ = st.step(logits)
+                    rows_seen.append(rows)
+                    # the row map is what the KV caches are gathered by: new prefixes = old prefixes of those rows
+                    assert torch.equal(st.running.view(B * k, -1)[:, :st.cur - 1], prev.view(B * k, -1)[rows][:, :st.cur - 1])
+                mine = st.result()
+                assert ref.shape == mine.shape and torch.equal(ref, mine), (kind, k, L, eos, lp, es, ref.tolist(), mine.tolist())
+                assert all(int(r.min()) >= 0 and int(r.max()) < B * k for r in rows_seen)

@@ -165,6 +165,33 @@ def test_greedy_generate_matches_reference_loop(cuda_device):
     assert forks <= ids.shape[0] // 2 + 1, forks       # and forks stay the exception
 
 
+@pytest.mark.parametrize("text", ["bart-mini", "t5-mini"])
+def test_beam_search_matches_hf_generate(text, cuda_device):
+    """``generate(num_beams=3)`` (KV-cached decoder kernels + beam.BeamState + cache reorder) against transformers' own
+    beam search run on the oracle's text model over the oracle's bridged speech states: identical ids in the fp32
+    verification mode; the bf16 run must return well-formed hypotheses of the same batch."""
+    from transformers import GenerationConfig
+    fx = dict(load_fixture("mini_eed_ds2"), text=text, kwargs={"down_scale": 2}, train_mode=False)
+    ora, x, _ = build_oracle(fx)
+    mine = _mine_from(ora, fx, cuda_device).eval()
+    cfg = ora.decoder_model.config
+    k, L = 3, 8
+    with torch.no_grad():
+        enc = ora.encoder_model(x, output_hidden_states=True)
+        emb = ora.bridge(enc)
+        feos = getattr(ora.decoder_model.generation_config, "forced_eos_token_id", None)
+        gc = GenerationConfig(num_beams=k, max_length=L, do_sample=False, early_stopping=False, length_penalty=1.0,
+                              eos_token_id=cfg.eos_token_id, pad_token_id=cfg.pad_token_id,
+                              decoder_start_token_id=cfg.decoder_start_token_id, forced_bos_token_id=None,
+                              no_repeat_ngram_size=0, min_length=0, use_cache=True)
+        ref = ora.decoder_model.generate(inputs_embeds=emb, generation_config=gc)
+    got = mine.generate(x.to(cuda_device), max_length=L, num_beams=k, precision="fp32", forced_eos_token_id=feos).cpu()
+    assert got.shape == ref.shape and torch.equal(got, ref), (got.tolist(), ref.tolist())
+    got16 = mine.generate(x.to(cuda_device), max_length=L, num_beams=k, forced_eos_token_id=feos).cpu()
+    assert got16.shape[0] == ref.shape[0] and got16.shape[1] <= L
+    assert torch.equal(got16[:, 0], ref[:, 0])
+
+
 def test_frozen_parameters_get_no_gradient(cuda_device):
     from oracle import hf_oracle as O
     from speechmix_b200 import SpeechMixFixed
