@@ -323,6 +323,9 @@ def main():
             stage_y[i & 1].copy_(host_y[i & 1], non_blocking=True)
             staged[i & 1].record(copy_stream)
 
+    host_loss = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    step_done = [torch.cuda.Event() for _ in range(2)]
+
     def timed(n, e2e):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -333,14 +336,25 @@ def main():
         for i in range(n):
             if e2e:
                 # every step: H2D copy of ITS batch from pinned host memory (issued on a copy stream while the
-                # previous step computes), the step, and a D2H read of its loss
+                # previous step computes), the step, and a D2H read of ITS loss.  The loss travels through a pinned
+                # slot and is read on the host one step later (after step i + 1 has been queued), the way a training
+                # loop logs: the GPU does not idle while the host reads a number.
                 torch.cuda.current_stream().wait_event(staged[i & 1])
                 loss = step(stage_x[i & 1], stage_y[i & 1])
+                host_loss[i & 1].copy_(loss.detach().reshape(1), non_blocking=True)
+                step_done[i & 1].record()
                 if i + 1 < n:
+                    if i >= 1:   # the staging buffer of batch i + 1 was last read by step i - 1
+                        copy_stream.wait_event(step_done[(i - 1) & 1])
                     prefetch(i + 1)
-                last = loss.item()
+                if i >= 1:
+                    step_done[(i - 1) & 1].synchronize()
+                    last = float(host_loss[(i - 1) & 1])
             else:
                 last = step(dev_x[i & 1], dev_y[i & 1])
+        if e2e:
+            step_done[(n - 1) & 1].synchronize()
+            last = float(host_loss[(n - 1) & 1])
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1) / n

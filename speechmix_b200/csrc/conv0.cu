@@ -178,31 +178,44 @@ __global__ void __launch_bounds__(256, 2) fwd_kernel(const float* __restrict__ a
 // kernel is two streaming reads plus 11 FMAs per element.
 // partial[b][c][0] = sum dz, [2+k] = sum_t dz * x[S t + k]; [1] (= sum dz*xhat) follows algebraically in finalize.
 constexpr int BWD_FR = 1024;
+// Issue-bound, not HBM-bound, as first written (~17 issue slots per element: 10 scalar FMAs, 2.5 LDS, unpacking): the
+// ten window FMAs of a channel now run as FIVE packed-pair FMAs (FFMA2: dz replicated x (win[k], win[k+1]) accumulating
+// (acc[k], acc[k+1])), and the window pairs come from shared memory as 8-byte loads.  S = 5 is odd, so the window of an
+// odd frame starts at an odd float: a second copy of the waveform slab shifted by one float keeps every pair load
+// 8-byte aligned (frame parity picks the copy).
 __global__ void __launch_bounds__(256, 2) bwd_kernel(const float* __restrict__ audio, const bf16* __restrict__ dy,
                                                   const bf16* __restrict__ gprime, float* __restrict__ partial,
                                                   long long n_samples, long long t_out, int channels) {
   pdl_trigger();
   pdl_wait();
-  __shared__ float xs[BWD_FR * S + K];
+  static_assert(K % 2 == 0 && (S & 1) == 1, "pair loads assume an even window and an odd stride");
+  constexpr int XS = BWD_FR * S + K + 2;
+  __shared__ __align__(16) float xs[2][XS];      // xs[1][i] = xs[0][i + 1]
   const int b = blockIdx.y;
   const long long t0 = (long long)blockIdx.x * BWD_FR;
   const long long nfr = (t_out - t0) < BWD_FR ? (t_out - t0) : BWD_FR;
   const float* x = audio + (long long)b * n_samples + t0 * S;
   const int nload = (int)nfr * S + (K - S);
-  for (int i = threadIdx.x; i < nload; i += blockDim.x) xs[i] = x[i];
+  for (int i = threadIdx.x; i < nload; i += blockDim.x) {
+    const float v = x[i];
+    xs[0][i] = v;
+    if (i > 0) xs[1][i - 1] = v;
+  }
   __syncthreads();
   const int quads = channels / 4;
   const int lanes = blockDim.x / 128;  // 2 frame lanes
   for (int qg = threadIdx.x % 128; qg < quads; qg += 128) {
     const int c0 = qg * 4;
-    float acc[4][K + 1];
+    f32x2 acc[4][K / 2];
+    float acc0[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < 4; ++j) {
+      acc0[j] = 0.f;
 #pragma unroll
-      for (int k = 0; k < K + 1; ++k) acc[j][k] = 0.f;
+      for (int k = 0; k < K / 2; ++k) acc[j][k] = f2_rep(0.f);
+    }
     const long long base = ((long long)b * t_out + t0) * channels + c0;
-    // frames in groups of 4 with the NEXT group's 8 loads issued before the current group's FMAs: the kernel is a
-    // latency-bound stream (2 x 8 bytes per thread and frame), so bytes in flight are what sets its bandwidth
+    // frames in groups of 4 with the NEXT group's 8 loads issued before the current group's FMAs
     constexpr int G = 4;
     uint2 cu[G], cg[G];
     const int f_first = threadIdx.x / 128;
@@ -227,16 +240,21 @@ __global__ void __launch_bounds__(256, 2) bwd_kernel(const float* __restrict__ a
       for (int i = 0; i < G; ++i) {
         const int f = f0 + i * lanes;
         const int fs = f < nfr ? f : 0;   // out-of-range frames carry dz = 0
-        float win[K];
+        // window pairs (win[2k], win[2k+1]): float offset fs*S is even for even frames (copy 0) and odd for odd
+        // frames, where copy 1 holds the same data one float earlier
+        const int odd = fs & 1;
+        const f32x2* wp = reinterpret_cast<const f32x2*>(&xs[odd][fs * S - odd]);
+        f32x2 win[K / 2];
 #pragma unroll
-        for (int k = 0; k < K; ++k) win[k] = xs[fs * S + k];
+        for (int k = 0; k < K / 2; ++k) win[k] = wp[k];
         const float dz[4] = {bf16_lo(cu[i].x) * bf16_lo(cg[i].x), bf16_hi(cu[i].x) * bf16_hi(cg[i].x),
                              bf16_lo(cu[i].y) * bf16_lo(cg[i].y), bf16_hi(cu[i].y) * bf16_hi(cg[i].y)};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          acc[j][0] += dz[j];
+          acc0[j] += dz[j];
+          const f32x2 d2 = f2_rep(dz[j]);
 #pragma unroll
-          for (int k = 0; k < K; ++k) acc[j][1 + k] = fmaf(dz[j], win[k], acc[j][1 + k]);
+          for (int k = 0; k < K / 2; ++k) acc[j][k] = f2_fma(d2, win[k], acc[j][k]);
         }
       }
 #pragma unroll
@@ -245,9 +263,130 @@ __global__ void __launch_bounds__(256, 2) bwd_kernel(const float* __restrict__ a
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float* pp = partial + ((long long)b * channels + c0 + j) * (K + 2);
-      atomicAdd(pp, acc[j][0]);
+      atomicAdd(pp, acc0[j]);
 #pragma unroll
-      for (int k = 0; k < K; ++k) atomicAdd(pp + 2 + k, acc[j][1 + k]);
+      for (int k = 0; k < K / 2; ++k) {
+        float lo, hi;
+        f2_unpack(acc[j][k], lo, hi);
+        atomicAdd(pp + 2 + 2 * k, lo);
+        atomicAdd(pp + 3 + 2 * k, hi);
+      }
+    }
+  }
+}
+
+// Ring-fed version (channels <= 512): the register-prefetch kernel above keeps 64 bytes per thread in flight = 32 KiB
+// per SM, which by Little's law is ~3.2 TB/s at the ~1.5 us loaded HBM latency -- exactly what it measured.  A block's
+// dy / gelu' tile is ONE contiguous chunk of memory per stream (channels-last, consecutive frames), so here thread 0
+// streams it through a 5-stage shared-memory ring with 16 KiB bulk copies per stream and stage (160 KiB in flight per
+// SM, no registers spent on prefetching) and every thread reads its 8-byte quads back from shared memory.
+constexpr int BWD_STAGES = 5;
+constexpr int BWD_STAGE_BYTES = 16384;                      // per stream and stage
+constexpr int BWD_XS = BWD_FR * S + K + 2;                  // floats per waveform copy
+constexpr int BWD_XS_BYTES = ((2 * BWD_XS * 4 + 127) / 128) * 128;
+constexpr int BWD_RING_SMEM = BWD_XS_BYTES + BWD_STAGES * 2 * BWD_STAGE_BYTES + 128;
+
+__global__ void __launch_bounds__(512, 1) bwd_ring_kernel(const float* __restrict__ audio, const bf16* __restrict__ dy,
+                                                          const bf16* __restrict__ gprime, float* __restrict__ partial,
+                                                          long long n_samples, long long t_out, int channels) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(128) uint8_t sm[];
+  float* xs0 = reinterpret_cast<float*>(sm);                 // xs1[i] = xs0[i + 1]
+  float* xs1 = xs0 + BWD_XS;
+  uint8_t* ring = sm + BWD_XS_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + BWD_STAGES * 2 * BWD_STAGE_BYTES);
+  const int b = blockIdx.y;
+  const long long t0 = (long long)blockIdx.x * BWD_FR;
+  const int nfr = (int)((t_out - t0) < BWD_FR ? (t_out - t0) : BWD_FR);
+  const int row_bytes = channels * 2;
+  const int F = BWD_STAGE_BYTES / row_bytes;                 // frames per stage (>= 16)
+  const int nst = (nfr + F - 1) / F;
+  const uint8_t* gdy = reinterpret_cast<const uint8_t*>(dy) + ((long long)b * t_out + t0) * row_bytes;
+  const uint8_t* ggp = reinterpret_cast<const uint8_t*>(gprime) + ((long long)b * t_out + t0) * row_bytes;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < BWD_STAGES; ++i) mbar_init(&full[i], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue = [&](int st) {                                 // thread 0 only
+    const int slot = st % BWD_STAGES;
+    const int f0 = st * F;
+    const uint32_t bytes = (uint32_t)((nfr - f0 < F ? nfr - f0 : F) * row_bytes);
+    uint8_t* dst = ring + slot * 2 * BWD_STAGE_BYTES;
+    mbar_expect_tx(&full[slot], 2 * bytes);
+    bulk_load_1d(dst, gdy + (long long)f0 * row_bytes, bytes, &full[slot]);
+    bulk_load_1d(dst + BWD_STAGE_BYTES, ggp + (long long)f0 * row_bytes, bytes, &full[slot]);
+  };
+  if (threadIdx.x == 0)
+    for (int st = 0; st < nst && st < BWD_STAGES; ++st) issue(st);
+  const float* x = audio + (long long)b * n_samples + t0 * S;
+  const int nload = nfr * S + (K - S);
+  for (int i = threadIdx.x; i < nload; i += blockDim.x) {
+    const float v = x[i];
+    xs0[i] = v;
+    if (i > 0) xs1[i - 1] = v;
+  }
+  __syncthreads();
+  const int quads = channels / 4;
+  const int qg = threadIdx.x & 127, fl = threadIdx.x >> 7;   // 128 channel quads x 4 frame lanes
+  const int lanes = blockDim.x >> 7;
+  const bool active = qg < quads;
+  f32x2 acc[4][K / 2];
+  float acc0[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    acc0[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < K / 2; ++k) acc[j][k] = f2_rep(0.f);
+  }
+  for (int st = 0; st < nst; ++st) {
+    const int slot = st % BWD_STAGES;
+    mbar_wait(&full[slot], (uint32_t)((st / BWD_STAGES) & 1));
+    const uint8_t* sdy = ring + slot * 2 * BWD_STAGE_BYTES + qg * 8;
+    const uint8_t* sgp = sdy + BWD_STAGE_BYTES;
+    const int f0 = st * F;
+    const int nf = nfr - f0 < F ? nfr - f0 : F;
+    if (active) {
+#pragma unroll 4
+      for (int fi = fl; fi < nf; fi += lanes) {
+        const uint2 u = *reinterpret_cast<const uint2*>(sdy + fi * row_bytes);
+        const uint2 g = *reinterpret_cast<const uint2*>(sgp + fi * row_bytes);
+        const int fs = f0 + fi;
+        const int odd = fs & 1;
+        const f32x2* wp = reinterpret_cast<const f32x2*>((odd ? xs1 : xs0) + fs * S - odd);
+        f32x2 win[K / 2];
+#pragma unroll
+        for (int k = 0; k < K / 2; ++k) win[k] = wp[k];
+        const float dz[4] = {bf16_lo(u.x) * bf16_lo(g.x), bf16_hi(u.x) * bf16_hi(g.x),
+                             bf16_lo(u.y) * bf16_lo(g.y), bf16_hi(u.y) * bf16_hi(g.y)};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc0[j] += dz[j];
+          const f32x2 d2 = f2_rep(dz[j]);
+#pragma unroll
+          for (int k = 0; k < K / 2; ++k) acc[j][k] = f2_fma(d2, win[k], acc[j][k]);
+        }
+      }
+    }
+    __syncthreads();                                         // every thread is done with this slot
+    if (threadIdx.x == 0 && st + BWD_STAGES < nst) {
+      fence_proxy_async_smem();                              // generic-proxy reads before the async-proxy refill
+      issue(st + BWD_STAGES);
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float* pp = partial + ((long long)b * channels + qg * 4 + j) * (K + 2);
+      atomicAdd(pp, acc0[j]);
+#pragma unroll
+      for (int k = 0; k < K / 2; ++k) {
+        float lo, hi;
+        f2_unpack(acc[j][k], lo, hi);
+        atomicAdd(pp + 2 + 2 * k, lo);
+        atomicAdd(pp + 3 + 2 * k, hi);
+      }
     }
   }
 }
@@ -492,8 +631,20 @@ int smx_conv0_gn_gelu_bwd(const float* audio, const float* w, const float* gamma
   SMX_REQUIRE(channels % 4 == 0, "conv0: channels must be a multiple of 4");
   cudaStream_t st = (cudaStream_t)stream;
   SMX_CHECK_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * (K + 2) * batch * channels, st));
-  launch_pdl(bwd_kernel, dim3(dim3((unsigned)ceil_div(t_out, BWD_FR), (unsigned)batch)), dim3(256), 0, st, 
-      audio, (const bf16*)dy, (const bf16*)gprime, partial, n_samples, t_out, channels);
+  const dim3 grid((unsigned)ceil_div(t_out, BWD_FR), (unsigned)batch);
+  const bool ring_ok = channels <= 512 && channels % 8 == 0 && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(gprime)) & 15) == 0;
+  if (ring_ok) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      SMX_CHECK_CUDA(cudaFuncSetAttribute(bwd_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_RING_SMEM));
+      attr_set = true;
+    }
+    launch_pdl(bwd_ring_kernel, grid, dim3(512), BWD_RING_SMEM, st, audio, (const bf16*)dy, (const bf16*)gprime, partial,
+               n_samples, t_out, channels);
+  } else {
+    launch_pdl(bwd_kernel, grid, dim3(256), 0, st, audio, (const bf16*)dy, (const bf16*)gprime, partial, n_samples, t_out,
+               channels);
+  }
   SMX_CHECK_CUDA(cudaGetLastError());
   launch_pdl(bwd_finalize_kernel, dim3((int)ceil_div(channels * (K + 2), 128)), dim3(128), 0, st, w, gamma, stats, moments, partial, dw,
                                                                              dgamma, dbeta, (int)batch, channels, t_out);

@@ -35,9 +35,59 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// A tensor map is a pure function of (base, type, rank, dims, strides, box, swizzle): nothing in it depends on what
+// the memory holds.  The caching allocator hands the same addresses back step after step, so an eager training step
+// re-encodes the same ~1500 descriptors every time (up to five per GEMM launch, ~1 us each through the driver).
+// Direct-mapped, thread-local cache keyed on the full argument tuple; a hit is one hash + one 128-byte compare.
+struct TmapKey {
+  const void* ptr;
+  uint64_t dims[5], strides[4];
+  uint32_t box[5];
+  int32_t dt, rank, swz;
+};
+struct TmapSlot {
+  TmapKey key;
+  CUtensorMap map;
+  bool used;
+};
+constexpr int TMAP_SLOTS = 8192;
+static thread_local TmapSlot* g_tmap_cache = nullptr;
+
+static int encode_uncached(CUtensorMap* out, CUtensorMapDataType dt, int esize, const void* ptr, int rank,
+                           const uint64_t* dims, const uint64_t* strides_elems, const uint32_t* box, bool swizzle128);
+
 static int encode_generic(CUtensorMap* out, CUtensorMapDataType dt, int esize, const void* ptr, int rank,
                           const uint64_t* dims, const uint64_t* strides_elems, const uint32_t* box,
                           bool swizzle128) {
+  if (rank < 1 || rank > 5) return set_error("tensor map rank %d unsupported", rank);
+  TmapKey k;
+  memset(&k, 0, sizeof(k));
+  k.ptr = ptr, k.dt = (int32_t)dt, k.rank = rank, k.swz = swizzle128 ? 1 : 0;
+  for (int i = 0; i < rank; ++i) {
+    k.dims[i] = dims[i], k.box[i] = box[i];
+    if (i > 0) k.strides[i - 1] = strides_elems[i - 1];
+  }
+  uint64_t h = 1469598103934665603ull;
+  const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+  for (size_t i = 0; i < sizeof(k) / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+  if (!g_tmap_cache) g_tmap_cache = static_cast<TmapSlot*>(calloc(TMAP_SLOTS, sizeof(TmapSlot)));
+  TmapSlot* slot = g_tmap_cache ? &g_tmap_cache[(h >> 17) & (TMAP_SLOTS - 1)] : nullptr;
+  if (slot && slot->used && memcmp(&slot->key, &k, sizeof(k)) == 0) {
+    memcpy(out, &slot->map, sizeof(CUtensorMap));
+    return 0;
+  }
+  const int rc = encode_uncached(out, dt, esize, ptr, rank, dims, strides_elems, box, swizzle128);
+  if (rc == 0 && slot) {
+    slot->key = k;
+    memcpy(&slot->map, out, sizeof(CUtensorMap));
+    slot->used = true;
+  }
+  return rc;
+}
+
+static int encode_uncached(CUtensorMap* out, CUtensorMapDataType dt, int esize, const void* ptr, int rank,
+                           const uint64_t* dims, const uint64_t* strides_elems, const uint32_t* box,
+                           bool swizzle128) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   cuuint64_t gdims[5];
