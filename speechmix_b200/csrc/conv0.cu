@@ -124,21 +124,32 @@ __global__ void __launch_bounds__(256, 2) fwd_kernel(const float* __restrict__ a
                                                   int channels) {
   pdl_trigger();
   pdl_wait();
-  __shared__ float xs[FWD_FR * S + K];
+  // The kernel is issue-bound (ncu: 33 instructions per element, 74 % issue-active, DRAM at 39 %), so the window
+  // arithmetic runs on packed fp32 pairs: z = b + sum over tap PAIRS of (w[2k], w[2k+1]) * (x[2k], x[2k+1]) = 5 FFMA2 +
+  // 1 add instead of 10 FFMA, the window pairs are 8-byte shared-memory loads (S = 5 is odd: a second copy of the
+  // slab shifted by one float keeps odd frames aligned), and GELU / GELU' are evaluated for two channels at once.
+  static_assert(K % 2 == 0 && (S & 1) == 1, "pair loads assume an even window and an odd stride");
+  constexpr int XS = FWD_FR * S + K + 2;
+  __shared__ __align__(16) float xs[2][XS];       // xs[1][i] = xs[0][i + 1]
   const int b = blockIdx.y;
   const long long t0 = (long long)blockIdx.x * FWD_FR;
   const long long nfr = (t_out - t0) < FWD_FR ? (t_out - t0) : FWD_FR;
   const float* x = audio + (long long)b * n_samples + t0 * S;
   const int nload = (int)nfr * S + (K - S);
-  for (int i = threadIdx.x; i < nload; i += blockDim.x) xs[i] = x[i];
+  for (int i = threadIdx.x; i < nload; i += blockDim.x) {
+    const float v = x[i];
+    xs[0][i] = v;
+    if (i > 0) xs[1][i - 1] = v;
+  }
   __syncthreads();
-  // 4 channels per thread (40 weight registers instead of 80: two resident blocks per SM), 128 channel quads x
-  // 2 frame lanes per block; a warp writes 256 contiguous bytes per frame and output tensor
+  // 4 channels per thread, 128 channel quads x 2 frame lanes per block; a warp writes 256 contiguous bytes per frame
+  // and output tensor
   const int quads = channels / 4;
   const int lanes = blockDim.x / 128;
   for (int qg = threadIdx.x % 128; qg < quads; qg += 128) {
     const int c0 = qg * 4;
-    float wf[4][K], bf[4];
+    f32x2 wf[4][K / 2];
+    float bf[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = c0 + j;
@@ -146,23 +157,33 @@ __global__ void __launch_bounds__(256, 2) fwd_kernel(const float* __restrict__ a
       const float rstd = stats[2 * ((long long)b * channels + c) + 1];
       const float g = gamma[c] * rstd;
 #pragma unroll
-      for (int k = 0; k < K; ++k) wf[j][k] = w[c * K + k] * g;
+      for (int k = 0; k < K / 2; ++k) wf[j][k] = f2_pack(w[c * K + 2 * k] * g, w[c * K + 2 * k + 1] * g);
       bf[j] = beta[c] - mean * g;
     }
     const long long base = ((long long)b * t_out + t0) * channels + c0;
 #pragma unroll 2
     for (int f = threadIdx.x / 128; f < nfr; f += lanes) {
-      float win[K];
+      const int odd = f & 1;
+      const f32x2* wp = reinterpret_cast<const f32x2*>(&xs[odd][f * S - odd]);
+      f32x2 win[K / 2];
 #pragma unroll
-      for (int k = 0; k < K; ++k) win[k] = xs[f * S + k];
+      for (int k = 0; k < K / 2; ++k) win[k] = wp[k];
       float o[4], d[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float z = bf[j];
+        f32x2 a = f2_mul(wf[j][0], win[0]);
 #pragma unroll
-        for (int k = 0; k < K; ++k) z = fmaf(wf[j][k], win[k], z);
-        if (gprime) gelu_erf_both(z, o[j], d[j]);   // training: also keep gelu'(z) so backward never recomputes the conv
-        else o[j] = gelu_erf(z);
+        for (int k = 1; k < K / 2; ++k) a = f2_fma(wf[j][k], win[k], a);
+        float lo, hi;
+        f2_unpack(a, lo, hi);
+        o[j] = (lo + hi) + bf[j];
+      }
+      if (gprime) {   // training: also keep gelu'(z) so backward never recomputes the conv
+        gelu_erf_both2(o[0], o[1], d[0], d[1]);
+        gelu_erf_both2(o[2], o[3], d[2], d[3]);
+      } else {
+        gelu_erf2(o[0], o[1]);
+        gelu_erf2(o[2], o[3]);
       }
       *reinterpret_cast<uint2*>(y + base + (long long)f * channels) =
           make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
@@ -285,6 +306,7 @@ constexpr int BWD_STAGE_BYTES = 16384;                      // per stream and st
 constexpr int BWD_XS = BWD_FR * S + K + 2;                  // floats per waveform copy
 constexpr int BWD_XS_BYTES = ((2 * BWD_XS * 4 + 127) / 128) * 128;
 constexpr int BWD_RING_SMEM = BWD_XS_BYTES + BWD_STAGES * 2 * BWD_STAGE_BYTES + 128;
+static_assert(4 * 512 * (K + 2) * 4 <= BWD_STAGES * 2 * BWD_STAGE_BYTES, "lane reduction reuses the ring");
 
 __global__ void __launch_bounds__(512, 1) bwd_ring_kernel(const float* __restrict__ audio, const bf16* __restrict__ dy,
                                                           const bf16* __restrict__ gprime, float* __restrict__ partial,
@@ -296,6 +318,7 @@ __global__ void __launch_bounds__(512, 1) bwd_ring_kernel(const float* __restric
   float* xs1 = xs0 + BWD_XS;
   uint8_t* ring = sm + BWD_XS_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + BWD_STAGES * 2 * BWD_STAGE_BYTES);
+  uint64_t* empty = full + BWD_STAGES;
   const int b = blockIdx.y;
   const long long t0 = (long long)blockIdx.x * BWD_FR;
   const int nfr = (int)((t_out - t0) < BWD_FR ? (t_out - t0) : BWD_FR);
@@ -305,20 +328,34 @@ __global__ void __launch_bounds__(512, 1) bwd_ring_kernel(const float* __restric
   const uint8_t* gdy = reinterpret_cast<const uint8_t*>(dy) + ((long long)b * t_out + t0) * row_bytes;
   const uint8_t* ggp = reinterpret_cast<const uint8_t*>(gprime) + ((long long)b * t_out + t0) * row_bytes;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < BWD_STAGES; ++i) mbar_init(&full[i], 1);
+    for (int i = 0; i < BWD_STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], blockDim.x >> 5);               // one arrival per warp
+    }
     fence_barrier_init();
   }
   __syncthreads();
-  auto issue = [&](int st) {                                 // thread 0 only
+  // warp 0 refills a slot: lane 0 arms the barrier, lanes 0..7 each issue one <= 4 KiB piece (four per stream) -- one
+  // 16 KiB copy per stream left the copy engine with two requests in flight per stage
+  auto issue = [&](int st) {                                 // all lanes of warp 0
     const int slot = st % BWD_STAGES;
     const int f0 = st * F;
-    const uint32_t bytes = (uint32_t)((nfr - f0 < F ? nfr - f0 : F) * row_bytes);
+    const int bytes = (nfr - f0 < F ? nfr - f0 : F) * row_bytes;
     uint8_t* dst = ring + slot * 2 * BWD_STAGE_BYTES;
-    mbar_expect_tx(&full[slot], 2 * bytes);
-    bulk_load_1d(dst, gdy + (long long)f0 * row_bytes, bytes, &full[slot]);
-    bulk_load_1d(dst + BWD_STAGE_BYTES, ggp + (long long)f0 * row_bytes, bytes, &full[slot]);
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) mbar_expect_tx(&full[slot], 2 * (uint32_t)bytes);
+    __syncwarp();
+    if (lane < 8) {
+      const int piece = lane & 3, stream = lane >> 2;
+      const int off = piece * (BWD_STAGE_BYTES / 4);
+      int n = bytes - off;
+      n = n > BWD_STAGE_BYTES / 4 ? BWD_STAGE_BYTES / 4 : n;
+      if (n > 0)
+        bulk_load_1d(dst + stream * BWD_STAGE_BYTES + off, (stream ? ggp : gdy) + (long long)f0 * row_bytes + off, (uint32_t)n,
+                     &full[slot]);
+    }
   };
-  if (threadIdx.x == 0)
+  if (threadIdx.x < 32)
     for (int st = 0; st < nst && st < BWD_STAGES; ++st) issue(st);
   const float* x = audio + (long long)b * n_samples + t0 * S;
   const int nload = nfr * S + (K - S);
@@ -342,6 +379,13 @@ __global__ void __launch_bounds__(512, 1) bwd_ring_kernel(const float* __restric
   }
   for (int st = 0; st < nst; ++st) {
     const int slot = st % BWD_STAGES;
+    // refill the slot consumed one iteration ago (no block-wide barrier: the warps drift up to a ring apart; warp 0
+    // only waits for the LAST stage's readers, who are at most one stage behind it)
+    if (threadIdx.x < 32 && st >= 1 && st - 1 + BWD_STAGES < nst) {
+      mbar_wait(&empty[(st - 1) % BWD_STAGES], (uint32_t)(((st - 1) / BWD_STAGES) & 1));
+      fence_proxy_async_smem();                            // generic-proxy reads before the async-proxy refill
+      issue(st - 1 + BWD_STAGES);
+    }
     mbar_wait(&full[slot], (uint32_t)((st / BWD_STAGES) & 1));
     const uint8_t* sdy = ring + slot * 2 * BWD_STAGE_BYTES + qg * 8;
     const uint8_t* sgp = sdy + BWD_STAGE_BYTES;
@@ -369,65 +413,84 @@ __global__ void __launch_bounds__(512, 1) bwd_ring_kernel(const float* __restric
         }
       }
     }
-    __syncthreads();                                         // every thread is done with this slot
-    if (threadIdx.x == 0 && st + BWD_STAGES < nst) {
-      fence_proxy_async_smem();                              // generic-proxy reads before the async-proxy refill
-      issue(st + BWD_STAGES);
-    }
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[slot]);  // this warp is done with the slot
   }
+  // Reduce the frame lanes through shared memory (the ring is idle now) and leave with COALESCED reductions: consecutive
+  // threads add consecutive floats of partial[b][c][0..K+1] (4 sectors per warp request).  One atomic per thread and
+  // accumulator straight from the registers was 44 requests of 32 sectors each per thread -- ncu showed the kernel's
+  // first stall reason to be lg_throttle (profiles/r02w_conv0.txt).
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(ring);               // [lanes][channels][K + 2]
+  const int per_lane = channels * (K + 2);
   if (active) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float* pp = partial + ((long long)b * channels + qg * 4 + j) * (K + 2);
-      atomicAdd(pp, acc0[j]);
+      float* pp = red + fl * per_lane + (qg * 4 + j) * (K + 2);
+      pp[0] = acc0[j];
+      pp[1] = 0.f;
 #pragma unroll
       for (int k = 0; k < K / 2; ++k) {
         float lo, hi;
         f2_unpack(acc[j][k], lo, hi);
-        atomicAdd(pp + 2 + 2 * k, lo);
-        atomicAdd(pp + 3 + 2 * k, hi);
+        pp[2 + 2 * k] = lo;
+        pp[3 + 2 * k] = hi;
       }
     }
   }
+  __syncthreads();
+  float* gp = partial + (long long)b * per_lane;
+  for (int i = threadIdx.x; i < per_lane; i += blockDim.x) {
+    float t = 0.f;
+    for (int l = 0; l < lanes; ++l) t += red[l * per_lane + i];
+    if ((i % (K + 2)) != 1) atomicAdd(gp + i, t);
+  }
 }
 
-// dw[c][j], dgamma[c], dbeta[c] from the per-(b,c) partial sums
-__global__ void bwd_finalize_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
-                                    const float* __restrict__ stats, const float* __restrict__ moments,
-                                    const float* __restrict__ partial, float* __restrict__ dw,
-                                    float* __restrict__ dgamma, float* __restrict__ dbeta, int batch, int channels,
-                                    long long t_out) {
+// dw[c][j], dgamma[c], dbeta[c] from the per-(b,c) partial sums.  One WARP per output, lanes over the batch (the first
+// version looped over the batch in one thread: 32 rounds of dependent L2-latency loads = 59 us for 6144 numbers).
+__global__ void __launch_bounds__(256) bwd_finalize_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+                                                           const float* __restrict__ stats, const float* __restrict__ moments,
+                                                           const float* __restrict__ partial, float* __restrict__ dw,
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta, int batch,
+                                                           int channels, long long t_out) {
   pdl_trigger();
   pdl_wait();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= channels * (K + 2)) return;
   const int c = i / (K + 2), j = i % (K + 2);
   const double inv_t = 1.0 / (double)t_out;
   double out = 0.0;
-  for (int b = 0; b < batch; ++b) {
+  for (int b = lane; b < batch; b += 32) {
     const float* pp = partial + ((long long)b * channels + c) * (K + 2);
     // sum_t dz*xhat = rstd * (sum_k w_k sum_t dz x[St+k] - mean * sum_t dz)   (xhat = (w.win - mean) * rstd)
     double pp1 = 0.0;
+#pragma unroll
     for (int l = 0; l < K; ++l) pp1 += (double)w[c * K + l] * (double)pp[2 + l];
-    pp1 = (pp1 - (double)stats[2 * ((long long)b * channels + c)] * (double)pp[0]) *
-          (double)stats[2 * ((long long)b * channels + c) + 1];
+    const double mean = stats[2 * ((long long)b * channels + c)];
+    const double rstd = stats[2 * ((long long)b * channels + c) + 1];
+    pp1 = (pp1 - mean * (double)pp[0]) * rstd;
     if (j == K) {
       out += pp1;  // dgamma
     } else if (j == K + 1) {
       out += pp[0];  // dbeta
     } else {
       const float* mo = moments + (long long)b * NMOM;
-      const double mean = stats[2 * ((long long)b * channels + c)];
-      const double rstd = stats[2 * ((long long)b * channels + c) + 1];
       double wr = 0.0;
+#pragma unroll
       for (int l = 0; l < K; ++l) wr += (double)w[c * K + l] * mo[K + l * K + j];
       const double sum_xhat_x = rstd * (wr - mean * mo[j]);
       out += (double)gamma[c] * rstd * ((double)pp[2 + j] - (double)pp[0] * inv_t * mo[j] - pp1 * inv_t * sum_xhat_x);
     }
   }
-  if (j == K) dgamma[c] = (float)out;
-  else if (j == K + 1) dbeta[c] = (float)out;
-  else dw[c * K + j] = (float)out;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) out += __shfl_xor_sync(0xffffffffu, out, o);
+  if (lane == 0) {
+    if (j == K) dgamma[c] = (float)out;
+    else if (j == K + 1) dbeta[c] = (float)out;
+    else dw[c * K + j] = (float)out;
+  }
 }
 
 
@@ -646,7 +709,7 @@ int smx_conv0_gn_gelu_bwd(const float* audio, const float* w, const float* gamma
                channels);
   }
   SMX_CHECK_CUDA(cudaGetLastError());
-  launch_pdl(bwd_finalize_kernel, dim3((int)ceil_div(channels * (K + 2), 128)), dim3(128), 0, st, w, gamma, stats, moments, partial, dw,
+  launch_pdl(bwd_finalize_kernel, dim3((int)ceil_div(channels * (K + 2), 8)), dim3(256), 0, st, w, gamma, stats, moments, partial, dw,
                                                                              dgamma, dbeta, (int)batch, channels, t_out);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
