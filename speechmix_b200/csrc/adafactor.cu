@@ -1,7 +1,8 @@
 // Multi-tensor Adafactor step (the optimizer of the reference recipe: ref:train.py:298 `optim="adafactor"`, i.e.
 // transformers.optimization.Adafactor with relative_step=False, scale_parameter=False, beta1=None as the HF Trainer
-// configures it).  All parameters of the model are updated by FOUR launches over a tile table instead of the ~15
-// small kernels per parameter of the eager implementation (~7000 launches per step for wav2vec2-base + bart-base):
+// configures it).  All parameters of the model are updated by SIX launches (four over a tile table, two block-per-slice)
+// instead of the ~15 small kernels per parameter of the eager implementation (~7000 launches per step for
+// wav2vec2-base + bart-base):
 //   1 stats     per 64 x 256 tile: row / column sums of g^2 -> fp32 atomics into per-tensor accumulators
 //   2 finalize  per (tensor, leading index): EMA of the factored second moments, mean of the row moments
 //   3 sumsq     per tile: u = g * rsqrt(row / mean(row)) * rsqrt(col)  (or g * rsqrt(v) for vectors), sum u^2

@@ -100,6 +100,9 @@ class GraphedTrainStep:
         self.x.copy_(x, non_blocking=True)
         self.y.copy_(y, non_blocking=True)
         self.graph.replay()
+        if self.opt_in_graph:          # the replayed optimizer step moved the masters (no Python hook runs in a replay)
+            ops.CACHE.dirty = True
+            ops.CACHE.epoch += 1
         K.LAUNCHES[0] += self.launches_per_step
         if self.reducer is not None:
             self.reducer.reduce_after_replay()

@@ -275,9 +275,11 @@ class SpeechMixEED(nn.Module):
         text_input_ids = text_input_ids.to(dev) if text_input_ids is not None else None
         if self.training and self.dropout_sites:
             ops.DROPOUT.begin_step(dev)      # new masks for this pass (device-side counter: survives CUDA-graph replay)
-        if encoder_outputs is None and torch.is_grad_enabled():
+        if encoder_outputs is None and (torch.is_grad_enabled() or ops.CACHE.dirty):
             # a training pass: the optimizer may have moved the fp32 masters since the last pass (fused
-            # optimizers do not bump tensor versions) -> refresh all bf16 working copies in one launch
+            # optimizers do not bump tensor versions) -> refresh all bf16 working copies in one launch.  A no_grad
+            # pass (evaluation in the middle of training, generate) does the same when an optimizer step has run
+            # since the last refresh (``dirty`` is set by a global optimizer-step hook and by graph replays).
             ops.CACHE.new_step()
         if encoder_outputs is None:
             # attention_mask is an extension: the reference calls the speech encoder without one
@@ -324,6 +326,8 @@ class SpeechMixEED(nn.Module):
                                      early_stopping=early_stopping, forced_eos_token_id=forced_eos_token_id)
         cfg = self.decoder_model.config
         eos = cfg.eos_token_id if eos_token_id is None else eos_token_id
+        if ops.CACHE.dirty:          # an optimizer step ran since the working copies were made
+            ops.CACHE.new_step()
         enc = self.encoder_model(input_values, attention_mask=attention_mask, output_hidden_states=True)
         B = input_values.shape[0]
         if use_cache:

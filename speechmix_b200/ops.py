@@ -30,6 +30,7 @@ class WeightCache:
     def __init__(self):
         self._store = {}
         self.epoch = 0
+        self.dirty = False  # an optimizer step ran since the last refresh (set by the hook below / graph replays)
         self._tables = {}   # device -> (signature, device table tensor, n_entries, total_chunks)
 
     def get(self, key_tensors, kind, build, simple=None):
@@ -56,6 +57,7 @@ class WeightCache:
     def new_step(self):
         """Start a new epoch and refresh every plain cast from its fp32 master in one launch."""
         self.epoch += 1
+        self.dirty = False
         per_dev = {}
         for key, ent in list(self._store.items()):
             spec = ent[4]
@@ -93,6 +95,18 @@ class WeightCache:
 
 
 CACHE = WeightCache()
+
+
+def _mark_weights_moved(optimizer, args, kwargs):
+    """global optimizer-step post-hook: ANY optimizer (fused ones do not bump tensor versions) may have moved the fp32
+    masters, so copies made before this point are stale for every later pass -- also a no_grad one."""
+    CACHE.dirty = True
+    CACHE.epoch += 1
+
+
+from torch.optim.optimizer import register_optimizer_step_post_hook as _register_step_hook  # noqa: E402
+
+_register_step_hook(_mark_weights_moved)
 
 
 def _rows_spec(val, srcs, f32):

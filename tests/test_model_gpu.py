@@ -317,6 +317,24 @@ def test_fused_optimizer_updates_reach_the_kernels(cuda_device):
     assert abs(drop_m - drop_o) < 0.35 * drop_o, (lo_hist, lm_hist)
 
 
+def test_no_grad_forward_after_fused_step_sees_the_new_weights(cuda_device):
+    """fused optimizers move the fp32 masters without bumping tensor versions; a no_grad forward (evaluation
+    in the middle of training, no train()/eval() toggle) must not run on the bf16 copies made BEFORE the step."""
+    fx = load_fixture("mini_eed_ds2")
+    ora, x, labels = build_oracle(fx)
+    mine = _mine_from(ora, fx, cuda_device)
+    xs, ys = x.to(cuda_device), labels.to(cuda_device)
+    opt = torch.optim.AdamW(mine.parameters(), lr=5e-3, weight_decay=0.0, fused=True)
+    l0 = mine(xs, labels=ys)["loss"]
+    l0.backward()
+    opt.step()
+    with torch.no_grad():
+        l_eval = float(mine(xs, labels=ys)["loss"])          # no toggle, no grad: must see the updated weights
+    l_train = float(mine(xs, labels=ys)["loss"])             # a training pass always refreshes
+    assert float(l0) - l_train > 0.05                        # the step moved the loss ...
+    assert abs(l_eval - l_train) < 2e-3, (float(l0), l_eval, l_train)   # ... and the no_grad pass saw it
+
+
 @pytest.mark.parametrize("text", ["t5-mini", "bart-mini"])
 def test_self_matches_oracle(text, cuda_device):
     """SpeechMixSelf (ref:speechmix/hf_model.py:505-583): CE + KLDiv(batchmean) + attention-projection MSE against
