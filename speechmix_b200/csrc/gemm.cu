@@ -168,7 +168,8 @@ __device__ __forceinline__ void epilogue_chunk_generic(const Params& p, float (&
       if (p.residual) v += __bfloat162float(p.residual[res_off + col]);
       if (p.out_f32) {
         float* cp = reinterpret_cast<float*>(p.c) + c_off + col;
-        *cp = p.accumulate_f32 ? *cp + v : v;
+        if (p.accumulate_f32 && p.atomic) atomicAdd(cp, v);          // split contraction: several CTAs add into this tile
+        else *cp = p.accumulate_f32 ? *cp + v : v;
       } else {
         reinterpret_cast<bf16*>(p.c)[c_off + col] = __float2bfloat16(v);
       }
@@ -230,7 +231,10 @@ __device__ __forceinline__ void epilogue_chunk_fast(const Params& p, float (&f)[
   }
   if (p.out_f32) {
     float* cp = reinterpret_cast<float*>(p.c) + c_off + col0;
-    if (p.accumulate_f32) {
+    if (p.accumulate_f32 && p.atomic) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) red_add_v4(cp + j, f[j], f[j + 1], f[j + 2], f[j + 3]);
+    } else if (p.accumulate_f32) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         float4 o = *reinterpret_cast<float4*>(cp + j);
@@ -1017,6 +1021,12 @@ int smx::gemm::run(const SmxGemm* g, const LmExtra* lm, void* stream) {
   p.m_tiles = p.m_tiles_per_batch * (int)g->batches;
   p.kblocks = (int)ceil_div(g->k, BK);
   p.kb_per_batch = p.kblocks;
+  // split contraction for fp32-ACCUMULATING outputs (the LM-head data gradient: 24 output tiles, K = 8192 per vocabulary
+  // chunk): partial sums are added with fp32 reductions, which the accumulate contract (C += A.B) already allows
+  if (p.out_f32 && p.accumulate_f32 && g->split_k > 1 && g->nseg == 1 && !g->bias && !g->residual && g->act == SMX_ACT_NONE) {
+    p.split_k = g->split_k < p.kblocks ? g->split_k : p.kblocks;
+    p.atomic = 1;
+  }
   // raster order: the LARGER operand should stream from DRAM once (see decode_tile)
   p.n_fastest = (g->m * (int64_t)g->batches > g->n) ? 1 : 0;
   const uint32_t a_box[3] = {64, 128, 1};

@@ -777,6 +777,9 @@ def gemm_nn_acc_f32(a, a_cols, w_rows_view, out_f32, alpha=1.0, accumulate=True)
     g.m, g.n, g.k, g.batches = M, K, a_cols, 1
     _set_seg(g, 1, a_cols)
     g.accumulate = 1 if accumulate else 0
+    if accumulate:      # few output tiles, long contraction: split it (fp32 reductions into the accumulating output)
+        tiles = math.ceil(M / 256) * math.ceil(K / 256)
+        g.split_k = _pick_split(tiles, math.ceil(a_cols / 64))
     _epilogue(g, out_f32, K, M * K, None, ACT_NONE, None, None, None, None, alpha)
     _run_gemm(g)
 

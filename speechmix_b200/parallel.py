@@ -81,12 +81,19 @@ class GradientAllReducer:
         """bytes each rank hands to the collective per step"""
         return sum(w.numel() * w.element_size() for w in self.wire)
 
-    def _views(self, bi):
+    def _views(self, bi, wire=False):
+        """per-parameter slices of bucket ``bi``: of the fp32 gradient buffer, or (``wire``) of the bf16 payload"""
+        buf = self.wire[bi] if wire else self.flat[bi]
         out, off = [], 0
         for p in self.buckets[bi]:
-            out.append(self.flat[bi][off:off + p.numel()].view_as(p))
+            out.append(buf[off:off + p.numel()].view_as(p))
             off += p.numel()
         return out
+
+    def _pack(self, bi, grads):
+        """gradients -> collective payload.  bf16 payload: ONE converting copy straight into the wire buffer (the fp32
+        bucket is only written by ``_unpack`` after the collective); fp32 payload: the bucket is the payload."""
+        torch._foreach_copy_(self._views(bi, wire=self.payload == "bf16"), grads)
 
     def _hook(self, p):
         if not self.enabled:    # gradient accumulation micro-step (no_sync): keep local gradients
@@ -123,13 +130,10 @@ class GradientAllReducer:
         self.pending = [len(b) for b in self.buckets]
 
     def _launch_captured(self, bi):
-        views = self._views(bi)
         grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.buckets[bi]]
-        torch._foreach_copy_(views, grads)
-        for p, v in zip(self.buckets[bi], views):
-            p.grad = v
-        if self.payload == "bf16":
-            self.wire[bi].copy_(self.flat[bi])
+        self._pack(bi, grads)
+        for p, v in zip(self.buckets[bi], self._views(bi)):
+            p.grad = v          # valid after the collective + _unpack, i.e. when the optimizer reads it
         self.events[bi].record()
         self.order.append(bi)
 
@@ -143,9 +147,8 @@ class GradientAllReducer:
             for bi in self.order:
                 self.comm_stream.wait_event(self.events[bi])
                 works.append(dist.all_reduce(self.wire[bi], op=op, group=self.group, async_op=True))
-            for w in works:
+            for w, bi in zip(works, self.order):     # bucket i is unpacked while the later collectives are in flight
                 w.wait()
-            for bi in self.order:
                 self._unpack(bi)
         main.wait_stream(self.comm_stream)
 
@@ -159,13 +162,10 @@ class GradientAllReducer:
     def _launch(self, bi):
         if self.graph_mode:
             return self._launch_captured(bi)
-        views = self._views(bi)
         grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.buckets[bi]]
-        torch._foreach_copy_(views, grads)
-        for p, v in zip(self.buckets[bi], views):
+        self._pack(bi, grads)
+        for p, v in zip(self.buckets[bi], self._views(bi)):
             p.grad = v          # gradients live in the bucket from here on: no copy back after the collective
-        if self.payload == "bf16":
-            self.wire[bi].copy_(self.flat[bi])
         op = dist.ReduceOp.AVG if self.avg_in_collective else dist.ReduceOp.SUM
         self.works[bi] = dist.all_reduce(self.wire[bi], op=op, group=self.group, async_op=True)
 
@@ -191,9 +191,7 @@ class GradientAllReducer:
         for bi, b in enumerate(self.buckets):
             grads = [p.grad for p in b]
             assert all(g is not None for g in grads), "reduce_inplace: every bucketed parameter needs a gradient"
-            torch._foreach_copy_(self._views(bi), grads)
-            if self.payload == "bf16":
-                self.wire[bi].copy_(self.flat[bi])
+            self._pack(bi, grads)
             op = dist.ReduceOp.AVG if self.avg_in_collective else dist.ReduceOp.SUM
             works.append(dist.all_reduce(self.wire[bi], op=op, group=self.group, async_op=True))
         for bi, b in enumerate(self.buckets):
