@@ -180,6 +180,8 @@ int smx_adafactor_step(const SmxAdafactorTensor* tensors, int32_t n_tensors, con
                        float weight_decay, int64_t* step_dev, float decay_rate, void* stream);
 
 int smx_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
+/* out = a * b: gate product of the gated feed-forward of T5 v1.1 / mT5 (hf:models/t5/modeling_t5.py T5DenseGatedActDense) */
+int smx_mul_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
 int smx_act_bf16(const void* x, void* y, int64_t n, int act, void* stream);
 /* out = dy * act'(pre), act in {SMX_ACT_GELU, SMX_ACT_RELU} */
 int smx_dact_bf16(const void* dy, const void* pre, void* out, int64_t n, int act, void* stream);

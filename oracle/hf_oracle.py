@@ -121,6 +121,9 @@ def text_config(kind: str = "bart-base", deterministic: bool = True):
     elif kind == "t5-base":
         cfg = T5Config(d_model=768, d_kv=64, d_ff=3072, num_layers=12, num_heads=12,
                        vocab_size=32128, feed_forward_proj="relu")
+    elif kind == "t5v11-mini":    # t5 v1.1 / mT5 / flan-T5 style: gated-GELU feed-forward, untied LM head
+        cfg = T5Config(d_model=256, d_kv=64, d_ff=512, num_layers=2, num_heads=4, vocab_size=1000,
+                       feed_forward_proj="gated-gelu", tie_word_embeddings=False, decoder_start_token_id=0)
     elif kind == "t5-mini":
         cfg = T5Config(d_model=256, d_kv=64, d_ff=512, num_layers=2, num_heads=4,
                        vocab_size=1000, feed_forward_proj="relu", decoder_start_token_id=0)

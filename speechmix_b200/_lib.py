@@ -84,6 +84,7 @@ SIGNATURES = {
     "smx_weightnorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _P]),
     "smx_multi_cast": (c_int, [_P, c_int32, c_int32, _P]),
     "smx_add_bf16": (c_int, [_P, _P, _P, _I64, _P]),
+    "smx_mul_bf16": (c_int, [_P, _P, _P, _I64, _P]),
     "smx_act_bf16": (c_int, [_P, _P, _I64, c_int, _P]),
     "smx_dact_bf16": (c_int, [_P, _P, _P, _I64, c_int, _P]),
     "smx_pack_conv_weight": (c_int, [_P, _P, _I64, _I64, _I64, _P]),

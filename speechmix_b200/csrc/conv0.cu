@@ -199,108 +199,13 @@ __global__ void __launch_bounds__(256, 2) fwd_kernel(const float* __restrict__ a
 // kernel is two streaming reads plus 11 FMAs per element.
 // partial[b][c][0] = sum dz, [2+k] = sum_t dz * x[S t + k]; [1] (= sum dz*xhat) follows algebraically in finalize.
 constexpr int BWD_FR = 1024;
-// Issue-bound, not HBM-bound, as first written (~17 issue slots per element: 10 scalar FMAs, 2.5 LDS, unpacking): the
-// ten window FMAs of a channel now run as FIVE packed-pair FMAs (FFMA2: dz replicated x (win[k], win[k+1]) accumulating
-// (acc[k], acc[k+1])), and the window pairs come from shared memory as 8-byte loads.  S = 5 is odd, so the window of an
-// odd frame starts at an odd float: a second copy of the waveform slab shifted by one float keeps every pair load
-// 8-byte aligned (frame parity picks the copy).
-__global__ void __launch_bounds__(256, 2) bwd_kernel(const float* __restrict__ audio, const bf16* __restrict__ dy,
-                                                  const bf16* __restrict__ gprime, float* __restrict__ partial,
-                                                  long long n_samples, long long t_out, int channels) {
-  pdl_trigger();
-  pdl_wait();
-  static_assert(K % 2 == 0 && (S & 1) == 1, "pair loads assume an even window and an odd stride");
-  constexpr int XS = BWD_FR * S + K + 2;
-  __shared__ __align__(16) float xs[2][XS];      // xs[1][i] = xs[0][i + 1]
-  const int b = blockIdx.y;
-  const long long t0 = (long long)blockIdx.x * BWD_FR;
-  const long long nfr = (t_out - t0) < BWD_FR ? (t_out - t0) : BWD_FR;
-  const float* x = audio + (long long)b * n_samples + t0 * S;
-  const int nload = (int)nfr * S + (K - S);
-  for (int i = threadIdx.x; i < nload; i += blockDim.x) {
-    const float v = x[i];
-    xs[0][i] = v;
-    if (i > 0) xs[1][i - 1] = v;
-  }
-  __syncthreads();
-  const int quads = channels / 4;
-  const int lanes = blockDim.x / 128;  // 2 frame lanes
-  for (int qg = threadIdx.x % 128; qg < quads; qg += 128) {
-    const int c0 = qg * 4;
-    f32x2 acc[4][K / 2];
-    float acc0[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      acc0[j] = 0.f;
-#pragma unroll
-      for (int k = 0; k < K / 2; ++k) acc[j][k] = f2_rep(0.f);
-    }
-    const long long base = ((long long)b * t_out + t0) * channels + c0;
-    // frames in groups of 4 with the NEXT group's 8 loads issued before the current group's FMAs
-    constexpr int G = 4;
-    uint2 cu[G], cg[G];
-    const int f_first = threadIdx.x / 128;
-    auto load_group = [&](int f0, uint2 (&u)[G], uint2 (&g)[G]) {
-#pragma unroll
-      for (int i = 0; i < G; ++i) {
-        const int f = f0 + i * lanes;
-        if (f < nfr) {
-          u[i] = *reinterpret_cast<const uint2*>(dy + base + (long long)f * channels);
-          g[i] = *reinterpret_cast<const uint2*>(gprime + base + (long long)f * channels);
-        } else {
-          u[i] = make_uint2(0u, 0u);
-          g[i] = make_uint2(0u, 0u);
-        }
-      }
-    };
-    load_group(f_first, cu, cg);
-    for (int f0 = f_first; f0 < nfr; f0 += G * lanes) {
-      uint2 nu[G], ng[G];
-      load_group(f0 + G * lanes, nu, ng);
-#pragma unroll
-      for (int i = 0; i < G; ++i) {
-        const int f = f0 + i * lanes;
-        const int fs = f < nfr ? f : 0;   // out-of-range frames carry dz = 0
-        // window pairs (win[2k], win[2k+1]): float offset fs*S is even for even frames (copy 0) and odd for odd
-        // frames, where copy 1 holds the same data one float earlier
-        const int odd = fs & 1;
-        const f32x2* wp = reinterpret_cast<const f32x2*>(&xs[odd][fs * S - odd]);
-        f32x2 win[K / 2];
-#pragma unroll
-        for (int k = 0; k < K / 2; ++k) win[k] = wp[k];
-        const float dz[4] = {bf16_lo(cu[i].x) * bf16_lo(cg[i].x), bf16_hi(cu[i].x) * bf16_hi(cg[i].x),
-                             bf16_lo(cu[i].y) * bf16_lo(cg[i].y), bf16_hi(cu[i].y) * bf16_hi(cg[i].y)};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          acc0[j] += dz[j];
-          const f32x2 d2 = f2_rep(dz[j]);
-#pragma unroll
-          for (int k = 0; k < K / 2; ++k) acc[j][k] = f2_fma(d2, win[k], acc[j][k]);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < G; ++i) cu[i] = nu[i], cg[i] = ng[i];
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float* pp = partial + ((long long)b * channels + c0 + j) * (K + 2);
-      atomicAdd(pp, acc0[j]);
-#pragma unroll
-      for (int k = 0; k < K / 2; ++k) {
-        float lo, hi;
-        f2_unpack(acc[j][k], lo, hi);
-        atomicAdd(pp + 2 + 2 * k, lo);
-        atomicAdd(pp + 3 + 2 * k, hi);
-      }
-    }
-  }
-}
-
-// Ring-fed version (channels <= 512): the register-prefetch kernel above keeps 64 bytes per thread in flight = 32 KiB
-// per SM, which by Little's law is ~3.2 TB/s at the ~1.5 us loaded HBM latency -- exactly what it measured.  A block's
-// dy / gelu' tile is ONE contiguous chunk of memory per stream (channels-last, consecutive frames), so here thread 0
-// streams it through a 5-stage shared-memory ring with 16 KiB bulk copies per stream and stage (160 KiB in flight per
-// SM, no registers spent on prefetching) and every thread reads its 8-byte quads back from shared memory.
+// The first version prefetched into registers: 64 bytes per thread in flight = 32 KiB per SM, which by Little's law is
+// ~3.2 TB/s at the ~1.5 us loaded HBM latency -- exactly what it measured (0.98 ms) -- and it was issue-heavy (ten scalar
+// FMAs per element).  A block's dy / gelu' tile is ONE contiguous chunk of memory per stream (channels-last, consecutive
+// frames), so warp 0 streams it through a 5-stage shared-memory ring of bulk copies (160 KiB in flight per SM, no
+// registers spent on prefetching) and every thread reads its 8-byte quads back from shared memory.  The ten window FMAs
+// of a channel run as FIVE packed-pair FMAs (dz replicated x (win[k], win[k+1])); S = 5 is odd, so a second copy of the
+// waveform slab shifted by one float keeps the 8-byte window-pair loads of odd frames aligned.  channels <= 512.
 constexpr int BWD_STAGES = 5;
 constexpr int BWD_STAGE_BYTES = 16384;                      // per stream and stage
 constexpr int BWD_XS = BWD_FR * S + K + 2;                  // floats per waveform copy
@@ -695,19 +600,16 @@ int smx_conv0_gn_gelu_bwd(const float* audio, const float* w, const float* gamma
   cudaStream_t st = (cudaStream_t)stream;
   SMX_CHECK_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * (K + 2) * batch * channels, st));
   const dim3 grid((unsigned)ceil_div(t_out, BWD_FR), (unsigned)batch);
-  const bool ring_ok = channels <= 512 && channels % 8 == 0 && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(gprime)) & 15) == 0;
-  if (ring_ok) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      SMX_CHECK_CUDA(cudaFuncSetAttribute(bwd_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_RING_SMEM));
-      attr_set = true;
-    }
-    launch_pdl(bwd_ring_kernel, grid, dim3(512), BWD_RING_SMEM, st, audio, (const bf16*)dy, (const bf16*)gprime, partial,
-               n_samples, t_out, channels);
-  } else {
-    launch_pdl(bwd_kernel, grid, dim3(256), 0, st, audio, (const bf16*)dy, (const bf16*)gprime, partial, n_samples, t_out,
-               channels);
+  SMX_REQUIRE(channels <= 512 && channels % 8 == 0, "conv0 bwd: channels %d unsupported (multiple of 8, <= 512)", channels);
+  SMX_REQUIRE(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(gprime)) & 15) == 0,
+              "conv0 bwd: dy / gprime must be 16-byte aligned");
+  static bool attr_set = false;
+  if (!attr_set) {
+    SMX_CHECK_CUDA(cudaFuncSetAttribute(bwd_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_RING_SMEM));
+    attr_set = true;
   }
+  launch_pdl(bwd_ring_kernel, grid, dim3(512), BWD_RING_SMEM, st, audio, (const bf16*)dy, (const bf16*)gprime, partial,
+             n_samples, t_out, channels);
   SMX_CHECK_CUDA(cudaGetLastError());
   launch_pdl(bwd_finalize_kernel, dim3((int)ceil_div(channels * (K + 2), 8)), dim3(256), 0, st, w, gamma, stats, moments, partial, dw,
                                                                              dgamma, dbeta, (int)batch, channels, t_out);

@@ -567,6 +567,16 @@ def add_bf16(a, b):
     return out
 
 
+def mul_bf16(a, b):
+    """a * b elementwise (bf16; fp32 tensors in the fp32 verification mode)"""
+    if FP32_MODE or a.dtype != BF16:
+        return a * b
+    assert a.shape == b.shape and a.is_contiguous() and b.is_contiguous()
+    out = torch.empty_like(a)
+    _lib.check(_L().smx_mul_bf16(_ptr(a), _ptr(b), _ptr(out), a.numel(), _stream()), "mul")
+    return out
+
+
 def dact(dy, pre, act=ACT_GELU):
     out = torch.empty_like(dy)
     _lib.check(_L().smx_dact_bf16(_ptr(dy), _ptr(pre), _ptr(out), dy.numel(), act, _stream()), "dact")

@@ -696,6 +696,76 @@ class ConvS2Fn(torch.autograd.Function):
         return dx, dw, db, None
 
 
+class GatedFFNBlockFn(torch.autograd.Function):
+    """T5 v1.1 / mT5 / flan-T5 feed-forward (hf:models/t5/modeling_t5.py T5DenseGatedActDense + T5LayerFF, pre-RMSNorm):
+        y = x + Wo ( act(W0 n) * (W1 n) ),   n = RMSNorm(x)
+    Kernels: the W0 GEMM's epilogue evaluates act and act' (stored, so the backward never recomputes it), the gate
+    product and its two gradients are one elementwise kernel each, the residual rides in the Wo GEMM's epilogue; in
+    the backward the second data-gradient GEMM adds the first one's result in its epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, cfg, w0, w1, wo, ln_w):
+        eps = cfg["eps"]
+        act, _ = _act_codes(cfg.get("act", "gelu_new"))
+        shp = x.shape
+        H = shp[-1]
+        x2 = x.reshape(-1, H)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        n, _, mean, rstd = K.layernorm_fwd(x2, ln_w.detach(), None, eps, rms_only=True)
+        need_bwd = any(ctx.needs_input_grad)
+        if not need_bwd:                                                 # inference (also the fp32 verification mode)
+            g = K.linear_fwd(n, w16(w0), None, act=ACT_GELU if act == ACT_GELU_G else act)
+            gp = None
+        elif act == ACT_RELU:
+            g, pre0 = K.linear_fwd(n, w16(w0), None, act=ACT_RELU, want_pre=True)
+            gp = K.dact(torch.ones_like(pre0), pre0, ACT_RELU)          # relu'(pre)
+        else:
+            g, gp = K.linear_fwd(n, w16(w0), None, act=act, want_pre=True)   # GELU_G: aux output = act'(pre)
+        u = K.linear_fwd(n, w16(w1), None)
+        h = K.mul_bf16(g, u)
+        drop_act = _drop_site(cfg.get("p_act"), x.device, "elementwise", tuple(shp[:-1]) + (w0.shape[0],))
+        drop_h = _drop_site(cfg.get("p_hidden"), x.device, "elementwise", shp)
+        if drop_act is not None:
+            h = K.dropout(h, *drop_act)
+        if drop_h is None:
+            y = K.linear_fwd(h, w16(wo), None, residual=x2)
+        else:
+            y = K.dropout(K.linear_fwd(h, w16(wo), None), *drop_h, residual=x2)
+        m = K.mul_bf16(u, gp) if need_bwd else None                      # d h / d pre0 (before dropout)
+        ctx.save_for_backward(x2, n, mean, rstd, g, m, h, ln_w)
+        ctx.shp, ctx.drop_act, ctx.drop_h, ctx.wrefs = shp, drop_act, drop_h, (w0, w1, wo)
+        return y.view(shp)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, n, mean, rstd, g, m, h, ln_w = ctx.saved_tensors
+        w0, w1, wo = ctx.wrefs
+        ds_res = dy.reshape(-1, ctx.shp[-1]).contiguous()
+        ds = K.dropout(ds_res, *ctx.drop_h) if ctx.drop_h is not None else ds_res
+        dwo = K.linear_wgrad(ds, h) if _need(ctx, 4) else None
+        dh = K.linear_dgrad(ds, w16(wo))
+        if ctx.drop_act is not None:
+            dh = K.dropout(dh, *ctx.drop_act)
+        dpre0 = K.mul_bf16(dh, m)
+        du = K.mul_bf16(dh, g)
+        dw0 = K.linear_wgrad(dpre0, n) if _need(ctx, 2) else None
+        dw1 = K.linear_wgrad(du, n) if _need(ctx, 3) else None
+        dn = K.linear_dgrad(du, w16(w1), residual=K.linear_dgrad(dpre0, w16(w0)))
+        dx, dlnw, _ = K.layernorm_bwd(dn, x2, ln_w.detach(), mean, rstd, dres=ds_res, rms_only=True, want_dbeta=False)
+        return dx.view(ctx.shp), None, dw0, dw1, dwo, dlnw
+
+
+@torch.no_grad()
+def decode_gated_ffn_step(x2, cfg, w0, w1, wo, ln_w):
+    act, _ = _act_codes(cfg.get("act", "gelu_new"))
+    if act == ACT_GELU_G:
+        act = ACT_GELU
+    a_in = _ln_maybe(x2, ln_w, None, cfg["eps"], True)
+    h = K.mul_bf16(K.linear_fwd(a_in, w16(w0), None, act=act), K.linear_fwd(a_in, w16(w1), None))
+    return K.linear_fwd(h, w16(wo), None, residual=x2)
+
+
 class ConvK2Fn(torch.autograd.Function):
     """Conv1d(C -> N, kernel 2, stride 2, bias) on channels-last input through the copy-free frame-group view
     (K.conv_ks_*): the non-final down_scale length adapters (ref:speechmix/hf_model.py:253-266, 426-427)."""

@@ -310,11 +310,34 @@ class _T5DenseActDense(nn.Module):
         self.wo = nn.Linear(config.d_ff, config.d_model, bias=False)
 
 
+class _T5DenseGatedActDense(nn.Module):
+    """hf:...t5.py T5DenseGatedActDense (t5 v1.1, mT5, flan-T5): wo(act(wi_0 x) * wi_1 x)"""
+
+    def __init__(self, config):
+        super().__init__()
+        self.wi_0 = nn.Linear(config.d_model, config.d_ff, bias=False)
+        self.wi_1 = nn.Linear(config.d_model, config.d_ff, bias=False)
+        self.wo = nn.Linear(config.d_ff, config.d_model, bias=False)
+
+
 class _T5LayerFF(nn.Module):
     def __init__(self, config):
         super().__init__()
-        self.DenseReluDense = _T5DenseActDense(config)
+        self.gated = bool(config.is_gated_act)
+        self.DenseReluDense = _T5DenseGatedActDense(config) if self.gated else _T5DenseActDense(config)
         self.layer_norm = _RMSNorm(config.d_model)
+
+    def forward(self, x, cfg):
+        d = self.DenseReluDense
+        if self.gated:
+            return ops.GatedFFNBlockFn.apply(x, cfg, d.wi_0.weight, d.wi_1.weight, d.wo.weight, self.layer_norm.weight)
+        return ops.FFNBlockFn.apply(x, cfg, d.wi.weight, None, d.wo.weight, None, self.layer_norm.weight, None)
+
+    def decode_step(self, x2, cfg):
+        d = self.DenseReluDense
+        if self.gated:
+            return ops.decode_gated_ffn_step(x2, cfg, d.wi_0.weight, d.wi_1.weight, d.wo.weight, self.layer_norm.weight)
+        return ops.decode_ffn_step(x2, cfg, d.wi.weight, None, d.wo.weight, None, self.layer_norm.weight, None)
 
 
 class _T5Block(nn.Module):
@@ -342,9 +365,7 @@ class _T5Block(nn.Module):
             ca = self.layer[1]
             x = ops.AttnBlockFn.apply(x, enc, cfg_cross, *ca.EncDecAttention.params(), ca.layer_norm.weight, None,
                                       None)
-        ff = self.layer[-1]
-        return ops.FFNBlockFn.apply(x, cfg_cross, ff.DenseReluDense.wi.weight, None, ff.DenseReluDense.wo.weight,
-                                    None, ff.layer_norm.weight, None)
+        return self.layer[-1](x, cfg_cross)
 
 
 class _T5Stack(nn.Module):
@@ -395,8 +416,8 @@ class T5Seq2SeqLM(nn.Module):
 
     def __init__(self, config):
         super().__init__()
-        if config.is_gated_act or config.dense_act_fn != "relu":
-            raise NotImplementedError("gated / non-ReLU T5 feed-forward (t5 v1.1) is not wired to the kernels")
+        if config.dense_act_fn not in ("relu", "gelu", "gelu_new"):
+            raise NotImplementedError("T5 feed-forward activation %r is not wired to the kernels" % (config.dense_act_fn,))
         if config.d_kv != 64:
             raise NotImplementedError("attention kernels are specialised for head_dim 64")
         self.config = config
@@ -469,8 +490,7 @@ class T5Seq2SeqLM(nn.Module):
             a = ca.EncDecAttention
             x = ops.decode_cross_attn_step(x, blk.cfg_cross, a.q.weight, None, a.o.weight, None, ca.layer_norm.weight,
                                            None, cross[blk._index])
-            x = ops.decode_ffn_step(x, blk.cfg_cross, ff.DenseReluDense.wi.weight, None, ff.DenseReluDense.wo.weight,
-                                    None, ff.layer_norm.weight, None)
+            x = ff.decode_step(x, blk.cfg_cross)
             if dec.layer_output_hook is not None:       # SpeechMixAdapter (ref:speechmix/hf_model.py:486-502)
                 x = dec.layer_output_hook(blk._index, x.view(B, 1, D)).reshape(B, D)
         return ops._ln_maybe(x, dec.final_layer_norm.weight, None, cfg.layer_norm_epsilon, True)

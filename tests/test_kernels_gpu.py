@@ -78,3 +78,19 @@ def test_fused_adafactor_matches_transformers(weight_decay, cuda_device):
     mine.step()
     assert float((late - late_ref).abs().max()) < 2e-6 and mine.state[late]["step"] == 1
     assert float((ref_p[2] - my_p[2]).abs().max()) < 5e-6
+
+
+@pytest.mark.parametrize("env", [{"SMX_ATTN_POLY": "4"}, {"SMX_ATTN_FWD_V1": "1"}, {"SMX_PDL": "0"}])
+def test_attention_forward_env_selected_variants(env, cuda_device):
+    """The A/B switches of the attention forward are read once per process, so each runs in its own interpreter:
+    SMX_ATTN_POLY=4 (every fourth pair of exponentials on the FMA pipe: Cody-Waite + cubic instead of MUFU.EX2),
+    SMX_ATTN_FWD_V1=1 (the general kernel also for the plain non-causal case), SMX_PDL=0 (no programmatic dependent
+    launch).  Same parity cases, same bounds."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for case in ("fwd_small", "fwd2_rescale"):
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "probe_attn.py"), "--case", case],
+                           env=dict(os.environ, **env), capture_output=True, text=True, timeout=600, cwd=root)
+        assert r.returncode == 0 and '"ok": true' in r.stdout, (env, case, r.stdout[-2000:], r.stderr[-2000:])

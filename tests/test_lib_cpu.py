@@ -83,7 +83,7 @@ def test_state_dict_layout_matches_reference_oracle():
     """drop-in boundary: same parameter names / shapes / requires_grad bookkeeping as HFSpeechMixEED."""
     from oracle import hf_oracle as O
     from speechmix_b200 import SpeechMixEED
-    for tx in ("bart-mini", "mbart-mini"):
+    for tx in ("bart-mini", "mbart-mini", "t5-mini", "t5v11-mini"):
         spc, txc = O.speech_config("mini"), O.text_config(tx)
         s, t = O.build_backbones(spc, txc)
         ora = O.OracleEED(s, t, down_scale=4, weighted_sum=True, fixed_parameters=True)

@@ -105,6 +105,41 @@ def test_bridge_projector_fusion_matches_oracle(name, mode, cuda_device):
         assert float((g - r).norm()) <= 5e-2 * float(r.norm()) + 1e-7, (k, float((g - r).norm()), float(r.norm()))
 
 
+def test_t5_v11_gated_feed_forward_matches_oracle(cuda_device):
+    """T5 v1.1 / mT5 / flan-T5 text backbones (gated-GELU feed-forward, untied LM head; hf:...t5.py T5DenseGatedActDense)
+    behind the same SpeechMixEED glue: loss, logits, ids, every gradient, and KV-cached greedy decode = full recompute."""
+    fx = dict(load_fixture("mini_eed_ds2"), text="t5v11-mini", kwargs={"down_scale": 2})
+    ora, x, labels = build_oracle(fx)
+    mine = _mine_from(ora, fx, cuda_device)
+    assert mine.list_grad == ora.list_grad
+    ref = ora(x, labels=labels, keep_full_logits=True)
+    out = mine(x.to(cuda_device), labels=labels.to(cuda_device))
+    assert abs(float(out["loss"]) - float(ref["loss"])) < 6e-3
+    assert _rel(mine.decoder_model.full_logits(out["decoder_last_hidden_state"]), ref["full_logits"]) < 2e-2
+    assert _ids_agree(out["logits"], ref["logits"])
+    ref["loss"].backward()
+    out["loss"].backward()
+    po, pm = dict(ora.named_parameters()), dict(mine.named_parameters())
+    scale = max(float(p.grad.norm()) for p in po.values() if p.grad is not None)
+    checked = 0
+    for k, p in po.items():
+        if p.grad is None:
+            continue
+        err = float((pm[k].grad.cpu() - p.grad).norm())
+        assert err <= 8e-2 * float(p.grad.norm()) + 2e-4 * scale, (k, err, float(p.grad.norm()))
+        checked += 1
+    assert checked == len(mine.list_grad) and any("wi_1" in k for k in po)
+    mine.eval()
+    xs = x.to(cuda_device)
+    a = mine.generate(xs, max_length=10, eos_token_id=-1, use_cache=True).cpu()
+    b = mine.generate(xs, max_length=10, eos_token_id=-1, use_cache=False).cpu()
+    assert torch.equal(a, b)
+    ora.eval()
+    from oracle import hf_oracle as O
+    ids32 = mine.generate(xs, max_length=10, eos_token_id=-1, precision="fp32").cpu()
+    assert torch.equal(ids32, O.greedy_full_recompute(ora, x, max_length=10, eos_token_id=-1))
+
+
 def test_mbart_pre_ln_stack(cuda_device):
     fx = dict(load_fixture("mini_eed_ds2"), text="mbart-mini", kwargs={"down_scale": 4})
     ora, x, labels = build_oracle(fx)
