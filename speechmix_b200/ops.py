@@ -713,8 +713,8 @@ class GatedFFNBlockFn(torch.autograd.Function):
         if not x2.is_contiguous():
             x2 = x2.contiguous()
         n, _, mean, rstd = K.layernorm_fwd(x2, ln_w.detach(), None, eps, rms_only=True)
-        need_bwd = any(ctx.needs_input_grad)
-        if not need_bwd:                                                 # inference (also the fp32 verification mode)
+        need_bwd = not K.FP32_MODE       # the fp32 verification mode is inference-only
+        if not need_bwd:
             g = K.linear_fwd(n, w16(w0), None, act=ACT_GELU if act == ACT_GELU_G else act)
             gp = None
         elif act == ACT_RELU:

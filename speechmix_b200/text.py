@@ -439,7 +439,14 @@ class T5Seq2SeqLM(nn.Module):
 
     def lm_head_params(self):
         """(weight [V, D], bias or None, logit scale)  hf:...t5.py:1105-1110"""
-        return self.lm_head.weight, None, (self.config.d_model ** -0.5) if self.config.tie_word_embeddings else 1.0
+        # original T5 scales the decoder output by d_model^-0.5 before the (tied) LM head, v1.1 / mT5 do not.  transformers
+        # >= 5 carries that as ``scale_decoder_outputs`` (set from the checkpoint's ``tie_word_embeddings``, which it then
+        # forces to True); older configs only have ``tie_word_embeddings``.
+        cfg = self.config
+        scaled = getattr(cfg, "scale_decoder_outputs", None)
+        if scaled is None:
+            scaled = bool(cfg.tie_word_embeddings)
+        return self.lm_head.weight, None, (cfg.d_model ** -0.5) if scaled else 1.0
 
     def encode(self, input_ids=None, inputs_embeds=None, output_hidden_states=False):
         return self.encoder(input_ids=input_ids, inputs_embeds=inputs_embeds, output_hidden_states=output_hidden_states)
