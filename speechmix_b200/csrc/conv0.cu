@@ -202,7 +202,7 @@ constexpr int BWD_FR = 1024;
 // The first version prefetched into registers: 64 bytes per thread in flight = 32 KiB per SM, which by Little's law is
 // ~3.2 TB/s at the ~1.5 us loaded HBM latency -- exactly what it measured (0.98 ms) -- and it was issue-heavy (ten scalar
 // FMAs per element).  A block's dy / gelu' tile is ONE contiguous chunk of memory per stream (channels-last, consecutive
-// frames), so warp 0 streams it through a 5-stage shared-memory ring of bulk copies (160 KiB in flight per SM, no
+// frames), so thread 0 streams it through a 5-stage shared-memory ring of bulk copies (160 KiB in flight per SM, no
 // registers spent on prefetching) and every thread reads its 8-byte quads back from shared memory.  The ten window FMAs
 // of a channel run as FIVE packed-pair FMAs (dz replicated x (win[k], win[k+1])); S = 5 is odd, so a second copy of the
 // waveform slab shifted by one float keeps the 8-byte window-pair loads of odd frames aligned.  channels <= 512.
@@ -240,27 +240,18 @@ __global__ void __launch_bounds__(512, 1) bwd_ring_kernel(const float* __restric
     fence_barrier_init();
   }
   __syncthreads();
-  // warp 0 refills a slot: lane 0 arms the barrier, lanes 0..7 each issue one <= 4 KiB piece (four per stream) -- one
-  // 16 KiB copy per stream left the copy engine with two requests in flight per stage
-  auto issue = [&](int st) {                                 // all lanes of warp 0
+  // thread 0 refills a slot with ONE bulk copy per stream (<= 16 KiB each).  Splitting a refill into eight 4 KiB pieces
+  // issued by eight lanes was measured slower: 908 vs 779 us (profiles/r02x_ncu_rowwise.txt, r02fin).
+  auto issue = [&](int st) {                                 // thread 0 only
     const int slot = st % BWD_STAGES;
     const int f0 = st * F;
-    const int bytes = (nfr - f0 < F ? nfr - f0 : F) * row_bytes;
+    const uint32_t bytes = (uint32_t)((nfr - f0 < F ? nfr - f0 : F) * row_bytes);
     uint8_t* dst = ring + slot * 2 * BWD_STAGE_BYTES;
-    const int lane = threadIdx.x & 31;
-    if (lane == 0) mbar_expect_tx(&full[slot], 2 * (uint32_t)bytes);
-    __syncwarp();
-    if (lane < 8) {
-      const int piece = lane & 3, stream = lane >> 2;
-      const int off = piece * (BWD_STAGE_BYTES / 4);
-      int n = bytes - off;
-      n = n > BWD_STAGE_BYTES / 4 ? BWD_STAGE_BYTES / 4 : n;
-      if (n > 0)
-        bulk_load_1d(dst + stream * BWD_STAGE_BYTES + off, (stream ? ggp : gdy) + (long long)f0 * row_bytes + off, (uint32_t)n,
-                     &full[slot]);
-    }
+    mbar_expect_tx(&full[slot], 2 * bytes);
+    bulk_load_1d(dst, gdy + (long long)f0 * row_bytes, bytes, &full[slot]);
+    bulk_load_1d(dst + BWD_STAGE_BYTES, ggp + (long long)f0 * row_bytes, bytes, &full[slot]);
   };
-  if (threadIdx.x < 32)
+  if (threadIdx.x == 0)
     for (int st = 0; st < nst && st < BWD_STAGES; ++st) issue(st);
   const float* x = audio + (long long)b * n_samples + t0 * S;
   const int nload = nfr * S + (K - S);
@@ -284,9 +275,9 @@ __global__ void __launch_bounds__(512, 1) bwd_ring_kernel(const float* __restric
   }
   for (int st = 0; st < nst; ++st) {
     const int slot = st % BWD_STAGES;
-    // refill the slot consumed one iteration ago (no block-wide barrier: the warps drift up to a ring apart; warp 0
+    // refill the slot consumed one iteration ago (no block-wide barrier: the warps drift up to a ring apart; thread 0
     // only waits for the LAST stage's readers, who are at most one stage behind it)
-    if (threadIdx.x < 32 && st >= 1 && st - 1 + BWD_STAGES < nst) {
+    if (threadIdx.x == 0 && st >= 1 && st - 1 + BWD_STAGES < nst) {
       mbar_wait(&empty[(st - 1) % BWD_STAGES], (uint32_t)(((st - 1) / BWD_STAGES) & 1));
       fence_proxy_async_smem();                            // generic-proxy reads before the async-proxy refill
       issue(st - 1 + BWD_STAGES);
