@@ -94,6 +94,8 @@ class _Plan:
         self.host = self.pinned.numpy().view(_TENSOR_DTYPE)     # structured view of the pinned block
         self.table = torch.empty_like(self.pinned, device=dev)
         self.uploaded = None   # event after the last host -> device copy of the table (the pinned block is reused)
+        # (pinned snapshot, device table) used by a CUDA-graph capture of step(): allocated here, outside any capture
+        self.captured = (torch.zeros_like(self.pinned).pin_memory(), torch.empty_like(self.table))
         sc, rm, o, om = self.scratch.data_ptr(), self.rmean.data_ptr(), 0, 0
         for i, (p, st, (f, b, r, c)) in enumerate(zip(params, states, dims)):
             e = self.host[i]
@@ -181,8 +183,15 @@ class FusedAdafactor(torch.optim.Optimizer):
                 if plan.uploaded is not None and not capturing:
                     plan.uploaded.synchronize()
                 plan.host["g"] = [g.data_ptr() for g in grads]      # the only per-step column of the table
-                plan.table.copy_(plan.pinned, non_blocking=True)    # (captured: replays re-copy the same pointers)
-                if not capturing:
+                table = plan.table
+                if capturing:
+                    # a captured step replays this host -> device copy: give the graph its OWN pinned snapshot and device
+                    # table, so that eager steps taken later (other gradient addresses) cannot change what it uploads
+                    plan.captured[0].copy_(plan.pinned)              # host-side copy (buffers pre-allocated in _Plan)
+                    table = plan.captured[1]
+                    table.copy_(plan.captured[0], non_blocking=True)
+                else:
+                    table.copy_(plan.pinned, non_blocking=True)
                     plan.uploaded = torch.cuda.Event()
                     plan.uploaded.record()
                 beta2t = 1.0 - math.pow(step_no, group["decay_rate"])
@@ -193,7 +202,7 @@ class FusedAdafactor(torch.optim.Optimizer):
                     if self._dev_step is None:
                         self._dev_step = torch.full((1,), step_no - 1, dtype=torch.int64, device=params[0].device)
                     step_dev = self._dev_step.data_ptr()
-                rc = lib.smx_adafactor_step(plan.table.data_ptr(), len(params), plan.tiles.data_ptr(), plan.n_tiles,
+                rc = lib.smx_adafactor_step(table.data_ptr(), len(params), plan.tiles.data_ptr(), plan.n_tiles,
                                             plan.slices.data_ptr(), plan.n_slices, plan.small.data_ptr(), plan.n_small,
                                             plan.small_floats, plan.scratch.data_ptr(),
                                             plan.scratch.numel() * 4, beta2t, group["eps"][0], group["lr"],

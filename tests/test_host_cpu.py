@@ -336,3 +336,34 @@ def test_beam_state_matches_transformers_beam_search():
                 mine = st.result()
                 assert ref.shape == mine.shape and torch.equal(ref, mine), (kind, k, L, eos, lp, es, ref.tolist(), mine.tolist())
                 assert all(int(r.min()) >= 0 and int(r.max()) < B * k for r in rows_seen)
+
+
+def test_bridge_projector_composition_algebra():
+    """The identities ops.BridgeProjFn relies on (ref:speechmix/hf_model.py:253-272, 426-430: bare Conv1d(k 2, s 2) then
+    nn.Linear, no non-linearity): forward W_eff = Wp.pack(W), b_eff = bp + Wp b over the frame-pair view; backward
+    dWp = G pack(W)^T + db_eff (x) b, dpack(W) = Wp^T G, db = Wp^T db_eff, dbp = db_eff with G = dW_eff -- checked in fp64
+    against torch autograd of the unfused pair, odd T (the tail frame gets no gradient)."""
+    import torch
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    B, T, C, D = 2, 7, 8, 6
+    x = torch.randn(B, T, C, dtype=torch.float64, requires_grad=True)
+    cw = torch.randn(C, C, 2, dtype=torch.float64, requires_grad=True)
+    cb = torch.randn(C, dtype=torch.float64, requires_grad=True)
+    pw = torch.randn(D, C, dtype=torch.float64, requires_grad=True)
+    pb = torch.randn(D, dtype=torch.float64, requires_grad=True)
+    y = F.linear(F.conv1d(x.transpose(1, 2), cw, cb, stride=2).transpose(1, 2), pw, pb)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    P = cw.detach().permute(0, 2, 1).reshape(C, 2 * C)                 # kernels.pack_conv_weight: tap-major
+    w_eff, b_eff = pw.detach() @ P, pb.detach() + pw.detach() @ cb.detach()
+    t_out = T // 2
+    xv = x.detach()[:, :t_out * 2].reshape(B, t_out, 2 * C)            # the copy-free frame-pair view
+    assert torch.allclose(xv @ w_eff.t() + b_eff, y.detach(), atol=1e-12)
+    G, db_eff = torch.einsum("btd,btk->dk", dy, xv), dy.sum((0, 1))
+    assert torch.allclose(G @ P.t() + torch.outer(db_eff, cb.detach()), pw.grad, atol=1e-12)
+    assert torch.allclose((pw.detach().t() @ G).view(C, 2, C).permute(0, 2, 1), cw.grad, atol=1e-12)   # unpack_conv_wgrad
+    assert torch.allclose(pw.detach().t() @ db_eff, cb.grad, atol=1e-12) and torch.allclose(db_eff, pb.grad, atol=1e-12)
+    dx = torch.zeros(B, T, C, dtype=torch.float64)
+    dx[:, :t_out * 2] = (dy @ w_eff).reshape(B, t_out * 2, C)
+    assert torch.allclose(dx, x.grad, atol=1e-12) and float(x.grad[:, -1].abs().max()) == 0.0

@@ -518,6 +518,14 @@ def test_graphed_step_matches_eager(optimizer, cuda_device):
     assert max(abs(a - b) / (1.0 + abs(a)) for a, b in zip(*losses)) < 3e-3, losses
     if optimizer == "adafactor":
         assert opt.steps_done() == 5 and g.opt_in_graph               # the device-side counter followed the replays
+        # an EAGER step between replays uses other gradient tensors: the captured step must keep uploading its own
+        # pointer table (optim._Plan.captured), and both kinds of step keep training the same parameters
+        opt.zero_grad(set_to_none=True)
+        le = m(xs, labels=ys, return_model_detail=False)["loss"]
+        le.backward()
+        opt.step()
+        lg = float(g(xs, ys))
+        assert opt.steps_done() == 7 and lg == lg and lg < float(le) + 0.05 and float(le) < losses[1][-1] + 0.05
 
 
 def test_graph_replay_survives_interleaved_eager_calls(cuda_device):
