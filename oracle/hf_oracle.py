@@ -411,6 +411,47 @@ class OracleSelf(OracleEED):
         return outputs
 
 
+ED_FIXED_EXCEPT = ["layer_norm", "encoder_attn", "enc_to_dec_proj", "length_adapter", "layernorm_embedding",
+                   "attention", "encoder"]
+
+
+class OracleED(nn.Module):
+    """ref:speechmix/hf_model.py:82-182 (HFSpeechMixED): ``SpeechEncoderDecoderModel`` over the speech encoder and the
+    DECODER half of the text model as a causal LM with cross-attention, feature encoder frozen.  Takes built modules
+    instead of hub names: ``text_model`` is the seq2seq model whose decoder weights (and shared embedding) the causal
+    decoder receives -- what ``from_encoder_decoder_pretrained`` loads from a BART checkpoint (under transformers 5.x the
+    token embedding is reported MISSING and re-drawn; golden and tests equalise it to the checkpoint's shared embedding)."""
+
+    def __init__(self, encoder_model, text_model, fixed_parameters=False, fixed_except=None, **kwargs):
+        super().__init__()
+        from transformers import AutoModelForCausalLM, SpeechEncoderDecoderConfig, SpeechEncoderDecoderModel
+        dec_cfg = copy.deepcopy(text_model.config)
+        dec_cfg.is_decoder, dec_cfg.add_cross_attention = True, True
+        decoder = AutoModelForCausalLM.from_config(dec_cfg)
+        src = text_model.model.decoder.state_dict()
+        decoder.model.decoder.load_state_dict(src)
+        with torch.no_grad():
+            decoder.model.decoder.embed_tokens.weight.copy_(text_model.model.shared.weight)
+        cfg = SpeechEncoderDecoderConfig.from_encoder_decoder_configs(encoder_model.config, dec_cfg)
+        self.model = SpeechEncoderDecoderModel(config=cfg, encoder=encoder_model, decoder=decoder)
+        self.model.config.decoder_start_token_id = self.model.config.decoder.decoder_start_token_id
+        self.model.config.pad_token_id = self.model.config.decoder.pad_token_id
+        self.model.freeze_feature_encoder()
+        if fixed_parameters:
+            fixed_except = ED_FIXED_EXCEPT if fixed_except is None else fixed_except
+            for name, param in self.model.named_parameters():
+                if param.requires_grad:
+                    param.requires_grad = any(k in name for k in fixed_except)
+
+    def forward(self, input_values, attention_mask=None, decoder_input_ids=None, labels=None):
+        if decoder_input_ids is None and labels is None:
+            decoder_input_ids = handle_decoder_input_none(self.model.config.decoder)
+        outputs = self.model(input_values=input_values, attention_mask=attention_mask,
+                             decoder_input_ids=decoder_input_ids, labels=labels)
+        return {"loss": outputs["loss"] if "loss" in outputs else None, "logits": outputs.logits,
+                "encoder_last_hidden_state": outputs.encoder_last_hidden_state}
+
+
 @torch.no_grad()
 def greedy_full_recompute(model, input_values, max_length=32, eos_token_id=None):
     """Greedy decode the way ``ref:eval.ipynb`` cell 6 does: no KV cache, every

@@ -12,7 +12,7 @@ from torch import nn
 
 from . import _lib, ops
 from .speech import SpeechOutput, speech_from_pretrained
-from .text import text_from_pretrained
+from .text import causal_from_pretrained, text_from_pretrained
 
 
 def handle_decoder_input_none(decoder_config, batch=1, device="cpu"):
@@ -375,6 +375,95 @@ class SpeechMixEED(nn.Module):
         return torch.cat((prompt.expand(inputs_embeds.shape[0], -1, -1), inputs_embeds), 1)
 
 
+ED_FIXED_EXCEPT = ["layer_norm", "encoder_attn", "enc_to_dec_proj", "length_adapter", "layernorm_embedding", "attention",
+                   "encoder"]
+
+
+class _EncoderDecoder(nn.Module):
+    """attribute layout (and therefore parameter names) of hf SpeechEncoderDecoderModel: ``encoder``, ``decoder``,
+    ``enc_to_dec_proj`` when the hidden sizes differ"""
+
+    def __init__(self, encoder, decoder):
+        super().__init__()
+        self.encoder, self.decoder = encoder, decoder
+        if encoder.config.hidden_size != decoder.config.hidden_size:
+            self.enc_to_dec_proj = nn.Linear(encoder.config.hidden_size, decoder.config.hidden_size)
+
+
+class SpeechMixED(nn.Module):
+    """ref:speechmix/hf_model.py:82-182 (HFSpeechMixED): the speech encoder feeding the DECODER half of the text model
+    directly (hf SpeechEncoderDecoderModel: no text encoder, no length adapters), feature encoder frozen.
+    ``forward(input_values, labels=...)`` returns ``loss`` (mean CE over labels != -100) and -- as the reference does for
+    this class -- the FULL-vocabulary ``logits`` (detached; the loss itself comes from the fused LM-head kernel that never
+    materialises them), plus ``argmax_ids``.  State-dict keys are those of the reference (``model.encoder.*``,
+    ``model.decoder.model.decoder.*``, ``model.decoder.lm_head.weight``)."""
+
+    main_input_name = "input_values"
+
+    def __init__(self, speech_model_config, nlp_model_config, fixed_parameters=False, fixed_except=None, tokenizer=None,
+                 **kwargs):
+        super().__init__()
+        _lib.load()
+        self.model = _EncoderDecoder(speech_from_pretrained(speech_model_config), causal_from_pretrained(nlp_model_config))
+        self.dropout_sites = _dropout_knobs(self.model.encoder.config, self.model.decoder.config)
+        self.config = SpeechMixConfig(self.model.encoder.config, self.model.decoder.config)
+        self.tokenizer = tokenizer
+        for p in self.model.encoder.feature_extractor.parameters():      # ref :115 freeze_feature_encoder()
+            p.requires_grad = False
+        if fixed_parameters:                                             # ref :116-122
+            fixed_except = ED_FIXED_EXCEPT if fixed_except is None else fixed_except
+            for name, param in self.model.named_parameters():
+                if param.requires_grad:
+                    param.requires_grad = any(k in name for k in fixed_except)
+        self.list_grad = [n for n, p in self.named_parameters() if p.requires_grad]
+        self.list_no_grad = [n for n, p in self.named_parameters() if not p.requires_grad]
+
+    device = property(lambda self: next(self.parameters()).device)
+    encoder_model = property(lambda self: self.model.encoder)
+    decoder_model = property(lambda self: self.model.decoder)
+
+    def get_encoder(self):
+        return self.model.encoder
+
+    def get_decoder(self):
+        return self.model.decoder
+
+    def prepare_decoder_input_ids_from_labels(self, labels):
+        cfg = self.model.decoder.config
+        return shift_tokens_right(labels, cfg.pad_token_id, cfg.decoder_start_token_id)
+
+    def forward(self, input_values, attention_mask=None, decoder_input_ids=None, labels=None, return_full_logits=True):
+        if attention_mask is not None:
+            raise NotImplementedError("SpeechMixED: the reference call passes no attention mask (ref :157-169)")
+        dev = self.device
+        if dev.type != "cuda" or not input_values.is_cuda:
+            raise RuntimeError("speechmix_b200 runs on a B200 only (model and input_values must be on the GPU); "
+                               "there is no CPU fallback")
+        dec = self.model.decoder
+        labels = labels.to(dev) if labels is not None else None
+        if self.training and self.dropout_sites:
+            ops.DROPOUT.begin_step(dev)
+        if torch.is_grad_enabled() or ops.CACHE.dirty:
+            ops.CACHE.new_step()
+        if decoder_input_ids is None and labels is None:
+            decoder_input_ids = handle_decoder_input_none(dec.config, device=dev)
+        elif decoder_input_ids is None:
+            decoder_input_ids = self.prepare_decoder_input_ids_from_labels(labels)
+        enc = self.model.encoder(input_values).last_hidden_state
+        if hasattr(self.model, "enc_to_dec_proj"):
+            enc = ops.linear(enc, self.model.enc_to_dec_proj.weight, self.model.enc_to_dec_proj.bias)
+        hidden = dec.decode_hidden(decoder_input_ids.to(dev), enc)
+        B, T, _ = hidden.shape
+        lab = labels if labels is not None else torch.full((B, T), -100, device=dev, dtype=torch.long)
+        w, b, scale = dec.lm_head_params()
+        loss, ids = ops.LMHeadCEFn.apply(hidden, w, b, lab, scale)
+        out = SpeechOutput(loss=loss if labels is not None else None, argmax_ids=ids, encoder_last_hidden_state=enc,
+                           decoder_last_hidden_state=hidden)
+        with torch.no_grad():
+            out["logits"] = dec.full_logits(hidden.detach()) if return_full_logits else ids
+        return out
+
+
 class SpeechMixFixed(SpeechMixEED):
     """ref:speechmix/hf_model.py:450-462"""
 
@@ -473,3 +562,4 @@ HFSpeechMixEED = SpeechMixEED
 HFSpeechMixSelf = SpeechMixSelf
 HFSpeechMixFixed = SpeechMixFixed
 HFSpeechMixAdapter = SpeechMixAdapter
+HFSpeechMixED = SpeechMixED

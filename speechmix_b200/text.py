@@ -264,6 +264,64 @@ class Seq2SeqLM(nn.Module):
 # scores plus a bucketed relative position bias owned by block 0 of each stack and shared by all of
 # its blocks, ReLU feed-forward, tied LM head scaled by d_model**-0.5.
 # =============================================================================================
+class _CausalBody(nn.Module):
+    """hf BartDecoderWrapper: ``model.decoder`` of a causal LM"""
+
+    def __init__(self, config):
+        super().__init__()
+        self.decoder = _Stack(config, nn.Embedding(config.vocab_size, config.d_model, config.pad_token_id), is_decoder=True)
+
+
+class CausalLM(nn.Module):
+    """The decoder half of a BART / mBART model as a causal LM WITH cross-attention and a tied LM head
+    (hf:models/bart/modeling_bart.py BartForCausalLM, built by ``SpeechEncoderDecoderModel.from_encoder_decoder_pretrained``
+    with ``is_decoder=True, add_cross_attention=True``): the decoder of ``SpeechMixED`` (ref:speechmix/hf_model.py:104).
+    Same parameter names as HF (``model.decoder.*``, ``lm_head.weight``)."""
+
+    def __init__(self, config):
+        super().__init__()
+        if config.model_type not in ("bart", "mbart"):
+            raise NotImplementedError("causal decoder %r is not wired to the sm_100a kernels" % config.model_type)
+        self.config = config
+        self.model = _CausalBody(config)
+        self.lm_head = nn.Linear(config.d_model, config.vocab_size, bias=False)
+        self.lm_head.weight = self.model.decoder.embed_tokens.weight
+
+    device = property(lambda self: self.lm_head.weight.device)
+
+    def lm_head_params(self):
+        return self.lm_head.weight, None, 1.0
+
+    def decode_hidden(self, decoder_input_ids, encoder_hidden_states):
+        x, _ = self.model.decoder(input_ids=decoder_input_ids, encoder_hidden_states=encoder_hidden_states)
+        return x
+
+    def full_logits(self, hidden):
+        h2 = hidden.reshape(-1, hidden.shape[-1]).contiguous()
+        return K.linear_fwd(h2, ops.w16(self.lm_head.weight), None, out_f32=True).view(*hidden.shape[:-1], -1)
+
+
+def causal_from_pretrained(path_or_config):
+    """config object (random init) or a local / cached SEQ2SEQ checkpoint whose decoder (``model.decoder.*``) and shared
+    token embedding are loaded -- what ``AutoModelForCausalLM.from_pretrained(<bart checkpoint>)`` is meant to give
+    (transformers 5.x reports the token embedding MISSING there and re-draws it; we take ``model.shared``)."""
+    from transformers import AutoConfig, PretrainedConfig
+    if isinstance(path_or_config, PretrainedConfig):
+        return CausalLM(path_or_config)
+    path = resolve_checkpoint(path_or_config)
+    model = CausalLM(AutoConfig.from_pretrained(path))
+    sd = dict(load_checkpoint_state(path))
+    emb = next((sd[k] for k in ("model.decoder.embed_tokens.weight", "model.shared.weight", "lm_head.weight") if k in sd), None)
+    for k in ("model.decoder.embed_tokens.weight", "lm_head.weight"):
+        sd.setdefault(k, emb)
+    own = model.state_dict()
+    missing = [k for k in own if k not in sd or sd[k] is None]
+    if missing:
+        raise RuntimeError("checkpoint %s lacks %d decoder tensors, e.g. %s" % (path, len(missing), missing[:3]))
+    model.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=False)
+    return model
+
+
 class _RMSNorm(nn.Module):
     """hf:...t5.py:46-69 (T5LayerNorm): weight only."""
 

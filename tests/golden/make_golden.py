@@ -272,6 +272,60 @@ def run_case(name):
     print("wrote", path, "loss", fixture["loss"])
 
 
+def run_ed_case(name="mini_ed"):
+    """HFSpeechMixED (ref:speechmix/hf_model.py:82-182): SpeechEncoderDecoderModel over the speech encoder and the text
+    model's decoder as a causal LM.  Under transformers 5.x ``from_encoder_decoder_pretrained`` re-draws the decoder's
+    token embedding (reported MISSING: a BART checkpoint stores it as ``model.shared``); both sides get the checkpoint's
+    shared embedding instead, so the fixture does not depend on the RNG state of the load."""
+    from transformers import Wav2Vec2FeatureExtractor
+    speechmix = import_reference()
+    sp_cfg, tx_cfg = O.speech_config("mini"), O.text_config("bart-mini")
+    speech, text = O.build_backbones(sp_cfg, tx_cfg, seed=0)
+    tmp = tempfile.mkdtemp(prefix="smx_golden_")
+    sp_dir, tx_dir = os.path.join(tmp, "wav2vec2"), os.path.join(tmp, "text")
+    speech.save_pretrained(sp_dir)
+    text.save_pretrained(tx_dir)
+    save_tokenizer(tx_dir, tx_cfg.vocab_size)
+    Wav2Vec2FeatureExtractor().save_pretrained(sp_dir)
+    ref = speechmix.HFSpeechMixED(sp_dir, tx_dir)
+    with torch.no_grad():
+        ref.model.decoder.model.decoder.embed_tokens.weight.copy_(text.model.shared.weight)
+    speech2, text2 = O.build_backbones(sp_cfg, tx_cfg, seed=0)
+    ora = O.OracleED(speech2, text2)
+    a, b = ref.state_dict(), ora.state_dict()
+    assert list(a) == list(b) and all(torch.equal(a[k], b[k]) for k in a)
+    frozen = [k for k, p in ref.named_parameters() if not p.requires_grad]
+    assert frozen == [k for k, p in ora.named_parameters() if not p.requires_grad]
+    B, secs, t_dec = 2, 1.0, 8
+    x, labels = O.synthetic_batch(B, secs, t_dec, tx_cfg.vocab_size, seed=0, ignore_tail=True)
+    ref.train()
+    ora.train()
+    out_ref, out_ora = ref(x, labels=labels), ora(x, labels=labels)
+    assert torch.equal(out_ref.loss, out_ora["loss"]) and torch.equal(out_ref.logits, out_ora["logits"])
+    out_ref.loss.backward()
+    out_ora["loss"].backward()
+    pr, po = dict(ref.named_parameters()), dict(ora.named_parameters())
+    grads = {}
+    for k in pr:
+        assert (pr[k].grad is None) == (po[k].grad is None), k
+    for k in ["model.decoder.model.decoder.embed_tokens.weight", "model.decoder.model.decoder.layers.0.encoder_attn.k_proj.weight",
+              "model.decoder.model.decoder.layers.1.fc1.weight", "model.encoder.encoder.layers.0.attention.q_proj.weight",
+              "model.encoder.feature_projection.projection.weight", "model.encoder.encoder.layers.1.feed_forward.output_dense.bias"]:
+        assert torch.equal(pr[k].grad, po[k].grad), k
+        grads[k] = {"norm": float(pr[k].grad.double().norm()), **sample(pr[k].grad, 16)}
+    fixture = {"case": name, "cls": "ED", "speech": "mini", "speech_type": "wav2vec2", "text": "bart-mini", "kwargs": {},
+               "batch": B, "seconds": secs, "t_dec": t_dec, "ignore_tail": True, "train_mode": True,
+               "transformers": __import__("transformers").__version__, "torch": torch.__version__,
+               "n_params": sum(p.numel() for p in ref.parameters()), "n_state_keys": len(a), "state_keys": list(a),
+               "frozen": frozen, "n_grads": sum(p.grad is not None for p in pr.values()),
+               "loss": float(out_ref.loss), "argmax_ids": out_ref.logits.argmax(-1).tolist(),
+               "logits": sample(out_ref.logits), "grads": grads}
+    path = os.path.join(HERE, name + ".json")
+    with open(path, "w") as f:
+        json.dump(fixture, f, indent=1)
+    print("wrote", path, "loss", fixture["loss"])
+
+
 if __name__ == "__main__":
-    for c in (sys.argv[1:] or list(CASES)):
-        run_case(c)
+    for c in (sys.argv[1:] or list(CASES) + ["mini_ed"]):
+        run_ed_case(c) if c == "mini_ed" else run_case(c)

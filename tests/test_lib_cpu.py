@@ -96,6 +96,24 @@ def test_state_dict_layout_matches_reference_oracle():
         mine.load_state_dict(a)
 
 
+def test_speechmix_ed_layout_matches_reference_oracle():
+    """SpeechMixED (ref:speechmix/hf_model.py:82-182): same state-dict keys in the same order, same shapes, same frozen
+    feature encoder as the hf SpeechEncoderDecoderModel the reference builds; fixed_parameters follows the reference's
+    substring rule."""
+    from oracle import hf_oracle as O
+    from speechmix_b200 import SpeechMixED
+    for kw in ({}, {"fixed_parameters": True}):
+        spc, txc = O.speech_config("mini"), O.text_config("bart-mini")
+        s, t = O.build_backbones(spc, txc)
+        ora = O.OracleED(s, t, **kw)
+        mine = SpeechMixED(spc, txc, **kw)
+        a, b = ora.state_dict(), mine.state_dict()
+        assert list(a) == list(b) and all(a[k].shape == b[k].shape for k in a)
+        assert [k for k, p in ora.named_parameters() if not p.requires_grad] == mine.list_no_grad
+        assert [k for k, p in ora.named_parameters() if p.requires_grad] == mine.list_grad
+        mine.load_state_dict(a)
+
+
 def test_share_layer_ratio_and_helpers():
     """ref:test/test_hf_model.py:18-33 restated on the product classes."""
     import torch

@@ -145,6 +145,47 @@ def test_t5_v11_gated_feed_forward_matches_oracle(cuda_device):
     assert torch.equal(ids32, O.greedy_full_recompute(ora, x, max_length=10, eos_token_id=-1))
 
 
+def test_speechmix_ed_matches_oracle(cuda_device):
+    """SpeechMixED (ref:speechmix/hf_model.py:82-182, hf SpeechEncoderDecoderModel: speech encoder -> causal BART decoder
+    with cross-attention, feature encoder frozen) against the oracle pinned by tests/golden/mini_ed.json: loss, the
+    full-vocabulary logits this class returns, argmax ids, and every gradient; frozen parameters get none."""
+    import speechmix_b200 as S
+    fx = load_fixture("mini_ed")
+    ora, x, labels = build_oracle(fx)
+    mine = S.SpeechMixED(O_speech(fx), O_text(fx))
+    mine.load_state_dict(ora.state_dict())
+    mine = mine.to(cuda_device).train()
+    ref = ora(x, labels=labels)
+    assert abs(float(ref["loss"]) - fx["loss"]) < 1e-4            # the oracle is the reference's own output
+    out = mine(x.to(cuda_device), labels=labels.to(cuda_device))
+    assert abs(float(out["loss"]) - float(ref["loss"])) < 3e-3
+    assert out["logits"].shape == ref["logits"].shape and _rel(out["logits"], ref["logits"]) < 2e-2
+    assert _ids_agree(out["argmax_ids"], ref["logits"].argmax(-1))
+    ref["loss"].backward()
+    out["loss"].backward()
+    po, pm = dict(ora.named_parameters()), dict(mine.named_parameters())
+    scale = max(float(p.grad.norm()) for p in po.values() if p.grad is not None)
+    checked = 0
+    for k, p in po.items():
+        if p.grad is None:
+            assert pm[k].grad is None, k
+            continue
+        err = float((pm[k].grad.cpu() - p.grad).norm())
+        assert err <= 5e-2 * float(p.grad.norm()) + 2e-4 * scale, (k, err, float(p.grad.norm()))
+        checked += 1
+    assert checked == fx["n_grads"] == len(mine.list_grad)
+
+
+def O_speech(fx):
+    from oracle import hf_oracle as O
+    return O.speech_config(fx["speech"], model_type=fx["speech_type"])
+
+
+def O_text(fx):
+    from oracle import hf_oracle as O
+    return O.text_config(fx["text"])
+
+
 def test_mbart_pre_ln_stack(cuda_device):
     fx = dict(load_fixture("mini_eed_ds2"), text="mbart-mini", kwargs={"down_scale": 4})
     ora, x, labels = build_oracle(fx)

@@ -91,3 +91,25 @@ def test_oracle_cfg1_full_size():
     assert abs(float(out["loss"]) - fx["loss"]) < 5e-5
     assert out["logits"].tolist() == fx["argmax_ids"]
     check_sample(out["full_logits"], fx["logits"], atol=5e-4)
+
+
+def test_oracle_ed_matches_reference_golden():
+    """HFSpeechMixED (ref:speechmix/hf_model.py:82-182): oracle.OracleED against the fixture written by the unmodified
+    reference class (tests/golden/make_golden.py::run_ed_case) -- state-dict keys, frozen feature encoder, loss, logits,
+    argmax ids and sampled gradients."""
+    fx = load_fixture("mini_ed")
+    model, x, labels = build_oracle(fx)
+    assert list(model.state_dict()) == fx["state_keys"]
+    assert [k for k, p in model.named_parameters() if not p.requires_grad] == fx["frozen"]
+    assert sum(p.numel() for p in model.parameters()) == fx["n_params"]
+    out = model(x, labels=labels)
+    assert abs(float(out["loss"]) - fx["loss"]) < 2e-5
+    assert out["logits"].argmax(-1).tolist() == fx["argmax_ids"]
+    check_sample(out["logits"], fx["logits"], atol=2e-4)
+    out["loss"].backward()
+    params = dict(model.named_parameters())
+    for k, rec in fx["grads"].items():
+        g = params[k].grad
+        assert abs(float(g.double().norm()) - rec["norm"]) <= 1e-3 * rec["norm"] + 1e-7, k
+        check_sample(g, rec, atol=1e-5, rtol=1e-3)
+    assert sum(p.grad is not None for p in params.values()) == fx["n_grads"]
