@@ -384,6 +384,17 @@ int smx_self_mse_bwd(const void* text_h, const void* speech_h, const float* attn
                      void* stream);
 
 /* ------------------------------------------------------------------------
+ * SpeechMixGAN discriminator features (ref:speechmix/hf_model.py:637-686): the reference feeds Linear(dim*dim, 1) with
+ * flatten(X.view(dim, t) . X.view(t, dim)) -- a memory reinterpretation of the [t, dim] states.  With W = weight.view(dim,
+ * dim) and Z = X W^T (a GEMM), logit[b] = sum_{t,i} Xflat[b][i t_len + t] * Z[b][t][i]: fwd accumulates that into out[b]
+ * (zeroed by the call); bwd writes dz[b][t][i] = g[b] Xflat[b][i t_len + t] and dx[b][f] = g[b] Z[b][f % t_len][f / t_len].
+ * x, z, dx, dz: bf16 [batch][t][dim] contiguous; out, g: fp32 [batch].
+ * ------------------------------------------------------------------------ */
+int smx_gram_dot_fwd(const void* x, const void* z, float* out, int64_t batch, int64_t t, int64_t dim, void* stream);
+int smx_gram_dot_bwd(const void* x, const void* z, const float* g, void* dx, void* dz, int64_t batch, int64_t t, int64_t dim,
+                     void* stream);
+
+/* ------------------------------------------------------------------------
  * T5 relative position bias (hf:models/t5/modeling_t5.py:188-247): bias[h][i][j] = weight[bucket][h] with
  * bucket = table[(j - (i + q_offset)) + (tq + q_offset - 1)]; the bucket table (tq + q_offset + tk - 1 int32)
  * is built on the host with the reference's own formula.  bwd accumulates into a zeroed dweight.

@@ -6,11 +6,11 @@
 
 The CUDA library must be built first (``python -m speechmix_b200.build``); there is no fallback.
 """
-from .model import (HFSpeechMixAdapter, HFSpeechMixED, HFSpeechMixEED, HFSpeechMixFixed, HFSpeechMixSelf,  # noqa: F401
-                    SpeechMixAdapter, SpeechMixConfig, SpeechMixED, SpeechMixEED, SpeechMixFixed, SpeechMixSelf,
+from .model import (HFSpeechMixAdapter, HFSpeechMixED, HFSpeechMixEED, HFSpeechMixFixed, HFSpeechMixGAN,  # noqa: F401
+                    HFSpeechMixSelf, SpeechMixAdapter, SpeechMixConfig, SpeechMixED, SpeechMixEED, SpeechMixFixed, SpeechMixGAN, SpeechMixSelf,
                     handle_decoder_input_none, shift_tokens_right)
 from .optim import FusedAdafactor  # noqa: F401
 
-__all__ = ["SpeechMixEED", "SpeechMixED", "HFSpeechMixED", "SpeechMixFixed", "SpeechMixAdapter", "SpeechMixSelf", "HFSpeechMixEED", "HFSpeechMixFixed",
+__all__ = ["SpeechMixEED", "SpeechMixED", "HFSpeechMixED", "SpeechMixFixed", "SpeechMixAdapter", "SpeechMixSelf", "SpeechMixGAN", "HFSpeechMixGAN", "HFSpeechMixEED", "HFSpeechMixFixed",
            "HFSpeechMixAdapter", "HFSpeechMixSelf", "SpeechMixConfig", "shift_tokens_right",
            "handle_decoder_input_none", "FusedAdafactor"]

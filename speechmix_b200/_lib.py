@@ -110,6 +110,8 @@ SIGNATURES = {
     "smx_kl_chunk_fwd": (c_int, [_P, _P, _I64, _I64, _I64, _P, _P, _P]),
     "smx_kl_finalize": (c_int, [_P, _P, _P, _I64, c_float, _P, _P]),
     "smx_kl_chunk_bwd": (c_int, [_P, _P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _I64, _P]),
+    "smx_gram_dot_fwd": (c_int, [_P, _P, _P, _I64, _I64, _I64, _P]),
+    "smx_gram_dot_bwd": (c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _P]),
     "smx_self_mse_fwd": (c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _P]),
     "smx_self_mse_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _P]),
     "smx_f32_gemm_nt": (c_int, [_P, _I64, _I64, _P, _P, _P, _I64, _I64, _P, _I64, _I64, _I64, _I64, _I64, _I64, c_int, c_float, _P]),

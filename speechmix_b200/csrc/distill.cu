@@ -255,6 +255,78 @@ __global__ void __launch_bounds__(256) relpos_bwd_kernel(const float* __restrict
 using namespace smx;
 using namespace smx::distill;
 
+
+namespace smx {
+namespace gan {
+__device__ __forceinline__ void load8(const bf16* p, float* f) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) f[2 * j] = bf16_lo(w[j]), f[2 * j + 1] = bf16_hi(w[j]);
+}
+__device__ __forceinline__ void store8(bf16* p, const float* f) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                                            pack_bf16x2(f[6], f[7]));
+}
+// SpeechMixGAN discriminator input (ref:speechmix/hf_model.py:637-686): the reference flattens the Gram-like matrix
+//   G_b = X_b.view(D, T) . X_b.view(T, D)        (a MEMORY REINTERPRETATION of the [T, D] states, not a transpose)
+// into D*D features and applies Linear(D*D, 1).  With W = weight.view(D, D):
+//   logit_b = <W, G_b> = sum_{t,i} Xflat_b[i T + t] * Z_b[t, i],     Z = X W^T   (one GEMM; G never exists).
+// These kernels are that last contraction and its two gradients.
+__global__ void __launch_bounds__(256) gram_dot_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ z,
+                                                           float* __restrict__ out, int t, int d) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float red[8];
+  const int b = blockIdx.y;
+  const long long n = (long long)t * d;
+  const bf16* xb = x + b * n;
+  const bf16* zb = z + b * n;
+  float acc = 0.f;
+  for (long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; e < n; e += (long long)gridDim.x * blockDim.x * 8) {
+    const int tt = (int)(e / d), i0 = (int)(e % d);          // 8 consecutive i of one frame of Z
+    float zv[8];
+    load8(zb + e, zv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc = fmaf(zv[k], __bfloat162float(xb[(long long)(i0 + k) * t + tt]), acc);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    atomicAdd(out + b, s);
+  }
+}
+// dz[b, t, i] = g[b] * Xflat_b[i T + t];   dxflat[b, f] = g[b] * Z_b[f % T, f / T]
+__global__ void __launch_bounds__(256) gram_dot_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ z,
+                                                           const float* __restrict__ g, bf16* __restrict__ dx,
+                                                           bf16* __restrict__ dz, int t, int d) {
+  pdl_trigger();
+  pdl_wait();
+  const int b = blockIdx.y;
+  const long long n = (long long)t * d;
+  const bf16* xb = x + b * n;
+  const bf16* zb = z + b * n;
+  const float gb = g[b];
+  for (long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; e < n; e += (long long)gridDim.x * blockDim.x * 8) {
+    const int tt = (int)(e / d), i0 = (int)(e % d);
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = gb * __bfloat162float(xb[(long long)(i0 + k) * t + tt]);
+    store8(dz + b * n + e, o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const long long f = e + k;                              // flat index of X: i = f / T, frame = f % T
+      o[k] = gb * __bfloat162float(zb[(f % t) * d + f / t]);
+    }
+    store8(dx + b * n + e, o);
+  }
+}
+}  // namespace gan
+}  // namespace smx
+
 extern "C" {
 
 int smx_kl_chunk_fwd(const float* s, const float* t, int64_t ld, int64_t rows, int64_t vn, const float* lse_t,
@@ -332,6 +404,30 @@ int smx_relpos_bias_bwd(const float* dbias, const int32_t* table, float* dweight
   dim3 grid((unsigned)g, (unsigned)heads);
   launch_pdl(relpos_bwd_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, dbias, table, dweight, (int)heads, (int)tq, (int)tk,
                                                            (int)q_offset, (int)n_buckets);
+  SMX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int smx_gram_dot_fwd(const void* x, const void* z, float* out, int64_t batch, int64_t t, int64_t dim, void* stream) {
+  using namespace smx;
+  SMX_REQUIRE(x && z && out && dim % 8 == 0 && batch > 0 && t > 0, "gram_dot_fwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  SMX_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * batch, st));
+  long long gx = ceil_div(t * dim, 256 * 8);
+  if (gx > 64) gx = 64;
+  launch_pdl(gan::gram_dot_fwd_kernel, dim3((unsigned)gx, (unsigned)batch), dim3(256), 0, st, (const bf16*)x, (const bf16*)z, out,
+             (int)t, (int)dim);
+  SMX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int smx_gram_dot_bwd(const void* x, const void* z, const float* g, void* dx, void* dz, int64_t batch, int64_t t, int64_t dim,
+                     void* stream) {
+  using namespace smx;
+  SMX_REQUIRE(x && z && g && dx && dz && dim % 8 == 0 && batch > 0 && t > 0, "gram_dot_bwd: bad arguments");
+  long long gx = ceil_div(t * dim, 256 * 8);
+  if (gx > 64) gx = 64;
+  launch_pdl(gan::gram_dot_bwd_kernel, dim3((unsigned)gx, (unsigned)batch), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x,
+             (const bf16*)z, g, (bf16*)dx, (bf16*)dz, (int)t, (int)dim);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -881,6 +881,22 @@ def self_mse_bwd(text_h, speech_h, attn, diff, gscale):
     return ds
 
 
+def gram_dot_fwd(x, z):
+    """x, z [B,T,D] bf16 contiguous -> out[B] fp32 = sum_{t,i} xflat[b][i T + t] z[b][t][i]  (SpeechMixGAN features)"""
+    B, T, D = x.shape
+    out = torch.empty(B, device=x.device, dtype=torch.float32)
+    _lib.check(_L().smx_gram_dot_fwd(_ptr(x), _ptr(z), _ptr(out), B, T, D, _stream()), "gram_dot_fwd")
+    return out
+
+
+def gram_dot_bwd(x, z, g):
+    """g [B] fp32 -> (dx, dz) bf16 [B,T,D]: gradients of gram_dot_fwd w.r.t. its two arguments"""
+    B, T, D = x.shape
+    dx, dz = torch.empty_like(x), torch.empty_like(z)
+    _lib.check(_L().smx_gram_dot_bwd(_ptr(x), _ptr(z), _ptr(g), _ptr(dx), _ptr(dz), B, T, D, _stream()), "gram_dot_bwd")
+    return dx, dz
+
+
 def relpos_bias_fwd(weight, table, heads, tq, tk, q_offset=0):
     bias = torch.empty(heads, tq, tk, device=weight.device, dtype=torch.float32)
     _lib.check(_L().smx_relpos_bias_fwd(_ptr(weight), _ptr(table), _ptr(bias), heads, tq, tk, q_offset, _stream()),

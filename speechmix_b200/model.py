@@ -1,13 +1,14 @@
 """SpeechMix model classes on the B200-native kernels -- the drop-in boundary.
 
 Same constructor surface, attributes, ``forward`` contract and ``state_dict`` layout as the
-reference's ``HFSpeechMixEED`` / ``HFSpeechMixFixed`` / ``HFSpeechMixAdapter`` / ``HFSpeechMixSelf``
-(ref:speechmix/hf_model.py:185-583); every FLOP runs in libspeechmix_sm100.so.  There is no CPU
+reference's ``HFSpeechMixEED`` / ``HFSpeechMixFixed`` / ``HFSpeechMixAdapter`` / ``HFSpeechMixSelf`` /
+``HFSpeechMixGAN`` / ``HFSpeechMixED`` (ref:speechmix/hf_model.py:82-694); every FLOP runs in libspeechmix_sm100.so.  There is no CPU
 path: constructing a model without the built library, or running it without a B200, raises.
 """
 import math
 
 import torch
+import torch.nn.functional as F
 from torch import nn
 
 from . import _lib, ops
@@ -558,7 +559,71 @@ class SpeechMixSelf(SpeechMixEED):
                             teacher_decoder_last_hidden_state=hid_t, encoder_hidden_states=tuple(hs_s))
 
 
+class SpeechMixGAN(SpeechMixEED):
+    """ref:speechmix/hf_model.py:586-694 (HFSpeechMixGAN).  No cross-entropy: the loss is four BCE-with-logits terms of
+    one ``Linear(D*D, 1)`` discriminator over flatten(X.view(D, T) . X.view(T, D)) for X = the speech embeddings fed to
+    the text encoder (target 1), the text encoder's states on the label ids (0), and the decoder's last states on the
+    speech (1) and text (0) paths.  The labels double as the text model's input ids (:630-633), so they carry no -100.
+    The D x D Gram features are never formed (``ops.GramLogitFn``).
+
+    Like ``HFSpeechMixSelf`` the reference's ``cal_loss`` rejects three keyword arguments its own ``forward`` passes; this
+    follows the body of the method, including the update-phase counters (:609-626), which only set ``p.grad = None`` on
+    one parameter family BEFORE this step's backward."""
+
+    def custom_modules(self, **kwargs):
+        self.discriminator = nn.Linear(self.decoder_model.config.hidden_size ** 2, 1)
+        self.des_update = 1000
+        self.update_count = 1
+        self.keep_update = 1000
+        return None
+
+    def _phase(self):
+        if self.update_count % self.des_update == 0:
+            if self.keep_update > 0:
+                self.keep_update -= 1
+                for name, p in self.named_parameters():
+                    if "discriminator" in name:
+                        p.grad = None
+            else:
+                self.keep_update = 1000
+                self.update_count += 1
+        else:
+            self.update_count += 1
+            for name, p in self.named_parameters():
+                if "discriminator" not in name:
+                    p.grad = None
+
+    def cal_loss(self, inputs_embeds=None, text_input_ids=None, attention_mask=None, decoder_outputs=None,
+                 decoder_input_ids=None, labels=None, past_key_values=None, use_cache=None):
+        lm = self.decoder_model
+        enc_s, hs_s = lm.encode(inputs_embeds=inputs_embeds, output_hidden_states=True)
+        hid_s = lm.decode_hidden(decoder_input_ids, enc_s)
+        w, b, scale = lm.lm_head_params()
+        ids = ops.lm_head_argmax(hid_s.reshape(-1, hid_s.shape[-1]), w, b, scale).view(hid_s.shape[:2])
+        out = SpeechOutput(loss=0, logits=ids, argmax_ids=ids, encoder_last_hidden_state=enc_s,
+                           decoder_last_hidden_state=hid_s, encoder_hidden_states=tuple(hs_s))
+        self.decoder_outputs = [enc_s]
+        if labels is None:
+            return out
+        if self.training:
+            self._phase()
+        enc_t, _ = lm.encode(input_ids=labels, output_hidden_states=True)
+        hid_t = lm.decode_hidden(decoder_input_ids, enc_t)
+        dw, db = self.discriminator.weight, self.discriminator.bias
+        terms = {}
+        for key, x, target in (("vt_enc", inputs_embeds, 1.0), ("nt_enc", enc_t, 0.0), ("vt", hid_s, 1.0),
+                               ("nt", hid_t, 0.0)):
+            logit = ops.GramLogitFn.apply(x, dw, db)
+            out[key + "_logit"] = logit
+            terms[key] = F.binary_cross_entropy_with_logits(logit, torch.full_like(logit, target))   # B scalars: torch
+            out[key + "_loss"] = terms[key]
+        out["loss"] = 0 + (terms["vt"] + terms["nt"] + terms["nt_enc"] + terms["vt_enc"])               # ref :692
+        out["teacher_decoder_last_hidden_state"] = hid_t
+        return out
+
+
 HFSpeechMixEED = SpeechMixEED
+HFSpeechMixGAN = SpeechMixGAN
 HFSpeechMixSelf = SpeechMixSelf
 HFSpeechMixFixed = SpeechMixFixed
 HFSpeechMixAdapter = SpeechMixAdapter

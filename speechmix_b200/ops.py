@@ -1109,6 +1109,39 @@ class SelfDistillHeadFn(torch.autograd.Function):
         return dh16, None, dE, None, None, None, None
 
 
+class GramLogitFn(torch.autograd.Function):
+    """SpeechMixGAN discriminator logit (ref:speechmix/hf_model.py:637-686):
+    ``Linear(D*D, 1)(flatten(bmm(X.view(B, D, T), X.view(B, T, D))))`` without the D x D Gram matrix: with
+    W = weight.view(D, D) the logit is <W, G_b> = sum_{t,i} Xflat_b[i T + t] Z_b[t, i] for Z = X W^T -- one GEMM on the
+    tensor cores plus a streaming contraction (``smx_gram_dot_*``); the D*D features per sample (590k for bart-base)
+    never reach HBM.  x [B, T, D] activations, weight [1, D*D] fp32 parameter, bias [1] -> logits [B] fp32."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        if K.FP32_MODE:
+            raise NotImplementedError("the GAN discriminator has no fp32 verification path (training-only term)")
+        B, T, D = x.shape
+        xc = x.contiguous()
+        wb = w16(weight).view(D, D)
+        z = K.linear_fwd(xc.view(B * T, D), wb, None).view(B, T, D)
+        out = K.gram_dot_fwd(xc, z)
+        ctx.save_for_backward(xc, z, wb)
+        return out + bias.detach().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        xc, z, wb = ctx.saved_tensors
+        B, T, D = xc.shape
+        g = g.float().contiguous()
+        dx, dz = K.gram_dot_bwd(xc, z, g)
+        dz2 = dz.view(B * T, D)
+        # both gradient paths of X: the reinterpreted factor (dx) and the GEMM operand (dZ W), summed in the GEMM epilogue
+        dx = K.linear_dgrad(dz2, wb, residual=dx.view(B * T, D)).view(B, T, D) if _need(ctx, 0) else None
+        dw = K.linear_wgrad(dz2, xc.view(B * T, D)).reshape(1, D * D) if _need(ctx, 1) else None
+        db = g.sum().reshape(1) if _need(ctx, 2) else None
+        return dx, dw, db
+
+
 class SelfMSEFn(torch.autograd.Function):
     """mse(softmax(T . view(S, [D, Ts]) / sqrt(D)) . S, T)   (ref:speechmix/hf_model.py:561-570);
     T = teacher text-encoder states (no gradient), S = text-encoder states of the speech path."""

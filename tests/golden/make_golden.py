@@ -62,6 +62,11 @@ CASES = {
     "mini_adapter_large": ("mini_large", "hubert", "mbart-mini", dict(down_scale=4), 2, 1.0, 8, True, True),
     "mini_self": ("mini", "wav2vec2", "bart-mini", dict(down_scale=2), 2, 1.0, 8, False, True),
     "mini_self_t5": ("mini_large", "wav2vec2", "t5-mini", dict(down_scale=4, share_layer_ratio=0.5), 2, 1.0, 8, True, True),
+    # HFSpeechMixGAN (ref :586-694): four BCE terms of one Linear(D*D, 1) discriminator over the .view-reinterpreted Gram
+    # features; the labels double as the text model's input ids (ref :630-633), so they carry no -100.  Same keyword
+    # filter as Self (its cal_loss signature, ref :596-603, lacks the three arguments forward always passes).
+    "mini_gan": ("mini", "wav2vec2", "bart-mini", dict(down_scale=2), 2, 1.0, 8, False, True),
+    "mini_gan_mbart": ("mini_large", "hubert", "mbart-mini", dict(down_scale=4), 3, 1.0, 6, False, True),
 }
 EXTRAS = {
     "mini_specaug": {"speech_overrides": {"apply_spec_augment": True, "mask_time_prob": 0.3, "mask_time_length": 3,
@@ -74,6 +79,8 @@ EXTRAS = {
     "mini_adapter_large": {"cls": "Adapter"},
     "mini_self": {"cls": "Self", "text_ids": (2, 6, 11)},
     "mini_self_t5": {"cls": "Self", "text_ids": (2, 5, 12)},
+    "mini_gan": {"cls": "GAN"},
+    "mini_gan_mbart": {"cls": "GAN"},
 }
 
 
@@ -94,7 +101,7 @@ def compat_shims(ref, cls):
             for layer in stack:
                 layer.register_forward_hook(lambda m, i, o: (o,) if torch.is_tensor(o) else o, prepend=True)
                 layer.register_forward_hook(lambda m, i, o: o[0] if (isinstance(o, tuple) and len(o) == 2 and o[1] == ()) else o)
-    elif cls == "Self":
+    elif cls in ("Self", "GAN"):
         inner = ref.cal_loss
         accepted = ("inputs_embeds", "text_input_ids", "attention_mask", "decoder_input_ids", "labels")
         ref.cal_loss = lambda **kw: inner(**{k: v for k, v in kw.items() if k in accepted})
@@ -220,6 +227,13 @@ def run_case(name):
         # the three terms of the reference's loss are not returned by it; the oracle (bit-equal total) reports them
         for k in ("ce_loss", "kld_loss", "mse_loss"):
             fixture[k] = float(out_ora[k])
+    if extra.get("cls") == "GAN":
+        fixture["compat_shim"] = "cal_loss keyword filter (decoder_outputs, past_key_values, use_cache dropped)"
+        for k in ("vt_enc_loss", "nt_enc_loss", "vt_loss", "nt_loss"):   # not returned by the reference; oracle total is bit-equal
+            fixture[k] = float(out_ora[k])
+            fixture[k.replace("loss", "logit")] = out_ora[k.replace("loss", "logit")].tolist()
+        fixture["update_count"], fixture["keep_update"] = ref.update_count, ref.keep_update
+        assert (ref.update_count, ref.keep_update) == (ora.update_count, ora.keep_update)
     if extra.get("cls") == "Adapter":
         fixture["compat_shim"] = "4.x tuple outputs around the reference's own forward hook"
     fixture["list_grad"] = len(ref.list_grad)
@@ -243,7 +257,7 @@ def run_case(name):
                 picks.append(k)
         if "weights_sum" in pr:
             picks.append("weights_sum")
-        picks += [k for k in pr if k.startswith("adapters.")]   # Adapter: only adapters[-1] has a gradient (late binding)
+        picks += [k for k in pr if k.startswith(("adapters.", "discriminator."))]   # Adapter: only adapters[-1] has a gradient (late binding)
         for k in picks:
             if k in pr and pr[k].grad is not None:
                 assert torch.equal(pr[k].grad, po[k].grad), k

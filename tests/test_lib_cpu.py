@@ -96,6 +96,55 @@ def test_state_dict_layout_matches_reference_oracle():
         mine.load_state_dict(a)
 
 
+def test_speechmix_gan_layout_and_update_phases_match_reference_oracle():
+    """SpeechMixGAN (ref:speechmix/hf_model.py:586-694): discriminator Linear(D*D, 1) under the reference's state-dict
+    key, nothing frozen, and the update-phase state machine (:609-626: counters + which family's ``.grad`` is cleared
+    before the step) walks through the same states as the oracle's literal restatement, including the switch at
+    ``update_count % des_update == 0`` and the ``keep_update`` countdown."""
+    from oracle import hf_oracle as O
+    import torch
+    from speechmix_b200 import HFSpeechMixGAN, SpeechMixGAN
+    assert HFSpeechMixGAN is SpeechMixGAN
+    spc, txc = O.speech_config("mini"), O.text_config("bart-mini")
+    s, t = O.build_backbones(spc, txc)
+    ora = O.OracleGAN(s, t, down_scale=2)
+    mine = SpeechMixGAN(spc, txc, down_scale=2)
+    a, b = ora.state_dict(), mine.state_dict()
+    assert set(a) == set(b) and all(a[k].shape == b[k].shape for k in a)
+    d = txc.d_model
+    assert b["discriminator.weight"].shape == (1, d * d) and b["discriminator.bias"].shape == (1,)
+    assert ora.list_grad == mine.list_grad and mine.list_no_grad == [] == ora.list_no_grad
+    mine.load_state_dict(a)
+
+    def oracle_phase(m):      # the block of OracleGAN.cal_loss under ``if self.training`` (ref :609-626), no model pass
+        if m.update_count % m.des_update == 0:
+            if m.keep_update > 0:
+                m.keep_update -= 1
+                for name, p in m.named_parameters():
+                    if "discriminator" in name:
+                        p.grad = None
+            else:
+                m.keep_update = 1000
+                m.update_count += 1
+        else:
+            m.update_count += 1
+            for name, p in m.named_parameters():
+                if "discriminator" not in name:
+                    p.grad = None
+    for m in (ora, mine):
+        m.des_update, m.keep_update = 3, 2          # short cycle: 1 -> 2 -> 3 (hold 2 steps) -> reset -> 4 ...
+    for step in range(9):
+        for m in (ora, mine):
+            for p in m.parameters():
+                p.grad = torch.zeros_like(p)
+        oracle_phase(ora)
+        mine._phase()
+        assert (ora.update_count, ora.keep_update) == (mine.update_count, mine.keep_update), step
+        ga = {k for k, p in ora.named_parameters() if p.grad is None}
+        gb = {k for k, p in mine.named_parameters() if p.grad is None}
+        assert ga == gb, step
+
+
 def test_speechmix_ed_layout_matches_reference_oracle():
     """SpeechMixED (ref:speechmix/hf_model.py:82-182): same state-dict keys in the same order, same shapes, same frozen
     feature encoder as the hf SpeechEncoderDecoderModel the reference builds; fixed_parameters follows the reference's

@@ -448,6 +448,76 @@ def test_self_matches_oracle(text, cuda_device):
     assert checked == len(mine.list_grad)
 
 
+@pytest.mark.parametrize("shape", [(2, 12, 64), (3, 37, 256), (4, 150, 768)])
+def test_gram_logit_matches_literal_bmm(shape, cuda_device):
+    """ops.GramLogitFn (SpeechMixGAN discriminator, ref:speechmix/hf_model.py:637-686) against the reference's literal
+    formula -- Linear(D*D, 1)(flatten(bmm(X.view(B, D, T), X.view(B, T, D)))) -- in fp64 on the same bf16-rounded X and W:
+    logits and all three gradients (X through both factors, weight, bias).  The Gram matrix is never formed on the GPU."""
+    from speechmix_b200 import ops
+    B, T, D = shape
+    g = torch.Generator().manual_seed(B * T)
+    x = torch.randn(B, T, D, generator=g).bfloat16()
+    w = (torch.randn(1, D * D, generator=g) / (D * T ** 0.5)).bfloat16().float()
+    b = torch.randn(1, generator=g)
+    gy = torch.randn(B, generator=g)
+    xr = x.double().requires_grad_(True)
+    wr, br = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    feats = torch.bmm(xr.view(B, D, -1), xr.view(B, -1, D)).flatten(start_dim=1)
+    ref = (feats @ wr.t() + br).flatten()
+    ref.backward(gy.double())
+    xm = x.to(cuda_device).requires_grad_(True)
+    wm, bm = w.to(cuda_device).requires_grad_(True), b.to(cuda_device).requires_grad_(True)
+    ops.CACHE.invalidate()
+    out = ops.GramLogitFn.apply(xm, wm, bm)
+    out.backward(gy.to(cuda_device))
+    scale = float(ref.abs().max())
+    assert float((out.double().cpu() - ref).abs().max()) <= 1e-2 * scale + 1e-3, (out.tolist(), ref.tolist())
+    for name, got, want in (("dx", xm.grad, xr.grad), ("dw", wm.grad, wr.grad), ("db", bm.grad, br.grad)):
+        err = float((got.double().cpu() - want).norm() / (want.norm() + 1e-30))
+        assert err < 2e-2, (name, err)
+
+
+@pytest.mark.parametrize("name", ["mini_gan", "mini_gan_mbart"])
+def test_gan_matches_oracle(name, cuda_device):
+    """SpeechMixGAN (ref:speechmix/hf_model.py:586-694) against oracle.OracleGAN, which is pinned bit for bit to the
+    unmodified reference class by the mini_gan* fixtures: four discriminator logits per sample, the four BCE terms, the
+    total, argmax ids, update-phase counters, and the gradient of EVERY parameter (speech encoder, bridge, text encoder
+    and decoder, discriminator)."""
+    from oracle import hf_oracle as O
+    from speechmix_b200 import SpeechMixGAN
+    fx = load_fixture(name)
+    ora, x, labels = build_oracle(fx)
+    mine = _mine_from(ora, fx, cuda_device, cls=SpeechMixGAN)
+    assert mine.list_grad == ora.list_grad and mine.list_no_grad == ora.list_no_grad == []
+    ref = ora(x, labels=labels)
+    assert abs(float(ref["loss"]) - fx["loss"]) < 2e-5 * abs(fx["loss"])      # oracle still pinned to the reference golden
+    out = mine(x.to(cuda_device), labels=labels.to(cuda_device))
+    assert (mine.update_count, mine.keep_update) == (ora.update_count, ora.keep_update) == (fx["update_count"], fx["keep_update"])
+    for k in ("vt_enc", "nt_enc", "vt", "nt"):
+        a, b = out[k + "_logit"].double().cpu(), ref[k + "_logit"].detach().double()
+        # logits are signed sums over T*D*D products: bound the error by the size of the largest one of the family
+        # (measured: 1-2 % of it, the doubled relative error of the bf16 states the quadratic form is taken of)
+        assert float((a - b).abs().max()) <= 3e-2 * float(b.abs().max()) + 1e-4, (k, a.tolist(), b.tolist())
+        assert abs(float(out[k + "_loss"]) - float(ref[k + "_loss"])) <= 3e-2 * abs(float(ref[k + "_loss"])) + 1e-3, k
+    assert abs(float(out["loss"]) - float(ref["loss"])) <= 3e-2 * abs(float(ref["loss"]))
+    assert _ids_agree(out["logits"], fx["argmax_ids"])
+    ref["loss"].backward()
+    out["loss"].backward()
+    po, pm = dict(ora.named_parameters()), dict(mine.named_parameters())
+    checked = 0
+    for k, p in po.items():
+        assert p.grad is not None and pm[k].grad is not None, k
+        fam = max(float(q.grad.norm()) for kk, q in po.items() if kk.split(".")[0] == k.split(".")[0])
+        err = float((pm[k].grad.cpu() - p.grad).norm())
+        assert err <= 6e-2 * float(p.grad.norm()) + 3e-3 * fam, (k, err, float(p.grad.norm()), fam)
+        checked += 1
+    assert checked == len(mine.list_grad) == fx["n_grads"]
+    # no labels: the plain decoder pass with loss 0 (ref :604-608, :693)
+    with torch.no_grad():
+        o2 = mine.eval()(x.to(cuda_device))
+    assert o2["loss"] == 0 and o2["logits"].shape == (fx["batch"], 1)
+
+
 @pytest.mark.parametrize("text", ["bart-mini", "mbart-mini", "t5-mini"])
 def test_generate_kv_cache_equals_full_recompute(text, cuda_device):
     """KV-cached greedy decode (one decoder pass per token) must return exactly the ids of the notebook-style
