@@ -619,6 +619,7 @@ class SpeechMixGAN(SpeechMixEED):
             out[key + "_loss"] = terms[key]
         out["loss"] = 0 + (terms["vt"] + terms["nt"] + terms["nt_enc"] + terms["vt_enc"])               # ref :692
         out["teacher_decoder_last_hidden_state"] = hid_t
+        out["teacher_encoder_last_hidden_state"] = enc_t
         return out
 
 

@@ -493,13 +493,22 @@ def test_gan_matches_oracle(name, cuda_device):
     assert abs(float(ref["loss"]) - fx["loss"]) < 2e-5 * abs(fx["loss"])      # oracle still pinned to the reference golden
     out = mine(x.to(cuda_device), labels=labels.to(cuda_device))
     assert (mine.update_count, mine.keep_update) == (ora.update_count, ora.keep_update) == (fx["update_count"], fx["keep_update"])
+    assert _rel(out["inputs_embeds"], ref["inputs_embeds"]) < 4e-2
+    assert _rel(out["decoder_last_hidden_state"], ref["decoder_hidden_states"][-1]) < 4e-2
+    states = {"vt_enc": out["inputs_embeds"], "nt_enc": out["teacher_encoder_last_hidden_state"],
+              "vt": out["decoder_last_hidden_state"], "nt": out["teacher_decoder_last_hidden_state"]}
+    dw, db = ora.discriminator.weight.detach().double(), ora.discriminator.bias.detach().double()
     for k in ("vt_enc", "nt_enc", "vt", "nt"):
         a, b = out[k + "_logit"].double().cpu(), ref[k + "_logit"].detach().double()
-        # logits are signed sums over T*D*D products: bound the error by the size of the largest one of the family
-        # (measured: 1-2 % of it, the doubled relative error of the bf16 states the quadratic form is taken of)
-        assert float((a - b).abs().max()) <= 4e-2 * float(b.abs().max()) + 5e-3, (k, a.tolist(), b.tolist())
-        assert abs(float(out[k + "_loss"]) - float(ref[k + "_loss"])) <= 3e-2 * abs(float(ref[k + "_loss"])) + 1e-3, k
-    assert abs(float(out["loss"]) - float(ref["loss"])) <= 3e-2 * abs(float(ref["loss"]))
+        # (1) the discriminator arithmetic itself: the reference's literal formula in fp64 on the product's OWN states
+        xs = states[k].detach().double().cpu().contiguous()
+        lit = (ora.gram_features(xs) @ dw.t() + db).flatten()
+        assert float((a - lit).abs().max()) <= 1e-2 * float(lit.abs().max()) + 1e-3, (k, a.tolist(), lit.tolist())
+        # (2) end to end against the oracle: the logit is a QUADRATIC form of the states, so their relative error (bounded
+        # by 4e-2 above, measured 1-3 %) arrives doubled -- measured 5-6 % on the un-normalised speech embeddings
+        assert float((a - b).abs().max()) <= 8e-2 * float(b.abs().max()) + 5e-3, (k, a.tolist(), b.tolist())
+        assert abs(float(out[k + "_loss"]) - float(ref[k + "_loss"])) <= 8e-2 * abs(float(ref[k + "_loss"])) + 1e-3, k
+    assert abs(float(out["loss"]) - float(ref["loss"])) <= 8e-2 * abs(float(ref["loss"]))
     assert _ids_agree(out["logits"], fx["argmax_ids"])
     ref["loss"].backward()
     out["loss"].backward()
