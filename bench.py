@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Benchmark of the SpeechMix speech-to-text training step on B200 -> train audio-seconds / second.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2|cfg3|cfg4|cfg5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2|cfg3|cfg4|cfg5|gan]
+                    [--dropout P]
 
 Default workload (the headline, BASELINE.json configs[1]): SpeechMixEED wav2vec2-base + bart-base, down_scale=2,
 batch 32 x 15 s per GPU, bf16 forward + loss + backward + optimizer step.  --config selects the other BASELINE
@@ -45,6 +46,11 @@ WORKLOADS = {
                  seconds=30.0, t_dec=128, cpu_batch=1,
                  desc="SpeechMixEED hubert-large + mbart-large-50 (V=250054) down_scale=8, 8 x 30 s per GPU = 64 x 30 s "
                       "at 8 GPUs (BASELINE.json configs[4])"),
+    # not a BASELINE configuration: the discriminator variant at the headline shapes (run with --no-graph: its update-phase
+    # counters are host state)
+    "gan": dict(cls="GAN", speech=("base", "wav2vec2"), text="bart-base", kwargs=dict(down_scale=2), batch=32,
+                seconds=15.0, t_dec=64, cpu_batch=2,
+                desc="SpeechMixGAN wav2vec2-base + bart-base down_scale=2, four BCE discriminator terms (cfg2 shapes)"),
 }
 SHAPES = {   # speech: (H, FF, L); text: (D, DFF, Le, Ld, V)
     ("base", "wav2vec2"): (768, 3072, 12), ("large", "hubert"): (1024, 4096, 24), ("large", "wav2vec2"): (1024, 4096, 24),
@@ -107,6 +113,14 @@ def step_flops_per_sample(w):
         t_txt = w["t_dec"]
         teacher = Le * (8.0 * t_txt * D * D + 4.0 * t_txt * t_txt * D + 4.0 * t_txt * D * DFF) + p["text_dec"] + p["head"]
         return 3.0 * (p["speech"] + p["bridge"]) + 2.0 * (p["text_enc"] + p["text_dec"] + p["head"]) + teacher
+    if w["cls"] == "GAN":       # everything trains; text model run twice (speech embeddings, label ids); the LM head only
+        D, DFF, Le, Ld, V = SHAPES[w["text"]]                                  # feeds the argmax ids (forward only)
+        t_txt, Tds = w["t_dec"], p["frames_ds"]
+        text_path = (Le * (8.0 * t_txt * D * D + 4.0 * t_txt * t_txt * D + 4.0 * t_txt * D * DFF) +
+                     Ld * (8.0 * t_txt * D * D + 4.0 * t_txt * t_txt * D + 8.0 * t_txt * D * D + 4.0 * t_txt * t_txt * D +
+                           4.0 * t_txt * D * DFF))
+        disc = 2.0 * D * D * (Tds + 3 * t_txt)                                  # Z = X W^T for the four state tensors
+        return 3.0 * (p["speech"] + p["bridge"] + p["text_enc"] + p["text_dec"] + text_path + disc) + p["head"]
     raise ValueError(w["cls"])
 
 
@@ -148,7 +162,17 @@ def _ncu_traffic():
         return None
 
 
-def build_cpu_reference(w, batch):
+def set_dropout(spc, txc, p):
+    """switch the train-mode dropout of the HF backbones on at probability p (every site the stock configs name)"""
+    if p > 0.0:
+        for cfg, keys in ((spc, ("hidden_dropout", "attention_dropout", "activation_dropout", "feat_proj_dropout")),
+                          (txc, ("dropout", "attention_dropout", "activation_dropout", "dropout_rate"))):
+            for k in keys:
+                if hasattr(cfg, k):
+                    setattr(cfg, k, float(p))
+
+
+def build_cpu_reference(w, batch, dropout=0.0):
     """The reference's CPU path, restated (oracle/hf_oracle.py; /root/reference does not exist on the
     GPU box): HFSpeechMix{EED,Adapter,Self} glue over the transformers backbones, fp32."""
     import torch
@@ -156,6 +180,7 @@ def build_cpu_reference(w, batch):
     spc, txc = O.speech_config(w["speech"][0], model_type=w["speech"][1]), O.text_config(w["text"])
     if w["text"] == "t5-base":
         txc.decoder_start_token_id = 0
+    set_dropout(spc, txc, dropout)
     s, t = O.build_backbones(spc, txc, seed=0)
     with contextlib.redirect_stdout(sys.stderr):
         model = getattr(O, "Oracle" + w["cls"])(s, t, **w["kwargs"]).train()
@@ -166,11 +191,11 @@ def build_cpu_reference(w, batch):
     return model, x, labels, extra
 
 
-def time_cpu_reference(w, steps, warmup, batch=None, optimizer="adafactor"):
+def time_cpu_reference(w, steps, warmup, batch=None, optimizer="adafactor", dropout=0.0):
     import torch
     batch = batch or w["cpu_batch"]
     torch.set_num_threads(os.cpu_count())
-    model, x, labels, extra = build_cpu_reference(w, batch)
+    model, x, labels, extra = build_cpu_reference(w, batch, dropout)
     params = [p for p in model.parameters() if p.requires_grad]
     if optimizer == "adafactor":   # the recipe's optimizer exactly as the HF Trainer builds it (ref:train.py:298)
         from transformers.optimization import Adafactor
@@ -195,12 +220,12 @@ def run_reference_arm(args, rank):
     if rank != 0:
         return
     w = WORKLOADS[args.config]
-    val, sec, threads = time_cpu_reference(w, args.steps, args.warmup, optimizer=args.optimizer)
+    val, sec, threads = time_cpu_reference(w, args.steps, args.warmup, optimizer=args.optimizer, dropout=args.dropout)
     oname = "Adafactor" if args.optimizer == "adafactor" else "AdamW"
     line = {"impl": "reference", "metric": "train audio-sec/s", "value": val, "unit": "audio-s/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["desc"] + ", fwd+bwd+" + oname, "name": args.config,
+            "config": {"workload": w["desc"] + ", fwd+bwd+" + oname, "name": args.config, "dropout": args.dropout,
                        "sample": "batch %d x %g s per step on host CPU" % (w["cpu_batch"], w["seconds"])},
             "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": threads, "kind": "port",
                              "sample": "oracle/hf_oracle.py Oracle%s (restated reference glue over transformers), "
@@ -223,6 +248,9 @@ def main():
                          "FusedAdafactor, reference arm: transformers' Adafactor; adamw = torch AdamW (fused on the GPU)")
     ap.add_argument("--grad-payload", default="bf16", choices=["fp32", "bf16"],
                     help="wire format of the data-parallel gradient all-reduce (N > 1)")
+    ap.add_argument("--dropout", type=float, default=0.0,
+                    help="dropout probability at every site of both backbones (stock checkpoints: 0.1).  Default 0 = the "
+                         "measurement plan of BASELINE.md section 4 (dropout / LayerDrop / SpecAugment zeroed on both arms)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="eager launches instead of a whole-step CUDA graph")
     args = ap.parse_args()
@@ -251,6 +279,7 @@ def main():
     SECONDS, T_DEC = w["seconds"], w["t_dec"]
     spc = presets.speech_config(w["speech"][0], model_type=w["speech"][1])
     txc = presets.text_config(w["text"])
+    set_dropout(spc, txc, args.dropout)
     torch.manual_seed(0)
     with contextlib.redirect_stdout(sys.stderr):   # the reference-compatible ctor prints its layer-sharing summary
         model = getattr(speechmix_b200, "SpeechMix" + w["cls"])(spc, txc, **w["kwargs"])
@@ -422,6 +451,7 @@ def main():
                 "config": {"workload": "%s, batch %d x %g s per GPU, T_dec=%d, fwd+loss+bwd+%s"
                                        % (w["desc"], B, SECONDS, T_DEC, "AdamW" if args.optimizer == "adamw" else "Adafactor"),
                            "name": args.config, "global_batch": B * world, "parallelism": "dp%d" % world,
+                           "dropout": args.dropout, "dropout_sites": len(model.dropout_sites),
                            "trainable_parameters": n_train,
                            "allreduce_bytes_per_step": dp.payload_bytes() if dp is not None else 0,
                            "grad_payload": args.grad_payload if dp is not None else None,
@@ -436,7 +466,7 @@ def main():
                 "clocks": sampler.summary(),
                 "roofline": roof}
         if not args.no_cpu_baseline and world == 1:
-            val, sec, threads = time_cpu_reference(w, steps=2, warmup=1, optimizer=args.optimizer)
+            val, sec, threads = time_cpu_reference(w, steps=2, warmup=1, optimizer=args.optimizer, dropout=args.dropout)
             line["cpu_baseline"] = {"value": val, "unit": "audio-s/s", "cores": threads, "kind": "port",
                                     "sample": "oracle Oracle%s fp32 fwd+bwd+%s, batch %d x %g s, 2 timed steps (%.1f s/step)"
                                               % (w["cls"], "Adafactor" if args.optimizer == "adafactor" else "AdamW",

@@ -187,6 +187,10 @@ enum { B_KV = 0, B_QFULL = 1, B_QEMPTY = B_QFULL + NST, B_STFULL = B_QEMPTY + NS
        B_DONE = B_PDSFULL + 1, B_COUNT = B_DONE + 1 };
 }  // namespace kv2
 
+// DROP = true adds a packed-pair path for plain attention WITH dropout on the probabilities (mask regenerated from the
+// counter-based generator); the general path (causal / bias, with or without dropout) is shared.  A separate
+// instantiation, so the kernel of the deterministic step is compiled exactly as before the path existed.
+template <bool DROP>
 __global__ void __launch_bounds__(BWD2_THREADS, 2)
 attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
                      const __grid_constant__ CUtensorMap mv, const __grid_constant__ CUtensorMap mdo,
@@ -292,7 +296,15 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_consta
     const DropKey dkey = drop_key(p.drop_state, p.drop_call, p.drop_p);   // thresh 0: off
     const uint32_t drop_hp = static_cast<uint32_t>((p.tk + 1) >> 1);
     const uint32_t drop_bh = static_cast<uint32_t>((long long)b * p.heads + head) * static_cast<uint32_t>(p.tq);
-    const bool lean = !p.causal && p.bias == nullptr && dkey.thresh == 0u;
+    const bool plain = !p.causal && p.bias == nullptr;
+    const bool lean = plain && dkey.thresh == 0u;           // packed-pair path of the deterministic step
+    const bool lean_drop = DROP && plain && !lean;          // the same plus the regenerated mask
+    // DROP, lean: this thread owns ONE key, so which 16 bits of a pair's hash are its own is a per-thread constant, and
+    // the hash input ((bh + q) * hp + (key >> 1)) * C + seed-key is linear in the query index: one IMAD per element
+    const uint32_t drop_sh = (kvi & 1) ? 0u : 16u;
+    const uint32_t drop_thi = dkey.thresh << 16;
+    const uint32_t drop_step = drop_hp * 0x9e3779b1u;
+    const uint32_t drop_in0 = (drop_bh * drop_hp + static_cast<uint32_t>(kvi >> 1)) * 0x9e3779b1u + dkey.key;
     // lse (log2 domain) / delta*scale of the 64 queries of a sub-tile: thread gt < 64 owns lse[gt], the others
     // delta[gt - 64]; the global load for the NEXT sub-tile is issued one sub-tile ahead.
     const float* stat_src = (gt < 64 ? p.lse : p.delta) + ((long long)b * p.heads + head) * p.tq;
@@ -311,7 +323,44 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_consta
       mbar_wait(&bars[B_STFULL], it & 1);
       tc_fence_after_sync();
       uint32_t pk[16], dk[16];   // P^T and dS^T of this thread's 32 queries, bf16 pairs
-      if (lean) {
+      if (lean_drop) {
+        // the plain path below plus the regenerated mask: dS = P (keep / (1-p) dP - delta), P_drop = keep ? P / (1-p) : 0
+        const f32x2 sl2 = f2_rep(p.scale_log2);
+        const float mk = p.scale * dkey.scale, ps = dkey.scale;
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          const int c = 2 * hf + c2;
+          uint32_t sv[16], dv[16];
+          tmem_ld_x16(t_row + COL_ST + c * 16, sv);
+          tmem_ld_x16(t_row + COL_DPT + c * 16, dv);
+          tmem_ld_wait();
+          const uint32_t in_c = drop_in0 + static_cast<uint32_t>(q0 + c * 16) * drop_step;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 l4 = *reinterpret_cast<const float4*>(st + c * 16 + i);        // -lse (log2 domain)
+            const float4 d4 = *reinterpret_cast<const float4*>(st + 64 + c * 16 + i);   // -delta * scale
+            float e0, e1, e2, e3;
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), sl2, f2_pack(l4.x, l4.y)), e0, e1);
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3])), sl2, f2_pack(l4.z, l4.w)), e2, e3);
+            e0 = ex2_approx(e0), e1 = ex2_approx(e1), e2 = ex2_approx(e2), e3 = ex2_approx(e3);
+            const bool k0 = (mix32(in_c + static_cast<uint32_t>(i) * drop_step) << drop_sh) >= drop_thi;
+            const bool k1 = (mix32(in_c + static_cast<uint32_t>(i + 1) * drop_step) << drop_sh) >= drop_thi;
+            const bool k2 = (mix32(in_c + static_cast<uint32_t>(i + 2) * drop_step) << drop_sh) >= drop_thi;
+            const bool k3 = (mix32(in_c + static_cast<uint32_t>(i + 3) * drop_step) << drop_sh) >= drop_thi;
+            float g0, g1, g2, g3;
+            f2_unpack(f2_mul(f2_pack(e0, e1), f2_fma(f2_pack(__uint_as_float(dv[i]), __uint_as_float(dv[i + 1])),
+                                                     f2_pack(k0 ? mk : 0.f, k1 ? mk : 0.f), f2_pack(d4.x, d4.y))), g0, g1);
+            f2_unpack(f2_mul(f2_pack(e2, e3), f2_fma(f2_pack(__uint_as_float(dv[i + 2]), __uint_as_float(dv[i + 3])),
+                                                     f2_pack(k2 ? mk : 0.f, k3 ? mk : 0.f), f2_pack(d4.z, d4.w))), g2, g3);
+            f2_unpack(f2_mul(f2_pack(e0, e1), f2_pack(k0 ? ps : 0.f, k1 ? ps : 0.f)), e0, e1);
+            f2_unpack(f2_mul(f2_pack(e2, e3), f2_pack(k2 ? ps : 0.f, k3 ? ps : 0.f)), e2, e3);
+            pk[c2 * 8 + (i >> 1)] = pack_bf16x2(e0, e1);
+            pk[c2 * 8 + (i >> 1) + 1] = pack_bf16x2(e2, e3);
+            dk[c2 * 8 + (i >> 1)] = pack_bf16x2(g0, g1);
+            dk[c2 * 8 + (i >> 1) + 1] = pack_bf16x2(g2, g3);
+          }
+        }
+      } else if (lean) {
         // two 16-column chunks; fp32 pairs
         const f32x2 sl2 = f2_rep(p.scale_log2), sc2 = f2_rep(p.scale);
 #pragma unroll
@@ -404,6 +453,7 @@ enum { B_Q = 0, B_QT = 1, B_KFULL = 2, B_KEMPTY = B_KFULL + NST, B_SFULL = B_KEM
        B_DONE = B_DSFULL + 1, B_COUNT = B_DONE + 1 };
 }  // namespace dq2
 
+template <bool DROP>
 __global__ void __launch_bounds__(BWD2_THREADS, 2)
 attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
                     const __grid_constant__ CUtensorMap mv, const __grid_constant__ CUtensorMap mdo,
@@ -510,7 +560,10 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
     }
     const DropKey dkey = drop_key(p.drop_state, p.drop_call, p.drop_p);   // thresh 0: off
     const uint32_t drop_row = static_cast<uint32_t>(((long long)b * p.heads + head) * p.tq + qi) * static_cast<uint32_t>((p.tk + 1) >> 1);
-    const bool lean = !p.causal && p.bias == nullptr && dkey.thresh == 0u;
+    const bool plain = !p.causal && p.bias == nullptr;
+    const bool lean = plain && dkey.thresh == 0u;           // packed-pair path of the deterministic step
+    const bool lean_drop = DROP && plain && !lean;          // the same plus the regenerated mask
+    const uint32_t drop_thi = dkey.thresh << 16;
     const int causal_lim = p.causal ? qi + (p.tk - p.tq) : 0x7fffffff;
     // stationary operands -> TMEM
     mbar_wait(&bars[B_Q], 0);
@@ -539,7 +592,33 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constan
       mbar_wait(&bars[B_SFULL], it & 1);
       tc_fence_after_sync();
       uint32_t dk[16];   // dS of this thread's 32 keys, bf16 pairs
-      if (lean) {
+      if (lean_drop) {
+        // the plain path below plus the regenerated mask; this thread owns ONE query, so the two keys of a column pair are
+        // the two 16-bit halves of one hash
+        const f32x2 sl2 = f2_rep(p.scale_log2), nl2 = f2_rep(-lse2), nd2 = f2_rep(-delta);
+        const float mk = p.scale * dkey.scale;
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          const int c = 2 * hf + c2;
+          uint32_t sv[16], dv[16];
+          tmem_ld_x16(t_row + COL_S + c * 16, sv);
+          tmem_ld_x16(t_row + COL_DP + c * 16, dv);
+          tmem_ld_wait();
+          const uint32_t pair0 = drop_row + static_cast<uint32_t>((k0 + c * 16) >> 1);
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const uint32_t bits = drop_bits(dkey, pair0 + static_cast<uint32_t>(i >> 1));
+            const float m0 = ((bits << 16) >= drop_thi) ? mk : 0.f;   // even key: low half of the hash
+            const float m1 = (bits >= drop_thi) ? mk : 0.f;           // odd key: high half
+            float e0, e1, g0, g1;
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), sl2, nl2), e0, e1);
+            e0 = ex2_approx(e0), e1 = ex2_approx(e1);
+            f2_unpack(f2_mul(f2_pack(e0, e1), f2_fma(f2_pack(__uint_as_float(dv[i]), __uint_as_float(dv[i + 1])),
+                                                     f2_pack(m0, m1), nd2)), g0, g1);
+            dk[c2 * 8 + (i >> 1)] = pack_bf16x2(g0, g1);
+          }
+        }
+      } else if (lean) {
         const f32x2 sl2 = f2_rep(p.scale_log2), sc2 = f2_rep(p.scale), nl2 = f2_rep(-lse2), nd2 = f2_rep(-delta);
 #pragma unroll
         for (int c2 = 0; c2 < 2; ++c2) {
@@ -632,8 +711,10 @@ extern "C" int smx_attn_bwd(const SmxAttn* a, void* stream) {
   p.drop_p = a->dropout_state ? a->dropout_p : 0.0f;
   static bool attr_set = false;
   if (!attr_set) {
-    SMX_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kv2::SMEM_BYTES));
-    SMX_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dq2::SMEM_BYTES));
+    SMX_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kv2::SMEM_BYTES));
+    SMX_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dq2::SMEM_BYTES));
+    SMX_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kv2::SMEM_BYTES));
+    SMX_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dq2::SMEM_BYTES));
     attr_set = true;
   }
   dim3 gkv((a->tk + 127) / 128, a->heads, a->batch);
@@ -648,9 +729,12 @@ extern "C" int smx_attn_bwd(const SmxAttn* a, void* stream) {
   if (make_head_map_rows(&sk, a->k, a->tk, a->heads, a->batch, a->k_row_stride, a->k_batch_stride, SUB)) return -1;
   if (make_head_map_rows(&sv, a->v, a->tk, a->heads, a->batch, a->v_row_stride, a->v_batch_stride, SUB)) return -1;
   // the dQ kernel also produces delta = rowsum(dO * O) (its dO tile is already in shared memory), so it runs first
-  launch_pdl(attn_bwd_dq2_kernel, dim3(gq), dim3(BWD2_THREADS), dq2::SMEM_BYTES, st, mq, sk, sv, mdo, p);
+  const bool drop = p.drop_state != nullptr && p.drop_p > 0.0f;
+  if (drop) launch_pdl(attn_bwd_dq2_kernel<true>, dim3(gq), dim3(BWD2_THREADS), dq2::SMEM_BYTES, st, mq, sk, sv, mdo, p);
+  else launch_pdl(attn_bwd_dq2_kernel<false>, dim3(gq), dim3(BWD2_THREADS), dq2::SMEM_BYTES, st, mq, sk, sv, mdo, p);
   SMX_CHECK_CUDA(cudaGetLastError());
-  launch_pdl(attn_bwd_dkv2_kernel, dim3(gkv), dim3(BWD2_THREADS), kv2::SMEM_BYTES, st, sq, mk, mv, sdo, p);
+  if (drop) launch_pdl(attn_bwd_dkv2_kernel<true>, dim3(gkv), dim3(BWD2_THREADS), kv2::SMEM_BYTES, st, sq, mk, mv, sdo, p);
+  else launch_pdl(attn_bwd_dkv2_kernel<false>, dim3(gkv), dim3(BWD2_THREADS), kv2::SMEM_BYTES, st, sq, mk, mv, sdo, p);
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

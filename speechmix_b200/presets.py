@@ -22,7 +22,7 @@ def speech_config(kind="base", model_type="wav2vec2", deterministic=True):
         cfg = cls(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, intermediate_size=4096)
     else:
         raise ValueError(kind)
-    if deterministic:             # the kernels implement no dropout / SpecAugment
+    if deterministic:             # both bench arms run with dropout / LayerDrop / SpecAugment zeroed
         _deterministic(cfg, ("hidden_dropout", "activation_dropout", "attention_dropout", "feat_proj_dropout", "layerdrop",
                              "mask_time_prob", "mask_feature_prob", "final_dropout", "feat_quantizer_dropout"))
         cfg.apply_spec_augment = False

@@ -14,7 +14,13 @@ from speechmix_b200 import SpeechMixEED, _lib, parallel, presets as O  # noqa: E
 
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+    drop = float(sys.argv[2]) if len(sys.argv) > 2 else 0.0     # dropout probability at every site (stock checkpoints: 0.1)
     spc, txc = O.speech_config("base"), O.text_config("bart-base")
+    if drop > 0:
+        for cfg, keys in ((spc, ("hidden_dropout", "attention_dropout", "activation_dropout", "feat_proj_dropout")),
+                          (txc, ("dropout", "attention_dropout", "activation_dropout"))):
+            for k in keys:
+                setattr(cfg, k, drop)
     model = SpeechMixEED(spc, txc, down_scale=2)
     parallel.init_like_reference(model)
     model = model.cuda().train()
