@@ -307,6 +307,20 @@ int smx_dropout(const void* x, const void* residual, void* out, const void* aux_
 int smx_dropout_mask(uint8_t* mask, int64_t n, int64_t tk, int mode, const uint64_t* state, uint32_t call, float p,
                      void* stream);
 
+/* Tail of a post-LN block with output dropout (hf:...wav2vec2.py:590-602, hf:...bart.py:280-309: dropout -> residual add ->
+ * LayerNorm), as ONE launch each way instead of dropout + LayerNorm (forward) and LayerNorm backward + dropout + column
+ * sums (backward).  Same mask as smx_dropout on the same [rows][cols] tensor with the same (state, call, p).
+ *   fwd: sum_out = (keep ? x / (1 - p) : 0) + res;  y = LN(sum_out) * gamma + beta;  mean / rstd of the stored sum
+ *   bwd: dx = LN'(dy) (the gradient of the residual branch);  dx_drop = keep ? dx / (1 - p) : 0 (the gradient of x);
+ *        dgamma / dbeta (dbeta may be NULL) and dxd_colsum (may be NULL) += column sums -- all three zeroed by the caller.
+ * x here is the stored sum (the LayerNorm input) with its saved mean / rstd. */
+int smx_layernorm_dropout_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* y, void* sum_out,
+                              float* mean, float* rstd, int64_t rows, int64_t cols, float eps, const uint64_t* state,
+                              uint32_t call, float p, void* stream);
+int smx_layernorm_dropout_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
+                              void* dx_drop, float* dgamma, float* dbeta, float* dxd_colsum, int64_t rows, int64_t cols,
+                              const uint64_t* state, uint32_t call, float p, void* stream);
+
 /* SpecAugment on the projected features (hf:models/wav2vec2/modeling_wav2vec2.py:1280-1324; the mask INDICES come
  * from the host, drawn exactly like the reference's _compute_mask_indices):
  *   y[b,t,:] = time_mask[b,t] ? embed : x[b,t,:];  y[b,t,c] = 0 where feat_mask[b,c]   (either mask may be NULL)

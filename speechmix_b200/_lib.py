@@ -75,6 +75,8 @@ SIGNATURES = {
     "smx_mask_rows": (c_int, [_P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _P]),
     "smx_dropout": (c_int, [_P, _P, _P, _P, _P, c_int, _I64, _P, ctypes.c_uint32, c_float, _P]),
     "smx_dropout_mask": (c_int, [_P, _I64, _I64, c_int, _P, ctypes.c_uint32, c_float, _P]),
+    "smx_layernorm_dropout_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, c_float, _P, ctypes.c_uint32, c_float, _P]),
+    "smx_layernorm_dropout_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _P, ctypes.c_uint32, c_float, _P]),
     "smx_adafactor_step": (c_int, [_P, c_int32, _P, c_int32, _P, c_int32, _P, c_int32, c_int32, _P, _I64, c_float, c_float,
                                    c_float, c_float, c_float, _P, c_float, _P]),
     "smx_spec_augment_fwd": (c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _P]),

@@ -254,6 +254,214 @@ ln_bwd_reg_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const
   }
 }
 
+// ------------------------------------------------------------------ post-LN block tail WITH output dropout (training)
+// forward:  s = (keep ? x / (1 - p) : 0) + res,  y = LN(s)    -- x = the sub-block's output; replaces the elementwise dropout
+//           launch (110 MB at [23968, 768]) + the LayerNorm launch; s is stored, and the statistics are those of the stored
+//           (bf16-rounded) values, exactly as the two separate kernels produce them.
+// backward: ds = LN'(dy) (the residual-branch gradient),  dsd = keep ? ds / (1 - p) : 0 (the sub-block's output gradient),
+//           column sums of dsd (bias gradient of the linear layer in front) -- replaces LayerNorm backward + the dropout
+//           launch on ds + the separate column-sum launch.  Same mask numbering as dropout_kernel: pair = element >> 1.
+// One warp per row, register variants (see ln_fwd_reg_kernel / ln_bwd_reg_kernel).
+template <int VPL>
+__global__ void __launch_bounds__(256, (VPL <= 3 ? 3 : 1)) ln_fwd_drop_kernel(const bf16* __restrict__ x, const bf16* __restrict__ res,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      bf16* __restrict__ y, bf16* __restrict__ sum_out,
+                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                      long long rows, int cols, float eps,
+                                                      const unsigned long long* __restrict__ state, uint32_t call, float p) {
+  pdl_trigger();
+  pdl_wait();
+  const DropKey key = drop_key(state, call, p);
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  uint4 nx[VPL];
+  if (warp_global < rows) {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      if (c < cols) nx[i] = *reinterpret_cast<const uint4*>(x + warp_global * cols + c);
+    }
+  }
+  for (long long row = warp_global; row < rows; row += nwarps) {
+    float v[VPL][8];
+    float s = 0.f;
+    uint4 cur[VPL], rr[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      cur[i] = nx[i];
+      const int c = (i * 32 + lane) * 8;
+      if (c < cols) rr[i] = *reinterpret_cast<const uint4*>(res + row * cols + c);   // in flight during the mask arithmetic
+    }
+    if (row + nwarps < rows) {
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int c = (i * 32 + lane) * 8;
+        if (c < cols) nx[i] = *reinterpret_cast<const uint4*>(x + (row + nwarps) * cols + c);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      if (c < cols) {
+        unpack_bf16x8(cur[i], v[i]);
+        const uint32_t pair0 = static_cast<uint32_t>((row * cols + c) >> 1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t bits = drop_bits(key, pair0 + j);
+          v[i][2 * j] = drop_keep_lo(key, bits) ? v[i][2 * j] * key.scale : 0.f;
+          v[i][2 * j + 1] = drop_keep_hi(key, bits) ? v[i][2 * j + 1] * key.scale : 0.f;
+        }
+        float r[8];
+        unpack_bf16x8(rr[i], r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] += r[j];
+        const uint4 pk = pack_bf16x8(v[i]);
+        *reinterpret_cast<uint4*>(sum_out + row * cols + c) = pk;
+        unpack_bf16x8(pk, v[i]);   // statistics of what backward will re-read
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[i][j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+      }
+    }
+    const float mean = warp_sum(s) / cols;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      if (c < cols) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[i][j] - mean;
+          sq += d * d;
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / cols + eps);
+    if (lane == 0) {
+      mean_out[row] = mean;
+      rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      if (c < cols) {
+        float g[8], b[8], o[8];
+        loadf8(gamma + c, g);
+        if (beta) loadf8(beta + c, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + (beta ? b[j] : 0.f);
+        store8(y + row * cols + c, o);
+      }
+    }
+  }
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(256, (VPL <= 3 ? 2 : 1))
+ln_bwd_drop_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ gamma,
+                   const float* __restrict__ mean_in, const float* __restrict__ rstd_in, bf16* __restrict__ dx,
+                   bf16* __restrict__ dx_drop, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                   float* __restrict__ dxd_colsum, long long rows, int cols, const unsigned long long* __restrict__ state,
+                   uint32_t call, float p) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float red[8][32 * 8 + 1];
+  const DropKey key = drop_key(state, call, p);
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long warp_global = (long long)blockIdx.x * 8 + warp;
+  const long long nwarps = (long long)gridDim.x * 8;
+  float ag[VPL][8], ab[VPL][8], ac[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ag[i][j] = 0.f, ab[i][j] = 0.f, ac[i][j] = 0.f;
+
+  for (long long row = warp_global; row < rows; row += nwarps) {
+    const float mean = mean_in[row];
+    const float rstd = rstd_in[row];
+    uint4 dp[VPL], xp[VPL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      if (c < cols) {
+        dp[i] = *reinterpret_cast<const uint4*>(dy + row * cols + c);
+        xp[i] = *reinterpret_cast<const uint4*>(x + row * cols + c);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      if (c < cols) {
+        float d[8], xh[8], gm[8];
+        unpack_bf16x8(dp[i], d);
+        unpack_bf16x8(xp[i], xh);
+        loadf8(gamma + c, gm);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float h = (xh[j] - mean) * rstd;
+          ag[i][j] = fmaf(d[j], h, ag[i][j]);
+          ab[i][j] += d[j];
+          const float gj = d[j] * gm[j];
+          s1 += gj;
+          s2 = fmaf(gj, h, s2);
+        }
+      }
+    }
+    s1 = warp_sum(s1) / cols;
+    s2 = warp_sum(s2) / cols;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      if (c < cols) {
+        float d[8], xh[8], gm[8], o[8];
+        unpack_bf16x8(dp[i], d);
+        unpack_bf16x8(xp[i], xh);
+        loadf8(gamma + c, gm);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (d[j] * gm[j] - s1 - (xh[j] - mean) * rstd * s2);
+        const uint4 po = pack_bf16x8(o);
+        *reinterpret_cast<uint4*>(dx + row * cols + c) = po;
+        unpack_bf16x8(po, o);     // the mask acts on the stored (bf16) gradient, as the separate dropout launch did
+        const uint32_t pair0 = static_cast<uint32_t>((row * cols + c) >> 1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t bits = drop_bits(key, pair0 + j);
+          o[2 * j] = drop_keep_lo(key, bits) ? o[2 * j] * key.scale : 0.f;
+          o[2 * j + 1] = drop_keep_hi(key, bits) ? o[2 * j + 1] * key.scale : 0.f;
+        }
+        const uint4 pd = pack_bf16x8(o);
+        *reinterpret_cast<uint4*>(dx_drop + row * cols + c) = pd;
+        unpack_bf16x8(pd, o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ac[i][j] += o[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+      float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : dxd_colsum);
+      if (dst == nullptr) continue;
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = pass == 0 ? ag[i][j] : (pass == 1 ? ab[i][j] : ac[i][j]);
+      __syncthreads();
+      const int col_local = threadIdx.x;
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[w][col_local];
+      const int c = i * 256 + col_local;
+      if (c < cols) atomicAdd(dst + c, t);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ LayerNorm forward / backward (ring variants)
 // Row kernels below run their fp32 arithmetic on PACKED PAIRS (FFMA2 / FMUL2 / FADD2, sm100_prims.cuh): the first
 // versions were instruction-issue-bound (ln_fwd ~21, ln_bwd ~28 warp instructions per element and lane at ~50 % of
@@ -1210,6 +1418,63 @@ int smx_dropout(const void* x, const void* residual, void* out, const void* aux_
   launch_pdl(dropout_kernel, dim3(grid_for(n / 8, 256)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, (const bf16*)residual, (bf16*)out,
                                                                        (const bf16*)aux_in, (bf16*)aux_out, aux_mode, n / 8,
                                                                        (const unsigned long long*)state, call, p);
+  SMX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int smx_layernorm_dropout_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* y, void* sum_out,
+                              float* mean, float* rstd, int64_t rows, int64_t cols, float eps, const uint64_t* state,
+                              uint32_t call, float p, void* stream) {
+  SMX_REQUIRE(x && res && gamma && y && sum_out && mean && rstd && state, "layernorm_dropout_fwd: null pointer");
+  SMX_REQUIRE(p > 0.0f && p < 1.0f, "layernorm_dropout_fwd: p = %g outside (0, 1)", (double)p);
+  SMX_REQUIRE(cols % 8 == 0 && cols <= 2048 && cols > 0, "layernorm_dropout_fwd: cols %lld unsupported", (long long)cols);
+  SMX_REQUIRE(rows * cols / 2 < (1ll << 32), "layernorm_dropout_fwd: more than 2^33 elements");
+  if (rows == 0) return 0;
+  SMX_REQUIRE(aligned16(x) && aligned16(res) && aligned16(y) && aligned16(sum_out), "layernorm_dropout_fwd: 16-byte alignment");
+  const int vpl = (int)ceil_div(cols, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(rows, 8);
+#define LN_FWD_DROP_LAUNCH(V)                                                                                              \
+  launch_pdl(ln_fwd_drop_kernel<V>, dim3(grid), dim3(256), 0, st, (const bf16*)x, (const bf16*)res, gamma, beta, (bf16*)y, \
+             (bf16*)sum_out, mean, rstd, (long long)rows, (int)cols, eps, (const unsigned long long*)state, call, p)
+  switch (vpl) {
+    case 1: LN_FWD_DROP_LAUNCH(1); break;
+    case 2: LN_FWD_DROP_LAUNCH(2); break;
+    case 3: LN_FWD_DROP_LAUNCH(3); break;
+    case 4: LN_FWD_DROP_LAUNCH(4); break;
+    case 5: case 6: LN_FWD_DROP_LAUNCH(6); break;
+    default: LN_FWD_DROP_LAUNCH(8); break;
+  }
+#undef LN_FWD_DROP_LAUNCH
+  SMX_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int smx_layernorm_dropout_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
+                              void* dx_drop, float* dgamma, float* dbeta, float* dxd_colsum, int64_t rows, int64_t cols,
+                              const uint64_t* state, uint32_t call, float p, void* stream) {
+  SMX_REQUIRE(dy && x && gamma && mean && rstd && dx && dx_drop && dgamma && state, "layernorm_dropout_bwd: null pointer");
+  SMX_REQUIRE(p > 0.0f && p < 1.0f, "layernorm_dropout_bwd: p = %g outside (0, 1)", (double)p);
+  SMX_REQUIRE(cols % 8 == 0 && cols <= 2048 && cols > 0, "layernorm_dropout_bwd: cols %lld unsupported", (long long)cols);
+  SMX_REQUIRE(rows * cols / 2 < (1ll << 32), "layernorm_dropout_bwd: more than 2^33 elements");
+  if (rows == 0) return 0;
+  SMX_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dx) && aligned16(dx_drop), "layernorm_dropout_bwd: 16-byte alignment");
+  const int vpl = (int)ceil_div(cols, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(rows, 8, vpl <= 3 ? 2 : 1);   // one persistent wave: the column accumulators live in registers
+#define LN_BWD_DROP_LAUNCH(V)                                                                                             \
+  launch_pdl(ln_bwd_drop_kernel<V>, dim3(grid), dim3(256), 0, st, (const bf16*)dy, (const bf16*)x, gamma, mean, rstd,     \
+             (bf16*)dx, (bf16*)dx_drop, dgamma, dbeta, dxd_colsum, (long long)rows, (int)cols,                            \
+             (const unsigned long long*)state, call, p)
+  switch (vpl) {
+    case 1: LN_BWD_DROP_LAUNCH(1); break;
+    case 2: LN_BWD_DROP_LAUNCH(2); break;
+    case 3: LN_BWD_DROP_LAUNCH(3); break;
+    case 4: LN_BWD_DROP_LAUNCH(4); break;
+    case 5: case 6: LN_BWD_DROP_LAUNCH(6); break;
+    default: LN_BWD_DROP_LAUNCH(8); break;
+  }
+#undef LN_BWD_DROP_LAUNCH
   SMX_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -471,6 +471,37 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, rms_only=False, want_dbet
     return (dx, dgamma, dbeta, csum) if want_colsum else (dx, dgamma, dbeta)
 
 
+def layernorm_dropout_fwd(x, res, gamma, beta, eps, state, call, p):
+    """post-LN block tail with output dropout in one launch: s = dropout(x) + res, y = LN(s).  Returns y, s, mean, rstd
+    (same mask as ``dropout(x, state, call, p, residual=res)``)."""
+    C = x.shape[-1]
+    rows = x.numel() // C
+    assert x.dtype == BF16 and res.dtype == BF16 and x.is_contiguous() and res.is_contiguous() and res.shape == x.shape
+    y, s = torch.empty_like(x), torch.empty_like(x)
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+    _lib.check(_L().smx_layernorm_dropout_fwd(_ptr(x), _ptr(res), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(s), _ptr(mean),
+                                              _ptr(rstd), rows, C, eps, _ptr(state), int(call), float(p), _stream()),
+               "layernorm_dropout_fwd")
+    return y, s, mean, rstd
+
+
+def layernorm_dropout_bwd(dy, x, gamma, mean, rstd, state, call, p, want_dbeta=True, want_colsum=True):
+    """backward of the same tail in one launch.  Returns dx (residual-branch gradient), dx_drop (= dropout mask applied to
+    dx: the gradient of the sub-block output), dgamma, dbeta, column sums of dx_drop."""
+    C = x.shape[-1]
+    rows = x.numel() // C
+    assert dy.dtype == BF16 and x.dtype == BF16 and dy.is_contiguous() and x.is_contiguous()
+    dx, dxd = torch.empty_like(x), torch.empty_like(x)
+    dgamma = zeros_f32(C, device=x.device)
+    dbeta = zeros_f32(C, device=x.device) if want_dbeta else None
+    csum = zeros_f32(C, device=x.device) if want_colsum else None
+    _lib.check(_L().smx_layernorm_dropout_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(dxd),
+                                              _ptr(dgamma), _ptr(dbeta), _ptr(csum), rows, C, _ptr(state), int(call),
+                                              float(p), _stream()), "layernorm_dropout_bwd")
+    return dx, dxd, dgamma, dbeta, csum
+
+
 def mask_rows(x, lens, col_begin=0, col_count=None):
     """In place: x[b, t, col_begin:col_begin+col_count] = 0 for t >= lens[b]  (x: bf16 [B, T, C], lens: int32 [B])."""
     B, T, C = x.shape

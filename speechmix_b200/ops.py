@@ -8,6 +8,7 @@ reference); bf16 / packed copies are cached per parameter version
 Weight gradients come out of the TN GEMM in fp32.
 """
 import math
+import os
 import weakref
 
 import torch
@@ -224,6 +225,15 @@ def conv_packed16(p):
     return CACHE.get(p, "convpack32" if K.FP32_MODE else "convpack", lambda t: K.pack_conv_weight(t))
 
 
+_DROPOUT_TAIL = os.environ.get("SMX_DROPOUT_TAIL", "1") != "0"   # A/B switch (development): "0" = the separate launches
+
+
+def _fused_dropout_tail(drop_h, pre_ln, rms):
+    """post-LN block with output dropout: dropout + residual add + LayerNorm run as one launch each way
+    (smx_layernorm_dropout_fwd / _bwd) instead of three / four"""
+    return drop_h is not None and not pre_ln and not rms and not K.FP32_MODE and _DROPOUT_TAIL
+
+
 def _act_codes(name):
     """(forward epilogue code, backward epilogue code).  For GELU the forward GEMM stores gelu'(pre) as its
     auxiliary output (ACT_GELU_G) so the data-gradient GEMM's epilogue is one multiply (ACT_MULAUX) -- the
@@ -396,16 +406,21 @@ class AttnBlockFn(torch.autograd.Function):
         drop_a = _drop_site(cfg.get("p_attn"), x.device, "attention", (B, heads, T, Ts))
         drop_h = _drop_site(cfg.get("p_hidden"), x.device, "elementwise", (B, T, H))
         o, lse = K.attn_fwd(q, k, v, heads, causal=causal, scale=scale, bias=pb, kv_len=kv_len, dropout=drop_a)
+        fused_tail = _fused_dropout_tail(drop_h, pre_ln, rms)
         if drop_h is None:
             s = K.linear_fwd(o.view(B * T, Hi), w16(o_w), None if o_b is None else o_b.detach(), residual=x2)
         else:
             s0 = K.linear_fwd(o.view(B * T, Hi), w16(o_w), None if o_b is None else o_b.detach())
-            s = K.dropout(s0, *drop_h, residual=x2)
+            if fused_tail:       # dropout + residual add + LayerNorm of a post-LN block: one launch
+                y, s, mean, rstd = K.layernorm_dropout_fwd(s0, x2, ln_w.detach(), ln_b_d, eps, *drop_h)
+            else:
+                s = K.dropout(s0, *drop_h, residual=x2)
         if pre_ln:
             y = s
             ctx.save_for_backward(x2, n, mean, rstd, o, lse, kv_src2, ln_w, pb, *(qkv if src is not None else (qkv,)))
         else:
-            y, _, mean, rstd = K.layernorm_fwd(s, ln_w.detach(), ln_b_d, eps, rms_only=rms)
+            if not fused_tail:
+                y, _, mean, rstd = K.layernorm_fwd(s, ln_w.detach(), ln_b_d, eps, rms_only=rms)
             ctx.save_for_backward(x2, s, mean, rstd, o, lse, kv_src2, ln_w, pb, *(qkv if src is not None else (qkv,)))
         ctx.cfg = dict(cfg, scale=scale, rms=rms)
         ctx.drop_a, ctx.drop_h = drop_a, drop_h
@@ -427,19 +442,25 @@ class AttnBlockFn(torch.autograd.Function):
         sv = ctx.saved_tensors
         x2, a, mean, rstd, o, lse, kv_src2, ln_w, pb = sv[:9]
         dy2 = dy.reshape(B * T, H).contiguous()
+        fused_tail = _fused_dropout_tail(ctx.drop_h, pre_ln, rms)
         if pre_ln:
             ds = dy2
             a_in = a          # normalised input
+        elif fused_tail:      # LayerNorm backward + the dropout mask on its result + the out-proj bias gradient: one launch
+            ds_res, ds, dlnw, dlnb, d_ob = K.layernorm_dropout_bwd(dy2, a, ln_w.detach(), mean, rstd, *ctx.drop_h,
+                                                                   want_dbeta=ctx.has_lnb, want_colsum=ctx.has_obias)
+            a_in = x2
         else:
             ds, dlnw, dlnb, d_ob = K.layernorm_bwd(dy2, a, ln_w.detach(), mean, rstd, rms_only=rms, want_dbeta=ctx.has_lnb,
                                                    want_colsum=True)   # colsum(ds) = out-proj bias gradient, fused
             a_in = x2
         o2 = o.view(B * T, Hi)
-        ds_res = ds                      # gradient of the residual branch (not dropped)
-        if ctx.drop_h is not None:       # gradient through the block-output dropout: the same mask on ds
-            ds = K.dropout(ds, *ctx.drop_h)
-        if pre_ln or not ctx.has_obias or ctx.drop_h is not None:
-            d_ob = K.colsum(ds) if ctx.has_obias else None
+        if not fused_tail:
+            ds_res = ds                      # gradient of the residual branch (not dropped)
+            if ctx.drop_h is not None:       # gradient through the block-output dropout: the same mask on ds
+                ds = K.dropout(ds, *ctx.drop_h)
+            if pre_ln or not ctx.has_obias or ctx.drop_h is not None:
+                d_ob = K.colsum(ds) if ctx.has_obias else None
         d_ow = K.linear_wgrad(ds, o2) if _need(ctx, 9) else None
         do = K.linear_dgrad(ds, w16(o_w)).view(B, T, Hi)
         ds = ds_res
@@ -518,21 +539,27 @@ class FFNBlockFn(torch.autograd.Function):
             # the masked multiplier keep * act'(pre) / (1 - p), so the backward epilogue stays a single multiply
             h, pre = K.dropout(h, *drop_act, aux_in=pre, aux_mode=2 if dact == ACT_DRELU else 1)
             dact = ACT_MULAUX
+        fused_tail = _fused_dropout_tail(drop_h, pre_ln, rms) and not no_res
         if drop_h is None:
             s = K.linear_fwd(h, w16(w2), None if b2 is None else b2.detach(), residual=None if no_res else x2)
         else:
             s0 = K.linear_fwd(h, w16(w2), None if b2 is None else b2.detach())
-            s = K.dropout(s0, *drop_h, residual=None if no_res else x2)
+            if fused_tail:       # dropout + residual add + LayerNorm of a post-LN block: one launch
+                y, s, mean, rstd = K.layernorm_dropout_fwd(s0, x2, ln_w.detach(), ln_b_d, eps, *drop_h)
+            else:
+                s = K.dropout(s0, *drop_h, residual=None if no_res else x2)
         if pre_ln:
             y = s
             ctx.save_for_backward(x2, n, mean, rstd, pre, h, ln_w)
         else:
-            y, _, mean, rstd = K.layernorm_fwd(s, ln_w.detach(), ln_b_d, eps, rms_only=rms)
+            if not fused_tail:
+                y, _, mean, rstd = K.layernorm_fwd(s, ln_w.detach(), ln_b_d, eps, rms_only=rms)
             ctx.save_for_backward(x2, s, mean, rstd, pre, h, ln_w)
         ctx.pre_ln, ctx.dact, ctx.shp = pre_ln, dact, shp
         ctx.rms, ctx.has_lnb = rms, ln_b is not None
         ctx.no_res = no_res
         ctx.drop_h = drop_h
+        ctx.fused_tail = fused_tail
         ctx.wrefs = (w1, w2)
         ctx.has_bias = b1 is not None
         return y.view(shp)
@@ -545,15 +572,20 @@ class FFNBlockFn(torch.autograd.Function):
         dy2 = dy.reshape(-1, H).contiguous()
         if ctx.pre_ln:
             ds, a_in = dy2, a
+        elif ctx.fused_tail:  # LayerNorm backward + the dropout mask on its result + the fc2 bias gradient: one launch
+            ds_res, ds, dlnw, dlnb, db2 = K.layernorm_dropout_bwd(dy2, a, ln_w.detach(), mean, rstd, *ctx.drop_h,
+                                                                  want_dbeta=ctx.has_lnb, want_colsum=ctx.has_bias)
+            a_in = x2
         else:
             ds, dlnw, dlnb, db2 = K.layernorm_bwd(dy2, a, ln_w.detach(), mean, rstd, rms_only=ctx.rms, want_dbeta=ctx.has_lnb,
                                                   want_colsum=True)    # colsum(ds) = fc2 bias gradient, fused
             a_in = x2
-        ds_res = ds
-        if ctx.drop_h is not None:       # gradient through the block-output dropout
-            ds = K.dropout(ds, *ctx.drop_h)
-        if ctx.pre_ln or not ctx.has_bias or ctx.drop_h is not None:
-            db2 = K.colsum(ds) if ctx.has_bias else None
+        if not ctx.fused_tail:
+            ds_res = ds
+            if ctx.drop_h is not None:       # gradient through the block-output dropout
+                ds = K.dropout(ds, *ctx.drop_h)
+            if ctx.pre_ln or not ctx.has_bias or ctx.drop_h is not None:
+                db2 = K.colsum(ds) if ctx.has_bias else None
         dw2 = K.linear_wgrad(ds, h) if _need(ctx, 4) else None
         dpre = K.linear_dgrad(ds, w16(w2), act=ctx.dact, aux_in=pre)
         ds = ds_res

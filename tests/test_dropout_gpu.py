@@ -49,6 +49,43 @@ def test_dropout_kernel_statistics_and_determinism(cuda_device):
     assert torch.equal(a2 != 0, mk & (aux > 0)) and abs(float(a2.max()) - 1 / 0.75) < 0.01
 
 
+@pytest.mark.parametrize("shape", [(300, 768), (77, 256), (1000, 1024), (64, 96)])
+def test_fused_dropout_layernorm_tail_equals_the_separate_launches(shape, cuda_device):
+    """smx_layernorm_dropout_fwd / _bwd (dropout + residual add + LayerNorm of a post-LN block as one launch each way)
+    against the three / four separate launches they replace, same (state, call, p): the stored sum and both gradient
+    tensors must be the same (same arithmetic, same rounding points, same mask), the normalised output / statistics / parameter
+    gradients / column sums equal up to summation order."""
+    from speechmix_b200 import kernels as K
+    R, C = shape
+    g = torch.Generator(device=cuda_device).manual_seed(R + C)
+    x, res, dy = (torch.randn(R, C, device=cuda_device, generator=g).to(torch.bfloat16) for _ in range(3))
+    gamma = 1 + 0.1 * torch.randn(C, device=cuda_device, generator=g)
+    beta = 0.1 * torch.randn(C, device=cuda_device, generator=g)
+    st = torch.tensor([77, 5], dtype=torch.int64, device=cuda_device)
+    call, p = 21, 0.1
+    s_ref = K.dropout(x, st, call, p, residual=res)
+    y_ref, _, mean_ref, rstd_ref = K.layernorm_fwd(s_ref, gamma, beta, 1e-5)
+    y, s, mean, rstd = K.layernorm_dropout_fwd(x, res, gamma, beta, 1e-5, st, call, p)
+    def same(a, b, what):      # identical up to FMA-contraction choices of the compiler: <= 0.1 % of elements, one bf16 ulp
+        diff = (a.float() - b.float()).abs()
+        assert float((diff > 0).float().mean()) < 1e-3 and float((diff / (b.float().abs() + 1e-3)).max()) < 2 ** -6, what
+        assert torch.equal(a == 0, b == 0), what                              # the same mask
+    same(s, s_ref, "sum")
+    assert float((mean - mean_ref).abs().max()) < 1e-5 and float((rstd / rstd_ref - 1).abs().max()) < 1e-5
+    assert float((y.float() - y_ref.float()).abs().max()) <= 2 ** -6          # one bf16 ulp at |y| < 4
+    dx_ref, dg_ref, db_ref, _ = K.layernorm_bwd(dy, s_ref, gamma, mean_ref, rstd_ref, want_colsum=True)
+    dxd_ref = K.dropout(dx_ref, st, call, p)
+    cs_ref = K.colsum(dxd_ref)
+    dx, dxd, dg, db, cs = K.layernorm_dropout_bwd(dy, s_ref, gamma, mean_ref, rstd_ref, st, call, p)
+    same(dx, dx_ref, "dx")
+    same(dxd, dxd_ref, "dx_drop")
+    for name, a, b in (("dgamma", dg, dg_ref), ("dbeta", db, db_ref), ("colsum", cs, cs_ref)):
+        assert float((a - b).abs().max()) <= 1e-4 * float(b.abs().max()) + 1e-5, name
+    dx2, dxd2, dg2, db2, cs2 = K.layernorm_dropout_bwd(dy, s_ref, gamma, mean_ref, rstd_ref, st, call, p, want_dbeta=False,
+                                                       want_colsum=False)
+    assert db2 is None and cs2 is None and torch.equal(dx2, dx) and torch.equal(dxd2, dxd)
+
+
 def _attention_mask_reference(q, k, v, heads, scale, mask, p, causal):
     B, Tq, _ = q.shape
     Tk = k.shape[1]
