@@ -21,6 +21,10 @@ def _capturable(opt):
 def _check_no_host_randomness(model):
     """Host-drawn randomness would be frozen into the graph (the same layers skipped / the same frames masked on
     every replay): refuse instead of training silently wrong."""
+    if hasattr(model, "update_count") and hasattr(model, "des_update"):
+        raise RuntimeError("GraphedTrainStep: SpeechMixGAN switches its update phase with host-side counters "
+                           "(ref:speechmix/hf_model.py:609-626: which family's .grad is cleared before the step); a "
+                           "captured step would replay one phase forever -- run it eagerly")
     enc = getattr(model, "encoder_model", None)
     cfg = getattr(enc, "config", None)
     if enc is None or cfg is None or not enc.training:

@@ -131,6 +131,10 @@ def test_speechmix_gan_layout_and_update_phases_match_reference_oracle():
             for name, p in m.named_parameters():
                 if "discriminator" not in name:
                     p.grad = None
+    import pytest as _pytest
+    from speechmix_b200 import graph
+    with _pytest.raises(RuntimeError, match="update phase"):    # host-side phase counters cannot live in a CUDA graph
+        graph._check_no_host_randomness(mine)
     for m in (ora, mine):
         m.des_update, m.keep_update = 3, 2          # short cycle: 1 -> 2 -> 3 (hold 2 steps) -> reset -> 4 ...
     for step in range(9):
