@@ -367,3 +367,30 @@ def test_bridge_projector_composition_algebra():
     dx = torch.zeros(B, T, C, dtype=torch.float64)
     dx[:, :t_out * 2] = (dy @ w_eff).reshape(B, t_out * 2, C)
     assert torch.allclose(dx, x.grad, atol=1e-12) and float(x.grad[:, -1].abs().max()) == 0.0
+
+
+def test_bench_flop_model_matches_survey_table():
+    """bench.py's algorithmic FLOP model (the numerator of ``step_tflops`` / ``roofline.step_frac_of_peak``) against
+    the per-sample forward GFLOP table of SURVEY.md section 8(d) / BASELINE.md section 3, and the workload table against
+    BASELINE.json's configurations."""
+    import bench
+    want = {"cfg2": 281.95, "cfg3": 660.26, "cfg5": 1486.35}
+    for name, gflop in want.items():
+        got = bench.fwd_flops_per_sample(bench.WORKLOADS[name]) / 1e9
+        assert abs(got - gflop) < 0.02 * gflop, (name, got, gflop)
+    assert bench.frames(15.0) == 749 and bench.frames(30.0) == 1499 and bench.frames(5.0) == 249
+    # training step: 3 x forward where everything trains; frozen configurations count less than that
+    w2 = bench.WORKLOADS["cfg2"]
+    assert abs(bench.step_flops_per_sample(w2) - 3 * bench.fwd_flops_per_sample(w2)) < 1.0
+    assert bench.step_flops_per_sample(bench.WORKLOADS["cfg3"]) < 3 * bench.fwd_flops_per_sample(bench.WORKLOADS["cfg3"])
+    assert bench.step_flops_per_sample(bench.WORKLOADS["gan"]) > bench.step_flops_per_sample(w2)
+    assert (w2["batch"], w2["seconds"], w2["t_dec"], w2["kwargs"]["down_scale"]) == (32, 15.0, 64, 2)
+    assert bench.WORKLOADS["cfg5"]["batch"] * 8 == 64 and bench.WORKLOADS["cfg5"]["seconds"] == 30.0
+    # --dropout switches every site of both backbones on (0 = the measurement plan's default leaves the presets alone)
+    from speechmix_b200 import presets
+    spc, txc = presets.speech_config("base"), presets.text_config("bart-base")
+    bench.set_dropout(spc, txc, 0.0)
+    assert spc.hidden_dropout == 0.0 and txc.dropout == 0.0
+    bench.set_dropout(spc, txc, 0.1)
+    assert (spc.hidden_dropout, spc.attention_dropout, spc.activation_dropout, spc.feat_proj_dropout) == (0.1,) * 4
+    assert (txc.dropout, txc.attention_dropout, txc.activation_dropout) == (0.1,) * 3
