@@ -190,7 +190,9 @@ KERNELS_PER_CALL = {"multi_cast": 1, "weightnorm_fwd": 2, "weightnorm_bwd": 2, "
                     "self_mse_bwd": 2, "relpos_fwd": 1, "relpos_bwd": 1, "smx_attn_fwd": 1, "smx_attn_bwd": 2, "dropout": 1, "dropout_mask": 1, "layernorm_fwd": 1, "layernorm_bwd": 1, "colsum": 1,
                     "cast": 1, "add": 1, "dact": 1, "conv0_stats": 3, "conv0_fwd": 1, "conv0_bwd": 2, "conv0_ln_fwd": 1, "conv0_ln_bwd": 1, "conv0_wgrad": 1,
                     "posconv_fwd": 1, "posconv_dgrad": 1, "posconv_wgrad": 1, "embed_fwd": 1, "embed_bwd": 1,
-                    "lmhead_ce_fwd": 2, "lmhead_dlogits": 1, "wsum_fwd": 1, "wsum_bwd": 1}
+                    "lmhead_ce_fwd": 2, "lmhead_dlogits": 1, "wsum_fwd": 1, "wsum_bwd": 1,
+                    "layernorm_dropout_fwd": 1, "layernorm_dropout_bwd": 1, "gram_dot_fwd": 1, "gram_dot_bwd": 1,
+                    "mask_rows": 1, "mul": 1, "spec_augment_fwd": 1, "spec_augment_bwd": 1}   # (+1 with a dembed output)
 LAUNCHES = [0]
 
 
